@@ -1,0 +1,109 @@
+// ============================================================================
+// CPU ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+//
+// Field-at-a-time CPU restatement of the QGDsolver hot path (fvsc face-centre
+// derivatives, QGDCoeffs, QGDThermo state, QGDFoam explicit step, QHDFoam step
+// with PCG).  Each function cites the reference listing it follows
+// (Name.C:N == /root/reference/docs/html/Name_8C_source.html, source line N).
+//
+// "Parity unpinned": the reference ships no tests, golden vectors or tutorials
+// for this path and cannot be compiled here (needs OpenFOAM v2312; SURVEY.md
+// 8c), so this restatement is checked only against manufactured known-answer
+// tests (tests/test_oracle_kat.py), not against reference outputs.
+// OpenFOAM-internal semantics are isolated in functions tagged [OF-v2312].
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may load this.  The product (qgdsolver_b200/) never does.
+// ============================================================================
+#pragma once
+#include <cstdint>
+
+extern "C" {
+
+// patch kinds (same numbering as include/qgd_b200.h)
+enum { OR_PATCH_GENERIC = 0, OR_PATCH_EMPTY = 1, OR_PATCH_PROCESSOR = 2, OR_PATCH_WEDGE = 3 };
+// boundary-condition kinds per patch and field
+enum { OR_BC_FIXED_VALUE = 0, OR_BC_ZERO_GRADIENT = 1, OR_BC_FIXED_GRADIENT = 2, OR_BC_QGD_FLUX = 3,
+       OR_BC_CALCULATED = 4, OR_BC_SLIP = 5 };
+// fvsc schemes
+enum { OR_FVSC_GAUSSVOLPOINT = 0, OR_FVSC_REDUCED = 1 };
+
+typedef struct {
+    int nCells, nFaces, nInternal, nPoints, nPatches;
+    const double* points;        // nPoints*3
+    const int* faceOff;          // nFaces+1
+    const int* faceVerts;
+    const int* owner;            // nFaces
+    const int* neighbour;        // nInternal
+    const int* patchStart;       // nPatches
+    const int* patchSize;
+    const int* patchKind;
+    const double* C;             // nCells*3
+    const double* V;             // nCells
+    const double* Cf;            // nFaces*3
+    const double* Sf;            // nFaces*3
+    const double* magSf;         // nFaces
+    const double* weights;       // nFaces
+    const double* deltaCoeffs;   // nFaces
+    const double* nonOrthDeltaCoeffs; // nFaces
+    const double* neighbCellCentres;  // nBnd*3 (processor patches)
+    int geometricD[3];
+} or_mesh_t;
+
+typedef struct {
+    double R;        // specific gas constant  [perfectGas]
+    double Cp;       // hConst
+    double Hf;
+    double Tref;     // hConst Tref / Hsref offsets [OF-v2312]
+    double Hsref;
+    double mu;       // constTransport
+    double Pr;
+    double ScQGD;    // constScPrModel1
+    double PrQGD;
+    int implicitDiffusion;     // only 0 supported by the step
+    int alphaEffGammaFactor;   // heThermo::alphaEff multiplies by gamma for internal energy [OF-v2312]
+    int energyDdtRhoEQuirk;    // 1: QGDEEqn.H:67-72 as in the doc snapshot, fvm::ddt(rho,e) - fvc::ddt(rhoE)
+                               // 0: fvm::ddt(rho,e) - fvc::ddt(rho,e)  (e keeps rhoE/rho - K)
+} or_qgd_params_t;
+
+typedef struct or_ctx or_ctx;
+
+or_ctx* or_create(const or_mesh_t* mesh, int nThreads);
+void    or_destroy(or_ctx*);
+
+// ---- derived mesh data (for KATs / parity of setup kernels)
+void or_get_hQGDf(or_ctx*, double* out /*nFaces*/);
+void or_get_hQGD(or_ctx*, double* out /*nCells*/);
+
+// ---- fvsc operators.  cell: nCells*k ; bnd: nBnd*k boundary values ; bndSnGrad: nBnd*k patch snGrad
+//      nbr: nBnd*k patchNeighbourField (processor patches only, may be NULL) ; out: nFaces*(3k | k/3)
+void or_fvsc_grad(or_ctx*, int scheme, int ncmpt /*1|3*/, const double* cell, const double* bnd,
+                  const double* bndSnGrad, const double* nbr, double* out);
+void or_fvsc_div(or_ctx*, int scheme, int ncmpt /*3|9*/, const double* cell, const double* bnd,
+                 const double* bndSnGrad, const double* nbr, double* out);
+void or_vol_point_interpolate(or_ctx*, int ncmpt, const double* cell, const double* bnd, double* outPoints);
+void or_linear_interpolate(or_ctx*, int ncmpt, const double* cell, const double* bnd, double* out);
+
+// ---- QGDFoam
+//  bc kinds per patch for U, T, p ; fixed values per boundary face (U: nBnd*3, T,p: nBnd)
+void or_qgd_init(or_ctx*, const or_qgd_params_t*, int fvscScheme,
+                 const int* bcU, const int* bcT, const int* bcP,
+                 const double* bvU, const double* bvT, const double* bvP,
+                 const double* U0, const double* T0, const double* p0, const double* alphaQGD /*nCells or NULL*/,
+                 double deltaT0);
+//  nSteps explicit steps.  adjustTimeStep: 0 fixed dt.  Returns last Courant number (or -1).
+double or_qgd_step(or_ctx*, int nSteps, int adjustTimeStep, double maxCo, double maxDeltaT, double cTau);
+double or_qgd_deltaT(or_ctx*);
+//  field ids: 0 rho, 1 rhoU(3), 2 rhoE, 3 U(3), 4 e, 5 p, 6 T, 7 c, 8 mu, 9 alpha, 10 tauQGD
+//  cells: nCells*k ; bnd (may be NULL): nBnd*k
+void or_qgd_get(or_ctx*, int field, double* cells, double* bnd);
+//  face fields of the last step: 0 phiJm, 1 phiJmU(3), 2 phiP(3), 3 phiPi(3), 4 phiJmH, 5 phiQ, 6 phiPiU,
+//  7 tauQGDf, 8 gradUf(9), 9 gradef(3), 10 gradRhof(3), 11 gradPf(3), 12 phiwStar
+void or_qgd_get_face(or_ctx*, int field, double* out /*nFaces*k*/);
+
+// ---- LDU PCG [OF-v2312 PCG + DIC / diagonal]  (QHDpEqn.H:45)
+//  symmetric: lower == upper.  precond: 0 none, 1 diagonal, 2 DIC.  returns iterations.
+int or_pcg_solve(or_ctx*, const double* diag, const double* upper, const double* b, double* x,
+                 double tol, double relTol, int maxIter, int precond, double* initRes, double* finalRes);
+
+} // extern "C"

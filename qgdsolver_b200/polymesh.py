@@ -1,0 +1,473 @@
+"""OpenFOAM-polyMesh-compatible mesh substrate (host side, numpy).
+
+The reference (QGDsolver) never builds meshes itself: it consumes OpenFOAM's
+``fvMesh`` (points / faces / owner / neighbour / boundary + the geometry
+OpenFOAM derives from them).  OpenFOAM is not available here, so this module
+produces exactly those arrays for synthetic cases:
+
+* topology in polyMesh conventions (upper-triangular internal face order,
+  boundary faces grouped per patch, face normals owner -> neighbour);
+* the geometry ``fvMesh`` exposes and the reference reads:
+  ``C, V, Cf, Sf, magSf, weights, deltaCoeffs, nonOrthDeltaCoeffs``
+  [OF-v2312 semantics; unverified here].
+
+Everything the reference itself derives (GaussVolPoint coefficients, hQGD,
+volPointInterpolation weights ...) is NOT computed here: the CUDA library and
+the CPU oracle each derive those independently from these arrays.
+
+Used by: tests, bench.py (synthetic inputs), and as the input format of the
+C-ABI ``qgd_mesh_create`` (include/qgd_b200.h).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# patch kinds (shared with include/qgd_b200.h : qgd_patch_kind)
+PATCH_GENERIC = 0      # patch / wall : ordinary boundary
+PATCH_EMPTY = 1        # empty        : 1D/2D reduction
+PATCH_PROCESSOR = 2    # processor    : inter-subdomain
+PATCH_WEDGE = 3        # wedge (recognised, skipped like the reference does)
+
+_KIND_NAMES = {"patch": PATCH_GENERIC, "wall": PATCH_GENERIC,
+               "empty": PATCH_EMPTY, "processor": PATCH_PROCESSOR,
+               "wedge": PATCH_WEDGE}
+
+
+@dataclass
+class Patch:
+    name: str
+    kind: int
+    start: int
+    size: int
+    neighb_rank: int = -1
+
+
+@dataclass
+class PolyMesh:
+    """polyMesh arrays + fvMesh geometry (all C-contiguous, float64/int32)."""
+    points: np.ndarray            # (nPoints,3)
+    face_offsets: np.ndarray      # (nFaces+1,) int32  CSR into face_verts
+    face_verts: np.ndarray        # (sum nv,)  int32
+    owner: np.ndarray             # (nFaces,)  int32
+    neighbour: np.ndarray         # (nInternal,) int32
+    patches: List[Patch]
+    n_cells: int
+    geometric_d: np.ndarray = field(default_factory=lambda: np.ones(3, np.int32))
+    # fvMesh geometry, filled by compute_geometry()
+    C: Optional[np.ndarray] = None        # (nCells,3)
+    V: Optional[np.ndarray] = None        # (nCells,)
+    Cf: Optional[np.ndarray] = None       # (nFaces,3)
+    Sf: Optional[np.ndarray] = None       # (nFaces,3)
+    magSf: Optional[np.ndarray] = None    # (nFaces,)
+    weights: Optional[np.ndarray] = None  # (nFaces,) boundary = 1 (coupled: see decompose)
+    deltaCoeffs: Optional[np.ndarray] = None         # (nFaces,)
+    nonOrthDeltaCoeffs: Optional[np.ndarray] = None  # (nFaces,)
+    # processor patches only: neighbour-side cell centres per boundary face (nBnd,3), NaN elsewhere
+    neighb_cell_centres: Optional[np.ndarray] = None
+
+    @property
+    def n_points(self) -> int:
+        return self.points.shape[0]
+
+    @property
+    def n_faces(self) -> int:
+        return self.owner.shape[0]
+
+    @property
+    def n_internal(self) -> int:
+        return self.neighbour.shape[0]
+
+    @property
+    def n_bnd(self) -> int:
+        return self.n_faces - self.n_internal
+
+    @property
+    def n_geometric_d(self) -> int:
+        return int((self.geometric_d > 0).sum())
+
+    def patch_kind_per_bface(self) -> np.ndarray:
+        k = np.zeros(self.n_bnd, np.int32)
+        for p in self.patches:
+            s = p.start - self.n_internal
+            k[s:s + p.size] = p.kind
+        return k
+
+    def patch_id_per_bface(self) -> np.ndarray:
+        k = np.full(self.n_bnd, -1, np.int32)
+        for i, p in enumerate(self.patches):
+            s = p.start - self.n_internal
+            k[s:s + p.size] = i
+        return k
+
+    def face_nverts(self) -> np.ndarray:
+        return np.diff(self.face_offsets)
+
+    # ------------------------------------------------------------------ geometry
+    def compute_geometry(self) -> "PolyMesh":
+        """fvMesh geometry [OF-v2312: primitiveMeshTools::faceCentresAndAreas,
+        cellCentresAndVols; surfaceInterpolation::makeWeights/makeDeltaCoeffs/
+        makeNonOrthDeltaCoeffs; fvPatch::delta = Cf - Cn]."""
+        pts = self.points
+        nF = self.n_faces
+        nI = self.n_internal
+        nv = self.face_nverts()
+        Cf = np.zeros((nF, 3))
+        Sf = np.zeros((nF, 3))
+        for n in np.unique(nv):
+            idx = np.nonzero(nv == n)[0]
+            v = self.face_verts[(self.face_offsets[idx][:, None] + np.arange(n)[None, :])]
+            P = pts[v]                                   # (m,n,3)
+            if n == 3:
+                Cf[idx] = (P[:, 0] + P[:, 1] + P[:, 2]) / 3.0
+                Sf[idx] = 0.5 * np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
+            else:
+                fC = P[:, 0].copy()
+                for k in range(1, n):
+                    fC += P[:, k]
+                fC /= n
+                sumN = np.zeros((idx.size, 3))
+                sumA = np.zeros(idx.size)
+                sumAc = np.zeros((idx.size, 3))
+                for k in range(n):
+                    p0 = P[:, k]
+                    p1 = P[:, (k + 1) % n]
+                    c = p0 + p1 + fC
+                    nn = np.cross(p1 - p0, fC - p0)
+                    a = np.sqrt((nn * nn).sum(1))
+                    sumN += nn
+                    sumA += a
+                    sumAc += a[:, None] * c
+                Cf[idx] = (1.0 / 3.0) * sumAc / sumA[:, None]
+                Sf[idx] = 0.5 * sumN
+        magSf = np.sqrt((Sf * Sf).sum(1))
+        own = self.owner
+        nei = self.neighbour
+        nC = self.n_cells
+        # cell centres / volumes
+        cEst = np.zeros((nC, 3))
+        cnt = np.bincount(own, minlength=nC) + np.bincount(nei, minlength=nC)
+        for d in range(3):
+            cEst[:, d] = (np.bincount(own, weights=Cf[:, d], minlength=nC)
+                          + np.bincount(nei, weights=Cf[:nI, d], minlength=nC))
+        cEst /= cnt[:, None]
+        pyrO = (Sf * (Cf - cEst[own])).sum(1)
+        pcO = 0.75 * Cf + 0.25 * cEst[own]
+        pyrN = (Sf[:nI] * (cEst[nei] - Cf[:nI])).sum(1)
+        pcN = 0.75 * Cf[:nI] + 0.25 * cEst[nei]
+        V3 = np.bincount(own, weights=pyrO, minlength=nC) + np.bincount(nei, weights=pyrN, minlength=nC)
+        C = np.zeros((nC, 3))
+        for d in range(3):
+            C[:, d] = (np.bincount(own, weights=pyrO * pcO[:, d], minlength=nC)
+                       + np.bincount(nei, weights=pyrN * pcN[:, d], minlength=nC))
+        C /= V3[:, None]
+        V = V3 * (1.0 / 3.0)
+        # interpolation weights and delta coefficients
+        w = np.ones(nF)
+        dC = np.zeros(nF)
+        ndC = np.zeros(nF)
+        SfOwn = np.abs((Sf[:nI] * (Cf[:nI] - C[own[:nI]])).sum(1))
+        SfNei = np.abs((Sf[:nI] * (C[nei] - Cf[:nI])).sum(1))
+        w[:nI] = SfNei / (SfOwn + SfNei)
+        delta = C[nei] - C[own[:nI]]
+        md = np.sqrt((delta * delta).sum(1))
+        dC[:nI] = 1.0 / md
+        nf = Sf[:nI] / magSf[:nI, None]
+        ndC[:nI] = 1.0 / np.maximum((nf * delta).sum(1), 0.05 * md)
+        # boundary: delta = Cf - Cn (ordinary); processor patches are fixed up by decompose()
+        db = Cf[nI:] - C[own[nI:]]
+        mdb = np.sqrt((db * db).sum(1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dC[nI:] = 1.0 / mdb
+            nfb = Sf[nI:] / magSf[nI:, None]
+            ndC[nI:] = 1.0 / np.maximum((nfb * db).sum(1), 0.05 * mdb)
+        self.C, self.V, self.Cf, self.Sf, self.magSf = C, V, Cf, Sf, magSf
+        self.weights, self.deltaCoeffs, self.nonOrthDeltaCoeffs = w, dC, ndC
+        if self.neighb_cell_centres is None:
+            self.neighb_cell_centres = np.full((self.n_bnd, 3), np.nan)
+        return self
+
+    # ------------------------------------------------------------------ adjacency helpers
+    def cell_faces_csr(self) -> Tuple[np.ndarray, np.ndarray]:
+        """cell -> faces (ascending face id per cell, like a sequential face loop visits them)."""
+        nC = self.n_cells
+        allc = np.concatenate([self.owner, self.neighbour])
+        allf = np.concatenate([np.arange(self.n_faces, dtype=np.int64),
+                               np.arange(self.n_internal, dtype=np.int64)])
+        order = np.lexsort((allf, allc))
+        off = np.zeros(nC + 1, np.int64)
+        np.cumsum(np.bincount(allc, minlength=nC), out=off[1:])
+        return off.astype(np.int32), allf[order].astype(np.int32)
+
+
+# ---------------------------------------------------------------------- generators
+def _axis(n: int, length: float, origin: float, grading: float) -> np.ndarray:
+    """n+1 node coordinates; grading = last/first cell-size ratio (blockMesh simpleGrading)."""
+    if n <= 0:
+        raise ValueError("n must be positive")
+    if grading == 1.0 or n == 1:
+        return origin + length * np.arange(n + 1) / n
+    r = grading ** (1.0 / (n - 1))
+    s = np.concatenate([[0.0], np.cumsum(r ** np.arange(n))])
+    return origin + length * s / s[-1]
+
+
+def hex_box(nx: int, ny: int, nz: int,
+            lengths: Sequence[float] = (1.0, 1.0, 1.0),
+            origin: Sequence[float] = (0.0, 0.0, 0.0),
+            grading: Sequence[float] = (1.0, 1.0, 1.0),
+            patch_kinds: Optional[Dict[str, str]] = None,
+            perturb: float = 0.0, seed: int = 0,
+            compute_geometry: bool = True) -> PolyMesh:
+    """Structured hex block in blockMesh ordering (cells and points i-fastest,
+    internal faces upper-triangular, six patches xMin,xMax,yMin,yMax,zMin,zMax).
+
+    patch_kinds maps patch name -> 'patch'|'wall'|'empty'.  ``perturb`` moves
+    interior vertices by perturb*min(spacing) (seeded) to give a genuinely
+    non-orthogonal unstructured-like geometry for tests.
+    """
+    kinds = {"xMin": "patch", "xMax": "patch", "yMin": "patch", "yMax": "patch",
+             "zMin": "patch", "zMax": "patch"}
+    if patch_kinds:
+        kinds.update(patch_kinds)
+    x = _axis(nx, lengths[0], origin[0], grading[0])
+    y = _axis(ny, lengths[1], origin[1], grading[1])
+    z = _axis(nz, lengths[2], origin[2], grading[2])
+    npx, npy, npz = nx + 1, ny + 1, nz + 1
+    K, J, I = np.meshgrid(np.arange(npz), np.arange(npy), np.arange(npx), indexing="ij")
+    pts = np.stack([x[I], y[J], z[K]], axis=-1).reshape(-1, 3).astype(np.float64)
+    if perturb > 0.0:
+        rng = np.random.default_rng(seed)
+        h = min(np.diff(x).min(), np.diff(y).min(), np.diff(z).min())
+        d = (rng.random(pts.shape) - 0.5) * 2.0 * perturb * h
+        # keep boundary points on their planes (and 2D/1D extrusion straight)
+        ii, jj, kk = I.reshape(-1), J.reshape(-1), K.reshape(-1)
+        d[(ii == 0) | (ii == nx), 0] = 0.0
+        d[(jj == 0) | (jj == ny), 1] = 0.0
+        d[(kk == 0) | (kk == nz), 2] = 0.0
+        if kinds["zMin"] == "empty":   # extruded: identical displacement through z, none in z
+            d[:, 2] = 0.0
+            d2 = d.reshape(npz, npy, npx, 3)
+            d2[:] = d2[0:1]
+        if kinds["yMin"] == "empty":
+            d[:, 1] = 0.0
+            d2 = d.reshape(npz, npy, npx, 3)
+            d2[:] = d2[:, 0:1]
+        if kinds["xMin"] == "empty":
+            d[:, 0] = 0.0
+            d2 = d.reshape(npz, npy, npx, 3)
+            d2[:] = d2[:, :, 0:1]
+        pts = pts + d
+
+    def pid(i, j, k):
+        return (k * npy + j) * npx + i
+
+    def cid(i, j, k):
+        return (k * ny + j) * nx + i
+
+    kc, jc, ic = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    ic, jc, kc = ic.reshape(-1), jc.reshape(-1), kc.reshape(-1)
+    cell = cid(ic, jc, kc)
+
+    def xface(i, j, k):   # normal +x, at node plane i
+        return np.stack([pid(i, j, k), pid(i, j + 1, k), pid(i, j + 1, k + 1), pid(i, j, k + 1)], 1)
+
+    def yface(i, j, k):   # normal +y
+        return np.stack([pid(i, j, k), pid(i, j, k + 1), pid(i + 1, j, k + 1), pid(i + 1, j, k)], 1)
+
+    def zface(i, j, k):   # normal +z
+        return np.stack([pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)], 1)
+
+    # internal faces: per owner cell in order, to +x, +y, +z neighbours
+    mx, my, mz = ic < nx - 1, jc < ny - 1, kc < nz - 1
+    fx = xface(ic[mx] + 1, jc[mx], kc[mx]); ox = cell[mx]; nxn = ox + 1
+    fy = yface(ic[my], jc[my] + 1, kc[my]); oy = cell[my]; nyn = oy + nx
+    fz = zface(ic[mz], jc[mz], kc[mz] + 1); oz = cell[mz]; nzn = oz + nx * ny
+    fi = np.concatenate([fx, fy, fz])
+    oi = np.concatenate([ox, oy, oz])
+    ni = np.concatenate([nxn, nyn, nzn])
+    order = np.lexsort((ni, oi))
+    fi, oi, ni = fi[order], oi[order], ni[order]
+
+    # boundary faces (outward normals), ordered by owner cell inside each patch
+    bfaces, bown, patches = [], [], []
+    start = fi.shape[0]
+
+    def add(name, verts, own):
+        nonlocal start
+        o = np.argsort(own, kind="stable")
+        bfaces.append(verts[o]); bown.append(own[o])
+        patches.append(Patch(name, _KIND_NAMES[kinds[name]], start, own.size))
+        start += own.size
+
+    m = ic == 0
+    add("xMin", xface(ic[m], jc[m], kc[m])[:, ::-1], cell[m])
+    m = ic == nx - 1
+    add("xMax", xface(ic[m] + 1, jc[m], kc[m]), cell[m])
+    m = jc == 0
+    add("yMin", yface(ic[m], jc[m], kc[m])[:, ::-1], cell[m])
+    m = jc == ny - 1
+    add("yMax", yface(ic[m], jc[m] + 1, kc[m]), cell[m])
+    m = kc == 0
+    add("zMin", zface(ic[m], jc[m], kc[m])[:, ::-1], cell[m])
+    m = kc == nz - 1
+    add("zMax", zface(ic[m], jc[m], kc[m] + 1), cell[m])
+
+    fv = np.concatenate([fi] + bfaces).astype(np.int32)
+    owner = np.concatenate([oi] + bown).astype(np.int32)
+    nF = fv.shape[0]
+    gd = np.ones(3, np.int32)
+    for d, nm in enumerate(("xMin", "yMin", "zMin")):
+        if kinds[nm] == "empty":
+            gd[d] = -1
+    mesh = PolyMesh(points=np.ascontiguousarray(pts),
+                    face_offsets=(4 * np.arange(nF + 1)).astype(np.int32),
+                    face_verts=np.ascontiguousarray(fv.reshape(-1)),
+                    owner=owner, neighbour=ni.astype(np.int32),
+                    patches=patches, n_cells=nx * ny * nz, geometric_d=gd)
+    if compute_geometry:
+        mesh.compute_geometry()
+    return mesh
+
+
+def prism_box(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0), perturb: float = 0.0,
+              seed: int = 0) -> PolyMesh:
+    """Each hex of a box split into two triangular prisms (diagonal in the xy plane):
+    z-faces become triangles, side faces stay quads -> exercises the tri-face
+    GaussVolPoint path (GaussVolPointBase3D.C:161-318, 844-854)."""
+    base = hex_box(nx, ny, nz, lengths, perturb=perturb, seed=seed, compute_geometry=False)
+    pts = base.points
+    npx, npy = nx + 1, ny + 1
+
+    def pid(i, j, k):
+        return (k * npy + j) * npx + i
+
+    faces: List[Tuple[Tuple[int, ...], int, int, str]] = []   # (verts, owner, neighbour|-1, patch)
+    # cell numbering: hex h -> prisms 2h (lower-right: (i,j),(i+1,j),(i+1,j+1)) and 2h+1 (upper-left)
+    def hid(i, j, k):
+        return (k * ny + j) * nx + i
+
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                h = hid(i, j, k)
+                a, b = 2 * h, 2 * h + 1
+                p00, p10, p11, p01 = pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)
+                q00, q10, q11, q01 = pid(i, j, k + 1), pid(i + 1, j, k + 1), pid(i + 1, j + 1, k + 1), pid(i, j + 1, k + 1)
+                # diagonal quad between a and b (normal from a to b): plane through p00-p11
+                faces.append(((p00, q00, q11, p11), a, b, ""))
+                # +x face of prism a
+                if i < nx - 1:
+                    faces.append(((p10, p11, q11, q10), a, 2 * hid(i + 1, j, k) + 1, ""))
+                else:
+                    faces.append(((p10, p11, q11, q10), a, -1, "xMax"))
+                # -y face of prism a
+                if j == 0:
+                    faces.append(((p00, p10, q10, q00), a, -1, "yMin"))
+                # +y face of prism b
+                if j < ny - 1:
+                    faces.append(((p01, q01, q11, p11), b, 2 * hid(i, j + 1, k), ""))
+                else:
+                    faces.append(((p01, q01, q11, p11), b, -1, "yMax"))
+                # -x face of prism b
+                if i == 0:
+                    faces.append(((p00, q00, q01, p01), b, -1, "xMin"))
+                # z faces (triangles)
+                if k < nz - 1:
+                    faces.append(((q00, q10, q11), a, 2 * hid(i, j, k + 1), ""))
+                    faces.append(((q00, q11, q01), b, 2 * hid(i, j, k + 1) + 1, ""))
+                else:
+                    faces.append(((q00, q10, q11), a, -1, "zMax"))
+                    faces.append(((q00, q11, q01), b, -1, "zMax"))
+                if k == 0:
+                    faces.append(((p00, p11, p10), a, -1, "zMin"))
+                    faces.append(((p00, p01, p11), b, -1, "zMin"))
+    return _assemble(pts, faces, 2 * nx * ny * nz,
+                     ["xMin", "xMax", "yMin", "yMax", "zMin", "zMax"])
+
+
+def hexprism_poly(nx: int, ny: int, nz: int, a: float = 1.0, lz: float = 1.0) -> PolyMesh:
+    """Honeycomb of hexagonal prisms extruded through nz layers: caps are hexagons
+    (>4 vertices -> the reference's "other faces" nf*snGrad path,
+    GaussVolPointBase3D.C:103-106,760-768), sides are quads.  Boundary: 'sides','zMin','zMax'."""
+    # pointy-top hexagons, axial rows offset by half a cell
+    s3 = np.sqrt(3.0)
+    pt_index: Dict[Tuple[int, int], int] = {}
+    xy: List[Tuple[float, float]] = []
+
+    def corner(cx, cy, m):
+        ang = np.pi / 6.0 + m * np.pi / 3.0
+        px, py = cx + a * np.cos(ang), cy + a * np.sin(ang)
+        key = (int(round(px / a * 1e6)), int(round(py / a * 1e6)))
+        if key not in pt_index:
+            pt_index[key] = len(xy)
+            xy.append((px, py))
+        return pt_index[key]
+
+    hexes = []
+    for j in range(ny):
+        for i in range(nx):
+            cx = s3 * a * (i + 0.5 * (j % 2))
+            cy = 1.5 * a * j
+            hexes.append([corner(cx, cy, m) for m in range(6)])   # counter-clockwise
+    n2 = len(xy)
+    xy_arr = np.array(xy)
+    pts = np.zeros(((nz + 1) * n2, 3))
+    for k in range(nz + 1):
+        pts[k * n2:(k + 1) * n2, :2] = xy_arr
+        pts[k * n2:(k + 1) * n2, 2] = lz * k / nz
+    edge_owner: Dict[Tuple[int, int], int] = {}
+    for c, hx in enumerate(hexes):
+        for m in range(6):
+            e = (hx[m], hx[(m + 1) % 6])
+            edge_owner[e] = c
+    faces = []
+    ncl = nx * ny
+    for k in range(nz):
+        for c, hx in enumerate(hexes):
+            cell = k * ncl + c
+            lo = [v + k * n2 for v in hx]
+            hi = [v + (k + 1) * n2 for v in hx]
+            for m in range(6):
+                e = (hx[m], hx[(m + 1) % 6])
+                other = edge_owner.get((e[1], e[0]), -1)
+                quad = (lo[m], lo[(m + 1) % 6], hi[(m + 1) % 6], hi[m])   # outward for ccw hexagon
+                if other < 0:
+                    faces.append((quad, cell, -1, "sides"))
+                elif other > c:
+                    faces.append((quad, cell, k * ncl + other, ""))
+            if k < nz - 1:
+                faces.append((tuple(hi), cell, cell + ncl, ""))
+            else:
+                faces.append((tuple(hi), cell, -1, "zMax"))
+            if k == 0:
+                faces.append((tuple(reversed(lo)), cell, -1, "zMin"))
+    return _assemble(pts, faces, ncl * nz, ["sides", "zMin", "zMax"])
+
+
+def _assemble(pts, faces, n_cells, patch_names, kinds: Optional[Dict[str, str]] = None) -> PolyMesh:
+    kinds = kinds or {}
+    internal = [(o, n, v) for (v, o, n, p) in faces if n >= 0]
+    internal.sort(key=lambda t: (t[0], t[1]))
+    fv, owner, neigh = [], [], []
+    for o, n, v in internal:
+        assert o < n, "owner must be the lower-numbered cell"
+        fv.append(v); owner.append(o); neigh.append(n)
+    patches = []
+    start = len(fv)
+    for nm in patch_names:
+        pf = [(o, v) for (v, o, n, p) in faces if n < 0 and p == nm]
+        pf.sort(key=lambda t: t[0])
+        for o, v in pf:
+            fv.append(v); owner.append(o)
+        patches.append(Patch(nm, _KIND_NAMES[kinds.get(nm, "patch")], start, len(pf)))
+        start += len(pf)
+    off = np.zeros(len(fv) + 1, np.int32)
+    off[1:] = np.cumsum([len(v) for v in fv])
+    mesh = PolyMesh(points=np.ascontiguousarray(pts, dtype=np.float64), face_offsets=off,
+                    face_verts=np.array([x for v in fv for x in v], np.int32),
+                    owner=np.array(owner, np.int32), neighbour=np.array(neigh, np.int32),
+                    patches=patches, n_cells=n_cells)
+    return mesh.compute_geometry()
