@@ -1,0 +1,185 @@
+/* ============================================================================
+ * qgd_b200.h — C ABI of the B200-native QGD/QHD hot path (libqgd_b200.so)
+ *
+ * The reference (unicfdlab/QGDsolver) has no FFI: its boundary is OpenFOAM
+ * runTimeSelection + objectRegistry in-process C++.  This header
+ * is what an OpenFOAM-side shim library binds instead; every entry point cites
+ * the reference interface it replaces as  File.C:line  ==
+ * /root/reference/docs/html/File_8C_source.html, original source line.
+ *
+ * Rules: plain pointers and sizes only; the caller owns all host arrays; the
+ * library copies on *_create / *_set and owns device memory behind opaque
+ * handles; every call returns 0 on success or a negative qgd_status, and
+ * qgd_last_error() returns the message the shim forwards to
+ * FatalErrorInFunction (the reference aborts with FatalError at
+ * fvscStencil.C:72-78, QGDCoeffs.C:72-78, fvsc.C:62).  Nothing here ever falls
+ * back to a CPU path: without a usable CUDA device every compute call fails.
+ * One host thread per handle; not thread-safe per handle (fvscStencil.C:57).
+ * ==========================================================================*/
+#ifndef QGD_B200_H
+#define QGD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QGD_OK = 0,
+    QGD_ERR_INVALID = -1,        /* bad argument / inconsistent mesh            */
+    QGD_ERR_UNKNOWN_MODEL = -2,  /* runTimeSelection lookup failed               */
+    QGD_ERR_UNSUPPORTED = -3,    /* recognised but not implemented on device     */
+    QGD_ERR_CUDA = -4,           /* CUDA runtime / no device                     */
+    QGD_ERR_COMM = -5,           /* NCCL                                         */
+    QGD_ERR_STATE = -6           /* call order (e.g. step before init_fields)    */
+} qgd_status;
+
+/* polyPatch kinds the path distinguishes (emptyFvPatch, wedgeFvPatch,
+ * processorFvPatch tests at QGDCoeffs.C:346-348, GaussVolPointBase2D.C:175-199,
+ * GaussVolPointBase3D.C:76-79) */
+typedef enum { QGD_PATCH_GENERIC = 0, QGD_PATCH_EMPTY = 1, QGD_PATCH_PROCESSOR = 2, QGD_PATCH_WEDGE = 3 } qgd_patch_kind;
+
+/* boundary-condition kinds of the closed device-native set */
+typedef enum {
+    QGD_BC_FIXED_VALUE = 0,      /* fixedValue                                   */
+    QGD_BC_ZERO_GRADIENT = 1,    /* zeroGradient                                 */
+    QGD_BC_FIXED_GRADIENT = 2,   /* fixedGradient                                */
+    QGD_BC_QGD_FLUX = 3,         /* qgdFlux  qgdFluxFvPatchScalarField.C:159-208 */
+    QGD_BC_CALCULATED = 4        /* calculated                                   */
+} qgd_bc_kind;
+
+typedef struct qgd_mesh qgd_mesh;       /* fvMesh image on the device             */
+typedef struct qgd_fvsc qgd_fvsc;       /* one fvsc::fvscStencil instance         */
+typedef struct qgd_solver qgd_solver;   /* QGDFoam time loop state                */
+
+/* ---- library / device ------------------------------------------------------ */
+int         qgd_init(int device);                 /* cudaSetDevice + stream; call once per process (rank) */
+const char* qgd_last_error(void);                 /* message of the last failing call on this thread     */
+int         qgd_version(void);
+int         qgd_device_synchronize(void);
+
+/* ---- mesh: what fvMesh hands to the reference ------------------------------ */
+typedef struct {
+    int n_cells, n_faces, n_internal_faces, n_points, n_patches;
+    const double* points;              /* n_points*3            polyMesh::points()                 */
+    const int*    face_offsets;        /* n_faces+1             faceList as CSR                    */
+    const int*    face_verts;
+    const int*    owner;               /* n_faces                                                   */
+    const int*    neighbour;           /* n_internal_faces                                          */
+    const int*    patch_start;         /* n_patches             polyPatch::start()                  */
+    const int*    patch_size;
+    const int*    patch_kind;          /* qgd_patch_kind                                            */
+    const double* C;                   /* n_cells*3             fvMesh::C()                         */
+    const double* V;                   /* n_cells               fvMesh::V()                         */
+    const double* Cf;                  /* n_faces*3             fvMesh::Cf() incl. boundary         */
+    const double* Sf;                  /* n_faces*3             fvMesh::Sf()                        */
+    const double* magSf;               /* n_faces                                                   */
+    const double* weights;             /* n_faces               surfaceInterpolation::weights()     */
+    const double* deltaCoeffs;         /* n_faces                                                   */
+    const double* nonOrthDeltaCoeffs;  /* n_faces                                                   */
+    const double* neighb_cell_centres; /* n_bnd*3, processor patches: neighbFaceCellCentres() or NULL */
+    int geometric_d[3];                /* fvMesh::geometricD()                                      */
+} qgd_mesh_desc;
+
+int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out);
+int qgd_mesh_destroy(qgd_mesh* mesh);
+/* derived fields, for write-back / parity checks.  what: 0 hQGDf (n_faces)  QGDCoeffs.C:298-318
+ *                                                        1 hQGD  (n_cells)  QGDCoeffs.C:320-362 */
+int qgd_mesh_get(qgd_mesh* mesh, int what, double* out);
+
+/* ---- fvsc face-centre derivative operators (operator-level integration) ----
+ * qgd_fvsc_create  replaces fvscStencil::New / lookupOrNew (fvscStencil.C:59-118); scheme_name is the
+ *   fvSchemes::fvsc entry (fvsc.C:47-58): "GaussVolPoint" | "reduced"; "leastSquares"/"leastSquaresOpt"
+ *   are rejected in 3D exactly like fvsc.C:60-63 and otherwise reported as QGD_ERR_UNSUPPORTED;
+ *   anything else -> QGD_ERR_UNKNOWN_MODEL with the reference's "Unknown Model type" message.
+ * qgd_fvsc_grad    replaces fvscStencil::Grad(volScalarField|volVectorField)  (fvscStencil.H:105-116,
+ *   GaussVolPointStencil.C:71-99, reducedFaceNormalStencil.C:69-88).  ncmpt = 1 | 3.
+ * qgd_fvsc_div     replaces fvscStencil::Div(volVectorField|volTensorField)   (fvscStencil.H:119-130,
+ *   GaussVolPointStencil.C:101-129).  ncmpt = 3 | 9.
+ * Array layout is OpenFOAM's (array of vectors/tensors):
+ *   cell        n_cells*ncmpt   primitiveField()
+ *   bnd         n_bnd*ncmpt     boundaryField() values, already evaluated (the shim calls
+ *                               correctBoundaryConditions() itself, GaussVolPointStencil.C:73)
+ *   bnd_sngrad  n_bnd*ncmpt     boundaryField()[patchi].snGrad()  (GaussVolPointBase3D.C:791)
+ *   nbr         n_bnd*ncmpt     patchNeighbourField() on processor patches, or NULL (:785-786)
+ *   out         n_faces*(3*ncmpt) for grad, n_faces*(ncmpt/3) for div; internal faces then boundary faces.
+ * All pointers are HOST pointers; the call does H2D, kernels, D2H and returns when `out` is valid. */
+int qgd_fvsc_create(qgd_mesh* mesh, const char* scheme_name, qgd_fvsc** out);
+int qgd_fvsc_destroy(qgd_fvsc* op);
+int qgd_fvsc_grad(qgd_fvsc* op, int ncmpt, const double* cell, const double* bnd, const double* bnd_sngrad,
+                  const double* nbr, double* out);
+int qgd_fvsc_div(qgd_fvsc* op, int ncmpt, const double* cell, const double* bnd, const double* bnd_sngrad,
+                 const double* nbr, double* out);
+
+/* ---- QGDFoam (solver-level integration) -------------------------------------
+ * Dictionary content the reference reads: thermophysicalProperties (thermoType hePsiQGDThermo /
+ * pureMixture / const / hConst / perfectGas / sensibleInternalEnergy, psiQGDThermos.C:65-111),
+ * its QGD sub-dictionary (QGDThermo.C:48-82, QGDCoeffs.C:58-117, constScPrModel1.C:58-89),
+ * fvSchemes::fvsc, controlDict (QGDCourantNo.H:36, setDeltaT-QGDQHD.H:41-58). */
+typedef struct {
+    const char* fvsc_scheme;        /* fvSchemes::fvsc::default                                     */
+    const char* qgd_coeffs_model;   /* QGD::QGDCoeffs : "constScPrModel1"                           */
+    double R;                       /* perfectGas: R = 8314.47/W                                    */
+    double Cp, Hf, Tref, Hsref;     /* hConst                                                       */
+    double mu, Pr;                  /* constTransport                                               */
+    double ScQGD, PrQGD;            /* constScPrModel1.C:58-89 (default 1, 1)                       */
+    int implicit_diffusion;         /* QGD::implicitDiffusion (QGDThermo.C:61: default true).
+                                       Only false runs on the device in this round.              */
+    int alpha_eff_gamma_factor;     /* heThermo::alphaEff for internal energy [OF-v2312]            */
+    int energy_ddt_rhoE_quirk;      /* 1 = QGDEEqn.H:67-72 literally (default), 0 = fvc::ddt(rho,e) */
+    /* controlDict */
+    int adjust_time_step;           /* QGDCourantNo.H:36                                            */
+    double max_co, max_delta_t, c_tau;   /* readTimeControls.H ; setDeltaT-QGDQHD.H:45 (cTau 0.75)  */
+    double delta_t;                 /* initial deltaT                                               */
+} qgd_qgdfoam_desc;
+
+int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* desc, qgd_solver** out);
+int qgd_qgdfoam_destroy(qgd_solver* s);
+/* boundary conditions of U, T, p per patch (0/U, 0/T, 0/p): kinds n_patches each (qgd_bc_kind),
+ * fixed values per boundary face: U n_bnd*3, T n_bnd, p n_bnd (read only where the kind is fixedValue). */
+int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const int* bc_p,
+                        const double* val_U, const double* val_T, const double* val_p);
+/* initial internal fields as read from 0/ (QGDFoam createFields.H:3-109): U n_cells*3, T, p n_cells,
+ * alphaQGD n_cells or NULL (QGDCoeffs.C:119-160: uniform 0.5).  Runs thermo construction on the device. */
+int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, const double* p, const double* alphaQGD);
+/* n_steps passes of the QGDFoam.C:90-163 loop body, fully on the device (no host sync inside). */
+int qgd_qgdfoam_step(qgd_solver* s, int n_steps);
+/* Same loop, but with HOST state buffers (operator / "plug-in" style hand-off on every call): the full cell
+ * state is uploaded before the steps and downloaded after them, inside the call.  This is the state the
+ * reference keeps in its registered fields (createFields.H:10-74 + thermo:mu); boundary fields stay on the
+ * device.  Buffers should be page-locked (cudaHostAlloc / cudaHostRegister) for full PCIe speed. */
+typedef struct {
+    double* rho;   /* n_cells   */
+    double* U;     /* n_cells*3 */
+    double* e;     /* n_cells   */
+    double* p;     /* n_cells   */
+    double* T;     /* n_cells   */
+    double* rhoU;  /* n_cells*3 */
+    double* rhoE;  /* n_cells   */
+    double* mu;    /* n_cells   thermo:mu incl. muQGD (QGDThermo.C:91-98) */
+} qgd_state_host;
+#define QGD_STATE_DOUBLES_PER_CELL 12
+int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, const qgd_state_host* out);
+/* fields: 0 rho, 1 rhoU(3), 2 rhoE, 3 U(3), 4 e, 5 p, 6 T, 7 c, 8 mu, 9 alpha, 10 tauQGD, 11 H.
+ * cells: n_cells*k host buffer, bnd: n_bnd*k host buffer or NULL. */
+int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd);
+/* face flux of the last step: 0 phiJm, 1 momentum flux (phiJmU+phiP-phiPi, 3), 2 energy flux
+ * (phiJmH+phiQ-phiPiU); n_faces*k host buffer */
+int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out);
+int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, double* time);
+/* kernel launches issued by this solver so far (bench bookkeeping) */
+long long qgd_qgdfoam_launch_count(qgd_solver* s);
+/* CUDA-event timing of the device step loop: call begin, steps, end -> milliseconds on the solver stream */
+int qgd_timer_begin(void);
+int qgd_timer_end(float* ms);
+
+/* ---- LDU PCG (QHDpEqn.H:45 -> lduMatrix::solver PCG + DIC|diagonal) ---------- */
+/* symmetric LDU matrix on the mesh addressing (lower == upper); precond: 0 none, 1 diagonal (Jacobi),
+ * 2 DIC (device: level-scheduled).  Host pointers. Returns iterations in *iters. */
+int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x,
+                  double tolerance, double rel_tol, int max_iter, int precond,
+                  int* iters, double* initial_residual, double* final_residual);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGD_B200_H */

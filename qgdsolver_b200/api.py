@@ -1,0 +1,309 @@
+"""ctypes binding of libqgd_b200.so (include/qgd_b200.h) for tests and bench.py.
+
+This is harness glue, not the product: the product is the C-ABI library plus the C++ host mirror under
+qgdsolver_b200/host/.  Names follow the reference: fvsc::fvscStencil (fvscStencil.H:46-137),
+fvsc::grad / fvsc::div (fvsc.H:46-68), QGDFoam (QGDFoam.C:68-168).
+There is no CPU fallback: every compute call raises QGDError when no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .polymesh import PolyMesh
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqgd_b200.so")
+
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED = 0, 1, 2, 3, 4
+QGD_OK, ERR_INVALID, ERR_UNKNOWN_MODEL, ERR_UNSUPPORTED, ERR_CUDA, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
+
+# every symbol include/qgd_b200.h declares (checked by tests/test_abi_cpu.py)
+ABI_SYMBOLS = [
+    "qgd_init", "qgd_last_error", "qgd_version", "qgd_device_synchronize",
+    "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get",
+    "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
+    "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
+    "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
+    "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_timer_begin", "qgd_timer_end",
+    "qgd_pcg_solve",
+]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class QGDError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[qgd status {code}] {msg}")
+        self.code = code
+        self.message = msg
+
+
+class _MeshDesc(C.Structure):
+    _fields_ = [("n_cells", C.c_int), ("n_faces", C.c_int), ("n_internal_faces", C.c_int), ("n_points", C.c_int),
+                ("n_patches", C.c_int),
+                ("points", _dp), ("face_offsets", _ip), ("face_verts", _ip), ("owner", _ip), ("neighbour", _ip),
+                ("patch_start", _ip), ("patch_size", _ip), ("patch_kind", _ip),
+                ("C", _dp), ("V", _dp), ("Cf", _dp), ("Sf", _dp), ("magSf", _dp), ("weights", _dp),
+                ("deltaCoeffs", _dp), ("nonOrthDeltaCoeffs", _dp), ("neighb_cell_centres", _dp),
+                ("geometric_d", C.c_int * 3)]
+
+
+class QGDFoamDesc(C.Structure):
+    _fields_ = [("fvsc_scheme", C.c_char_p), ("qgd_coeffs_model", C.c_char_p),
+                ("R", C.c_double), ("Cp", C.c_double), ("Hf", C.c_double), ("Tref", C.c_double), ("Hsref", C.c_double),
+                ("mu", C.c_double), ("Pr", C.c_double), ("ScQGD", C.c_double), ("PrQGD", C.c_double),
+                ("implicit_diffusion", C.c_int), ("alpha_eff_gamma_factor", C.c_int), ("energy_ddt_rhoE_quirk", C.c_int),
+                ("adjust_time_step", C.c_int),
+                ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double)]
+
+
+class _StateHost(C.Structure):
+    _fields_ = [(n, _dp) for n in ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; fails loudly when it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QGDError(ERR_CUDA, f"{LIB_PATH} is missing: build it with `python -m qgdsolver_b200.build` "
+                                 "(the product has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.qgd_last_error.restype = C.c_char_p
+    L.qgd_init.argtypes = [C.c_int]
+    L.qgd_mesh_create.argtypes = [C.POINTER(_MeshDesc), C.POINTER(C.c_void_p)]
+    L.qgd_mesh_destroy.argtypes = [C.c_void_p]
+    L.qgd_mesh_get.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.qgd_fvsc_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.qgd_fvsc_destroy.argtypes = [C.c_void_p]
+    for fn in (L.qgd_fvsc_grad, L.qgd_fvsc_div):
+        fn.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
+    L.qgd_qgdfoam_create.argtypes = [C.c_void_p, C.POINTER(QGDFoamDesc), C.POINTER(C.c_void_p)]
+    L.qgd_qgdfoam_destroy.argtypes = [C.c_void_p]
+    L.qgd_qgdfoam_set_bcs.argtypes = [C.c_void_p, _ip, _ip, _ip, _dp, _dp, _dp]
+    L.qgd_qgdfoam_init_fields.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    L.qgd_qgdfoam_step.argtypes = [C.c_void_p, C.c_int]
+    L.qgd_qgdfoam_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(_StateHost), C.POINTER(_StateHost)]
+    L.qgd_qgdfoam_get.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L.qgd_qgdfoam_get_flux.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.qgd_qgdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.qgd_qgdfoam_launch_count.restype = C.c_longlong
+    L.qgd_qgdfoam_launch_count.argtypes = [C.c_void_p]
+    L.qgd_timer_end.argtypes = [C.POINTER(C.c_float)]
+    L.qgd_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
+                                _ip, _dp, _dp]
+    _lib = L
+    return L
+
+
+def _check(code: int):
+    if code != QGD_OK:
+        raise QGDError(code, load_library().qgd_last_error().decode(errors="replace"))
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def init(device: int = 0):
+    _check(load_library().qgd_init(device))
+
+
+def synchronize():
+    _check(load_library().qgd_device_synchronize())
+
+
+class Mesh:
+    """Device image of an fvMesh (qgd_mesh_create)."""
+
+    def __init__(self, mesh: PolyMesh):
+        self.mesh = mesh
+        d = _MeshDesc()
+        d.n_cells, d.n_faces, d.n_internal_faces, d.n_points = mesh.n_cells, mesh.n_faces, mesh.n_internal, mesh.n_points
+        d.n_patches = len(mesh.patches)
+        k = dict(points=_f64(mesh.points), C=_f64(mesh.C), V=_f64(mesh.V), Cf=_f64(mesh.Cf), Sf=_f64(mesh.Sf),
+                 magSf=_f64(mesh.magSf), weights=_f64(mesh.weights), deltaCoeffs=_f64(mesh.deltaCoeffs),
+                 nonOrthDeltaCoeffs=_f64(mesh.nonOrthDeltaCoeffs),
+                 neighb_cell_centres=_f64(np.nan_to_num(mesh.neighb_cell_centres)))
+        ki = dict(face_offsets=np.ascontiguousarray(mesh.face_offsets, np.int32),
+                  face_verts=np.ascontiguousarray(mesh.face_verts, np.int32),
+                  owner=np.ascontiguousarray(mesh.owner, np.int32),
+                  neighbour=np.ascontiguousarray(mesh.neighbour, np.int32),
+                  patch_start=np.array([p.start for p in mesh.patches], np.int32),
+                  patch_size=np.array([p.size for p in mesh.patches], np.int32),
+                  patch_kind=np.array([p.kind for p in mesh.patches], np.int32))
+        for n, a in k.items():
+            setattr(d, n, _d(a))
+        for n, a in ki.items():
+            setattr(d, n, _i(a))
+        for j in range(3):
+            d.geometric_d[j] = int(mesh.geometric_d[j])
+        self._h = C.c_void_p()
+        _check(load_library().qgd_mesh_create(C.byref(d), C.byref(self._h)))
+
+    def hQGDf(self):
+        out = np.empty(self.mesh.n_faces)
+        _check(load_library().qgd_mesh_get(self._h, 0, _d(out)))
+        return out
+
+    def hQGD(self):
+        out = np.empty(self.mesh.n_cells)
+        _check(load_library().qgd_mesh_get(self._h, 1, _d(out)))
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().qgd_mesh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FvscStencil:
+    """fvsc::fvscStencil::New(name, mesh) + Grad/Div (fvscStencil.H:86-130)."""
+
+    def __init__(self, mesh: Mesh, name: str):
+        self.mesh = mesh
+        self._h = C.c_void_p()
+        _check(load_library().qgd_fvsc_create(mesh._h, name.encode(), C.byref(self._h)))
+
+    def _apply(self, fn, k, ok, cell, bnd, bsg, nbr):
+        m = self.mesh.mesh
+        cell, bnd, bsg, nbr = _f64(cell), _f64(bnd), _f64(bsg), _f64(nbr)
+        out = np.zeros((m.n_faces, ok) if ok > 1 else m.n_faces)
+        _check(fn(self._h, k, _d(cell), _d(bnd), _d(bsg), _d(nbr), _d(out)))
+        return out
+
+    def Grad(self, cell, bnd, bnd_sngrad, nbr=None):
+        k = 1 if np.ndim(cell) == 1 else cell.shape[1]
+        return self._apply(load_library().qgd_fvsc_grad, k, 3 * k, cell, bnd, bnd_sngrad, nbr)
+
+    def Div(self, cell, bnd, bnd_sngrad, nbr=None):
+        k = cell.shape[1]
+        return self._apply(load_library().qgd_fvsc_div, k, k // 3, cell, bnd, bnd_sngrad, nbr)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().qgd_fvsc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+CELL_FIELDS = {"rho": (0, 1), "rhoU": (1, 3), "rhoE": (2, 1), "U": (3, 3), "e": (4, 1), "p": (5, 1), "T": (6, 1),
+               "c": (7, 1), "mu": (8, 1), "alpha": (9, 1), "tauQGD": (10, 1), "H": (11, 1)}
+
+
+class QGDFoam:
+    """The QGDFoam time loop on the device (QGDFoam.C:68-168)."""
+
+    def __init__(self, mesh: Mesh, *, R, Cp, mu=0.0, Pr=1.0, Hf=0.0, Tref=0.0, Hsref=0.0, ScQGD=1.0, PrQGD=1.0,
+                 fvsc_scheme="GaussVolPoint", qgd_coeffs="constScPrModel1", implicit_diffusion=False,
+                 alpha_eff_gamma_factor=True, energy_ddt_rhoE_quirk=True, adjust_time_step=False, max_co=0.3,
+                 max_delta_t=1e30, c_tau=0.75, delta_t=1e-4):
+        self.mesh = mesh
+        d = QGDFoamDesc()
+        self._names = (fvsc_scheme.encode(), qgd_coeffs.encode())
+        d.fvsc_scheme, d.qgd_coeffs_model = self._names
+        d.R, d.Cp, d.Hf, d.Tref, d.Hsref, d.mu, d.Pr, d.ScQGD, d.PrQGD = R, Cp, Hf, Tref, Hsref, mu, Pr, ScQGD, PrQGD
+        d.implicit_diffusion = int(implicit_diffusion)
+        d.alpha_eff_gamma_factor = int(alpha_eff_gamma_factor)
+        d.energy_ddt_rhoE_quirk = int(energy_ddt_rhoE_quirk)
+        d.adjust_time_step = int(adjust_time_step)
+        d.max_co, d.max_delta_t, d.c_tau, d.delta_t = max_co, max_delta_t, c_tau, delta_t
+        self._h = C.c_void_p()
+        _check(load_library().qgd_qgdfoam_create(mesh._h, C.byref(d), C.byref(self._h)))
+
+    def set_bcs(self, bcU, bcT, bcP, valU=None, valT=None, valP=None):
+        a = [np.ascontiguousarray(x, np.int32) for x in (bcU, bcT, bcP)]
+        v = [_f64(x) for x in (valU, valT, valP)]
+        _check(load_library().qgd_qgdfoam_set_bcs(self._h, _i(a[0]), _i(a[1]), _i(a[2]), _d(v[0]), _d(v[1]), _d(v[2])))
+
+    def init_fields(self, U, T, p, alphaQGD=None):
+        U, T, p, alphaQGD = _f64(U), _f64(T), _f64(p), _f64(alphaQGD)
+        _check(load_library().qgd_qgdfoam_init_fields(self._h, _d(U), _d(T), _d(p), _d(alphaQGD)))
+
+    def step(self, n_steps: int = 1):
+        _check(load_library().qgd_qgdfoam_step(self._h, n_steps))
+
+    @staticmethod
+    def _state_struct(bufs) -> _StateHost:
+        s = _StateHost()
+        for n in ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu"):
+            setattr(s, n, _d(bufs[n]))
+        return s
+
+    def step_host(self, n_steps, state_in: Optional[dict], state_out: Optional[dict]):
+        """state dicts hold contiguous float64 arrays rho,U,e,p,T,rhoU,rhoE,mu (ideally page-locked)."""
+        si = self._state_struct(state_in) if state_in is not None else None
+        so = self._state_struct(state_out) if state_out is not None else None
+        _check(load_library().qgd_qgdfoam_step_host(self._h, n_steps, C.byref(si) if si else None,
+                                                    C.byref(so) if so else None))
+
+    def get(self, name: str, with_bnd: bool = False):
+        fid, k = CELL_FIELDS[name]
+        m = self.mesh.mesh
+        cells = np.zeros((m.n_cells, k) if k > 1 else m.n_cells)
+        bnd = np.zeros((m.n_bnd, k) if k > 1 else m.n_bnd) if with_bnd else None
+        _check(load_library().qgd_qgdfoam_get(self._h, fid, _d(cells), _d(bnd)))
+        return (cells, bnd) if with_bnd else cells
+
+    def get_flux(self, which: int):
+        m = self.mesh.mesh
+        out = np.zeros((m.n_faces, 3) if which == 1 else m.n_faces)
+        _check(load_library().qgd_qgdfoam_get_flux(self._h, which, _d(out)))
+        return out
+
+    def scalars(self):
+        dt, co, t = C.c_double(), C.c_double(), C.c_double()
+        _check(load_library().qgd_qgdfoam_get_scalars(self._h, C.byref(dt), C.byref(co), C.byref(t)))
+        return dict(deltaT=dt.value, CoNum=co.value, time=t.value)
+
+    def launch_count(self) -> int:
+        return int(load_library().qgd_qgdfoam_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().qgd_qgdfoam_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def timer_begin():
+    _check(load_library().qgd_timer_begin())
+
+
+def timer_end() -> float:
+    ms = C.c_float()
+    _check(load_library().qgd_timer_end(C.byref(ms)))
+    return float(ms.value)

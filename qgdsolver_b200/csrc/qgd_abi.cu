@@ -1,0 +1,533 @@
+// C-ABI layer of libqgd_b200.so (include/qgd_b200.h): opaque handles, model selection with the reference's
+// error behaviour, H2D/D2H staging for the operator-level calls.  No compute happens on the host here.
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <memory>
+
+#include "qgd_kernels.cuh"
+
+namespace qgd {
+
+static thread_local std::string g_lastError;
+void setLastError(const std::string& m) { g_lastError = m; }
+
+static cudaStream_t g_stream = nullptr;
+static bool g_initialised = false;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
+static void requireInit()
+{
+    if (!g_initialised) throw Error(QGD_ERR_STATE, "qgd_init(device) must be called first (no CPU fallback exists)");
+}
+
+template <class F> static int guarded(F&& fn)
+{
+    try { fn(); return QGD_OK; }
+    catch (const Error& e) { setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { setLastError(e.what()); return QGD_ERR_INVALID; }
+}
+
+// runTimeSelection tables of the path (names only; the OpenFOAM shim registers the same TypeNames)
+static const char* const kFvscTable[] = {"GaussVolPoint", "leastSquares", "leastSquaresOpt", "reduced"};          // sortedToc order
+static const char* const kCoeffsTable[] = {"H2bynuQHD", "HbyUQHD", "T0byGr", "constScPrModel1", "constScPrModel1n",
+                                           "constScPrModel2", "constTau", "varScModel5", "varScModel6", "varScModel7"};
+
+template <size_t N> static std::string toc(const char* const (&t)[N])
+{
+    std::string s = std::to_string(N) + "\n(\n";
+    for (size_t i = 0; i < N; ++i) { s += t[i]; s += "\n"; }
+    s += ")\n";
+    return s;
+}
+template <size_t N> static bool inTable(const char* const (&t)[N], const std::string& n)
+{
+    for (size_t i = 0; i < N; ++i) if (n == t[i]) return true;
+    return false;
+}
+
+} // namespace qgd
+
+using namespace qgd;
+
+struct qgd_fvsc {
+    qgd_mesh* mesh = nullptr;
+    bool reduced = false;
+    DevBuf<int4> vtx;
+    DevBuf<int> flags;
+    DevBuf<double> G, halfDist;
+    // staging for operator-level calls (grown on demand)
+    DevBuf<double> dCell, dBnd, dBsg, dNbr, dPts, dOut;
+    FaceView view() const
+    {
+        const qgd_mesh& m = *mesh;
+        FaceView v;
+        v.nI = m.h.nInternal; v.nF = m.h.nFaces; v.nB = m.h.nBnd;
+        v.zeroDivCmpt = -1;
+        if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
+        v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
+        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
+        return v;
+    }
+};
+
+struct qgd_solver {
+    qgd_mesh* mesh = nullptr;
+    std::unique_ptr<qgd_fvsc> fvsc;
+    qgd_qgdfoam_desc desc{};
+    Consts k{};
+    DevBuf<RecA> A, bA;
+    DevBuf<RecB> B, bB;
+    DevBuf<RecP> P;
+    DevBuf<double> aQGD, Fm, FU, FE, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage;
+    DevBuf<int> bcU, bcT, bcP;
+    DevBuf<StepScalars> sc;
+    long long launches = 0;
+    bool anyQgdFlux = false, bcsSet = false, fieldsSet = false;
+    int gridFaces = 148;
+    SolverView sview() const
+    {
+        const qgd_mesh& m = *mesh;
+        SolverView s;
+        s.nCells = m.h.nCells; s.nPoints = m.h.nPoints; s.nPatchPoints = (int)m.h.patchPoints.size();
+        s.A = A.p; s.B = B.p; s.P = P.p;
+        s.pcOff = m.pcOff.p; s.pcCell = m.pcCell.p; s.pcW = m.pcW.p;
+        s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
+        s.cfOff = m.cfOff.p; s.cfEnc = m.cfEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
+        s.Fm = Fm.p; s.FU = FU.p; s.FE = FE.p; s.sc = sc.p;
+        return s;
+    }
+    BndState bview() const
+    {
+        BndState b;
+        b.A = bA.p; b.B = bB.p; b.psi = psiB.p; b.pGrad = pGrad.p; b.pNew = pNew.p; b.phiw = phiw.p;
+        b.bcU = bcU.p; b.bcT = bcT.p; b.bcP = bcP.p; b.bvU = bvU.p; b.bvT = bvT.p; b.bvP = bvP.p;
+        return b;
+    }
+};
+
+namespace {
+
+template <class T> void h2d(DevBuf<T>& d, const T* h, size_t n)
+{
+    if (d.n < n) d.alloc(n);
+    if (n) QGD_CUDA(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, g_stream));
+}
+template <class T> void d2h(T* h, const T* d, size_t n)
+{
+    if (n) QGD_CUDA(cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, g_stream));
+}
+
+// state hand-off kernels for qgd_qgdfoam_step_host
+__global__ void k_pack_state(Consts k, int n, RecA* A, RecB* B, const double* __restrict__ aQGD, const double* __restrict__ st)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const size_t N = n;
+    const double rho = st[c], Ux = st[N + 3 * (size_t)c], Uy = st[N + 3 * (size_t)c + 1], Uz = st[N + 3 * (size_t)c + 2];
+    const double e = st[4 * N + c], p = st[5 * N + c], T = st[6 * N + c];
+    const double rUx = st[7 * N + 3 * (size_t)c], rUy = st[7 * N + 3 * (size_t)c + 1], rUz = st[7 * N + 3 * (size_t)c + 2];
+    const double rhoE = st[10 * N + c], mu = st[11 * N + c];
+    const double psi = 1.0 / (k.R * T);
+    const double cs = sqrt(k.gamma / psi);
+    const double alpha = k.mu / k.Pr + (mu - k.mu) / k.PrQGD;
+    A[c] = RecA{rho, Ux, Uy, Uz, e, p, T, (rhoE + p) / rho};
+    B[c] = RecB{rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD[c] / cs};
+}
+__global__ void k_unpack_state(int n, const RecA* __restrict__ A, const RecB* __restrict__ B, double* st)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const size_t N = n;
+    const RecA a = A[c];
+    const RecB b = B[c];
+    st[c] = a.rho;
+    st[N + 3 * (size_t)c] = a.Ux; st[N + 3 * (size_t)c + 1] = a.Uy; st[N + 3 * (size_t)c + 2] = a.Uz;
+    st[4 * N + c] = a.e; st[5 * N + c] = a.p; st[6 * N + c] = a.T;
+    st[7 * N + 3 * (size_t)c] = b.rhoUx; st[7 * N + 3 * (size_t)c + 1] = b.rhoUy; st[7 * N + 3 * (size_t)c + 2] = b.rhoUz;
+    st[10 * N + c] = b.rhoE; st[11 * N + c] = b.mu;
+}
+
+void runSteps(qgd_solver* s, int n)
+{
+    const FaceView fv = s->fvsc->view();
+    const SolverView sv = s->sview();
+    const BndState bs = s->bview();
+    for (int i = 0; i < n; ++i)
+        s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0);
+    QGD_CUDA(cudaGetLastError());
+}
+
+} // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int qgd_version(void) { return 100; }
+
+const char* qgd_last_error(void) { return g_lastError.c_str(); }
+
+int qgd_init(int device)
+{
+    return guarded([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw Error(QGD_ERR_CUDA, std::string("qgd_init: no CUDA device available (") + cudaGetErrorString(e) +
+                                          "); libqgd_b200 has no CPU fallback");
+        if (device < 0 || device >= n) throw Error(QGD_ERR_INVALID, "qgd_init: device index out of range");
+        QGD_CUDA(cudaSetDevice(device));
+        if (!g_stream) QGD_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+        if (!g_ev0) { QGD_CUDA(cudaEventCreate(&g_ev0)); QGD_CUDA(cudaEventCreate(&g_ev1)); }
+        g_initialised = true;
+    });
+}
+
+int qgd_device_synchronize(void)
+{
+    return guarded([&] { requireInit(); QGD_CUDA(cudaStreamSynchronize(g_stream)); });
+}
+
+int qgd_timer_begin(void) { return guarded([&] { requireInit(); QGD_CUDA(cudaEventRecord(g_ev0, g_stream)); }); }
+int qgd_timer_end(float* ms)
+{
+    return guarded([&] {
+        requireInit();
+        QGD_CUDA(cudaEventRecord(g_ev1, g_stream));
+        QGD_CUDA(cudaEventSynchronize(g_ev1));
+        QGD_CUDA(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    });
+}
+
+// ---------------------------------------------------------------- mesh
+int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
+{
+    return guarded([&] {
+        requireInit();
+        if (!desc || !out) throw Error(QGD_ERR_INVALID, "qgd_mesh_create: null argument");
+        std::unique_ptr<qgd_mesh> m(new qgd_mesh());
+        m->h.build(*desc);
+        const HostMesh& h = m->h;
+        m->owner.upload(h.owner, g_stream); m->neighbour.upload(h.neighbour, g_stream);
+        m->cfOff.upload(h.cfOff, g_stream); m->cfEnc.upload(h.cfEnc, g_stream);
+        m->pcOff.upload(h.pcOff, g_stream); m->pcCell.upload(h.pcCell, g_stream); m->pcW.upload(h.pcW, g_stream);
+        m->patchPoints.upload(h.patchPoints, g_stream); m->ppOff.upload(h.ppOff, g_stream);
+        m->ppFace.upload(h.ppFace, g_stream); m->ppW.upload(h.ppW, g_stream);
+        std::vector<int> bk(h.nBnd);
+        for (int b = 0; b < h.nBnd; ++b) bk[b] = h.patchKind[h.bfacePatch[b]];
+        m->bfaceKind.upload(bk, g_stream);
+        std::vector<double> sfSoA(3 * (size_t)h.nFaces);
+        for (int f = 0; f < h.nFaces; ++f)
+            for (int d = 0; d < 3; ++d) sfSoA[(size_t)d * h.nFaces + f] = h.Sf[3 * (size_t)f + d];
+        m->Sf.upload(sfSoA, g_stream);
+        m->magSf.upload(h.magSf, g_stream); m->w.upload(h.w, g_stream); m->dC.upload(h.dC, g_stream);
+        m->ndC.upload(h.ndC, g_stream); m->V.upload(h.V, g_stream);
+        m->hQGDf.upload(h.hQGDf, g_stream); m->hQGD.upload(h.hQGD, g_stream);
+        *out = m.release();
+    });
+}
+
+int qgd_mesh_destroy(qgd_mesh* mesh) { return guarded([&] { delete mesh; }); }
+
+int qgd_mesh_get(qgd_mesh* mesh, int what, double* out)
+{
+    return guarded([&] {
+        if (!mesh || !out) throw Error(QGD_ERR_INVALID, "qgd_mesh_get: null argument");
+        if (what == 0) { d2h(out, mesh->hQGDf.p, mesh->hQGDf.n); }
+        else if (what == 1) { d2h(out, mesh->hQGD.p, mesh->hQGD.n); }
+        else throw Error(QGD_ERR_INVALID, "qgd_mesh_get: unknown field id");
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+    });
+}
+
+// ---------------------------------------------------------------- fvsc
+static void fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
+{
+    // fvsc.C:47-85 (fvscOpName checks) + fvscStencil.C:59-95 (New)
+    if (!inTable(kFvscTable, name))
+        throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown Model type " + name + "\n\nValid model types are:\n" + toc(kFvscTable));
+    if ((name == "leastSquares" || name == "leastSquaresOpt")) {
+        if (mesh->h.nD == 3) throw Error(QGD_ERR_INVALID, "Can't use leastSquares or leastSquaresOpt in 3D case.");
+        throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " is not available on the device yet (no CPU fallback)");
+    }
+    op.mesh = mesh;
+    op.reduced = (name == "reduced");
+    std::vector<int> vtx, flags;
+    std::vector<double> G, hd;
+    mesh->h.buildFaceRecords(op.reduced, vtx, flags, G, hd);
+    std::vector<int4> v4(mesh->h.nFaces);
+    for (int f = 0; f < mesh->h.nFaces; ++f) v4[f] = make_int4(vtx[4 * (size_t)f], vtx[4 * (size_t)f + 1], vtx[4 * (size_t)f + 2], vtx[4 * (size_t)f + 3]);
+    op.vtx.upload(v4, g_stream); op.flags.upload(flags, g_stream); op.G.upload(G, g_stream); op.halfDist.upload(hd, g_stream);
+}
+
+int qgd_fvsc_create(qgd_mesh* mesh, const char* scheme_name, qgd_fvsc** out)
+{
+    return guarded([&] {
+        requireInit();
+        if (!mesh || !scheme_name || !out) throw Error(QGD_ERR_INVALID, "qgd_fvsc_create: null argument");
+        std::unique_ptr<qgd_fvsc> op(new qgd_fvsc());
+        fvscBuild(*op, mesh, scheme_name);
+        *out = op.release();
+    });
+}
+
+int qgd_fvsc_destroy(qgd_fvsc* op) { return guarded([&] { delete op; }); }
+
+static void fvscApply(qgd_fvsc* op, bool isGrad, int K, const double* cell, const double* bnd, const double* bsg,
+                      const double* nbr, double* out)
+{
+    requireInit();
+    if (!op || !cell || !out) throw Error(QGD_ERR_INVALID, "fvsc operator: null argument");
+    const HostMesh& h = op->mesh->h;
+    if (h.nBnd && (!bnd || !bsg)) throw Error(QGD_ERR_INVALID, "fvsc operator: boundary values and snGrad are required");
+    if (isGrad && K != 1 && K != 3) throw Error(QGD_ERR_INVALID, "fvsc::grad: ncmpt must be 1 or 3");
+    if (!isGrad && K != 3 && K != 9) throw Error(QGD_ERR_INVALID, "fvsc::div: ncmpt must be 3 or 9");
+    const size_t outK = isGrad ? 3 * (size_t)K : (size_t)K / 3;
+    h2d(op->dCell, cell, (size_t)h.nCells * K);
+    h2d(op->dBnd, bnd, (size_t)h.nBnd * K);
+    h2d(op->dBsg, bsg, (size_t)h.nBnd * K);
+    if (nbr) h2d(op->dNbr, nbr, (size_t)h.nBnd * K);
+    if (op->dPts.n < (size_t)h.nPoints * K) op->dPts.alloc((size_t)h.nPoints * K);
+    if (op->dOut.n < (size_t)h.nFaces * outK) op->dOut.alloc((size_t)h.nFaces * outK);
+    const FaceView fv = op->view();
+    const bool needPoints = !op->reduced && h.nD > 1;
+    if (needPoints) launchPointGather(g_stream, K, *op->mesh, op->dCell.p, op->dBnd.p, op->dPts.p);
+    if (isGrad) launchFvscGrad(g_stream, K, fv, op->dCell.p, op->dPts.p, op->dBnd.p, op->dBsg.p, nbr ? op->dNbr.p : nullptr, op->dOut.p);
+    else launchFvscDiv(g_stream, K, fv, op->dCell.p, op->dPts.p, op->dBnd.p, op->dBsg.p, nbr ? op->dNbr.p : nullptr, op->dOut.p);
+    d2h(out, op->dOut.p, (size_t)h.nFaces * outK);
+    QGD_CUDA(cudaStreamSynchronize(g_stream));
+}
+
+int qgd_fvsc_grad(qgd_fvsc* op, int ncmpt, const double* cell, const double* bnd, const double* bsg, const double* nbr, double* out)
+{
+    return guarded([&] { fvscApply(op, true, ncmpt, cell, bnd, bsg, nbr, out); });
+}
+int qgd_fvsc_div(qgd_fvsc* op, int ncmpt, const double* cell, const double* bnd, const double* bsg, const double* nbr, double* out)
+{
+    return guarded([&] { fvscApply(op, false, ncmpt, cell, bnd, bsg, nbr, out); });
+}
+
+// ---------------------------------------------------------------- QGDFoam
+int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** out)
+{
+    return guarded([&] {
+        requireInit();
+        if (!mesh || !d || !out || !d->fvsc_scheme || !d->qgd_coeffs_model) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_create: null argument");
+        const std::string model = d->qgd_coeffs_model;
+        if (!inTable(kCoeffsTable, model))     // QGDCoeffs.C:70-79
+            throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown QGD coeffs evaluation approach type " + model +
+                                                   "\n\nValid model types are:\n" + toc(kCoeffsTable));
+        if (model != "constScPrModel1")
+            throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not available on the device yet (no CPU fallback)");
+        if (d->implicit_diffusion)
+            throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true is not available on the device yet; set QGD::implicitDiffusion false");
+        for (int pk : mesh->h.patchKind)
+            if (pk == QGD_PATCH_PROCESSOR)
+                throw Error(QGD_ERR_UNSUPPORTED, "processor patches: use the multi-GPU entry points");
+        if (!(d->delta_t > 0.0)) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_create: deltaT must be positive");
+        std::unique_ptr<qgd_solver> s(new qgd_solver());
+        s->mesh = mesh;
+        s->desc = *d;
+        s->fvsc.reset(new qgd_fvsc());
+        fvscBuild(*s->fvsc, mesh, d->fvsc_scheme);
+        Consts& k = s->k;
+        k.R = d->R; k.Cp = d->Cp; k.Cv = d->Cp - d->R; k.Tref = d->Tref; k.Hsref = d->Hsref; k.mu = d->mu; k.Pr = d->Pr;
+        k.ScQGD = d->ScQGD; k.PrQGD = d->PrQGD; k.gamma = d->Cp / (d->Cp - d->R);
+        k.alphaEffGamma = d->alpha_eff_gamma_factor; k.energyQuirk = d->energy_ddt_rhoE_quirk; k.reducedScheme = s->fvsc->reduced;
+        const HostMesh& h = mesh->h;
+        s->A.alloc(h.nCells); s->B.alloc(h.nCells); s->P.alloc(h.nPoints);
+        s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
+        s->aQGD.alloc(h.nCells);
+        s->Fm.alloc(h.nFaces); s->FU.alloc(3 * (size_t)h.nFaces); s->FE.alloc(h.nFaces);
+        s->psiB.alloc(h.nBnd); s->pGrad.alloc(h.nBnd); s->pNew.alloc(h.nBnd); s->phiw.alloc(h.nBnd);
+        s->P.zero(g_stream); s->Fm.zero(g_stream); s->FU.zero(g_stream); s->FE.zero(g_stream);
+        StepScalars sc{};
+        sc.dt = d->delta_t; sc.time = 0.0; sc.coNum = -1.0; sc.coMaxBits = 0ull;
+        const double big = DBL_MAX;
+        std::memcpy(&sc.tauMinBits, &big, sizeof(double));
+        sc.maxCo = d->max_co; sc.maxDeltaT = d->max_delta_t; sc.cTau = d->c_tau; sc.adjust = d->adjust_time_step;
+        s->sc.upload(std::vector<StepScalars>(1, sc), g_stream);
+        s->gridFaces = faceKernelGrid();
+        *out = s.release();
+    });
+}
+
+int qgd_qgdfoam_destroy(qgd_solver* s) { return guarded([&] { delete s; }); }
+
+int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const int* bc_p, const double* val_U,
+                        const double* val_T, const double* val_p)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || !bc_U || !bc_T || !bc_p) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_bcs: null argument");
+        const HostMesh& h = s->mesh->h;
+        std::vector<int> u(h.nBnd), t(h.nBnd), p(h.nBnd);
+        s->anyQgdFlux = false;
+        for (int b = 0; b < h.nBnd; ++b) {
+            const int pi = h.bfacePatch[b];
+            u[b] = bc_U[pi]; t[b] = bc_T[pi]; p[b] = bc_p[pi];
+            if (h.patchKind[pi] == QGD_PATCH_EMPTY) continue;
+            if (u[b] != QGD_BC_FIXED_VALUE && u[b] != QGD_BC_ZERO_GRADIENT)
+                throw Error(QGD_ERR_UNSUPPORTED, "U boundary condition outside the device-native set (fixedValue, zeroGradient)");
+            if (t[b] != QGD_BC_FIXED_VALUE && t[b] != QGD_BC_ZERO_GRADIENT)
+                throw Error(QGD_ERR_UNSUPPORTED, "T boundary condition outside the device-native set (fixedValue, zeroGradient)");
+            if (p[b] != QGD_BC_FIXED_VALUE && p[b] != QGD_BC_ZERO_GRADIENT && p[b] != QGD_BC_QGD_FLUX)
+                throw Error(QGD_ERR_UNSUPPORTED, "p boundary condition outside the device-native set (fixedValue, zeroGradient, qgdFlux)");
+            if (p[b] == QGD_BC_QGD_FLUX) s->anyQgdFlux = true;
+            if ((u[b] == QGD_BC_FIXED_VALUE && !val_U) || (t[b] == QGD_BC_FIXED_VALUE && !val_T) || (p[b] == QGD_BC_FIXED_VALUE && !val_p))
+                throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_bcs: fixedValue patch without values");
+        }
+        s->bcU.upload(u, g_stream); s->bcT.upload(t, g_stream); s->bcP.upload(p, g_stream);
+        std::vector<double> zero3(3 * (size_t)h.nBnd, 0.0), zero1(h.nBnd, 0.0);
+        h2d(s->bvU, val_U ? val_U : zero3.data(), 3 * (size_t)h.nBnd);
+        h2d(s->bvT, val_T ? val_T : zero1.data(), (size_t)h.nBnd);
+        h2d(s->bvP, val_p ? val_p : zero1.data(), (size_t)h.nBnd);
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        s->bcsSet = true;
+    });
+}
+
+int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, const double* p, const double* alphaQGD)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || !U || !T || !p) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_init_fields: null argument");
+        if (!s->bcsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_init_fields: call qgd_qgdfoam_set_bcs first");
+        const HostMesh& h = s->mesh->h;
+        const size_t n = h.nCells;
+        if (s->stage.n < QGD_STATE_DOUBLES_PER_CELL * n) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * n);
+        QGD_CUDA(cudaMemcpyAsync(s->stage.p, U, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        QGD_CUDA(cudaMemcpyAsync(s->stage.p + 3 * n, T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        QGD_CUDA(cudaMemcpyAsync(s->stage.p + 4 * n, p, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        if (alphaQGD) QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, alphaQGD, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        else { std::vector<double> a(n, 0.5); QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, a.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream)); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
+        launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), s->stage.p, s->stage.p + 3 * n, s->stage.p + 4 * n);
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        s->fieldsSet = true;
+    });
+}
+
+int qgd_qgdfoam_step(qgd_solver* s, int n_steps)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step: null solver");
+        if (!s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_step: call qgd_qgdfoam_init_fields first");
+        runSteps(s, n_steps);
+    });
+}
+
+int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, const qgd_state_host* out)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_host: null solver");
+        if (!s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_step_host: call qgd_qgdfoam_init_fields first");
+        const size_t n = s->mesh->h.nCells;
+        if (s->stage.n < QGD_STATE_DOUBLES_PER_CELL * n) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * n);
+        double* st = s->stage.p;
+        const int nb = (int)((n + 255) / 256);
+        if (in) {
+            if (!in->rho || !in->U || !in->e || !in->p || !in->T || !in->rhoU || !in->rhoE || !in->mu)
+                throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_host: incomplete input state");
+            const double* src[8] = {in->rho, in->U, in->e, in->p, in->T, in->rhoU, in->rhoE, in->mu};
+            const size_t off[8] = {0, 1, 4, 5, 6, 7, 10, 11}, len[8] = {1, 3, 1, 1, 1, 3, 1, 1};
+            for (int i = 0; i < 8; ++i)
+                QGD_CUDA(cudaMemcpyAsync(st + off[i] * n, src[i], len[i] * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+            k_pack_state<<<nb, 256, 0, g_stream>>>(s->k, (int)n, s->A.p, s->B.p, s->aQGD.p, st);
+            s->launches++;
+        }
+        runSteps(s, n_steps);
+        if (out) {
+            k_unpack_state<<<nb, 256, 0, g_stream>>>((int)n, s->A.p, s->B.p, st);
+            s->launches++;
+            double* dst[8] = {out->rho, out->U, out->e, out->p, out->T, out->rhoU, out->rhoE, out->mu};
+            const size_t off[8] = {0, 1, 4, 5, 6, 7, 10, 11}, len[8] = {1, 3, 1, 1, 1, 3, 1, 1};
+            for (int i = 0; i < 8; ++i)
+                if (dst[i]) QGD_CUDA(cudaMemcpyAsync(dst[i], st + off[i] * n, len[i] * n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+        }
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+    });
+}
+
+int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: null solver");
+        if (!s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_get: no fields yet");
+        const HostMesh& h = s->mesh->h;
+        auto fetch = [&](const RecA* dA, const RecB* dB, size_t n, double* outp) {
+            if (!outp || !n) return;
+            std::vector<RecA> a(n);
+            std::vector<RecB> b(n);
+            QGD_CUDA(cudaMemcpyAsync(a.data(), dA, n * sizeof(RecA), cudaMemcpyDeviceToHost, g_stream));
+            QGD_CUDA(cudaMemcpyAsync(b.data(), dB, n * sizeof(RecB), cudaMemcpyDeviceToHost, g_stream));
+            QGD_CUDA(cudaStreamSynchronize(g_stream));
+            const double gam = s->k.gamma;
+            for (size_t i = 0; i < n; ++i) {
+                switch (field) {
+                    case 0: outp[i] = a[i].rho; break;
+                    case 1: outp[3 * i] = b[i].rhoUx; outp[3 * i + 1] = b[i].rhoUy; outp[3 * i + 2] = b[i].rhoUz; break;
+                    case 2: outp[i] = b[i].rhoE; break;
+                    case 3: outp[3 * i] = a[i].Ux; outp[3 * i + 1] = a[i].Uy; outp[3 * i + 2] = a[i].Uz; break;
+                    case 4: outp[i] = a[i].e; break;
+                    case 5: outp[i] = a[i].p; break;
+                    case 6: outp[i] = a[i].T; break;
+                    case 7: outp[i] = b[i].c; break;
+                    case 8: outp[i] = b[i].mu; break;
+                    case 9: outp[i] = s->k.alphaEffGamma ? b[i].alphaEff / gam : b[i].alphaEff; break;
+                    case 10: outp[i] = b[i].aByC; break;   // scaled below for cells
+                    case 11: outp[i] = a[i].H; break;
+                    default: throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: unknown field id");
+                }
+            }
+        };
+        fetch(s->A.p, s->B.p, h.nCells, cells);
+        if (field == 10 && cells) for (int c = 0; c < h.nCells; ++c) cells[c] *= h.hQGD[c];
+        fetch(s->bA.p, s->bB.p, h.nBnd, bnd);
+        if (field == 10 && bnd) for (int b = 0; b < h.nBnd; ++b) bnd[b] *= h.hQGDf[h.nInternal + b];
+    });
+}
+
+int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || !out) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: null argument");
+        const size_t nF = s->mesh->h.nFaces;
+        if (which == 0) d2h(out, s->Fm.p, nF);
+        else if (which == 2) d2h(out, s->FE.p, nF);
+        else if (which == 1) {
+            std::vector<double> t(3 * nF);
+            d2h(t.data(), s->FU.p, 3 * nF);
+            QGD_CUDA(cudaStreamSynchronize(g_stream));
+            for (size_t f = 0; f < nF; ++f) for (int d = 0; d < 3; ++d) out[3 * f + d] = t[d * nF + f];
+        } else throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: unknown flux id");
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+    });
+}
+
+int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, double* time)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_scalars: null solver");
+        StepScalars sc;
+        QGD_CUDA(cudaMemcpyAsync(&sc, s->sc.p, sizeof(sc), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        if (delta_t) *delta_t = sc.dt;
+        if (courant) *courant = sc.coNum;
+        if (time) *time = sc.time;
+    });
+}
+
+long long qgd_qgdfoam_launch_count(qgd_solver* s) { return s ? s->launches : 0; }
+
+int qgd_pcg_solve(qgd_mesh*, const double*, const double*, const double*, double*, double, double, int, int, int*, double*, double*)
+{
+    setLastError("qgd_pcg_solve: device PCG not built in this revision");
+    return QGD_ERR_UNSUPPORTED;
+}
+
+} // extern "C"

@@ -1,0 +1,102 @@
+// Internal declarations shared by the host set-up code, the kernels and the C-ABI layer.
+// Device data model (DESIGN.md "Data layout in HBM"):
+//   * gathered data   -> 64-byte AoS records (one or two 32-byte sectors per gather, 128-bit loads)
+//   * streamed data   -> SoA arrays (perfectly coalesced)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/qgd_b200.h"
+
+namespace qgd {
+
+// ---------------------------------------------------------------- errors
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void setLastError(const std::string& m);
+#define QGD_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            throw qgd::Error(QGD_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " \
+                                               + __FILE__ + ":" + std::to_string(__LINE__));             \
+    } while (0)
+
+// ---------------------------------------------------------------- device buffers
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) QGD_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void upload(const std::vector<T>& h, cudaStream_t st = 0) {
+        alloc(h.size());
+        if (n) QGD_CUDA(cudaMemcpyAsync(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, st));
+        QGD_CUDA(cudaStreamSynchronize(st));
+    }
+    void zero(cudaStream_t st = 0) { if (n) QGD_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+};
+
+// ---------------------------------------------------------------- records
+// cell / boundary-face state, gathered by the face kernels.  64 B each, 64-B aligned.
+struct __align__(16) RecA { double rho, Ux, Uy, Uz, e, p, T, H; };
+struct __align__(16) RecB { double rhoUx, rhoUy, rhoUz, rhoE, c, mu, alphaEff, aByC; };
+// point values produced by the point gather (rho,U,e,p), 48 B
+struct __align__(16) RecP { double rho, Ux, Uy, Uz, e, p; };
+
+// face gradient record: grad(phi) = G1 (phi[v1]-phi[v3]) + G2 (phi[v2]-phi[v4]) + GP (phiP - phiN)
+// which covers GaussVolPoint 3D quad (GaussVolPointBase3D.C:320-390), tri (:161-230), "other" faces
+// (:760-768, G1=G2=0, GP=-nf*delta), 2D (GaussVolPointBase2D.C:122-169), 1D and `reduced`.
+enum FaceFlags : int {
+    FF_POINTS = 1,     // uses vertex values (G1/G2 non-zero)
+    FF_TRI_QUIRK = 2,  // internal triangular face: vector-gradient index pattern of GaussVolPointBase3D.C:844-854
+    FF_NORMAL_ONLY = 4 // boundary face evaluated as nf*snGrad (1D, reduced, other faces)
+};
+
+// ---------------------------------------------------------------- host-side derived mesh data
+struct HostMesh {
+    int nCells = 0, nFaces = 0, nInternal = 0, nPoints = 0, nPatches = 0, nBnd = 0;
+    int nD = 3;
+    int gD[3] = {1, 1, 1};
+    std::vector<double> points, C, V, Cf, Sf, magSf, w, dC, ndC, nbrCC;
+    std::vector<int> faceOff, faceVerts, owner, neighbour, patchStart, patchSize, patchKind;
+    std::vector<int> bfacePatch;
+    // derived
+    std::vector<int> cfOff, cfEnc;                 // cell -> faces, enc = (face<<1)|isNeighbourSide
+    std::vector<int> pcOff, pcCell;                // non-patch point -> cells
+    std::vector<double> pcW;
+    std::vector<int> patchPoints;                  // list of patch points
+    std::vector<int> ppOff, ppFace;                // patch point (by list position) -> boundary faces
+    std::vector<double> ppW;
+    std::vector<double> hQGDf, hQGD;
+    void build(const qgd_mesh_desc& d);
+    // face gradient records for a scheme ("GaussVolPoint" / "reduced")
+    void buildFaceRecords(bool reduced, std::vector<int>& vtx /*nFaces*4*/, std::vector<int>& flags /*nFaces*/,
+                          std::vector<double>& G /*9 arrays of nFaces, SoA: G[k*nFaces+f]*/,
+                          std::vector<double>& halfDist /*nBnd*/) const;
+};
+
+} // namespace qgd
+
+// ---------------------------------------------------------------- opaque handles
+struct qgd_mesh {
+    qgd::HostMesh h;
+    // device copies
+    qgd::DevBuf<int> owner, neighbour, cfOff, cfEnc, pcOff, pcCell, patchPoints, ppOff, ppFace, bfaceKind;
+    qgd::DevBuf<double> pcW, ppW;
+    qgd::DevBuf<double> Sf;        // SoA 3*nFaces
+    qgd::DevBuf<double> magSf, w, dC, ndC, V, hQGDf, hQGD;
+};

@@ -1,0 +1,832 @@
+// Hand-written FP64 CUDA for sm_100a: fvsc face-centre derivative operators and the fused QGDFoam step.
+//
+// Step structure (DESIGN.md "Kernels"):
+//   k_points          cell -> point inverse-distance gather of (rho,U,e,p)        [volPointInterpolation, OF]
+//   k_patch_points    boundary points from boundary-face values
+//   k_bnd_pre         phiwStar on boundary faces, qgdFlux re-evaluation of p_b     (QGDFoam/updateFluxes.H:54-65)
+//   k_face_flux       fused: 11 interpolations + 4 face gradients + QGD flux algebra (updateFields.H:45-80,
+//                     updateFluxes.H:41-139, QGDCourantNo.H:38-50) -> 5 flux scalars per face
+//   k_bnd_flux        same on boundary faces (ghost values, GaussVolPointBase3D.C:771-819)
+//   k_dt              setDeltaT-QGDQHD.H:41-61 on the device (no host sync)
+//   k_cell_update     atomic-free face->cell reduction over the signed cell-face CSR + Euler update
+//                     (QGDRhoEqn/UEqn/EEqn.H) + hePsiQGDThermo::calculate + constScPrModel1::correct
+//   k_bnd_post        boundary state after the update (correctBoundaryConditions sequence of QGDFoam.C:133-156)
+#include <cfloat>
+#include <cstdio>
+
+#include "qgd_kernels.cuh"
+
+namespace qgd {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+__device__ __forceinline__ RecA loadA(const RecA* base, int i)
+{
+    const double* p = reinterpret_cast<const double*>(base + i);
+    const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4), d = ldg2(p + 6);
+    return RecA{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+}
+__device__ __forceinline__ RecB loadB(const RecB* base, int i)
+{
+    const double* p = reinterpret_cast<const double*>(base + i);
+    const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4), d = ldg2(p + 6);
+    return RecB{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+}
+__device__ __forceinline__ RecP loadP(const RecP* base, int i)
+{
+    const double* p = reinterpret_cast<const double*>(base + i);
+    const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4);
+    return RecP{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+__device__ __forceinline__ void storeRec(double* p, const double (&v)[8])
+{
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(v[0], v[1]); q[1] = make_double2(v[2], v[3]);
+    q[2] = make_double2(v[4], v[5]); q[3] = make_double2(v[6], v[7]);
+}
+
+// ---- thermo: perfectGas + hConst + sensibleInternalEnergy  [OF-v2312; SURVEY 8c item 9]
+__device__ __forceinline__ double thermoEs(const Consts& k, double T) { return k.Cp * (T - k.Tref) + k.Hsref - k.R * T; }
+__device__ __forceinline__ double thermoTHE(const Consts& k, double e, double T0)
+{
+    double Test = T0, Tnew = T0;
+    const double Ttol = T0 * 1e-4;
+    int iter = 0;
+    do {
+        Test = Tnew;
+        Tnew = Test - (thermoEs(k, Test) - e) / k.Cv;
+        if (iter++ > 100) break;
+    } while (fabs(Tnew - Test) > Ttol);
+    return Tnew;
+}
+
+// ============================================================================ generic fvsc operator kernels
+template <int K>
+__global__ void k_point_gather_generic(int nPoints, const int* __restrict__ pcOff, const int* __restrict__ pcCell,
+                                       const double* __restrict__ pcW, const double* __restrict__ cell, double* __restrict__ pts)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nPoints) return;
+    const int b = pcOff[p], e = pcOff[p + 1];
+    if (b == e) return;                       // patch point: written by k_patch_point_gather_generic
+    double acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.0;
+    for (int q = b; q < e; ++q) {
+        const int c = pcCell[q];
+        const double wq = pcW[q];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] += wq * __ldg(&cell[(size_t)c * K + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) pts[(size_t)p * K + j] = acc[j];
+}
+
+template <int K>
+__global__ void k_patch_point_gather_generic(int nPP, const int* __restrict__ patchPoints, const int* __restrict__ ppOff,
+                                             const int* __restrict__ ppFace, const double* __restrict__ ppW,
+                                             const double* __restrict__ bnd, double* __restrict__ pts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nPP) return;
+    double acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = 0.0;
+    for (int q = ppOff[i]; q < ppOff[i + 1]; ++q) {
+        const int b = ppFace[q];
+        const double wq = ppW[q];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] += wq * bnd[(size_t)b * K + j];
+    }
+    const int p = patchPoints[i];
+#pragma unroll
+    for (int j = 0; j < K; ++j) pts[(size_t)p * K + j] = acc[j];
+}
+
+// differences (phi[v1]-phi[v3], phi[v2]-phi[v4], phiP-phiN) of one face for K components
+template <int K>
+__device__ __forceinline__ void faceDiffs(const FaceView& fv, int f, const double* __restrict__ cell, const double* __restrict__ pts,
+                                          const double* __restrict__ bnd, const double* __restrict__ bsg,
+                                          const double* __restrict__ nbr, int flags, double (&d1)[K], double (&d2)[K], double (&dP)[K])
+{
+    const int P = fv.own[f];
+    if (flags & FF_POINTS) {
+        const int4 v = fv.vtx[f];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            d1[j] = pts[(size_t)v.x * K + j] - pts[(size_t)v.z * K + j];
+            d2[j] = pts[(size_t)v.y * K + j] - pts[(size_t)v.w * K + j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { d1[j] = 0.0; d2[j] = 0.0; }
+    }
+    if (f < fv.nI) {
+        const int N = fv.nei[f];
+#pragma unroll
+        for (int j = 0; j < K; ++j) dP[j] = cell[(size_t)P * K + j] - cell[(size_t)N * K + j];
+    } else {
+        const int b = f - fv.nI;
+        const bool proc = fv.bKind[b] == QGD_PATCH_PROCESSOR;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double psiN = (proc && nbr) ? nbr[(size_t)b * K + j] : bnd[(size_t)b * K + j] + bsg[(size_t)b * K + j] * fv.halfDist[b];
+            dP[j] = cell[(size_t)P * K + j] - psiN;
+        }
+    }
+}
+
+// grad: out[f][3*i... ] tensor index K*i + j = d_i phi_j
+template <int K>
+__global__ void k_fvsc_grad(FaceView fv, const double* __restrict__ cell, const double* __restrict__ pts,
+                            const double* __restrict__ bnd, const double* __restrict__ bsg, const double* __restrict__ nbr,
+                            double* __restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= fv.nF) return;
+    double* o = out + (size_t)f * 3 * K;
+    const int flags = fv.flags[f];
+    double g1[3], g2[3], gp[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g1[i] = fv.G[(size_t)(0 + i) * fv.nF + f];
+        g2[i] = fv.G[(size_t)(3 + i) * fv.nF + f];
+        gp[i] = fv.G[(size_t)(6 + i) * fv.nF + f];
+    }
+    if (f >= fv.nI) {
+        const int b = f - fv.nI;
+        if (fv.bKind[b] == QGD_PATCH_EMPTY) {
+#pragma unroll
+            for (int q = 0; q < 3 * K; ++q) o[q] = 0.0;
+            return;
+        }
+        if (flags & FF_NORMAL_ONLY) {          // nf * snGrad  (GaussVolPointBase1D.C:49-63, GaussVolPointBase3D.C:808-817)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < K; ++j) o[K * i + j] = gp[i] * bsg[(size_t)b * K + j];
+            return;
+        }
+    }
+    double d1[K], d2[K], dP[K];
+    faceDiffs<K>(fv, f, cell, pts, bnd, bsg, nbr, flags, d1, d2, dP);
+    if (K == 3 && (flags & FF_TRI_QUIRK)) {     // GaussVolPointBase3D.C:844-854
+#pragma unroll
+        for (int row = 0; row < 3; ++row)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) o[3 * row + d] = g1[d] * d1[d] + g2[d] * d2[d] + gp[d] * dP[d];
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < K; ++j) o[K * i + j] = g1[i] * d1[j] + g2[i] * d2[j] + gp[i] * dP[j];
+}
+
+// div: K=3 -> scalar (sum_i d_i phi_i), K=9 -> vector_j = sum_i d_i T_ij
+template <int K>
+__global__ void k_fvsc_div(FaceView fv, const double* __restrict__ cell, const double* __restrict__ pts,
+                           const double* __restrict__ bnd, const double* __restrict__ bsg, const double* __restrict__ nbr,
+                           double* __restrict__ out)
+{
+    constexpr int OK = K / 3;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= fv.nF) return;
+    double* o = out + (size_t)f * OK;
+    const int flags = fv.flags[f];
+    double g1[3], g2[3], gp[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g1[i] = fv.G[(size_t)(0 + i) * fv.nF + f];
+        g2[i] = fv.G[(size_t)(3 + i) * fv.nF + f];
+        gp[i] = fv.G[(size_t)(6 + i) * fv.nF + f];
+    }
+    if (f >= fv.nI) {
+        const int b = f - fv.nI;
+        if (fv.bKind[b] == QGD_PATCH_EMPTY) {
+#pragma unroll
+            for (int q = 0; q < OK; ++q) o[q] = 0.0;
+            return;
+        }
+        if (flags & FF_NORMAL_ONLY) {          // nf & snGrad
+#pragma unroll
+            for (int j = 0; j < OK; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) s += gp[i] * bsg[(size_t)b * K + OK * i + j];
+                o[j] = s;
+            }
+            return;
+        }
+    }
+    double d1[K], d2[K], dP[K];
+    faceDiffs<K>(fv, f, cell, pts, bnd, bsg, nbr, flags, d1, d2, dP);
+#pragma unroll
+    for (int j = 0; j < OK; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s += g1[i] * d1[OK * i + j] + g2[i] * d2[OK * i + j] + gp[i] * dP[OK * i + j];
+        o[j] = (K == 9 && j == fv.zeroDivCmpt) ? 0.0 : s;
+    }
+}
+
+// ============================================================================ QGDFoam step kernels
+struct FaceState {            // interpolated face quantities (QGDFoam/updateFields.H:45-80)
+    double rho, U[3], rhoU[3], UrhoU[9], p, c, H, alpha, mu, tau;
+};
+struct FaceGrads { double U[9], e[3], rho[3], p[3]; };
+
+// QGDFoam/updateFluxes.H:54-63 : rhoW* and phiwStar
+__device__ __forceinline__ void qgdRhoWStar(const FaceState& s, const FaceGrads& g, double divU, double (&rhoW)[3])
+{
+    const double gRU = g.rho[0] * s.U[0] + g.rho[1] * s.U[1] + g.rho[2] * s.U[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double rUG = s.rhoU[0] * g.U[j] + s.rhoU[1] * g.U[3 + j] + s.rhoU[2] * g.U[6 + j];
+        rhoW[j] = s.tau * (s.U[j] * gRU + s.rhoU[j] * divU + rUG);
+    }
+}
+
+// QGDFoam/updateFluxes.H:67-139 (explicit branch): mass, momentum, energy face fluxes
+__device__ __forceinline__ void qgdFluxes(const Consts& k, const FaceState& s, const FaceGrads& g, const double (&Sf)[3],
+                                          double& Fm, double (&FU)[3], double& FE, double& phiw)
+{
+    const double divU = g.U[0] + g.U[4] + g.U[8];
+    double rhoW[3];
+    qgdRhoWStar(s, g, divU, rhoW);
+    phiw = Sf[0] * rhoW[0] + Sf[1] * rhoW[1] + Sf[2] * rhoW[2];
+    double jm[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { rhoW[j] += s.tau * g.p[j]; jm[j] = s.rhoU[j] - rhoW[j]; }
+    const double phiJm = Sf[0] * jm[0] + Sf[1] * jm[1] + Sf[2] * jm[2];
+    Fm = phiJm;
+    const double UgP = s.U[0] * g.p[0] + s.U[1] * g.p[1] + s.U[2] * g.p[2];
+    const double iso = UgP + (k.gamma * s.p * divU);
+    double Pi[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double UrUG = s.UrhoU[3 * i] * g.U[j] + s.UrhoU[3 * i + 1] * g.U[3 + j] + s.UrhoU[3 * i + 2] * g.U[6 + j];
+            double v = s.tau * (UrUG + s.U[i] * g.p[j]) + s.tau * ((i == j) ? iso : 0.0);
+            v += s.mu * (g.U[3 * i + j] + g.U[3 * j + i] - ((i == j) ? (2.0 / 3.0) * divU : 0.0));
+            Pi[3 * i + j] = v;
+        }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double phiPi = Sf[0] * Pi[j] + Sf[1] * Pi[3 + j] + Sf[2] * Pi[6 + j];
+        FU[j] = phiJm * s.U[j] + Sf[j] * s.p - phiPi;
+    }
+    const double pr2 = s.p / s.rho / s.rho;
+    double v[3], q[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[j] = g.e[j] - pr2 * g.rho[j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        q[i] = -s.tau * (s.UrhoU[3 * i] * v[0] + s.UrhoU[3 * i + 1] * v[1] + s.UrhoU[3 * i + 2] * v[2]);
+        q[i] -= s.alpha * g.e[i];
+    }
+    const double phiQ = Sf[0] * q[0] + Sf[1] * q[1] + Sf[2] * q[2];
+    double PiU[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) PiU[i] = Pi[3 * i] * s.U[0] + Pi[3 * i + 1] * s.U[1] + Pi[3 * i + 2] * s.U[2];
+    const double phiPiU = Sf[0] * PiU[0] + Sf[1] * PiU[1] + Sf[2] * PiU[2];
+    FE = phiJm * s.H + phiQ - phiPiU;
+}
+
+__device__ __forceinline__ void gradsFromDiffs(const double (&g1)[3], const double (&g2)[3], const double (&gp)[3], int flags,
+                                               const RecP& d1, const RecP& d2, const RecP& dP, FaceGrads& g)
+{
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g.rho[i] = g1[i] * d1.rho + g2[i] * d2.rho + gp[i] * dP.rho;
+        g.e[i] = g1[i] * d1.e + g2[i] * d2.e + gp[i] * dP.e;
+        g.p[i] = g1[i] * d1.p + g2[i] * d2.p + gp[i] * dP.p;
+        g.U[3 * i + 0] = g1[i] * d1.Ux + g2[i] * d2.Ux + gp[i] * dP.Ux;
+        g.U[3 * i + 1] = g1[i] * d1.Uy + g2[i] * d2.Uy + gp[i] * dP.Uy;
+        g.U[3 * i + 2] = g1[i] * d1.Uz + g2[i] * d2.Uz + gp[i] * dP.Uz;
+    }
+    if (flags & FF_TRI_QUIRK) {                 // GaussVolPointBase3D.C:844-854
+        const double dxx = g.U[0], dyy = g.U[4], dzz = g.U[8];
+#pragma unroll
+        for (int row = 0; row < 3; ++row) { g.U[3 * row] = dxx; g.U[3 * row + 1] = dyy; g.U[3 * row + 2] = dzz; }
+    }
+}
+
+__device__ __forceinline__ RecP recDiff(const RecP& a, const RecP& b)
+{
+    return RecP{a.rho - b.rho, a.Ux - b.Ux, a.Uy - b.Uy, a.Uz - b.Uz, a.e - b.e, a.p - b.p};
+}
+
+__device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+// block-wide max / min of non-negative doubles, one atomic per block
+__device__ __forceinline__ void blockReduceCo(double coMax, double tauMin, StepScalars* sc)
+{
+    __shared__ double sMax[kBlock / 32];
+    __shared__ double sMin[kBlock / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        coMax = fmax(coMax, __shfl_xor_sync(0xffffffffu, coMax, o));
+        tauMin = fmin(tauMin, __shfl_xor_sync(0xffffffffu, tauMin, o));
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sMax[wid] = coMax; sMin[wid] = tauMin; }
+    __syncthreads();
+    if (wid == 0) {
+        coMax = (lane < kBlock / 32) ? sMax[lane] : 0.0;
+        tauMin = (lane < kBlock / 32) ? sMin[lane] : DBL_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            coMax = fmax(coMax, __shfl_xor_sync(0xffffffffu, coMax, o));
+            tauMin = fmin(tauMin, __shfl_xor_sync(0xffffffffu, tauMin, o));
+        }
+        if (lane == 0) {
+            atomicMax(&sc->coMaxBits, dbits(coMax));
+            atomicMin(&sc->tauMinBits, dbits(tauMin));
+        }
+    }
+}
+
+// ---- cell -> point gather of (rho,U,e,p)
+__global__ void __launch_bounds__(kBlock) k_points(SolverView sv)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= sv.nPoints) return;
+    const int b = sv.pcOff[p], e = sv.pcOff[p + 1];
+    if (b == e) return;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+    for (int q = b; q < e; ++q) {
+        const int c = __ldg(&sv.pcCell[q]);
+        const double wq = __ldg(&sv.pcW[q]);
+        const double* r = reinterpret_cast<const double*>(sv.A + c);
+        const double2 x = ldg2(r), y = ldg2(r + 2), z = ldg2(r + 4);
+        a0 += wq * x.x; a1 += wq * x.y; a2 += wq * y.x; a3 += wq * y.y; a4 += wq * z.x; a5 += wq * z.y;
+    }
+    double2* o = reinterpret_cast<double2*>(sv.P + p);
+    o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
+}
+
+// boundary points from boundary-face values; onlyP: refresh p only (after the qgdFlux re-evaluation)
+__global__ void k_patch_points(SolverView sv, BndState bs, int onlyP)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.nPatchPoints) return;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+    for (int q = sv.ppOff[i]; q < sv.ppOff[i + 1]; ++q) {
+        const int b = sv.ppFace[q];
+        const double wq = sv.ppW[q];
+        const RecA r = bs.A[b];
+        a0 += wq * r.rho; a1 += wq * r.Ux; a2 += wq * r.Uy; a3 += wq * r.Uz; a4 += wq * r.e; a5 += wq * bs.pNew[b];
+    }
+    RecP* o = sv.P + sv.patchPoints[i];
+    if (onlyP) { o->p = a5; return; }
+    *o = RecP{a0, a1, a2, a3, a4, a5};
+}
+
+// boundary-face inputs shared by k_bnd_pre and k_bnd_flux
+struct BndFace { FaceState s; FaceGrads g; double Sf[3]; };
+
+__device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv, const SolverView& sv, const BndState& bs,
+                                             int b, bool usePNew, BndFace& o)
+{
+    const int f = fv.nI + b;
+    const int P = fv.own[f];
+    const RecA a = bs.A[b];
+    const RecB bb = bs.B[b];
+    const RecA cA = loadA(sv.A, P);
+    const int flags = fv.flags[f];
+    const double delta = fv.dC[f];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o.Sf[i] = fv.Sf[(size_t)i * fv.nF + f];
+    // face values = boundary values
+    o.s.rho = a.rho; o.s.U[0] = a.Ux; o.s.U[1] = a.Uy; o.s.U[2] = a.Uz;
+    o.s.rhoU[0] = bb.rhoUx; o.s.rhoU[1] = bb.rhoUy; o.s.rhoU[2] = bb.rhoUz;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o.s.UrhoU[3 * i + j] = o.s.U[i] * o.s.rhoU[j];
+    o.s.p = a.p; o.s.c = bb.c; o.s.H = a.H; o.s.alpha = bb.alphaEff; o.s.mu = bb.mu;
+    o.s.tau = bb.aByC * fv.hf[f];
+    // patch snGrad per field [OF fvPatchField::snGrad / zeroGradient / fixedGradient]
+    const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
+    const double pB = usePNew ? bs.pNew[b] : a.p;
+    RecP sn;
+    sn.rho = delta * (a.rho - cA.rho);
+    sn.Ux = fixU ? delta * (a.Ux - cA.Ux) : 0.0;
+    sn.Uy = fixU ? delta * (a.Uy - cA.Uy) : 0.0;
+    sn.Uz = fixU ? delta * (a.Uz - cA.Uz) : 0.0;
+    sn.e = fixT ? delta * (a.e - cA.e) : 0.0;
+    const int bcP = bs.bcP[b];
+    sn.p = (bcP == QGD_BC_FIXED_VALUE) ? delta * (pB - cA.p) : ((bcP == QGD_BC_ZERO_GRADIENT) ? 0.0 : bs.pGrad[b]);
+    double g1[3], g2[3], gp[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g1[i] = fv.G[(size_t)(0 + i) * fv.nF + f];
+        g2[i] = fv.G[(size_t)(3 + i) * fv.nF + f];
+        gp[i] = fv.G[(size_t)(6 + i) * fv.nF + f];
+    }
+    if (flags & FF_NORMAL_ONLY) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            o.g.rho[i] = gp[i] * sn.rho; o.g.e[i] = gp[i] * sn.e; o.g.p[i] = gp[i] * sn.p;
+            o.g.U[3 * i] = gp[i] * sn.Ux; o.g.U[3 * i + 1] = gp[i] * sn.Uy; o.g.U[3 * i + 2] = gp[i] * sn.Uz;
+        }
+        return;
+    }
+    const double hd = fv.halfDist[b];
+    RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
+    if (flags & FF_POINTS) {
+        const int4 v = fv.vtx[f];
+        d1 = recDiff(loadP(sv.P, v.x), loadP(sv.P, v.z));
+        d2 = recDiff(loadP(sv.P, v.y), loadP(sv.P, v.w));
+    }
+    // phiP - psiN, psiN = phi_b + snGrad_b*|d|/2   (GaussVolPointBase3D.C:790-793)
+    RecP dP;
+    dP.rho = cA.rho - (a.rho + sn.rho * hd);
+    dP.Ux = cA.Ux - (a.Ux + sn.Ux * hd);
+    dP.Uy = cA.Uy - (a.Uy + sn.Uy * hd);
+    dP.Uz = cA.Uz - (a.Uz + sn.Uz * hd);
+    dP.e = cA.e - (a.e + sn.e * hd);
+    dP.p = cA.p - (pB + sn.p * hd);
+    gradsFromDiffs(g1, g2, gp, flags, d1, d2, dP, o.g);
+}
+
+// phiwStar on boundary faces, then qgdFlux::updateCoeffs + fixedGradient::evaluate for p
+__global__ void k_bnd_pre(Consts k, FaceView fv, SolverView sv, BndState bs)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= fv.nB) return;
+    const int f = fv.nI + b;
+    if (fv.bKind[b] == QGD_PATCH_EMPTY) return;
+    BndFace bf;
+    bndFaceSetup(k, fv, sv, bs, b, false, bf);
+    const double divU = bf.g.U[0] + bf.g.U[4] + bf.g.U[8];
+    double rhoW[3];
+    qgdRhoWStar(bf.s, bf.g, divU, rhoW);
+    const double phiw = bf.Sf[0] * rhoW[0] + bf.Sf[1] * rhoW[1] + bf.Sf[2] * rhoW[2];
+    bs.phiw[b] = phiw;
+    double pNew = bs.A[b].p;
+    if (bs.bcP[b] == QGD_BC_QGD_FLUX && !k.reducedScheme) {
+        const double grad = -(phiw / bf.s.tau / fv.magSf[f]);     // qgdFluxFvPatchScalarField.C:184-192
+        bs.pGrad[b] = grad;
+        pNew = loadA(sv.A, fv.own[f]).p + grad / fv.dC[f];
+    }
+    bs.pNew[b] = pNew;
+}
+
+__global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    double coMax = 0.0, tauMin = DBL_MAX;
+    if (b < fv.nB) {
+        const int f = fv.nI + b;
+        if (fv.bKind[b] == QGD_PATCH_EMPTY) {
+            sv.Fm[f] = 0.0; sv.FE[f] = 0.0;
+            sv.FU[f] = 0.0; sv.FU[(size_t)fv.nF + f] = 0.0; sv.FU[2 * (size_t)fv.nF + f] = 0.0;
+        } else {
+            BndFace bf;
+            bndFaceSetup(k, fv, sv, bs, b, true, bf);
+            double Fm, FU[3], FE, phiw;
+            qgdFluxes(k, bf.s, bf.g, bf.Sf, Fm, FU, FE, phiw);
+            sv.Fm[f] = Fm; sv.FE[f] = FE;
+            sv.FU[f] = FU[0]; sv.FU[(size_t)fv.nF + f] = FU[1]; sv.FU[2 * (size_t)fv.nF + f] = FU[2];
+            const double ms = fv.magSf[f];
+            const double Unf = bf.s.U[0] * (bf.Sf[0] / ms) + bf.s.U[1] * (bf.Sf[1] / ms) + bf.s.U[2] * (bf.Sf[2] / ms);
+            coMax = fmax(fabs(Unf + bf.s.c), fabs(Unf - bf.s.c)) / fv.hf[f];
+            tauMin = bf.s.tau;
+        }
+    }
+    blockReduceCo(coMax, tauMin, sv.sc);
+}
+
+// ---- the fused internal-face kernel
+template <bool ADJUST>
+__global__ void __launch_bounds__(kBlock) k_face_flux(Consts k, FaceView fv, SolverView sv)
+{
+    double coMax = 0.0, tauMin = DBL_MAX;
+    const size_t nF = fv.nF;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < fv.nI; f += gridDim.x * blockDim.x) {
+        const int P = __ldg(&fv.own[f]), N = __ldg(&fv.nei[f]);
+        const int flags = __ldg(&fv.flags[f]);
+        const RecA aP = loadA(sv.A, P), aN = loadA(sv.A, N);
+        const RecB bP = loadB(sv.B, P), bN = loadB(sv.B, N);
+        RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
+        if (flags & FF_POINTS) {
+            const int4 v = __ldg(&fv.vtx[f]);
+            d1 = recDiff(loadP(sv.P, v.x), loadP(sv.P, v.z));
+            d2 = recDiff(loadP(sv.P, v.y), loadP(sv.P, v.w));
+        }
+        const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
+        double g1[3], g2[3], gp[3], Sf[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
+            g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
+            gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
+            Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
+        }
+        FaceGrads g;
+        gradsFromDiffs(g1, g2, gp, flags, d1, d2, dP, g);
+        // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
+        const double w = __ldg(&fv.w[f]);
+        FaceState s;
+        s.rho = w * (aP.rho - aN.rho) + aN.rho;
+        s.U[0] = w * (aP.Ux - aN.Ux) + aN.Ux; s.U[1] = w * (aP.Uy - aN.Uy) + aN.Uy; s.U[2] = w * (aP.Uz - aN.Uz) + aN.Uz;
+        s.rhoU[0] = w * (bP.rhoUx - bN.rhoUx) + bN.rhoUx; s.rhoU[1] = w * (bP.rhoUy - bN.rhoUy) + bN.rhoUy;
+        s.rhoU[2] = w * (bP.rhoUz - bN.rhoUz) + bN.rhoUz;
+        {
+            const double uP[3] = {aP.Ux, aP.Uy, aP.Uz}, uN[3] = {aN.Ux, aN.Uy, aN.Uz};
+            const double rP[3] = {bP.rhoUx, bP.rhoUy, bP.rhoUz}, rN[3] = {bN.rhoUx, bN.rhoUy, bN.rhoUz};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const double tP = uP[i] * rP[j], tN = uN[i] * rN[j];
+                    s.UrhoU[3 * i + j] = w * (tP - tN) + tN;
+                }
+        }
+        s.p = w * (aP.p - aN.p) + aN.p;
+        s.c = w * (bP.c - bN.c) + bN.c;
+        s.H = w * (aP.H - aN.H) + aN.H;
+        s.alpha = w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
+        s.mu = w * (bP.mu - bN.mu) + bN.mu;
+        const double hf = __ldg(&fv.hf[f]);
+        s.tau = (w * (bP.aByC - bN.aByC) + bN.aByC) * hf;       // constScPrModel1.C:103
+        double Fm, FU[3], FE, phiw;
+        qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
+        sv.Fm[f] = Fm; sv.FE[f] = FE;
+        sv.FU[f] = FU[0]; sv.FU[nF + f] = FU[1]; sv.FU[2 * nF + f] = FU[2];
+        if (ADJUST) {                                           // QGDCourantNo.H:38-50
+            const double ms = __ldg(&fv.magSf[f]);
+            const double Unf = s.U[0] * (Sf[0] / ms) + s.U[1] * (Sf[1] / ms) + s.U[2] * (Sf[2] / ms);
+            coMax = fmax(coMax, fmax(fabs(Unf + s.c), fabs(Unf - s.c)) / hf);
+            tauMin = fmin(tauMin, s.tau);
+        }
+    }
+    if (ADJUST) blockReduceCo(coMax, tauMin, sv.sc);
+}
+
+// setDeltaT-QGDQHD.H:41-61 ; QGDCourantNo.H:47-50
+__global__ void k_dt(StepScalars* sc)
+{
+    if (sc->adjust) {
+        const double coNum = __longlong_as_double((long long)sc->coMaxBits) * sc->dt;
+        const double tauMin = __longlong_as_double((long long)sc->tauMinBits);
+        sc->coNum = coNum;
+        const double maxDeltaTFact = sc->maxCo / (coNum + 1e-15);
+        const double deltaTFact = fmin(fmin(maxDeltaTFact, 1.0 + 0.1 * maxDeltaTFact), 1.2);
+        double maxDeltaT1 = sc->cTau * tauMin;
+        maxDeltaT1 = fmin(sc->maxDeltaT, maxDeltaT1);
+        sc->dt = fmin(deltaTFact * sc->dt, maxDeltaT1);
+    }
+    sc->time += sc->dt;
+    sc->coMaxBits = 0ull;
+    sc->tauMinBits = dbits(DBL_MAX);
+}
+
+// per-cell closing of the step: new thermo state from (rho, U, rhoU, rhoE, e) and the OLD p, T
+__device__ __forceinline__ void cellThermo(const Consts& k, double rho, const double (&U)[3], const double (&rhoU)[3], double rhoE,
+                                           double e, double pOld, double TOld, double aQGD, double hQGD, double* outA, double* outB)
+{
+    // hePsiQGDThermo::calculate  hePsiQGDThermo.C:48-64,123-124
+    const double T = thermoTHE(k, e, TOld);
+    const double psi = 1.0 / (k.R * T);
+    const double c = sqrt(k.gamma / psi);
+    // constScPrModel1::correct  constScPrModel1.C:104-114  (p is still the old pressure here: QGDFoam.C:149-154)
+    const double tau = aQGD * hQGD / c;
+    const double muQGD = pOld * k.ScQGD * tau;
+    const double alphauQGD = muQGD / k.PrQGD;
+    const double mu = k.mu + muQGD;                      // QGDThermo.C:91-98
+    const double alpha = k.mu / k.Pr + alphauQGD;
+    const double p = rho / psi;                          // QGDFoam.C:152-154
+    const double H = (rhoE + p) / rho;                   // updateFields.H:71 (of the next step)
+    const double a[8] = {rho, U[0], U[1], U[2], e, p, T, H};
+    const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD / c};
+    storeRec(outA, a);
+    storeRec(outB, b);
+}
+
+__global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nF)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nCells) return;
+    const RecA a = loadA(sv.A, c);
+    const RecB b = loadB(sv.B, c);
+    double sm = 0.0, su0 = 0.0, su1 = 0.0, su2 = 0.0, se = 0.0;
+    const int q0 = __ldg(&sv.cfOff[c]), q1 = __ldg(&sv.cfOff[c + 1]);
+    for (int q = q0; q < q1; ++q) {                      // fvc::surfaceIntegrate, ascending face order, no atomics
+        const int enc = __ldg(&sv.cfEnc[q]);
+        const int f = enc >> 1;
+        const double sgn = (enc & 1) ? -1.0 : 1.0;
+        sm += sgn * __ldg(&sv.Fm[f]);
+        su0 += sgn * __ldg(&sv.FU[f]);
+        su1 += sgn * __ldg(&sv.FU[(size_t)nF + f]);
+        su2 += sgn * __ldg(&sv.FU[2 * (size_t)nF + f]);
+        se += sgn * __ldg(&sv.FE[f]);
+    }
+    const double V = __ldg(&sv.V[c]);
+    const double rDeltaT = 1.0 / sv.sc->dt;
+    const double diag = rDeltaT * V;
+    // QGDRhoEqn.H:40-47
+    const double rho = (rDeltaT * a.rho * V - V * (sm / V)) / diag;
+    // QGDUEqn.H:36-51, 79-86
+    double rhoU[3], U[3];
+    rhoU[0] = (rDeltaT * b.rhoUx * V - V * (su0 / V)) / diag;
+    rhoU[1] = (rDeltaT * b.rhoUy * V - V * (su1 / V)) / diag;
+    rhoU[2] = (rDeltaT * b.rhoUz * V - V * (su2 / V)) / diag;
+    const double diagR = rDeltaT * rho * V;
+    U[0] = (rDeltaT * a.rho * a.Ux * V + V * (rDeltaT * (rhoU[0] - b.rhoUx))) / diagR;
+    U[1] = (rDeltaT * a.rho * a.Uy * V + V * (rDeltaT * (rhoU[1] - b.rhoUy))) / diagR;
+    U[2] = (rDeltaT * a.rho * a.Uz * V + V * (rDeltaT * (rhoU[2] - b.rhoUz))) / diagR;
+    // QGDEEqn.H:37-50, 65-73
+    const double rhoE = (rDeltaT * b.rhoE * V - V * (se / V)) / diag;
+    double e = rhoE / rho - 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
+    const double ddt = k.energyQuirk ? (rDeltaT * (rhoE - b.rhoE)) : (rDeltaT * (rho * e - a.rho * a.e));
+    e = (rDeltaT * a.rho * a.e * V + V * ddt) / diagR;
+    cellThermo(k, rho, U, rhoU, rhoE, e, a.p, a.T, __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]),
+               reinterpret_cast<double*>(sv.A + c), reinterpret_cast<double*>(sv.B + c));
+}
+
+// boundary state after the cell update: the correctBoundaryConditions() sequence of QGDUEqn.H:51,88 ; QGDEEqn.H:50,75 ;
+// hePsiQGDThermo.C:84-121 ; constScPrModel1.C:117-130 ; QGDFoam.C:155-156
+__device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, const SolverView& sv, const BndState& bs, int b,
+                                         bool init, const RecA& cA, double aQGD)
+{
+    const int f = fv.nI + b;
+    RecA a = bs.A[b];
+    const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
+    // p_b as left by the last p.correctBoundaryConditions() (mid-step for qgdFlux patches)
+    const double rhoOld = a.rho, pOld = init ? a.p : bs.pNew[b];
+    double U[3] = {cA.Ux, cA.Uy, cA.Uz};
+    if (fixU) { U[0] = bs.bvU[3 * (size_t)b]; U[1] = bs.bvU[3 * (size_t)b + 1]; U[2] = bs.bvU[3 * (size_t)b + 2]; }
+    double T, e;
+    if (fixT) { T = bs.bvT[b]; e = thermoEs(k, T); }                     // fixedEnergy ; hePsiQGDThermo.C:93-105
+    else { e = cA.e; T = thermoTHE(k, e, init ? cA.T : a.T); }           // gradientEnergy (gradient 0) ; :109-119
+    const double psi = 1.0 / (k.R * T);
+    const double rhoB = init ? psi * pOld : rhoOld;                      // rho_b is refreshed last (QGDFoam.C:156)
+    const double rhoU[3] = {rhoB * U[0], rhoB * U[1], rhoB * U[2]};      // QGDUEqn.H:88-89
+    const double rhoE = rhoB * (e + 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]));   // QGDEEqn.H:75-76
+    const double c = sqrt(k.gamma / psi);
+    const double hf = fv.hf[f];
+    const double tauB = aQGD * hf / c;                                   // hQGD_b = hQGDf_b  QGDCoeffs.C:373
+    const double muQGD = pOld * k.ScQGD * tauB;                          // constScPrModel1.C:121-124
+    const double mu = k.mu + muQGD;
+    const double alpha = k.mu / k.Pr + muQGD / k.PrQGD;
+    const double aByC = aQGD / c;
+    // p.correctBoundaryConditions()   QGDFoam.C:155 ; qgdFluxFvPatchScalarField.C:159-208
+    double p;
+    const int bcP = bs.bcP[b];
+    if (bcP == QGD_BC_FIXED_VALUE) p = bs.bvP[b];
+    else if (bcP == QGD_BC_ZERO_GRADIENT) p = cA.p;
+    else {
+        double grad = bs.pGrad[b];
+        if (!init) { grad = -(bs.phiw[b] / (aByC * hf) / fv.magSf[f]); bs.pGrad[b] = grad; }
+        p = cA.p + grad / fv.dC[f];
+    }
+    const double rhoNew = init ? rhoB : psi * p;                         // QGDFoam.C:156
+    a.rho = rhoNew; a.Ux = U[0]; a.Uy = U[1]; a.Uz = U[2]; a.e = e; a.p = p; a.T = T;
+    a.H = (rhoE + p) / rhoNew;                                           // updateFields.H:71 boundary part
+    bs.A[b] = a;
+    bs.B[b] = RecB{rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aByC};
+    bs.psi[b] = psi;
+    bs.pNew[b] = p;
+}
+
+__global__ void k_bnd_post(Consts k, FaceView fv, SolverView sv, BndState bs)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= fv.nB) return;
+    if (fv.bKind[b] == QGD_PATCH_EMPTY) return;
+    const int P = fv.own[fv.nI + b];
+    bndClose(k, fv, sv, bs, b, false, loadA(sv.A, P), sv.aQGD[P]);
+}
+
+// ---- initialisation: QGDFoam/createFields.H:3-87 on the device
+__global__ void k_init_cells(Consts k, SolverView sv, const double* __restrict__ U0, const double* __restrict__ T0,
+                             const double* __restrict__ p0)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nCells) return;
+    const double p = p0[c];
+    double T = T0[c];
+    const double e = thermoEs(k, T);                       // heThermo::init  he = HE(p,T)
+    T = thermoTHE(k, e, T);                                // hePsiQGDThermo ctor: calculate()
+    T = thermoTHE(k, e, T);                                // createFields.H:8  thermo.correct()
+    const double psi = 1.0 / (k.R * T);
+    const double rho = psi * p;                            // psiThermo::rho()
+    const double U[3] = {U0[3 * (size_t)c], U0[3 * (size_t)c + 1], U0[3 * (size_t)c + 2]};
+    const double rhoU[3] = {rho * U[0], rho * U[1], rho * U[2]};
+    const double rhoE = rho * e + rho * 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
+    // cellThermo recomputes p = rho/psi; at start-up p is the field as read -> store explicitly afterwards
+    cellThermo(k, rho, U, rhoU, rhoE, e, p, T, sv.aQGD[c], sv.hQGD[c], reinterpret_cast<double*>(sv.A + c),
+               reinterpret_cast<double*>(sv.B + c));
+    sv.A[c].p = p;
+    sv.A[c].H = (rhoE + p) / rho;
+}
+
+__global__ void k_init_bnd(Consts k, FaceView fv, SolverView sv, BndState bs, const double* __restrict__ T0)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= fv.nB) return;
+    bs.pGrad[b] = 0.0; bs.phiw[b] = 0.0; bs.pNew[b] = 0.0; bs.psi[b] = 0.0;
+    if (fv.bKind[b] == QGD_PATCH_EMPTY) { bs.A[b] = RecA{1, 0, 0, 0, 0, 0, 1, 0}; bs.B[b] = RecB{0, 0, 0, 0, 1, 0, 0, 0}; return; }
+    const int P = fv.own[fv.nI + b];
+    RecA cA = loadA(sv.A, P);
+    cA.T = T0[P];
+    // boundary values of the fields as read: p_b (value / internal), then the common closing sequence
+    RecA a{};
+    a.p = (bs.bcP[b] == QGD_BC_FIXED_VALUE) ? bs.bvP[b] : cA.p;
+    bs.A[b] = a;
+    bndClose(k, fv, sv, bs, b, true, cA, sv.aQGD[P]);
+}
+
+} // namespace
+
+// ============================================================================ launchers
+static inline int nblk(long n, int b = kBlock) { return (int)((n + b - 1) / b); }
+
+int faceKernelGrid()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int perSM = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux<false>, kBlock, 0);
+    if (perSM < 1) perSM = 1;
+    return sms * perSM;
+}
+
+void launchPointGather(cudaStream_t st, int K, const qgd_mesh& m, const double* cell, const double* bnd, double* pts)
+{
+    const int nP = m.h.nPoints, nPP = (int)m.h.patchPoints.size();
+#define QGD_PG(KK)                                                                                                          \
+    k_point_gather_generic<KK><<<nblk(nP), kBlock, 0, st>>>(nP, m.pcOff.p, m.pcCell.p, m.pcW.p, cell, pts);                \
+    if (nPP) k_patch_point_gather_generic<KK><<<nblk(nPP), kBlock, 0, st>>>(nPP, m.patchPoints.p, m.ppOff.p, m.ppFace.p, m.ppW.p, bnd, pts);
+    switch (K) {
+        case 1: QGD_PG(1) break;
+        case 3: QGD_PG(3) break;
+        case 9: QGD_PG(9) break;
+        default: throw Error(QGD_ERR_INVALID, "fvsc: unsupported number of components");
+    }
+#undef QGD_PG
+    QGD_CUDA(cudaGetLastError());
+}
+
+void launchFvscGrad(cudaStream_t st, int K, const FaceView& fv, const double* cell, const double* pts, const double* bnd,
+                    const double* bsg, const double* nbr, double* out)
+{
+    if (K == 1) k_fvsc_grad<1><<<nblk(fv.nF), kBlock, 0, st>>>(fv, cell, pts, bnd, bsg, nbr, out);
+    else if (K == 3) k_fvsc_grad<3><<<nblk(fv.nF), kBlock, 0, st>>>(fv, cell, pts, bnd, bsg, nbr, out);
+    else throw Error(QGD_ERR_INVALID, "fvsc::grad: ncmpt must be 1 or 3");
+    QGD_CUDA(cudaGetLastError());
+}
+
+void launchFvscDiv(cudaStream_t st, int K, const FaceView& fv, const double* cell, const double* pts, const double* bnd,
+                   const double* bsg, const double* nbr, double* out)
+{
+    if (K == 3) k_fvsc_div<3><<<nblk(fv.nF), kBlock, 0, st>>>(fv, cell, pts, bnd, bsg, nbr, out);
+    else if (K == 9) k_fvsc_div<9><<<nblk(fv.nF), kBlock, 0, st>>>(fv, cell, pts, bnd, bsg, nbr, out);
+    else throw Error(QGD_ERR_INVALID, "fvsc::div: ncmpt must be 3 or 9");
+    QGD_CUDA(cudaGetLastError());
+}
+
+void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
+                const double* U0, const double* T0, const double* p0)
+{
+    k_init_cells<<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, U0, T0, p0);
+    if (fv.nB) k_init_bnd<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs, T0);
+    QGD_CUDA(cudaGetLastError());
+}
+
+int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
+               bool anyQgdFlux, int gridFaces, bool adjust)
+{
+    int n = 0;
+    const bool pointsNeeded = !c.reducedScheme;
+    if (pointsNeeded) {
+        k_points<<<nblk(sv.nPoints), kBlock, 0, st>>>(sv); ++n;
+        if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
+    }
+    if (fv.nB && anyQgdFlux) {
+        k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+        if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
+    }
+    if (fv.nI) {
+        const int grid = std::min(gridFaces, nblk(fv.nI));
+        if (adjust) k_face_flux<true><<<grid, kBlock, 0, st>>>(c, fv, sv);
+        else k_face_flux<false><<<grid, kBlock, 0, st>>>(c, fv, sv);
+        ++n;
+    }
+    if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
+    k_dt<<<1, 1, 0, st>>>(sv.sc); ++n;
+    k_cell_update<<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF); ++n;
+    if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
+    return n;
+}
+
+} // namespace qgd

@@ -1,0 +1,78 @@
+// Kernel-side declarations: device views (POD structs of raw pointers passed by value) and launchers.
+#pragma once
+#include "qgd_internal.h"
+
+namespace qgd {
+
+// thermo + model constants (perfectGas / hConst / sensibleInternalEnergy / constTransport / constScPrModel1)
+struct Consts {
+    double R, Cp, Cv, Tref, Hsref, mu, Pr, ScQGD, PrQGD, gamma;
+    int alphaEffGamma, energyQuirk, reducedScheme;
+};
+
+struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
+    int nI, nF, nB;
+    int zeroDivCmpt;         // 2D: out-of-plane component of Div(tensor) stays 0 (GaussVolPointBase2D.C:447-485), else -1
+    const int* own;          // nF
+    const int* nei;          // nI
+    const int4* vtx;         // nF
+    const int* flags;        // nF
+    const double* Sf;        // SoA 3*nF
+    const double* magSf;     // nF
+    const double* w;         // nF
+    const double* hf;        // nF  hQGDf
+    const double* dC;        // nF  deltaCoeffs
+    const double* G;         // SoA 9*nF
+    const double* halfDist;  // nB
+    const int* bKind;        // nB patch kind per boundary face
+};
+
+struct BndState {            // per boundary face
+    RecA* A;                 // rho,U,e,p,T,H   (p = value used by interpolation, see quirk (h) in DESIGN.md)
+    RecB* B;
+    double* psi;
+    double* pGrad;           // qgdFlux gradient
+    double* pNew;            // p boundary value seen by fvsc::grad(p) inside the step
+    double* phiw;            // phiwStar
+    const int* bcU; const int* bcT; const int* bcP;     // kinds per boundary face
+    const double* bvU; const double* bvT; const double* bvP;
+};
+
+struct StepScalars {         // device-resident time-step control
+    double dt;
+    double time;
+    double coNum;            // last Courant number
+    unsigned long long coMaxBits;   // max over faces of max(|Un+c|,|Un-c|)/h   (bit pattern of a non-negative double)
+    unsigned long long tauMinBits;  // min over faces of tauQGDf
+    double maxCo, maxDeltaT, cTau;
+    int adjust;
+};
+
+// ---- generic fvsc operator kernels (operator-level API)
+void launchPointGather(cudaStream_t st, int K, const qgd_mesh& m, const double* cell, const double* bnd, double* pts);
+void launchFvscGrad(cudaStream_t st, int K, const FaceView& fv, const double* cell, const double* pts,
+                    const double* bnd, const double* bsg, const double* nbr, double* out);
+void launchFvscDiv(cudaStream_t st, int K, const FaceView& fv, const double* cell, const double* pts,
+                   const double* bnd, const double* bsg, const double* nbr, double* out);
+
+// ---- QGDFoam step kernels
+struct SolverView {
+    int nCells, nPoints, nPatchPoints;
+    RecA* A; RecB* B;            // cells
+    RecP* P;                     // points
+    const int* pcOff; const int* pcCell; const double* pcW;
+    const int* patchPoints; const int* ppOff; const int* ppFace; const double* ppW;
+    const int* cfOff; const int* cfEnc;
+    const double* V; const double* hQGD; const double* aQGD;
+    double* Fm; double* FU; double* FE;   // face fluxes, SoA: Fm[nF], FU[3*nF], FE[nF]
+    StepScalars* sc;
+};
+
+void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
+                const double* U0, const double* T0, const double* p0);
+// one QGDFoam.C:90-163 loop body; returns number of kernel launches issued
+int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
+               bool anyQgdFlux, int gridFaces, bool adjust);
+int faceKernelGrid();
+
+} // namespace qgd

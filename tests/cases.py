@@ -1,0 +1,132 @@
+"""Seeded synthetic cases shared by the oracle KATs and the GPU parity tests."""
+from __future__ import annotations
+
+import numpy as np
+
+from qgdsolver_b200 import polymesh as pm
+
+FV, ZG, FG, QF = 0, 1, 2, 3   # bc kinds (fixedValue, zeroGradient, fixedGradient, qgdFlux)
+
+GAS = dict(R=1.0, Cp=3.5, Hf=0.0, Tref=0.0, Hsref=0.0, mu=1.0e-3, Pr=0.71, ScQGD=1.0, PrQGD=1.0)
+GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5, Pr=0.71, ScQGD=0.7, PrQGD=0.9)
+
+
+class Case:
+    def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, gas=GAS, dt=1e-4, scheme="GaussVolPoint",
+                 alphaQGD=None, **opts):
+        self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
+        self.bcU, self.bcT, self.bcP = [np.asarray(x, np.int32) for x in (bcU, bcT, bcP)]
+        self.bvU, self.bvT, self.bvP = bvU, bvT, bvP
+        self.gas, self.dt, self.scheme, self.alphaQGD = dict(gas), dt, scheme, alphaQGD
+        self.opts = dict(alpha_eff_gamma_factor=True, energy_ddt_rhoE_quirk=True, adjust_time_step=False,
+                         max_co=0.3, max_delta_t=1e30, c_tau=0.75)
+        self.opts.update(opts)
+
+    # ---- CPU oracle
+    def make_oracle(self, O, n_threads=1):
+        o = O.Oracle(self.mesh, n_threads=n_threads)
+        g = self.gas
+        prm = O.QGDParams(R=g["R"], Cp=g["Cp"], Hf=g["Hf"], Tref=g["Tref"], Hsref=g["Hsref"], mu=g["mu"], Pr=g["Pr"],
+                          ScQGD=g["ScQGD"], PrQGD=g["PrQGD"], implicitDiffusion=0,
+                          alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
+                          energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]))
+        scheme = O.FVSC_GAUSSVOLPOINT if self.scheme == "GaussVolPoint" else O.FVSC_REDUCED
+        o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
+                   alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme)
+        return o
+
+    def oracle_step(self, o, n):
+        return o.qgd_step(n, adjust=self.opts["adjust_time_step"], maxCo=self.opts["max_co"],
+                          maxDeltaT=self.opts["max_delta_t"], cTau=self.opts["c_tau"])
+
+    # ---- product
+    def make_solver(self, api, dmesh=None):
+        dmesh = dmesh or api.Mesh(self.mesh)
+        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, delta_t=self.dt, **self.gas, **self.opts)
+        s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
+        s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
+        return s
+
+
+def smooth_ic(mesh, gas=GAS, seed=12345, mach=0.1):
+    """Taylor-Green-like smooth state, non-trivial in all primitives, plus a seeded perturbation."""
+    x, y, z = mesh.C[:, 0], mesh.C[:, 1], mesh.C[:, 2]
+    g = gas["Cp"] / (gas["Cp"] - gas["R"])
+    tp = 2.0 * np.pi
+    act = (mesh.geometric_d > 0).astype(float)
+    rho = 1.0 + 0.1 * np.sin(tp * x) * np.cos(tp * y * act[1]) * np.cos(tp * z * act[2])
+    p = (1.0 / g) * (1.0 + 0.1 * np.cos(tp * x) * np.cos(tp * y * act[1]))
+    U = np.stack([mach * np.sin(tp * x) * np.cos(tp * y) * np.cos(tp * z) * act[0],
+                  -mach * np.cos(tp * x) * np.sin(tp * y) * np.cos(tp * z) * act[1],
+                  0.05 * mach * np.sin(tp * z) * np.cos(tp * x) * act[2]], axis=1)
+    rng = np.random.default_rng(seed)
+    T = p / (rho * gas["R"]) * (1.0 + 1e-3 * (rng.random(mesh.n_cells) - 0.5))
+    return np.ascontiguousarray(U), T, p
+
+
+def uniform_bcs(mesh, kU=ZG, kT=ZG, kP=ZG, U=(0.0, 0.0, 0.0), T=1.0, p=1.0):
+    nP, nB = len(mesh.patches), mesh.n_bnd
+    bvU = np.tile(np.asarray(U, float), (nB, 1))
+    return (np.full(nP, kU, np.int32), np.full(nP, kT, np.int32), np.full(nP, kP, np.int32),
+            bvU, np.full(nB, float(T)), np.full(nB, float(p)))
+
+
+def case_hex3d(n=(8, 7, 6), perturb=0.0, grading=(1, 1, 1), bcs="zg", gas=GAS, dt=2e-4, **opts):
+    mesh = pm.hex_box(*n, perturb=perturb, grading=grading, seed=3)
+    return _with_bcs(mesh, bcs, gas, dt, **opts)
+
+
+def case_prism(n=(5, 4, 4), perturb=0.1, bcs="zg", **opts):
+    return _with_bcs(pm.prism_box(*n, perturb=perturb, seed=5), bcs, GAS, 1e-4, **opts)
+
+
+def case_poly(n=(5, 5, 4), bcs="zg", **opts):
+    mesh = pm.hexprism_poly(*n, a=0.1, lz=0.5)
+    return _with_bcs(mesh, bcs, GAS, 1e-4, **opts)
+
+
+def case_2d(n=(24, 20), perturb=0.0, bcs="zg", axis=2, **opts):
+    kinds = {0: {"xMin": "empty", "xMax": "empty"}, 1: {"yMin": "empty", "yMax": "empty"},
+             2: {"zMin": "empty", "zMax": "empty"}}[axis]
+    dims = [n[0], n[1]]
+    dims.insert(axis, 1)
+    lengths = [1.0, 1.0]
+    lengths.insert(axis, 0.1)
+    mesh = pm.hex_box(*dims, lengths=lengths, patch_kinds=kinds, perturb=perturb, seed=7)
+    return _with_bcs(mesh, bcs, GAS, 2e-4, **opts)
+
+
+def case_sod(n=200, dt=2e-4, **opts):
+    mesh = pm.hex_box(n, 1, 1, lengths=(1.0, 0.1, 0.1),
+                      patch_kinds={"zMin": "empty", "zMax": "empty", "yMin": "empty", "yMax": "empty"})
+    x = mesh.C[:, 0]
+    rho = np.where(x < 0.5, 1.0, 0.125)
+    p = np.where(x < 0.5, 1.0, 0.1)
+    gas = dict(GAS, mu=0.0, Pr=1.0)
+    bc = uniform_bcs(mesh)
+    return Case(mesh, np.zeros((n, 3)), p / rho, p, *bc, gas=gas, dt=dt, **opts)
+
+
+def _with_bcs(mesh, bcs, gas, dt, **opts):
+    U0, T0, p0 = smooth_ic(mesh, gas)
+    nP, nB = len(mesh.patches), mesh.n_bnd
+    if bcs == "zg":
+        bc = uniform_bcs(mesh)
+    elif bcs == "fixed":       # everything fixedValue (values from a smooth function of the face centre)
+        bc = list(uniform_bcs(mesh, FV, FV, FV))
+        cf = mesh.Cf[mesh.n_internal:]
+        g = gas["Cp"] / (gas["Cp"] - gas["R"])
+        bc[3] = np.stack([0.05 * np.sin(cf[:, 1] * 3), 0.05 * np.cos(cf[:, 0] * 2), 0.01 * np.sin(cf[:, 2])], 1) * (mesh.geometric_d > 0)
+        bc[4] = (1.0 / g) / gas["R"] * (1.0 + 0.05 * np.sin(cf[:, 0] * 4))
+        bc[5] = (1.0 / g) * (1.0 + 0.05 * np.cos(cf[:, 1] * 3))
+    elif bcs == "mixed":       # wall-like: U fixed 0, T zeroGradient, p qgdFlux on odd patches; in/outflow on even
+        kU = np.array([FV if i % 2 else ZG for i in range(nP)], np.int32)
+        kT = np.array([ZG if i % 2 else FV for i in range(nP)], np.int32)
+        kP = np.array([QF if i % 2 else ZG for i in range(nP)], np.int32)
+        g = gas["Cp"] / (gas["Cp"] - gas["R"])
+        bc = (kU, kT, kP, np.zeros((nB, 3)), np.full(nB, (1.0 / g) / gas["R"]), np.full(nB, 1.0 / g))
+    elif bcs == "qgdflux":     # all walls: U fixed 0, T zeroGradient, p qgdFlux
+        bc = list(uniform_bcs(mesh, FV, ZG, QF))
+    else:
+        raise ValueError(bcs)
+    return Case(mesh, U0, T0, p0, *bc, gas=gas, dt=dt, **opts)

@@ -1,0 +1,183 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances: FP64 path; north_star asks <= 1e-10 relative L-inf on conserved fields after 100 steps.  Operators and
+set-up quantities are checked much tighter (1e-12) because they involve no time accumulation.
+"""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-10      # north_star tolerance, conserved fields after 100 steps
+TOL_OP = 1e-12        # single operator application
+
+
+def rel_linf(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+MESHES = {
+    "hex_uniform": lambda: cases.pm.hex_box(7, 6, 5),
+    "hex_perturbed": lambda: cases.pm.hex_box(7, 6, 5, perturb=0.25, grading=(2, 1, 0.5), seed=11),
+    "prism": lambda: cases.pm.prism_box(4, 4, 3, perturb=0.15, seed=2),
+    "poly": lambda: cases.pm.hexprism_poly(5, 4, 3, a=0.1, lz=0.4),
+    "2d_z": lambda: cases.case_2d(perturb=0.2).mesh,
+    "2d_y": lambda: cases.case_2d(perturb=0.2, axis=1).mesh,
+    "2d_x": lambda: cases.case_2d(perturb=0.2, axis=0).mesh,
+    "1d": lambda: cases.case_sod(40).mesh,
+}
+
+
+def _fields(mesh, k, seed):
+    rng = np.random.default_rng(seed)
+    nI = mesh.n_internal
+    shape = (mesh.n_cells, k) if k > 1 else (mesh.n_cells,)
+    cell = np.sin(3 * mesh.C[:, :1] + np.arange(k)) + 0.3 * rng.random((mesh.n_cells, k))
+    bnd = np.cos(2 * mesh.Cf[nI:, 1:2] + np.arange(k)) + 0.3 * rng.random((mesh.n_bnd, k))
+    # mixed patch behaviour: generic snGrad on even faces, prescribed gradient on odd faces
+    bsg = mesh.deltaCoeffs[nI:, None] * (bnd - cell[mesh.owner[nI:]])
+    bsg[1::2] = rng.random((mesh.n_bnd, k))[1::2]
+    return cell.reshape(shape), bnd.reshape((mesh.n_bnd,) + shape[1:]), bsg.reshape((mesh.n_bnd,) + shape[1:])
+
+
+@pytest.mark.parametrize("mesh_name", list(MESHES))
+@pytest.mark.parametrize("scheme", ["GaussVolPoint", "reduced"])
+def test_fvsc_operators_match_oracle(qgd, oracle_mod, mesh_name, scheme):
+    mesh = MESHES[mesh_name]()
+    o = oracle_mod.Oracle(mesh)
+    osch = oracle_mod.FVSC_GAUSSVOLPOINT if scheme == "GaussVolPoint" else oracle_mod.FVSC_REDUCED
+    dm = qgd.Mesh(mesh)
+    st = qgd.FvscStencil(dm, scheme)
+    for k in (1, 3):
+        cell, bnd, bsg = _fields(mesh, k, 100 + k)
+        assert rel_linf(st.Grad(cell, bnd, bsg), o.fvsc_grad(cell, bnd, bsg, scheme=osch)) < TOL_OP
+    for k in (3, 9):
+        cell, bnd, bsg = _fields(mesh, k, 200 + k)
+        assert rel_linf(st.Div(cell, bnd, bsg), o.fvsc_div(cell, bnd, bsg, scheme=osch)) < TOL_OP
+
+
+@pytest.mark.parametrize("mesh_name", list(MESHES))
+def test_qgd_lengths_match_oracle(qgd, oracle_mod, mesh_name):
+    mesh = MESHES[mesh_name]()
+    o = oracle_mod.Oracle(mesh)
+    dm = qgd.Mesh(mesh)
+    kind = mesh.patch_kind_per_bface()
+    keep = np.ones(mesh.n_faces, bool)
+    keep[mesh.n_internal:] = kind != 1
+    assert rel_linf(dm.hQGDf()[keep], o.hQGDf()[keep]) < 1e-14
+    assert rel_linf(dm.hQGD(), o.hQGD()) < 1e-14
+
+
+STEP_CASES = {
+    "hex_zg": lambda: cases.case_hex3d(),
+    "hex_perturbed_mixed": lambda: cases.case_hex3d(perturb=0.2, grading=(2, 1, 0.5), bcs="mixed"),
+    "hex_fixed_offsetgas": lambda: cases.case_hex3d(bcs="fixed", gas=dict(cases.GAS, Tref=0.2, Hsref=0.1)),
+    "hex_qgdflux_walls": lambda: cases.case_hex3d(perturb=0.1, bcs="qgdflux"),
+    "hex_adjust_dt": lambda: cases.case_hex3d(bcs="fixed", adjust_time_step=True, dt=1e-3, max_co=0.1, c_tau=0.3),
+    "hex_no_quirk": lambda: cases.case_hex3d(perturb=0.1, bcs="mixed", energy_ddt_rhoE_quirk=False, alpha_eff_gamma_factor=False),
+    "hex_reduced": lambda: cases.case_hex3d(perturb=0.1, bcs="mixed", scheme="reduced"),
+    "prism_fixed": lambda: cases.case_prism(bcs="fixed"),
+    "poly_qgdflux": lambda: cases.case_poly(bcs="qgdflux"),
+    "2d_mixed": lambda: cases.case_2d(perturb=0.2, bcs="mixed"),
+    "2d_y_fixed": lambda: cases.case_2d(perturb=0.1, bcs="fixed", axis=1),
+    "sod_1d": lambda: cases.case_sod(200),
+}
+
+
+@pytest.mark.parametrize("name", list(STEP_CASES))
+def test_qgdfoam_100_steps_match_oracle(qgd, oracle_mod, name):
+    c = STEP_CASES[name]()
+    o = c.make_oracle(oracle_mod)
+    s = c.make_solver(qgd)
+    # initial state (thermo construction on the device)
+    for f in ("rho", "rhoU", "rhoE", "e", "p", "T", "c", "mu"):
+        assert rel_linf(s.get(f), o.get(f)) < 1e-13, f"init {f}"
+    c.oracle_step(o, 100)
+    s.step(100)
+    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T"):
+        gc, gb = s.get(f, with_bnd=True)
+        oc, ob = o.get(f, with_bnd=True)
+        assert np.isfinite(gc).all()
+        scale = float(np.abs(oc).max())
+        assert float(np.abs(gc - oc).max()) / scale < TOL_STEP, f"{name}: cells {f}"
+        kind = c.mesh.patch_kind_per_bface()
+        if (kind != 1).any():        # boundary values, relative to the magnitude of the cell field
+            assert float(np.abs(gb[kind != 1] - ob[kind != 1]).max()) / scale < TOL_STEP, f"{name}: boundary {f}"
+    if c.opts["adjust_time_step"]:
+        assert abs(s.scalars()["deltaT"] - o.deltaT()) < 1e-10 * o.deltaT()
+
+
+def test_fluxes_match_oracle_after_one_step(qgd, oracle_mod):
+    c = cases.case_hex3d(perturb=0.2, bcs="mixed")
+    o = c.make_oracle(oracle_mod)
+    s = c.make_solver(qgd)
+    c.oracle_step(o, 1)
+    s.step(1)
+    Fm = o.get_face("phiJm")
+    FU = o.get_face("phiJmU") + o.get_face("phiP") - o.get_face("phiPi")
+    FE = o.get_face("phiJmH") + o.get_face("phiQ") - o.get_face("phiPiU")
+    assert rel_linf(s.get_flux(0), Fm) < 1e-12
+    assert rel_linf(s.get_flux(1), FU) < 1e-12
+    assert rel_linf(s.get_flux(2), FE) < 1e-12
+
+
+def test_step_host_equals_device_resident_loop(qgd):
+    c = cases.case_hex3d(perturb=0.1, bcs="mixed")
+    s1 = c.make_solver(qgd)
+    s2 = c.make_solver(qgd)
+    s1.step(10)
+    n = c.mesh.n_cells
+    st = {k: np.zeros((n, 3) if k in ("U", "rhoU") else n) for k in ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")}
+    s2.step_host(0, None, st)                      # download the initial state
+    for _ in range(10):
+        s2.step_host(1, st, st)                    # upload, one step, download - every step
+    for f in ("rho", "rhoU", "rhoE", "e", "p"):
+        assert rel_linf(s2.get(f), s1.get(f)) < 1e-12
+        assert rel_linf(st[f].reshape(s1.get(f).shape), s1.get(f)) < 1e-12
+
+
+def test_conservation_and_finiteness_at_scale(qgd):
+    """Size-independent properties at a size the oracle is not run at: with qgdFlux walls (U=0) the mass flux through
+    every boundary face vanishes, so total mass is conserved to round-off; energy/momentum stay finite."""
+    mesh = cases.pm.hex_box(96, 96, 96)
+    c = cases._with_bcs(mesh, "qgdflux", cases.GAS, 2e-4)
+    s = c.make_solver(qgd)
+    m0 = float((s.get("rho") * mesh.V).sum())
+    s.step(50)
+    rho = s.get("rho")
+    assert np.isfinite(rho).all() and np.isfinite(s.get("rhoE")).all()
+    assert abs(float((rho * mesh.V).sum()) - m0) < 1e-12 * m0
+
+
+def test_uniform_state_is_preserved(qgd):
+    mesh = cases.pm.hex_box(12, 10, 8, perturb=0.2, seed=4)
+    n = mesh.n_cells
+    bc = cases.uniform_bcs(mesh)
+    U0 = np.tile([0.3, -0.2, 0.1], (n, 1))
+    c = cases.Case(mesh, U0, np.full(n, 1.0 / 1.4), np.full(n, 1.0 / 1.4), *bc)
+    s = c.make_solver(qgd)
+    r0, u0 = s.get("rho").copy(), s.get("U").copy()
+    s.step(20)
+    assert rel_linf(s.get("rho"), r0) < 1e-12
+    assert rel_linf(s.get("U"), u0) < 1e-12
+
+
+def test_error_behaviour_matches_reference_messages(qgd):
+    mesh = cases.pm.hex_box(3, 3, 3)
+    dm = qgd.Mesh(mesh)
+    with pytest.raises(qgd.QGDError) as e:
+        qgd.FvscStencil(dm, "noSuchScheme")            # fvscStencil.C:72-78
+    assert e.value.code == qgd.ERR_UNKNOWN_MODEL and "Unknown Model type noSuchScheme" in e.value.message
+    assert "Valid model types are:" in e.value.message and "GaussVolPoint" in e.value.message
+    with pytest.raises(qgd.QGDError) as e:
+        qgd.FvscStencil(dm, "leastSquares")            # fvsc.C:60-63
+    assert "Can't use leastSquares or leastSquaresOpt in 3D case." in e.value.message
+    with pytest.raises(qgd.QGDError) as e:
+        qgd.QGDFoam(dm, R=1.0, Cp=3.5, qgd_coeffs="noModel")      # QGDCoeffs.C:72-78
+    assert "Unknown QGD coeffs evaluation approach type noModel" in e.value.message
+    with pytest.raises(qgd.QGDError) as e:
+        s = qgd.QGDFoam(dm, R=1.0, Cp=3.5)
+        s.step(1)
+    assert e.value.code == qgd.ERR_STATE
