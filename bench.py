@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — MCUPS of the QGDFoam step (BASELINE.json metric) on N B200s.
+
+  python bench.py --gpus 1 --steps K --warmup W            product arm (CUDA, through the C-ABI)
+  python bench.py --impl reference --steps K --warmup W    reference arm: the CPU oracle port on the host cores
+                                                           (the reference itself needs OpenFOAM v2312 and cannot
+                                                           be built here - DESIGN.md)
+A "step" is one pass of the QGDFoam.C:90-163 loop body over the whole mesh.  Workload at N=1: BASELINE.json configs[3],
+QGDFoam 3D synthetic hex box 256^3 (16 777 216 cells, FP64, GaussVolPoint, constScPrModel1, explicit), which is the
+configuration the metric's roofline target is quoted on; state (>2 GB) is far larger than L2, so no flush is needed.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "cell-updates/s per QGDFoam step"
+UNIT = "MCUPS"
+GAS = dict(R=1.0, Cp=3.5, Hf=0.0, Tref=0.0, Hsref=0.0, mu=1.8e-5, Pr=0.71, ScQGD=1.0, PrQGD=1.0)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_case(n: int, dt: float = None):
+    """SURVEY 8(d) synthetic C4 inputs: uniform hex box n^3, six zeroGradient patches, Taylor-Green-like IC."""
+    import cases
+    mesh = _cached_hex_box(cases.pm, n)
+    dt = dt if dt is not None else 2.0e-4 * (256.0 / n)     # Co ~ 0.06 at any n
+    U0, T0, p0 = cases.smooth_ic(mesh, GAS)
+    bc = cases.uniform_bcs(mesh)
+    return cases.Case(mesh, U0, T0, p0, *bc, gas=GAS, dt=dt)
+
+
+def _cached_hex_box(pm, n):
+    """hex_box(n,n,n) with an on-box cache under /tmp (mesh synthesis is input generation, not the measured path)."""
+    path = f"/tmp/qgd_hexbox_{n}.npz"
+    fields = ("points", "face_offsets", "face_verts", "owner", "neighbour", "C", "V", "Cf", "Sf", "magSf", "weights",
+              "deltaCoeffs", "nonOrthDeltaCoeffs", "neighb_cell_centres", "geometric_d")
+    if n >= 128 and os.path.exists(path):
+        try:
+            z = np.load(path)
+            m = pm.hex_box(2, 2, 2)
+            patches = [pm.Patch(str(a), int(b), int(c), int(d)) for a, b, c, d in
+                       zip(z["patch_name"], z["patch_kind"], z["patch_start"], z["patch_size"])]
+            mesh = pm.PolyMesh(points=z["points"], face_offsets=z["face_offsets"], face_verts=z["face_verts"],
+                               owner=z["owner"], neighbour=z["neighbour"], patches=patches, n_cells=n * n * n)
+            for f in fields[5:]:
+                setattr(mesh, f, z[f])
+            return mesh
+        except Exception:
+            pass
+    mesh = pm.hex_box(n, n, n)
+    if n >= 128 and int(os.environ.get("RANK", "0")) == 0:
+        try:
+            np.savez(path, **{f: getattr(mesh, f) for f in fields},
+                     patch_name=np.array([p.name for p in mesh.patches]), patch_kind=np.array([p.kind for p in mesh.patches]),
+                     patch_start=np.array([p.start for p in mesh.patches]), patch_size=np.array([p.size for p in mesh.patches]))
+        except Exception:
+            pass
+    return mesh
+
+
+def alg_bytes(mesh):
+    """Algorithmic bytes per step: total and per kernel."""
+    nC, nF, nP = mesh.n_cells, mesh.n_internal, mesh.n_points
+    face = 184 * nF + 40 * nC + 48 * nP
+    points = 148 * nP
+    cell = 40 * nF + 64 * nC
+    return dict(total=face + points + cell, face=face, points=points, cell=cell)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def time_oracle(n: int, budget_s: float, threads: int, min_steps: int = 2):
+    """CPU oracle on an n^3 sample of the same workload; returns MCUPS and the sample description."""
+    import oracle as O
+    O.build()
+    c = build_case(n)
+    o = c.make_oracle(O, n_threads=threads)
+    c.oracle_step(o, 1)                                      # warm-up
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        c.oracle_step(o, 1)
+        steps += 1
+        el = time.perf_counter() - t0
+        if steps >= min_steps and el > budget_s:
+            break
+    return c.mesh.n_cells * steps / el / 1e6, f"{n}^3 hex box ({c.mesh.n_cells} cells), {steps} steps in {el:.1f} s", steps, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_size
+    # each "step" = one oracle step over the bounded sample mesh
+    import oracle as O
+    O.build()
+    c = build_case(n)
+    o = c.make_oracle(O, n_threads=threads)
+    c.oracle_step(o, max(args.warmup, 1))
+    t0 = time.perf_counter()
+    c.oracle_step(o, args.steps)
+    el = time.perf_counter() - t0
+    val = c.mesh.n_cells * args.steps / el / 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QGDFoam 3D hex box, CPU oracle port on a bounded {n}^3 sample of the 256^3 case",
+                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n}^3 hex box ({c.mesh.n_cells} cells) x {args.steps} steps, OpenMP {threads} threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_product(args):
+    import torch
+    from qgdsolver_b200 import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    api.init(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from qgdsolver_b200 import multigpu
+        return multigpu.bench(args, rank, world, local)
+
+    n = args.size
+    c = build_case(n)
+    mesh = c.mesh
+    s = c.make_solver(api)
+    ab = alg_bytes(mesh)
+    # ---- device-resident loop
+    s.step(args.warmup)
+    api.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = s.launch_count()
+    s.profile(True)
+    torch.cuda.synchronize()
+    api.timer_begin()
+    s.step(args.steps)
+    ms = api.timer_end()
+    torch.cuda.synchronize()
+    kt = s.kernel_times()
+    s.profile(False)
+    launches = s.launch_count() - l0
+    clocks = sampler.stop()
+    ms_step = ms / args.steps
+    value = mesh.n_cells / (ms_step * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    face_ms = kt["face_ms"] / max(kt["steps"], 1)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "face_flux_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+            if tj.get("n_cells") == mesh.n_cells:
+                traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_face_flux", "achieved": ab["face"] / (face_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": ab["face"] / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": ab["face"], "avg_launch_ms": face_ms,
+                "step": {"alg_bytes": ab["total"], "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
+                         "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak},
+                "kernel_ms": {"k_points": kt["points_ms"] / max(kt["steps"], 1), "k_face_flux": face_ms,
+                              "k_cell_update": kt["cell_ms"] / max(kt["steps"], 1)}}
+    # ---- end-to-end through the C-ABI with host (pinned) buffers: state uploaded and downloaded every step
+    nC = mesh.n_cells
+    names = ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")
+    pinned = {k: torch.empty((nC, 3) if k in ("U", "rhoU") else (nC,), dtype=torch.float64, pin_memory=True) for k in names}
+    st = {k: v.numpy() for k, v in pinned.items()}
+    s.step_host(0, None, st)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        s.step_host(1, st, st)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.step_host(1, st, st)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    nbytes = 12 * 8 * nC
+    e2e = {"value": nC / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "qgd_qgdfoam_step_host: full cell state (12 doubles/cell) H2D + 1 step + D2H per call, pinned host buffers"}
+    # ---- CPU baseline (oracle port) on a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sample, _, _ = time_oracle(args.ref_size, args.cpu_budget, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"QGDFoam 3D synthetic hex box {n}^3 ({nC} cells), explicit, FP64",
+                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False,
+                       "deltaT": c.dt, "l2": "inputs (>2 GB of state and mesh records) exceed the 126 MB L2; no flush"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--size", type=int, default=256, help="hex box edge (cells); 256 = BASELINE configs[3]")
+    ap.add_argument("--ref-size", type=int, default=64, help="edge of the bounded CPU sample")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

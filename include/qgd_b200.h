@@ -168,6 +168,10 @@ int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out);
 int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, double* time);
 /* kernel launches issued by this solver so far (bench bookkeeping) */
 long long qgd_qgdfoam_launch_count(qgd_solver* s);
+/* per-kernel CUDA-event timing on the solver stream: enable, run steps, then read the summed durations (ms) of the
+ * point-gather, face-flux and cell-update kernels over the profiled steps */
+int qgd_qgdfoam_profile(qgd_solver* s, int enable);
+int qgd_qgdfoam_kernel_times(qgd_solver* s, double* ms_points, double* ms_face, double* ms_cell, int* n_steps);
 /* CUDA-event timing of the device step loop: call begin, steps, end -> milliseconds on the solver stream */
 int qgd_timer_begin(void);
 int qgd_timer_end(float* ms);

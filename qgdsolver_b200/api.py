@@ -28,7 +28,8 @@ ABI_SYMBOLS = [
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
-    "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_timer_begin", "qgd_timer_end",
+    "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
+    "qgd_timer_begin", "qgd_timer_end",
     "qgd_pcg_solve",
 ]
 
@@ -98,6 +99,8 @@ def load_library():
     L.qgd_qgdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
     L.qgd_qgdfoam_launch_count.restype = C.c_longlong
     L.qgd_qgdfoam_launch_count.argtypes = [C.c_void_p]
+    L.qgd_qgdfoam_profile.argtypes = [C.c_void_p, C.c_int]
+    L.qgd_qgdfoam_kernel_times.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip]
     L.qgd_timer_end.argtypes = [C.POINTER(C.c_float)]
     L.qgd_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
                                 _ip, _dp, _dp]
@@ -283,6 +286,14 @@ class QGDFoam:
         dt, co, t = C.c_double(), C.c_double(), C.c_double()
         _check(load_library().qgd_qgdfoam_get_scalars(self._h, C.byref(dt), C.byref(co), C.byref(t)))
         return dict(deltaT=dt.value, CoNum=co.value, time=t.value)
+
+    def profile(self, enable: bool):
+        _check(load_library().qgd_qgdfoam_profile(self._h, int(enable)))
+
+    def kernel_times(self):
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        _check(load_library().qgd_qgdfoam_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        return dict(points_ms=a.value, face_ms=b.value, cell_ms=c.value, steps=n.value)
 
     def launch_count(self) -> int:
         return int(load_library().qgd_qgdfoam_launch_count(self._h))

@@ -2,6 +2,7 @@
 // error behaviour, H2D/D2H staging for the operator-level calls.  No compute happens on the host here.
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -76,21 +77,26 @@ struct qgd_solver {
     std::unique_ptr<qgd_fvsc> fvsc;
     qgd_qgdfoam_desc desc{};
     Consts k{};
-    DevBuf<RecA> A, bA;
-    DevBuf<RecB> B, bB;
-    DevBuf<RecP> P;
+    DevBuf<RecA> bA;
+    DevBuf<RecB> bB;
+    DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
     DevBuf<double> aQGD, Fm, FU, FE, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage;
     DevBuf<int> bcU, bcT, bcP;
     DevBuf<StepScalars> sc;
     long long launches = 0;
     bool anyQgdFlux = false, bcsSet = false, fieldsSet = false;
     int gridFaces = 148;
+    // per-kernel CUDA-event timing (bench): events of the profiled steps, 6 per step
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    size_t eventsUsed = 0;
+    ~qgd_solver() { for (cudaEvent_t e : events) cudaEventDestroy(e); }
     SolverView sview() const
     {
         const qgd_mesh& m = *mesh;
         SolverView s;
         s.nCells = m.h.nCells; s.nPoints = m.h.nPoints; s.nPatchPoints = (int)m.h.patchPoints.size();
-        s.A = A.p; s.B = B.p; s.P = P.p;
+        s.S = S.p; s.P = P.p;
         s.pcOff = m.pcOff.p; s.pcCell = m.pcCell.p; s.pcW = m.pcW.p;
         s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
         s.cfOff = m.cfOff.p; s.cfEnc = m.cfEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
@@ -119,7 +125,7 @@ template <class T> void d2h(T* h, const T* d, size_t n)
 }
 
 // state hand-off kernels for qgd_qgdfoam_step_host
-__global__ void k_pack_state(Consts k, int n, RecA* A, RecB* B, const double* __restrict__ aQGD, const double* __restrict__ st)
+__global__ void k_pack_state(Consts k, int n, double* S, const double* __restrict__ aQGD, const double* __restrict__ st)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -131,21 +137,21 @@ __global__ void k_pack_state(Consts k, int n, RecA* A, RecB* B, const double* __
     const double psi = 1.0 / (k.R * T);
     const double cs = sqrt(k.gamma / psi);
     const double alpha = k.mu / k.Pr + (mu - k.mu) / k.PrQGD;
-    A[c] = RecA{rho, Ux, Uy, Uz, e, p, T, (rhoE + p) / rho};
-    B[c] = RecB{rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD[c] / cs};
+    const double v[16] = {rho, Ux, Uy, Uz, e, p, T, (rhoE + p) / rho,
+                          rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD[c] / cs};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) S[j * N + c] = v[j];
 }
-__global__ void k_unpack_state(int n, const RecA* __restrict__ A, const RecB* __restrict__ B, double* st)
+__global__ void k_unpack_state(int n, const double* __restrict__ S, double* st)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const size_t N = n;
-    const RecA a = A[c];
-    const RecB b = B[c];
-    st[c] = a.rho;
-    st[N + 3 * (size_t)c] = a.Ux; st[N + 3 * (size_t)c + 1] = a.Uy; st[N + 3 * (size_t)c + 2] = a.Uz;
-    st[4 * N + c] = a.e; st[5 * N + c] = a.p; st[6 * N + c] = a.T;
-    st[7 * N + 3 * (size_t)c] = b.rhoUx; st[7 * N + 3 * (size_t)c + 1] = b.rhoUy; st[7 * N + 3 * (size_t)c + 2] = b.rhoUz;
-    st[10 * N + c] = b.rhoE; st[11 * N + c] = b.mu;
+    st[c] = S[c];
+    st[N + 3 * (size_t)c] = S[N + c]; st[N + 3 * (size_t)c + 1] = S[2 * N + c]; st[N + 3 * (size_t)c + 2] = S[3 * N + c];
+    st[4 * N + c] = S[4 * N + c]; st[5 * N + c] = S[5 * N + c]; st[6 * N + c] = S[6 * N + c];
+    st[7 * N + 3 * (size_t)c] = S[8 * N + c]; st[7 * N + 3 * (size_t)c + 1] = S[9 * N + c]; st[7 * N + 3 * (size_t)c + 2] = S[10 * N + c];
+    st[10 * N + c] = S[11 * N + c]; st[11 * N + c] = S[13 * N + c];
 }
 
 void runSteps(qgd_solver* s, int n)
@@ -153,8 +159,16 @@ void runSteps(qgd_solver* s, int n)
     const FaceView fv = s->fvsc->view();
     const SolverView sv = s->sview();
     const BndState bs = s->bview();
-    for (int i = 0; i < n; ++i)
-        s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0);
+    for (int i = 0; i < n; ++i) {
+        cudaEvent_t* ev = nullptr;
+        if (s->profiling) {
+            if (s->eventsUsed + 6 > s->events.size())
+                for (int j = 0; j < 6; ++j) { cudaEvent_t e; QGD_CUDA(cudaEventCreate(&e)); s->events.push_back(e); }
+            ev = &s->events[s->eventsUsed];
+            s->eventsUsed += 6;
+        }
+        s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev);
+    }
     QGD_CUDA(cudaGetLastError());
 }
 
@@ -335,7 +349,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         k.ScQGD = d->ScQGD; k.PrQGD = d->PrQGD; k.gamma = d->Cp / (d->Cp - d->R);
         k.alphaEffGamma = d->alpha_eff_gamma_factor; k.energyQuirk = d->energy_ddt_rhoE_quirk; k.reducedScheme = s->fvsc->reduced;
         const HostMesh& h = mesh->h;
-        s->A.alloc(h.nCells); s->B.alloc(h.nCells); s->P.alloc(h.nPoints);
+        s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
         s->aQGD.alloc(h.nCells);
         s->Fm.alloc(h.nFaces); s->FU.alloc(3 * (size_t)h.nFaces); s->FE.alloc(h.nFaces);
@@ -347,6 +361,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         std::memcpy(&sc.tauMinBits, &big, sizeof(double));
         sc.maxCo = d->max_co; sc.maxDeltaT = d->max_delta_t; sc.cTau = d->c_tau; sc.adjust = d->adjust_time_step;
         s->sc.upload(std::vector<StepScalars>(1, sc), g_stream);
+        if (const char* v = getenv("QGD_FACE_VARIANT")) setFaceVariant(atoi(v));
         s->gridFaces = faceKernelGrid();
         *out = s.release();
     });
@@ -434,12 +449,12 @@ int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, 
             const size_t off[8] = {0, 1, 4, 5, 6, 7, 10, 11}, len[8] = {1, 3, 1, 1, 1, 3, 1, 1};
             for (int i = 0; i < 8; ++i)
                 QGD_CUDA(cudaMemcpyAsync(st + off[i] * n, src[i], len[i] * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-            k_pack_state<<<nb, 256, 0, g_stream>>>(s->k, (int)n, s->A.p, s->B.p, s->aQGD.p, st);
+            k_pack_state<<<nb, 256, 0, g_stream>>>(s->k, (int)n, s->S.p, s->aQGD.p, st);
             s->launches++;
         }
         runSteps(s, n_steps);
         if (out) {
-            k_unpack_state<<<nb, 256, 0, g_stream>>>((int)n, s->A.p, s->B.p, st);
+            k_unpack_state<<<nb, 256, 0, g_stream>>>((int)n, s->S.p, st);
             s->launches++;
             double* dst[8] = {out->rho, out->U, out->e, out->p, out->T, out->rhoU, out->rhoE, out->mu};
             const size_t off[8] = {0, 1, 4, 5, 6, 7, 10, 11}, len[8] = {1, 3, 1, 1, 1, 3, 1, 1};
@@ -483,8 +498,24 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
                 }
             }
         };
-        fetch(s->A.p, s->B.p, h.nCells, cells);
-        if (field == 10 && cells) for (int c = 0; c < h.nCells; ++c) cells[c] *= h.hQGD[c];
+        if (cells) {
+            // SoA field index of each public field id (vectors: first component)
+            static const int fieldOf[12] = {0, 8, 11, 1, 4, 5, 6, 12, 13, 14, 15, 7};
+            if (field < 0 || field > 11) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: unknown field id");
+            const size_t n = h.nCells;
+            const int k0 = fieldOf[field];
+            if (field == 1 || field == 3) {
+                std::vector<double> t(3 * n);
+                d2h(t.data(), s->S.p + (size_t)k0 * n, 3 * n);
+                QGD_CUDA(cudaStreamSynchronize(g_stream));
+                for (size_t c = 0; c < n; ++c) for (int d = 0; d < 3; ++d) cells[3 * c + d] = t[d * n + c];
+            } else {
+                d2h(cells, s->S.p + (size_t)k0 * n, n);
+                QGD_CUDA(cudaStreamSynchronize(g_stream));
+                if (field == 9 && s->k.alphaEffGamma) for (size_t c = 0; c < n; ++c) cells[c] /= s->k.gamma;
+                if (field == 10) for (size_t c = 0; c < n; ++c) cells[c] *= h.hQGD[c];
+            }
+        }
         fetch(s->bA.p, s->bB.p, h.nBnd, bnd);
         if (field == 10 && bnd) for (int b = 0; b < h.nBnd; ++b) bnd[b] *= h.hQGDf[h.nInternal + b];
     });
@@ -523,6 +554,38 @@ int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, dou
 }
 
 long long qgd_qgdfoam_launch_count(qgd_solver* s) { return s ? s->launches : 0; }
+
+int qgd_qgdfoam_profile(qgd_solver* s, int enable)
+{
+    return guarded([&] {
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_profile: null solver");
+        s->profiling = enable != 0;
+        s->eventsUsed = 0;
+    });
+}
+
+int qgd_qgdfoam_kernel_times(qgd_solver* s, double* ms_points, double* ms_face, double* ms_cell, int* n_steps)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_kernel_times: null solver");
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        double t[3] = {0, 0, 0};
+        const size_t steps = s->eventsUsed / 6;
+        const bool pts = !s->k.reducedScheme;
+        for (size_t i = 0; i < steps; ++i)
+            for (int k = 0; k < 3; ++k) {
+                if (k == 0 && !pts) continue;
+                float ms = 0.f;
+                QGD_CUDA(cudaEventElapsedTime(&ms, s->events[6 * i + 2 * k], s->events[6 * i + 2 * k + 1]));
+                t[k] += ms;
+            }
+        if (ms_points) *ms_points = t[0];
+        if (ms_face) *ms_face = t[1];
+        if (ms_cell) *ms_cell = t[2];
+        if (n_steps) *n_steps = (int)steps;
+    });
+}
 
 int qgd_pcg_solve(qgd_mesh*, const double*, const double*, const double*, double*, double, double, int, int, int*, double*, double*)
 {

@@ -24,29 +24,33 @@ constexpr int kBlock = 256;
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-__device__ __forceinline__ RecA loadA(const RecA* base, int i)
+__device__ __forceinline__ RecA loadA(const SolverView& sv, int i)
 {
-    const double* p = reinterpret_cast<const double*>(base + i);
-    const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4), d = ldg2(p + 6);
-    return RecA{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+    const double* p = sv.S + i;
+    const size_t n = sv.nCells;
+    return RecA{__ldg(p), __ldg(p + n), __ldg(p + 2 * n), __ldg(p + 3 * n), __ldg(p + 4 * n), __ldg(p + 5 * n),
+                __ldg(p + 6 * n), __ldg(p + 7 * n)};
 }
-__device__ __forceinline__ RecB loadB(const RecB* base, int i)
+__device__ __forceinline__ RecB loadB(const SolverView& sv, int i)
 {
-    const double* p = reinterpret_cast<const double*>(base + i);
-    const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4), d = ldg2(p + 6);
-    return RecB{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+    const double* p = sv.S + 8 * (size_t)sv.nCells + i;
+    const size_t n = sv.nCells;
+    return RecB{__ldg(p), __ldg(p + n), __ldg(p + 2 * n), __ldg(p + 3 * n), __ldg(p + 4 * n), __ldg(p + 5 * n),
+                __ldg(p + 6 * n), __ldg(p + 7 * n)};
 }
-__device__ __forceinline__ RecP loadP(const RecP* base, int i)
+__device__ __forceinline__ RecP loadP(const SolverView& sv, int i)
 {
-    const double* p = reinterpret_cast<const double*>(base + i);
-    const double2 a = ldg2(p), b = ldg2(p + 2), c = ldg2(p + 4);
-    return RecP{a.x, a.y, b.x, b.y, c.x, c.y};
+    const double* p = sv.P + i;
+    const size_t n = sv.nPoints;
+    return RecP{__ldg(p), __ldg(p + n), __ldg(p + 2 * n), __ldg(p + 3 * n), __ldg(p + 4 * n), __ldg(p + 5 * n)};
 }
-__device__ __forceinline__ void storeRec(double* p, const double (&v)[8])
+// 8 fields of cell i starting at field k0
+__device__ __forceinline__ void storeRec(const SolverView& sv, int k0, int i, const double (&v)[8])
 {
-    double2* q = reinterpret_cast<double2*>(p);
-    q[0] = make_double2(v[0], v[1]); q[1] = make_double2(v[2], v[3]);
-    q[2] = make_double2(v[4], v[5]); q[3] = make_double2(v[6], v[7]);
+    double* p = sv.S + (size_t)k0 * sv.nCells + i;
+    const size_t n = sv.nCells;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) p[k * n] = v[k];
 }
 
 // ---- thermo: perfectGas + hConst + sensibleInternalEnergy  [OF-v2312; SURVEY 8c item 9]
@@ -325,10 +329,11 @@ __device__ __forceinline__ RecP recDiff(const RecP& a, const RecP& b)
 __device__ __forceinline__ unsigned long long dbits(double v) { return (unsigned long long)__double_as_longlong(v); }
 
 // block-wide max / min of non-negative doubles, one atomic per block
+template <int BLOCK>
 __device__ __forceinline__ void blockReduceCo(double coMax, double tauMin, StepScalars* sc)
 {
-    __shared__ double sMax[kBlock / 32];
-    __shared__ double sMin[kBlock / 32];
+    __shared__ double sMax[BLOCK / 32];
+    __shared__ double sMin[BLOCK / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         coMax = fmax(coMax, __shfl_xor_sync(0xffffffffu, coMax, o));
@@ -338,8 +343,8 @@ __device__ __forceinline__ void blockReduceCo(double coMax, double tauMin, StepS
     if (lane == 0) { sMax[wid] = coMax; sMin[wid] = tauMin; }
     __syncthreads();
     if (wid == 0) {
-        coMax = (lane < kBlock / 32) ? sMax[lane] : 0.0;
-        tauMin = (lane < kBlock / 32) ? sMin[lane] : DBL_MAX;
+        coMax = (lane < BLOCK / 32) ? sMax[lane] : 0.0;
+        tauMin = (lane < BLOCK / 32) ? sMin[lane] : DBL_MAX;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             coMax = fmax(coMax, __shfl_xor_sync(0xffffffffu, coMax, o));
@@ -360,15 +365,32 @@ __global__ void __launch_bounds__(kBlock) k_points(SolverView sv)
     const int b = sv.pcOff[p], e = sv.pcOff[p + 1];
     if (b == e) return;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-    for (int q = b; q < e; ++q) {
-        const int c = __ldg(&sv.pcCell[q]);
-        const double wq = __ldg(&sv.pcW[q]);
-        const double* r = reinterpret_cast<const double*>(sv.A + c);
-        const double2 x = ldg2(r), y = ldg2(r + 2), z = ldg2(r + 4);
-        a0 += wq * x.x; a1 += wq * x.y; a2 += wq * y.x; a3 += wq * y.y; a4 += wq * z.x; a5 += wq * z.y;
+    for (int q0 = b; q0 < e; q0 += 8) {           // batches of 8: all indices, then all gathers in flight together
+        int ids[8];
+        double wq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool ok = q0 + j < e;
+            ids[j] = ok ? __ldg(&sv.pcCell[q0 + j]) : -1;
+            wq[j] = ok ? __ldg(&sv.pcW[q0 + j]) : 0.0;
+        }
+        const size_t n = sv.nCells;
+        double v[8][6];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double* r = sv.S + (ids[j] >= 0 ? ids[j] : 0);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[j][k] = __ldg(r + k * n);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a0 += wq[j] * v[j][0]; a1 += wq[j] * v[j][1]; a2 += wq[j] * v[j][2]; a3 += wq[j] * v[j][3];
+            a4 += wq[j] * v[j][4]; a5 += wq[j] * v[j][5];
+        }
     }
-    double2* o = reinterpret_cast<double2*>(sv.P + p);
-    o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3); o[2] = make_double2(a4, a5);
+    const size_t nP = sv.nPoints;
+    double* o = sv.P + p;
+    o[0] = a0; o[nP] = a1; o[2 * nP] = a2; o[3 * nP] = a3; o[4 * nP] = a4; o[5 * nP] = a5;
 }
 
 // boundary points from boundary-face values; onlyP: refresh p only (after the qgdFlux re-evaluation)
@@ -383,9 +405,11 @@ __global__ void k_patch_points(SolverView sv, BndState bs, int onlyP)
         const RecA r = bs.A[b];
         a0 += wq * r.rho; a1 += wq * r.Ux; a2 += wq * r.Uy; a3 += wq * r.Uz; a4 += wq * r.e; a5 += wq * bs.pNew[b];
     }
-    RecP* o = sv.P + sv.patchPoints[i];
-    if (onlyP) { o->p = a5; return; }
-    *o = RecP{a0, a1, a2, a3, a4, a5};
+    const size_t nP = sv.nPoints;
+    double* o = sv.P + sv.patchPoints[i];
+    o[5 * nP] = a5;
+    if (onlyP) return;
+    o[0] = a0; o[nP] = a1; o[2 * nP] = a2; o[3 * nP] = a3; o[4 * nP] = a4;
 }
 
 // boundary-face inputs shared by k_bnd_pre and k_bnd_flux
@@ -398,7 +422,7 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     const int P = fv.own[f];
     const RecA a = bs.A[b];
     const RecB bb = bs.B[b];
-    const RecA cA = loadA(sv.A, P);
+    const RecA cA = loadA(sv, P);
     const int flags = fv.flags[f];
     const double delta = fv.dC[f];
 #pragma unroll
@@ -442,8 +466,8 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
     if (flags & FF_POINTS) {
         const int4 v = fv.vtx[f];
-        d1 = recDiff(loadP(sv.P, v.x), loadP(sv.P, v.z));
-        d2 = recDiff(loadP(sv.P, v.y), loadP(sv.P, v.w));
+        d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
+        d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
     }
     // phiP - psiN, psiN = phi_b + snGrad_b*|d|/2   (GaussVolPointBase3D.C:790-793)
     RecP dP;
@@ -474,7 +498,7 @@ __global__ void k_bnd_pre(Consts k, FaceView fv, SolverView sv, BndState bs)
     if (bs.bcP[b] == QGD_BC_QGD_FLUX && !k.reducedScheme) {
         const double grad = -(phiw / bf.s.tau / fv.magSf[f]);     // qgdFluxFvPatchScalarField.C:184-192
         bs.pGrad[b] = grad;
-        pNew = loadA(sv.A, fv.own[f]).p + grad / fv.dC[f];
+        pNew = loadA(sv, fv.own[f]).p + grad / fv.dC[f];
     }
     bs.pNew[b] = pNew;
 }
@@ -501,25 +525,25 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
             tauMin = bf.s.tau;
         }
     }
-    blockReduceCo(coMax, tauMin, sv.sc);
+    blockReduceCo<kBlock>(coMax, tauMin, sv.sc);
 }
 
 // ---- the fused internal-face kernel
-template <bool ADJUST>
-__global__ void __launch_bounds__(kBlock) k_face_flux(Consts k, FaceView fv, SolverView sv)
+template <bool ADJUST, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv, SolverView sv)
 {
     double coMax = 0.0, tauMin = DBL_MAX;
     const size_t nF = fv.nF;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < fv.nI; f += gridDim.x * blockDim.x) {
         const int P = __ldg(&fv.own[f]), N = __ldg(&fv.nei[f]);
         const int flags = __ldg(&fv.flags[f]);
-        const RecA aP = loadA(sv.A, P), aN = loadA(sv.A, N);
-        const RecB bP = loadB(sv.B, P), bN = loadB(sv.B, N);
+        const RecA aP = loadA(sv, P), aN = loadA(sv, N);
+        const RecB bP = loadB(sv, P), bN = loadB(sv, N);
         RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
         if (flags & FF_POINTS) {
             const int4 v = __ldg(&fv.vtx[f]);
-            d1 = recDiff(loadP(sv.P, v.x), loadP(sv.P, v.z));
-            d2 = recDiff(loadP(sv.P, v.y), loadP(sv.P, v.w));
+            d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
+            d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
         }
         const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
         double g1[3], g2[3], gp[3], Sf[3];
@@ -568,7 +592,7 @@ __global__ void __launch_bounds__(kBlock) k_face_flux(Consts k, FaceView fv, Sol
             tauMin = fmin(tauMin, s.tau);
         }
     }
-    if (ADJUST) blockReduceCo(coMax, tauMin, sv.sc);
+    if (ADJUST) blockReduceCo<BLOCK>(coMax, tauMin, sv.sc);
 }
 
 // setDeltaT-QGDQHD.H:41-61 ; QGDCourantNo.H:47-50
@@ -591,7 +615,7 @@ __global__ void k_dt(StepScalars* sc)
 
 // per-cell closing of the step: new thermo state from (rho, U, rhoU, rhoE, e) and the OLD p, T
 __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const double (&U)[3], const double (&rhoU)[3], double rhoE,
-                                           double e, double pOld, double TOld, double aQGD, double hQGD, double* outA, double* outB)
+                                           double e, double pOld, double TOld, double aQGD, double hQGD, const SolverView& sv, int cell)
 {
     // hePsiQGDThermo::calculate  hePsiQGDThermo.C:48-64,123-124
     const double T = thermoTHE(k, e, TOld);
@@ -607,27 +631,37 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     const double H = (rhoE + p) / rho;                   // updateFields.H:71 (of the next step)
     const double a[8] = {rho, U[0], U[1], U[2], e, p, T, H};
     const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD / c};
-    storeRec(outA, a);
-    storeRec(outB, b);
+    storeRec(sv, 0, cell, a);
+    storeRec(sv, 8, cell, b);
 }
 
 __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nF)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= sv.nCells) return;
-    const RecA a = loadA(sv.A, c);
-    const RecB b = loadB(sv.B, c);
+    const RecA a = loadA(sv, c);
+    const RecB b = loadB(sv, c);
     double sm = 0.0, su0 = 0.0, su1 = 0.0, su2 = 0.0, se = 0.0;
     const int q0 = __ldg(&sv.cfOff[c]), q1 = __ldg(&sv.cfOff[c + 1]);
-    for (int q = q0; q < q1; ++q) {                      // fvc::surfaceIntegrate, ascending face order, no atomics
-        const int enc = __ldg(&sv.cfEnc[q]);
-        const int f = enc >> 1;
-        const double sgn = (enc & 1) ? -1.0 : 1.0;
-        sm += sgn * __ldg(&sv.Fm[f]);
-        su0 += sgn * __ldg(&sv.FU[f]);
-        su1 += sgn * __ldg(&sv.FU[(size_t)nF + f]);
-        su2 += sgn * __ldg(&sv.FU[2 * (size_t)nF + f]);
-        se += sgn * __ldg(&sv.FE[f]);
+    constexpr int FB = 3;                                // faces fetched per batch (all loads of a batch in flight together)
+    for (int qb = q0; qb < q1; qb += FB) {                // fvc::surfaceIntegrate, ascending face order, no atomics
+        int enc[FB];
+#pragma unroll
+        for (int j = 0; j < FB; ++j) enc[j] = (qb + j < q1) ? __ldg(&sv.cfEnc[qb + j]) : -1;
+        double fm[FB], f0[FB], f1[FB], f2[FB], fe[FB];
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+            if (enc[j] >= 0) {
+                const int f = enc[j] >> 1;
+                fm[j] = __ldg(&sv.Fm[f]); f0[j] = __ldg(&sv.FU[f]); f1[j] = __ldg(&sv.FU[(size_t)nF + f]);
+                f2[j] = __ldg(&sv.FU[2 * (size_t)nF + f]); fe[j] = __ldg(&sv.FE[f]);
+            } else { fm[j] = f0[j] = f1[j] = f2[j] = fe[j] = 0.0; }
+        }
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+            const double sgn = (enc[j] & 1) ? -1.0 : 1.0;
+            sm += sgn * fm[j]; su0 += sgn * f0[j]; su1 += sgn * f1[j]; su2 += sgn * f2[j]; se += sgn * fe[j];
+        }
     }
     const double V = __ldg(&sv.V[c]);
     const double rDeltaT = 1.0 / sv.sc->dt;
@@ -648,8 +682,7 @@ __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv,
     double e = rhoE / rho - 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
     const double ddt = k.energyQuirk ? (rDeltaT * (rhoE - b.rhoE)) : (rDeltaT * (rho * e - a.rho * a.e));
     e = (rDeltaT * a.rho * a.e * V + V * ddt) / diagR;
-    cellThermo(k, rho, U, rhoU, rhoE, e, a.p, a.T, __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]),
-               reinterpret_cast<double*>(sv.A + c), reinterpret_cast<double*>(sv.B + c));
+    cellThermo(k, rho, U, rhoU, rhoE, e, a.p, a.T, __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]), sv, c);
 }
 
 // boundary state after the cell update: the correctBoundaryConditions() sequence of QGDUEqn.H:51,88 ; QGDEEqn.H:50,75 ;
@@ -703,7 +736,7 @@ __global__ void k_bnd_post(Consts k, FaceView fv, SolverView sv, BndState bs)
     if (b >= fv.nB) return;
     if (fv.bKind[b] == QGD_PATCH_EMPTY) return;
     const int P = fv.own[fv.nI + b];
-    bndClose(k, fv, sv, bs, b, false, loadA(sv.A, P), sv.aQGD[P]);
+    bndClose(k, fv, sv, bs, b, false, loadA(sv, P), sv.aQGD[P]);
 }
 
 // ---- initialisation: QGDFoam/createFields.H:3-87 on the device
@@ -723,10 +756,9 @@ __global__ void k_init_cells(Consts k, SolverView sv, const double* __restrict__
     const double rhoU[3] = {rho * U[0], rho * U[1], rho * U[2]};
     const double rhoE = rho * e + rho * 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
     // cellThermo recomputes p = rho/psi; at start-up p is the field as read -> store explicitly afterwards
-    cellThermo(k, rho, U, rhoU, rhoE, e, p, T, sv.aQGD[c], sv.hQGD[c], reinterpret_cast<double*>(sv.A + c),
-               reinterpret_cast<double*>(sv.B + c));
-    sv.A[c].p = p;
-    sv.A[c].H = (rhoE + p) / rho;
+    cellThermo(k, rho, U, rhoU, rhoE, e, p, T, sv.aQGD[c], sv.hQGD[c], sv, c);
+    sv.S[5 * (size_t)sv.nCells + c] = p;
+    sv.S[7 * (size_t)sv.nCells + c] = (rhoE + p) / rho;
 }
 
 __global__ void k_init_bnd(Consts k, FaceView fv, SolverView sv, BndState bs, const double* __restrict__ T0)
@@ -736,7 +768,7 @@ __global__ void k_init_bnd(Consts k, FaceView fv, SolverView sv, BndState bs, co
     bs.pGrad[b] = 0.0; bs.phiw[b] = 0.0; bs.pNew[b] = 0.0; bs.psi[b] = 0.0;
     if (fv.bKind[b] == QGD_PATCH_EMPTY) { bs.A[b] = RecA{1, 0, 0, 0, 0, 0, 1, 0}; bs.B[b] = RecB{0, 0, 0, 0, 1, 0, 0, 0}; return; }
     const int P = fv.own[fv.nI + b];
-    RecA cA = loadA(sv.A, P);
+    RecA cA = loadA(sv, P);
     cA.T = T0[P];
     // boundary values of the fields as read: p_b (value / internal), then the common closing sequence
     RecA a{};
@@ -750,13 +782,24 @@ __global__ void k_init_bnd(Consts k, FaceView fv, SolverView sv, BndState bs, co
 // ============================================================================ launchers
 static inline int nblk(long n, int b = kBlock) { return (int)((n + b - 1) / b); }
 
+namespace {
+struct FaceVariant { int block; void (*fn[2])(Consts, FaceView, SolverView); };
+template <int BLOCK, int MINB> constexpr FaceVariant mkVariant() { return {BLOCK, {k_face_flux<false, BLOCK, MINB>, k_face_flux<true, BLOCK, MINB>}}; }
+const FaceVariant kFaceVariants[] = {mkVariant<256, 1>(), mkVariant<256, 2>(), mkVariant<128, 4>(), mkVariant<128, 5>(),
+                                     mkVariant<128, 6>(), mkVariant<64, 12>(), mkVariant<256, 3>()};
+int g_faceVariant = 1;
+}
+
+void setFaceVariant(int v) { if (v >= 0 && v < (int)(sizeof(kFaceVariants) / sizeof(kFaceVariants[0]))) g_faceVariant = v; }
+
 int faceKernelGrid()
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int perSM = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux<false>, kBlock, 0);
+    const FaceVariant& fvn = kFaceVariants[g_faceVariant];
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fvn.fn[0], fvn.block, 0);
     if (perSM < 1) perSM = 1;
     return sms * perSM;
 }
@@ -804,12 +847,14 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 }
 
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust)
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev)
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
     if (pointsNeeded) {
+        if (ev) cudaEventRecord(ev[0], st);
         k_points<<<nblk(sv.nPoints), kBlock, 0, st>>>(sv); ++n;
+        if (ev) cudaEventRecord(ev[1], st);
         if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
     }
     if (fv.nB && anyQgdFlux) {
@@ -817,14 +862,18 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
     }
     if (fv.nI) {
-        const int grid = std::min(gridFaces, nblk(fv.nI));
-        if (adjust) k_face_flux<true><<<grid, kBlock, 0, st>>>(c, fv, sv);
-        else k_face_flux<false><<<grid, kBlock, 0, st>>>(c, fv, sv);
+        const int grid = std::min(gridFaces, nblk(fv.nI, kFaceVariants[g_faceVariant].block));
+        if (ev) cudaEventRecord(ev[2], st);
+        const FaceVariant& fvn = kFaceVariants[g_faceVariant];
+        fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
         ++n;
+        if (ev) cudaEventRecord(ev[3], st);
     }
     if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     k_dt<<<1, 1, 0, st>>>(sv.sc); ++n;
+    if (ev) cudaEventRecord(ev[4], st);
     k_cell_update<<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF); ++n;
+    if (ev) cudaEventRecord(ev[5], st);
     if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     return n;
 }

@@ -58,8 +58,11 @@ void launchFvscDiv(cudaStream_t st, int K, const FaceView& fv, const double* cel
 // ---- QGDFoam step kernels
 struct SolverView {
     int nCells, nPoints, nPatchPoints;
-    RecA* A; RecB* B;            // cells
-    RecP* P;                     // points
+    // cell state, SoA: field k of cell c at S[k*nCells + c]; fields 0-7 = RecA (rho,Ux,Uy,Uz,e,p,T,H),
+    // 8-15 = RecB (rhoUx,rhoUy,rhoUz,rhoE,c,mu,alphaEff,aByC).  SoA keeps the owner-ordered gathers of the face
+    // kernel and the streaming point/cell kernels at one or two 128-B L1 wavefronts per warp-level load.
+    double* S;
+    double* P;                   // point values, SoA: field k (rho,Ux,Uy,Uz,e,p) of point i at P[k*nPoints + i]
     const int* pcOff; const int* pcCell; const double* pcW;
     const int* patchPoints; const int* ppOff; const int* ppFace; const double* ppW;
     const int* cfOff; const int* cfEnc;
@@ -71,8 +74,10 @@ struct SolverView {
 void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                 const double* U0, const double* T0, const double* p0);
 // one QGDFoam.C:90-163 loop body; returns number of kernel launches issued
+// ev (optional): 6 events recorded around k_points, k_face_flux, k_cell_update (begin/end pairs)
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust);
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr);
 int faceKernelGrid();
+void setFaceVariant(int v);   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
 } // namespace qgd

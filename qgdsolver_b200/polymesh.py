@@ -117,25 +117,31 @@ class PolyMesh:
         Cf = np.zeros((nF, 3))
         Sf = np.zeros((nF, 3))
         for n in np.unique(nv):
-            idx = np.nonzero(nv == n)[0]
-            v = self.face_verts[(self.face_offsets[idx][:, None] + np.arange(n)[None, :])]
+            if (nv == n).all():
+                idx = slice(None)
+                v = self.face_verts.reshape(-1, n)
+                cnt_n = nF
+            else:
+                idx = np.nonzero(nv == n)[0]
+                v = self.face_verts[(self.face_offsets[idx][:, None] + np.arange(n)[None, :])]
+                cnt_n = idx.size
             P = pts[v]                                   # (m,n,3)
             if n == 3:
                 Cf[idx] = (P[:, 0] + P[:, 1] + P[:, 2]) / 3.0
-                Sf[idx] = 0.5 * np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
+                Sf[idx] = 0.5 * _cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])
             else:
                 fC = P[:, 0].copy()
                 for k in range(1, n):
                     fC += P[:, k]
                 fC /= n
-                sumN = np.zeros((idx.size, 3))
-                sumA = np.zeros(idx.size)
-                sumAc = np.zeros((idx.size, 3))
+                sumN = np.zeros((cnt_n, 3))
+                sumA = np.zeros(cnt_n)
+                sumAc = np.zeros((cnt_n, 3))
                 for k in range(n):
                     p0 = P[:, k]
                     p1 = P[:, (k + 1) % n]
                     c = p0 + p1 + fC
-                    nn = np.cross(p1 - p0, fC - p0)
+                    nn = _cross(p1 - p0, fC - p0)
                     a = np.sqrt((nn * nn).sum(1))
                     sumN += nn
                     sumA += a
@@ -200,6 +206,14 @@ class PolyMesh:
         off = np.zeros(nC + 1, np.int64)
         np.cumsum(np.bincount(allc, minlength=nC), out=off[1:])
         return off.astype(np.int32), allf[order].astype(np.int32)
+
+
+def _cross(a, b):
+    out = np.empty_like(a)
+    out[:, 0] = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    out[:, 1] = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+    out[:, 2] = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+    return out
 
 
 # ---------------------------------------------------------------------- generators
@@ -280,16 +294,18 @@ def hex_box(nx: int, ny: int, nz: int,
     def zface(i, j, k):   # normal +z
         return np.stack([pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)], 1)
 
-    # internal faces: per owner cell in order, to +x, +y, +z neighbours
-    mx, my, mz = ic < nx - 1, jc < ny - 1, kc < nz - 1
-    fx = xface(ic[mx] + 1, jc[mx], kc[mx]); ox = cell[mx]; nxn = ox + 1
-    fy = yface(ic[my], jc[my] + 1, kc[my]); oy = cell[my]; nyn = oy + nx
-    fz = zface(ic[mz], jc[mz], kc[mz] + 1); oz = cell[mz]; nzn = oz + nx * ny
-    fi = np.concatenate([fx, fy, fz])
-    oi = np.concatenate([ox, oy, oz])
-    ni = np.concatenate([nxn, nyn, nzn])
-    order = np.lexsort((ni, oi))
-    fi, oi, ni = fi[order], oi[order], ni[order]
+    # internal faces: per owner cell in order, to +x, +y, +z neighbours (ascending neighbour => upper-triangular
+    # order falls out of a cell-major (cell, direction) layout without sorting)
+    nC = nx * ny * nz
+    valid = np.stack([ic < nx - 1, jc < ny - 1, kc < nz - 1], axis=1).reshape(-1)
+    fall = np.empty((nC, 3, 4), np.int32)
+    fall[:, 0] = xface(np.minimum(ic + 1, nx), jc, kc)
+    fall[:, 1] = yface(ic, np.minimum(jc + 1, ny), kc)
+    fall[:, 2] = zface(ic, jc, np.minimum(kc + 1, nz))
+    fi = fall.reshape(-1, 4)[valid]
+    del fall
+    oi = np.repeat(cell, 3)[valid]
+    ni = (cell[:, None] + np.array([1, nx, nx * ny])[None, :]).reshape(-1)[valid]
 
     # boundary faces (outward normals), ordered by owner cell inside each patch
     bfaces, bown, patches = [], [], []
