@@ -68,6 +68,7 @@ struct qgd_fvsc {
         if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
         v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
         v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
+        v.perm = m.facePermDev.p;
         return v;
     }
 };
@@ -97,9 +98,10 @@ struct qgd_solver {
         SolverView s;
         s.nCells = m.h.nCells; s.nPoints = m.h.nPoints; s.nPatchPoints = (int)m.h.patchPoints.size();
         s.S = S.p; s.P = P.p;
-        s.pcOff = m.pcOff.p; s.pcCell = m.pcCell.p; s.pcW = m.pcW.p;
+        s.pcEllW = m.pcEllW; s.pcEll = m.pcEll.p; s.pcEllWt = m.pcEllWt.p; s.pcCount = m.pcCount.p;
+        s.pcTailOff = m.pcTailOff.p; s.pcTailCell = m.pcTailCell.p; s.pcTailW = m.pcTailW.p;
         s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
-        s.cfOff = m.cfOff.p; s.cfEnc = m.cfEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
+        s.cfEllW = m.cfEllW; s.cfEll = m.cfEll.p; s.cfTailOff = m.cfTailOff.p; s.cfTailEnc = m.cfTailEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
         s.Fm = Fm.p; s.FU = FU.p; s.FE = FE.p; s.sc = sc.p;
         return s;
     }
@@ -222,21 +224,83 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         std::unique_ptr<qgd_mesh> m(new qgd_mesh());
         m->h.build(*desc);
         const HostMesh& h = m->h;
-        m->owner.upload(h.owner, g_stream); m->neighbour.upload(h.neighbour, g_stream);
-        m->cfOff.upload(h.cfOff, g_stream); m->cfEnc.upload(h.cfEnc, g_stream);
-        m->pcOff.upload(h.pcOff, g_stream); m->pcCell.upload(h.pcCell, g_stream); m->pcW.upload(h.pcW, g_stream);
+        const int nF = h.nFaces, nI = h.nInternal;
+        // ---- device face order (env QGD_FACE_TILE: owners per tile, 0 keeps the polyMesh order)
+        int tile = 32;
+        if (const char* v = getenv("QGD_FACE_TILE")) tile = atoi(v);
+        m->facePerm.resize(nF);
+        for (int f = 0; f < nF; ++f) m->facePerm[f] = f;
+        if (tile > 0 && nI > 0) {
+            // rank of each internal face among the faces owned by its owner (faces are owner-sorted: upper-triangular order)
+            std::vector<int> rank(nI, 0);
+            for (int f = 1; f < nI; ++f) rank[f] = (h.owner[f] == h.owner[f - 1]) ? rank[f - 1] + 1 : 0;
+            std::stable_sort(m->facePerm.begin(), m->facePerm.begin() + nI, [&](int a, int b) {
+                const int ta = h.owner[a] / tile, tb = h.owner[b] / tile;
+                if (ta != tb) return ta < tb;
+                if (rank[a] != rank[b]) return rank[a] < rank[b];
+                return h.owner[a] < h.owner[b];
+            });
+        }
+        m->faceInv.resize(nF);
+        for (int f = 0; f < nF; ++f) m->faceInv[m->facePerm[f]] = f;
+        const std::vector<int>& perm = m->facePerm;
+        auto permI = [&](const std::vector<int>& v, int n) { std::vector<int> o(n); for (int f = 0; f < n; ++f) o[f] = v[perm[f]]; return o; };
+        auto permD = [&](const std::vector<double>& v) { std::vector<double> o(nF); for (int f = 0; f < nF; ++f) o[f] = v[perm[f]]; return o; };
+        m->facePermDev.upload(perm, g_stream);
+        m->owner.upload(permI(h.owner, nF), g_stream); m->neighbour.upload(permI(h.neighbour, nI), g_stream);
+        // ---- cell -> faces ELL (+ tail), device face ids, polyMesh ascending order inside each row
+        {
+            int maxRow = 0;
+            for (int c = 0; c < h.nCells; ++c) maxRow = std::max(maxRow, h.cfOff[c + 1] - h.cfOff[c]);
+            const int W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+            m->cfEllW = W;
+            std::vector<int> ell((size_t)W * h.nCells, -1), tailOff(h.nCells + 1, 0), tail;
+            for (int c = 0; c < h.nCells; ++c) {
+                int j = 0;
+                for (int q = h.cfOff[c]; q < h.cfOff[c + 1]; ++q, ++j) {
+                    const int enc = (m->faceInv[h.cfEnc[q] >> 1] << 1) | (h.cfEnc[q] & 1);
+                    if (j < W) ell[(size_t)j * h.nCells + c] = enc; else tail.push_back(enc);
+                }
+                tailOff[c + 1] = (int)tail.size();
+            }
+            if (tail.empty()) tail.push_back(-1);
+            m->cfEll.upload(ell, g_stream); m->cfTailOff.upload(tailOff, g_stream); m->cfTailEnc.upload(tail, g_stream);
+        }
+        // ---- point -> cells ELL (+ tail)
+        {
+            int maxRow = 0;
+            for (int p = 0; p < h.nPoints; ++p) maxRow = std::max(maxRow, h.pcOff[p + 1] - h.pcOff[p]);
+            const int W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+            m->pcEllW = W;
+            std::vector<int> ell((size_t)W * h.nPoints, 0), cnt(h.nPoints, 0), tailOff(h.nPoints + 1, 0), tailC;
+            std::vector<double> ellW((size_t)W * h.nPoints, 0.0), tailW;
+            for (int p = 0; p < h.nPoints; ++p) {
+                cnt[p] = h.pcOff[p + 1] - h.pcOff[p];
+                const int first = cnt[p] ? h.pcCell[h.pcOff[p]] : 0;
+                for (int j = 0; j < W; ++j) ell[(size_t)j * h.nPoints + p] = first;
+                int j = 0;
+                for (int q = h.pcOff[p]; q < h.pcOff[p + 1]; ++q, ++j) {
+                    if (j < W) { ell[(size_t)j * h.nPoints + p] = h.pcCell[q]; ellW[(size_t)j * h.nPoints + p] = h.pcW[q]; }
+                    else { tailC.push_back(h.pcCell[q]); tailW.push_back(h.pcW[q]); }
+                }
+                tailOff[p + 1] = (int)tailC.size();
+            }
+            if (tailC.empty()) { tailC.push_back(0); tailW.push_back(0.0); }
+            m->pcEll.upload(ell, g_stream); m->pcEllWt.upload(ellW, g_stream); m->pcCount.upload(cnt, g_stream);
+            m->pcTailOff.upload(tailOff, g_stream); m->pcTailCell.upload(tailC, g_stream); m->pcTailW.upload(tailW, g_stream);
+        }
         m->patchPoints.upload(h.patchPoints, g_stream); m->ppOff.upload(h.ppOff, g_stream);
         m->ppFace.upload(h.ppFace, g_stream); m->ppW.upload(h.ppW, g_stream);
         std::vector<int> bk(h.nBnd);
         for (int b = 0; b < h.nBnd; ++b) bk[b] = h.patchKind[h.bfacePatch[b]];
         m->bfaceKind.upload(bk, g_stream);
-        std::vector<double> sfSoA(3 * (size_t)h.nFaces);
-        for (int f = 0; f < h.nFaces; ++f)
-            for (int d = 0; d < 3; ++d) sfSoA[(size_t)d * h.nFaces + f] = h.Sf[3 * (size_t)f + d];
+        std::vector<double> sfSoA(3 * (size_t)nF);
+        for (int f = 0; f < nF; ++f)
+            for (int d = 0; d < 3; ++d) sfSoA[(size_t)d * nF + f] = h.Sf[3 * (size_t)perm[f] + d];
         m->Sf.upload(sfSoA, g_stream);
-        m->magSf.upload(h.magSf, g_stream); m->w.upload(h.w, g_stream); m->dC.upload(h.dC, g_stream);
-        m->ndC.upload(h.ndC, g_stream); m->V.upload(h.V, g_stream);
-        m->hQGDf.upload(h.hQGDf, g_stream); m->hQGD.upload(h.hQGD, g_stream);
+        m->magSf.upload(permD(h.magSf), g_stream); m->w.upload(permD(h.w), g_stream); m->dC.upload(permD(h.dC), g_stream);
+        m->ndC.upload(permD(h.ndC), g_stream); m->V.upload(h.V, g_stream);
+        m->hQGDf.upload(permD(h.hQGDf), g_stream); m->hQGD.upload(h.hQGD, g_stream);
         *out = m.release();
     });
 }
@@ -247,7 +311,7 @@ int qgd_mesh_get(qgd_mesh* mesh, int what, double* out)
 {
     return guarded([&] {
         if (!mesh || !out) throw Error(QGD_ERR_INVALID, "qgd_mesh_get: null argument");
-        if (what == 0) { d2h(out, mesh->hQGDf.p, mesh->hQGDf.n); }
+        if (what == 0) std::copy(mesh->h.hQGDf.begin(), mesh->h.hQGDf.end(), out);
         else if (what == 1) { d2h(out, mesh->hQGD.p, mesh->hQGD.n); }
         else throw Error(QGD_ERR_INVALID, "qgd_mesh_get: unknown field id");
         QGD_CUDA(cudaStreamSynchronize(g_stream));
@@ -269,9 +333,18 @@ static void fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
     std::vector<int> vtx, flags;
     std::vector<double> G, hd;
     mesh->h.buildFaceRecords(op.reduced, vtx, flags, G, hd);
-    std::vector<int4> v4(mesh->h.nFaces);
-    for (int f = 0; f < mesh->h.nFaces; ++f) v4[f] = make_int4(vtx[4 * (size_t)f], vtx[4 * (size_t)f + 1], vtx[4 * (size_t)f + 2], vtx[4 * (size_t)f + 3]);
-    op.vtx.upload(v4, g_stream); op.flags.upload(flags, g_stream); op.G.upload(G, g_stream); op.halfDist.upload(hd, g_stream);
+    const int nF = mesh->h.nFaces;
+    const std::vector<int>& perm = mesh->facePerm;
+    std::vector<int4> v4(nF);
+    std::vector<int> fl(nF);
+    std::vector<double> Gp(G.size());
+    for (int f = 0; f < nF; ++f) {
+        const size_t o = perm[f];
+        v4[f] = make_int4(vtx[4 * o], vtx[4 * o + 1], vtx[4 * o + 2], vtx[4 * o + 3]);
+        fl[f] = flags[o];
+        for (int k = 0; k < 9; ++k) Gp[(size_t)k * nF + f] = G[(size_t)k * nF + o];
+    }
+    op.vtx.upload(v4, g_stream); op.flags.upload(fl, g_stream); op.G.upload(Gp, g_stream); op.halfDist.upload(hd, g_stream);
 }
 
 int qgd_fvsc_create(qgd_mesh* mesh, const char* scheme_name, qgd_fvsc** out)
@@ -527,15 +600,14 @@ int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out)
         requireInit();
         if (!s || !out) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: null argument");
         const size_t nF = s->mesh->h.nFaces;
-        if (which == 0) d2h(out, s->Fm.p, nF);
-        else if (which == 2) d2h(out, s->FE.p, nF);
-        else if (which == 1) {
-            std::vector<double> t(3 * nF);
-            d2h(t.data(), s->FU.p, 3 * nF);
-            QGD_CUDA(cudaStreamSynchronize(g_stream));
-            for (size_t f = 0; f < nF; ++f) for (int d = 0; d < 3; ++d) out[3 * f + d] = t[d * nF + f];
-        } else throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: unknown flux id");
+        const std::vector<int>& perm = s->mesh->facePerm;
+        const int k = (which == 1) ? 3 : 1;
+        const double* src = which == 0 ? s->Fm.p : (which == 1 ? s->FU.p : (which == 2 ? s->FE.p : nullptr));
+        if (!src) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: unknown flux id");
+        std::vector<double> t(k * nF);
+        d2h(t.data(), src, k * nF);
         QGD_CUDA(cudaStreamSynchronize(g_stream));
+        for (size_t f = 0; f < nF; ++f) for (int d = 0; d < k; ++d) out[(size_t)k * perm[f] + d] = t[d * nF + f];
     });
 }
 

@@ -95,8 +95,18 @@ struct HostMesh {
 struct qgd_mesh {
     qgd::HostMesh h;
     // device copies
-    qgd::DevBuf<int> owner, neighbour, cfOff, cfEnc, pcOff, pcCell, patchPoints, ppOff, ppFace, bfaceKind;
-    qgd::DevBuf<double> pcW, ppW;
+    // device face order: internal faces renumbered (tile, rank-in-owner, owner) so that a warp's faces have
+    // consecutive owners AND consecutive neighbours/vertices; boundary faces keep their polyMesh position.
+    std::vector<int> facePerm;     // device face -> polyMesh face
+    std::vector<int> faceInv;      // polyMesh face -> device face
+    qgd::DevBuf<int> facePermDev;
+    // ELL (column-major, width W) + CSR tail stencils: coalesced row access for thread-per-row kernels
+    int pcEllW = 8, cfEllW = 6;
+    qgd::DevBuf<int> pcEll, pcCount, pcTailOff, pcTailCell;      // point -> cells
+    qgd::DevBuf<double> pcEllWt, pcTailW;
+    qgd::DevBuf<int> cfEll, cfTailOff, cfTailEnc;                // cell -> faces, enc = (deviceFace<<1)|neighbourSide, -1 pad
+    qgd::DevBuf<int> owner, neighbour, patchPoints, ppOff, ppFace, bfaceKind;
+    qgd::DevBuf<double> ppW;
     qgd::DevBuf<double> Sf;        // SoA 3*nFaces
     qgd::DevBuf<double> magSf, w, dC, ndC, V, hQGDf, hQGD;
 };

@@ -70,22 +70,31 @@ __device__ __forceinline__ double thermoTHE(const Consts& k, double e, double T0
 
 // ============================================================================ generic fvsc operator kernels
 template <int K>
-__global__ void k_point_gather_generic(int nPoints, const int* __restrict__ pcOff, const int* __restrict__ pcCell,
-                                       const double* __restrict__ pcW, const double* __restrict__ cell, double* __restrict__ pts)
+__global__ void k_point_gather_generic(int nPoints, int W, const int* __restrict__ ell, const double* __restrict__ ellW,
+                                       const int* __restrict__ cnt, const int* __restrict__ tailOff,
+                                       const int* __restrict__ tailCell, const double* __restrict__ tailW,
+                                       const double* __restrict__ cell, double* __restrict__ pts)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nPoints) return;
-    const int b = pcOff[p], e = pcOff[p + 1];
-    if (b == e) return;                       // patch point: written by k_patch_point_gather_generic
+    const int n = cnt[p];
+    if (n == 0) return;                       // patch point: written by k_patch_point_gather_generic
     double acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = 0.0;
-    for (int q = b; q < e; ++q) {
-        const int c = pcCell[q];
-        const double wq = pcW[q];
+    for (int q = 0; q < W && q < n; ++q) {
+        const int c = ell[(size_t)q * nPoints + p];
+        const double wq = ellW[(size_t)q * nPoints + p];
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] += wq * __ldg(&cell[(size_t)c * K + j]);
     }
+    if (n > W)
+        for (int q = tailOff[p]; q < tailOff[p + 1]; ++q) {
+            const int c = tailCell[q];
+            const double wq = tailW[q];
+#pragma unroll
+            for (int j = 0; j < K; ++j) acc[j] += wq * __ldg(&cell[(size_t)c * K + j]);
+        }
 #pragma unroll
     for (int j = 0; j < K; ++j) pts[(size_t)p * K + j] = acc[j];
 }
@@ -152,7 +161,7 @@ __global__ void k_fvsc_grad(FaceView fv, const double* __restrict__ cell, const 
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= fv.nF) return;
-    double* o = out + (size_t)f * 3 * K;
+    double* o = out + (size_t)fv.perm[f] * 3 * K;
     const int flags = fv.flags[f];
     double g1[3], g2[3], gp[3];
 #pragma unroll
@@ -200,7 +209,7 @@ __global__ void k_fvsc_div(FaceView fv, const double* __restrict__ cell, const d
     constexpr int OK = K / 3;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= fv.nF) return;
-    double* o = out + (size_t)f * OK;
+    double* o = out + (size_t)fv.perm[f] * OK;
     const int flags = fv.flags[f];
     double g1[3], g2[3], gp[3];
 #pragma unroll
@@ -357,40 +366,44 @@ __device__ __forceinline__ void blockReduceCo(double coMax, double tauMin, StepS
     }
 }
 
-// ---- cell -> point gather of (rho,U,e,p)
+// ---- cell -> point gather of (rho,U,e,p); ELL rows: every index/weight load of a warp is one coalesced line
+template <int W>
 __global__ void __launch_bounds__(kBlock) k_points(SolverView sv)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= sv.nPoints) return;
-    const int b = sv.pcOff[p], e = sv.pcOff[p + 1];
-    if (b == e) return;
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-    for (int q0 = b; q0 < e; q0 += 8) {           // batches of 8: all indices, then all gathers in flight together
-        int ids[8];
-        double wq[8];
+    const int cnt = __ldg(&sv.pcCount[p]);
+    if (cnt == 0) return;                                   // patch point
+    const size_t nP = sv.nPoints, n = sv.nCells;
+    int ids[W];
+    double wq[W];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool ok = q0 + j < e;
-            ids[j] = ok ? __ldg(&sv.pcCell[q0 + j]) : -1;
-            wq[j] = ok ? __ldg(&sv.pcW[q0 + j]) : 0.0;
-        }
-        const size_t n = sv.nCells;
-        double v[8][6];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const double* r = sv.S + (ids[j] >= 0 ? ids[j] : 0);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) v[j][k] = __ldg(r + k * n);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            a0 += wq[j] * v[j][0]; a1 += wq[j] * v[j][1]; a2 += wq[j] * v[j][2]; a3 += wq[j] * v[j][3];
-            a4 += wq[j] * v[j][4]; a5 += wq[j] * v[j][5];
-        }
+    for (int j = 0; j < W; ++j) {
+        ids[j] = __ldg(&sv.pcEll[j * nP + p]);
+        wq[j] = __ldg(&sv.pcEllWt[j * nP + p]);            // padded entries: weight 0, id = first cell of the row
     }
-    const size_t nP = sv.nPoints;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    double v[W][6];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const double* r = sv.S + ids[j];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[j][k] = __ldg(r + k * n);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a[k] += wq[j] * v[j][k];
+    if (cnt > W)
+        for (int q = __ldg(&sv.pcTailOff[p]); q < __ldg(&sv.pcTailOff[p + 1]); ++q) {
+            const double* r = sv.S + __ldg(&sv.pcTailCell[q]);
+            const double w1 = __ldg(&sv.pcTailW[q]);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a[k] += w1 * __ldg(r + k * n);
+        }
     double* o = sv.P + p;
-    o[0] = a0; o[nP] = a1; o[2 * nP] = a2; o[3 * nP] = a3; o[4 * nP] = a4; o[5 * nP] = a5;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o[k * nP] = a[k];
 }
 
 // boundary points from boundary-face values; onlyP: refresh p only (after the qgdFlux re-evaluation)
@@ -534,16 +547,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
 {
     double coMax = 0.0, tauMin = DBL_MAX;
     const size_t nF = fv.nF;
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < fv.nI; f += gridDim.x * blockDim.x) {
-        const int P = __ldg(&fv.own[f]), N = __ldg(&fv.nei[f]);
-        const int flags = __ldg(&fv.flags[f]);
+    // software-pipelined indices: the addressing of face f+stride is fetched while face f is computed, so each
+    // iteration exposes one memory latency (the gathers), not two (indices -> gathers)
+    const int stride = gridDim.x * blockDim.x;
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    int P = 0, N = 0, flags = 0;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (f < fv.nI) { P = __ldg(&fv.own[f]); N = __ldg(&fv.nei[f]); flags = __ldg(&fv.flags[f]); v = __ldg(&fv.vtx[f]); }
+    for (; f < fv.nI; f += stride) {
         const RecA aP = loadA(sv, P), aN = loadA(sv, N);
         const RecB bP = loadB(sv, P), bN = loadB(sv, N);
         RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
         if (flags & FF_POINTS) {
-            const int4 v = __ldg(&fv.vtx[f]);
             d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
             d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
+        }
+        const int flagsCur = flags;
+        {
+            const int fn = f + stride;
+            if (fn < fv.nI) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
         }
         const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
         double g1[3], g2[3], gp[3], Sf[3];
@@ -555,7 +577,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
             Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
         }
         FaceGrads g;
-        gradsFromDiffs(g1, g2, gp, flags, d1, d2, dP, g);
+        gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
         // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
         const double w = __ldg(&fv.w[f]);
         FaceState s;
@@ -635,6 +657,7 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     storeRec(sv, 8, cell, b);
 }
 
+template <int W>
 __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nF)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -642,15 +665,14 @@ __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv,
     const RecA a = loadA(sv, c);
     const RecB b = loadB(sv, c);
     double sm = 0.0, su0 = 0.0, su1 = 0.0, su2 = 0.0, se = 0.0;
-    const int q0 = __ldg(&sv.cfOff[c]), q1 = __ldg(&sv.cfOff[c + 1]);
-    constexpr int FB = 3;                                // faces fetched per batch (all loads of a batch in flight together)
-    for (int qb = q0; qb < q1; qb += FB) {                // fvc::surfaceIntegrate, ascending face order, no atomics
-        int enc[FB];
+    // fvc::surfaceIntegrate: the cell's faces in ascending polyMesh order, no atomics (ELL row, then CSR tail)
+    int enc[W];
 #pragma unroll
-        for (int j = 0; j < FB; ++j) enc[j] = (qb + j < q1) ? __ldg(&sv.cfEnc[qb + j]) : -1;
-        double fm[FB], f0[FB], f1[FB], f2[FB], fe[FB];
+    for (int j = 0; j < W; ++j) enc[j] = __ldg(&sv.cfEll[(size_t)j * sv.nCells + c]);
+    {
+        double fm[W], f0[W], f1[W], f2[W], fe[W];
 #pragma unroll
-        for (int j = 0; j < FB; ++j) {
+        for (int j = 0; j < W; ++j) {
             if (enc[j] >= 0) {
                 const int f = enc[j] >> 1;
                 fm[j] = __ldg(&sv.Fm[f]); f0[j] = __ldg(&sv.FU[f]); f1[j] = __ldg(&sv.FU[(size_t)nF + f]);
@@ -658,11 +680,19 @@ __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv,
             } else { fm[j] = f0[j] = f1[j] = f2[j] = fe[j] = 0.0; }
         }
 #pragma unroll
-        for (int j = 0; j < FB; ++j) {
+        for (int j = 0; j < W; ++j) {
             const double sgn = (enc[j] & 1) ? -1.0 : 1.0;
             sm += sgn * fm[j]; su0 += sgn * f0[j]; su1 += sgn * f1[j]; su2 += sgn * f2[j]; se += sgn * fe[j];
         }
     }
+    if (enc[W - 1] >= 0)
+        for (int q = __ldg(&sv.cfTailOff[c]); q < __ldg(&sv.cfTailOff[c + 1]); ++q) {
+            const int e1 = __ldg(&sv.cfTailEnc[q]);
+            const int f = e1 >> 1;
+            const double sgn = (e1 & 1) ? -1.0 : 1.0;
+            sm += sgn * __ldg(&sv.Fm[f]); su0 += sgn * __ldg(&sv.FU[f]); su1 += sgn * __ldg(&sv.FU[(size_t)nF + f]);
+            su2 += sgn * __ldg(&sv.FU[2 * (size_t)nF + f]); se += sgn * __ldg(&sv.FE[f]);
+        }
     const double V = __ldg(&sv.V[c]);
     const double rDeltaT = 1.0 / sv.sc->dt;
     const double diag = rDeltaT * V;
@@ -808,7 +838,7 @@ void launchPointGather(cudaStream_t st, int K, const qgd_mesh& m, const double* 
 {
     const int nP = m.h.nPoints, nPP = (int)m.h.patchPoints.size();
 #define QGD_PG(KK)                                                                                                          \
-    k_point_gather_generic<KK><<<nblk(nP), kBlock, 0, st>>>(nP, m.pcOff.p, m.pcCell.p, m.pcW.p, cell, pts);                \
+    k_point_gather_generic<KK><<<nblk(nP), kBlock, 0, st>>>(nP, m.pcEllW, m.pcEll.p, m.pcEllWt.p, m.pcCount.p, m.pcTailOff.p, m.pcTailCell.p, m.pcTailW.p, cell, pts); \
     if (nPP) k_patch_point_gather_generic<KK><<<nblk(nPP), kBlock, 0, st>>>(nPP, m.patchPoints.p, m.ppOff.p, m.ppFace.p, m.ppW.p, bnd, pts);
     switch (K) {
         case 1: QGD_PG(1) break;
@@ -853,7 +883,10 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
     const bool pointsNeeded = !c.reducedScheme;
     if (pointsNeeded) {
         if (ev) cudaEventRecord(ev[0], st);
-        k_points<<<nblk(sv.nPoints), kBlock, 0, st>>>(sv); ++n;
+        if (sv.pcEllW == 4) k_points<4><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+        else if (sv.pcEllW == 6) k_points<6><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+        else k_points<8><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+        ++n;
         if (ev) cudaEventRecord(ev[1], st);
         if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
     }
@@ -872,7 +905,10 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
     if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     k_dt<<<1, 1, 0, st>>>(sv.sc); ++n;
     if (ev) cudaEventRecord(ev[4], st);
-    k_cell_update<<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF); ++n;
+    if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF);
+    else if (sv.cfEllW == 6) k_cell_update<6><<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF);
+    else k_cell_update<8><<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF);
+    ++n;
     if (ev) cudaEventRecord(ev[5], st);
     if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     return n;

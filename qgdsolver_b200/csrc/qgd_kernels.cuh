@@ -25,6 +25,7 @@ struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     const double* G;         // SoA 9*nF
     const double* halfDist;  // nB
     const int* bKind;        // nB patch kind per boundary face
+    const int* perm;         // nF device face -> polyMesh face (operator outputs are written in polyMesh order)
 };
 
 struct BndState {            // per boundary face
@@ -63,9 +64,11 @@ struct SolverView {
     // kernel and the streaming point/cell kernels at one or two 128-B L1 wavefronts per warp-level load.
     double* S;
     double* P;                   // point values, SoA: field k (rho,Ux,Uy,Uz,e,p) of point i at P[k*nPoints + i]
-    const int* pcOff; const int* pcCell; const double* pcW;
+    int pcEllW; const int* pcEll; const double* pcEllWt; const int* pcCount;   // ELL point -> cells [W][nPoints]
+    const int* pcTailOff; const int* pcTailCell; const double* pcTailW;        // CSR tail for rows longer than W
     const int* patchPoints; const int* ppOff; const int* ppFace; const double* ppW;
-    const int* cfOff; const int* cfEnc;
+    int cfEllW; const int* cfEll;                                              // ELL cell -> faces [W][nCells], -1 pad
+    const int* cfTailOff; const int* cfTailEnc;
     const double* V; const double* hQGD; const double* aQGD;
     double* Fm; double* FU; double* FE;   // face fluxes, SoA: Fm[nF], FU[3*nF], FE[nF]
     StepScalars* sc;
