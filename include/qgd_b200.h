@@ -78,6 +78,11 @@ typedef struct {
     const double* nonOrthDeltaCoeffs;  /* n_faces                                                   */
     const double* neighb_cell_centres; /* n_bnd*3, processor patches: neighbFaceCellCentres() or NULL */
     int geometric_d[3];                /* fvMesh::geometricD()                                      */
+    /* multi-GPU extended sub-mesh (qgdsolver_b200/decompose.py): cells [0,n_owned_cells) are owned by this
+     * rank, the rest are halo copies; internal faces flagged here join an owned and a halo cell and follow the
+     * reference's processor-patch rules (hQGDf = 1/deltaCoeffs, QGDCoeffs.C:195-199,310-317).  0 / NULL = serial. */
+    int n_owned_cells;
+    const int* coupled_internal_face;  /* n_internal_faces flags or NULL                             */
 } qgd_mesh_desc;
 
 int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out);
@@ -175,6 +180,21 @@ int qgd_qgdfoam_kernel_times(qgd_solver* s, double* ms_points, double* ms_face, 
 /* CUDA-event timing of the device step loop: call begin, steps, end -> milliseconds on the solver stream */
 int qgd_timer_begin(void);
 int qgd_timer_end(float* ms);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink replaces Pstream ------------------
+ * qgd_comm_unique_id: rank 0 creates the 128-byte NCCL id, the launcher broadcasts it (torch.distributed / MPI).
+ * qgd_comm_init: every rank, after qgd_init.  qgd_qgdfoam_set_halo: exchange lists of this rank's extended sub-mesh:
+ * for neighbour k (rank nbr_rank[k]) cells  send_cells[send_cell_off[k] .. send_cell_off[k+1])  are packed and sent,
+ * and the received block is scattered to recv_cells[...]; same for the boundary-face state of physical boundary
+ * faces of halo cells (boundary-face indices = face - n_internal_faces).  Order on both sides: ascending global id.
+ * After set_halo every qgd_qgdfoam_step does: cell update -> ONE packed exchange (16 doubles/cell, 20/boundary face)
+ * -> next step; with adjust_time_step the Courant max / tau min are all-reduced on the device before k_dt. */
+int qgd_comm_unique_id(void* out128);
+int qgd_comm_init(int rank, int n_ranks, const void* id128);
+int qgd_comm_finalize(void);
+int qgd_qgdfoam_set_halo(qgd_solver* s, int n_neighbours, const int* nbr_rank,
+                         const int* send_cell_off, const int* send_cells, const int* recv_cell_off, const int* recv_cells,
+                         const int* send_bf_off, const int* send_bfaces, const int* recv_bf_off, const int* recv_bfaces);
 
 /* ---- LDU PCG (QHDpEqn.H:45 -> lduMatrix::solver PCG + DIC|diagonal) ---------- */
 /* symmetric LDU matrix on the mesh addressing (lower == upper); precond: 0 none, 1 diagonal (Jacobi),

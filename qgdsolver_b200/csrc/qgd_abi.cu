@@ -4,6 +4,9 @@
 #include <cfloat>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <memory>
 
 #include "qgd_kernels.cuh"
@@ -16,6 +19,49 @@ void setLastError(const std::string& m) { g_lastError = m; }
 static cudaStream_t g_stream = nullptr;
 static bool g_initialised = false;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+
+// ---- NCCL, bound at run time (dlopen) so that single-GPU users need no NCCL and the copy already loaded by the
+// launcher process (e.g. torch's) is reused
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static ncclComm_t g_comm = nullptr;
+static int g_rank = 0, g_nranks = 1;
+
+static void loadNccl()
+{
+    if (g_nccl.lib) return;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) throw Error(QGD_ERR_COMM, std::string("cannot load libnccl: ") + dlerror());
+    auto sym = [&](const char* n) { void* p = dlsym(g_nccl.lib, n); if (!p) throw Error(QGD_ERR_COMM, std::string("libnccl lacks ") + n); return p; };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+}
+#define QGD_NCCL(expr)                                                                                        \
+    do {                                                                                                      \
+        ncclResult_t _r = (expr);                                                                             \
+        if (_r != ncclSuccess)                                                                                \
+            throw qgd::Error(QGD_ERR_COMM, std::string("NCCL error: ") + g_nccl.GetErrorString(_r) + " at " + \
+                                               __FILE__ + ":" + std::to_string(__LINE__));                    \
+    } while (0)
 
 static void requireInit()
 {
@@ -64,6 +110,7 @@ struct qgd_fvsc {
         const qgd_mesh& m = *mesh;
         FaceView v;
         v.nI = m.h.nInternal; v.nF = m.h.nFaces; v.nB = m.h.nBnd;
+        v.nIActive = m.nIActive;
         v.zeroDivCmpt = -1;
         if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
         v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
@@ -87,6 +134,14 @@ struct qgd_solver {
     long long launches = 0;
     bool anyQgdFlux = false, bcsSet = false, fieldsSet = false;
     int gridFaces = 148;
+    // halo exchange (multi-GPU): per neighbour rank, contiguous slices of the id lists / buffers
+    struct Halo {
+        std::vector<int> nbr, sendCellOff, recvCellOff, sendBfOff, recvBfOff;
+        DevBuf<int> sendCells, recvCells, sendBf, recvBf;
+        DevBuf<double> sendBuf, recvBuf;      // [cells: 16 doubles each][bfaces: 20 doubles each] per neighbour
+        DevBuf<double> midSend, midRecv;      // p_b of halo boundary faces (qgdFlux mid-step refresh)
+        bool active = false;
+    } halo;
     // per-kernel CUDA-event timing (bench): events of the profiled steps, 6 per step
     bool profiling = false;
     std::vector<cudaEvent_t> events;
@@ -97,6 +152,7 @@ struct qgd_solver {
         const qgd_mesh& m = *mesh;
         SolverView s;
         s.nCells = m.h.nCells; s.nPoints = m.h.nPoints; s.nPatchPoints = (int)m.h.patchPoints.size();
+        s.nOwned = m.h.nOwned;
         s.S = S.p; s.P = P.p;
         s.pcEllW = m.pcEllW; s.pcEll = m.pcEll.p; s.pcEllWt = m.pcEllWt.p; s.pcCount = m.pcCount.p;
         s.pcTailOff = m.pcTailOff.p; s.pcTailCell = m.pcTailCell.p; s.pcTailW = m.pcTailW.p;
@@ -156,11 +212,138 @@ __global__ void k_unpack_state(int n, const double* __restrict__ S, double* st)
     st[10 * N + c] = S[11 * N + c]; st[11 * N + c] = S[13 * N + c];
 }
 
+// ---- halo exchange: pack (gather) -> ncclSend/ncclRecv in one group -> unpack (scatter)
+constexpr int kCellDoubles = 16, kBfDoubles = 20;
+__global__ void k_halo_pack(int nC, const int* __restrict__ cells, int nB, const int* __restrict__ bfaces, const double* __restrict__ S,
+                            size_t nCells, const RecA* __restrict__ bA, const RecB* __restrict__ bB, const double* __restrict__ psi,
+                            const double* __restrict__ pGrad, const double* __restrict__ pNew, const double* __restrict__ phiw,
+                            double* __restrict__ buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nC) {
+        const int c = cells[i];
+#pragma unroll
+        for (int k = 0; k < kCellDoubles; ++k) buf[(size_t)k * nC + i] = S[(size_t)k * nCells + c];
+    } else if (i < nC + nB) {
+        const int j = i - nC;
+        const int b = bfaces[j];
+        double* o = buf + (size_t)kCellDoubles * nC + (size_t)j * kBfDoubles;
+        const double* a = reinterpret_cast<const double*>(bA + b);
+        const double* bb = reinterpret_cast<const double*>(bB + b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { o[k] = a[k]; o[8 + k] = bb[k]; }
+        o[16] = psi[b]; o[17] = pGrad[b]; o[18] = pNew[b]; o[19] = phiw[b];
+    }
+}
+__global__ void k_halo_unpack(int nC, const int* __restrict__ cells, int nB, const int* __restrict__ bfaces, double* __restrict__ S,
+                              size_t nCells, RecA* __restrict__ bA, RecB* __restrict__ bB, double* __restrict__ psi,
+                              double* __restrict__ pGrad, double* __restrict__ pNew, double* __restrict__ phiw,
+                              const double* __restrict__ buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nC) {
+        const int c = cells[i];
+#pragma unroll
+        for (int k = 0; k < kCellDoubles; ++k) S[(size_t)k * nCells + c] = buf[(size_t)k * nC + i];
+    } else if (i < nC + nB) {
+        const int j = i - nC;
+        const int b = bfaces[j];
+        const double* o = buf + (size_t)kCellDoubles * nC + (size_t)j * kBfDoubles;
+        double* a = reinterpret_cast<double*>(bA + b);
+        double* bb = reinterpret_cast<double*>(bB + b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] = o[k]; bb[k] = o[8 + k]; }
+        psi[b] = o[16]; pGrad[b] = o[17]; pNew[b] = o[18]; phiw[b] = o[19];
+    }
+}
+__global__ void k_gather1(int n, const int* __restrict__ ids, const double* __restrict__ src, double* __restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[ids[i]];
+}
+__global__ void k_scatter1(int n, const int* __restrict__ ids, const double* __restrict__ src, double* __restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[ids[i]] = src[i];
+}
+
+// full state exchange after the cell update (SURVEY 5.8 C1+C3 in one message per neighbour)
+int haloExchange(qgd_solver* s)
+{
+    qgd_solver::Halo& h = s->halo;
+    if (!h.active) return 0;
+    const size_t nCells = s->mesh->h.nCells;
+    const int nn = (int)h.nbr.size();
+    int launches = 0;
+    auto blockOff = [&](const std::vector<int>& cOff, const std::vector<int>& bOff, int k) {
+        return (size_t)kCellDoubles * cOff[k] + (size_t)kBfDoubles * bOff[k];
+    };
+    for (int k = 0; k < nn; ++k) {
+        const int nC = h.sendCellOff[k + 1] - h.sendCellOff[k], nB = h.sendBfOff[k + 1] - h.sendBfOff[k];
+        if (nC + nB == 0) continue;
+        k_halo_pack<<<(nC + nB + 255) / 256, 256, 0, g_stream>>>(nC, h.sendCells.p + h.sendCellOff[k], nB, h.sendBf.p + h.sendBfOff[k],
+                                                                  s->S.p, nCells, s->bA.p, s->bB.p, s->psiB.p, s->pGrad.p, s->pNew.p,
+                                                                  s->phiw.p, h.sendBuf.p + blockOff(h.sendCellOff, h.sendBfOff, k));
+        ++launches;
+    }
+    QGD_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < nn; ++k) {
+        const size_t ns = blockOff(h.sendCellOff, h.sendBfOff, k + 1) - blockOff(h.sendCellOff, h.sendBfOff, k);
+        const size_t nr = blockOff(h.recvCellOff, h.recvBfOff, k + 1) - blockOff(h.recvCellOff, h.recvBfOff, k);
+        if (ns) QGD_NCCL(g_nccl.Send(h.sendBuf.p + blockOff(h.sendCellOff, h.sendBfOff, k), ns, ncclDouble, h.nbr[k], g_comm, g_stream));
+        if (nr) QGD_NCCL(g_nccl.Recv(h.recvBuf.p + blockOff(h.recvCellOff, h.recvBfOff, k), nr, ncclDouble, h.nbr[k], g_comm, g_stream));
+    }
+    QGD_NCCL(g_nccl.GroupEnd());
+    for (int k = 0; k < nn; ++k) {
+        const int nC = h.recvCellOff[k + 1] - h.recvCellOff[k], nB = h.recvBfOff[k + 1] - h.recvBfOff[k];
+        if (nC + nB == 0) continue;
+        k_halo_unpack<<<(nC + nB + 255) / 256, 256, 0, g_stream>>>(nC, h.recvCells.p + h.recvCellOff[k], nB, h.recvBf.p + h.recvBfOff[k],
+                                                                    s->S.p, nCells, s->bA.p, s->bB.p, s->psiB.p, s->pGrad.p, s->pNew.p,
+                                                                    s->phiw.p, h.recvBuf.p + blockOff(h.recvCellOff, h.recvBfOff, k));
+        ++launches;
+    }
+    return launches;
+}
+
+// mid-step refresh of p_b on halo boundary faces after the qgdFlux re-evaluation (QGDFoam/updateFluxes.H:63-65)
+int haloExchangeMid(qgd_solver* s)
+{
+    qgd_solver::Halo& h = s->halo;
+    if (!h.active) return 0;
+    const int nn = (int)h.nbr.size();
+    int launches = 0;
+    const int nS = h.sendBfOff[nn], nR = h.recvBfOff[nn];
+    if (nS) { k_gather1<<<(nS + 255) / 256, 256, 0, g_stream>>>(nS, h.sendBf.p, s->pNew.p, h.midSend.p); ++launches; }
+    QGD_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < nn; ++k) {
+        const int ns = h.sendBfOff[k + 1] - h.sendBfOff[k], nr = h.recvBfOff[k + 1] - h.recvBfOff[k];
+        if (ns) QGD_NCCL(g_nccl.Send(h.midSend.p + h.sendBfOff[k], ns, ncclDouble, h.nbr[k], g_comm, g_stream));
+        if (nr) QGD_NCCL(g_nccl.Recv(h.midRecv.p + h.recvBfOff[k], nr, ncclDouble, h.nbr[k], g_comm, g_stream));
+    }
+    QGD_NCCL(g_nccl.GroupEnd());
+    if (nR) { k_scatter1<<<(nR + 255) / 256, 256, 0, g_stream>>>(nR, h.recvBf.p, h.midRecv.p, s->pNew.p); ++launches; }
+    return launches;
+}
+
 void runSteps(qgd_solver* s, int n)
 {
     const FaceView fv = s->fvsc->view();
     const SolverView sv = s->sview();
     const BndState bs = s->bview();
+    StepHooks hooks;
+    const bool multi = s->halo.active && g_nranks > 1;
+    if (multi) {
+        hooks.midStep = [s] { s->launches += haloExchangeMid(s); };
+        if (s->desc.adjust_time_step)
+            hooks.beforeDt = [s] {
+                // Courant max / tau min over all ranks, on the device (gMax/gMin of QGDCourantNo.H:50, setDeltaT-QGDQHD.H:46)
+                StepScalars* sc = s->sc.p;
+                QGD_NCCL(g_nccl.GroupStart());
+                QGD_NCCL(g_nccl.AllReduce(&sc->coMaxBits, &sc->coMaxBits, 1, ncclDouble, ncclMax, g_comm, g_stream));
+                QGD_NCCL(g_nccl.AllReduce(&sc->tauMinBits, &sc->tauMinBits, 1, ncclDouble, ncclMin, g_comm, g_stream));
+                QGD_NCCL(g_nccl.GroupEnd());
+            };
+    }
     for (int i = 0; i < n; ++i) {
         cudaEvent_t* ev = nullptr;
         if (s->profiling) {
@@ -169,7 +352,9 @@ void runSteps(qgd_solver* s, int n)
             ev = &s->events[s->eventsUsed];
             s->eventsUsed += 6;
         }
-        s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev);
+        s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev,
+                                  multi ? &hooks : nullptr);
+        if (multi) s->launches += haloExchange(s);
     }
     QGD_CUDA(cudaGetLastError());
 }
@@ -234,13 +419,18 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
             // rank of each internal face among the faces owned by its owner (faces are owner-sorted: upper-triangular order)
             std::vector<int> rank(nI, 0);
             for (int f = 1; f < nI; ++f) rank[f] = (h.owner[f] == h.owner[f - 1]) ? rank[f - 1] + 1 : 0;
+            const int nOwn = h.nOwned;
             std::stable_sort(m->facePerm.begin(), m->facePerm.begin() + nI, [&](int a, int b) {
+                const bool ha = h.owner[a] >= nOwn, hb = h.owner[b] >= nOwn;      // halo-owned faces last (never computed)
+                if (ha != hb) return hb;
                 const int ta = h.owner[a] / tile, tb = h.owner[b] / tile;
                 if (ta != tb) return ta < tb;
                 if (rank[a] != rank[b]) return rank[a] < rank[b];
                 return h.owner[a] < h.owner[b];
             });
         }
+        m->nIActive = 0;
+        for (int f = 0; f < nI; ++f) if (h.owner[m->facePerm[f]] < h.nOwned) m->nIActive = f + 1;
         m->faceInv.resize(nF);
         for (int f = 0; f < nF; ++f) m->faceInv[m->facePerm[f]] = f;
         const std::vector<int>& perm = m->facePerm;
@@ -656,6 +846,69 @@ int qgd_qgdfoam_kernel_times(qgd_solver* s, double* ms_points, double* ms_face, 
         if (ms_face) *ms_face = t[1];
         if (ms_cell) *ms_cell = t[2];
         if (n_steps) *n_steps = (int)steps;
+    });
+}
+
+int qgd_comm_unique_id(void* out128)
+{
+    return guarded([&] {
+        if (!out128) throw Error(QGD_ERR_INVALID, "qgd_comm_unique_id: null buffer");
+        loadNccl();
+        ncclUniqueId id;
+        QGD_NCCL(g_nccl.GetUniqueId(&id));
+        static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id is 128 bytes");
+        std::memcpy(out128, &id, sizeof(id));
+    });
+}
+
+int qgd_comm_init(int rank, int n_ranks, const void* id128)
+{
+    return guarded([&] {
+        requireInit();
+        if (!id128 || n_ranks < 1 || rank < 0 || rank >= n_ranks) throw Error(QGD_ERR_INVALID, "qgd_comm_init: bad arguments");
+        loadNccl();
+        ncclUniqueId id;
+        std::memcpy(&id, id128, sizeof(id));
+        QGD_NCCL(g_nccl.CommInitRank(&g_comm, n_ranks, id, rank));
+        g_rank = rank; g_nranks = n_ranks;
+    });
+}
+
+int qgd_comm_finalize(void)
+{
+    return guarded([&] {
+        if (g_comm) { cudaStreamSynchronize(g_stream); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+        g_nranks = 1; g_rank = 0;
+    });
+}
+
+int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* send_cell_off, const int* send_cells,
+                         const int* recv_cell_off, const int* recv_cells, const int* send_bf_off, const int* send_bfaces,
+                         const int* recv_bf_off, const int* recv_bfaces)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || nn < 0) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_halo: bad arguments");
+        if (nn > 0 && !g_comm) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_halo: call qgd_comm_init first");
+        qgd_solver::Halo& h = s->halo;
+        h.nbr.assign(nbr_rank, nbr_rank + nn);
+        h.sendCellOff.assign(send_cell_off, send_cell_off + nn + 1); h.recvCellOff.assign(recv_cell_off, recv_cell_off + nn + 1);
+        h.sendBfOff.assign(send_bf_off, send_bf_off + nn + 1); h.recvBfOff.assign(recv_bf_off, recv_bf_off + nn + 1);
+        const HostMesh& hm = s->mesh->h;
+        auto check = [&](const int* ids, int n, int lo, int hi, const char* what) {
+            for (int i = 0; i < n; ++i) if (ids[i] < lo || ids[i] >= hi) throw Error(QGD_ERR_INVALID, std::string("qgd_qgdfoam_set_halo: ") + what + " out of range");
+        };
+        check(send_cells, h.sendCellOff[nn], 0, hm.nOwned, "send cell");
+        check(recv_cells, h.recvCellOff[nn], hm.nOwned, hm.nCells, "recv cell");
+        check(send_bfaces, h.sendBfOff[nn], 0, hm.nBnd, "send boundary face");
+        check(recv_bfaces, h.recvBfOff[nn], 0, hm.nBnd, "recv boundary face");
+        auto up = [&](DevBuf<int>& d, const int* p, int n) { std::vector<int> v(p, p + n); if (v.empty()) v.push_back(0); d.upload(v, g_stream); };
+        up(h.sendCells, send_cells, h.sendCellOff[nn]); up(h.recvCells, recv_cells, h.recvCellOff[nn]);
+        up(h.sendBf, send_bfaces, h.sendBfOff[nn]); up(h.recvBf, recv_bfaces, h.recvBfOff[nn]);
+        h.sendBuf.alloc((size_t)kCellDoubles * h.sendCellOff[nn] + (size_t)kBfDoubles * h.sendBfOff[nn] + 1);
+        h.recvBuf.alloc((size_t)kCellDoubles * h.recvCellOff[nn] + (size_t)kBfDoubles * h.recvBfOff[nn] + 1);
+        h.midSend.alloc(h.sendBfOff[nn] + 1); h.midRecv.alloc(h.recvBfOff[nn] + 1);
+        h.active = nn > 0;
     });
 }
 

@@ -41,6 +41,8 @@ void HostMesh::build(const qgd_mesh_desc& d)
     nBnd = nFaces - nInternal;
     for (int i = 0; i < 3; ++i) gD[i] = d.geometric_d[i];
     nD = (gD[0] > 0) + (gD[1] > 0) + (gD[2] > 0);
+    nOwned = (d.n_owned_cells > 0 && d.n_owned_cells <= nCells) ? d.n_owned_cells : nCells;
+    if (d.coupled_internal_face) coupledFace.assign(d.coupled_internal_face, d.coupled_internal_face + nInternal);
     points.assign(d.points, d.points + 3 * (size_t)nPoints);
     faceOff.assign(d.face_offsets, d.face_offsets + nFaces + 1);
     faceVerts.assign(d.face_verts, d.face_verts + faceOff[nFaces]);
@@ -165,6 +167,7 @@ void HostMesh::build(const qgd_mesh_desc& d)
     for (int f = 0; f < nInternal; ++f) {
         const Vec3 cf = at(Cf, f);
         hQGDf[f] = 2.0 * std::min(norm3(sub(at(C, owner[f]), cf)), norm3(sub(at(C, neighbour[f]), cf)));
+        if (!coupledFace.empty() && coupledFace[f]) hQGDf[f] = 1.0 / std::fabs(dC[f]);   // processor-patch rule
     }
     for (int b = 0; b < nBnd; ++b) {
         const int f = nInternal + b;

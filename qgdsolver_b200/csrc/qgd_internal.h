@@ -71,6 +71,8 @@ struct HostMesh {
     int nCells = 0, nFaces = 0, nInternal = 0, nPoints = 0, nPatches = 0, nBnd = 0;
     int nD = 3;
     int gD[3] = {1, 1, 1};
+    int nOwned = 0;                                // cells owned by this rank (== nCells in serial runs)
+    std::vector<int> coupledFace;                  // internal faces joining an owned and a halo cell (may be empty)
     std::vector<double> points, C, V, Cf, Sf, magSf, w, dC, ndC, nbrCC;
     std::vector<int> faceOff, faceVerts, owner, neighbour, patchStart, patchSize, patchKind;
     std::vector<int> bfacePatch;
@@ -100,6 +102,7 @@ struct qgd_mesh {
     std::vector<int> facePerm;     // device face -> polyMesh face
     std::vector<int> faceInv;      // polyMesh face -> device face
     qgd::DevBuf<int> facePermDev;
+    int nIActive = 0;              // internal faces with an owned owner cell (first in device order)
     // ELL (column-major, width W) + CSR tail stencils: coalesced row access for thread-per-row kernels
     int pcEllW = 8, cfEllW = 6;
     qgd::DevBuf<int> pcEll, pcCount, pcTailOff, pcTailCell;      // point -> cells

@@ -499,7 +499,7 @@ __global__ void k_bnd_pre(Consts k, FaceView fv, SolverView sv, BndState bs)
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= fv.nB) return;
     const int f = fv.nI + b;
-    if (fv.bKind[b] == QGD_PATCH_EMPTY) return;
+    if (fv.bKind[b] == QGD_PATCH_EMPTY || fv.own[f] >= sv.nOwned) return;      // halo faces: state comes from the owner rank
     BndFace bf;
     bndFaceSetup(k, fv, sv, bs, b, false, bf);
     const double divU = bf.g.U[0] + bf.g.U[4] + bf.g.U[8];
@@ -522,7 +522,7 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
     double coMax = 0.0, tauMin = DBL_MAX;
     if (b < fv.nB) {
         const int f = fv.nI + b;
-        if (fv.bKind[b] == QGD_PATCH_EMPTY) {
+        if (fv.bKind[b] == QGD_PATCH_EMPTY || fv.own[f] >= sv.nOwned) {
             sv.Fm[f] = 0.0; sv.FE[f] = 0.0;
             sv.FU[f] = 0.0; sv.FU[(size_t)fv.nF + f] = 0.0; sv.FU[2 * (size_t)fv.nF + f] = 0.0;
         } else {
@@ -553,8 +553,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     int P = 0, N = 0, flags = 0;
     int4 v = make_int4(0, 0, 0, 0);
-    if (f < fv.nI) { P = __ldg(&fv.own[f]); N = __ldg(&fv.nei[f]); flags = __ldg(&fv.flags[f]); v = __ldg(&fv.vtx[f]); }
-    for (; f < fv.nI; f += stride) {
+    const int nIA = fv.nIActive;
+    if (f < nIA) { P = __ldg(&fv.own[f]); N = __ldg(&fv.nei[f]); flags = __ldg(&fv.flags[f]); v = __ldg(&fv.vtx[f]); }
+    for (; f < nIA; f += stride) {
         const RecA aP = loadA(sv, P), aN = loadA(sv, N);
         const RecB bP = loadB(sv, P), bN = loadB(sv, N);
         RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
@@ -565,7 +566,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
         const int flagsCur = flags;
         {
             const int fn = f + stride;
-            if (fn < fv.nI) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
+            if (fn < nIA) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
         }
         const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
         double g1[3], g2[3], gp[3], Sf[3];
@@ -661,7 +662,7 @@ template <int W>
 __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nF)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= sv.nCells) return;
+    if (c >= sv.nOwned) return;
     const RecA a = loadA(sv, c);
     const RecB b = loadB(sv, c);
     double sm = 0.0, su0 = 0.0, su1 = 0.0, su2 = 0.0, se = 0.0;
@@ -766,6 +767,7 @@ __global__ void k_bnd_post(Consts k, FaceView fv, SolverView sv, BndState bs)
     if (b >= fv.nB) return;
     if (fv.bKind[b] == QGD_PATCH_EMPTY) return;
     const int P = fv.own[fv.nI + b];
+    if (P >= sv.nOwned) return;
     bndClose(k, fv, sv, bs, b, false, loadA(sv, P), sv.aQGD[P]);
 }
 
@@ -877,7 +879,7 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 }
 
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev)
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev, const StepHooks* hooks)
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
@@ -892,10 +894,11 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
     }
     if (fv.nB && anyQgdFlux) {
         k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+        if (hooks && hooks->midStep) hooks->midStep();
         if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
     }
-    if (fv.nI) {
-        const int grid = std::min(gridFaces, nblk(fv.nI, kFaceVariants[g_faceVariant].block));
+    if (fv.nIActive) {
+        const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
         if (ev) cudaEventRecord(ev[2], st);
         const FaceVariant& fvn = kFaceVariants[g_faceVariant];
         fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
@@ -903,11 +906,12 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         if (ev) cudaEventRecord(ev[3], st);
     }
     if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
+    if (hooks && hooks->beforeDt) hooks->beforeDt();
     k_dt<<<1, 1, 0, st>>>(sv.sc); ++n;
     if (ev) cudaEventRecord(ev[4], st);
-    if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF);
-    else if (sv.cfEllW == 6) k_cell_update<6><<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF);
-    else k_cell_update<8><<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, fv.nF);
+    if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nF);
+    else if (sv.cfEllW == 6) k_cell_update<6><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nF);
+    else k_cell_update<8><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nF);
     ++n;
     if (ev) cudaEventRecord(ev[5], st);
     if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }

@@ -1,5 +1,7 @@
 // Kernel-side declarations: device views (POD structs of raw pointers passed by value) and launchers.
 #pragma once
+#include <functional>
+
 #include "qgd_internal.h"
 
 namespace qgd {
@@ -12,6 +14,7 @@ struct Consts {
 
 struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     int nI, nF, nB;
+    int nIActive;            // internal faces whose owner is an owned cell (device order puts the others last)
     int zeroDivCmpt;         // 2D: out-of-plane component of Div(tensor) stays 0 (GaussVolPointBase2D.C:447-485), else -1
     const int* own;          // nF
     const int* nei;          // nI
@@ -59,6 +62,7 @@ void launchFvscDiv(cudaStream_t st, int K, const FaceView& fv, const double* cel
 // ---- QGDFoam step kernels
 struct SolverView {
     int nCells, nPoints, nPatchPoints;
+    int nOwned;                  // cells updated by this rank; [nOwned, nCells) are halo copies filled by the exchange
     // cell state, SoA: field k of cell c at S[k*nCells + c]; fields 0-7 = RecA (rho,Ux,Uy,Uz,e,p,T,H),
     // 8-15 = RecB (rhoUx,rhoUy,rhoUz,rhoE,c,mu,alphaEff,aByC).  SoA keeps the owner-ordered gathers of the face
     // kernel and the streaming point/cell kernels at one or two 128-B L1 wavefronts per warp-level load.
@@ -78,8 +82,11 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
                 const double* U0, const double* T0, const double* p0);
 // one QGDFoam.C:90-163 loop body; returns number of kernel launches issued
 // ev (optional): 6 events recorded around k_points, k_face_flux, k_cell_update (begin/end pairs)
+// hooks (optional, multi-GPU): midStep runs after the qgdFlux re-evaluation of p_b (exchange of halo p_b),
+// beforeDt runs before the time-step kernel (all-reduce of the Courant max / tau min)
+struct StepHooks { std::function<void()> midStep, beforeDt; };
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr);
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr);
 int faceKernelGrid();
 void setFaceVariant(int v);   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
