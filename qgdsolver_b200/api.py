@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
     "qgd_timer_begin", "qgd_timer_end",
+    "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
     "qgd_pcg_solve",
 ]
 
@@ -51,7 +52,7 @@ class _MeshDesc(C.Structure):
                 ("patch_start", _ip), ("patch_size", _ip), ("patch_kind", _ip),
                 ("C", _dp), ("V", _dp), ("Cf", _dp), ("Sf", _dp), ("magSf", _dp), ("weights", _dp),
                 ("deltaCoeffs", _dp), ("nonOrthDeltaCoeffs", _dp), ("neighb_cell_centres", _dp),
-                ("geometric_d", C.c_int * 3)]
+                ("geometric_d", C.c_int * 3), ("n_owned_cells", C.c_int), ("coupled_internal_face", _ip)]
 
 
 class QGDFoamDesc(C.Structure):
@@ -102,6 +103,9 @@ def load_library():
     L.qgd_qgdfoam_profile.argtypes = [C.c_void_p, C.c_int]
     L.qgd_qgdfoam_kernel_times.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip]
     L.qgd_timer_end.argtypes = [C.POINTER(C.c_float)]
+    L.qgd_comm_unique_id.argtypes = [C.c_void_p]
+    L.qgd_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
+    L.qgd_qgdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 9
     L.qgd_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
                                 _ip, _dp, _dp]
     _lib = L
@@ -133,12 +137,31 @@ def synchronize():
     _check(load_library().qgd_device_synchronize())
 
 
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load_library().qgd_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(rank: int, n_ranks: int, uid: bytes):
+    buf = C.create_string_buffer(uid, 128)
+    _check(load_library().qgd_comm_init(rank, n_ranks, buf))
+
+
+def comm_finalize():
+    _check(load_library().qgd_comm_finalize())
+
+
 class Mesh:
     """Device image of an fvMesh (qgd_mesh_create)."""
 
-    def __init__(self, mesh: PolyMesh):
+    def __init__(self, mesh: PolyMesh, n_owned: int = 0, coupled_face=None):
         self.mesh = mesh
+        self.n_owned = n_owned or mesh.n_cells
         d = _MeshDesc()
+        d.n_owned_cells = int(n_owned)
+        self._coupled = None if coupled_face is None else np.ascontiguousarray(coupled_face, np.int32)
+        d.coupled_internal_face = None if self._coupled is None else _i(self._coupled)
         d.n_cells, d.n_faces, d.n_internal_faces, d.n_points = mesh.n_cells, mesh.n_faces, mesh.n_internal, mesh.n_points
         d.n_patches = len(mesh.patches)
         k = dict(points=_f64(mesh.points), C=_f64(mesh.C), V=_f64(mesh.V), Cf=_f64(mesh.Cf), Sf=_f64(mesh.Sf),
@@ -253,6 +276,29 @@ class QGDFoam:
 
     def step(self, n_steps: int = 1):
         _check(load_library().qgd_qgdfoam_step(self._h, n_steps))
+
+    def set_halo(self, sub):
+        """Register the exchange lists of a decompose.SubDomain (call after comm_init)."""
+        nbrs = sorted(set(sub.send_cells) | set(sub.recv_cells))
+
+        def pack(d):
+            off = np.zeros(len(nbrs) + 1, np.int32)
+            parts = []
+            for k, r in enumerate(nbrs):
+                a = np.asarray(d.get(r, np.zeros(0, np.int32)), np.int32)
+                parts.append(a)
+                off[k + 1] = off[k] + a.size
+            ids = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+            if ids.size == 0:
+                ids = np.zeros(1, np.int32)
+            return off, np.ascontiguousarray(ids)
+        sco, sc = pack(sub.send_cells)
+        rco, rc = pack(sub.recv_cells)
+        sbo, sb = pack(sub.send_bfaces)
+        rbo, rb = pack(sub.recv_bfaces)
+        nb = np.asarray(nbrs, np.int32) if nbrs else np.zeros(1, np.int32)
+        _check(load_library().qgd_qgdfoam_set_halo(self._h, len(nbrs), _i(nb), _i(sco), _i(sc), _i(rco), _i(rc),
+                                                   _i(sbo), _i(sb), _i(rbo), _i(rb)))
 
     @staticmethod
     def _state_struct(bufs) -> _StateHost:

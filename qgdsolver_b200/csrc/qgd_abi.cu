@@ -680,6 +680,7 @@ int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, con
         if (alphaQGD) QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, alphaQGD, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         else { std::vector<double> a(n, 0.5); QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, a.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream)); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
         launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), s->stage.p, s->stage.p + 3 * n, s->stage.p + 4 * n);
+        if (s->halo.active) s->launches += haloExchange(s);
         QGD_CUDA(cudaStreamSynchronize(g_stream));
         s->fieldsSet = true;
     });
@@ -909,6 +910,8 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* 
         h.recvBuf.alloc((size_t)kCellDoubles * h.recvCellOff[nn] + (size_t)kBfDoubles * h.recvBfOff[nn] + 1);
         h.midSend.alloc(h.sendBfOff[nn] + 1); h.midRecv.alloc(h.recvBfOff[nn] + 1);
         h.active = nn > 0;
+        // halo copies initialised locally carry wrong mesh-derived values (hQGD of an open halo cell): take the owners'
+        if (h.active && s->fieldsSet) { s->launches += haloExchange(s); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
     });
 }
 

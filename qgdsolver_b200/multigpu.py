@@ -1,0 +1,105 @@
+"""Multi-GPU driver glue (harness side): one process per GPU, torch.distributed only for the NCCL-id broadcast,
+barriers and max-over-ranks timing; the data path (halo exchange, all-reduce) is inside libqgd_b200.so."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+
+from . import api, decompose
+
+
+def init_comm(rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8).clone()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    uid = uid.to(dev)
+    dist.broadcast(uid, 0)
+    api.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+
+def make_rank_solver(case, rank: int, world: int, cell_rank=None):
+    """Extended sub-mesh of `rank` + solver with halo lists.  `case` is a tests/cases.Case on the GLOBAL mesh."""
+    mesh = case.mesh
+    if cell_rank is None:
+        cell_rank = decompose.geometric_split(mesh, world)
+    sub = decompose.extended_submeshes(mesh, cell_rank, ranks=[rank])[0]
+    dm = api.Mesh(sub.mesh, n_owned=sub.n_owned, coupled_face=sub.coupled_face)
+    s = api.QGDFoam(dm, fvsc_scheme=case.scheme, delta_t=case.dt, **case.gas, **case.opts)
+    # per-patch BC kinds: global patches + the cut patch (kind irrelevant); per-face values follow the local faces
+    nI_g = mesh.n_internal
+    bf_g = sub.face_global[sub.mesh.n_internal:]
+    is_phys = bf_g >= nI_g
+    idx = np.where(is_phys, bf_g - nI_g, 0)
+    pad = lambda k: np.concatenate([np.asarray(k, np.int32), [1]]).astype(np.int32)
+    valU = np.where(is_phys[:, None], case.bvU[idx], 0.0)
+    valT = np.where(is_phys, case.bvT[idx], 1.0)
+    valP = np.where(is_phys, case.bvP[idx], 1.0)
+    s.set_bcs(pad(case.bcU), pad(case.bcT), pad(case.bcP), valU, valT, valP)
+    cg = sub.cell_global
+    s.init_fields(case.U0[cg], case.T0[cg], case.p0[cg], None if case.alphaQGD is None else case.alphaQGD[cg])
+    s.set_halo(sub)
+    return s, sub, dm
+
+
+def bench(args, rank: int, world: int, local: int):
+    """bench.py body for --gpus > 1 (strong scaling of the 256^3 box; rank 0 prints the JSON line)."""
+    import torch
+    import torch.distributed as dist
+    import bench as B
+    init_comm(rank, world)
+    case = B.build_case(args.size)
+    mesh = case.mesh
+    s, sub, dm = make_rank_solver(case, rank, world)
+    s.step(args.warmup)
+    api.synchronize()
+    sampler = B.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = s.launch_count()
+    dist.barrier(); torch.cuda.synchronize(); api.synchronize()
+    s.profile(True)
+    api.timer_begin()
+    s.step(args.steps)
+    ms = api.timer_end()
+    api.synchronize(); torch.cuda.synchronize()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    ms = float(t.item())
+    kt = s.kernel_times()
+    launches = s.launch_count() - l0
+    if rank == 0:
+        clocks = sampler.stop()
+        ms_step = ms / args.steps
+        value = mesh.n_cells / (ms_step * 1e-3) / 1e6
+        ab = B.alg_bytes(mesh)
+        peak, src = B.peaks()
+        face_ms = kt["face_ms"] / max(kt["steps"], 1)
+        ab_face_rank = 184 * sub.mesh.n_internal + 40 * sub.mesh.n_cells + 48 * sub.mesh.n_points
+        halo_bytes = 8 * (16 * sum(a.size for a in sub.send_cells.values()) + 20 * sum(a.size for a in sub.send_bfaces.values()))
+        line = {"metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"QGDFoam 3D synthetic hex box {args.size}^3 ({mesh.n_cells} cells), explicit, FP64, "
+                                       f"geometric {'x'.join(map(str, decompose.split_factors(world)))} decomposition",
+                           "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False,
+                           "deltaT": case.dt, "owned_cells_rank0": sub.n_owned, "halo_cells_rank0": sub.mesh.n_cells - sub.n_owned,
+                           "halo_bytes_sent_per_step_rank0": halo_bytes,
+                           "l2": "per-rank state and mesh records exceed the 126 MB L2; no flush"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": None,
+                "roofline": {"bound": "hbm", "kernel": "k_face_flux (rank 0)", "achieved": ab_face_rank / (face_ms * 1e-3) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": ab_face_rank / (face_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                             "peak_source": src, "avg_launch_ms": face_ms,
+                             "step": {"alg_bytes_global": ab["total"], "achieved_aggregate": ab["total"] / (ms_step * 1e-3) / 1e9,
+                                      "frac_of_n_gpus_peak": ab["total"] / (ms_step * 1e-3) / 1e9 / (peak * world)}},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    api.comm_finalize()
+    dist.destroy_process_group()
