@@ -1,0 +1,6 @@
+#!/bin/bash
+# scaling check of bench.py under torchrun: N given as $1
+N=${1:-2}
+mkdir -p gpurun_out
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus $N --steps 50 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+tail -5 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json
