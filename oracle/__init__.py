@@ -39,8 +39,20 @@ class QGDParams(C.Structure):
                 ("energyDdtRhoEQuirk", C.c_int)]
 
 
+class QHDParams(C.Structure):
+    _fields_ = [("rho0", C.c_double), ("mu", C.c_double), ("Pr", C.c_double), ("beta", C.c_double),
+                ("g", C.c_double * 3), ("qgdModel", C.c_int), ("Tau", C.c_double), ("UQHD", C.c_double),
+                ("Gr", C.c_double), ("T0", C.c_double), ("implicitDiffusion", C.c_int),
+                ("pTol", C.c_double), ("pRelTol", C.c_double), ("pMaxIter", C.c_int), ("pPrecond", C.c_int),
+                ("pRefCell", C.c_int), ("pRefValue", C.c_double)]
+
+
+QHD_MODELS = {"constTau": 0, "H2bynuQHD": 1, "HbyUQHD": 2, "T0byGr": 3}
+PRECONDS = {"none": 0, "diagonal": 1, "DIC": 2}
+
+
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("qgd_oracle.cpp", "qgd_oracle.hpp")]
+    src = [os.path.join(_HERE, f) for f in ("qgd_oracle.cpp", "qgd_oracle.hpp", "qhd_oracle.inc")]
     if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
@@ -74,6 +86,15 @@ def lib():
         L.or_qgd_get_face.argtypes = [C.c_void_p, C.c_int, _dp]
         L.or_pcg_solve.restype = C.c_int
         L.or_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp]
+        L.or_qhd_init.argtypes = [C.c_void_p, C.POINTER(QHDParams), C.c_int, _ip, _ip, _ip, _dp, _dp, _dp,
+                                  _dp, _dp, _dp, _dp, C.c_double]
+        L.or_qhd_step.restype = C.c_double
+        L.or_qhd_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.or_qhd_deltaT.restype = C.c_double
+        L.or_qhd_deltaT.argtypes = [C.c_void_p]
+        L.or_qhd_get.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+        L.or_qhd_get_face.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.or_qhd_solver_info.argtypes = [C.c_void_p, _ip, _dp, _dp]
         _lib = L
     return _lib
 
@@ -214,3 +235,39 @@ class Oracle:
         it = lib().or_pcg_solve(self._h, _d(diag), _d(upper), _d(b), _d(x), tol, relTol, maxIter, precond,
                                 C.byref(r0), C.byref(r1))
         return x, it, r0.value, r1.value
+
+    # ---- QHDFoam
+    QHD_CELL = {"U": (0, 3), "T": (1, 1), "p": (2, 1), "tauQGD": (3, 1)}
+    QHD_FACE = {"phi": (0, 1), "phiu": (1, 1), "phiwo": (2, 1), "tauQGDf": (3, 1), "gradPf": (4, 3), "gradUf": (5, 9),
+                "gradTf": (6, 3)}
+
+    def qhd_init(self, params: QHDParams, bcU, bcT, bcP, bvU, bvT, bvP, U0, T0, p0, alphaQGD=None,
+                 deltaT=1e-4, scheme=FVSC_GAUSSVOLPOINT):
+        a = [np.ascontiguousarray(x, np.int32) for x in (bcU, bcT, bcP)]
+        f = [_f64(x) for x in (bvU, bvT, bvP, U0, T0, p0, alphaQGD)]
+        lib().or_qhd_init(self._h, C.byref(params), scheme, _i(a[0]), _i(a[1]), _i(a[2]),
+                          *[_d(x) for x in f], deltaT)
+
+    def qhd_step(self, n_steps=1, adjust=False, maxCo=0.3, maxDeltaT=1e30, cTau=0.75):
+        return lib().or_qhd_step(self._h, n_steps, int(adjust), maxCo, maxDeltaT, cTau)
+
+    def qhd_deltaT(self):
+        return lib().or_qhd_deltaT(self._h)
+
+    def qhd_get(self, name, with_bnd=False):
+        fid, k = self.QHD_CELL[name]
+        cells = np.zeros((self.mesh.n_cells, k) if k > 1 else self.mesh.n_cells)
+        bnd = np.zeros((self.mesh.n_bnd, k) if k > 1 else self.mesh.n_bnd)
+        lib().or_qhd_get(self._h, fid, _d(cells), _d(bnd))
+        return (cells, bnd) if with_bnd else cells
+
+    def qhd_get_face(self, name):
+        fid, k = self.QHD_FACE[name]
+        out = np.zeros((self.mesh.n_faces, k) if k > 1 else self.mesh.n_faces)
+        lib().or_qhd_get_face(self._h, fid, _d(out))
+        return out
+
+    def qhd_solver_info(self):
+        it, r0, r1 = C.c_int(), C.c_double(), C.c_double()
+        lib().or_qhd_solver_info(self._h, C.byref(it), C.byref(r0), C.byref(r1))
+        return dict(iters=it.value, initial_residual=r0.value, final_residual=r1.value)

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -34,7 +35,22 @@ const double SMALL = 1e-15;   // OpenFOAM SMALL (double)
 
 } // namespace
 
+// QHDFoam state (oracle/qhd_oracle.inc)
+struct QhdState {
+    or_qhd_params_t prm{};
+    int scheme = OR_FVSC_GAUSSVOLPOINT;
+    IVec bcU, bcT, bcP;
+    Vec bvU, bvT, bvP;          // fixedValue: value ; fixedGradient / qhdFlux: gradient
+    double deltaT = 0, CoNum = -1;
+    Vec U, UB, T, TB, p, pB, rho, rhoB, mu, muB, alpha, alphaB, aQGD, aQGDB, tau, tauB, BdFrc, BdFrcB;
+    Vec tauf, rhof, Uf, Tf, muf, alphaf, Hif, BdFrcf, gradUf, gradTf, gradPf, phiu, phiwo, taubyrhof, phi, Wf, phiUf,
+        phiTf, phiTauTReg;
+    int lastIters = 0;
+    double lastRes0 = 0, lastRes = 0;
+};
+
 struct or_ctx {
+    std::unique_ptr<QhdState> qhd;
     // ---- mesh (borrowed pointers are copied)
     int nCells = 0, nFaces = 0, nInternal = 0, nPoints = 0, nPatches = 0, nBnd = 0;
     Vec points, C, V, Cf, Sf, magSf, w, dC, ndC, nbrCC;
@@ -1110,3 +1126,5 @@ int or_pcg_solve(or_ctx* sp, const double* diag, const double* upper, const doub
 }
 
 } // extern "C"
+
+#include "qhd_oracle.inc"

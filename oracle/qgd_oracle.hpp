@@ -101,6 +101,30 @@ void or_qgd_get(or_ctx*, int field, double* cells, double* bnd);
 //  7 tauQGDf, 8 gradUf(9), 9 gradef(3), 10 gradRhof(3), 11 gradPf(3), 12 phiwStar
 void or_qgd_get_face(or_ctx*, int field, double* out /*nFaces*k*/);
 
+// ---- QHDFoam (explicit branch).  heRhoQGDThermo with rhoConst + hConst + constTransport (+ beta), laminar.
+typedef struct {
+    double rho0;               // rhoConst
+    double mu, Pr, beta;       // constTransport ; beta from mixture.transport (QHDFoam/createFields.H:110-115)
+    double g[3];               // constant/gravitationalProperties
+    int qgdModel;              // 0 constTau, 1 H2bynuQHD, 2 HbyUQHD, 3 T0byGr
+    double Tau, UQHD, Gr, T0;  // model coefficients
+    int implicitDiffusion;     // only 0 supported
+    double pTol, pRelTol;      // fvSolution::solvers::p
+    int pMaxIter, pPrecond;    // precond: 0 none, 1 diagonal, 2 DIC
+    int pRefCell; double pRefValue;   // setRefCell(p, thermo.subDict("QGD"), ...)
+} or_qhd_params_t;
+//  bc kinds per patch: fixedValue | zeroGradient | fixedGradient (qhdFlux behaves as fixedGradient in QHDFoam, see
+//  DESIGN.md quirk (i)); bv*: value on fixedValue faces, gradient on fixedGradient faces
+void or_qhd_init(or_ctx*, const or_qhd_params_t*, int fvscScheme, const int* bcU, const int* bcT, const int* bcP,
+                 const double* bvU, const double* bvT, const double* bvP, const double* U0, const double* T0,
+                 const double* p0, const double* alphaQGD, double deltaT0);
+double or_qhd_step(or_ctx*, int nSteps, int adjustTimeStep, double maxCo, double maxDeltaT, double cTau);
+double or_qhd_deltaT(or_ctx*);
+//  cell fields: 0 U(3), 1 T, 2 p, 3 tauQGD ; face fields: 0 phi, 1 phiu, 2 phiwo, 3 tauQGDf, 4 gradPf(3), 5 gradUf(9), 6 gradTf(3)
+void or_qhd_get(or_ctx*, int field, double* cells, double* bnd);
+void or_qhd_get_face(or_ctx*, int field, double* out);
+void or_qhd_solver_info(or_ctx*, int* iters, double* res0, double* res);
+
 // ---- LDU PCG [OF-v2312 PCG + DIC / diagonal]  (QHDpEqn.H:45)
 //  symmetric: lower == upper.  precond: 0 none, 1 diagonal, 2 DIC.  returns iterations.
 int or_pcg_solve(or_ctx*, const double* diag, const double* upper, const double* b, double* x,

@@ -130,3 +130,85 @@ def _with_bcs(mesh, bcs, gas, dt, **opts):
     else:
         raise ValueError(bcs)
     return Case(mesh, U0, T0, p0, *bc, gas=gas, dt=dt, **opts)
+
+
+# ============================================================================ QHDFoam cases
+QHD_FLUID = dict(rho0=1.0, mu=1.0e-2, Pr=0.71, beta=3.0e-3, g=(0.0, -9.81, 0.0))
+
+
+class QHDCase:
+    """Seeded QHDFoam case: heRhoQGDThermo(rhoConst, hConst, const) + a QHD tau model + PCG controls for p."""
+
+    def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, fluid=QHD_FLUID, model="constTau",
+                 coeffs=None, dt=1e-3, scheme="GaussVolPoint", alphaQGD=None, tol=1e-13, rel_tol=0.0, max_iter=5000,
+                 precond="DIC", p_ref_cell=0, p_ref_value=0.0, adjust_time_step=False, max_co=0.3, max_delta_t=1e30,
+                 c_tau=0.75):
+        self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
+        self.bcU, self.bcT, self.bcP = [np.asarray(x, np.int32) for x in (bcU, bcT, bcP)]
+        self.bvU, self.bvT, self.bvP = bvU, bvT, bvP
+        self.fluid, self.model, self.dt, self.scheme, self.alphaQGD = dict(fluid), model, dt, scheme, alphaQGD
+        self.coeffs = dict(Tau=1e-3, UQHD=1.0, Gr=1.0e4, T0=1.0)
+        self.coeffs.update(coeffs or {})
+        self.solver = dict(tol=tol, rel_tol=rel_tol, max_iter=max_iter, precond=precond)
+        self.p_ref_cell, self.p_ref_value = p_ref_cell, p_ref_value
+        self.opts = dict(adjust_time_step=adjust_time_step, max_co=max_co, max_delta_t=max_delta_t, c_tau=c_tau)
+
+    def make_oracle(self, O, n_threads=1):
+        o = O.Oracle(self.mesh, n_threads=n_threads)
+        f, c, sv = self.fluid, self.coeffs, self.solver
+        prm = O.QHDParams(rho0=f["rho0"], mu=f["mu"], Pr=f["Pr"], beta=f["beta"], qgdModel=O.QHD_MODELS[self.model],
+                          Tau=c["Tau"], UQHD=c["UQHD"], Gr=c["Gr"], T0=c["T0"], implicitDiffusion=0,
+                          pTol=sv["tol"], pRelTol=sv["rel_tol"], pMaxIter=sv["max_iter"],
+                          pPrecond=O.PRECONDS[sv["precond"]], pRefCell=self.p_ref_cell, pRefValue=self.p_ref_value)
+        for j in range(3):
+            prm.g[j] = f["g"][j]
+        scheme = O.FVSC_GAUSSVOLPOINT if self.scheme == "GaussVolPoint" else O.FVSC_REDUCED
+        o.qhd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
+                   alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme)
+        return o
+
+    def oracle_step(self, o, n):
+        return o.qhd_step(n, adjust=self.opts["adjust_time_step"], maxCo=self.opts["max_co"],
+                          maxDeltaT=self.opts["max_delta_t"], cTau=self.opts["c_tau"])
+
+    def make_solver(self, api, dmesh=None):
+        dmesh = dmesh or api.Mesh(self.mesh)
+        s = api.QHDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, p_ref_cell=self.p_ref_cell,
+                        p_ref_value=self.p_ref_value, **self.fluid, **self.coeffs, **self.solver, **self.opts)
+        s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
+        s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
+        return s
+
+
+def qhd_cavity(n=(16, 16), dims=2, perturb=0.0, model="constTau", p_bc="qhdflux", seed=21, **kw):
+    """Differentially heated cavity (BASELINE configs[2] in miniature): hot xMin wall, cold xMax wall, adiabatic
+    others, no-slip U, qhdFlux (== fixedGradient 0 in QHDFoam) or zeroGradient p; smooth non-trivial initial U,T."""
+    if dims == 2:
+        mesh = pm.hex_box(n[0], n[1], 1, lengths=(1.0, 1.0, 0.1), patch_kinds={"zMin": "empty", "zMax": "empty"},
+                          perturb=perturb, seed=seed)
+    else:
+        mesh = pm.hex_box(*n, perturb=perturb, seed=seed)
+    nP, nB = len(mesh.patches), mesh.n_bnd
+    names = [p.name for p in mesh.patches]
+    kU = np.full(nP, FV, np.int32)
+    kT = np.array([FV if nm in ("xMin", "xMax") else ZG for nm in names], np.int32)
+    kP = np.full(nP, FG if p_bc == "qhdflux" else ZG, np.int32)
+    bvU = np.zeros((nB, 3))
+    bvT = np.zeros(nB)
+    bvP = np.zeros(nB)
+    pid = mesh.patch_id_per_bface()
+    for i, nm in enumerate(names):
+        if nm == "xMin":
+            bvT[pid == i] = 1.0
+        if nm == "xMax":
+            bvT[pid == i] = 0.0
+    x, y, z = mesh.C[:, 0], mesh.C[:, 1], mesh.C[:, 2]
+    act = (mesh.geometric_d > 0).astype(float)
+    rng = np.random.default_rng(seed)
+    psi = np.sin(np.pi * x) ** 2 * np.sin(np.pi * y) ** 2
+    U0 = np.stack([0.05 * np.sin(np.pi * x) ** 2 * np.sin(2 * np.pi * y),
+                   -0.05 * np.sin(2 * np.pi * x) * np.sin(np.pi * y) ** 2,
+                   0.01 * np.sin(np.pi * z) * psi * act[2]], axis=1)
+    T0 = 1.0 - x + 0.05 * np.sin(2 * np.pi * y) + 1e-3 * (rng.random(mesh.n_cells) - 0.5)
+    p0 = 1e-3 * np.cos(np.pi * x) * np.cos(np.pi * y)
+    return QHDCase(mesh, np.ascontiguousarray(U0), T0, p0, kU, kT, kP, bvU, bvT, bvP, model=model, **kw)

@@ -193,3 +193,97 @@ def test_oracle_reproduces_committed_golden_vectors(oracle_mod, name):
     for f in ("rho", "rhoU", "rhoE", "e", "p"):
         ref = z[f]
         assert np.abs(o.get(f) - ref).max() <= 1e-13 * np.abs(ref).max(), f
+
+
+# ============================================================================ QHDFoam oracle KATs
+def _div(mesh, phi):
+    nI = mesh.n_internal
+    d = np.zeros(mesh.n_cells)
+    np.add.at(d, mesh.owner[:nI], phi[:nI])
+    np.add.at(d, mesh.neighbour, -phi[:nI])
+    np.add.at(d, mesh.owner[nI:], phi[nI:])
+    return d
+
+
+def test_qhd_hydrostatic_balance_keeps_fluid_at_rest(oracle_mod):
+    """U = 0, uniform T, uniform body force, p BC = fixedGradient rho*BdFrc.n: the discrete solution is the linear
+    hydrostatic pressure, every face flux phi vanishes and U, T do not move (QHDpEqn.H:36-47, QHDUEqn.H:36-84)."""
+    import cases
+    c = cases.qhd_cavity(n=(10, 12), dt=1e-3)
+    m = c.mesh
+    c.U0[:] = 0.0
+    c.T0[:] = 0.7
+    c.bcT[:] = cases.ZG
+    f = c.fluid
+    bd = f["beta"] * 0.7 * np.asarray(f["g"])
+    nI = m.n_internal
+    nf = m.Sf[nI:] / m.magSf[nI:, None]
+    c.bvP = f["rho0"] * (nf @ bd)
+    c.p0 = f["rho0"] * (m.C @ bd)
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 5)
+    assert np.abs(o.qhd_get("U")).max() < 1e-11
+    assert np.abs(o.qhd_get("T") - 0.7).max() < 1e-12
+    assert np.abs(o.qhd_get_face("phi")).max() < 1e-13
+    p = o.qhd_get("p")
+    pl = f["rho0"] * (m.C @ bd)
+    assert np.abs((p - p[0]) - (pl - pl[0])).max() < 1e-10
+
+
+def test_qhd_temperature_diffusion_matches_discrete_eigenmode(oracle_mod):
+    """U = 0, g = 0: T_t = div(Hi grad T) with zeroGradient walls; cos(pi x) is an exact eigenvector of the cell-centred
+    discrete Laplacian, so n Euler steps multiply it by (1 - dt*lambda_h)^n (QHDTEqn.H:83-91)."""
+    import cases
+    n = 16
+    c = cases.qhd_cavity(n=(n, 4), dt=2e-3, fluid=dict(cases.QHD_FLUID, g=(0.0, 0.0, 0.0)))
+    m = c.mesh
+    c.U0[:] = 0.0
+    c.bcT[:] = cases.ZG
+    c.T0 = 1.0 + 0.3 * np.cos(np.pi * m.C[:, 0])
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 20)
+    h = 1.0 / n
+    Hi = (c.fluid["mu"] / c.fluid["Pr"]) / c.fluid["rho0"]
+    lam = Hi * (2.0 - 2.0 * np.cos(np.pi * h)) / h ** 2
+    ref = 1.0 + 0.3 * (1.0 - c.dt * lam) ** 20 * np.cos(np.pi * m.C[:, 0])
+    assert np.abs(o.qhd_get("T") - ref).max() < 1e-13
+    assert np.abs(o.qhd_get("U")).max() < 1e-14
+
+
+@pytest.mark.parametrize("model", ["constTau", "H2bynuQHD", "HbyUQHD", "T0byGr"])
+def test_qhd_projection_is_divergence_free(oracle_mod, model):
+    """After pEqn the flux phi = phiu - phiwo + pEqn.flux() balances in every cell except the reference cell, whose
+    equation fvMatrix::setReference relaxes (QHDpEqn.H:43-47); tauQGD follows the selected model."""
+    import cases
+    c = cases.qhd_cavity(n=(12, 10), dt=1e-3, model=model, perturb=0.15, coeffs=dict(Tau=2e-3, UQHD=5.0, Gr=500.0, T0=1.0))
+    c.bcT[:] = cases.ZG
+    m = c.mesh
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 3)
+    d = _div(m, o.qhd_get_face("phi"))
+    scale = np.abs(o.qhd_get_face("phi")).max()
+    d[c.p_ref_cell] = 0.0
+    assert np.abs(d).max() < 1e-9 * scale
+    info = o.qhd_solver_info()
+    assert 0 < info["iters"] < 400 and info["final_residual"] < 1e-12
+    tau = o.qhd_get("tauQGD")
+    h = o.hQGD()
+    f, k = c.fluid, c.coeffs
+    expect = {"constTau": np.full_like(h, k["Tau"]), "H2bynuQHD": 0.5 * h * h / (f["mu"] / f["rho0"]),
+              "HbyUQHD": 0.5 * h / k["UQHD"], "T0byGr": np.full_like(h, k["T0"] / k["Gr"])}[model]
+    assert np.allclose(tau, expect, rtol=1e-14, atol=0)
+
+
+def test_qhd_preconditioners_agree(oracle_mod):
+    """DIC / diagonal / none change the PCG iteration count, not the converged step."""
+    import cases
+    res = {}
+    for pc in ("DIC", "diagonal", "none"):
+        c = cases.qhd_cavity(n=(10, 9, 8), dims=3, dt=1e-3, precond=pc, perturb=0.1)
+        o = c.make_oracle(oracle_mod)
+        c.oracle_step(o, 3)
+        res[pc] = (o.qhd_get("U"), o.qhd_get("T"), o.qhd_get("p"), o.qhd_solver_info()["iters"])
+    for pc in ("diagonal", "none"):
+        for a, b in zip(res[pc][:3], res["DIC"][:3]):
+            assert np.abs(a - b).max() < 1e-9 * max(np.abs(b).max(), 1e-30)
+    assert res["DIC"][3] < res["diagonal"][3] <= res["none"][3]
