@@ -44,12 +44,14 @@ typedef enum {
     QGD_BC_ZERO_GRADIENT = 1,    /* zeroGradient                                 */
     QGD_BC_FIXED_GRADIENT = 2,   /* fixedGradient                                */
     QGD_BC_QGD_FLUX = 3,         /* qgdFlux  qgdFluxFvPatchScalarField.C:159-208 */
-    QGD_BC_CALCULATED = 4        /* calculated                                   */
+    QGD_BC_CALCULATED = 4,       /* calculated                                   */
+    QGD_BC_QHD_FLUX = 5          /* qhdFlux  qhdFluxFvPatchScalarField.C:159-219 */
 } qgd_bc_kind;
 
 typedef struct qgd_mesh qgd_mesh;       /* fvMesh image on the device             */
 typedef struct qgd_fvsc qgd_fvsc;       /* one fvsc::fvscStencil instance         */
 typedef struct qgd_solver qgd_solver;   /* QGDFoam time loop state                */
+typedef struct qgd_qhd_solver qgd_qhd_solver;   /* QHDFoam time loop state        */
 
 /* ---- library / device ------------------------------------------------------ */
 int         qgd_init(int device);                 /* cudaSetDevice + stream; call once per process (rank) */
@@ -196,9 +198,51 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int n_neighbours, const int* nbr_rank,
                          const int* send_cell_off, const int* send_cells, const int* recv_cell_off, const int* recv_cells,
                          const int* send_bf_off, const int* send_bfaces, const int* recv_bf_off, const int* recv_bfaces);
 
+/* ---- QHDFoam (solver-level integration) -------------------------------------
+ * Replaces the loop body QHDFoam.C:83-139 (explicit branch) with rhoQGDThermo::New -> heRhoQGDThermo<rhoConst,
+ * hConst, const> (rhoQGDThermos.C:76-140, heRhoQGDThermo.C:38-139), a QHD-family QGDCoeffs model
+ * (constTau.C:48-85, H2bynuQHD.C:77-83, HbyUQHD.C:79-84, T0byGr.C:83-88) and the fvSolution PCG controls of p.
+ * fvSchemes assumed: ddt Euler, grad Gauss linear, laplacian Gauss linear (un)corrected on orthogonal meshes,
+ * interpolation linear, no div(phi,U)/div(phi,T) entries (QGDInterpolate.H:86-104 -> flux*psif). */
+typedef struct {
+    const char* fvsc_scheme;        /* fvSchemes::fvsc::default                                     */
+    const char* qgd_coeffs_model;   /* "constTau" | "H2bynuQHD" | "HbyUQHD" | "T0byGr"              */
+    double rho0;                    /* rhoConst                                                     */
+    double mu, Pr, beta;            /* constTransport + beta (QHDFoam/createFields.H:110-115)       */
+    double g[3];                    /* constant/gravitationalProperties (createFields.H:108)        */
+    double Tau, UQHD, Gr, T0;       /* model coefficients                                           */
+    int implicit_diffusion;         /* QGD::implicitDiffusion; only false runs on the device        */
+    double p_tolerance, p_rel_tol;  /* fvSolution::solvers::p                                       */
+    int p_max_iter;
+    const char* p_preconditioner;   /* "DIC" | "diagonal" | "none"                                  */
+    int p_ref_cell; double p_ref_value;   /* setRefCell(p, thermo.subDict("QGD"), ...) createFields.H:162-165 */
+    int adjust_time_step;           /* QHDCourantNo.H:37                                            */
+    double max_co, max_delta_t, c_tau, delta_t;
+} qgd_qhdfoam_desc;
+int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* desc, qgd_qhd_solver** out);
+int qgd_qhdfoam_destroy(qgd_qhd_solver* s);
+/* kinds per patch for U, T, p: fixedValue | zeroGradient | fixedGradient | qhdFlux (a fixed-gradient patch in this solver:
+ * no field is registered as "phiwStar" in QHDFoam, qhdFluxFvPatchScalarField.C:166-206).  val_*: per boundary face, the
+ * value on fixedValue patches, the gradient on fixedGradient / qhdFlux patches (U: n_bnd*3). */
+int qgd_qhdfoam_set_bcs(qgd_qhd_solver* s, const int* bc_U, const int* bc_T, const int* bc_p,
+                        const double* val_U, const double* val_T, const double* val_p);
+/* U n_cells*3, T, p n_cells, alphaQGD n_cells or NULL (0.5).  Assembles the (time-constant) pressure matrix and its
+ * preconditioner on the device. */
+int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T, const double* p, const double* alphaQGD);
+int qgd_qhdfoam_step(qgd_qhd_solver* s, int n_steps);
+/* fields: 0 U(3), 1 T, 2 p, 3 tauQGD */
+int qgd_qhdfoam_get(qgd_qhd_solver* s, int field, double* cells, double* bnd);
+/* phi = phiu - phiwo + pEqn.flux() of the last step (QHDpEqn.H:47), n_faces */
+int qgd_qhdfoam_get_flux(qgd_qhd_solver* s, double* phi);
+int qgd_qhdfoam_get_scalars(qgd_qhd_solver* s, double* delta_t, double* courant, double* time);
+/* SolverPerformance of the last pEqn.solve(): nIterations, initialResidual, finalResidual */
+int qgd_qhdfoam_solver_info(qgd_qhd_solver* s, int* iters, double* initial_residual, double* final_residual);
+long long qgd_qhdfoam_launch_count(qgd_qhd_solver* s);
+
 /* ---- LDU PCG (QHDpEqn.H:45 -> lduMatrix::solver PCG + DIC|diagonal) ---------- */
 /* symmetric LDU matrix on the mesh addressing (lower == upper); precond: 0 none, 1 diagonal (Jacobi),
- * 2 DIC (device: level-scheduled).  Host pointers. Returns iterations in *iters. */
+ * 2 DIC (device: level-scheduled, bit-identical operation order to the sequential sweeps).  Host pointers; the whole
+ * solve is one cooperative kernel launch.  Returns iterations in *iters. */
 int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x,
                   double tolerance, double rel_tol, int max_iter, int precond,
                   int* iters, double* initial_residual, double* final_residual);

@@ -18,7 +18,7 @@ from .polymesh import PolyMesh
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqgd_b200.so")
 
-BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED = 0, 1, 2, 3, 4
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED, BC_QHD_FLUX = 0, 1, 2, 3, 4, 5
 QGD_OK, ERR_INVALID, ERR_UNKNOWN_MODEL, ERR_UNSUPPORTED, ERR_CUDA, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 # every symbol include/qgd_b200.h declares (checked by tests/test_abi_cpu.py)
@@ -32,6 +32,9 @@ ABI_SYMBOLS = [
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
     "qgd_pcg_solve",
+    "qgd_qhdfoam_create", "qgd_qhdfoam_destroy", "qgd_qhdfoam_set_bcs", "qgd_qhdfoam_init_fields", "qgd_qhdfoam_step",
+    "qgd_qhdfoam_get", "qgd_qhdfoam_get_flux", "qgd_qhdfoam_get_scalars", "qgd_qhdfoam_solver_info",
+    "qgd_qhdfoam_launch_count",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -61,6 +64,16 @@ class QGDFoamDesc(C.Structure):
                 ("mu", C.c_double), ("Pr", C.c_double), ("ScQGD", C.c_double), ("PrQGD", C.c_double),
                 ("implicit_diffusion", C.c_int), ("alpha_eff_gamma_factor", C.c_int), ("energy_ddt_rhoE_quirk", C.c_int),
                 ("adjust_time_step", C.c_int),
+                ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double)]
+
+
+class QHDFoamDesc(C.Structure):
+    _fields_ = [("fvsc_scheme", C.c_char_p), ("qgd_coeffs_model", C.c_char_p),
+                ("rho0", C.c_double), ("mu", C.c_double), ("Pr", C.c_double), ("beta", C.c_double), ("g", C.c_double * 3),
+                ("Tau", C.c_double), ("UQHD", C.c_double), ("Gr", C.c_double), ("T0", C.c_double),
+                ("implicit_diffusion", C.c_int), ("p_tolerance", C.c_double), ("p_rel_tol", C.c_double),
+                ("p_max_iter", C.c_int), ("p_preconditioner", C.c_char_p), ("p_ref_cell", C.c_int),
+                ("p_ref_value", C.c_double), ("adjust_time_step", C.c_int),
                 ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double)]
 
 
@@ -108,6 +121,17 @@ def load_library():
     L.qgd_qgdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 9
     L.qgd_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
                                 _ip, _dp, _dp]
+    L.qgd_qhdfoam_create.argtypes = [C.c_void_p, C.POINTER(QHDFoamDesc), C.POINTER(C.c_void_p)]
+    L.qgd_qhdfoam_destroy.argtypes = [C.c_void_p]
+    L.qgd_qhdfoam_set_bcs.argtypes = [C.c_void_p, _ip, _ip, _ip, _dp, _dp, _dp]
+    L.qgd_qhdfoam_init_fields.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    L.qgd_qhdfoam_step.argtypes = [C.c_void_p, C.c_int]
+    L.qgd_qhdfoam_get.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
+    L.qgd_qhdfoam_get_flux.argtypes = [C.c_void_p, _dp]
+    L.qgd_qhdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.qgd_qhdfoam_solver_info.argtypes = [C.c_void_p, _ip, _dp, _dp]
+    L.qgd_qhdfoam_launch_count.restype = C.c_longlong
+    L.qgd_qhdfoam_launch_count.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -347,6 +371,95 @@ class QGDFoam:
     def close(self):
         if getattr(self, "_h", None):
             load_library().qgd_qgdfoam_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+PRECONDS = {"none": 0, "diagonal": 1, "DIC": 2}
+
+
+def pcg_solve(mesh: Mesh, diag, upper, b, x0, tol=1e-8, rel_tol=0.0, max_iter=1000, precond="DIC"):
+    """lduMatrix PCG on the mesh addressing, fully on the device (qgd_pcg_solve)."""
+    diag, upper, b = _f64(diag), _f64(upper), _f64(b)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    it, r0, r1 = C.c_int(), C.c_double(), C.c_double()
+    _check(load_library().qgd_pcg_solve(mesh._h, _d(diag), _d(upper), _d(b), _d(x), tol, rel_tol, max_iter,
+                                        PRECONDS[precond], C.byref(it), C.byref(r0), C.byref(r1)))
+    return x, it.value, r0.value, r1.value
+
+
+QHD_FIELDS = {"U": (0, 3), "T": (1, 1), "p": (2, 1), "tauQGD": (3, 1)}
+
+
+class QHDFoam:
+    """The QHDFoam time loop on the device (QHDFoam.C:83-139, explicit branch)."""
+
+    def __init__(self, mesh: Mesh, *, rho0, mu, Pr, beta, g, fvsc_scheme="GaussVolPoint", qgd_coeffs="constTau",
+                 Tau=0.0, UQHD=1.0, Gr=1.0, T0=1.0, implicit_diffusion=False, tol=1e-8, rel_tol=0.0, max_iter=1000,
+                 precond="DIC", p_ref_cell=0, p_ref_value=0.0, adjust_time_step=False, max_co=0.3, max_delta_t=1e30,
+                 c_tau=0.75, delta_t=1e-3):
+        self.mesh = mesh
+        d = QHDFoamDesc()
+        self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), precond.encode())
+        d.fvsc_scheme, d.qgd_coeffs_model, d.p_preconditioner = self._names
+        d.rho0, d.mu, d.Pr, d.beta = rho0, mu, Pr, beta
+        for j in range(3):
+            d.g[j] = g[j]
+        d.Tau, d.UQHD, d.Gr, d.T0 = Tau, UQHD, Gr, T0
+        d.implicit_diffusion = int(implicit_diffusion)
+        d.p_tolerance, d.p_rel_tol, d.p_max_iter = tol, rel_tol, max_iter
+        d.p_ref_cell, d.p_ref_value = p_ref_cell, p_ref_value
+        d.adjust_time_step = int(adjust_time_step)
+        d.max_co, d.max_delta_t, d.c_tau, d.delta_t = max_co, max_delta_t, c_tau, delta_t
+        self._h = C.c_void_p()
+        _check(load_library().qgd_qhdfoam_create(mesh._h, C.byref(d), C.byref(self._h)))
+
+    def set_bcs(self, bcU, bcT, bcP, valU=None, valT=None, valP=None):
+        a = [np.ascontiguousarray(x, np.int32) for x in (bcU, bcT, bcP)]
+        v = [_f64(x) for x in (valU, valT, valP)]
+        _check(load_library().qgd_qhdfoam_set_bcs(self._h, _i(a[0]), _i(a[1]), _i(a[2]), _d(v[0]), _d(v[1]), _d(v[2])))
+
+    def init_fields(self, U, T, p, alphaQGD=None):
+        U, T, p, alphaQGD = _f64(U), _f64(T), _f64(p), _f64(alphaQGD)
+        _check(load_library().qgd_qhdfoam_init_fields(self._h, _d(U), _d(T), _d(p), _d(alphaQGD)))
+
+    def step(self, n_steps: int = 1):
+        _check(load_library().qgd_qhdfoam_step(self._h, n_steps))
+
+    def get(self, name: str, with_bnd: bool = False):
+        fid, k = QHD_FIELDS[name]
+        m = self.mesh.mesh
+        cells = np.zeros((m.n_cells, k) if k > 1 else m.n_cells)
+        bnd = np.zeros((m.n_bnd, k) if k > 1 else m.n_bnd) if with_bnd else None
+        _check(load_library().qgd_qhdfoam_get(self._h, fid, _d(cells), _d(bnd)))
+        return (cells, bnd) if with_bnd else cells
+
+    def get_flux(self):
+        out = np.zeros(self.mesh.mesh.n_faces)
+        _check(load_library().qgd_qhdfoam_get_flux(self._h, _d(out)))
+        return out
+
+    def scalars(self):
+        dt, co, t = C.c_double(), C.c_double(), C.c_double()
+        _check(load_library().qgd_qhdfoam_get_scalars(self._h, C.byref(dt), C.byref(co), C.byref(t)))
+        return dict(deltaT=dt.value, CoNum=co.value, time=t.value)
+
+    def solver_info(self):
+        it, r0, r1 = C.c_int(), C.c_double(), C.c_double()
+        _check(load_library().qgd_qhdfoam_solver_info(self._h, C.byref(it), C.byref(r0), C.byref(r1)))
+        return dict(iters=it.value, initial_residual=r0.value, final_residual=r1.value)
+
+    def launch_count(self) -> int:
+        return int(load_library().qgd_qhdfoam_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().qgd_qhdfoam_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -10,6 +10,7 @@
 #include <memory>
 
 #include "qgd_kernels.cuh"
+#include "qgd_pcg.cuh"
 
 namespace qgd {
 
@@ -63,17 +64,11 @@ static void loadNccl()
                                                __FILE__ + ":" + std::to_string(__LINE__));                    \
     } while (0)
 
-static void requireInit()
+void requireInit()
 {
     if (!g_initialised) throw Error(QGD_ERR_STATE, "qgd_init(device) must be called first (no CPU fallback exists)");
 }
-
-template <class F> static int guarded(F&& fn)
-{
-    try { fn(); return QGD_OK; }
-    catch (const Error& e) { setLastError(e.what()); return e.code; }
-    catch (const std::exception& e) { setLastError(e.what()); return QGD_ERR_INVALID; }
-}
+cudaStream_t runtimeStream() { return g_stream; }
 
 // runTimeSelection tables of the path (names only; the OpenFOAM shim registers the same TypeNames)
 static const char* const kFvscTable[] = {"GaussVolPoint", "leastSquares", "leastSquaresOpt", "reduced"};          // sortedToc order
@@ -92,33 +87,12 @@ template <size_t N> static bool inTable(const char* const (&t)[N], const std::st
     for (size_t i = 0; i < N; ++i) if (n == t[i]) return true;
     return false;
 }
+bool isCoeffsModel(const std::string& n) { return inTable(kCoeffsTable, n); }
+std::string coeffsModelToc() { return toc(kCoeffsTable); }
 
 } // namespace qgd
 
 using namespace qgd;
-
-struct qgd_fvsc {
-    qgd_mesh* mesh = nullptr;
-    bool reduced = false;
-    DevBuf<int4> vtx;
-    DevBuf<int> flags;
-    DevBuf<double> G, halfDist;
-    // staging for operator-level calls (grown on demand)
-    DevBuf<double> dCell, dBnd, dBsg, dNbr, dPts, dOut;
-    FaceView view() const
-    {
-        const qgd_mesh& m = *mesh;
-        FaceView v;
-        v.nI = m.h.nInternal; v.nF = m.h.nFaces; v.nB = m.h.nBnd;
-        v.nIActive = m.nIActive;
-        v.zeroDivCmpt = -1;
-        if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
-        v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
-        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
-        v.perm = m.facePermDev.p;
-        return v;
-    }
-};
 
 struct qgd_solver {
     qgd_mesh* mesh = nullptr;
@@ -361,6 +335,35 @@ void runSteps(qgd_solver* s, int n)
 
 } // namespace
 
+void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
+{
+    // fvsc.C:47-85 (fvscOpName checks) + fvscStencil.C:59-95 (New)
+    if (!inTable(kFvscTable, name))
+        throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown Model type " + name + "\n\nValid model types are:\n" + toc(kFvscTable));
+    if ((name == "leastSquares" || name == "leastSquaresOpt")) {
+        if (mesh->h.nD == 3) throw Error(QGD_ERR_INVALID, "Can't use leastSquares or leastSquaresOpt in 3D case.");
+        throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " is not available on the device yet (no CPU fallback)");
+    }
+    op.mesh = mesh;
+    op.reduced = (name == "reduced");
+    std::vector<int> vtx, flags;
+    std::vector<double> G, hd;
+    mesh->h.buildFaceRecords(op.reduced, vtx, flags, G, hd);
+    const int nF = mesh->h.nFaces;
+    const std::vector<int>& perm = mesh->facePerm;
+    std::vector<int4> v4(nF);
+    std::vector<int> fl(nF);
+    std::vector<double> Gp(G.size());
+    for (int f = 0; f < nF; ++f) {
+        const size_t o = perm[f];
+        v4[f] = make_int4(vtx[4 * o], vtx[4 * o + 1], vtx[4 * o + 2], vtx[4 * o + 3]);
+        fl[f] = flags[o];
+        for (int k = 0; k < 9; ++k) Gp[(size_t)k * nF + f] = G[(size_t)k * nF + o];
+    }
+    op.vtx.upload(v4, g_stream); op.flags.upload(fl, g_stream); op.G.upload(Gp, g_stream); op.halfDist.upload(hd, g_stream);
+}
+
+
 // ============================================================================ C ABI
 extern "C" {
 
@@ -509,34 +512,6 @@ int qgd_mesh_get(qgd_mesh* mesh, int what, double* out)
 }
 
 // ---------------------------------------------------------------- fvsc
-static void fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
-{
-    // fvsc.C:47-85 (fvscOpName checks) + fvscStencil.C:59-95 (New)
-    if (!inTable(kFvscTable, name))
-        throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown Model type " + name + "\n\nValid model types are:\n" + toc(kFvscTable));
-    if ((name == "leastSquares" || name == "leastSquaresOpt")) {
-        if (mesh->h.nD == 3) throw Error(QGD_ERR_INVALID, "Can't use leastSquares or leastSquaresOpt in 3D case.");
-        throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " is not available on the device yet (no CPU fallback)");
-    }
-    op.mesh = mesh;
-    op.reduced = (name == "reduced");
-    std::vector<int> vtx, flags;
-    std::vector<double> G, hd;
-    mesh->h.buildFaceRecords(op.reduced, vtx, flags, G, hd);
-    const int nF = mesh->h.nFaces;
-    const std::vector<int>& perm = mesh->facePerm;
-    std::vector<int4> v4(nF);
-    std::vector<int> fl(nF);
-    std::vector<double> Gp(G.size());
-    for (int f = 0; f < nF; ++f) {
-        const size_t o = perm[f];
-        v4[f] = make_int4(vtx[4 * o], vtx[4 * o + 1], vtx[4 * o + 2], vtx[4 * o + 3]);
-        fl[f] = flags[o];
-        for (int k = 0; k < 9; ++k) Gp[(size_t)k * nF + f] = G[(size_t)k * nF + o];
-    }
-    op.vtx.upload(v4, g_stream); op.flags.upload(fl, g_stream); op.G.upload(Gp, g_stream); op.halfDist.upload(hd, g_stream);
-}
-
 int qgd_fvsc_create(qgd_mesh* mesh, const char* scheme_name, qgd_fvsc** out)
 {
     return guarded([&] {
@@ -915,10 +890,27 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* 
     });
 }
 
-int qgd_pcg_solve(qgd_mesh*, const double*, const double*, const double*, double*, double, double, int, int, int*, double*, double*)
+int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x, double tolerance,
+                  double rel_tol, int max_iter, int precond, int* iters, double* initial_residual, double* final_residual)
 {
-    setLastError("qgd_pcg_solve: device PCG not built in this revision");
-    return QGD_ERR_UNSUPPORTED;
+    return guarded([&] {
+        requireInit();
+        if (!mesh || !diag || !b || !x || (mesh->h.nInternal > 0 && !upper)) throw Error(QGD_ERR_INVALID, "qgd_pcg_solve: null argument");
+        if (precond < 0 || precond > 2) throw Error(QGD_ERR_INVALID, "qgd_pcg_solve: preconditioner must be 0 (none), 1 (diagonal) or 2 (DIC)");
+        PcgMatrix A;
+        A.build(mesh->h, diag, upper, precond, g_stream);
+        const size_t n = mesh->h.nCells;
+        QGD_CUDA(cudaMemcpyAsync(A.b.p, b, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        QGD_CUDA(cudaMemcpyAsync(A.x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        A.solve(tolerance, rel_tol, max_iter, g_stream);
+        PcgResult r;
+        QGD_CUDA(cudaMemcpyAsync(x, A.x.p, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaMemcpyAsync(&r, A.out.p, sizeof(r), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        if (iters) *iters = r.iters;
+        if (initial_residual) *initial_residual = r.res0;
+        if (final_residual) *final_residual = r.res;
+    });
 }
 
 } // extern "C"

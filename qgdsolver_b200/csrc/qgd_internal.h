@@ -28,6 +28,18 @@ void setLastError(const std::string& m);
                                                + __FILE__ + ":" + std::to_string(__LINE__));             \
     } while (0)
 
+// ---------------------------------------------------------------- runtime shared by the C-ABI translation units
+void requireInit();                  // throws QGD_ERR_STATE before qgd_init
+cudaStream_t runtimeStream();        // the library's compute stream
+bool isCoeffsModel(const std::string& name);       // QGDCoeffs runTimeSelection table (QGDCoeffs.C:58-117)
+std::string coeffsModelToc();
+template <class F> int guarded(F&& fn)
+{
+    try { fn(); return QGD_OK; }
+    catch (const Error& e) { setLastError(e.what()); return e.code; }
+    catch (const std::exception& e) { setLastError(e.what()); return QGD_ERR_INVALID; }
+}
+
 // ---------------------------------------------------------------- device buffers
 template <class T> struct DevBuf {
     T* p = nullptr;

@@ -25,6 +25,7 @@ struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     const double* w;         // nF
     const double* hf;        // nF  hQGDf
     const double* dC;        // nF  deltaCoeffs
+    const double* ndC;       // nF  nonOrthDeltaCoeffs
     const double* G;         // SoA 9*nF
     const double* halfDist;  // nB
     const int* bKind;        // nB patch kind per boundary face
@@ -91,3 +92,32 @@ int faceKernelGrid();
 void setFaceVariant(int v);   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
 } // namespace qgd
+
+// one fvsc::fvscStencil instance (fvscStencil.H:46-137): face gradient records of a scheme on a mesh
+struct qgd_fvsc {
+    qgd_mesh* mesh = nullptr;
+    bool reduced = false;
+    qgd::DevBuf<int4> vtx;
+    qgd::DevBuf<int> flags;
+    qgd::DevBuf<double> G, halfDist;
+    // staging for operator-level calls (grown on demand)
+    qgd::DevBuf<double> dCell, dBnd, dBsg, dNbr, dPts, dOut;
+    qgd::FaceView view() const
+    {
+        const qgd_mesh& m = *mesh;
+        qgd::FaceView v;
+        v.nI = m.h.nInternal; v.nF = m.h.nFaces; v.nB = m.h.nBnd;
+        v.nIActive = m.nIActive;
+        v.zeroDivCmpt = -1;
+        if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
+        v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
+        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
+        v.perm = m.facePermDev.p;
+        return v;
+    }
+};
+
+namespace qgd {
+// fvsc.C:47-85 (fvscOpName checks) + fvscStencil.C:59-95 (New); throws qgd::Error with the reference's messages
+void fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name);
+}

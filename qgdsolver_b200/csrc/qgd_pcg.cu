@@ -1,0 +1,337 @@
+// Device-resident PCG for symmetric LDU matrices (see qgd_pcg.cuh).  Algorithm = OpenFOAM v2312 PCG.C / DICPreconditioner.C /
+// diagonalPreconditioner.C / lduMatrix::solver::normFactor as restated in SURVEY.md App. A.5 (call site QHDpEqn.H:45):
+//   wA = A x ; rA = b - wA ; normFactor = sum(|wA - xRef*sumA| + |b - xRef*sumA|) + 1e-20 ; residual = sum|rA|/normFactor
+//   loop: wA = M^-1 rA ; wArA = wA.rA ; pA = wA + (wArA/wArAold) pA ; wA = A pA ; alpha = wArA/(wA.pA) ; x += alpha pA ;
+//         rA -= alpha wA
+// B200 design: one cooperative persistent kernel, 2 grid-wide reductions per iteration (Jacobi), SpMV as an atomic-free
+// row gather over the cell->face ELL, p-update fused into the SpMV by recomputing the neighbours' p on the fly,
+// reductions = warp shuffles -> per-block partial -> every block sums the partials in a fixed order (deterministic).
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "qgd_pcg.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace qgd {
+
+namespace {
+
+constexpr int kPcgBlock = 256;
+
+// grid-wide sum of two values; identical result in every thread of the grid
+__device__ double2 gridSum2(cg::grid_group& grid, double a, double b, double* partials, int& slot)
+{
+    __shared__ double sa[kPcgBlock / 32], sb[kPcgBlock / 32];
+    __shared__ double2 tot;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sa[wid] = a; sb[wid] = b; }
+    __syncthreads();
+    const int G = gridDim.x;
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+#pragma unroll
+        for (int k = 0; k < kPcgBlock / 32; ++k) { x += sa[k]; y += sb[k]; }
+        __stcg(&partials[(size_t)(slot * 2 + 0) * G + blockIdx.x], x);
+        __stcg(&partials[(size_t)(slot * 2 + 1) * G + blockIdx.x], y);
+    }
+    grid.sync();
+    if (threadIdx.x < 32) {
+        double x = 0.0, y = 0.0;
+        for (int i = lane; i < G; i += 32) {
+            x += __ldcg(&partials[(size_t)(slot * 2 + 0) * G + i]);
+            y += __ldcg(&partials[(size_t)(slot * 2 + 1) * G + i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { x += __shfl_down_sync(0xffffffffu, x, o); y += __shfl_down_sync(0xffffffffu, y, o); }
+        if (lane == 0) tot = make_double2(x, y);
+    }
+    __syncthreads();
+    const double2 r = tot;
+    __syncthreads();
+    slot ^= 1;
+    return r;
+}
+
+// DIC: z = rD r ; forward sweep (ascending levels) ; backward sweep (descending levels) ; returns sum(z*r) contributions
+template <int WT>
+__device__ void dicSweeps(cg::grid_group& grid, const PcgView& v, int tid, int nth)
+{
+    const int n = v.n, W = WT ? WT : v.W;
+    for (int c = tid; c < n; c += nth) v.z[c] = __ldg(&v.rD[c]) * v.r[c];
+    grid.sync();
+    for (int l = 1; l < v.nLevels; ++l) {          // wA[u] -= rD[u]*upper*wA[l], faces ascending
+        for (int i = __ldg(&v.lvlOff[l]) + tid; i < __ldg(&v.lvlOff[l + 1]); i += nth) {
+            const int c = __ldg(&v.lvlCells[i]);
+            const double rd = __ldg(&v.rD[c]);
+            double zc = v.z[c];
+            for (int j = 0; j < W; ++j) {
+                const int e = __ldg(&v.enc[(size_t)j * n + c]);
+                if (e & 1) zc -= rd * __ldg(&v.coef[(size_t)j * n + c]) * v.z[e >> 1];
+            }
+            for (int q = __ldg(&v.tailOff[c]); q < __ldg(&v.tailOff[c + 1]); ++q) {
+                const int e = __ldg(&v.tailEnc[q]);
+                if (e & 1) zc -= rd * __ldg(&v.tailCoef[q]) * v.z[e >> 1];
+            }
+            v.z[c] = zc;
+        }
+        grid.sync();
+    }
+    for (int l = v.nLevels - 2; l >= 0; --l) {     // wA[l] -= rD[l]*upper*wA[u], faces descending
+        for (int i = __ldg(&v.lvlOff[l]) + tid; i < __ldg(&v.lvlOff[l + 1]); i += nth) {
+            const int c = __ldg(&v.lvlCells[i]);
+            const double rd = __ldg(&v.rD[c]);
+            double zc = v.z[c];
+            for (int q = __ldg(&v.tailOff[c + 1]) - 1; q >= __ldg(&v.tailOff[c]); --q) {
+                const int e = __ldg(&v.tailEnc[q]);
+                if (!(e & 1)) zc -= rd * __ldg(&v.tailCoef[q]) * v.z[e >> 1];
+            }
+            for (int j = W - 1; j >= 0; --j) {
+                const int e = __ldg(&v.enc[(size_t)j * n + c]);
+                if (!(e & 1)) zc -= rd * __ldg(&v.coef[(size_t)j * n + c]) * v.z[e >> 1];
+            }
+            v.z[c] = zc;
+        }
+        grid.sync();
+    }
+}
+
+template <int WT>
+__global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgView v)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int n = v.n, W = WT ? WT : v.W;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    int slot = 0;
+    // ---- wA = A x ; rA = b - wA ; xRef = average(x)
+    double sx = 0.0;
+    for (int c = tid; c < n; c += nth) {
+        const double xc = v.x[c];
+        double y = __ldg(&v.diag[c]) * xc;
+#pragma unroll
+        for (int j = 0; j < W; ++j) y += __ldg(&v.coef[(size_t)j * n + c]) * v.x[__ldg(&v.enc[(size_t)j * n + c]) >> 1];
+        for (int q = __ldg(&v.tailOff[c]); q < __ldg(&v.tailOff[c + 1]); ++q) y += __ldg(&v.tailCoef[q]) * v.x[__ldg(&v.tailEnc[q]) >> 1];
+        v.w[c] = y;
+        v.r[c] = __ldg(&v.b[c]) - y;
+        v.p0[c] = 0.0;
+        sx += xc;
+    }
+    double2 s = gridSum2(grid, sx, 0.0, v.partials, slot);
+    const double xRef = s.x / (double)n;
+    // ---- normFactor and initial residual
+    double nf = 0.0, sr = 0.0;
+    for (int c = tid; c < n; c += nth) {
+        double sumA = __ldg(&v.diag[c]);
+#pragma unroll
+        for (int j = 0; j < W; ++j) sumA += __ldg(&v.coef[(size_t)j * n + c]);
+        for (int q = __ldg(&v.tailOff[c]); q < __ldg(&v.tailOff[c + 1]); ++q) sumA += __ldg(&v.tailCoef[q]);
+        const double t = sumA * xRef;
+        nf += fabs(v.w[c] - t) + fabs(__ldg(&v.b[c]) - t);
+        const double rc = v.r[c];
+        sr += fabs(rc);
+        if (v.precond < 2) v.z[c] = v.precond ? __ldg(&v.rD[c]) * rc : rc;
+    }
+    s = gridSum2(grid, nf, sr, v.partials, slot);
+    const double normFactor = s.x + 1e-20;
+    const double res0 = s.y / normFactor;
+    double res = res0;
+    int it = 0;
+    auto converged = [&]() { return res < v.tol || (v.relTol > 1e-20 && res < v.relTol * res0); };
+    if (!converged() && v.maxIter > 0) {
+        if (v.precond == 2) dicSweeps<WT>(grid, v, tid, nth);
+        double zr = 0.0;
+        for (int c = tid; c < n; c += nth) zr += v.z[c] * v.r[c];
+        s = gridSum2(grid, zr, 0.0, v.partials, slot);
+        double wArA = s.x, wArAold = wArA;
+        double* po = v.p0;
+        double* pn = v.p1;
+        while (true) {
+            const double beta = (it == 0) ? 0.0 : wArA / wArAold;
+            // ---- pA = wA + beta pA (own cell stored, neighbours recomputed) ; wA = A pA ; wApA
+            double wp = 0.0;
+            for (int c = tid; c < n; c += nth) {
+                const double pc = v.z[c] + beta * po[c];
+                double y = __ldg(&v.diag[c]) * pc;
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const int o = __ldg(&v.enc[(size_t)j * n + c]) >> 1;
+                    y += __ldg(&v.coef[(size_t)j * n + c]) * (v.z[o] + beta * po[o]);
+                }
+                for (int q = __ldg(&v.tailOff[c]); q < __ldg(&v.tailOff[c + 1]); ++q) {
+                    const int o = __ldg(&v.tailEnc[q]) >> 1;
+                    y += __ldg(&v.tailCoef[q]) * (v.z[o] + beta * po[o]);
+                }
+                pn[c] = pc;
+                v.w[c] = y;
+                wp += y * pc;
+            }
+            s = gridSum2(grid, wp, 0.0, v.partials, slot);
+            const double wApA = s.x;
+            if (fabs(wApA) / normFactor < 1e-300) break;          // solverPerformance::checkSingularity
+            const double alpha = wArA / wApA;
+            // ---- x += alpha pA ; rA -= alpha wA ; residual ; (Jacobi / none) next wA = M^-1 rA and wArA
+            sr = 0.0; zr = 0.0;
+            for (int c = tid; c < n; c += nth) {
+                v.x[c] += alpha * pn[c];
+                const double rc = v.r[c] - alpha * v.w[c];
+                v.r[c] = rc;
+                sr += fabs(rc);
+                if (v.precond < 2) {
+                    const double zc = v.precond ? __ldg(&v.rD[c]) * rc : rc;
+                    v.z[c] = zc;
+                    zr += zc * rc;
+                }
+            }
+            s = gridSum2(grid, sr, zr, v.partials, slot);
+            res = s.x / normFactor;
+            ++it;
+            double* t = po; po = pn; pn = t;
+            if (it >= v.maxIter || converged()) break;
+            wArAold = wArA;
+            wArA = s.y;
+            if (v.precond == 2) {
+                dicSweeps<WT>(grid, v, tid, nth);
+                zr = 0.0;
+                for (int c = tid; c < n; c += nth) zr += v.z[c] * v.r[c];
+                s = gridSum2(grid, zr, 0.0, v.partials, slot);
+                wArA = s.x;
+            }
+        }
+    }
+    if (tid == 0) { v.out->iters = it; v.out->res0 = res0; v.out->res = res; v.out->normFactor = normFactor; }
+}
+
+// DIC::calcReciprocalD: rD = diag ; for faces ascending: rD[u] -= upper^2/rD[l] ; rD = 1/rD   (level-scheduled, exact order)
+__global__ void __launch_bounds__(kPcgBlock) k_dic_factor(PcgView v, double* rDraw)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int n = v.n, W = v.W;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int l = 0; l < v.nLevels; ++l) {
+        for (int i = __ldg(&v.lvlOff[l]) + tid; i < __ldg(&v.lvlOff[l + 1]); i += nth) {
+            const int c = __ldg(&v.lvlCells[i]);
+            double rc = __ldg(&v.diag[c]);
+            for (int j = 0; j < W; ++j) {
+                const int e = __ldg(&v.enc[(size_t)j * n + c]);
+                const double a = __ldg(&v.coef[(size_t)j * n + c]);
+                if (e & 1) rc -= a * a / rDraw[e >> 1];
+            }
+            for (int q = __ldg(&v.tailOff[c]); q < __ldg(&v.tailOff[c + 1]); ++q) {
+                const int e = __ldg(&v.tailEnc[q]);
+                const double a = __ldg(&v.tailCoef[q]);
+                if (e & 1) rc -= a * a / rDraw[e >> 1];
+            }
+            rDraw[c] = rc;
+        }
+        grid.sync();
+    }
+    for (int c = tid; c < n; c += nth) rDraw[c] = 1.0 / rDraw[c];
+}
+
+__global__ void k_recip(int n, const double* __restrict__ d, double* __restrict__ o)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) o[c] = 1.0 / d[c];
+}
+
+template <class K> int coopGrid(K kernel)
+{
+    int dev = 0, sms = 148, perSM = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kPcgBlock, 0);
+    if (perSM < 1) perSM = 1;
+    if (perSM > 4) perSM = 4;
+    return sms * perSM;
+}
+
+} // namespace
+
+void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* upper, int pc, cudaStream_t st)
+{
+    n = h.nCells;
+    precond = pc;
+    const int nI = h.nInternal;
+    // rows in ascending polyMesh face order (HostMesh::cfEnc), internal faces only
+    int maxRow = 0;
+    std::vector<int> rowLen(n, 0);
+    for (int c = 0; c < n; ++c) {
+        int k = 0;
+        for (int q = h.cfOff[c]; q < h.cfOff[c + 1]; ++q) if ((h.cfEnc[q] >> 1) < nI) ++k;
+        rowLen[c] = k;
+        maxRow = std::max(maxRow, k);
+    }
+    W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+    std::vector<int> e((size_t)W * n), tOff(n + 1, 0), tEnc, level(n, 0);
+    std::vector<double> a((size_t)W * n, 0.0), tCoef;
+    for (int c = 0; c < n; ++c) {
+        for (int j = 0; j < W; ++j) e[(size_t)j * n + c] = c << 1;
+        int j = 0;
+        for (int q = h.cfOff[c]; q < h.cfOff[c + 1]; ++q) {
+            const int f = h.cfEnc[q] >> 1;
+            if (f >= nI) continue;
+            const int lowerSide = h.cfEnc[q] & 1;                  // this cell is the face's neighbour (upper) cell
+            const int o = lowerSide ? h.owner[f] : h.neighbour[f];
+            const int enc1 = (o << 1) | lowerSide;
+            if (lowerSide) level[c] = std::max(level[c], level[o] + 1);      // owner < neighbour: level[o] is final
+            if (j < W) { e[(size_t)j * n + c] = enc1; a[(size_t)j * n + c] = upper[f]; }
+            else { tEnc.push_back(enc1); tCoef.push_back(upper[f]); }
+            ++j;
+        }
+        tOff[c + 1] = (int)tEnc.size();
+    }
+    if (tEnc.empty()) { tEnc.push_back(0); tCoef.push_back(0.0); }
+    for (int f = 0; f < nI; ++f)
+        if (h.owner[f] >= h.neighbour[f]) throw Error(QGD_ERR_INVALID, "PCG: mesh is not in upper-triangular order (owner < neighbour)");
+    nLevels = 0;
+    for (int c = 0; c < n; ++c) nLevels = std::max(nLevels, level[c] + 1);
+    std::vector<int> lOff(nLevels + 1, 0), lCells(n);
+    for (int c = 0; c < n; ++c) lOff[level[c] + 1]++;
+    for (int l = 0; l < nLevels; ++l) lOff[l + 1] += lOff[l];
+    {
+        std::vector<int> pos(lOff.begin(), lOff.end() - 1);
+        for (int c = 0; c < n; ++c) lCells[pos[level[c]]++] = c;
+    }
+    enc.upload(e, st); coef.upload(a, st); tailOff.upload(tOff, st); tailEnc.upload(tEnc, st); tailCoef.upload(tCoef, st);
+    lvlOff.upload(lOff, st); lvlCells.upload(lCells, st);
+    diag.upload(std::vector<double>(hdiag, hdiag + n), st);
+    rD.alloc(n); b.alloc(n); x.alloc(n); r.alloc(n); w.alloc(n); z.alloc(n); p0.alloc(n); p1.alloc(n);
+    out.alloc(1);
+    gridBlocks = std::min(std::min(coopGrid(k_pcg<4>), coopGrid(k_pcg<6>)), coopGrid(k_pcg<8>));
+    gridBlocks = std::max(1, std::min(gridBlocks, (n + kPcgBlock - 1) / kPcgBlock));
+    partials.alloc(4 * (size_t)gridBlocks);
+    if (precond == 1) k_recip<<<(n + 255) / 256, 256, 0, st>>>(n, diag.p, rD.p);
+    else if (precond == 2) {
+        PcgView v = view(0, 0, 0);
+        double* raw = rD.p;
+        void* args[] = {&v, &raw};
+        const int g = std::max(1, std::min(coopGrid(k_dic_factor), (n + kPcgBlock - 1) / kPcgBlock));
+        QGD_CUDA(cudaLaunchCooperativeKernel((void*)k_dic_factor, dim3(g), dim3(kPcgBlock), args, 0, st));
+    }
+    QGD_CUDA(cudaGetLastError());
+    QGD_CUDA(cudaStreamSynchronize(st));
+}
+
+PcgView PcgMatrix::view(double tol, double relTol, int maxIter) const
+{
+    PcgView v;
+    v.n = n; v.W = W; v.enc = enc.p; v.coef = coef.p; v.tailOff = tailOff.p; v.tailEnc = tailEnc.p; v.tailCoef = tailCoef.p;
+    v.diag = diag.p; v.rD = rD.p; v.b = b.p; v.x = xExternal ? xExternal : x.p; v.r = r.p; v.w = w.p; v.z = z.p; v.p0 = p0.p; v.p1 = p1.p;
+    v.partials = partials.p; v.nLevels = nLevels; v.lvlOff = lvlOff.p; v.lvlCells = lvlCells.p;
+    v.tol = tol; v.relTol = relTol; v.maxIter = maxIter; v.precond = precond; v.out = out.p;
+    return v;
+}
+
+int PcgMatrix::solve(double tol, double relTol, int maxIter, cudaStream_t st)
+{
+    PcgView v = view(tol, relTol, maxIter);
+    void* args[] = {&v};
+    void* fn = (W == 4) ? (void*)k_pcg<4> : (W == 6 ? (void*)k_pcg<6> : (void*)k_pcg<8>);
+    QGD_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks), dim3(kPcgBlock), args, 0, st));
+    return 1;
+}
+
+} // namespace qgd

@@ -1,0 +1,42 @@
+// Device-resident LDU PCG (lduMatrix PCG + DIC | diagonal | none, [OF-v2312], called at QHDpEqn.H:45).
+// The whole solve — initial residual, normFactor, every iteration and the convergence test — runs inside ONE
+// cooperative persistent kernel; vectors of a ~1M-cell problem stay resident in the 126 MB L2.
+#pragma once
+#include "qgd_internal.h"
+
+namespace qgd {
+
+struct PcgResult { int iters; int pad; double res0, res, normFactor; };
+
+// symmetric matrix in row form: ELL (column-major [W][n]) + CSR tail, entries of a row in ascending polyMesh face order;
+// enc = (otherCell << 1) | lowerSide   (lowerSide: the other cell has the smaller index -> forward-sweep dependency)
+struct PcgView {
+    int n, W;
+    const int* enc; const double* coef;
+    const int* tailOff; const int* tailEnc; const double* tailCoef;
+    const double* diag;          // incl. boundary (internalCoeffs) contribution
+    const double* rD;            // precond 1: 1/diag ; precond 2: DIC reciprocal diagonal ; precond 0: unused
+    const double* b;
+    double* x;
+    double* r; double* w; double* z; double* p0; double* p1;
+    double* partials;            // [2 slots][2 values][gridDim.x]
+    int nLevels; const int* lvlOff; const int* lvlCells;     // DIC level schedule (cells grouped by dependency depth)
+    double tol, relTol; int maxIter, precond;
+    PcgResult* out;
+};
+
+struct PcgMatrix {
+    int n = 0, W = 0, nLevels = 0, precond = -1;
+    DevBuf<int> enc, tailOff, tailEnc, lvlOff, lvlCells;
+    DevBuf<double> coef, tailCoef, diag, rD, b, x, r, w, z, p0, p1, partials;
+    DevBuf<PcgResult> out;
+    int gridBlocks = 0;
+    double* xExternal = nullptr;     // when set, the solution vector lives in the caller's array (e.g. the p slice of the QHD state)
+    // diag: nCells (boundary contributions already added), upper: nInternal in polyMesh face order
+    void build(const HostMesh& h, const double* diag, const double* upper, int precond, cudaStream_t st);
+    PcgView view(double tol, double relTol, int maxIter) const;
+    // solves A x = b for the device vectors b, x (in place); returns kernel launches issued
+    int solve(double tol, double relTol, int maxIter, cudaStream_t st);
+};
+
+} // namespace qgd
