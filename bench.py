@@ -220,14 +220,17 @@ def run_product(args):
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-            if tj.get("n_cells") == mesh.n_cells:
+            if tj.get("n_cells") == mesh.n_cells and kname in tj.get("kernel", ""):
                 traffic = tj.get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "k_face_flux", "achieved": ab["face"] / (face_ms * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": ab["face"] / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                "alg_bytes_per_launch": ab["face"], "avg_launch_ms": face_ms,
+    pipe = s.get_pipeline()
+    kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else "k_face_flux"
+    kbytes = ab["face"] + ab["cell"] if pipe["mode"] == 1 else ab["face"]
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": kbytes / (face_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": kbytes / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": kbytes, "avg_launch_ms": face_ms, "pipeline": pipe,
                 "step": {"alg_bytes": ab["total"], "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
                          "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak},
-                "kernel_ms": {"k_points": kt["points_ms"] / max(kt["steps"], 1), "k_face_flux": face_ms,
+                "kernel_ms": {"k_points": kt["points_ms"] / max(kt["steps"], 1), kname: face_ms,
                               "k_cell_update": kt["cell_ms"] / max(kt["steps"], 1)}}
     # ---- end-to-end through the C-ABI with host (pinned) buffers: state uploaded and downloaded every step
     nC = mesh.n_cells

@@ -173,6 +173,14 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd);
  * (phiJmH+phiQ-phiPiU); n_faces*k host buffer */
 int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out);
 int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, double* time);
+/* Step form.  mode 0 (default): two kernels (faces, then cells) with a full-size flux array; always used with
+ * adjustTimeStep, whose global Courant maximum must be known before any cell is updated; needed for
+ * qgd_qgdfoam_get_flux.  mode 1 (fixed deltaT only): internal faces and cells are processed by ONE persistent kernel whose
+ * work queue interleaves face chunks and cell chunks; the 5 flux doubles per face live in an L2-resident ring instead of
+ * an HBM array (DESIGN.md "flux ring").  chunk_cells / lag / ring_slots: 0 / -1 / 0 select the defaults.  Results are
+ * bit-identical in both forms. */
+int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, int ring_slots);
+int qgd_qgdfoam_get_pipeline(qgd_solver* s, int* mode, int* chunk_cells, int* lag, int* ring_slots, int* n_chunks, int* grid);
 /* kernel launches issued by this solver so far (bench bookkeeping) */
 long long qgd_qgdfoam_launch_count(qgd_solver* s);
 /* per-kernel CUDA-event timing on the solver stream: enable, run steps, then read the summed durations (ms) of the

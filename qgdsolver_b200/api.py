@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
+    "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline",
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
     "qgd_pcg_solve",
@@ -116,6 +117,8 @@ def load_library():
     L.qgd_qgdfoam_profile.argtypes = [C.c_void_p, C.c_int]
     L.qgd_qgdfoam_kernel_times.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip]
     L.qgd_timer_end.argtypes = [C.POINTER(C.c_float)]
+    L.qgd_qgdfoam_set_pipeline.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.qgd_qgdfoam_get_pipeline.argtypes = [C.c_void_p] + [_ip] * 6
     L.qgd_comm_unique_id.argtypes = [C.c_void_p]
     L.qgd_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.qgd_qgdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 9
@@ -356,6 +359,15 @@ class QGDFoam:
         dt, co, t = C.c_double(), C.c_double(), C.c_double()
         _check(load_library().qgd_qgdfoam_get_scalars(self._h, C.byref(dt), C.byref(co), C.byref(t)))
         return dict(deltaT=dt.value, CoNum=co.value, time=t.value)
+
+    def set_pipeline(self, mode: int, chunk_cells: int = 0, lag: int = -1, ring_slots: int = 0):
+        """mode 1: pipelined face+cell kernel with the L2-resident flux ring; mode 0: two kernels, fluxes kept in HBM."""
+        _check(load_library().qgd_qgdfoam_set_pipeline(self._h, mode, chunk_cells, lag, ring_slots))
+
+    def get_pipeline(self):
+        v = [C.c_int() for _ in range(6)]
+        _check(load_library().qgd_qgdfoam_get_pipeline(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("mode", "chunk_cells", "lag", "ring_slots", "n_chunks", "grid"), [x.value for x in v]))
 
     def profile(self, enable: bool):
         _check(load_library().qgd_qgdfoam_profile(self._h, int(enable)))

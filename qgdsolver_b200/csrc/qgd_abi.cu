@@ -102,7 +102,25 @@ struct qgd_solver {
     DevBuf<RecA> bA;
     DevBuf<RecB> bB;
     DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
-    DevBuf<double> aQGD, Fm, FU, FE, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage;
+    DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage;
+    // face fluxes (layout: SolverView::F): one [5][nF] array (two-kernel form) or [5][ring] + [5][nB] (pipelined form)
+    size_t strideI = 0, strideB = 0, bndOff = 0;
+    int ringSize = 0x7fffffff;
+    // pipelined face+cell kernel (fixed deltaT): plan + flags.  mode: 0 two kernels, 1 pipelined
+    struct Pipe {
+        int mode = 0, chunkCells = 512, lag = 0, ringSlots = 0, nChunks = 0, epoch = 0, grid = 0;
+        bool windowSet = false;
+        DevBuf<int> cellOff, faceOff, depOff, depList, ringOff, ringList, doneF, doneC, queue;
+    } pipe;
+    PipeView pview()
+    {
+        PipeView v;
+        v.nChunks = pipe.nChunks; v.lag = std::min(pipe.lag, pipe.nChunks); v.epoch = pipe.epoch;
+        v.cellOff = pipe.cellOff.p; v.faceOff = pipe.faceOff.p; v.depOff = pipe.depOff.p; v.depList = pipe.depList.p;
+        v.ringOff = pipe.ringOff.p; v.ringList = pipe.ringList.p;
+        v.doneF = pipe.doneF.p; v.doneC = pipe.doneC.p; v.queue = pipe.queue.p;
+        return v;
+    }
     DevBuf<int> bcU, bcT, bcP;
     DevBuf<StepScalars> sc;
     long long launches = 0;
@@ -132,7 +150,8 @@ struct qgd_solver {
         s.pcTailOff = m.pcTailOff.p; s.pcTailCell = m.pcTailCell.p; s.pcTailW = m.pcTailW.p;
         s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
         s.cfEllW = m.cfEllW; s.cfEll = m.cfEll.p; s.cfTailOff = m.cfTailOff.p; s.cfTailEnc = m.cfTailEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
-        s.Fm = Fm.p; s.FU = FU.p; s.FE = FE.p; s.sc = sc.p;
+        for (int q = 0; q < 5; ++q) { s.FI[q] = Fflux.p + q * strideI; s.FB[q] = Fflux.p + bndOff + q * strideB; }
+        s.ringSize = ringSize; s.sc = sc.p;
         return s;
     }
     BndState bview() const
@@ -299,6 +318,133 @@ int haloExchangeMid(qgd_solver* s)
     return launches;
 }
 
+// (Re)build the flux storage and, for mode 1, the work plan of k_face_cell_pipeline.
+//   chunkCells: cells per work item (multiple of 32; 0 = default) ; lag: chunks between F(k) and C(k) in the queue (<0 = default)
+//   ringSlots: ring size in faces (power of two; 0 = sized from the mesh band width and the L2 persisting carve-out)
+void configurePipeline(qgd_solver* s, int mode, int chunkCells, int lag, int ringSlots)
+{
+    const qgd_mesh& m = *s->mesh;
+    const HostMesh& h = m.h;
+    const int nI = h.nInternal, nIA = m.nIActive, nOwn = h.nOwned;
+    qgd_solver::Pipe& P = s->pipe;
+    if (mode == 1 && s->desc.adjust_time_step) mode = 0;        // the global Courant max is needed before any cell update
+    if (mode == 1 && nIA == 0) mode = 0;
+    auto fullArrays = [&] {
+        P.mode = 0;
+        s->strideI = s->strideB = (size_t)h.nFaces; s->bndOff = (size_t)nI;
+        s->ringSize = 0x7fffffff;
+        s->Fflux.alloc(5 * (size_t)h.nFaces + 1); s->Fflux.zero(g_stream);
+    };
+    if (mode == 0) { fullArrays(); return; }
+    if (const char* v = getenv("QGD_PIPE_CHUNK")) if (!chunkCells) chunkCells = atoi(v);
+    if (const char* v = getenv("QGD_PIPE_LAG")) if (lag < 0) lag = atoi(v);
+    if (const char* v = getenv("QGD_PIPE_RING")) if (!ringSlots) ringSlots = atoi(v);
+    if (chunkCells <= 0) chunkCells = 1024;
+    chunkCells = ((chunkCells + 31) / 32) * 32;
+    P.grid = pipelineKernelGrid(m.cfEllW);
+    if (lag < 0) lag = P.grid / 2 + 8;
+    const int nCh = (nOwn + chunkCells - 1) / chunkCells;
+    lag = std::min(lag, nCh);
+    // device-order face -> owner chunk must be non-decreasing (faces are sorted by owner tile of 32)
+    std::vector<int> cellOff(nCh + 1), faceOff(nCh + 1, 0), depLo(nCh);
+    std::vector<std::vector<int>> deps(nCh), cons(nCh);           // C(k) <- F(deps[k]) ; faces owned by chunk i are read by C(cons[i])
+    auto addUnique = [](std::vector<int>& v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (int k = 0; k <= nCh; ++k) cellOff[k] = std::min(k * chunkCells, nOwn);
+    for (int k = 0; k < nCh; ++k) depLo[k] = k;
+    int prev = 0;
+    for (int f = 0; f < nIA; ++f) {
+        const int pf = m.facePerm[f];
+        const int co = h.owner[pf] / chunkCells;
+        if (co < prev) { fullArrays(); return; }                  // unexpected order: keep the two-kernel form
+        prev = co;
+        faceOff[co + 1]++;
+        addUnique(deps[co], co); addUnique(cons[co], co);
+        const int nb = h.neighbour[pf];
+        if (nb < nOwn) {
+            const int cn = nb / chunkCells;
+            if (cn < co) { fullArrays(); return; }                // not upper-triangular
+            addUnique(deps[cn], co); addUnique(cons[co], cn);
+            depLo[cn] = std::min(depLo[cn], co);
+        }
+    }
+    for (int k = 0; k < nCh; ++k) faceOff[k + 1] += faceOff[k];
+    // ring size
+    int maxChunkFaces = 1;
+    for (int k = 0; k < nCh; ++k) maxChunkFaces = std::max(maxChunkFaces, faceOff[k + 1] - faceOff[k]);
+    int R = ringSlots;
+    if (R <= 0) {
+        // faces that must coexist: from the oldest face a C item still needs to the newest face in flight
+        // (lag chunks queued ahead of C(j) + one F item per two resident CTAs)
+        long need = 0;
+        for (int j = 0; j < nCh; ++j) {
+            const int hiChunk = std::min(nCh, j + lag + P.grid / 2 + 8);
+            need = std::max(need, (long)faceOff[hiChunk] - faceOff[depLo[j]]);
+        }
+        R = (int)std::min<long>(need, nIA);
+    }
+    R = std::max(R, 2 * maxChunkFaces);
+    R = ((R + 31) / 32) * 32;
+    std::vector<std::vector<int>> ring(nCh);
+    if (R >= nIA) R = ((nIA + 31) / 32) * 32;                    // no wrap-around
+    else {
+        // F(k) rewrites the slots of faces [faceOff[k]-R, faceOff[k+1]-R): their consumers must be done
+        auto chunkOf = [&](int f) { return (int)(std::upper_bound(faceOff.begin(), faceOff.end(), f) - faceOff.begin()) - 1; };
+        std::vector<int> posF(nCh), posC(nCh);                    // queue position of every item
+        for (int k = 0; k < nCh; ++k) posF[k] = k < lag ? k : lag + 2 * (k - lag);
+        for (int j = 0; j < nCh; ++j) posC[j] = j < nCh - lag ? lag + 2 * j + 1 : lag + 2 * (nCh - lag) + (j - (nCh - lag));
+        bool ok = true;
+        for (int k = 0; k < nCh && ok; ++k) {
+            const int a = faceOff[k] - R, b = faceOff[k + 1] - R;
+            if (b <= 0 || faceOff[k + 1] == faceOff[k]) continue;
+            const int i0 = chunkOf(std::max(a, 0)), i1 = chunkOf(b - 1);
+            for (int i = i0; i <= i1; ++i)
+                for (int c : cons[i]) { addUnique(ring[k], c); if (posC[c] >= posF[k]) ok = false; }   // later item: deadlock
+        }
+        if (!ok) {
+            if (ringSlots > 0) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_pipeline: ring too small for this mesh band width / lag");
+            fullArrays();
+            return;
+        }
+    }
+    auto csr = [&](const std::vector<std::vector<int>>& v, std::vector<int>& off, std::vector<int>& list) {
+        off.assign(nCh + 1, 0);
+        list.clear();
+        for (int k = 0; k < nCh; ++k) { list.insert(list.end(), v[k].begin(), v[k].end()); off[k + 1] = (int)list.size(); }
+        if (list.empty()) list.push_back(0);
+    };
+    std::vector<int> depOff, depList, ringOff, ringList;
+    csr(deps, depOff, depList); csr(ring, ringOff, ringList);
+    P.mode = 1; P.chunkCells = chunkCells; P.lag = lag; P.ringSlots = R; P.nChunks = nCh; P.epoch = 0;
+    s->strideI = (size_t)R; s->strideB = (size_t)std::max(h.nBnd, 1); s->bndOff = 5 * (size_t)R; s->ringSize = R;
+    s->Fflux.alloc(5 * (size_t)R + 5 * s->strideB); s->Fflux.zero(g_stream);
+    P.cellOff.upload(cellOff, g_stream); P.faceOff.upload(faceOff, g_stream);
+    P.depOff.upload(depOff, g_stream); P.depList.upload(depList, g_stream); P.ringOff.upload(ringOff, g_stream); P.ringList.upload(ringList, g_stream);
+    P.doneF.alloc(nCh); P.doneC.alloc(nCh); P.queue.alloc(1);
+    P.doneF.zero(g_stream); P.doneC.zero(g_stream); P.queue.zero(g_stream);
+    // keep the ring resident: L2 persisting carve-out + access-policy window on the library stream
+    {
+        int dev = 0, maxPersist = 0, maxWindow = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t bytes = 5 * (size_t)R * sizeof(double);
+        const bool wrap = (size_t)R < (size_t)nIA;
+        if (wrap && maxPersist > 0 && maxWindow > 0 && !getenv("QGD_PIPE_NO_PERSIST")) {
+            const size_t carve = std::min((size_t)maxPersist, bytes);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = s->Fflux.p;
+            attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)maxWindow);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)std::min(bytes, (size_t)maxWindow));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) P.windowSet = true;
+            cudaGetLastError();
+        }
+    }
+    QGD_CUDA(cudaStreamSynchronize(g_stream));
+}
+
 void runSteps(qgd_solver* s, int n)
 {
     const FaceView fv = s->fvsc->view();
@@ -326,8 +472,11 @@ void runSteps(qgd_solver* s, int n)
             ev = &s->events[s->eventsUsed];
             s->eventsUsed += 6;
         }
+        PipeView pv;
+        const bool usePipe = s->pipe.mode == 1 && !s->desc.adjust_time_step;
+        if (usePipe) { ++s->pipe.epoch; pv = s->pview(); }
         s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev,
-                                  multi ? &hooks : nullptr);
+                                  multi ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid);
         if (multi) s->launches += haloExchange(s);
     }
     QGD_CUDA(cudaGetLastError());
@@ -590,9 +739,10 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
         s->aQGD.alloc(h.nCells);
-        s->Fm.alloc(h.nFaces); s->FU.alloc(3 * (size_t)h.nFaces); s->FE.alloc(h.nFaces);
         s->psiB.alloc(h.nBnd); s->pGrad.alloc(h.nBnd); s->pNew.alloc(h.nBnd); s->phiw.alloc(h.nBnd);
-        s->P.zero(g_stream); s->Fm.zero(g_stream); s->FU.zero(g_stream); s->FE.zero(g_stream);
+        s->P.zero(g_stream);
+        // default step form: two kernels (measured faster on B200 at 256^3); QGD_PIPELINE=1 opts in
+        configurePipeline(s.get(), (getenv("QGD_PIPELINE") && atoi(getenv("QGD_PIPELINE")) && !d->adjust_time_step) ? 1 : 0, 0, -1, 0);
         StepScalars sc{};
         sc.dt = d->delta_t; sc.time = 0.0; sc.coNum = -1.0; sc.coMaxBits = 0ull;
         const double big = DBL_MAX;
@@ -765,15 +915,20 @@ int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out)
     return guarded([&] {
         requireInit();
         if (!s || !out) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: null argument");
-        const size_t nF = s->mesh->h.nFaces;
+        if (s->pipe.mode != 0)
+            throw Error(QGD_ERR_STATE, "qgd_qgdfoam_get_flux: face fluxes are not kept in HBM by the pipelined step; call "
+                                       "qgd_qgdfoam_set_pipeline(s, 0, ...) before stepping to keep them");
+        if (which < 0 || which > 2) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: unknown flux id");
+        const HostMesh& h = s->mesh->h;
+        const size_t nF = h.nFaces;
         const std::vector<int>& perm = s->mesh->facePerm;
         const int k = (which == 1) ? 3 : 1;
-        const double* src = which == 0 ? s->Fm.p : (which == 1 ? s->FU.p : (which == 2 ? s->FE.p : nullptr));
-        if (!src) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_flux: unknown flux id");
-        std::vector<double> t(k * nF);
-        d2h(t.data(), src, k * nF);
+        const size_t off = which == 0 ? 0 : (which == 1 ? 1 : 4);
+        std::vector<double> t(k * nF + 1);
+        d2h(t.data(), s->Fflux.p + off * nF, k * nF);              // two-kernel form: one [5][nF] array
         QGD_CUDA(cudaStreamSynchronize(g_stream));
-        for (size_t f = 0; f < nF; ++f) for (int d = 0; d < k; ++d) out[(size_t)k * perm[f] + d] = t[d * nF + f];
+        for (size_t f = 0; f < nF; ++f)
+            for (int d = 0; d < k; ++d) out[(size_t)k * perm[f] + d] = t[d * nF + f];
     });
 }
 
@@ -792,6 +947,30 @@ int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, dou
 }
 
 long long qgd_qgdfoam_launch_count(qgd_solver* s) { return s ? s->launches : 0; }
+
+int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, int ring_slots)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_pipeline: null solver");
+        if (mode != 0 && mode != 1) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_pipeline: mode must be 0 or 1");
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        configurePipeline(s, mode, chunk_cells, lag, ring_slots);
+    });
+}
+
+int qgd_qgdfoam_get_pipeline(qgd_solver* s, int* mode, int* chunk_cells, int* lag, int* ring_slots, int* n_chunks, int* grid)
+{
+    return guarded([&] {
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get_pipeline: null solver");
+        if (mode) *mode = s->pipe.mode;
+        if (chunk_cells) *chunk_cells = s->pipe.chunkCells;
+        if (lag) *lag = s->pipe.lag;
+        if (ring_slots) *ring_slots = s->pipe.mode ? s->pipe.ringSlots : 0;
+        if (n_chunks) *n_chunks = s->pipe.mode ? s->pipe.nChunks : 0;
+        if (grid) *grid = s->pipe.grid;
+    });
+}
 
 int qgd_qgdfoam_profile(qgd_solver* s, int enable)
 {

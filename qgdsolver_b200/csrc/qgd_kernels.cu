@@ -523,15 +523,14 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
     if (b < fv.nB) {
         const int f = fv.nI + b;
         if (fv.bKind[b] == QGD_PATCH_EMPTY || fv.own[f] >= sv.nOwned) {
-            sv.Fm[f] = 0.0; sv.FE[f] = 0.0;
-            sv.FU[f] = 0.0; sv.FU[(size_t)fv.nF + f] = 0.0; sv.FU[2 * (size_t)fv.nF + f] = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) sv.FB[q][b] = 0.0;
         } else {
             BndFace bf;
             bndFaceSetup(k, fv, sv, bs, b, true, bf);
             double Fm, FU[3], FE, phiw;
             qgdFluxes(k, bf.s, bf.g, bf.Sf, Fm, FU, FE, phiw);
-            sv.Fm[f] = Fm; sv.FE[f] = FE;
-            sv.FU[f] = FU[0]; sv.FU[(size_t)fv.nF + f] = FU[1]; sv.FU[2 * (size_t)fv.nF + f] = FU[2];
+            sv.FB[0][b] = Fm; sv.FB[1][b] = FU[0]; sv.FB[2][b] = FU[1]; sv.FB[3][b] = FU[2]; sv.FB[4][b] = FE;
             const double ms = fv.magSf[f];
             const double Unf = bf.s.U[0] * (bf.Sf[0] / ms) + bf.s.U[1] * (bf.Sf[1] / ms) + bf.s.U[2] * (bf.Sf[2] / ms);
             coMax = fmax(fabs(Unf + bf.s.c), fabs(Unf - bf.s.c)) / fv.hf[f];
@@ -541,12 +540,71 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
     blockReduceCo<kBlock>(coMax, tauMin, sv.sc);
 }
 
-// ---- the fused internal-face kernel
+// ---- one internal face: 11 interpolations + 4 GaussVolPoint gradients + QGD flux algebra -> 5 flux doubles at `slot`
+template <bool ADJUST>
+__device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv, const SolverView& sv, int f, size_t slot, int P, int N,
+                                            int flagsCur, const int4& v, double& coMax, double& tauMin)
+{
+    const size_t nF = fv.nF;
+    const RecA aP = loadA(sv, P), aN = loadA(sv, N);
+    const RecB bP = loadB(sv, P), bN = loadB(sv, N);
+    RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
+    if (flagsCur & FF_POINTS) {
+        d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
+        d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
+    }
+    const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
+    double g1[3], g2[3], gp[3], Sf[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
+        g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
+        gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
+        Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
+    }
+    FaceGrads g;
+    gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
+    // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
+    const double w = __ldg(&fv.w[f]);
+    FaceState s;
+    s.rho = w * (aP.rho - aN.rho) + aN.rho;
+    s.U[0] = w * (aP.Ux - aN.Ux) + aN.Ux; s.U[1] = w * (aP.Uy - aN.Uy) + aN.Uy; s.U[2] = w * (aP.Uz - aN.Uz) + aN.Uz;
+    s.rhoU[0] = w * (bP.rhoUx - bN.rhoUx) + bN.rhoUx; s.rhoU[1] = w * (bP.rhoUy - bN.rhoUy) + bN.rhoUy;
+    s.rhoU[2] = w * (bP.rhoUz - bN.rhoUz) + bN.rhoUz;
+    {
+        const double uP[3] = {aP.Ux, aP.Uy, aP.Uz}, uN[3] = {aN.Ux, aN.Uy, aN.Uz};
+        const double rP[3] = {bP.rhoUx, bP.rhoUy, bP.rhoUz}, rN[3] = {bN.rhoUx, bN.rhoUy, bN.rhoUz};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double tP = uP[i] * rP[j], tN = uN[i] * rN[j];
+                s.UrhoU[3 * i + j] = w * (tP - tN) + tN;
+            }
+    }
+    s.p = w * (aP.p - aN.p) + aN.p;
+    s.c = w * (bP.c - bN.c) + bN.c;
+    s.H = w * (aP.H - aN.H) + aN.H;
+    s.alpha = w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
+    s.mu = w * (bP.mu - bN.mu) + bN.mu;
+    const double hf = __ldg(&fv.hf[f]);
+    s.tau = (w * (bP.aByC - bN.aByC) + bN.aByC) * hf;       // constScPrModel1.C:103
+    double Fm, FU[3], FE, phiw;
+    qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
+    sv.FI[0][slot] = Fm; sv.FI[1][slot] = FU[0]; sv.FI[2][slot] = FU[1]; sv.FI[3][slot] = FU[2]; sv.FI[4][slot] = FE;
+    if (ADJUST) {                                           // QGDCourantNo.H:38-50
+        const double ms = __ldg(&fv.magSf[f]);
+        const double Unf = s.U[0] * (Sf[0] / ms) + s.U[1] * (Sf[1] / ms) + s.U[2] * (Sf[2] / ms);
+        coMax = fmax(coMax, fmax(fabs(Unf + s.c), fabs(Unf - s.c)) / hf);
+        tauMin = fmin(tauMin, s.tau);
+    }
+}
+
+// ---- the fused internal-face kernel (two-kernel form: fluxes go to a full-size array)
 template <bool ADJUST, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv, SolverView sv)
 {
     double coMax = 0.0, tauMin = DBL_MAX;
-    const size_t nF = fv.nF;
     // software-pipelined indices: the addressing of face f+stride is fetched while face f is computed, so each
     // iteration exposes one memory latency (the gathers), not two (indices -> gathers)
     const int stride = gridDim.x * blockDim.x;
@@ -556,71 +614,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
     const int nIA = fv.nIActive;
     if (f < nIA) { P = __ldg(&fv.own[f]); N = __ldg(&fv.nei[f]); flags = __ldg(&fv.flags[f]); v = __ldg(&fv.vtx[f]); }
     for (; f < nIA; f += stride) {
-        const RecA aP = loadA(sv, P), aN = loadA(sv, N);
-        const RecB bP = loadB(sv, P), bN = loadB(sv, N);
-        RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
-        if (flags & FF_POINTS) {
-            d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
-            d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
-        }
-        const int flagsCur = flags;
+        const int Pc = P, Nc = N, flagsCur = flags;
+        const int4 vc = v;
         {
             const int fn = f + stride;
             if (fn < nIA) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
         }
-        const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
-        double g1[3], g2[3], gp[3], Sf[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
-            g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
-            gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
-            Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
-        }
-        FaceGrads g;
-        gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
-        // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
-        const double w = __ldg(&fv.w[f]);
-        FaceState s;
-        s.rho = w * (aP.rho - aN.rho) + aN.rho;
-        s.U[0] = w * (aP.Ux - aN.Ux) + aN.Ux; s.U[1] = w * (aP.Uy - aN.Uy) + aN.Uy; s.U[2] = w * (aP.Uz - aN.Uz) + aN.Uz;
-        s.rhoU[0] = w * (bP.rhoUx - bN.rhoUx) + bN.rhoUx; s.rhoU[1] = w * (bP.rhoUy - bN.rhoUy) + bN.rhoUy;
-        s.rhoU[2] = w * (bP.rhoUz - bN.rhoUz) + bN.rhoUz;
-        {
-            const double uP[3] = {aP.Ux, aP.Uy, aP.Uz}, uN[3] = {aN.Ux, aN.Uy, aN.Uz};
-            const double rP[3] = {bP.rhoUx, bP.rhoUy, bP.rhoUz}, rN[3] = {bN.rhoUx, bN.rhoUy, bN.rhoUz};
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double tP = uP[i] * rP[j], tN = uN[i] * rN[j];
-                    s.UrhoU[3 * i + j] = w * (tP - tN) + tN;
-                }
-        }
-        s.p = w * (aP.p - aN.p) + aN.p;
-        s.c = w * (bP.c - bN.c) + bN.c;
-        s.H = w * (aP.H - aN.H) + aN.H;
-        s.alpha = w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
-        s.mu = w * (bP.mu - bN.mu) + bN.mu;
-        const double hf = __ldg(&fv.hf[f]);
-        s.tau = (w * (bP.aByC - bN.aByC) + bN.aByC) * hf;       // constScPrModel1.C:103
-        double Fm, FU[3], FE, phiw;
-        qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
-        sv.Fm[f] = Fm; sv.FE[f] = FE;
-        sv.FU[f] = FU[0]; sv.FU[nF + f] = FU[1]; sv.FU[2 * nF + f] = FU[2];
-        if (ADJUST) {                                           // QGDCourantNo.H:38-50
-            const double ms = __ldg(&fv.magSf[f]);
-            const double Unf = s.U[0] * (Sf[0] / ms) + s.U[1] * (Sf[1] / ms) + s.U[2] * (Sf[2] / ms);
-            coMax = fmax(coMax, fmax(fabs(Unf + s.c), fabs(Unf - s.c)) / hf);
-            tauMin = fmin(tauMin, s.tau);
-        }
+        faceFluxOne<ADJUST>(k, fv, sv, f, (size_t)f, Pc, Nc, flagsCur, vc, coMax, tauMin);
     }
     if (ADJUST) blockReduceCo<BLOCK>(coMax, tauMin, sv.sc);
 }
 
 // setDeltaT-QGDQHD.H:41-61 ; QGDCourantNo.H:47-50
-__global__ void k_dt(StepScalars* sc)
+__global__ void k_dt(StepScalars* sc, int* pipeQueue)
 {
+    if (pipeQueue) *pipeQueue = 0;
     if (sc->adjust) {
         const double coNum = __longlong_as_double((long long)sc->coMaxBits) * sc->dt;
         const double tauMin = __longlong_as_double((long long)sc->tauMinBits);
@@ -658,11 +666,25 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     storeRec(sv, 8, cell, b);
 }
 
-template <int W>
-__global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nF)
+// flux of face f (device id) as seen by the cell update: internal faces live in the flux array / ring, boundary faces
+// in their own arrays.  Ring reads bypass L1 (slots are rewritten within one launch of the pipelined kernel).
+template <bool RING>
+__device__ __forceinline__ void loadFlux(const SolverView& sv, int nI, int f, double& fm, double& f0, double& f1, double& f2, double& fe)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= sv.nOwned) return;
+    if (RING) {      // ring slots are rewritten within one launch: read through L2 only
+        const bool internal = f < nI;
+        const int idx = internal ? (int)((unsigned)f % (unsigned)sv.ringSize) : f - nI;
+        fm = __ldcg((internal ? sv.FI[0] : sv.FB[0]) + idx); f0 = __ldcg((internal ? sv.FI[1] : sv.FB[1]) + idx);
+        f1 = __ldcg((internal ? sv.FI[2] : sv.FB[2]) + idx); f2 = __ldcg((internal ? sv.FI[3] : sv.FB[3]) + idx);
+        fe = __ldcg((internal ? sv.FI[4] : sv.FB[4]) + idx);
+    } else {         // one [5][nF] array: FB[k] = FI[k] + nI, so every face is FI[k][f]
+        fm = __ldg(&sv.FI[0][f]); f0 = __ldg(&sv.FI[1][f]); f1 = __ldg(&sv.FI[2][f]); f2 = __ldg(&sv.FI[3][f]); fe = __ldg(&sv.FI[4][f]);
+    }
+}
+
+template <int W, bool RING>
+__device__ __forceinline__ void cellUpdateOne(const Consts& k, const SolverView& sv, int nI, int c)
+{
     const RecA a = loadA(sv, c);
     const RecB b = loadB(sv, c);
     double sm = 0.0, su0 = 0.0, su1 = 0.0, su2 = 0.0, se = 0.0;
@@ -674,11 +696,8 @@ __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv,
         double fm[W], f0[W], f1[W], f2[W], fe[W];
 #pragma unroll
         for (int j = 0; j < W; ++j) {
-            if (enc[j] >= 0) {
-                const int f = enc[j] >> 1;
-                fm[j] = __ldg(&sv.Fm[f]); f0[j] = __ldg(&sv.FU[f]); f1[j] = __ldg(&sv.FU[(size_t)nF + f]);
-                f2[j] = __ldg(&sv.FU[2 * (size_t)nF + f]); fe[j] = __ldg(&sv.FE[f]);
-            } else { fm[j] = f0[j] = f1[j] = f2[j] = fe[j] = 0.0; }
+            if (enc[j] >= 0) loadFlux<RING>(sv, nI, enc[j] >> 1, fm[j], f0[j], f1[j], f2[j], fe[j]);
+            else { fm[j] = f0[j] = f1[j] = f2[j] = fe[j] = 0.0; }
         }
 #pragma unroll
         for (int j = 0; j < W; ++j) {
@@ -689,10 +708,10 @@ __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv,
     if (enc[W - 1] >= 0)
         for (int q = __ldg(&sv.cfTailOff[c]); q < __ldg(&sv.cfTailOff[c + 1]); ++q) {
             const int e1 = __ldg(&sv.cfTailEnc[q]);
-            const int f = e1 >> 1;
             const double sgn = (e1 & 1) ? -1.0 : 1.0;
-            sm += sgn * __ldg(&sv.Fm[f]); su0 += sgn * __ldg(&sv.FU[f]); su1 += sgn * __ldg(&sv.FU[(size_t)nF + f]);
-            su2 += sgn * __ldg(&sv.FU[2 * (size_t)nF + f]); se += sgn * __ldg(&sv.FE[f]);
+            double fm, f0, f1, f2, fe;
+            loadFlux<RING>(sv, nI, e1 >> 1, fm, f0, f1, f2, fe);
+            sm += sgn * fm; su0 += sgn * f0; su1 += sgn * f1; su2 += sgn * f2; se += sgn * fe;
         }
     const double V = __ldg(&sv.V[c]);
     const double rDeltaT = 1.0 / sv.sc->dt;
@@ -714,6 +733,96 @@ __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv,
     const double ddt = k.energyQuirk ? (rDeltaT * (rhoE - b.rhoE)) : (rDeltaT * (rho * e - a.rho * a.e));
     e = (rDeltaT * a.rho * a.e * V + V * ddt) / diagR;
     cellThermo(k, rho, U, rhoU, rhoE, e, a.p, a.T, __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]), sv, c);
+}
+
+template <int W>
+__global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nI)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nOwned) return;
+    cellUpdateOne<W, false>(k, sv, nI, c);
+}
+
+// ---- pipelined face+cell kernel (fixed deltaT): see DESIGN.md "flux ring".
+// Faces are owner-sorted and owner < neighbour, so once the faces owned by cells < X are done, cells < X are final and no
+// later face reads them.  A persistent grid pulls work items from an in-order queue: F(k) = fluxes of the faces owned by
+// cell chunk k, C(k) = update of cell chunk k, C(k) queued `lag` chunks behind F(k).  Fluxes live in an L2-resident ring
+// (slot = face % ringSize) instead of a full HBM array; completion flags (epoch-valued) order producers and consumers:
+//   C(k) waits for F(depLo[k] .. k)                 (all faces of its cells)
+//   F(k) waits for C(ringLo[k] .. ringHi[k])        (consumers of the ring slots it overwrites)
+// Every wait targets items that were dequeued earlier (checked on the host when the plan is built), so the persistent
+// grid cannot deadlock.
+__device__ __forceinline__ int ldAcquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// block-wide wait until every listed item carries this epoch: warp 0 polls up to 32 flags per round
+__device__ __forceinline__ void waitList(const int* flags, const int* list, int lo, int hi, int epoch)
+{
+    if (threadIdx.x < 32) {
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + (int)threadIdx.x;
+            const int* fp = flags + (i < hi ? __ldg(&list[i]) : 0);
+            bool ok;
+            do {
+                ok = (i >= hi) || (ldAcquire(fp) == epoch);
+            } while (!__all_sync(0xffffffffu, ok));
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void publish(int* flags, int item, int epoch)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicExch(flags + item, epoch);
+}
+
+template <int W, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_face_cell_pipeline(Consts k, FaceView fv, SolverView sv, PipeView pv)
+{
+    __shared__ int sItem[2];
+    const int nCh = pv.nChunks, lag = pv.lag;
+    const int nItems = 2 * nCh;
+    double coMax = 0.0, tauMin = DBL_MAX;
+    if (threadIdx.x == 0) sItem[0] = atomicAdd(pv.queue, 1);
+    int par = 0;
+    while (true) {
+        __syncthreads();
+        const int q = sItem[par];
+        if (q >= nItems) break;
+        if (threadIdx.x == 0) sItem[par ^ 1] = atomicAdd(pv.queue, 1);      // next item, fetched while this one runs
+        par ^= 1;
+        int kind, ch;       // 0 = faces, 1 = cells
+        if (q < lag) { kind = 0; ch = q; }
+        else if (q < lag + 2 * (nCh - lag)) { const int t = q - lag; kind = t & 1; ch = kind ? (t >> 1) : lag + (t >> 1); }
+        else { kind = 1; ch = nCh - lag + (q - (lag + 2 * (nCh - lag))); }
+        if (kind == 0) {
+            const int r0 = __ldg(&pv.ringOff[ch]), r1 = __ldg(&pv.ringOff[ch + 1]);
+            if (r1 > r0) waitList(pv.doneC, pv.ringList, r0, r1, pv.epoch);
+            const int f0 = __ldg(&pv.faceOff[ch]), f1 = __ldg(&pv.faceOff[ch + 1]);
+            int f = f0 + (int)threadIdx.x;
+            int P = 0, N = 0, flags = 0;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (f < f1) { P = __ldg(&fv.own[f]); N = __ldg(&fv.nei[f]); flags = __ldg(&fv.flags[f]); v = __ldg(&fv.vtx[f]); }
+            for (; f < f1; f += BLOCK) {
+                const int Pc = P, Nc = N, flagsCur = flags;
+                const int4 vc = v;
+                const int fn = f + BLOCK;
+                if (fn < f1) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
+                faceFluxOne<false>(k, fv, sv, f, (size_t)((unsigned)f % (unsigned)sv.ringSize), Pc, Nc, flagsCur, vc, coMax, tauMin);
+            }
+            publish(pv.doneF, ch, pv.epoch);
+        } else {
+            waitList(pv.doneF, pv.depList, __ldg(&pv.depOff[ch]), __ldg(&pv.depOff[ch + 1]), pv.epoch);
+            const int c0 = __ldg(&pv.cellOff[ch]), c1 = __ldg(&pv.cellOff[ch + 1]);
+            for (int c = c0 + (int)threadIdx.x; c < c1; c += BLOCK) cellUpdateOne<W, true>(k, sv, fv.nI, c);
+            publish(pv.doneC, ch, pv.epoch);
+        }
+    }
 }
 
 // boundary state after the cell update: the correctBoundaryConditions() sequence of QGDUEqn.H:51,88 ; QGDEEqn.H:50,75 ;
@@ -878,8 +987,26 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
     QGD_CUDA(cudaGetLastError());
 }
 
+namespace {
+template <int W> void launchPipe(cudaStream_t st, int grid, const Consts& c, const FaceView& fv, const SolverView& sv, const PipeView& pv)
+{
+    k_face_cell_pipeline<W, 256, 2><<<grid, 256, 0, st>>>(c, fv, sv, pv);
+}
+template <int W> int pipeGrid()
+{
+    int dev = 0, sms = 148, perSM = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_cell_pipeline<W, 256, 2>, 256, 0);
+    return sms * (perSM < 1 ? 1 : perSM);
+}
+}
+
+// resident CTAs of the pipelined kernel: the persistent grid must be fully co-resident (its items wait on each other)
+int pipelineKernelGrid(int cfEllW) { return cfEllW == 4 ? pipeGrid<4>() : (cfEllW == 6 ? pipeGrid<6>() : pipeGrid<8>()); }
+
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev, const StepHooks* hooks)
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev, const StepHooks* hooks, const PipeView* pipe, int gridPipe)
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
@@ -897,23 +1024,36 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         if (hooks && hooks->midStep) hooks->midStep();
         if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
     }
-    if (fv.nIActive) {
-        const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
-        if (ev) cudaEventRecord(ev[2], st);
-        const FaceVariant& fvn = kFaceVariants[g_faceVariant];
-        fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
-        ++n;
-        if (ev) cudaEventRecord(ev[3], st);
-    }
     if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
-    if (hooks && hooks->beforeDt) hooks->beforeDt();
-    k_dt<<<1, 1, 0, st>>>(sv.sc); ++n;
-    if (ev) cudaEventRecord(ev[4], st);
-    if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nF);
-    else if (sv.cfEllW == 6) k_cell_update<6><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nF);
-    else k_cell_update<8><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nF);
-    ++n;
-    if (ev) cudaEventRecord(ev[5], st);
+    if (pipe && !adjust) {
+        // fixed deltaT: faces and cells in one persistent kernel, fluxes stay in the L2-resident ring
+        k_dt<<<1, 1, 0, st>>>(sv.sc, pipe->queue); ++n;
+        if (ev) cudaEventRecord(ev[2], st);
+        if (pipe->nChunks > 0) {
+            if (sv.cfEllW == 4) launchPipe<4>(st, gridPipe, c, fv, sv, *pipe);
+            else if (sv.cfEllW == 6) launchPipe<6>(st, gridPipe, c, fv, sv, *pipe);
+            else launchPipe<8>(st, gridPipe, c, fv, sv, *pipe);
+            ++n;
+        }
+        if (ev) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); cudaEventRecord(ev[5], st); }
+    } else {
+        if (fv.nIActive) {
+            const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
+            if (ev) cudaEventRecord(ev[2], st);
+            const FaceVariant& fvn = kFaceVariants[g_faceVariant];
+            fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+            ++n;
+            if (ev) cudaEventRecord(ev[3], st);
+        }
+        if (hooks && hooks->beforeDt) hooks->beforeDt();
+        k_dt<<<1, 1, 0, st>>>(sv.sc, nullptr); ++n;
+        if (ev) cudaEventRecord(ev[4], st);
+        if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
+        else if (sv.cfEllW == 6) k_cell_update<6><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
+        else k_cell_update<8><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
+        ++n;
+        if (ev) cudaEventRecord(ev[5], st);
+    }
     if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     return n;
 }

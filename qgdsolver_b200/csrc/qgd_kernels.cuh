@@ -75,8 +75,27 @@ struct SolverView {
     int cfEllW; const int* cfEll;                                              // ELL cell -> faces [W][nCells], -1 pad
     const int* cfTailOff; const int* cfTailEnc;
     const double* V; const double* hQGD; const double* aQGD;
-    double* Fm; double* FU; double* FE;   // face fluxes, SoA: Fm[nF], FU[3*nF], FE[nF]
+    // face fluxes, 5 doubles per face (k = Fm, FUx, FUy, FUz, FE), SoA:
+    //   internal face f : FI[k][slot(f)]            boundary face b : FB[k][b]
+    // two-kernel form : one [5][nF] array, FI[k] = F + k*nF, FB[k] = FI[k] + nI, slot = f
+    // pipelined form  : FI[k] = ring + k*ringSize, slot = f % ringSize (L2-resident ring) ; FB[k] = bnd + k*nB
+    double* FI[5];
+    double* FB[5];
+    int ringSize;
     StepScalars* sc;
+};
+
+// work plan of the pipelined face+cell kernel (k_face_cell_pipeline)
+struct PipeView {
+    int nChunks, lag, epoch;
+    const int* cellOff;      // nChunks+1  owned cells of chunk k
+    const int* faceOff;      // nChunks+1  device faces owned by chunk k
+    const int* depOff;       // nChunks+1  C(k) needs F(depList[depOff[k] .. depOff[k+1]))  (owner chunks of its cells' faces)
+    const int* depList;
+    const int* ringOff;      // nChunks+1  F(k) rewrites ring slots last read by C(ringList[ringOff[k] .. ringOff[k+1]))
+    const int* ringList;
+    int* doneF; int* doneC;  // completion flags, epoch-valued
+    int* queue;              // work-item counter, reset by k_dt
 };
 
 void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
@@ -87,8 +106,10 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 // beforeDt runs before the time-step kernel (all-reduce of the Courant max / tau min)
 struct StepHooks { std::function<void()> midStep, beforeDt; };
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr);
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr,
+               const PipeView* pipe = nullptr, int gridPipe = 0);
 int faceKernelGrid();
+int pipelineKernelGrid(int cfEllW);
 void setFaceVariant(int v);   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
 } // namespace qgd
