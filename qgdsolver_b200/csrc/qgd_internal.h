@@ -75,7 +75,9 @@ struct __align__(16) RecP { double rho, Ux, Uy, Uz, e, p; };
 enum FaceFlags : int {
     FF_POINTS = 1,     // uses vertex values (G1/G2 non-zero)
     FF_TRI_QUIRK = 2,  // internal triangular face: vector-gradient index pattern of GaussVolPointBase3D.C:844-854
-    FF_NORMAL_ONLY = 4 // boundary face evaluated as nf*snGrad (1D, reduced, other faces)
+    FF_NORMAL_ONLY = 4, // boundary face evaluated as nf*snGrad (1D, reduced, other faces)
+    FF_GEOM = 8        // internal 3D quad face: the step kernel rebuilds G from point coordinates and cell centres
+                       // (18 cached gathers) instead of streaming the 72-byte record
 };
 
 // ---------------------------------------------------------------- host-side derived mesh data
@@ -124,4 +126,6 @@ struct qgd_mesh {
     qgd::DevBuf<double> ppW;
     qgd::DevBuf<double> Sf;        // SoA 3*nFaces
     qgd::DevBuf<double> magSf, w, dC, ndC, V, hQGDf, hQGD;
+    qgd::DevBuf<double> ptsSoA;    // SoA 3*nPoints  polyMesh::points()
+    qgd::DevBuf<double> ctrSoA;    // SoA 3*nCells   fvMesh::C()
 };

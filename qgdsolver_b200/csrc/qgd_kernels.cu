@@ -541,7 +541,7 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
 }
 
 // ---- one internal face: 11 interpolations + 4 GaussVolPoint gradients + QGD flux algebra -> 5 flux doubles at `slot`
-template <bool ADJUST>
+template <bool ADJUST, bool GEOM>
 __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv, const SolverView& sv, int f, size_t slot, int P, int N,
                                             int flagsCur, const int4& v, double& coMax, double& tauMin)
 {
@@ -556,11 +556,32 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
     double g1[3], g2[3], gp[3], Sf[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
-        g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
-        gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
-        Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
+    for (int i = 0; i < 3; ++i) Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
+    if (GEOM) {
+        // every internal face is a 3D quad (FaceView::allGeom): G rebuilt from the four vertices and the two cell centres (SURVEY A.2 closed form, same operation
+        // order as HostMesh::buildFaceRecords): e1 = p2-p4, e2 = p3-p1, d = C_N-C_P, D = e2.(e1 x d),
+        // G1 = (d x e1)/D, G2 = (d x e2)/D, GP = (e1 x e2)/D.  18 gathers that hit L1/L2 replace a 72-byte stream.
+        double e1[3], e2[3], d[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double* X = fv.X + (size_t)i * fv.nPts;
+            const double* Cc = fv.Cc + (size_t)i * fv.nCls;
+            e1[i] = __ldg(X + v.y) - __ldg(X + v.w);
+            e2[i] = __ldg(X + v.z) - __ldg(X + v.x);
+            d[i] = __ldg(Cc + N) - __ldg(Cc + P);
+        }
+        const double c1x = e1[1] * d[2] - e1[2] * d[1], c1y = e1[2] * d[0] - e1[0] * d[2], c1z = e1[0] * d[1] - e1[1] * d[0];   // e1 x d
+        const double rD = 1.0 / (e2[0] * c1x + e2[1] * c1y + e2[2] * c1z);
+        g1[0] = rD * (d[1] * e1[2] - d[2] * e1[1]); g1[1] = rD * (d[2] * e1[0] - d[0] * e1[2]); g1[2] = rD * (d[0] * e1[1] - d[1] * e1[0]);
+        g2[0] = rD * (d[1] * e2[2] - d[2] * e2[1]); g2[1] = rD * (d[2] * e2[0] - d[0] * e2[2]); g2[2] = rD * (d[0] * e2[1] - d[1] * e2[0]);
+        gp[0] = rD * (e1[1] * e2[2] - e1[2] * e2[1]); gp[1] = rD * (e1[2] * e2[0] - e1[0] * e2[2]); gp[2] = rD * (e1[0] * e2[1] - e1[1] * e2[0]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
+            g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
+            gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
+        }
     }
     FaceGrads g;
     gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
@@ -601,7 +622,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
 }
 
 // ---- the fused internal-face kernel (two-kernel form: fluxes go to a full-size array)
-template <bool ADJUST, int BLOCK, int MINB>
+template <bool ADJUST, bool GEOM, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv, SolverView sv)
 {
     double coMax = 0.0, tauMin = DBL_MAX;
@@ -620,7 +641,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
             const int fn = f + stride;
             if (fn < nIA) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
         }
-        faceFluxOne<ADJUST>(k, fv, sv, f, (size_t)f, Pc, Nc, flagsCur, vc, coMax, tauMin);
+        faceFluxOne<ADJUST, GEOM>(k, fv, sv, f, (size_t)f, Pc, Nc, flagsCur, vc, coMax, tauMin);
     }
     if (ADJUST) blockReduceCo<BLOCK>(coMax, tauMin, sv.sc);
 }
@@ -813,7 +834,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_cell_pipeline(Consts k, Fa
                 const int4 vc = v;
                 const int fn = f + BLOCK;
                 if (fn < f1) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
-                faceFluxOne<false>(k, fv, sv, f, (size_t)((unsigned)f % (unsigned)sv.ringSize), Pc, Nc, flagsCur, vc, coMax, tauMin);
+                faceFluxOne<false, false>(k, fv, sv, f, (size_t)((unsigned)f % (unsigned)sv.ringSize), Pc, Nc, flagsCur, vc, coMax, tauMin);
             }
             publish(pv.doneF, ch, pv.epoch);
         } else {
@@ -924,8 +945,12 @@ __global__ void k_init_bnd(Consts k, FaceView fv, SolverView sv, BndState bs, co
 static inline int nblk(long n, int b = kBlock) { return (int)((n + b - 1) / b); }
 
 namespace {
-struct FaceVariant { int block; void (*fn[2])(Consts, FaceView, SolverView); };
-template <int BLOCK, int MINB> constexpr FaceVariant mkVariant() { return {BLOCK, {k_face_flux<false, BLOCK, MINB>, k_face_flux<true, BLOCK, MINB>}}; }
+struct FaceVariant { int block; void (*fn[4])(Consts, FaceView, SolverView); };     // [adjust + 2*geom]
+template <int BLOCK, int MINB> constexpr FaceVariant mkVariant()
+{
+    return {BLOCK, {k_face_flux<false, false, BLOCK, MINB>, k_face_flux<true, false, BLOCK, MINB>,
+                    k_face_flux<false, true, BLOCK, MINB>, k_face_flux<true, true, BLOCK, MINB>}};
+}
 const FaceVariant kFaceVariants[] = {mkVariant<256, 1>(), mkVariant<256, 2>(), mkVariant<128, 4>(), mkVariant<128, 5>(),
                                      mkVariant<128, 6>(), mkVariant<64, 12>(), mkVariant<256, 3>()};
 int g_faceVariant = 1;
@@ -1041,7 +1066,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
             const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
             if (ev) cudaEventRecord(ev[2], st);
             const FaceVariant& fvn = kFaceVariants[g_faceVariant];
-            fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+            fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
             ++n;
             if (ev) cudaEventRecord(ev[3], st);
         }

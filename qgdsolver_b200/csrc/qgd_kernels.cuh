@@ -27,6 +27,10 @@ struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     const double* dC;        // nF  deltaCoeffs
     const double* ndC;       // nF  nonOrthDeltaCoeffs
     const double* G;         // SoA 9*nF
+    const double* X;         // SoA 3*nPoints point coordinates (FF_GEOM faces)
+    const double* Cc;        // SoA 3*nCells  cell centres      (FF_GEOM faces)
+    int nPts, nCls;
+    int allGeom;             // every active internal face carries FF_GEOM: the step uses the geometry-rebuilding face kernel
     const double* halfDist;  // nB
     const int* bKind;        // nB patch kind per boundary face
     const int* perm;         // nF device face -> polyMesh face (operator outputs are written in polyMesh order)
@@ -121,6 +125,7 @@ struct qgd_fvsc {
     qgd::DevBuf<int4> vtx;
     qgd::DevBuf<int> flags;
     qgd::DevBuf<double> G, halfDist;
+    bool allGeom = false;
     // staging for operator-level calls (grown on demand)
     qgd::DevBuf<double> dCell, dBnd, dBsg, dNbr, dPts, dOut;
     qgd::FaceView view() const
@@ -132,7 +137,7 @@ struct qgd_fvsc {
         v.zeroDivCmpt = -1;
         if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
         v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
-        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
+        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.X = m.ptsSoA.p; v.Cc = m.ctrSoA.p; v.nPts = m.h.nPoints; v.nCls = m.h.nCells; v.allGeom = allGeom ? 1 : 0; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
         v.perm = m.facePermDev.p;
         return v;
     }
