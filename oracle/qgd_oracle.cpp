@@ -94,6 +94,7 @@ struct or_ctx {
         phiJmH, qf, phiQ, phiPiU, phiSigmaDotU;
     bool qgdReady = false;
     bool havePhiwStar = false;
+    bool haveU = false;         // a volVectorField "U" is registered (false while the thermo is constructed, createFields.H:3-24)
 };
 
 namespace {
@@ -641,25 +642,55 @@ void thermoCorrect(or_ctx& s)
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
     for (int c = 0; c < s.nCells; ++c) { s.gamma[c] = g; s.c[c] = std::sqrt(s.gamma[c] / s.psi[c]); }   // :124
     for (int b = 0; b < s.nBnd; ++b) { s.gammaB[b] = g; s.cB[b] = patchIsEmpty(s, b) ? 1.0 : std::sqrt(s.gammaB[b] / s.psiB[b]); }
-    // ---- constScPrModel1::correct
+    // ---- QGDCoeffs::correct : constScPrModel1.C:97-131 | constScPrModel1n.C:98-156 | constScPrModel2.C:75-113
     {
         Vec aByC(s.nCells), aByCB(s.nBnd);
+        const int model = s.prm.qgdModel;
+        if (model == 1 && s.haveU) {                                                       // constScPrModel1n.C:107-129
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
-        for (int c = 0; c < s.nCells; ++c) aByC[c] = s.aQGD[c] / s.c[c];
-        for (int b = 0; b < s.nBnd; ++b) aByCB[b] = s.aQGDB[b] / s.cB[b];
-        linearInterpolate(s, 1, aByC.data(), aByCB.data(), nullptr, s.tauQGDf.data());
-        for (int f = 0; f < s.nFaces; ++f) s.tauQGDf[f] *= s.hQGDf[f];                     // :103
+            for (int c = 0; c < s.nCells; ++c) {
+                const double* u = &s.U[3 * (size_t)c];
+                s.tauQGD[c] = s.aQGD[c] * s.hQGD[c] / (std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) + s.c[c]);
+            }
+            for (int b = 0; b < s.nBnd; ++b) {
+                if (patchIsEmpty(s, b)) continue;
+                const double* u = &s.UB[3 * (size_t)b];
+                s.tauQGDB[b] = s.aQGDB[b] * s.hQGDB[b] / (std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]) + s.cB[b]);
+            }
+            linearInterpolate(s, 1, s.tauQGD.data(), s.tauQGDB.data(), nullptr, s.tauQGDf.data());
+        } else {
+            if (model == 1) {                                                              // constScPrModel1n.C:104-105
+                Vec af(s.nFaces), cf(s.nFaces);
+                linearInterpolate(s, 1, s.aQGD.data(), s.aQGDB.data(), nullptr, af.data());
+                linearInterpolate(s, 1, s.c.data(), s.cB.data(), nullptr, cf.data());
+                for (int f = 0; f < s.nFaces; ++f) {
+                    if (f >= s.nInternal && patchIsEmpty(s, f - s.nInternal)) { s.tauQGDf[f] = 0.0; continue; }
+                    s.tauQGDf[f] = af[f] * s.hQGDf[f] / cf[f];
+                }
+            } else {
+#pragma omp parallel for num_threads(s.nThreads) schedule(static)
+                for (int c = 0; c < s.nCells; ++c) aByC[c] = s.aQGD[c] / s.c[c];
+                for (int b = 0; b < s.nBnd; ++b) aByCB[b] = s.aQGDB[b] / s.cB[b];
+                linearInterpolate(s, 1, aByC.data(), aByCB.data(), nullptr, s.tauQGDf.data());
+                for (int f = 0; f < s.nFaces; ++f) s.tauQGDf[f] *= s.hQGDf[f];             // constScPrModel1.C:103
+            }
+#pragma omp parallel for num_threads(s.nThreads) schedule(static)
+            for (int c = 0; c < s.nCells; ++c) s.tauQGD[c] = s.aQGD[c] * s.hQGD[c] / s.c[c];   // :104
+            for (int b = 0; b < s.nBnd; ++b) if (!patchIsEmpty(s, b)) s.tauQGDB[b] = s.aQGDB[b] * s.hQGDB[b] / s.cB[b];
+        }
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < s.nCells; ++c) {
-            s.tauQGD[c] = s.aQGD[c] * s.hQGD[c] / s.c[c];                                  // :104
             s.muQGD[c] = s.p[c] * s.ScQGD[c] * s.tauQGD[c];                                // :108-111
             s.alphauQGD[c] = s.muQGD[c] / s.PrQGD[c];                                      // :113-114
         }
         for (int b = 0; b < s.nBnd; ++b) {
             if (patchIsEmpty(s, b)) continue;
-            s.tauQGDB[b] = s.aQGDB[b] * s.hQGDB[b] / s.cB[b];
             s.muQGDB[b] = s.pB[b] * s.ScQGDB[b] * s.tauQGDB[b];                            // :121-124
             s.alphauQGDB[b] = s.muQGDB[b] / s.PrQGDB[b];
+        }
+        if (model == 2) {                                                                  // constScPrModel2.C:112 (mu: molecular, not yet + muQGD)
+            for (int c = 0; c < s.nCells; ++c) s.tauQGD[c] += s.mu[c] / (s.p[c] * s.ScQGD[c]);
+            for (int b = 0; b < s.nBnd; ++b) if (!patchIsEmpty(s, b)) s.tauQGDB[b] += s.muB[b] / (s.pB[b] * s.ScQGDB[b]);
         }
     }
     // ---- correctQGD
@@ -902,8 +933,10 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
     for (int b = 0; b < nB; ++b) if (!patchIsEmpty(s, b)) s.eB[b] = th.HE(s.pB[b], s.TB[b]);
     // hePsiQGDThermo ctor: calculate() ; createFields.H:8 thermo.correct()
     s.havePhiwStar = false;
+    s.haveU = false;                  // psiQGDThermo::New runs before U is read (createFields.H:3-24)
     thermoCorrect(s);
     thermoCorrect(s);
+    s.haveU = true;
     // createFields.H:37-87
     for (int c = 0; c < nC; ++c) {
         s.rho[c] = s.psi[c] * s.p[c];                                                     // psiThermo::rho()

@@ -64,6 +64,7 @@ typedef struct {
     int alphaEffGammaFactor;   // heThermo::alphaEff multiplies by gamma for internal energy [OF-v2312]
     int energyDdtRhoEQuirk;    // 1: QGDEEqn.H:67-72 as in the doc snapshot, fvm::ddt(rho,e) - fvc::ddt(rhoE)
                                // 0: fvm::ddt(rho,e) - fvc::ddt(rho,e)  (e keeps rhoE/rho - K)
+    int qgdModel;              // 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2
 } or_qgd_params_t;
 
 typedef struct or_ctx or_ctx;

@@ -102,7 +102,8 @@ struct qgd_solver {
     DevBuf<RecA> bA;
     DevBuf<RecB> bB;
     DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
-    DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage;
+    DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage, tauOut, tauOutB;
+    int stepsDone = 0;
     // face fluxes (layout: SolverView::F): one [5][nF] array (two-kernel form) or [5][ring] + [5][nB] (pipelined form)
     size_t strideI = 0, strideB = 0, bndOff = 0;
     int ringSize = 0x7fffffff;
@@ -150,6 +151,7 @@ struct qgd_solver {
         s.pcTailOff = m.pcTailOff.p; s.pcTailCell = m.pcTailCell.p; s.pcTailW = m.pcTailW.p;
         s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
         s.cfEllW = m.cfEllW; s.cfEll = m.cfEll.p; s.cfTailOff = m.cfTailOff.p; s.cfTailEnc = m.cfTailEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
+        s.tauOut = tauOut.n ? tauOut.p : nullptr;
         for (int q = 0; q < 5; ++q) { s.FI[q] = Fflux.p + q * strideI; s.FB[q] = Fflux.p + bndOff + q * strideB; }
         s.ringSize = ringSize; s.sc = sc.p;
         return s;
@@ -159,6 +161,7 @@ struct qgd_solver {
         BndState b;
         b.A = bA.p; b.B = bB.p; b.psi = psiB.p; b.pGrad = pGrad.p; b.pNew = pNew.p; b.phiw = phiw.p;
         b.bcU = bcU.p; b.bcT = bcT.p; b.bcP = bcP.p; b.bvU = bvU.p; b.bvT = bvT.p; b.bvP = bvP.p;
+        b.tauOutB = tauOutB.n ? tauOutB.p : nullptr;
         return b;
     }
 };
@@ -176,7 +179,8 @@ template <class T> void d2h(T* h, const T* d, size_t n)
 }
 
 // state hand-off kernels for qgd_qgdfoam_step_host
-__global__ void k_pack_state(Consts k, int n, double* S, const double* __restrict__ aQGD, const double* __restrict__ st)
+__global__ void k_pack_state(Consts k, int n, double* S, const double* __restrict__ aQGD, const double* __restrict__ hQGD,
+                             const double* __restrict__ st)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -189,7 +193,8 @@ __global__ void k_pack_state(Consts k, int n, double* S, const double* __restric
     const double cs = sqrt(k.gamma / psi);
     const double alpha = k.mu / k.Pr + (mu - k.mu) / k.PrQGD;
     const double v[16] = {rho, Ux, Uy, Uz, e, p, T, (rhoE + p) / rho,
-                          rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD[c] / cs};
+                          rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha,
+                          k.tauMode == 1 ? aQGD[c] * hQGD[c] / (sqrt(Ux * Ux + Uy * Uy + Uz * Uz) + cs) : aQGD[c] / cs};
 #pragma unroll
     for (int j = 0; j < 16; ++j) S[j * N + c] = v[j];
 }
@@ -472,6 +477,8 @@ void runSteps(qgd_solver* s, int n)
             ev = &s->events[s->eventsUsed];
             s->eventsUsed += 6;
         }
+        if (s->k.model == 1) s->k.tauMode = s->stepsDone == 0 ? 2 : 1;      // constScPrModel1n.C:102-129
+        ++s->stepsDone;
         PipeView pv;
         const bool usePipe = s->pipe.mode == 1 && !s->desc.adjust_time_step;
         if (usePipe) { ++s->pipe.epoch; pv = s->pview(); }
@@ -732,7 +739,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         if (!inTable(kCoeffsTable, model))     // QGDCoeffs.C:70-79
             throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown QGD coeffs evaluation approach type " + model +
                                                    "\n\nValid model types are:\n" + toc(kCoeffsTable));
-        if (model != "constScPrModel1")
+        if (model != "constScPrModel1" && model != "constScPrModel1n" && model != "constScPrModel2")
             throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not available on the device yet (no CPU fallback)");
         if (d->implicit_diffusion)
             throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true is not available on the device yet; set QGD::implicitDiffusion false");
@@ -749,10 +756,13 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         k.R = d->R; k.Cp = d->Cp; k.Cv = d->Cp - d->R; k.Tref = d->Tref; k.Hsref = d->Hsref; k.mu = d->mu; k.Pr = d->Pr;
         k.ScQGD = d->ScQGD; k.PrQGD = d->PrQGD; k.gamma = d->Cp / (d->Cp - d->R);
         k.alphaEffGamma = d->alpha_eff_gamma_factor; k.energyQuirk = d->energy_ddt_rhoE_quirk; k.reducedScheme = s->fvsc->reduced;
+        k.model = model == "constScPrModel1" ? 0 : (model == "constScPrModel1n" ? 1 : 2);
+        k.tauMode = 0; k.alphaUniform = 0.5;
         const HostMesh& h = mesh->h;
         s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
         s->aQGD.alloc(h.nCells);
+        if (k.model != 0) { s->tauOut.alloc(h.nCells); s->tauOutB.alloc(h.nBnd + 1); s->tauOut.zero(g_stream); s->tauOutB.zero(g_stream); }
         s->psiB.alloc(h.nBnd); s->pGrad.alloc(h.nBnd); s->pNew.alloc(h.nBnd); s->phiw.alloc(h.nBnd);
         s->P.zero(g_stream);
         // default step form: two kernels (measured faster on B200 at 256^3); QGD_PIPELINE=1 opts in
@@ -816,6 +826,15 @@ int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, con
         QGD_CUDA(cudaMemcpyAsync(s->stage.p, U, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         QGD_CUDA(cudaMemcpyAsync(s->stage.p + 3 * n, T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         QGD_CUDA(cudaMemcpyAsync(s->stage.p + 4 * n, p, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        if (s->k.model == 1) {
+            // constScPrModel1n forms tauQGDf = I(alphaQGD)*hQGDf/I(c) until "U" is registered (first step): the device
+            // path keeps alphaQGD as a constant there
+            s->k.alphaUniform = alphaQGD ? alphaQGD[0] : 0.5;
+            if (alphaQGD) for (size_t c = 0; c < n; ++c) if (alphaQGD[c] != alphaQGD[0])
+                throw Error(QGD_ERR_UNSUPPORTED, "constScPrModel1n on the device needs a uniform alphaQGD field");
+            s->k.tauMode = 2;
+            s->stepsDone = 0;
+        }
         if (alphaQGD) QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, alphaQGD, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         else { std::vector<double> a(n, 0.5); QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, a.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream)); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
         launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), s->stage.p, s->stage.p + 3 * n, s->stage.p + 4 * n);
@@ -852,7 +871,8 @@ int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, 
             const size_t off[8] = {0, 1, 4, 5, 6, 7, 10, 11}, len[8] = {1, 3, 1, 1, 1, 3, 1, 1};
             for (int i = 0; i < 8; ++i)
                 QGD_CUDA(cudaMemcpyAsync(st + off[i] * n, src[i], len[i] * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
-            k_pack_state<<<nb, 256, 0, g_stream>>>(s->k, (int)n, s->S.p, s->aQGD.p, st);
+            if (s->k.model == 1) s->k.tauMode = s->stepsDone == 0 ? 2 : 1;
+            k_pack_state<<<nb, 256, 0, g_stream>>>(s->k, (int)n, s->S.p, s->aQGD.p, s->mesh->hQGD.p, st);
             s->launches++;
         }
         runSteps(s, n_steps);
@@ -916,11 +936,17 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
                 d2h(cells, s->S.p + (size_t)k0 * n, n);
                 QGD_CUDA(cudaStreamSynchronize(g_stream));
                 if (field == 9 && s->k.alphaEffGamma) for (size_t c = 0; c < n; ++c) cells[c] /= s->k.gamma;
-                if (field == 10) for (size_t c = 0; c < n; ++c) cells[c] *= h.hQGD[c];
+                if (field == 10) {
+                    if (s->tauOut.n) { d2h(cells, s->tauOut.p, n); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
+                    else for (size_t c = 0; c < n; ++c) cells[c] *= h.hQGD[c];
+                }
             }
         }
         fetch(s->bA.p, s->bB.p, h.nBnd, bnd);
-        if (field == 10 && bnd) for (int b = 0; b < h.nBnd; ++b) bnd[b] *= h.hQGDf[h.nInternal + b];
+        if (field == 10 && bnd) {
+            if (s->tauOutB.n) { d2h(bnd, s->tauOutB.p, (size_t)h.nBnd); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
+            else for (int b = 0; b < h.nBnd; ++b) bnd[b] *= h.hQGDf[h.nInternal + b];
+        }
     });
 }
 

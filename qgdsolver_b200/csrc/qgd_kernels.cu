@@ -448,7 +448,7 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
 #pragma unroll
         for (int j = 0; j < 3; ++j) o.s.UrhoU[3 * i + j] = o.s.U[i] * o.s.rhoU[j];
     o.s.p = a.p; o.s.c = bb.c; o.s.H = a.H; o.s.alpha = bb.alphaEff; o.s.mu = bb.mu;
-    o.s.tau = bb.aByC * fv.hf[f];
+    o.s.tau = k.tauMode == 1 ? bb.aByC : bb.aByC * fv.hf[f];
     // patch snGrad per field [OF fvPatchField::snGrad / zeroGradient / fixedGradient]
     const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
     const double pB = usePNew ? bs.pNew[b] : a.p;
@@ -609,7 +609,12 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     s.alpha = w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
     s.mu = w * (bP.mu - bN.mu) + bN.mu;
     const double hf = __ldg(&fv.hf[f]);
-    s.tau = (w * (bP.aByC - bN.aByC) + bN.aByC) * hf;       // constScPrModel1.C:103
+    {
+        const double tI = w * (bP.aByC - bN.aByC) + bN.aByC;
+        s.tau = k.tauMode == 0 ? tI * hf                     // constScPrModel1.C:103
+                               : (k.tauMode == 1 ? tI        // constScPrModel1n.C:128
+                                                 : k.alphaUniform * hf / s.c);   // constScPrModel1n.C:104
+    }
     double Fm, FU[3], FE, phiw;
     qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
     sv.FI[0][slot] = Fm; sv.FI[1][slot] = FU[0]; sv.FI[2][slot] = FU[1]; sv.FI[3][slot] = FU[2]; sv.FI[4][slot] = FE;
@@ -667,14 +672,16 @@ __global__ void k_dt(StepScalars* sc, int* pipeQueue)
 
 // per-cell closing of the step: new thermo state from (rho, U, rhoU, rhoE, e) and the OLD p, T
 __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const double (&U)[3], const double (&rhoU)[3], double rhoE,
-                                           double e, double pOld, double TOld, double aQGD, double hQGD, const SolverView& sv, int cell)
+                                           double e, double pOld, double TOld, double aQGD, double hQGD, const SolverView& sv, int cell,
+                                           bool haveU = true)
 {
     // hePsiQGDThermo::calculate  hePsiQGDThermo.C:48-64,123-124
     const double T = thermoTHE(k, e, TOld);
     const double psi = 1.0 / (k.R * T);
     const double c = sqrt(k.gamma / psi);
     // constScPrModel1::correct  constScPrModel1.C:104-114  (p is still the old pressure here: QGDFoam.C:149-154)
-    const double tau = aQGD * hQGD / c;
+    const bool tauByU = (k.model == 1) && haveU;           // constScPrModel1n.C:119-126
+    const double tau = tauByU ? aQGD * hQGD / (sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + c) : aQGD * hQGD / c;
     const double muQGD = pOld * k.ScQGD * tau;
     const double alphauQGD = muQGD / k.PrQGD;
     const double mu = k.mu + muQGD;                      // QGDThermo.C:91-98
@@ -682,9 +689,10 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     const double p = rho / psi;                          // QGDFoam.C:152-154
     const double H = (rhoE + p) / rho;                   // updateFields.H:71 (of the next step)
     const double a[8] = {rho, U[0], U[1], U[2], e, p, T, H};
-    const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, aQGD / c};
+    const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, tauByU ? tau : aQGD / c};
     storeRec(sv, 0, cell, a);
     storeRec(sv, 8, cell, b);
+    if (sv.tauOut) sv.tauOut[cell] = (k.model == 2) ? tau + k.mu / (pOld * k.ScQGD) : tau;     // constScPrModel2.C:112
 }
 
 // flux of face f (device id) as seen by the cell update: internal faces live in the flux array / ring, boundary faces
@@ -867,11 +875,15 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
     const double rhoE = rhoB * (e + 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]));   // QGDEEqn.H:75-76
     const double c = sqrt(k.gamma / psi);
     const double hf = fv.hf[f];
-    const double tauB = aQGD * hf / c;                                   // hQGD_b = hQGDf_b  QGDCoeffs.C:373
+    const bool tauByU = (k.model == 1) && !init;                         // constScPrModel1n.C:119-126 (boundary part)
+    const double tauB = tauByU ? aQGD * hf / (sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + c)
+                               : aQGD * hf / c;                          // hQGD_b = hQGDf_b  QGDCoeffs.C:373
     const double muQGD = pOld * k.ScQGD * tauB;                          // constScPrModel1.C:121-124
     const double mu = k.mu + muQGD;
     const double alpha = k.mu / k.Pr + muQGD / k.PrQGD;
-    const double aByC = aQGD / c;
+    const double aByC = tauByU ? tauB : aQGD / c;                        // slot: see Consts::tauMode
+    const double tauFace = tauByU ? tauB : aByC * hf;                    // tauQGDf on this boundary face after correct()
+    if (bs.tauOutB) bs.tauOutB[b] = (k.model == 2) ? tauB + k.mu / (pOld * k.ScQGD) : tauB;
     // p.correctBoundaryConditions()   QGDFoam.C:155 ; qgdFluxFvPatchScalarField.C:159-208
     double p;
     const int bcP = bs.bcP[b];
@@ -879,7 +891,7 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
     else if (bcP == QGD_BC_ZERO_GRADIENT) p = cA.p;
     else {
         double grad = bs.pGrad[b];
-        if (!init) { grad = -(bs.phiw[b] / (aByC * hf) / fv.magSf[f]); bs.pGrad[b] = grad; }
+        if (!init) { grad = -(bs.phiw[b] / tauFace / fv.magSf[f]); bs.pGrad[b] = grad; }
         p = cA.p + grad / fv.dC[f];
     }
     const double rhoNew = init ? rhoB : psi * p;                         // QGDFoam.C:156
@@ -918,7 +930,7 @@ __global__ void k_init_cells(Consts k, SolverView sv, const double* __restrict__
     const double rhoU[3] = {rho * U[0], rho * U[1], rho * U[2]};
     const double rhoE = rho * e + rho * 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
     // cellThermo recomputes p = rho/psi; at start-up p is the field as read -> store explicitly afterwards
-    cellThermo(k, rho, U, rhoU, rhoE, e, p, T, sv.aQGD[c], sv.hQGD[c], sv, c);
+    cellThermo(k, rho, U, rhoU, rhoE, e, p, T, sv.aQGD[c], sv.hQGD[c], sv, c, false);    // "U" not registered yet
     sv.S[5 * (size_t)sv.nCells + c] = p;
     sv.S[7 * (size_t)sv.nCells + c] = (rhoE + p) / rho;
 }

@@ -10,6 +10,13 @@ namespace qgd {
 struct Consts {
     double R, Cp, Cv, Tref, Hsref, mu, Pr, ScQGD, PrQGD, gamma;
     int alphaEffGamma, energyQuirk, reducedScheme;
+    // QGDCoeffs model: 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2.
+    // tauMode selects how tauQGDf is formed from the per-cell slot `aByC` of the state:
+    //   0: I(alphaQGD/c)*hQGDf            slot = alphaQGD/c         constScPrModel1.C:103, constScPrModel2.C:82
+    //   1: I(tauQGD)                      slot = tauQGD = alphaQGD*hQGD/(|U|+c)   constScPrModel1n.C:126-128
+    //   2: I(alphaQGD)*hQGDf/I(c)         (constScPrModel1n before "U" is registered, i.e. the first step; alphaQGD uniform)
+    int model, tauMode;
+    double alphaUniform;
 };
 
 struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
@@ -45,6 +52,7 @@ struct BndState {            // per boundary face
     double* phiw;            // phiwStar
     const int* bcU; const int* bcT; const int* bcP;     // kinds per boundary face
     const double* bvU; const double* bvT; const double* bvP;
+    double* tauOutB;         // nB or null: boundary tauQGD as reported by models 1n and 2
 };
 
 struct StepScalars {         // device-resident time-step control
@@ -79,6 +87,7 @@ struct SolverView {
     int cfEllW; const int* cfEll;                                              // ELL cell -> faces [W][nCells], -1 pad
     const int* cfTailOff; const int* cfTailEnc;
     const double* V; const double* hQGD; const double* aQGD;
+    double* tauOut;              // nCells or null: tauQGD as the model reports it (models 1n and 2), for qgd_qgdfoam_get
     // face fluxes, 5 doubles per face (k = Fm, FUx, FUy, FUz, FE), SoA:
     //   internal face f : FI[k][slot(f)]            boundary face b : FB[k][b]
     // two-kernel form : one [5][nF] array, FI[k] = F + k*nF, FB[k] = FI[k] + nI, slot = f

@@ -30,7 +30,7 @@ def make_rank_solver(case, rank: int, world: int, cell_rank=None):
         cell_rank = decompose.geometric_split(mesh, world)
     sub = decompose.extended_submeshes(mesh, cell_rank, ranks=[rank])[0]
     dm = api.Mesh(sub.mesh, n_owned=sub.n_owned, coupled_face=sub.coupled_face)
-    s = api.QGDFoam(dm, fvsc_scheme=case.scheme, delta_t=case.dt, **case.gas, **case.opts)
+    s = api.QGDFoam(dm, fvsc_scheme=case.scheme, qgd_coeffs=getattr(case, 'model', 'constScPrModel1'), delta_t=case.dt, **case.gas, **case.opts)
     # per-patch BC kinds: global patches + the cut patch (kind irrelevant); per-face values follow the local faces
     nI_g = mesh.n_internal
     bf_g = sub.face_global[sub.mesh.n_internal:]

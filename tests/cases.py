@@ -13,7 +13,8 @@ GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5,
 
 class Case:
     def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, gas=GAS, dt=1e-4, scheme="GaussVolPoint",
-                 alphaQGD=None, **opts):
+                 alphaQGD=None, model="constScPrModel1", **opts):
+        self.model = model
         self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
         self.bcU, self.bcT, self.bcP = [np.asarray(x, np.int32) for x in (bcU, bcT, bcP)]
         self.bvU, self.bvT, self.bvP = bvU, bvT, bvP
@@ -29,7 +30,7 @@ class Case:
         prm = O.QGDParams(R=g["R"], Cp=g["Cp"], Hf=g["Hf"], Tref=g["Tref"], Hsref=g["Hsref"], mu=g["mu"], Pr=g["Pr"],
                           ScQGD=g["ScQGD"], PrQGD=g["PrQGD"], implicitDiffusion=0,
                           alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
-                          energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]))
+                          energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model])
         scheme = O.FVSC_GAUSSVOLPOINT if self.scheme == "GaussVolPoint" else O.FVSC_REDUCED
         o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
                    alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme)
@@ -42,7 +43,7 @@ class Case:
     # ---- product
     def make_solver(self, api, dmesh=None):
         dmesh = dmesh or api.Mesh(self.mesh)
-        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, delta_t=self.dt, **self.gas, **self.opts)
+        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, **self.gas, **self.opts)
         s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
         s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
         return s

@@ -83,6 +83,10 @@ STEP_CASES = {
     "2d_mixed": lambda: cases.case_2d(perturb=0.2, bcs="mixed"),
     "2d_y_fixed": lambda: cases.case_2d(perturb=0.1, bcs="fixed", axis=1),
     "sod_1d": lambda: cases.case_sod(200),
+    "hex_model1n": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel1n"),
+    "hex_model2": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel2"),
+    "2d_model1n_qgdflux": lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", model="constScPrModel1n"),
+    "prism_model1n_adjust": lambda: cases.case_prism(bcs="fixed", model="constScPrModel1n", adjust_time_step=True, max_co=0.1),
 }
 
 
@@ -96,7 +100,7 @@ def test_qgdfoam_100_steps_match_oracle(qgd, oracle_mod, name):
         assert rel_linf(s.get(f), o.get(f)) < 1e-13, f"init {f}"
     c.oracle_step(o, 100)
     s.step(100)
-    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T"):
+    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T", "mu", "tauQGD"):
         gc, gb = s.get(f, with_bnd=True)
         oc, ob = o.get(f, with_bnd=True)
         assert np.isfinite(gc).all()
