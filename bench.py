@@ -215,6 +215,9 @@ def run_product(args):
     value = mesh.n_cells / (ms_step * 1e-3) / 1e6
     peak, peak_src = peaks()
     face_ms = kt["face_ms"] / max(kt["steps"], 1)
+    pipe = s.get_pipeline()
+    kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else "k_face_flux"
+    kbytes = ab["face"] + ab["cell"] if pipe["mode"] == 1 else ab["face"]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "face_flux_traffic.json")
     if os.path.exists(tp):
@@ -222,9 +225,6 @@ def run_product(args):
             tj = json.load(f)
             if tj.get("n_cells") == mesh.n_cells and kname in tj.get("kernel", ""):
                 traffic = tj.get("dram_bytes_per_launch")
-    pipe = s.get_pipeline()
-    kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else "k_face_flux"
-    kbytes = ab["face"] + ab["cell"] if pipe["mode"] == 1 else ab["face"]
     roofline = {"bound": "hbm", "kernel": kname, "achieved": kbytes / (face_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": kbytes / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": kbytes, "avg_launch_ms": face_ms, "pipeline": pipe,
@@ -267,6 +267,40 @@ def run_product(args):
     print(json.dumps(line), flush=True)
 
 
+def run_qhd(args):
+    """Extra line (not the driver's default): BASELINE configs[2], QHDFoam 2D differentially heated cavity, n x n cells,
+    pressure PCG on the device.  A step = one QHDFoam.C:83-139 pass including the whole PCG solve."""
+    import torch
+    import cases
+    from qgdsolver_b200 import api
+    torch.cuda.set_device(0)
+    api.init(0)
+    n = args.qhd_size
+    c = cases.qhd_cavity(n=(n, n), dt=args.qhd_dt, precond=args.precond, tol=args.p_tol, rel_tol=args.p_rel_tol, max_iter=100000,
+                         model="constTau", coeffs=dict(Tau=args.qhd_dt))
+    s = c.make_solver(api)
+    s.step(args.warmup)
+    api.synchronize()
+    its = []
+    api.timer_begin()
+    for _ in range(args.steps):
+        s.step(1)
+    ms = api.timer_end() / args.steps
+    info = s.solver_info()
+    nC, nI = c.mesh.n_cells, c.mesh.n_internal
+    peak, src = peaks()
+    line = {"metric": "cell-updates/s per QHDFoam step", "value": nC / ms / 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QHDFoam 2D buoyant differentially-heated cavity {n}x{n} ({nC} cells), explicit, FP64",
+                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constTau", "p_solver": f"PCG + {args.precond}",
+                       "tolerance": args.p_tol, "relTol": args.p_rel_tol, "last_pcg_iterations": info["iters"],
+                       "last_final_residual": info["final_residual"],
+                       "pcg_alg_bytes_per_iter": 120 * nC + 48 * nI},
+            "gpu_launches": int(s.launch_count())}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -277,10 +311,18 @@ def main():
     ap.add_argument("--ref-size", type=int, default=64, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--case", default="qgd3d", choices=["qgd3d", "qhd2d"], help="qgd3d = BASELINE configs[3] (default); qhd2d = configs[2]")
+    ap.add_argument("--precond", default="diagonal")
+    ap.add_argument("--p-tol", type=float, default=1e-8)
+    ap.add_argument("--p-rel-tol", type=float, default=0.0)
+    ap.add_argument("--qhd-dt", type=float, default=1e-5, help="explicit QHD step: dt < h^2/(4 nu) = 2.5e-5 at 1000^2")
+    ap.add_argument("--qhd-size", type=int, default=1000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.case == "qhd2d":
+        run_qhd(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_product(args)

@@ -73,7 +73,28 @@ def bench(args, rank: int, world: int, local: int):
     dist.barrier()
     ms = float(t.item())
     kt = s.kernel_times()
+    s.profile(False)
     launches = s.launch_count() - l0
+    # ---- end to end through the C-ABI with pinned HOST state buffers: every rank uploads its sub-domain state, steps once
+    # (halo exchange included) and downloads it again, every step
+    nL = sub.mesh.n_cells
+    names = ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")
+    pinned = {k: torch.empty((nL, 3) if k in ("U", "rhoU") else (nL,), dtype=torch.float64, pin_memory=True) for k in names}
+    st = {k: v.numpy() for k, v in pinned.items()}
+    s.step_host(0, None, st)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        s.step_host(1, st, st)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.step_host(1, st, st)
+    torch.cuda.synchronize()
+    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    tb = torch.tensor([12.0 * 8 * nL], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+    e2e_s, e2e_bytes = float(te.item()), int(tb.item())
     if rank == 0:
         clocks = sampler.stop()
         ms_step = ms / args.steps
@@ -93,7 +114,10 @@ def bench(args, rank: int, world: int, local: int):
                            "halo_bytes_sent_per_step_rank0": halo_bytes,
                            "l2": "per-rank state and mesh records exceed the 126 MB L2; no flush"},
                 "clocks": clocks, "gpu_launches": int(launches),
-                "e2e": None,
+                "e2e": {"value": mesh.n_cells / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": e2e_bytes,
+                        "d2h_bytes_per_step": e2e_bytes, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                        "api": "qgd_qgdfoam_step_host on every rank: sub-domain cell state (12 doubles/cell, halo included) H2D + "
+                               "1 step with NCCL halo exchange + D2H per call, pinned host buffers; max over ranks"},
                 "roofline": {"bound": "hbm", "kernel": "k_face_flux (rank 0)", "achieved": ab_face_rank / (face_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": ab_face_rank / (face_ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "peak_source": src, "avg_launch_ms": face_ms,
