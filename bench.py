@@ -185,6 +185,10 @@ def run_product(args):
     torch.cuda.set_device(local)
     api.init(local)
     if world > 1:
+        # keep stdout to the single JSON line: library banners (e.g. "NCCL version ...") go to stderr
+        sys.stdout.flush()
+        args.json_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from qgdsolver_b200 import multigpu

@@ -124,6 +124,10 @@ def bench(args, rank: int, world: int, local: int):
                              "step": {"alg_bytes_global": ab["total"], "achieved_aggregate": ab["total"] / (ms_step * 1e-3) / 1e9,
                                       "frac_of_n_gpus_peak": ab["total"] / (ms_step * 1e-3) / 1e9 / (peak * world)}},
                 "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        fd = getattr(args, "json_fd", None)
+        if fd is not None:
+            os.write(fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     api.comm_finalize()
     dist.destroy_process_group()
