@@ -129,14 +129,18 @@ typedef struct {
     double Cp, Hf, Tref, Hsref;     /* hConst                                                       */
     double mu, Pr;                  /* constTransport                                               */
     double ScQGD, PrQGD;            /* constScPrModel1.C:58-89 (default 1, 1)                       */
-    int implicit_diffusion;         /* QGD::implicitDiffusion (QGDThermo.C:61: default true).
-                                       Only false runs on the device in this round.              */
+    int implicit_diffusion;         /* QGD::implicitDiffusion (QGDThermo.C:61: default true): QGDUEqn.H:54-75,
+                                       QGDEEqn.H:53-64 with the PCG controls below                  */
     int alpha_eff_gamma_factor;     /* heThermo::alphaEff for internal energy [OF-v2312]            */
     int energy_ddt_rhoE_quirk;      /* 1 = QGDEEqn.H:67-72 literally (default), 0 = fvc::ddt(rho,e) */
     /* controlDict */
     int adjust_time_step;           /* QGDCourantNo.H:36                                            */
     double max_co, max_delta_t, c_tau;   /* readTimeControls.H ; setDeltaT-QGDQHD.H:45 (cTau 0.75)  */
     double delta_t;                 /* initial deltaT                                               */
+    /* fvSolution::solvers::"(U|e)" for the implicit-diffusion branch: PCG + preconditioner                  */
+    double diff_tolerance, diff_rel_tol;
+    int diff_max_iter;
+    const char* diff_preconditioner;   /* "DIC" | "diagonal" | "none" ; NULL = "DIC"                */
 } qgd_qgdfoam_desc;
 
 int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* desc, qgd_solver** out);
@@ -181,6 +185,8 @@ int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, dou
  * bit-identical in both forms. */
 int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, int ring_slots);
 int qgd_qgdfoam_get_pipeline(qgd_solver* s, int* mode, int* chunk_cells, int* lag, int* ring_slots, int* n_chunks, int* grid);
+/* implicit-diffusion branch: PCG iterations of the last Ux, Uy, Uz and e solves */
+int qgd_qgdfoam_diffusion_iterations(qgd_solver* s, int iters[4]);
 /* kernel launches issued by this solver so far (bench bookkeeping) */
 long long qgd_qgdfoam_launch_count(qgd_solver* s);
 /* per-kernel CUDA-event timing on the solver stream: enable, run steps, then read the summed durations (ms) of the

@@ -36,7 +36,8 @@ class QGDParams(C.Structure):
     _fields_ = [("R", C.c_double), ("Cp", C.c_double), ("Hf", C.c_double), ("Tref", C.c_double),
                 ("Hsref", C.c_double), ("mu", C.c_double), ("Pr", C.c_double), ("ScQGD", C.c_double),
                 ("PrQGD", C.c_double), ("implicitDiffusion", C.c_int), ("alphaEffGammaFactor", C.c_int),
-                ("energyDdtRhoEQuirk", C.c_int), ("qgdModel", C.c_int)]
+                ("energyDdtRhoEQuirk", C.c_int), ("qgdModel", C.c_int),
+                ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int)]
 
 
 QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2}

@@ -91,7 +91,8 @@ struct or_ctx {
     // surface fields (nFaces*k)
     Vec tauQGDf, rhof, Uf, rhoUf, UrhoUf, pf, cf, gammaf, Hf, alphauf, muf;
     Vec gradUf, divUf, gradef, gradRhof, gradPf, rhoW, phiw, jm, phiJm, phi, phiJmU, phiP, Pif, phiPi,
-        phiJmH, qf, phiQ, phiPiU, phiSigmaDotU;
+        phiJmH, qf, phiQ, phiPiU, phiSigmaDotU, tauMC, phiTauMC;
+    int lastDiffIters[4] = {0, 0, 0, 0};     // PCG iterations of the last Ux,Uy,Uz,e solves (implicit branch)
     bool qgdReady = false;
     bool havePhiwStar = false;
     bool haveU = false;         // a volVectorField "U" is registered (false while the thermo is constructed, createFields.H:3-24)
@@ -725,6 +726,39 @@ template <class F> void forFaces(const or_ctx& s, F fn)
     }
 }
 
+// [OF-v2312] fvc::grad, Gauss linear, cell values only: (1/V) sum_f Sf (x) phi_f  (owner +, neighbour -)
+void gaussGradCells(const or_ctx& s, int k, const double* phif, double* out /*nCells*3k: index 3... [i*k+j] = d_i phi_j*/)
+{
+#pragma omp parallel for num_threads(s.nThreads) schedule(static)
+    for (int c = 0; c < s.nCells; ++c) {
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = s.cfOff[c]; q < s.cfOff[c + 1]; ++q) {
+            const int f = s.cfFace[q];
+            if (f >= s.nInternal && patchIsEmpty(s, f - s.nInternal)) continue;
+            const double sgn = (s.owner[f] == c) ? 1.0 : -1.0;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < k; ++j) acc[i * k + j] += sgn * (s.Sf[3 * (size_t)f + i] * phif[(size_t)f * k + j]);
+        }
+        for (int q = 0; q < 3 * k; ++q) out[(size_t)c * 3 * k + q] = acc[q] / s.V[c];
+    }
+}
+
+// [OF-v2312] gaussGrad::correctBoundaryConditions: boundary value of fvc::grad(vsf) on non-coupled patches,
+//   gradB = grad_P + n (x) (snGrad_b - n . grad_P)
+void gaussGradBoundary(const or_ctx& s, const double* gradCells, const double* sn3 /*nBnd*3 patch snGrad of the vector*/, double* gradB)
+{
+    for (int b = 0; b < s.nBnd; ++b) {
+        if (patchIsEmpty(s, b)) { for (int q = 0; q < 9; ++q) gradB[9 * (size_t)b + q] = 0.0; continue; }
+        const int f = s.nInternal + b; const int P = s.owner[f];
+        const double* n = &s.nf[3 * (size_t)f];
+        for (int j = 0; j < 3; ++j) {
+            double nG = 0.0;
+            for (int i = 0; i < 3; ++i) nG += n[i] * gradCells[9 * (size_t)P + 3 * i + j];
+            for (int i = 0; i < 3; ++i) gradB[9 * (size_t)b + 3 * i + j] = gradCells[9 * (size_t)P + 3 * i + j] + n[i] * (sn3[3 * (size_t)b + j] - nG);
+        }
+    }
+}
+
 // QGDFoam/updateFields.H:45-80
 void updateFields(or_ctx& s)
 {
@@ -799,6 +833,28 @@ void updateFluxes(or_ctx& s)
     if (gvp) correctP(s);
     patchSnGrad(s, 1, s.bcP, s.p.data(), s.pB.data(), s.pGrad.data(), sg1.data());
     fvscGrad(s, s.scheme, 1, s.p.data(), s.pB.data(), sg1.data(), nullptr, s.gradPf.data());
+    if (s.prm.implicitDiffusion) {
+        // :107-111  tauMC = qgdInterpolate(muEff*dev2(T(fvc::grad(U)))) ; phiTauMC = Sf & tauMC
+        const int nC = s.nCells;
+        Vec gU(9 * (size_t)nC), gUB(9 * (size_t)nB), t(9 * (size_t)nC), tB(9 * (size_t)nB), snU(3 * (size_t)nB);
+        patchSnGrad(s, 3, s.bcU, s.U.data(), s.UB.data(), nullptr, snU.data());
+        gaussGradCells(s, 3, s.Uf.data(), gU.data());
+        gaussGradBoundary(s, gU.data(), snU.data(), gUB.data());
+        auto dev2T = [](double mu, const double* g, double* o) {       // mu * dev2(T(g)) ; dev2(A) = A - (2/3) tr(A) I
+            const double tr = g[0] + g[4] + g[8];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[3 * i + j] = mu * (g[3 * j + i] - (2.0 / 3.0) * tr * (i == j ? 1.0 : 0.0));
+        };
+        for (int c = 0; c < nC; ++c) dev2T(s.mu[c], &gU[9 * (size_t)c], &t[9 * (size_t)c]);
+        for (int b = 0; b < nB; ++b) dev2T(s.muB[b], &gUB[9 * (size_t)b], &tB[9 * (size_t)b]);
+        linearInterpolate(s, 9, t.data(), tB.data(), nullptr, s.tauMC.data());
+        forFaces(s, [&](int f) {
+            for (int j = 0; j < 3; ++j) {
+                double v = 0.0;
+                for (int i = 0; i < 3; ++i) v += s.Sf[3 * (size_t)f + i] * s.tauMC[9 * (size_t)f + 3 * i + j];
+                s.phiTauMC[3 * (size_t)f + j] = v;
+            }
+        });
+    }
     forFaces(s, [&](int f) {
         const double* Sf = &s.Sf[3 * (size_t)f]; const double* Uf = &s.Uf[3 * (size_t)f];
         const double* gP = &s.gradPf[3 * (size_t)f]; const double* G = &s.gradUf[9 * (size_t)f];
@@ -820,9 +876,10 @@ void updateFluxes(or_ctx& s)
                 Pi[3 * i + j] = tau * (UrUG + Uf[i] * gP[j]) + tau * ((i == j ? 1.0 : 0.0) * iso);
             }
         // :95-106  explicit branch: Navier-Stokes stress
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j)
-                Pi[3 * i + j] += s.muf[f] * (G[3 * i + j] + G[3 * j + i] - (2.0 / 3.0) * (i == j ? 1.0 : 0.0) * s.divUf[f]);
+        if (!s.prm.implicitDiffusion)
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    Pi[3 * i + j] += s.muf[f] * (G[3 * i + j] + G[3 * j + i] - (2.0 / 3.0) * (i == j ? 1.0 : 0.0) * s.divUf[f]);
         for (int j = 0; j < 3; ++j) s.phiPi[3 * (size_t)f + j] = Sf[0] * Pi[j] + Sf[1] * Pi[3 + j] + Sf[2] * Pi[6 + j];   // :113
         s.phiJmH[f] = s.phiJm[f] * s.Hf[f];                                               // :119
         // :121-135  qf
@@ -831,7 +888,7 @@ void updateFluxes(or_ctx& s)
         double v[3], q[3];
         for (int j = 0; j < 3; ++j) v[j] = ge[j] - pr2 * gR[j];
         for (int i = 0; i < 3; ++i) q[i] = -tau * (UrU[3 * i] * v[0] + UrU[3 * i + 1] * v[1] + UrU[3 * i + 2] * v[2]);
-        for (int i = 0; i < 3; ++i) q[i] -= s.alphauf[f] * ge[i];
+        if (!s.prm.implicitDiffusion) for (int i = 0; i < 3; ++i) q[i] -= s.alphauf[f] * ge[i];              // :131-135
         for (int i = 0; i < 3; ++i) s.qf[3 * (size_t)f + i] = q[i];
         s.phiQ[f] = Sf[0] * q[0] + Sf[1] * q[1] + Sf[2] * q[2];                           // :137
         double PiU[3];
@@ -917,7 +974,8 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
     for (Vec* v : {&s.tauQGDf, &s.rhof, &s.pf, &s.cf, &s.gammaf, &s.Hf, &s.alphauf, &s.muf, &s.divUf, &s.phiw, &s.phiJm, &s.phi,
                    &s.phiJmH, &s.phiQ, &s.phiPiU, &s.phiSigmaDotU}) z(*v, nF);
     for (Vec* v : {&s.Uf, &s.rhoUf, &s.gradef, &s.gradRhof, &s.gradPf, &s.rhoW, &s.jm, &s.phiJmU, &s.phiP, &s.phiPi, &s.qf}) z(*v, 3 * (size_t)nF);
-    for (Vec* v : {&s.UrhoUf, &s.gradUf, &s.Pif}) z(*v, 9 * (size_t)nF);
+    for (Vec* v : {&s.UrhoUf, &s.gradUf, &s.Pif, &s.tauMC}) z(*v, 9 * (size_t)nF);
+    z(s.phiTauMC, 3 * (size_t)nF);
     const Thermo th = thermoOf(s);
     // boundary values of the read fields T, p, U as given by their BCs
     for (int b = 0; b < nB; ++b) {
@@ -1011,6 +1069,54 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < nC; ++c) for (int j = 0; j < 3; ++j) s.U[3 * (size_t)c + j] = s.rhoU[3 * (size_t)c + j] / s.rho[c];
         correctU(s);
+        if (s.prm.implicitDiffusion) {
+            // :54-74  fvm::ddt(rho,U) - fvc::ddt(rho,U) - fvm::laplacian(muf,U) - fvc::div(phiTauMC) == 0, component-wise
+            fvcDiv(s, 3, s.phiTauMC.data(), d3.data());
+            Vec upper(std::max(s.nInternal, 1)), diagL(nC, 0.0), diag(nC), src(nC), x(nC);
+            for (int f = 0; f < s.nInternal; ++f) {                          // -fvm::laplacian(muf,U) [OF gaussLaplacianScheme]
+                const double up = s.ndC[f] * (s.muf[f] * s.magSf[f]);
+                upper[f] = -up; diagL[s.owner[f]] += up; diagL[s.neighbour[f]] += up;
+            }
+            for (int j = 0; j < 3; ++j) {
+                for (int c = 0; c < nC; ++c) {
+                    const size_t i = 3 * (size_t)c + j;
+                    diag[c] = rDeltaT * s.rho[c] * s.V[c] + diagL[c];
+                    src[c] = rDeltaT * rho0[c] * U0[i] * s.V[c] + s.V[c] * (rDeltaT * (s.rho[c] * s.U[i] - rho0[c] * U0[i])) + s.V[c] * d3[i];
+                    x[c] = s.U[i];
+                }
+                for (int b = 0; b < nB; ++b) {                               // fixedValue: internalCoeffs / boundaryCoeffs
+                    const int pi = s.bfacePatch[b];
+                    if (s.patchKind[pi] == OR_PATCH_EMPTY || s.bcU[pi] != OR_BC_FIXED_VALUE) continue;
+                    const int f = s.nInternal + b; const int P = s.owner[f];
+                    const double gS = s.muf[f] * s.magSf[f];
+                    diag[P] += gS * s.ndC[f];
+                    src[P] += gS * (s.ndC[f] * s.UB[3 * (size_t)b + j]);
+                }
+                s.lastDiffIters[j] = or_pcg_solve(sp, diag.data(), upper.data(), src.data(), x.data(), s.prm.diffTol, s.prm.diffRelTol,
+                                                  s.prm.diffMaxIter, s.prm.diffPrecond, nullptr, nullptr);
+                for (int c = 0; c < nC; ++c) s.U[3 * (size_t)c + j] = x[c];
+            }
+            correctU(s);
+            for (int c = 0; c < nC; ++c) for (int j = 0; j < 3; ++j) s.rhoU[3 * (size_t)c + j] = s.rho[c] * s.U[3 * (size_t)c + j];   // :70
+            // :72-74  sigmaDotU = (muf*linearInterpolate(fvc::grad(U)) + tauMC) & Uf ; phiSigmaDotU = Sf & sigmaDotU
+            {
+                Vec UfN(3 * (size_t)s.nFaces), gU(9 * (size_t)nC), gUB(9 * (size_t)nB), gUf(9 * (size_t)s.nFaces), snU(3 * (size_t)nB);
+                linearInterpolate(s, 3, s.U.data(), s.UB.data(), nullptr, UfN.data());
+                patchSnGrad(s, 3, s.bcU, s.U.data(), s.UB.data(), nullptr, snU.data());
+                gaussGradCells(s, 3, UfN.data(), gU.data());
+                gaussGradBoundary(s, gU.data(), snU.data(), gUB.data());
+                linearInterpolate(s, 9, gU.data(), gUB.data(), nullptr, gUf.data());
+                forFaces(s, [&](int f) {
+                    const double* Uf = &s.Uf[3 * (size_t)f];                  // Uf of updateFields.H (old U)
+                    double sg[3];
+                    for (int i = 0; i < 3; ++i) {
+                        sg[i] = 0.0;
+                        for (int j = 0; j < 3; ++j) sg[i] += (s.muf[f] * gUf[9 * (size_t)f + 3 * i + j] + s.tauMC[9 * (size_t)f + 3 * i + j]) * Uf[j];
+                    }
+                    s.phiSigmaDotU[f] = s.Sf[3 * (size_t)f] * sg[0] + s.Sf[3 * (size_t)f + 1] * sg[1] + s.Sf[3 * (size_t)f + 2] * sg[2];
+                });
+            }
+        } else {
         // :79-86  solve(fvm::ddt(rho,U) - fvc::ddt(rhoU) == 0)
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < nC; ++c)
@@ -1021,6 +1127,7 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
                 s.U[i] = source / diag;
             }
         correctU(s);
+        }
         for (int b = 0; b < nB; ++b) for (int j = 0; j < 3; ++j) s.rhoUB[3 * (size_t)b + j] = s.rhoB[b] * s.UB[3 * (size_t)b + j];   // :88-89
         // ---- QGDEEqn.H:37-46
         fvcDiv(s, 1, s.phiJmH.data(), d1.data());
@@ -1041,6 +1148,33 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
             s.e[c] = s.rhoE[c] / s.rho[c] - 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
         }
         correctE(s);
+        if (s.prm.implicitDiffusion) {
+            // :53-63  fvm::ddt(rho,e) - fvc::ddt(rho,e) - fvm::laplacian(alphauf,e) == 0 ; rhoE = rho*(e + 0.5*magSqr(U))
+            Vec upper(std::max(s.nInternal, 1)), diag(nC), src(nC);
+            for (int c = 0; c < nC; ++c) {
+                diag[c] = rDeltaT * s.rho[c] * s.V[c];
+                src[c] = rDeltaT * rho0[c] * e0[c] * s.V[c] + s.V[c] * (rDeltaT * (s.rho[c] * s.e[c] - rho0[c] * e0[c]));
+            }
+            for (int f = 0; f < s.nInternal; ++f) {
+                const double up = s.ndC[f] * (s.alphauf[f] * s.magSf[f]);
+                upper[f] = -up; diag[s.owner[f]] += up; diag[s.neighbour[f]] += up;
+            }
+            for (int b = 0; b < nB; ++b) {                                   // fixedEnergy: value BC ; gradientEnergy: gradient 0
+                const int pi = s.bfacePatch[b];
+                if (s.patchKind[pi] == OR_PATCH_EMPTY || s.bcT[pi] != OR_BC_FIXED_VALUE) continue;
+                const int f = s.nInternal + b; const int P = s.owner[f];
+                const double gS = s.alphauf[f] * s.magSf[f];
+                diag[P] += gS * s.ndC[f];
+                src[P] += gS * (s.ndC[f] * s.eB[b]);
+            }
+            s.lastDiffIters[3] = or_pcg_solve(sp, diag.data(), upper.data(), src.data(), s.e.data(), s.prm.diffTol, s.prm.diffRelTol,
+                                              s.prm.diffMaxIter, s.prm.diffPrecond, nullptr, nullptr);
+            correctE(s);
+            for (int c = 0; c < nC; ++c) {
+                const double* u = &s.U[3 * (size_t)c];
+                s.rhoE[c] = s.rho[c] * (s.e[c] + 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]));
+            }
+        } else {
         // :65-73  solve(fvm::ddt(rho,e) - fvc::ddt(rhoE) == 0)
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < nC; ++c) {
@@ -1051,6 +1185,7 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
             s.e[c] = source / diag;
         }
         correctE(s);
+        }
         for (int b = 0; b < nB; ++b) {                                                    // :75-76
             const double* u = &s.UB[3 * (size_t)b];
             s.rhoEB[b] = s.rhoB[b] * (s.eB[b] + 0.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]));

@@ -60,11 +60,14 @@ typedef struct {
     double Pr;
     double ScQGD;    // constScPrModel1
     double PrQGD;
-    int implicitDiffusion;     // only 0 supported by the step
+    int implicitDiffusion;     // QGD::implicitDiffusion (QGDThermo.C:61)
     int alphaEffGammaFactor;   // heThermo::alphaEff multiplies by gamma for internal energy [OF-v2312]
     int energyDdtRhoEQuirk;    // 1: QGDEEqn.H:67-72 as in the doc snapshot, fvm::ddt(rho,e) - fvc::ddt(rhoE)
                                // 0: fvm::ddt(rho,e) - fvc::ddt(rho,e)  (e keeps rhoE/rho - K)
     int qgdModel;              // 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2
+    // implicitDiffusion branch (QGDUEqn.H:54-75, QGDEEqn.H:53-64): fvSolution controls of the U and e solvers (PCG)
+    double diffTol, diffRelTol;
+    int diffMaxIter, diffPrecond;
 } or_qgd_params_t;
 
 typedef struct or_ctx or_ctx;

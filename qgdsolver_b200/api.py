@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
-    "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline",
+    "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
     "qgd_pcg_solve",
@@ -65,7 +65,9 @@ class QGDFoamDesc(C.Structure):
                 ("mu", C.c_double), ("Pr", C.c_double), ("ScQGD", C.c_double), ("PrQGD", C.c_double),
                 ("implicit_diffusion", C.c_int), ("alpha_eff_gamma_factor", C.c_int), ("energy_ddt_rhoE_quirk", C.c_int),
                 ("adjust_time_step", C.c_int),
-                ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double)]
+                ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double),
+                ("diff_tolerance", C.c_double), ("diff_rel_tol", C.c_double), ("diff_max_iter", C.c_int),
+                ("diff_preconditioner", C.c_char_p)]
 
 
 class QHDFoamDesc(C.Structure):
@@ -278,11 +280,13 @@ class QGDFoam:
     def __init__(self, mesh: Mesh, *, R, Cp, mu=0.0, Pr=1.0, Hf=0.0, Tref=0.0, Hsref=0.0, ScQGD=1.0, PrQGD=1.0,
                  fvsc_scheme="GaussVolPoint", qgd_coeffs="constScPrModel1", implicit_diffusion=False,
                  alpha_eff_gamma_factor=True, energy_ddt_rhoE_quirk=True, adjust_time_step=False, max_co=0.3,
-                 max_delta_t=1e30, c_tau=0.75, delta_t=1e-4):
+                 max_delta_t=1e30, c_tau=0.75, delta_t=1e-4, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000,
+                 diff_precond="DIC"):
         self.mesh = mesh
         d = QGDFoamDesc()
-        self._names = (fvsc_scheme.encode(), qgd_coeffs.encode())
-        d.fvsc_scheme, d.qgd_coeffs_model = self._names
+        self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), diff_precond.encode())
+        d.fvsc_scheme, d.qgd_coeffs_model, d.diff_preconditioner = self._names
+        d.diff_tolerance, d.diff_rel_tol, d.diff_max_iter = diff_tol, diff_rel_tol, diff_max_iter
         d.R, d.Cp, d.Hf, d.Tref, d.Hsref, d.mu, d.Pr, d.ScQGD, d.PrQGD = R, Cp, Hf, Tref, Hsref, mu, Pr, ScQGD, PrQGD
         d.implicit_diffusion = int(implicit_diffusion)
         d.alpha_eff_gamma_factor = int(alpha_eff_gamma_factor)
@@ -376,6 +380,11 @@ class QGDFoam:
         a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
         _check(load_library().qgd_qgdfoam_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
         return dict(points_ms=a.value, face_ms=b.value, cell_ms=c.value, steps=n.value)
+
+    def diffusion_iterations(self):
+        it = (C.c_int * 4)()
+        _check(load_library().qgd_qgdfoam_diffusion_iterations(self._h, it))
+        return list(it)
 
     def launch_count(self) -> int:
         return int(load_library().qgd_qgdfoam_launch_count(self._h))

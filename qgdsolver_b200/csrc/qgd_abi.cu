@@ -104,6 +104,20 @@ struct qgd_solver {
     DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
     DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage, tauOut, tauOutB;
     int stepsDone = 0;
+    // implicit-diffusion branch
+    struct Implicit {
+        DevBuf<double> GU0, GU1, old, FT, aU, aE, Fs, diagU, bU, diagE, bE;
+        PcgMatrix AU, AE;
+        int precond = 2;
+        bool built = false;
+    } impl;
+    ImplicitView iview()
+    {
+        ImplicitView v;
+        v.GU0 = impl.GU0.p; v.GU1 = impl.GU1.p; v.old = impl.old.p; v.FT = impl.FT.p; v.aU = impl.aU.p; v.aE = impl.aE.p; v.Fs = impl.Fs.p;
+        v.diagU = impl.diagU.p; v.bU = impl.bU.p; v.diagE = impl.diagE.p; v.bE = impl.bE.p;
+        return v;
+    }
     // face fluxes (layout: SolverView::F): one [5][nF] array (two-kernel form) or [5][ring] + [5][nB] (pipelined form)
     size_t strideI = 0, strideB = 0, bndOff = 0;
     int ringSize = 0x7fffffff;
@@ -450,8 +464,56 @@ void configurePipeline(qgd_solver* s, int mode, int chunkCells, int lag, int rin
     QGD_CUDA(cudaStreamSynchronize(g_stream));
 }
 
+void runStepsImplicit(qgd_solver* s, int n)
+{
+    const HostMesh& h = s->mesh->h;
+    const size_t nC = h.nCells, nF = h.nFaces;
+    qgd_solver::Implicit& I = s->impl;
+    if (!I.built) {
+        I.GU0.alloc(9 * nC); I.GU1.alloc(9 * nC); I.old.alloc(4 * nC); I.FT.alloc(3 * nF); I.aU.alloc(nF); I.aE.alloc(nF); I.Fs.alloc(nF);
+        I.diagU.alloc(nC); I.bU.alloc(3 * nC); I.diagE.alloc(nC); I.bE.alloc(nC);
+        std::vector<double> ones(nC, 1.0), zeros(std::max(h.nInternal, 1), 0.0);
+        I.AU.build(h, ones.data(), zeros.data(), I.precond, g_stream, &s->mesh->faceInv);
+        I.AE.build(h, ones.data(), zeros.data(), I.precond, g_stream, &s->mesh->faceInv);
+        I.built = true;
+    }
+    const FaceView fv = s->fvsc->view();
+    const SolverView sv = s->sview();
+    const BndState bs = s->bview();
+    const ImplicitView iv = s->iview();
+    const bool adjust = s->desc.adjust_time_step != 0;
+    const double tol = s->desc.diff_tolerance, rel = s->desc.diff_rel_tol;
+    const int maxIter = s->desc.diff_max_iter > 0 ? s->desc.diff_max_iter : 1000;
+    for (int i = 0; i < n; ++i) {
+        if (s->k.model == 1) s->k.tauMode = s->stepsDone == 0 ? 2 : 1;
+        ++s->stepsDone;
+        s->launches += launchImplicitPhase(g_stream, 0, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust);
+        I.AU.refresh(iv.aU, iv.diagU, g_stream);
+        for (int j = 0; j < 3; ++j) {                               // QGDUEqn.H:65-68, segregated components
+            I.AU.bExternal = iv.bU + j * nC;
+            I.AU.xExternal = s->S.p + (1 + j) * nC;
+            s->launches += I.AU.solve(tol, rel, maxIter, g_stream);
+            QGD_CUDA(cudaMemcpyAsync(s->stage.p + j * 4, I.AU.out.p, sizeof(PcgResult), cudaMemcpyDeviceToDevice, g_stream));
+        }
+        s->launches += 2 + launchImplicitPhase(g_stream, 1, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust);
+        I.AE.refresh(iv.aE, iv.diagE, g_stream);
+        I.AE.bExternal = iv.bE;
+        I.AE.xExternal = s->S.p + 4 * nC;
+        s->launches += 2 + I.AE.solve(tol, rel, maxIter, g_stream);   // QGDEEqn.H:55-61
+        QGD_CUDA(cudaMemcpyAsync(s->stage.p + 12, I.AE.out.p, sizeof(PcgResult), cudaMemcpyDeviceToDevice, g_stream));
+        s->launches += launchImplicitPhase(g_stream, 2, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust);
+    }
+    QGD_CUDA(cudaGetLastError());
+}
+
 void runSteps(qgd_solver* s, int n)
 {
+    if (s->k.implicit) {
+        if (s->halo.active) throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true with a halo exchange (multi-GPU) is not available yet");
+        if (s->stage.n < 16) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * (size_t)s->mesh->h.nCells + 16);
+        runStepsImplicit(s, n);
+        return;
+    }
     const FaceView fv = s->fvsc->view();
     const SolverView sv = s->sview();
     const BndState bs = s->bview();
@@ -741,8 +803,14 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
                                                    "\n\nValid model types are:\n" + toc(kCoeffsTable));
         if (model != "constScPrModel1" && model != "constScPrModel1n" && model != "constScPrModel2")
             throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not available on the device yet (no CPU fallback)");
-        if (d->implicit_diffusion)
-            throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true is not available on the device yet; set QGD::implicitDiffusion false");
+        int diffPrecond = 2;
+        if (d->implicit_diffusion) {
+            const std::string pc = d->diff_preconditioner ? d->diff_preconditioner : "DIC";
+            if (pc == "DIC") diffPrecond = 2; else if (pc == "diagonal") diffPrecond = 1; else if (pc == "none") diffPrecond = 0;
+            else throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown symmetric matrix preconditioner " + pc + "\n\nValid symmetric matrix preconditioners are:\n3\n(\nDIC\ndiagonal\nnone\n)\n");
+            if (mesh->h.nOwned != mesh->h.nCells)
+                throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true on extended sub-meshes (multi-GPU) is not available yet");
+        }
         for (int pk : mesh->h.patchKind)
             if (pk == QGD_PATCH_PROCESSOR)
                 throw Error(QGD_ERR_UNSUPPORTED, "processor patches: use the multi-GPU entry points");
@@ -750,6 +818,8 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         std::unique_ptr<qgd_solver> s(new qgd_solver());
         s->mesh = mesh;
         s->desc = *d;
+        s->desc.diff_preconditioner = nullptr;
+        s->impl.precond = diffPrecond;
         s->fvsc.reset(new qgd_fvsc());
         fvscBuild(*s->fvsc, mesh, d->fvsc_scheme);
         Consts& k = s->k;
@@ -757,7 +827,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         k.ScQGD = d->ScQGD; k.PrQGD = d->PrQGD; k.gamma = d->Cp / (d->Cp - d->R);
         k.alphaEffGamma = d->alpha_eff_gamma_factor; k.energyQuirk = d->energy_ddt_rhoE_quirk; k.reducedScheme = s->fvsc->reduced;
         k.model = model == "constScPrModel1" ? 0 : (model == "constScPrModel1n" ? 1 : 2);
-        k.tauMode = 0; k.alphaUniform = 0.5;
+        k.tauMode = 0; k.alphaUniform = 0.5; k.implicit = d->implicit_diffusion ? 1 : 0;
         const HostMesh& h = mesh->h;
         s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
@@ -987,6 +1057,20 @@ int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, dou
 }
 
 long long qgd_qgdfoam_launch_count(qgd_solver* s) { return s ? s->launches : 0; }
+
+int qgd_qgdfoam_diffusion_iterations(qgd_solver* s, int iters[4])
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || !iters) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_diffusion_iterations: null argument");
+        if (!s->k.implicit || !s->impl.built) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_diffusion_iterations: no implicit step yet");
+        PcgResult r[4];
+        static_assert(sizeof(PcgResult) == 4 * sizeof(double), "PcgResult staging layout");
+        QGD_CUDA(cudaMemcpyAsync(r, s->stage.p, sizeof(r), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        for (int j = 0; j < 4; ++j) iters[j] = r[j].iters;
+    });
+}
 
 int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, int ring_slots)
 {

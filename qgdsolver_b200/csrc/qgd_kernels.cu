@@ -447,7 +447,7 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) o.s.UrhoU[3 * i + j] = o.s.U[i] * o.s.rhoU[j];
-    o.s.p = a.p; o.s.c = bb.c; o.s.H = a.H; o.s.alpha = bb.alphaEff; o.s.mu = bb.mu;
+    o.s.p = a.p; o.s.c = bb.c; o.s.H = a.H; o.s.alpha = k.implicit ? 0.0 : bb.alphaEff; o.s.mu = k.implicit ? 0.0 : bb.mu;
     o.s.tau = k.tauMode == 1 ? bb.aByC : bb.aByC * fv.hf[f];
     // patch snGrad per field [OF fvPatchField::snGrad / zeroGradient / fixedGradient]
     const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
@@ -606,8 +606,9 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     s.p = w * (aP.p - aN.p) + aN.p;
     s.c = w * (bP.c - bN.c) + bN.c;
     s.H = w * (aP.H - aN.H) + aN.H;
-    s.alpha = w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
-    s.mu = w * (bP.mu - bN.mu) + bN.mu;
+    // implicitDiffusion: the mu / alpha terms are solved implicitly, the explicit fluxes carry none (updateFluxes.H:95,131)
+    s.alpha = k.implicit ? 0.0 : w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
+    s.mu = k.implicit ? 0.0 : w * (bP.mu - bN.mu) + bN.mu;
     const double hf = __ldg(&fv.hf[f]);
     {
         const double tI = w * (bP.aByC - bN.aByC) + bN.aByC;
@@ -951,6 +952,299 @@ __global__ void k_init_bnd(Consts k, FaceView fv, SolverView sv, BndState bs, co
     bndClose(k, fv, sv, bs, b, true, cA, sv.aQGD[P]);
 }
 
+
+// ============================================================================ implicit-diffusion branch
+// QGDFoam/updateFluxes.H:107-111, QGDUEqn.H:54-75, QGDEEqn.H:53-64.  Not the headline path: written for correctness
+// with plain thread-per-item kernels; the three U solves and the e solve run in the persistent PCG kernel (qgd_pcg.cu).
+
+// iterate over the faces of cell c in ascending polyMesh order: fn(deviceFace, isNeighbourSide)
+template <class F>
+__device__ __forceinline__ void forCellFacesS(const SolverView& sv, int c, F fn)
+{
+    int last = -1;
+    for (int j = 0; j < sv.cfEllW; ++j) {
+        const int e = __ldg(&sv.cfEll[(size_t)j * sv.nCells + c]);
+        last = e;
+        if (e >= 0) fn(e >> 1, e & 1);
+    }
+    if (last >= 0)
+        for (int t = __ldg(&sv.cfTailOff[c]); t < __ldg(&sv.cfTailOff[c + 1]); ++t) {
+            const int e = __ldg(&sv.cfTailEnc[t]);
+            fn(e >> 1, e & 1);
+        }
+}
+
+// boundary value of U.  newU: after the solve (fixedValue keeps its value, zeroGradient follows the cell)
+__device__ __forceinline__ void bndU(const SolverView& sv, const BndState& bs, int b, int P, bool newU, double (&u)[3])
+{
+    if (!newU) { const RecA a = bs.A[b]; u[0] = a.Ux; u[1] = a.Uy; u[2] = a.Uz; return; }
+    if (bs.bcU[b] == QGD_BC_FIXED_VALUE) { u[0] = bs.bvU[3 * (size_t)b]; u[1] = bs.bvU[3 * (size_t)b + 1]; u[2] = bs.bvU[3 * (size_t)b + 2]; }
+    else { const size_t n = sv.nCells; u[0] = sv.S[n + P]; u[1] = sv.S[2 * n + P]; u[2] = sv.S[3 * n + P]; }
+}
+
+// [OF-v2312] fvc::grad(U), Gauss linear, cell values: (1/V) sum_f +-Sf (x) U_f
+__global__ void __launch_bounds__(kBlock) k_gauss_gradU(FaceView fv, SolverView sv, BndState bs, double* __restrict__ GU, int newU)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nCells) return;
+    const size_t n = sv.nCells, nF = fv.nF;
+    const double uc[3] = {sv.S[n + c], sv.S[2 * n + c], sv.S[3 * n + c]};
+    double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    forCellFacesS(sv, c, [&](int f, int side) {
+        const double sgn = side ? -1.0 : 1.0;
+        double uf[3];
+        if (f < fv.nI) {
+            const int o = side ? __ldg(&fv.own[f]) : __ldg(&fv.nei[f]);
+            const double w = __ldg(&fv.w[f]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double uo = sv.S[(1 + j) * n + o];
+                uf[j] = side ? (w * (uo - uc[j]) + uc[j]) : (w * (uc[j] - uo) + uo);
+            }
+        } else {
+            const int b = f - fv.nI;
+            if (__ldg(&fv.bKind[b]) == QGD_PATCH_EMPTY) return;
+            bndU(sv, bs, b, c, newU != 0, uf);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double Si = __ldg(&fv.Sf[(size_t)i * nF + f]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) G[3 * i + j] += sgn * (Si * uf[j]);
+        }
+    });
+    const double V = __ldg(&sv.V[c]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) GU[t * n + c] = G[t] / V;
+}
+
+// mu * dev2(T(g)) ; dev2(A) = A - (2/3) tr(A) I
+__device__ __forceinline__ void muDev2T(double mu, const double (&g)[9], double (&o)[9])
+{
+    const double tr = g[0] + g[4] + g[8];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[3 * i + j] = mu * (g[3 * j + i] - (2.0 / 3.0) * tr * (i == j ? 1.0 : 0.0));
+}
+__device__ __forceinline__ void loadG(const double* GU, size_t n, int c, double (&g)[9])
+{
+#pragma unroll
+    for (int t = 0; t < 9; ++t) g[t] = GU[t * n + c];
+}
+// boundary value of fvc::grad(U): gaussGrad::correctBoundaryConditions  [OF-v2312]
+__device__ __forceinline__ void bndGrad(const double (&gP)[9], const double (&nrm)[3], const double (&sn)[3], double (&gB)[9])
+{
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double nG = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) nG += nrm[i] * gP[3 * i + j];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) gB[3 * i + j] = gP[3 * i + j] + nrm[i] * (sn[j] - nG);
+    }
+}
+
+// phase "diff": per face phiTauMC (3) and the Laplacian coefficients of the U and e equations
+__global__ void __launch_bounds__(kBlock) k_face_diff(FaceView fv, SolverView sv, BndState bs, ImplicitView iv)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= fv.nF) return;
+    const size_t n = sv.nCells, nF = fv.nF;
+    double Sf[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Sf[i] = fv.Sf[(size_t)i * nF + f];
+    const double ms = fv.magSf[f], nd = fv.ndC[f];
+    double tMC[9], muf, alf;
+    if (f < fv.nI) {
+        const int P = fv.own[f], N = fv.nei[f];
+        const double w = fv.w[f];
+        const double muP = sv.S[13 * n + P], muN = sv.S[13 * n + N], aP = sv.S[14 * n + P], aN = sv.S[14 * n + N];
+        muf = w * (muP - muN) + muN;
+        alf = w * (aP - aN) + aN;
+        double gP[9], gN[9], tP[9], tN[9];
+        loadG(iv.GU0, n, P, gP); loadG(iv.GU0, n, N, gN);
+        muDev2T(muP, gP, tP); muDev2T(muN, gN, tN);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) tMC[t] = w * (tP[t] - tN[t]) + tN[t];
+    } else {
+        const int b = f - fv.nI;
+        if (fv.bKind[b] == QGD_PATCH_EMPTY) {
+            iv.FT[f] = 0.0; iv.FT[nF + f] = 0.0; iv.FT[2 * nF + f] = 0.0; iv.aU[f] = 0.0; iv.aE[f] = 0.0;
+            return;
+        }
+        const int P = fv.own[f];
+        const RecA a = bs.A[b];
+        const RecB bb = bs.B[b];
+        muf = bb.mu; alf = bb.alphaEff;
+        const double nrm[3] = {Sf[0] / ms, Sf[1] / ms, Sf[2] / ms};
+        const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE;
+        const double delta = fv.dC[f];
+        const double sn[3] = {fixU ? delta * (a.Ux - sv.S[n + P]) : 0.0, fixU ? delta * (a.Uy - sv.S[2 * n + P]) : 0.0,
+                              fixU ? delta * (a.Uz - sv.S[3 * n + P]) : 0.0};
+        double gP[9], gB[9];
+        loadG(iv.GU0, n, P, gP);
+        bndGrad(gP, nrm, sn, gB);
+        muDev2T(bb.mu, gB, tMC);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) iv.FT[j * nF + f] = Sf[0] * tMC[j] + Sf[1] * tMC[3 + j] + Sf[2] * tMC[6 + j];
+    iv.aU[f] = nd * (muf * ms);
+    iv.aE[f] = nd * (alf * ms);
+}
+
+// phase A: rho, rhoU (explicit), U* = rhoU/rho ; U-equation diagonal and sources
+template <int W>
+__global__ void __launch_bounds__(kBlock) k_cell_implA(Consts k, FaceView fv, SolverView sv, BndState bs, ImplicitView iv)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nOwned) return;
+    const size_t n = sv.nCells, nF = fv.nF;
+    const RecA a = loadA(sv, c);
+    const RecB b = loadB(sv, c);
+    double sm = 0.0, su[3] = {0, 0, 0}, st[3] = {0, 0, 0}, dL = 0.0, bI = 0.0, bB[3] = {0, 0, 0};
+    forCellFacesS(sv, c, [&](int f, int side) {
+        const double sgn = side ? -1.0 : 1.0;
+        double fm, f0, f1, f2, fe;
+        loadFlux<false>(sv, fv.nI, f, fm, f0, f1, f2, fe);
+        sm += sgn * fm; su[0] += sgn * f0; su[1] += sgn * f1; su[2] += sgn * f2;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) st[j] += sgn * iv.FT[j * nF + f];
+        if (f < fv.nI) dL += iv.aU[f];
+        else {
+            const int bf = f - fv.nI;
+            if (fv.bKind[bf] != QGD_PATCH_EMPTY && bs.bcU[bf] == QGD_BC_FIXED_VALUE) {      // internalCoeffs / boundaryCoeffs
+                const double gS = iv.aU[f];
+                bI += gS;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) bB[j] += gS * bs.bvU[3 * (size_t)bf + j];
+            }
+        }
+    });
+    const double V = __ldg(&sv.V[c]);
+    const double rDeltaT = 1.0 / sv.sc->dt;
+    const double diag = rDeltaT * V;
+    const double rho = (rDeltaT * a.rho * V - V * (sm / V)) / diag;                         // QGDRhoEqn.H:40-47
+    const double u0[3] = {a.Ux, a.Uy, a.Uz}, r0[3] = {b.rhoUx, b.rhoUy, b.rhoUz};
+    iv.old[c] = a.Ux; iv.old[n + c] = a.Uy; iv.old[2 * n + c] = a.Uz; iv.old[3 * n + c] = a.rho;
+    sv.S[c] = rho;
+    iv.diagU[c] = rDeltaT * rho * V + dL + bI;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const double rhoU = (rDeltaT * r0[j] * V - V * (su[j] / V)) / diag;                 // QGDUEqn.H:36-45
+        const double Us = rhoU / rho;                                                       // :48-50
+        sv.S[(8 + j) * n + c] = rhoU;
+        sv.S[(1 + j) * n + c] = Us;
+        // :56-62  fvm::ddt(rho,U) - fvc::ddt(rho,U) - fvm::laplacian(muf,U) - fvc::div(phiTauMC) == 0
+        iv.bU[j * n + c] = rDeltaT * a.rho * u0[j] * V + V * (rDeltaT * (rho * Us - a.rho * u0[j])) + V * (st[j] / V) + bB[j];
+    }
+}
+
+// phase "sigma": phiSigmaDotU = Sf & ((muf*linearInterpolate(fvc::grad(U)) + tauMC) & Uf)   QGDUEqn.H:72-74
+__global__ void __launch_bounds__(kBlock) k_face_sigma(FaceView fv, SolverView sv, BndState bs, ImplicitView iv)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= fv.nF) return;
+    const size_t n = sv.nCells, nF = fv.nF;
+    double Sf[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Sf[i] = fv.Sf[(size_t)i * nF + f];
+    const double ms = fv.magSf[f];
+    double T[9], Uf[3];
+    if (f < fv.nI) {
+        const int P = fv.own[f], N = fv.nei[f];
+        const double w = fv.w[f];
+        const double muP = sv.S[13 * n + P], muN = sv.S[13 * n + N];
+        const double muf = w * (muP - muN) + muN;
+        double g0P[9], g0N[9], g1P[9], g1N[9], tP[9], tN[9];
+        loadG(iv.GU0, n, P, g0P); loadG(iv.GU0, n, N, g0N); loadG(iv.GU1, n, P, g1P); loadG(iv.GU1, n, N, g1N);
+        muDev2T(muP, g0P, tP); muDev2T(muN, g0N, tN);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) T[t] = muf * (w * (g1P[t] - g1N[t]) + g1N[t]) + (w * (tP[t] - tN[t]) + tN[t]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const double uP = iv.old[j * n + P], uN = iv.old[j * n + N]; Uf[j] = w * (uP - uN) + uN; }
+    } else {
+        const int b = f - fv.nI;
+        if (fv.bKind[b] == QGD_PATCH_EMPTY) { iv.Fs[f] = 0.0; return; }
+        const int P = fv.own[f];
+        const RecA a = bs.A[b];
+        const RecB bb = bs.B[b];
+        const double nrm[3] = {Sf[0] / ms, Sf[1] / ms, Sf[2] / ms};
+        const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE;
+        const double delta = fv.dC[f];
+        const double uOld[3] = {iv.old[P], iv.old[n + P], iv.old[2 * n + P]};
+        const double ub[3] = {a.Ux, a.Uy, a.Uz};
+        double un[3];
+        bndU(sv, bs, b, P, true, un);
+        double sn0[3], sn1[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            sn0[j] = fixU ? delta * (ub[j] - uOld[j]) : 0.0;
+            sn1[j] = fixU ? delta * (un[j] - sv.S[(1 + j) * n + P]) : 0.0;
+        }
+        double g0[9], g1[9], g0B[9], g1B[9], tB[9];
+        loadG(iv.GU0, n, P, g0); loadG(iv.GU1, n, P, g1);
+        bndGrad(g0, nrm, sn0, g0B); bndGrad(g1, nrm, sn1, g1B);
+        muDev2T(bb.mu, g0B, tB);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) T[t] = bb.mu * g1B[t] + tB[t];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Uf[j] = ub[j];
+    }
+    double sg[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) sg[i] = T[3 * i] * Uf[0] + T[3 * i + 1] * Uf[1] + T[3 * i + 2] * Uf[2];
+    iv.Fs[f] = Sf[0] * sg[0] + Sf[1] * sg[1] + Sf[2] * sg[2];
+}
+
+// phase B: rhoU = rho*U ; rhoE (explicit, with phiSigmaDotU) ; e* ; e-equation diagonal and source
+__global__ void __launch_bounds__(kBlock) k_cell_implB(Consts k, FaceView fv, SolverView sv, BndState bs, ImplicitView iv)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nOwned) return;
+    const size_t n = sv.nCells;
+    double se = 0.0, ss = 0.0, dL = 0.0, bI = 0.0, bB = 0.0;
+    forCellFacesS(sv, c, [&](int f, int side) {
+        const double sgn = side ? -1.0 : 1.0;
+        double fm, f0, f1, f2, fe;
+        loadFlux<false>(sv, fv.nI, f, fm, f0, f1, f2, fe);
+        se += sgn * fe; ss += sgn * iv.Fs[f];
+        if (f < fv.nI) dL += iv.aE[f];
+        else {
+            const int bf = f - fv.nI;
+            if (fv.bKind[bf] != QGD_PATCH_EMPTY && bs.bcT[bf] == QGD_BC_FIXED_VALUE) {      // fixedEnergy
+                bI += iv.aE[f];
+                bB += iv.aE[f] * thermoEs(k, bs.bvT[bf]);
+            }
+        }
+    });
+    const double V = __ldg(&sv.V[c]);
+    const double rDeltaT = 1.0 / sv.sc->dt;
+    const double rho = sv.S[c], rho0 = iv.old[3 * n + c], e0 = sv.S[4 * n + c], rhoE0 = sv.S[11 * n + c];
+    const double U[3] = {sv.S[n + c], sv.S[2 * n + c], sv.S[3 * n + c]};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sv.S[(8 + j) * n + c] = rho * U[j];                         // QGDUEqn.H:70
+    const double rhoE = (rDeltaT * rhoE0 * V - V * (se / V) + V * (ss / V)) / (rDeltaT * V);   // QGDEEqn.H:37-46
+    const double es = rhoE / rho - 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);         // :49
+    sv.S[11 * n + c] = rhoE;
+    sv.S[4 * n + c] = es;
+    iv.diagE[c] = rDeltaT * rho * V + dL + bI;                                              // :55-60
+    iv.bE[c] = rDeltaT * rho0 * e0 * V + V * (rDeltaT * (rho * es - rho0 * e0)) + bB;
+}
+
+// phase C: rhoE = rho (e + 0.5 |U|^2) ; thermo.correct() ; p = rho/psi   (QGDEEqn.H:63, QGDFoam.C:149-154)
+__global__ void __launch_bounds__(kBlock) k_cell_implC(Consts k, SolverView sv)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nOwned) return;
+    const size_t n = sv.nCells;
+    const double rho = sv.S[c], e = sv.S[4 * n + c], pOld = sv.S[5 * n + c], TOld = sv.S[6 * n + c];
+    const double U[3] = {sv.S[n + c], sv.S[2 * n + c], sv.S[3 * n + c]};
+    const double rhoU[3] = {rho * U[0], rho * U[1], rho * U[2]};
+    const double rhoE = rho * (e + 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]));
+    cellThermo(k, rho, U, rhoU, rhoE, e, pOld, TOld, __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]), sv, c);
+}
+
 } // namespace
 
 // ============================================================================ launchers
@@ -1094,5 +1388,48 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
     if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     return n;
 }
+
+int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
+                        const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust)
+{
+    int n = 0;
+    const bool pointsNeeded = !c.reducedScheme;
+    if (phase == 0) {          // updateFields + updateFluxes (reduced explicit fluxes), phiTauMC, rho/rhoU update, U system
+        if (pointsNeeded) {
+            if (sv.pcEllW == 4) k_points<4><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+            else if (sv.pcEllW == 6) k_points<6><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+            else k_points<8><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+            ++n;
+            if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
+        }
+        if (fv.nB && anyQgdFlux) {
+            k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+            if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
+        }
+        k_gauss_gradU<<<nblk(sv.nCells), kBlock, 0, st>>>(fv, sv, bs, iv.GU0, 0); ++n;
+        if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
+        if (fv.nIActive) {
+            const FaceVariant& fvn = kFaceVariants[g_faceVariant];
+            const int grid = std::min(gridFaces, nblk(fv.nIActive, fvn.block));
+            fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+            ++n;
+        }
+        k_face_diff<<<nblk(fv.nF), kBlock, 0, st>>>(fv, sv, bs, iv); ++n;
+        k_dt<<<1, 1, 0, st>>>(sv.sc, nullptr); ++n;
+        if (sv.cfEllW == 4) k_cell_implA<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv);
+        else if (sv.cfEllW == 6) k_cell_implA<6><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv);
+        else k_cell_implA<8><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv);
+        ++n;
+    } else if (phase == 1) {   // after the U solves: sigmaDotU, rhoE update, e system
+        k_gauss_gradU<<<nblk(sv.nCells), kBlock, 0, st>>>(fv, sv, bs, iv.GU1, 1); ++n;
+        k_face_sigma<<<nblk(fv.nF), kBlock, 0, st>>>(fv, sv, bs, iv); ++n;
+        k_cell_implB<<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv); ++n;
+    } else {                   // after the e solve: conserved variables, thermo, boundary state
+        k_cell_implC<<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv); ++n;
+        if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
+    }
+    return n;
+}
+
 
 } // namespace qgd

@@ -17,6 +17,7 @@ struct Consts {
     //   2: I(alphaQGD)*hQGDf/I(c)         (constScPrModel1n before "U" is registered, i.e. the first step; alphaQGD uniform)
     int model, tauMode;
     double alphaUniform;
+    int implicit;            // QGD::implicitDiffusion: the mu / alpha terms leave the explicit fluxes (updateFluxes.H:95-111,131-135)
 };
 
 struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
@@ -98,6 +99,19 @@ struct SolverView {
     StepScalars* sc;
 };
 
+// scratch of the implicit-diffusion branch (QGDUEqn.H:54-75, QGDEEqn.H:53-64)
+struct ImplicitView {
+    double* GU0;      // [9][nCells] fvc::grad(U) of the old U (Gauss linear)
+    double* GU1;      // [9][nCells] fvc::grad(U) of the solved U
+    double* old;      // [4][nCells] U old (3), rho old
+    double* FT;       // [3][nF] phiTauMC
+    double* aU;       // [nF] muf |Sf| nonOrthDeltaCoeffs   (laplacian(muf,U) coefficient)
+    double* aE;       // [nF] alphauf |Sf| nonOrthDeltaCoeffs
+    double* Fs;       // [nF] phiSigmaDotU
+    double* diagU; double* bU;      // [nCells], [3][nCells]
+    double* diagE; double* bE;      // [nCells], [nCells]
+};
+
 // work plan of the pipelined face+cell kernel (k_face_cell_pipeline)
 struct PipeView {
     int nChunks, lag, epoch;
@@ -121,6 +135,9 @@ struct StepHooks { std::function<void()> midStep, beforeDt; };
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr,
                const PipeView* pipe = nullptr, int gridPipe = 0);
+// implicit-diffusion step, phase by phase (the PCG solves run between the phases, see runStepsImplicit in qgd_abi.cu)
+int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
+                        const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust);
 int faceKernelGrid();
 int pipelineKernelGrid(int cfEllW);
 void setFaceVariant(int v);   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux

@@ -250,7 +250,36 @@ template <class K> int coopGrid(K kernel)
 
 } // namespace
 
-void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* upper, int pc, cudaStream_t st)
+__global__ void k_fill_coef(int n, int W, const int* __restrict__ encFace, const double* __restrict__ faceCoef, double* __restrict__ coef,
+                            int nTail, const int* __restrict__ tailFace, double* __restrict__ tailCoef)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n)
+        for (int j = 0; j < W; ++j) {
+            const int f = encFace[(size_t)j * n + c];
+            coef[(size_t)j * n + c] = f >= 0 ? -faceCoef[f] : 0.0;
+        }
+    if (c < nTail) { const int f = tailFace[c]; tailCoef[c] = f >= 0 ? -faceCoef[f] : 0.0; }
+}
+
+void PcgMatrix::refresh(const double* faceCoef, const double* diagDev, cudaStream_t st)
+{
+    if (!encFace.n) throw Error(QGD_ERR_STATE, "PcgMatrix::refresh: matrix was built without face ids");
+    const int nTail = (int)tailFace.n;
+    k_fill_coef<<<(std::max(n, nTail) + 255) / 256, 256, 0, st>>>(n, W, encFace.p, faceCoef, coef.p, nTail, tailFace.p, tailCoef.p);
+    QGD_CUDA(cudaMemcpyAsync(diag.p, diagDev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (precond == 1) k_recip<<<(n + 255) / 256, 256, 0, st>>>(n, diag.p, rD.p);
+    else if (precond == 2) {
+        PcgView v = view(0, 0, 0);
+        double* raw = rD.p;
+        void* args[] = {&v, &raw};
+        const int g = std::max(1, std::min(coopGrid(k_dic_factor), (n + kPcgBlock - 1) / kPcgBlock));
+        QGD_CUDA(cudaLaunchCooperativeKernel((void*)k_dic_factor, dim3(g), dim3(kPcgBlock), args, 0, st));
+    }
+    QGD_CUDA(cudaGetLastError());
+}
+
+void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* upper, int pc, cudaStream_t st, const std::vector<int>* faceInv)
 {
     n = h.nCells;
     precond = pc;
@@ -265,7 +294,7 @@ void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* uppe
         maxRow = std::max(maxRow, k);
     }
     W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
-    std::vector<int> e((size_t)W * n), tOff(n + 1, 0), tEnc, level(n, 0);
+    std::vector<int> e((size_t)W * n), tOff(n + 1, 0), tEnc, level(n, 0), eFace((size_t)W * n, -1), tFace;
     std::vector<double> a((size_t)W * n, 0.0), tCoef;
     for (int c = 0; c < n; ++c) {
         for (int j = 0; j < W; ++j) e[(size_t)j * n + c] = c << 1;
@@ -277,13 +306,15 @@ void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* uppe
             const int o = lowerSide ? h.owner[f] : h.neighbour[f];
             const int enc1 = (o << 1) | lowerSide;
             if (lowerSide) level[c] = std::max(level[c], level[o] + 1);      // owner < neighbour: level[o] is final
-            if (j < W) { e[(size_t)j * n + c] = enc1; a[(size_t)j * n + c] = upper[f]; }
-            else { tEnc.push_back(enc1); tCoef.push_back(upper[f]); }
+            const int devFace = faceInv ? (*faceInv)[f] : f;
+            if (j < W) { e[(size_t)j * n + c] = enc1; a[(size_t)j * n + c] = upper[f]; eFace[(size_t)j * n + c] = devFace; }
+            else { tEnc.push_back(enc1); tCoef.push_back(upper[f]); tFace.push_back(devFace); }
             ++j;
         }
         tOff[c + 1] = (int)tEnc.size();
     }
-    if (tEnc.empty()) { tEnc.push_back(0); tCoef.push_back(0.0); }
+    if (tEnc.empty()) { tEnc.push_back(0); tCoef.push_back(0.0); tFace.push_back(-1); }
+    if (faceInv) { encFace.upload(eFace, st); tailFace.upload(tFace, st); }
     for (int f = 0; f < nI; ++f)
         if (h.owner[f] >= h.neighbour[f]) throw Error(QGD_ERR_INVALID, "PCG: mesh is not in upper-triangular order (owner < neighbour)");
     nLevels = 0;
@@ -319,7 +350,7 @@ PcgView PcgMatrix::view(double tol, double relTol, int maxIter) const
 {
     PcgView v;
     v.n = n; v.W = W; v.enc = enc.p; v.coef = coef.p; v.tailOff = tailOff.p; v.tailEnc = tailEnc.p; v.tailCoef = tailCoef.p;
-    v.diag = diag.p; v.rD = rD.p; v.b = b.p; v.x = xExternal ? xExternal : x.p; v.r = r.p; v.w = w.p; v.z = z.p; v.p0 = p0.p; v.p1 = p1.p;
+    v.diag = diag.p; v.rD = rD.p; v.b = bExternal ? bExternal : b.p; v.x = xExternal ? xExternal : x.p; v.r = r.p; v.w = w.p; v.z = z.p; v.p0 = p0.p; v.p1 = p1.p;
     v.partials = partials.p; v.nLevels = nLevels; v.lvlOff = lvlOff.p; v.lvlCells = lvlCells.p;
     v.tol = tol; v.relTol = relTol; v.maxIter = maxIter; v.precond = precond; v.out = out.p;
     return v;

@@ -30,10 +30,16 @@ struct PcgMatrix {
     DevBuf<int> enc, tailOff, tailEnc, lvlOff, lvlCells;
     DevBuf<double> coef, tailCoef, diag, rD, b, x, r, w, z, p0, p1, partials;
     DevBuf<PcgResult> out;
+    DevBuf<int> encFace, tailFace;   // device face id of every ELL / tail entry (-1: padding), for refresh()
     int gridBlocks = 0;
+    double* bExternal = nullptr;     // when set, the right-hand side lives in the caller's array
     double* xExternal = nullptr;     // when set, the solution vector lives in the caller's array (e.g. the p slice of the QHD state)
     // diag: nCells (boundary contributions already added), upper: nInternal in polyMesh face order
-    void build(const HostMesh& h, const double* diag, const double* upper, int precond, cudaStream_t st);
+    void build(const HostMesh& h, const double* diag, const double* upper, int precond, cudaStream_t st,
+               const std::vector<int>* faceInv = nullptr);
+    // new coefficients on the same addressing, all on the device: upper[f] = -faceCoef[deviceFace f], diagonal = diagDev;
+    // the preconditioner is rebuilt (needs build(..., faceInv))
+    void refresh(const double* faceCoef, const double* diagDev, cudaStream_t st);
     PcgView view(double tol, double relTol, int maxIter) const;
     // solves A x = b for the device vectors b, x (in place); returns kernel launches issued
     int solve(double tol, double relTol, int maxIter, cudaStream_t st);

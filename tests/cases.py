@@ -13,8 +13,10 @@ GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5,
 
 class Case:
     def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, gas=GAS, dt=1e-4, scheme="GaussVolPoint",
-                 alphaQGD=None, model="constScPrModel1", **opts):
-        self.model = model
+                 alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, **opts):
+        self.model, self.implicit = model, implicit
+        self.diff_solver = dict(tol=1e-14, rel_tol=0.0, max_iter=2000, precond="DIC")
+        self.diff_solver.update(diff_solver or {})
         self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
         self.bcU, self.bcT, self.bcP = [np.asarray(x, np.int32) for x in (bcU, bcT, bcP)]
         self.bvU, self.bvT, self.bvP = bvU, bvT, bvP
@@ -28,7 +30,9 @@ class Case:
         o = O.Oracle(self.mesh, n_threads=n_threads)
         g = self.gas
         prm = O.QGDParams(R=g["R"], Cp=g["Cp"], Hf=g["Hf"], Tref=g["Tref"], Hsref=g["Hsref"], mu=g["mu"], Pr=g["Pr"],
-                          ScQGD=g["ScQGD"], PrQGD=g["PrQGD"], implicitDiffusion=0,
+                          ScQGD=g["ScQGD"], PrQGD=g["PrQGD"], implicitDiffusion=int(self.implicit),
+                          diffTol=self.diff_solver["tol"], diffRelTol=self.diff_solver["rel_tol"],
+                          diffMaxIter=self.diff_solver["max_iter"], diffPrecond=O.PRECONDS[self.diff_solver["precond"]],
                           alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
                           energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model])
         scheme = O.FVSC_GAUSSVOLPOINT if self.scheme == "GaussVolPoint" else O.FVSC_REDUCED
@@ -43,7 +47,10 @@ class Case:
     # ---- product
     def make_solver(self, api, dmesh=None):
         dmesh = dmesh or api.Mesh(self.mesh)
-        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, **self.gas, **self.opts)
+        ds = self.diff_solver
+        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, implicit_diffusion=self.implicit,
+                        diff_tol=ds["tol"], diff_rel_tol=ds["rel_tol"], diff_max_iter=ds["max_iter"], diff_precond=ds["precond"],
+                        **self.gas, **self.opts)
         s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
         s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
         return s

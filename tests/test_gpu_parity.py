@@ -87,6 +87,13 @@ STEP_CASES = {
     "hex_model2": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel2"),
     "2d_model1n_qgdflux": lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", model="constScPrModel1n"),
     "prism_model1n_adjust": lambda: cases.case_prism(bcs="fixed", model="constScPrModel1n", adjust_time_step=True, max_co=0.1),
+    # implicitDiffusion true (the reference's default): QGDUEqn.H:54-75, QGDEEqn.H:53-64
+    "hex_implicit": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", implicit=True),
+    "hex_implicit_fixed_diag": lambda: cases.case_hex3d(bcs="fixed", implicit=True, diff_solver=dict(precond="diagonal"),
+                                                        gas=dict(cases.GAS, mu=5e-3)),
+    "2d_implicit_qgdflux": lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", implicit=True),
+    "prism_implicit_adjust": lambda: cases.case_prism(bcs="fixed", implicit=True, adjust_time_step=True, max_co=0.1),
+    "sod_implicit": lambda: cases.case_sod(200, implicit=True),
 }
 
 
@@ -111,6 +118,8 @@ def test_qgdfoam_100_steps_match_oracle(qgd, oracle_mod, name):
             assert float(np.abs(gb[kind != 1] - ob[kind != 1]).max()) / scale < TOL_STEP, f"{name}: boundary {f}"
     if c.opts["adjust_time_step"]:
         assert abs(s.scalars()["deltaT"] - o.deltaT()) < 1e-10 * o.deltaT()
+    if c.implicit:
+        assert all(0 <= it < c.diff_solver["max_iter"] for it in s.diffusion_iterations())
 
 
 def test_fluxes_match_oracle_after_one_step(qgd, oracle_mod):

@@ -287,3 +287,39 @@ def test_qhd_preconditioners_agree(oracle_mod):
         for a, b in zip(res[pc][:3], res["DIC"][:3]):
             assert np.abs(a - b).max() < 1e-9 * max(np.abs(b).max(), 1e-30)
     assert res["DIC"][3] < res["diagonal"][3] <= res["none"][3]
+
+
+@pytest.mark.parametrize("implicit", [False, True])
+def test_shear_wave_decay_matches_discrete_eigenvalue(oracle_mod, implicit):
+    """U = (0, A sin(pi x), 0) between no-slip x-walls in a uniform gas: every QGD regularisation term vanishes (no
+    pressure / density gradient, div U = 0, U.grad U = 0), leaving d(rho Uy)/dt = d/dx(mu dUy/dx) with mu = mu_mol + muQGD.
+    sin(pi x_c) is an exact eigenvector of the cell-centred Dirichlet Laplacian, so one step multiplies the amplitude by
+    (1 - dt nu lambda_h) in the explicit branch (Pi = mu(...) through the fvsc face gradient, QGDFoam/updateFluxes.H:95-106)
+    and by 1/(1 + dt nu lambda_h) in the implicit branch (fvm::laplacian(muf,U), QGDUEqn.H:56-62).  (Only the first step
+    is exact: the patch-point values on the wall edges then feed a small div U into the wall faces.)"""
+    import cases
+    n, A, N, dt = 16, 1e-3, 1, 1e-3
+    mesh = cases.pm.hex_box(n, 2, 2, lengths=(1.0, 2.0 / n, 2.0 / n))      # cubic cells: hQGD == hQGDf everywhere
+    nP, nB = len(mesh.patches), mesh.n_bnd
+    names = [p.name for p in mesh.patches]
+    kU = np.array([cases.FV if nm in ("xMin", "xMax") else cases.ZG for nm in names], np.int32)
+    kT = np.full(nP, cases.ZG, np.int32)
+    gas = dict(cases.GAS, mu=0.05)
+    g = gas["Cp"] / (gas["Cp"] - gas["R"])
+    x = mesh.C[:, 0]
+    U0 = np.zeros((mesh.n_cells, 3))
+    U0[:, 1] = A * np.sin(np.pi * x)
+    p0 = np.full(mesh.n_cells, 1.0 / g)
+    T0 = p0 / gas["R"]
+    c = cases.Case(mesh, U0, T0, p0, kU, kT, kT, np.zeros((nB, 3)), np.ones(nB), np.ones(nB), gas=gas, dt=dt, implicit=implicit)
+    o = c.make_oracle(oracle_mod)
+    mu = o.get("mu")
+    assert np.ptp(mu) < 1e-14 * mu.mean()
+    nu = mu.mean() / 1.0
+    c.oracle_step(o, N)
+    h = 1.0 / n
+    lam = (2.0 - 2.0 * np.cos(np.pi * h)) / h ** 2
+    fac = (1.0 + dt * nu * lam) ** (-N) if implicit else (1.0 - dt * nu * lam) ** N
+    rhoU = o.get("rhoU")
+    assert np.abs(rhoU[:, 1] - fac * A * np.sin(np.pi * x)).max() < 1e-11 * A
+    assert abs(fac - 1.0) > 5e-4
