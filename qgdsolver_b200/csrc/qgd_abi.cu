@@ -844,6 +844,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         sc.maxCo = d->max_co; sc.maxDeltaT = d->max_delta_t; sc.cTau = d->c_tau; sc.adjust = d->adjust_time_step;
         s->sc.upload(std::vector<StepScalars>(1, sc), g_stream);
         if (const char* v = getenv("QGD_FACE_VARIANT")) setFaceVariant(atoi(v));
+        if (const char* v = getenv("QGD_FACE_TMA")) setFaceTma(atoi(v));
         s->gridFaces = faceKernelGrid();
         *out = s.release();
     });

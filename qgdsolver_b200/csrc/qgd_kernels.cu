@@ -541,9 +541,11 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
 }
 
 // ---- one internal face: 11 interpolations + 4 GaussVolPoint gradients + QGD flux algebra -> 5 flux doubles at `slot`
-template <bool ADJUST, bool GEOM>
+// SMEM: the streamed per-face constants (G, Sf, w, hQGDf, |Sf|) were staged by TMA into shared memory: sd[k*kTmaTile + li]
+constexpr int kTmaTile = 256;
+template <bool ADJUST, bool GEOM, bool SMEM = false>
 __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv, const SolverView& sv, int f, size_t slot, int P, int N,
-                                            int flagsCur, const int4& v, double& coMax, double& tauMin)
+                                            int flagsCur, const int4& v, double& coMax, double& tauMin, const double* sd = nullptr, int li = 0)
 {
     const size_t nF = fv.nF;
     const RecA aP = loadA(sv, P), aN = loadA(sv, N);
@@ -556,7 +558,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
     double g1[3], g2[3], gp[3], Sf[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
+    for (int i = 0; i < 3; ++i) Sf[i] = SMEM ? sd[(9 + i) * kTmaTile + li] : __ldg(&fv.Sf[(size_t)i * nF + f]);
     if (GEOM) {
         // every internal face is a 3D quad (FaceView::allGeom): G rebuilt from the four vertices and the two cell centres (SURVEY A.2 closed form, same operation
         // order as HostMesh::buildFaceRecords): e1 = p2-p4, e2 = p3-p1, d = C_N-C_P, D = e2.(e1 x d),
@@ -578,15 +580,15 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     } else {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
-            g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
-            gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
+            g1[i] = SMEM ? sd[(0 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
+            g2[i] = SMEM ? sd[(3 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
+            gp[i] = SMEM ? sd[(6 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
         }
     }
     FaceGrads g;
     gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
     // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
-    const double w = __ldg(&fv.w[f]);
+    const double w = SMEM ? sd[12 * kTmaTile + li] : __ldg(&fv.w[f]);
     FaceState s;
     s.rho = w * (aP.rho - aN.rho) + aN.rho;
     s.U[0] = w * (aP.Ux - aN.Ux) + aN.Ux; s.U[1] = w * (aP.Uy - aN.Uy) + aN.Uy; s.U[2] = w * (aP.Uz - aN.Uz) + aN.Uz;
@@ -609,7 +611,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     // implicitDiffusion: the mu / alpha terms are solved implicitly, the explicit fluxes carry none (updateFluxes.H:95,131)
     s.alpha = k.implicit ? 0.0 : w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
     s.mu = k.implicit ? 0.0 : w * (bP.mu - bN.mu) + bN.mu;
-    const double hf = __ldg(&fv.hf[f]);
+    const double hf = SMEM ? sd[13 * kTmaTile + li] : __ldg(&fv.hf[f]);
     {
         const double tI = w * (bP.aByC - bN.aByC) + bN.aByC;
         s.tau = k.tauMode == 0 ? tI * hf                     // constScPrModel1.C:103
@@ -620,7 +622,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
     sv.FI[0][slot] = Fm; sv.FI[1][slot] = FU[0]; sv.FI[2][slot] = FU[1]; sv.FI[3][slot] = FU[2]; sv.FI[4][slot] = FE;
     if (ADJUST) {                                           // QGDCourantNo.H:38-50
-        const double ms = __ldg(&fv.magSf[f]);
+        const double ms = SMEM ? sd[14 * kTmaTile + li] : __ldg(&fv.magSf[f]);
         const double Unf = s.U[0] * (Sf[0] / ms) + s.U[1] * (Sf[1] / ms) + s.U[2] * (Sf[2] / ms);
         coMax = fmax(coMax, fmax(fabs(Unf + s.c), fabs(Unf - s.c)) / hf);
         tauMin = fmin(tauMin, s.tau);
@@ -694,6 +696,111 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     storeRec(sv, 0, cell, a);
     storeRec(sv, 8, cell, b);
     if (sv.tauOut) sv.tauOut[cell] = (k.model == 2) ? tau + k.mu / (pOld * k.ScQGD) : tau;     // constScPrModel2.C:112
+}
+
+// ---- TMA-staged variant of the face kernel.  The 140 B of streamed per-face constants (own, nei, flags, vtx, G[9],
+// Sf[3], w, hQGDf [, |Sf|]) of a 256-face tile are fetched by 18 (19) bulk asynchronous copies (cp.async.bulk -> UBLKCP)
+// into a 2-stage shared-memory ring, armed on an mbarrier with the expected byte count; while tile i is computed, tile
+// i+1 is already in flight, so only the cell/point gathers remain on the register-latency path.
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smemAddr(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+
+template <bool ADJUST> struct TmaStage {
+    static constexpr int kDoubles = ADJUST ? 15 : 14;
+    static constexpr int kBytes = kTmaTile * (3 * 4 + 16 + 8 * kDoubles);
+    // layout inside a stage: vtx int4[T] | doubles [kDoubles][T] | own int[T] | nei int[T] | flags int[T]
+    static constexpr int oVtx = 0, oD = kTmaTile * 16, oOwn = oD + kTmaTile * 8 * kDoubles, oNei = oOwn + kTmaTile * 4, oFlags = oNei + kTmaTile * 4;
+};
+
+template <bool ADJUST>
+__device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* stage, unsigned long long* bar, int tile)
+{
+    using L = TmaStage<ADJUST>;
+    const size_t f0 = (size_t)tile * kTmaTile, nF = fv.nF;
+    mbarExpectTx(bar, (unsigned)L::kBytes);
+    bulkLoad(stage + L::oVtx, fv.vtx + f0, kTmaTile * 16, bar);
+    double* d = reinterpret_cast<double*>(stage + L::oD);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) bulkLoad(d + q * kTmaTile, fv.G + q * nF + f0, kTmaTile * 8, bar);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) bulkLoad(d + (9 + q) * kTmaTile, fv.Sf + q * nF + f0, kTmaTile * 8, bar);
+    bulkLoad(d + 12 * kTmaTile, fv.w + f0, kTmaTile * 8, bar);
+    bulkLoad(d + 13 * kTmaTile, fv.hf + f0, kTmaTile * 8, bar);
+    if (ADJUST) bulkLoad(d + 14 * kTmaTile, fv.magSf + f0, kTmaTile * 8, bar);
+    bulkLoad(stage + L::oOwn, fv.own + f0, kTmaTile * 4, bar);
+    bulkLoad(stage + L::oNei, fv.nei + f0, kTmaTile * 4, bar);
+    bulkLoad(stage + L::oFlags, fv.flags + f0, kTmaTile * 4, bar);
+}
+
+template <bool ADJUST, int NST>
+__global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceView fv, SolverView sv)
+{
+    using L = TmaStage<ADJUST>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long bars[NST];
+    double coMax = 0.0, tauMin = DBL_MAX;
+    const int nIA = fv.nIActive;
+    const int nTiles = nIA / kTmaTile;                       // full tiles go through TMA, the remainder through plain loads
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NST; ++q) mbarInit(&bars[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (threadIdx.x == 0) {                                  // prologue: NST-1 tiles in flight
+#pragma unroll
+        for (int q = 0; q < NST - 1; ++q)
+            if (tile + q * (int)gridDim.x < nTiles) tmaIssueTile<ADJUST>(fv, smem + q * L::kBytes, &bars[q], tile + q * gridDim.x);
+    }
+    for (int it = 0; tile < nTiles; ++it, tile += gridDim.x) {
+        const int st = it % NST;
+        const int next = tile + (NST - 1) * (int)gridDim.x;    // refills the stage consumed in the previous iteration
+        const int sn = (it + NST - 1) % NST;
+        if (threadIdx.x == 0 && next < nTiles) tmaIssueTile<ADJUST>(fv, smem + sn * L::kBytes, &bars[sn], next);
+        mbarWait(&bars[st], (unsigned)((it / NST) & 1));
+        const unsigned char* sg = smem + st * L::kBytes;
+        const int li = threadIdx.x;
+        const int f = tile * kTmaTile + li;
+        const int P = reinterpret_cast<const int*>(sg + L::oOwn)[li], N = reinterpret_cast<const int*>(sg + L::oNei)[li];
+        const int flags = reinterpret_cast<const int*>(sg + L::oFlags)[li];
+        const int4 v = reinterpret_cast<const int4*>(sg + L::oVtx)[li];
+        faceFluxOne<ADJUST, false, true>(k, fv, sv, f, (size_t)f, P, N, flags, v, coMax, tauMin, reinterpret_cast<const double*>(sg + L::oD), li);
+        __syncthreads();                                     // every thread is done with this stage before it is refilled
+    }
+    // remainder (< one tile): plain loads, one CTA
+    if (blockIdx.x == gridDim.x - 1) {
+        const int f = nTiles * kTmaTile + (int)threadIdx.x;
+        if (f < nIA)
+            faceFluxOne<ADJUST, false, false>(k, fv, sv, f, (size_t)f, __ldg(&fv.own[f]), __ldg(&fv.nei[f]), __ldg(&fv.flags[f]), __ldg(&fv.vtx[f]),
+                                              coMax, tauMin);
+    }
+    if (ADJUST) blockReduceCo<kTmaTile>(coMax, tauMin, sv.sc);
 }
 
 // flux of face f (device id) as seen by the cell update: internal faces live in the flux array / ring, boundary faces
@@ -1260,8 +1367,26 @@ template <int BLOCK, int MINB> constexpr FaceVariant mkVariant()
 const FaceVariant kFaceVariants[] = {mkVariant<256, 1>(), mkVariant<256, 2>(), mkVariant<128, 4>(), mkVariant<128, 5>(),
                                      mkVariant<128, 6>(), mkVariant<64, 12>(), mkVariant<256, 3>()};
 int g_faceVariant = 1;
+int g_faceTma = 2;          // stages of the TMA ring; QGD_FACE_TMA=0 selects the register-prefetch kernel, 3 a 3-stage ring
+template <bool ADJUST, int NST> int tmaGridOf()
+{
+    int dev = 0, sms = 148, perSM = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_face_flux_tma<ADJUST, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, NST * TmaStage<ADJUST>::kBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux_tma<ADJUST, NST>, kTmaTile, NST * TmaStage<ADJUST>::kBytes);
+    return sms * (perSM < 1 ? 1 : perSM);
+}
+int faceTmaGrid(bool adjust)
+{
+    static int grid[2][2] = {{0, 0}, {0, 0}};
+    int& g = grid[g_faceTma == 3 ? 1 : 0][adjust ? 1 : 0];
+    if (!g) g = g_faceTma == 3 ? (adjust ? tmaGridOf<true, 3>() : tmaGridOf<false, 3>()) : (adjust ? tmaGridOf<true, 2>() : tmaGridOf<false, 2>());
+    return g;
+}
 }
 
+void setFaceTma(int on) { g_faceTma = on == 0 ? 0 : (on == 3 ? 3 : 2); }
 void setFaceVariant(int v) { if (v >= 0 && v < (int)(sizeof(kFaceVariants) / sizeof(kFaceVariants[0]))) g_faceVariant = v; }
 
 int faceKernelGrid()
@@ -1372,7 +1497,17 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
             const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
             if (ev) cudaEventRecord(ev[2], st);
             const FaceVariant& fvn = kFaceVariants[g_faceVariant];
-            fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+            if (g_faceTma && !fv.allGeom && fv.nF % 2 == 0 && fv.nIActive >= kTmaTile) {
+                const int gridT = std::min(faceTmaGrid(adjust), fv.nIActive / kTmaTile);
+                if (g_faceTma == 3) {
+                    if (adjust) k_face_flux_tma<true, 3><<<gridT, kTmaTile, 3 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
+                    else k_face_flux_tma<false, 3><<<gridT, kTmaTile, 3 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
+                } else {
+                    if (adjust) k_face_flux_tma<true, 2><<<gridT, kTmaTile, 2 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
+                    else k_face_flux_tma<false, 2><<<gridT, kTmaTile, 2 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
+                }
+            } else
+                fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
             ++n;
             if (ev) cudaEventRecord(ev[3], st);
         }

@@ -140,7 +140,8 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
                         const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust);
 int faceKernelGrid();
 int pipelineKernelGrid(int cfEllW);
-void setFaceVariant(int v);   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
+void setFaceVariant(int v);
+void setFaceTma(int on);      // env QGD_FACE_TMA: TMA-staged face kernel (default) vs register-prefetch kernel   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
 } // namespace qgd
 

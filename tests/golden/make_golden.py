@@ -10,13 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle as O  # noqa: E402
-from test_oracle_kat import GOLDEN_CASES  # noqa: E402
+from test_oracle_kat import GOLDEN_CASES, golden_fields  # noqa: E402
 
+only = set(sys.argv[1:])
 for name, mk in GOLDEN_CASES.items():
+    if only and name not in only:
+        continue
     c = mk()
     o = c.make_oracle(O)
     steps = 25
     c.oracle_step(o, steps)
-    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"{name}.npz"), steps=steps,
-                        **{f: o.get(f) for f in ("rho", "rhoU", "rhoE", "e", "p")})
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"{name}.npz"), steps=steps, **golden_fields(c, o))
     print(name, "written")

@@ -122,6 +122,20 @@ def test_qgdfoam_100_steps_match_oracle(qgd, oracle_mod, name):
         assert all(0 <= it < c.diff_solver["max_iter"] for it in s.diffusion_iterations())
 
 
+@pytest.mark.parametrize("name", ["hex_perturbed_mixed", "2d_mixed", "sod_1d", "hex_implicit", "prism_model1n", "qhd_cavity2d",
+                                  "qhd_cavity3d_H2bynu"])
+def test_cuda_path_reproduces_committed_golden_fixtures(qgd, name):
+    """tests/golden/*.npz (written by tests/golden/make_golden.py from the oracle) against the CUDA path, no oracle run."""
+    import os
+    from test_oracle_kat import GOLDEN, GOLDEN_CASES, golden_fields
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    c = GOLDEN_CASES[name]()
+    s = c.make_solver(qgd)
+    s.step(int(z["steps"]))
+    for f, v in golden_fields(c, s).items():
+        assert float(np.abs(v - z[f]).max()) / float(np.abs(z[f]).max()) < TOL_STEP, f
+
+
 def test_fluxes_match_oracle_after_one_step(qgd, oracle_mod):
     c = cases.case_hex3d(perturb=0.2, bcs="mixed")
     o = c.make_oracle(oracle_mod)
