@@ -147,6 +147,8 @@ struct qgd_solver {
         DevBuf<int> sendCells, recvCells, sendBf, recvBf;
         DevBuf<double> sendBuf, recvBuf;      // [cells: 16 doubles each][bfaces: 20 doubles each] per neighbour
         DevBuf<double> midSend, midRecv;      // p_b of halo boundary faces (qgdFlux mid-step refresh)
+        DevBuf<int> planSendItem, planSendCell, planSendBf, planRecvItem, planRecvCell, planRecvBf;   // k_halo_all plans
+        DevBuf<long long> planSendBuf, planRecvBuf;
         bool active = false;
     } halo;
     // per-kernel CUDA-event timing (bench): events of the profiled steps, 6 per step
@@ -226,48 +228,45 @@ __global__ void k_unpack_state(int n, const double* __restrict__ S, double* st)
 
 // ---- halo exchange: pack (gather) -> ncclSend/ncclRecv in one group -> unpack (scatter)
 constexpr int kCellDoubles = 16, kBfDoubles = 20;
-__global__ void k_halo_pack(int nC, const int* __restrict__ cells, int nB, const int* __restrict__ bfaces, const double* __restrict__ S,
-                            size_t nCells, const RecA* __restrict__ bA, const RecB* __restrict__ bB, const double* __restrict__ psi,
-                            const double* __restrict__ pGrad, const double* __restrict__ pNew, const double* __restrict__ phiw,
-                            double* __restrict__ buf)
+// all neighbours in one launch: item i of the concatenated (cells | boundary faces) lists belongs to neighbour k with
+// itemOff[k] <= i < itemOff[k+1]; its block starts at bufOff[k] doubles and holds nC_k cells then nB_k boundary faces
+struct HaloPlan { int nn; const int* itemOff; const int* cellOff; const int* bfOff; const long long* bufOff; };
+template <bool PACK>
+__global__ void k_halo_all(HaloPlan hp, const int* __restrict__ cells, const int* __restrict__ bfaces, double* __restrict__ S, size_t nCells,
+                           RecA* __restrict__ bA, RecB* __restrict__ bB, double* __restrict__ psi, double* __restrict__ pGrad,
+                           double* __restrict__ pNew, double* __restrict__ phiw, double* __restrict__ buf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nC) {
-        const int c = cells[i];
+    if (i >= hp.itemOff[hp.nn]) return;
+    int k = 0;
+    while (i >= hp.itemOff[k + 1]) ++k;                    // <= 26 neighbours
+    const int nC = hp.cellOff[k + 1] - hp.cellOff[k], j = i - hp.itemOff[k];
+    double* blk = buf + hp.bufOff[k];
+    if (j < nC) {
+        const int c = cells[hp.cellOff[k] + j];
 #pragma unroll
-        for (int k = 0; k < kCellDoubles; ++k) buf[(size_t)k * nC + i] = S[(size_t)k * nCells + c];
-    } else if (i < nC + nB) {
-        const int j = i - nC;
-        const int b = bfaces[j];
-        double* o = buf + (size_t)kCellDoubles * nC + (size_t)j * kBfDoubles;
-        const double* a = reinterpret_cast<const double*>(bA + b);
-        const double* bb = reinterpret_cast<const double*>(bB + b);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { o[k] = a[k]; o[8 + k] = bb[k]; }
-        o[16] = psi[b]; o[17] = pGrad[b]; o[18] = pNew[b]; o[19] = phiw[b];
-    }
-}
-__global__ void k_halo_unpack(int nC, const int* __restrict__ cells, int nB, const int* __restrict__ bfaces, double* __restrict__ S,
-                              size_t nCells, RecA* __restrict__ bA, RecB* __restrict__ bB, double* __restrict__ psi,
-                              double* __restrict__ pGrad, double* __restrict__ pNew, double* __restrict__ phiw,
-                              const double* __restrict__ buf)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nC) {
-        const int c = cells[i];
-#pragma unroll
-        for (int k = 0; k < kCellDoubles; ++k) S[(size_t)k * nCells + c] = buf[(size_t)k * nC + i];
-    } else if (i < nC + nB) {
-        const int j = i - nC;
-        const int b = bfaces[j];
-        const double* o = buf + (size_t)kCellDoubles * nC + (size_t)j * kBfDoubles;
+        for (int q = 0; q < kCellDoubles; ++q) {
+            if (PACK) blk[(size_t)q * nC + j] = S[(size_t)q * nCells + c];
+            else S[(size_t)q * nCells + c] = blk[(size_t)q * nC + j];
+        }
+    } else {
+        const int jb = j - nC;
+        const int b = bfaces[hp.bfOff[k] + jb];
+        double* o = blk + (size_t)kCellDoubles * nC + (size_t)jb * kBfDoubles;
         double* a = reinterpret_cast<double*>(bA + b);
         double* bb = reinterpret_cast<double*>(bB + b);
+        if (PACK) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { a[k] = o[k]; bb[k] = o[8 + k]; }
-        psi[b] = o[16]; pGrad[b] = o[17]; pNew[b] = o[18]; phiw[b] = o[19];
+            for (int q = 0; q < 8; ++q) { o[q] = a[q]; o[8 + q] = bb[q]; }
+            o[16] = psi[b]; o[17] = pGrad[b]; o[18] = pNew[b]; o[19] = phiw[b];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { a[q] = o[q]; bb[q] = o[8 + q]; }
+            psi[b] = o[16]; pGrad[b] = o[17]; pNew[b] = o[18]; phiw[b] = o[19];
+        }
     }
 }
+
 __global__ void k_gather1(int n, const int* __restrict__ ids, const double* __restrict__ src, double* __restrict__ dst)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,13 +289,14 @@ int haloExchange(qgd_solver* s)
     auto blockOff = [&](const std::vector<int>& cOff, const std::vector<int>& bOff, int k) {
         return (size_t)kCellDoubles * cOff[k] + (size_t)kBfDoubles * bOff[k];
     };
-    for (int k = 0; k < nn; ++k) {
-        const int nC = h.sendCellOff[k + 1] - h.sendCellOff[k], nB = h.sendBfOff[k + 1] - h.sendBfOff[k];
-        if (nC + nB == 0) continue;
-        k_halo_pack<<<(nC + nB + 255) / 256, 256, 0, g_stream>>>(nC, h.sendCells.p + h.sendCellOff[k], nB, h.sendBf.p + h.sendBfOff[k],
-                                                                  s->S.p, nCells, s->bA.p, s->bB.p, s->psiB.p, s->pGrad.p, s->pNew.p,
-                                                                  s->phiw.p, h.sendBuf.p + blockOff(h.sendCellOff, h.sendBfOff, k));
-        ++launches;
+    {
+        HaloPlan hp{nn, h.planSendItem.p, h.planSendCell.p, h.planSendBf.p, h.planSendBuf.p};
+        const int items = h.sendCellOff[nn] + h.sendBfOff[nn];
+        if (items) {
+            k_halo_all<true><<<(items + 255) / 256, 256, 0, g_stream>>>(hp, h.sendCells.p, h.sendBf.p, s->S.p, nCells, s->bA.p, s->bB.p, s->psiB.p,
+                                                                        s->pGrad.p, s->pNew.p, s->phiw.p, h.sendBuf.p);
+            ++launches;
+        }
     }
     QGD_NCCL(g_nccl.GroupStart());
     for (int k = 0; k < nn; ++k) {
@@ -306,13 +306,14 @@ int haloExchange(qgd_solver* s)
         if (nr) QGD_NCCL(g_nccl.Recv(h.recvBuf.p + blockOff(h.recvCellOff, h.recvBfOff, k), nr, ncclDouble, h.nbr[k], g_comm, g_stream));
     }
     QGD_NCCL(g_nccl.GroupEnd());
-    for (int k = 0; k < nn; ++k) {
-        const int nC = h.recvCellOff[k + 1] - h.recvCellOff[k], nB = h.recvBfOff[k + 1] - h.recvBfOff[k];
-        if (nC + nB == 0) continue;
-        k_halo_unpack<<<(nC + nB + 255) / 256, 256, 0, g_stream>>>(nC, h.recvCells.p + h.recvCellOff[k], nB, h.recvBf.p + h.recvBfOff[k],
-                                                                    s->S.p, nCells, s->bA.p, s->bB.p, s->psiB.p, s->pGrad.p, s->pNew.p,
-                                                                    s->phiw.p, h.recvBuf.p + blockOff(h.recvCellOff, h.recvBfOff, k));
-        ++launches;
+    {
+        HaloPlan hp{nn, h.planRecvItem.p, h.planRecvCell.p, h.planRecvBf.p, h.planRecvBuf.p};
+        const int items = h.recvCellOff[nn] + h.recvBfOff[nn];
+        if (items) {
+            k_halo_all<false><<<(items + 255) / 256, 256, 0, g_stream>>>(hp, h.recvCells.p, h.recvBf.p, s->S.p, nCells, s->bA.p, s->bB.p, s->psiB.p,
+                                                                         s->pGrad.p, s->pNew.p, s->phiw.p, h.recvBuf.p);
+            ++launches;
+        }
     }
     return launches;
 }
@@ -1188,6 +1189,15 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* 
         h.sendBuf.alloc((size_t)kCellDoubles * h.sendCellOff[nn] + (size_t)kBfDoubles * h.sendBfOff[nn] + 1);
         h.recvBuf.alloc((size_t)kCellDoubles * h.recvCellOff[nn] + (size_t)kBfDoubles * h.recvBfOff[nn] + 1);
         h.midSend.alloc(h.sendBfOff[nn] + 1); h.midRecv.alloc(h.recvBfOff[nn] + 1);
+        auto plan = [&](const std::vector<int>& cOff, const std::vector<int>& bOff, DevBuf<int>& item, DevBuf<int>& cell, DevBuf<int>& bf,
+                        DevBuf<long long>& bufOff) {
+            std::vector<int> it(nn + 1, 0);
+            std::vector<long long> bo(nn + 1, 0);
+            for (int k = 0; k <= nn; ++k) { it[k] = cOff[k] + bOff[k]; bo[k] = (long long)kCellDoubles * cOff[k] + (long long)kBfDoubles * bOff[k]; }
+            item.upload(it, g_stream); cell.upload(cOff, g_stream); bf.upload(bOff, g_stream); bufOff.upload(bo, g_stream);
+        };
+        plan(h.sendCellOff, h.sendBfOff, h.planSendItem, h.planSendCell, h.planSendBf, h.planSendBuf);
+        plan(h.recvCellOff, h.recvBfOff, h.planRecvItem, h.planRecvCell, h.planRecvBf, h.planRecvBuf);
         h.active = nn > 0;
         // halo copies initialised locally carry wrong mesh-derived values (hQGD of an open halo cell): take the owners'
         if (h.active && s->fieldsSet) { s->launches += haloExchange(s); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
