@@ -73,6 +73,8 @@ struct or_ctx {
     Vec bmvON;                  // nBnd
     Vec gcoef;                  // nFaces*18 : [dir][6]
     Vec gvol;                   // nFaces
+    // leastSquares (extendedFaceStencil*.C): per internal face CSR of neighbour cells, wf2 and Gdf, degenerate flag
+    IVec lsOff, lsCell; Vec lsWf2, lsGdf; std::vector<char> lsDeg; bool lsBuilt = false;
     // GaussVolPointBase2D
     int ie1 = -1, ie2 = -1, ie3 = -1;
     Vec c1, c2, c3, c4, mv42, mv13;    // nFaces (boundary entries for "ordinary" patches)
@@ -413,9 +415,99 @@ static inline double dfdx(const or_ctx& m, int f, int dir, int k, int icmpt, con
 // out: nFaces*3k, tensor index 3*i+j = d_i phi_j.   GaussVolPointStencil.C:71-99, GaussVolPointBase.C:54-121,
 // GaussVolPointBase1D.C:49-63, GaussVolPointBase2D.C:301-367, GaussVolPointBase3D.C:740-993,
 // reducedFaceNormalStencil.C:69-88.  The caller has already applied correctBoundaryConditions().
+// leastSquares scheme: leastSquaresBase::findNeighbours (extendedFaceStencilFindNeighbours.C:41-86, serial part) and
+// calculateWeights (extendedFaceStencilCalculateWeights.C:43-155)
+void buildLeastSquares(or_ctx& m)
+{
+    if (m.lsBuilt) return;
+    // [OF-v2312] primitiveMesh::pointCells(): cells of each point in ascending order
+    std::vector<std::vector<int>> pc(m.nPoints);
+    for (int f = 0; f < m.nFaces; ++f)
+        for (int q = m.faceOff[f]; q < m.faceOff[f + 1]; ++q) {
+            pc[m.faceVerts[q]].push_back(m.owner[f]);
+            if (f < m.nInternal) pc[m.faceVerts[q]].push_back(m.neighbour[f]);
+        }
+    for (auto& v : pc) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    m.lsOff.assign(m.nInternal + 1, 0);
+    m.lsCell.clear(); m.lsWf2.clear(); m.lsGdf.clear();
+    m.lsDeg.assign(std::max(m.nInternal, 1), 0);
+    for (int f = 0; f < m.nInternal; ++f) {
+        std::vector<int> nb;                                                               // :52-82, first-seen order
+        for (int q = m.faceOff[f]; q < m.faceOff[f + 1]; ++q)
+            for (int c : pc[m.faceVerts[q]]) if (std::find(nb.begin(), nb.end(), c) == nb.end()) nb.push_back(c);
+        const V3 Cf = ld3(m.Cf.data(), f);
+        std::vector<V3> df(nb.size());
+        std::vector<double> wf2(nb.size());
+        double G[6] = {0, 0, 0, 0, 0, 0};                                                  // symmTensor xx,xy,xz,yy,yz,zz
+        for (size_t i = 0; i < nb.size(); ++i) {                                           // :70-78
+            df[i] = ld3(m.C.data(), nb[i]) - Cf;
+            wf2[i] = 1.0 / dot(df[i], df[i]);
+            const V3 d = df[i];
+            const double a[6] = {d.x * d.x, d.x * d.y, d.x * d.z, d.y * d.y, d.y * d.z, d.z * d.z};
+            for (int t = 0; t < 6; ++t) G[t] += a[t] * wf2[i];
+        }
+        double G0[6] = {0, 0, 0, 0, 0, 0};
+        if (std::fabs(G[0]) < SMALL) G0[0] = 1;                                            // :85-99
+        if (std::fabs(G[3]) < SMALL) G0[3] = 1;
+        if (std::fabs(G[5]) < SMALL) G0[5] = 1;
+        for (int t = 0; t < 6; ++t) G[t] += G0[t];                                         // :129
+        const double xx = G[0], xy = G[1], xz = G[2], yy = G[3], yz = G[4], zz = G[5];
+        const double detG = xx * yy * zz + xy * yz * xz + xz * xy * yz - xx * yz * yz - xy * xy * zz - xz * yy * xz;   // [OF det(symmTensor)]
+        double Gi[6] = {G[0], G[1], G[2], G[3], G[4], G[5]};
+        if (detG < 1) m.lsDeg[f] = 1;                                                      // :136-140
+        else {                                                                             // :143-144  inv(G) - G0  [OF inv(symmTensor)]
+            Gi[0] = (yy * zz - yz * yz) / detG; Gi[1] = (xz * yz - xy * zz) / detG; Gi[2] = (xy * yz - xz * yy) / detG;
+            Gi[3] = (xx * zz - xz * xz) / detG; Gi[4] = (xy * xz - xx * yz) / detG; Gi[5] = (xx * yy - xy * xy) / detG;
+            for (int t = 0; t < 6; ++t) Gi[t] -= G0[t];
+        }
+        for (size_t i = 0; i < nb.size(); ++i) {                                           // :147-150  G & df
+            const V3 d = df[i];
+            m.lsCell.push_back(nb[i]);
+            m.lsWf2.push_back(wf2[i]);
+            m.lsGdf.push_back(Gi[0] * d.x + Gi[1] * d.y + Gi[2] * d.z);
+            m.lsGdf.push_back(Gi[1] * d.x + Gi[3] * d.y + Gi[4] * d.z);
+            m.lsGdf.push_back(Gi[2] * d.x + Gi[4] * d.y + Gi[5] * d.z);
+        }
+        m.lsOff[f + 1] = (int)m.lsCell.size();
+    }
+    m.lsBuilt = true;
+}
+
+// leastSquares::Grad(volScalarField) applied per component (extendedFaceStencilScalarGrad.C:50-109 ;
+// leastSquaresStencil.C:145-196 for vectors): out[f][k*i + j] = d_i phi_j
+void leastSquaresGrad(const or_ctx& mc, int k, const double* cell, const double* bnd, const double* bsg, double* out)
+{
+    or_ctx& m = const_cast<or_ctx&>(mc);
+    buildLeastSquares(m);
+    const int ok = 3 * k;
+    Vec sF((size_t)m.nFaces * k), sn((size_t)m.nFaces * k);
+    linearInterpolate(m, k, cell, bnd, nullptr, sF.data());                                // :52
+    snGrad(m, k, cell, bsg, sn.data());                                                    // :53
+#pragma omp parallel for num_threads(m.nThreads) schedule(static)
+    for (int f = 0; f < m.nInternal; ++f)
+        for (int j = 0; j < k; ++j) {
+            double g[3] = {0, 0, 0};
+            if (m.lsDeg[f]) for (int i = 0; i < 3; ++i) g[i] = sn[(size_t)f * k + j] * m.nf[3 * (size_t)f + i];        // :78-83
+            else
+                for (int q = m.lsOff[f]; q < m.lsOff[f + 1]; ++q) {                        // :67-70
+                    const double d = cell[(size_t)m.lsCell[q] * k + j] - sF[(size_t)f * k + j];
+                    for (int i = 0; i < 3; ++i) g[i] = g[i] + m.lsWf2[q] * m.lsGdf[3 * (size_t)q + i] * d;
+                }
+            for (int i = 0; i < 3; ++i) out[(size_t)f * ok + k * i + j] = g[i];
+        }
+    for (int b = 0; b < m.nBnd; ++b) {                                                     // :86-109
+        const int f = m.nInternal + b;
+        const int kind = m.patchKind[m.bfacePatch[b]];
+        const bool constrained = kind == OR_PATCH_EMPTY || kind == OR_PATCH_WEDGE || kind == OR_PATCH_PROCESSOR;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < k; ++j) out[(size_t)f * ok + k * i + j] = constrained ? 0.0 : m.nf[3 * (size_t)f + i] * bsg[(size_t)b * k + j];
+    }
+}
+
 void fvscGrad(const or_ctx& m, int scheme, int k, const double* cell, const double* bnd, const double* bsg,
               const double* nbr, double* out)
 {
+    if (scheme == OR_FVSC_LEASTSQUARES) { leastSquaresGrad(m, k, cell, bnd, bsg, out); return; }
     const int ok = 3 * k;
     std::fill(out, out + (size_t)m.nFaces * ok, 0.0);          // vector::zero * fvc::snGrad(vF)
     Vec sn((size_t)m.nFaces * k);
@@ -482,6 +574,19 @@ void fvscGrad(const or_ctx& m, int scheme, int k, const double* cell, const doub
 void fvscDiv(const or_ctx& m, int scheme, int k, const double* cell, const double* bnd, const double* bsg,
              const double* nbr, double* out)
 {
+    if (scheme == OR_FVSC_LEASTSQUARES) {
+        // leastSquaresStencil.C:204-275: Div(vector) = sum_i d_i U_i ; Div(tensor)_j = sum_i d_i T_ij, from the component gradients
+        const int okd = k / 3;
+        Vec g((size_t)m.nFaces * 3 * k);
+        leastSquaresGrad(m, k, cell, bnd, bsg, g.data());
+        for (int f = 0; f < m.nFaces; ++f)
+            for (int jj = 0; jj < okd; ++jj) {
+                double sacc = 0.0;
+                for (int i = 0; i < 3; ++i) sacc += g[(size_t)f * 3 * k + k * i + (okd * i + jj)];
+                out[(size_t)f * okd + jj] = sacc;
+            }
+        return;
+    }
     const int ok = k / 3;
     std::fill(out, out + (size_t)m.nFaces * ok, 0.0);
     Vec sn((size_t)m.nFaces * k);

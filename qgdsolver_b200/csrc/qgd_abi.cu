@@ -348,7 +348,7 @@ void configurePipeline(qgd_solver* s, int mode, int chunkCells, int lag, int rin
     const int nI = h.nInternal, nIA = m.nIActive, nOwn = h.nOwned;
     qgd_solver::Pipe& P = s->pipe;
     if (mode == 1 && s->desc.adjust_time_step) mode = 0;        // the global Courant max is needed before any cell update
-    if (mode == 1 && nIA == 0) mode = 0;
+    if (mode == 1 && (nIA == 0 || s->fvsc->lsq)) mode = 0;
     auto fullArrays = [&] {
         P.mode = 0;
         s->strideI = s->strideB = (size_t)h.nFaces; s->bndOff = (size_t)nI;
@@ -561,10 +561,14 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown Model type " + name + "\n\nValid model types are:\n" + toc(kFvscTable));
     if ((name == "leastSquares" || name == "leastSquaresOpt")) {
         if (mesh->h.nD == 3) throw Error(QGD_ERR_INVALID, "Can't use leastSquares or leastSquaresOpt in 3D case.");
-        throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " is not available on the device yet (no CPU fallback)");
+        if (name == "leastSquaresOpt")
+            throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " is not available on the device yet (no CPU fallback)");
+        if (mesh->h.nOwned != mesh->h.nCells)
+            throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme leastSquares on extended sub-meshes (multi-GPU) is not available yet");
     }
     op.mesh = mesh;
-    op.reduced = (name == "reduced");
+    op.lsq = (name == "leastSquares");
+    op.reduced = (name == "reduced") || op.lsq;      // boundary faces nf*snGrad, no point values (extendedFaceStencilScalarGrad.C:86-109)
     std::vector<int> vtx, flags;
     std::vector<double> G, hd;
     mesh->h.buildFaceRecords(op.reduced, vtx, flags, G, hd);
@@ -585,7 +589,29 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
             fl[f] |= FF_GEOM;
         for (int k = 0; k < 9; ++k) Gp[(size_t)k * nF + f] = G[(size_t)k * nF + o];
     }
-    op.allGeom = geomFaces && mesh->nIActive > 0;
+    if (op.lsq) {
+        // internal faces: least-squares cell stencil; the G record keeps the nf*snGrad fallback of degenerate faces
+        int W = 0;
+        std::vector<int> cells;
+        std::vector<double> coef;
+        std::vector<char> deg;
+        mesh->h.buildLeastSquares(W, cells, coef, deg);
+        const int nI = mesh->h.nInternal;
+        const size_t nIs = (size_t)std::max(nI, 1);
+        std::vector<int> cd((size_t)W * nIs, 0);
+        std::vector<double> kd((size_t)W * 3 * nIs, 0.0);
+        for (int f = 0; f < nI; ++f) {
+            const size_t o = perm[f];
+            if (!deg[o]) fl[f] |= FF_LSQ;
+            for (int j = 0; j < W; ++j) {
+                cd[(size_t)j * nIs + f] = cells[(size_t)j * nIs + o];
+                for (int q = 0; q < 3; ++q) kd[((size_t)j * 3 + q) * nIs + f] = coef[((size_t)j * 3 + q) * nIs + o];
+            }
+        }
+        op.lsqW = W;
+        op.lsqCells.upload(cd, g_stream); op.lsqCoef.upload(kd, g_stream);
+    }
+    op.allGeom = geomFaces && mesh->nIActive > 0 && !op.lsq;
     for (int f = 0; f < mesh->nIActive && op.allGeom; ++f) if (!(fl[f] & FF_GEOM)) op.allGeom = false;
     op.vtx.upload(v4, g_stream); op.flags.upload(fl, g_stream); op.G.upload(Gp, g_stream); op.halfDist.upload(hd, g_stream);
 }

@@ -271,4 +271,63 @@ void HostMesh::buildFaceRecords(bool reduced, std::vector<int>& vtx, std::vector
     }
 }
 
+void HostMesh::buildLeastSquares(int& W, std::vector<int>& cells, std::vector<double>& coef, std::vector<char>& deg) const
+{
+    const double SMALLv = 1e-15;
+    // [OF-v2312] primitiveMesh::pointCells(): ascending cell order per point
+    std::vector<std::vector<int>> pc(nPoints);
+    for (int f = 0; f < nFaces; ++f)
+        for (int q = faceOff[f]; q < faceOff[f + 1]; ++q) {
+            pc[faceVerts[q]].push_back(owner[f]);
+            if (f < nInternal) pc[faceVerts[q]].push_back(neighbour[f]);
+        }
+    for (auto& v : pc) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    std::vector<std::vector<int>> nbs(nInternal);
+    W = 1;
+    for (int f = 0; f < nInternal; ++f) {
+        std::vector<int>& nb = nbs[f];
+        for (int q = faceOff[f]; q < faceOff[f + 1]; ++q)
+            for (int c : pc[faceVerts[q]]) if (std::find(nb.begin(), nb.end(), c) == nb.end()) nb.push_back(c);
+        W = std::max(W, (int)nb.size());
+    }
+    const size_t nI = (size_t)std::max(nInternal, 1);
+    cells.assign((size_t)W * nI, 0);
+    coef.assign((size_t)W * 3 * nI, 0.0);
+    deg.assign(nI, 0);
+    for (int f = 0; f < nInternal; ++f) {
+        const std::vector<int>& nb = nbs[f];
+        const Vec3 cf = at(Cf, f);
+        std::vector<Vec3> df(nb.size());
+        std::vector<double> wf2(nb.size());
+        double G[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t i = 0; i < nb.size(); ++i) {
+            df[i] = sub(at(C, nb[i]), cf);
+            wf2[i] = 1.0 / dot3(df[i], df[i]);
+            const Vec3 d = df[i];
+            const double a[6] = {d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[1], d[1] * d[2], d[2] * d[2]};
+            for (int t = 0; t < 6; ++t) G[t] += a[t] * wf2[i];
+        }
+        double G0[6] = {0, 0, 0, 0, 0, 0};
+        if (std::fabs(G[0]) < SMALLv) G0[0] = 1;
+        if (std::fabs(G[3]) < SMALLv) G0[3] = 1;
+        if (std::fabs(G[5]) < SMALLv) G0[5] = 1;
+        for (int t = 0; t < 6; ++t) G[t] += G0[t];
+        const double xx = G[0], xy = G[1], xz = G[2], yy = G[3], yz = G[4], zz = G[5];
+        const double detG = xx * yy * zz + xy * yz * xz + xz * xy * yz - xx * yz * yz - xy * xy * zz - xz * yy * xz;
+        for (size_t j = 0; j < (size_t)W; ++j) cells[j * nI + f] = owner[f];
+        if (detG < 1) { deg[f] = 1; continue; }
+        double Gi[6];
+        Gi[0] = (yy * zz - yz * yz) / detG; Gi[1] = (xz * yz - xy * zz) / detG; Gi[2] = (xy * yz - xz * yy) / detG;
+        Gi[3] = (xx * zz - xz * xz) / detG; Gi[4] = (xy * xz - xx * yz) / detG; Gi[5] = (xx * yy - xy * xy) / detG;
+        for (int t = 0; t < 6; ++t) Gi[t] -= G0[t];
+        for (size_t i = 0; i < nb.size(); ++i) {
+            const Vec3 d = df[i];
+            const double gd[3] = {Gi[0] * d[0] + Gi[1] * d[1] + Gi[2] * d[2], Gi[1] * d[0] + Gi[3] * d[1] + Gi[4] * d[2],
+                                  Gi[2] * d[0] + Gi[4] * d[1] + Gi[5] * d[2]};
+            cells[i * nI + f] = nb[i];
+            for (int q = 0; q < 3; ++q) coef[(i * 3 + q) * nI + f] = wf2[i] * gd[q];
+        }
+    }
+}
+
 } // namespace qgd

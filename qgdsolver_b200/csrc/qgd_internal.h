@@ -76,6 +76,7 @@ enum FaceFlags : int {
     FF_POINTS = 1,     // uses vertex values (G1/G2 non-zero)
     FF_TRI_QUIRK = 2,  // internal triangular face: vector-gradient index pattern of GaussVolPointBase3D.C:844-854
     FF_NORMAL_ONLY = 4, // boundary face evaluated as nf*snGrad (1D, reduced, other faces)
+    FF_LSQ = 16,       // internal face evaluated with the leastSquares cell stencil (FaceView::lsq*)
     FF_GEOM = 8        // internal 3D quad face: the step kernel rebuilds G from point coordinates and cell centres
                        // (18 cached gathers) instead of streaming the 72-byte record
 };
@@ -100,6 +101,11 @@ struct HostMesh {
     std::vector<double> hQGDf, hQGD;
     void build(const qgd_mesh_desc& d);
     // face gradient records for a scheme ("GaussVolPoint" / "reduced")
+    // leastSquares scheme (extendedFaceStencilFindNeighbours.C:41-86, extendedFaceStencilCalculateWeights.C:43-155):
+    // per internal face (polyMesh order) an ELL row of W neighbour cells and coefficient vectors wf2*Gdf; deg[f] = 1 where
+    // the reference falls back to nf*snGrad (det G < 1)
+    void buildLeastSquares(int& W, std::vector<int>& cells /*W*nInternal*/, std::vector<double>& coef /*W*3*nInternal*/,
+                           std::vector<char>& deg /*nInternal*/) const;
     void buildFaceRecords(bool reduced, std::vector<int>& vtx /*nFaces*4*/, std::vector<int>& flags /*nFaces*/,
                           std::vector<double>& G /*9 arrays of nFaces, SoA: G[k*nFaces+f]*/,
                           std::vector<double>& halfDist /*nBnd*/) const;

@@ -153,6 +153,31 @@ __device__ __forceinline__ void faceDiffs(const FaceView& fv, int f, const doubl
     }
 }
 
+// leastSquares gradient of K components on internal face f: g[K*i + j] = sum_s c_s[i] (phi_s[j] - phi_f[j]),
+// phi_f = linearInterpolate(phi)
+template <int K>
+__device__ __forceinline__ void lsqGradGeneric(const FaceView& fv, int f, const double* __restrict__ cell, double (&g)[3 * K])
+{
+    const int P = fv.own[f], N = fv.nei[f];
+    const double w = fv.w[f];
+    const size_t nI = fv.nI;
+    double sF[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { const double a = cell[(size_t)P * K + j], b = cell[(size_t)N * K + j]; sF[j] = w * (a - b) + b; }
+#pragma unroll
+    for (int q = 0; q < 3 * K; ++q) g[q] = 0.0;
+    for (int s = 0; s < fv.lsqW; ++s) {
+        const int c = fv.lsqCells[(size_t)s * nI + f];
+        const double cx = fv.lsqCoef[((size_t)s * 3 + 0) * nI + f], cy = fv.lsqCoef[((size_t)s * 3 + 1) * nI + f],
+                     cz = fv.lsqCoef[((size_t)s * 3 + 2) * nI + f];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const double d = cell[(size_t)c * K + j] - sF[j];
+            g[j] += cx * d; g[K + j] += cy * d; g[2 * K + j] += cz * d;
+        }
+    }
+}
+
 // grad: out[f][3*i... ] tensor index K*i + j = d_i phi_j
 template <int K>
 __global__ void k_fvsc_grad(FaceView fv, const double* __restrict__ cell, const double* __restrict__ pts,
@@ -184,6 +209,13 @@ __global__ void k_fvsc_grad(FaceView fv, const double* __restrict__ cell, const 
                 for (int j = 0; j < K; ++j) o[K * i + j] = gp[i] * bsg[(size_t)b * K + j];
             return;
         }
+    }
+    if (flags & FF_LSQ) {                       // leastSquares::Grad  extendedFaceStencilScalarGrad.C:52-72
+        double gl[3 * K];
+        lsqGradGeneric<K>(fv, f, cell, gl);
+#pragma unroll
+        for (int q = 0; q < 3 * K; ++q) o[q] = gl[q];
+        return;
     }
     double d1[K], d2[K], dP[K];
     faceDiffs<K>(fv, f, cell, pts, bnd, bsg, nbr, flags, d1, d2, dP);
@@ -235,6 +267,18 @@ __global__ void k_fvsc_div(FaceView fv, const double* __restrict__ cell, const d
             }
             return;
         }
+    }
+    if (flags & FF_LSQ) {                       // leastSquares::Div  leastSquaresStencil.C:204-275
+        double gl[3 * K];
+        lsqGradGeneric<K>(fv, f, cell, gl);
+#pragma unroll
+        for (int j = 0; j < OK; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) s += gl[K * i + OK * i + j];
+            o[j] = s;
+        }
+        return;
     }
     double d1[K], d2[K], dP[K];
     faceDiffs<K>(fv, f, cell, pts, bnd, bsg, nbr, flags, d1, d2, dP);
@@ -543,7 +587,36 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
 // ---- one internal face: 11 interpolations + 4 GaussVolPoint gradients + QGD flux algebra -> 5 flux doubles at `slot`
 // SMEM: the streamed per-face constants (G, Sf, w, hQGDf, |Sf|) were staged by TMA into shared memory: sd[k*kTmaTile + li]
 constexpr int kTmaTile = 256;
-template <bool ADJUST, bool GEOM, bool SMEM = false>
+// leastSquares gradients of (rho, U, e, p) on an internal face of the step kernel
+__device__ __forceinline__ void lsqGrads(const FaceView& fv, const SolverView& sv, int f, const RecA& aP, const RecA& aN, double w, FaceGrads& g)
+{
+    const size_t nI = fv.nI, n = sv.nCells;
+    const double sF[6] = {w * (aP.rho - aN.rho) + aN.rho, w * (aP.Ux - aN.Ux) + aN.Ux, w * (aP.Uy - aN.Uy) + aN.Uy,
+                          w * (aP.Uz - aN.Uz) + aN.Uz, w * (aP.e - aN.e) + aN.e, w * (aP.p - aN.p) + aN.p};
+    double acc[3][6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[i][q] = 0.0;
+    for (int s = 0; s < fv.lsqW; ++s) {
+        const int c = __ldg(&fv.lsqCells[(size_t)s * nI + f]);
+        const double cf[3] = {__ldg(&fv.lsqCoef[((size_t)s * 3 + 0) * nI + f]), __ldg(&fv.lsqCoef[((size_t)s * 3 + 1) * nI + f]),
+                              __ldg(&fv.lsqCoef[((size_t)s * 3 + 2) * nI + f])};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            const double d = __ldg(sv.S + q * n + c) - sF[q];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) acc[i][q] += cf[i] * d;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        g.rho[i] = acc[i][0]; g.U[3 * i] = acc[i][1]; g.U[3 * i + 1] = acc[i][2]; g.U[3 * i + 2] = acc[i][3];
+        g.e[i] = acc[i][4]; g.p[i] = acc[i][5];
+    }
+}
+
+template <bool ADJUST, bool GEOM, bool SMEM = false, bool LSQ = false>
 __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv, const SolverView& sv, int f, size_t slot, int P, int N,
                                             int flagsCur, const int4& v, double& coMax, double& tauMin, const double* sd = nullptr, int li = 0)
 {
@@ -586,9 +659,10 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
         }
     }
     FaceGrads g;
-    gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
     // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
     const double w = SMEM ? sd[12 * kTmaTile + li] : __ldg(&fv.w[f]);
+    if (LSQ && (flagsCur & FF_LSQ)) lsqGrads(fv, sv, f, aP, aN, w, g);
+    else gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
     FaceState s;
     s.rho = w * (aP.rho - aN.rho) + aN.rho;
     s.U[0] = w * (aP.Ux - aN.Ux) + aN.Ux; s.U[1] = w * (aP.Uy - aN.Uy) + aN.Uy; s.U[2] = w * (aP.Uz - aN.Uz) + aN.Uz;
@@ -696,6 +770,17 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     storeRec(sv, 0, cell, a);
     storeRec(sv, 8, cell, b);
     if (sv.tauOut) sv.tauOut[cell] = (k.model == 2) ? tau + k.mu / (pOld * k.ScQGD) : tau;     // constScPrModel2.C:112
+}
+
+// ---- leastSquares variant (2D / 1D meshes only, fvsc.C:60-63): cell-stencil gradients instead of the G record
+template <bool ADJUST>
+__global__ void __launch_bounds__(256, 2) k_face_flux_lsq(Consts k, FaceView fv, SolverView sv)
+{
+    double coMax = 0.0, tauMin = DBL_MAX;
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < fv.nIActive; f += gridDim.x * blockDim.x)
+        faceFluxOne<ADJUST, false, false, true>(k, fv, sv, f, (size_t)f, __ldg(&fv.own[f]), __ldg(&fv.nei[f]), __ldg(&fv.flags[f]),
+                                                __ldg(&fv.vtx[f]), coMax, tauMin);
+    if (ADJUST) blockReduceCo<256>(coMax, tauMin, sv.sc);
 }
 
 // ---- TMA-staged variant of the face kernel.  The 140 B of streamed per-face constants (own, nei, flags, vtx, G[9],
@@ -1443,6 +1528,28 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
     QGD_CUDA(cudaGetLastError());
 }
 
+// internal-face kernel of the two-kernel step form: leastSquares | TMA-staged | register-prefetch (+ GEOM) variants
+static void launchFaceKernel(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, bool adjust, int gridFaces)
+{
+    const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
+    const FaceVariant& fvn = kFaceVariants[g_faceVariant];
+    if (fv.lsqW > 0) {
+        const int gl = std::min(2 * 148, nblk(fv.nIActive, 256));
+        if (adjust) k_face_flux_lsq<true><<<gl, 256, 0, st>>>(c, fv, sv);
+        else k_face_flux_lsq<false><<<gl, 256, 0, st>>>(c, fv, sv);
+    } else if (g_faceTma && !fv.allGeom && fv.nF % 2 == 0 && fv.nIActive >= kTmaTile) {
+        const int gridT = std::min(faceTmaGrid(adjust), fv.nIActive / kTmaTile);
+        if (g_faceTma == 3) {
+            if (adjust) k_face_flux_tma<true, 3><<<gridT, kTmaTile, 3 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
+            else k_face_flux_tma<false, 3><<<gridT, kTmaTile, 3 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
+        } else {
+            if (adjust) k_face_flux_tma<true, 2><<<gridT, kTmaTile, 2 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
+            else k_face_flux_tma<false, 2><<<gridT, kTmaTile, 2 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
+        }
+    } else
+        fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+}
+
 namespace {
 template <int W> void launchPipe(cudaStream_t st, int grid, const Consts& c, const FaceView& fv, const SolverView& sv, const PipeView& pv)
 {
@@ -1494,20 +1601,8 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         if (ev) { cudaEventRecord(ev[3], st); cudaEventRecord(ev[4], st); cudaEventRecord(ev[5], st); }
     } else {
         if (fv.nIActive) {
-            const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
             if (ev) cudaEventRecord(ev[2], st);
-            const FaceVariant& fvn = kFaceVariants[g_faceVariant];
-            if (g_faceTma && !fv.allGeom && fv.nF % 2 == 0 && fv.nIActive >= kTmaTile) {
-                const int gridT = std::min(faceTmaGrid(adjust), fv.nIActive / kTmaTile);
-                if (g_faceTma == 3) {
-                    if (adjust) k_face_flux_tma<true, 3><<<gridT, kTmaTile, 3 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
-                    else k_face_flux_tma<false, 3><<<gridT, kTmaTile, 3 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
-                } else {
-                    if (adjust) k_face_flux_tma<true, 2><<<gridT, kTmaTile, 2 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
-                    else k_face_flux_tma<false, 2><<<gridT, kTmaTile, 2 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
-                }
-            } else
-                fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+            launchFaceKernel(st, c, fv, sv, adjust, gridFaces);
             ++n;
             if (ev) cudaEventRecord(ev[3], st);
         }
@@ -1544,9 +1639,7 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
         k_gauss_gradU<<<nblk(sv.nCells), kBlock, 0, st>>>(fv, sv, bs, iv.GU0, 0); ++n;
         if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
         if (fv.nIActive) {
-            const FaceVariant& fvn = kFaceVariants[g_faceVariant];
-            const int grid = std::min(gridFaces, nblk(fv.nIActive, fvn.block));
-            fvn.fn[adjust ? 1 : 0]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+            launchFaceKernel(st, c, fv, sv, adjust, gridFaces);
             ++n;
         }
         k_face_diff<<<nblk(fv.nF), kBlock, 0, st>>>(fv, sv, bs, iv); ++n;

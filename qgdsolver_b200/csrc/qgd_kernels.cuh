@@ -38,6 +38,8 @@ struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     const double* X;         // SoA 3*nPoints point coordinates (FF_GEOM faces)
     const double* Cc;        // SoA 3*nCells  cell centres      (FF_GEOM faces)
     int nPts, nCls;
+    int lsqW;                // leastSquares: ELL width, cells [lsqW][nI] and coefficient vectors [lsqW][3][nI] (device face order)
+    const int* lsqCells; const double* lsqCoef;
     int allGeom;             // every active internal face carries FF_GEOM: the step uses the geometry-rebuilding face kernel
     const double* halfDist;  // nB
     const int* bKind;        // nB patch kind per boundary face
@@ -153,6 +155,10 @@ struct qgd_fvsc {
     qgd::DevBuf<int> flags;
     qgd::DevBuf<double> G, halfDist;
     bool allGeom = false;
+    bool lsq = false;              // leastSquares scheme
+    int lsqW = 0;
+    qgd::DevBuf<int> lsqCells;
+    qgd::DevBuf<double> lsqCoef;
     // staging for operator-level calls (grown on demand)
     qgd::DevBuf<double> dCell, dBnd, dBsg, dNbr, dPts, dOut;
     qgd::FaceView view() const
@@ -164,7 +170,7 @@ struct qgd_fvsc {
         v.zeroDivCmpt = -1;
         if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
         v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
-        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.X = m.ptsSoA.p; v.Cc = m.ctrSoA.p; v.nPts = m.h.nPoints; v.nCls = m.h.nCells; v.allGeom = allGeom ? 1 : 0; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
+        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.X = m.ptsSoA.p; v.Cc = m.ctrSoA.p; v.nPts = m.h.nPoints; v.nCls = m.h.nCells; v.allGeom = allGeom ? 1 : 0; v.lsqW = lsq ? lsqW : 0; v.lsqCells = lsqCells.p; v.lsqCoef = lsqCoef.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
         v.perm = m.facePermDev.p;
         return v;
     }

@@ -666,6 +666,7 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
         s->desc.fvsc_scheme = nullptr; s->desc.qgd_coeffs_model = nullptr; s->desc.p_preconditioner = nullptr;
         s->fvsc.reset(new qgd_fvsc());
         fvscBuild(*s->fvsc, mesh, d->fvsc_scheme);
+        if (s->fvsc->lsq) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam with fvsc scheme leastSquares is not available on the device yet");
         QhdConsts& k = s->k;
         k.rho0 = d->rho0; k.nu = d->mu / d->rho0; k.Hi = (d->mu / d->Pr) / d->rho0; k.beta = d->beta;
         for (int j = 0; j < 3; ++j) k.g[j] = d->g[j];

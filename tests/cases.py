@@ -35,7 +35,7 @@ class Case:
                           diffMaxIter=self.diff_solver["max_iter"], diffPrecond=O.PRECONDS[self.diff_solver["precond"]],
                           alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
                           energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model])
-        scheme = O.FVSC_GAUSSVOLPOINT if self.scheme == "GaussVolPoint" else O.FVSC_REDUCED
+        scheme = O.FVSC_SCHEMES[self.scheme]
         o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
                    alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme)
         return o
@@ -170,7 +170,7 @@ class QHDCase:
                           pPrecond=O.PRECONDS[sv["precond"]], pRefCell=self.p_ref_cell, pRefValue=self.p_ref_value)
         for j in range(3):
             prm.g[j] = f["g"][j]
-        scheme = O.FVSC_GAUSSVOLPOINT if self.scheme == "GaussVolPoint" else O.FVSC_REDUCED
+        scheme = O.FVSC_SCHEMES[self.scheme]
         o.qhd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
                    alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme)
         return o

@@ -43,11 +43,13 @@ def _fields(mesh, k, seed):
 
 
 @pytest.mark.parametrize("mesh_name", list(MESHES))
-@pytest.mark.parametrize("scheme", ["GaussVolPoint", "reduced"])
+@pytest.mark.parametrize("scheme", ["GaussVolPoint", "reduced", "leastSquares"])
 def test_fvsc_operators_match_oracle(qgd, oracle_mod, mesh_name, scheme):
     mesh = MESHES[mesh_name]()
+    if scheme == "leastSquares" and mesh.n_geometric_d == 3:
+        pytest.skip("leastSquares is rejected in 3D (fvsc.C:60-63)")
     o = oracle_mod.Oracle(mesh)
-    osch = oracle_mod.FVSC_GAUSSVOLPOINT if scheme == "GaussVolPoint" else oracle_mod.FVSC_REDUCED
+    osch = oracle_mod.FVSC_SCHEMES[scheme]
     dm = qgd.Mesh(mesh)
     st = qgd.FvscStencil(dm, scheme)
     for k in (1, 3):
@@ -94,6 +96,10 @@ STEP_CASES = {
     "2d_implicit_qgdflux": lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", implicit=True),
     "prism_implicit_adjust": lambda: cases.case_prism(bcs="fixed", implicit=True, adjust_time_step=True, max_co=0.1),
     "sod_implicit": lambda: cases.case_sod(200, implicit=True),
+    # fvsc leastSquares (2D / 1D only): extendedFaceStencil*.C
+    "2d_leastSquares": lambda: cases.case_2d(perturb=0.2, bcs="mixed", scheme="leastSquares"),
+    "2d_y_leastSquares_implicit": lambda: cases.case_2d(perturb=0.1, bcs="fixed", axis=1, scheme="leastSquares", implicit=True),
+    "sod_leastSquares": lambda: cases.case_sod(200, scheme="leastSquares"),
 }
 
 
