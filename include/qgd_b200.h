@@ -95,9 +95,8 @@ int qgd_mesh_get(qgd_mesh* mesh, int what, double* out);
 
 /* ---- fvsc face-centre derivative operators (operator-level integration) ----
  * qgd_fvsc_create  replaces fvscStencil::New / lookupOrNew (fvscStencil.C:59-118); scheme_name is the
- *   fvSchemes::fvsc entry (fvsc.C:47-58): "GaussVolPoint" | "reduced" | "leastSquares" (2D/1D meshes);
- *   "leastSquares"/"leastSquaresOpt" are rejected in 3D exactly like fvsc.C:60-63, "leastSquaresOpt" is otherwise
- *   reported as QGD_ERR_UNSUPPORTED;
+ *   fvSchemes::fvsc entry (fvsc.C:47-58): "GaussVolPoint" | "reduced" | "leastSquares" | "leastSquaresOpt" (the last
+ *   two on 2D/1D meshes: they are rejected in 3D exactly like fvsc.C:60-63);
  *   anything else -> QGD_ERR_UNKNOWN_MODEL with the reference's "Unknown Model type" message.
  * qgd_fvsc_grad    replaces fvscStencil::Grad(volScalarField|volVectorField)  (fvscStencil.H:105-116,
  *   GaussVolPointStencil.C:71-99, reducedFaceNormalStencil.C:69-88).  ncmpt = 1 | 3.

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libqgd_oracle.so")
 
 FVSC_GAUSSVOLPOINT, FVSC_REDUCED, FVSC_LEASTSQUARES = 0, 1, 2
-FVSC_SCHEMES = {"GaussVolPoint": 0, "reduced": 1, "leastSquares": 2}
+FVSC_SCHEMES = {"GaussVolPoint": 0, "reduced": 1, "leastSquares": 2, "leastSquaresOpt": 3}
 BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED = 0, 1, 2, 3, 4
 
 _dp = C.POINTER(C.c_double)

@@ -475,7 +475,9 @@ void buildLeastSquares(or_ctx& m)
 
 // leastSquares::Grad(volScalarField) applied per component (extendedFaceStencilScalarGrad.C:50-109 ;
 // leastSquaresStencil.C:145-196 for vectors): out[f][k*i + j] = d_i phi_j
-void leastSquaresGrad(const or_ctx& mc, int k, const double* cell, const double* bnd, const double* bsg, double* out)
+// opt: leastSquaresOpt (leastSquaresStencilOpt.C:75-181, extendedFaceStencilScalarDer.C:40-52): the same sums, but the
+// degenerate faces are not replaced by nf*snGrad - their Gdf is the un-inverted (G+G0)&df
+void leastSquaresGrad(const or_ctx& mc, int k, const double* cell, const double* bnd, const double* bsg, double* out, bool opt = false)
 {
     or_ctx& m = const_cast<or_ctx&>(mc);
     buildLeastSquares(m);
@@ -487,7 +489,7 @@ void leastSquaresGrad(const or_ctx& mc, int k, const double* cell, const double*
     for (int f = 0; f < m.nInternal; ++f)
         for (int j = 0; j < k; ++j) {
             double g[3] = {0, 0, 0};
-            if (m.lsDeg[f]) for (int i = 0; i < 3; ++i) g[i] = sn[(size_t)f * k + j] * m.nf[3 * (size_t)f + i];        // :78-83
+            if (m.lsDeg[f] && !opt) for (int i = 0; i < 3; ++i) g[i] = sn[(size_t)f * k + j] * m.nf[3 * (size_t)f + i];        // :78-83
             else
                 for (int q = m.lsOff[f]; q < m.lsOff[f + 1]; ++q) {                        // :67-70
                     const double d = cell[(size_t)m.lsCell[q] * k + j] - sF[(size_t)f * k + j];
@@ -507,7 +509,10 @@ void leastSquaresGrad(const or_ctx& mc, int k, const double* cell, const double*
 void fvscGrad(const or_ctx& m, int scheme, int k, const double* cell, const double* bnd, const double* bsg,
               const double* nbr, double* out)
 {
-    if (scheme == OR_FVSC_LEASTSQUARES) { leastSquaresGrad(m, k, cell, bnd, bsg, out); return; }
+    if (scheme == OR_FVSC_LEASTSQUARES || scheme == OR_FVSC_LEASTSQUARESOPT) {
+        leastSquaresGrad(m, k, cell, bnd, bsg, out, scheme == OR_FVSC_LEASTSQUARESOPT);
+        return;
+    }
     const int ok = 3 * k;
     std::fill(out, out + (size_t)m.nFaces * ok, 0.0);          // vector::zero * fvc::snGrad(vF)
     Vec sn((size_t)m.nFaces * k);
@@ -574,11 +579,11 @@ void fvscGrad(const or_ctx& m, int scheme, int k, const double* cell, const doub
 void fvscDiv(const or_ctx& m, int scheme, int k, const double* cell, const double* bnd, const double* bsg,
              const double* nbr, double* out)
 {
-    if (scheme == OR_FVSC_LEASTSQUARES) {
-        // leastSquaresStencil.C:204-275: Div(vector) = sum_i d_i U_i ; Div(tensor)_j = sum_i d_i T_ij, from the component gradients
+    if (scheme == OR_FVSC_LEASTSQUARES || scheme == OR_FVSC_LEASTSQUARESOPT) {
+        // leastSquaresStencil.C:204-275, leastSquaresStencilOpt.C:189-260: Div(vector) = sum_i d_i U_i ; Div(tensor)_j = sum_i d_i T_ij, from the component gradients
         const int okd = k / 3;
         Vec g((size_t)m.nFaces * 3 * k);
-        leastSquaresGrad(m, k, cell, bnd, bsg, g.data());
+        leastSquaresGrad(m, k, cell, bnd, bsg, g.data(), scheme == OR_FVSC_LEASTSQUARESOPT);
         for (int f = 0; f < m.nFaces; ++f)
             for (int jj = 0; jj < okd; ++jj) {
                 double sacc = 0.0;

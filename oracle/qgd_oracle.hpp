@@ -26,7 +26,7 @@ enum { OR_PATCH_GENERIC = 0, OR_PATCH_EMPTY = 1, OR_PATCH_PROCESSOR = 2, OR_PATC
 enum { OR_BC_FIXED_VALUE = 0, OR_BC_ZERO_GRADIENT = 1, OR_BC_FIXED_GRADIENT = 2, OR_BC_QGD_FLUX = 3,
        OR_BC_CALCULATED = 4, OR_BC_SLIP = 5 };
 // fvsc schemes
-enum { OR_FVSC_GAUSSVOLPOINT = 0, OR_FVSC_REDUCED = 1, OR_FVSC_LEASTSQUARES = 2 };
+enum { OR_FVSC_GAUSSVOLPOINT = 0, OR_FVSC_REDUCED = 1, OR_FVSC_LEASTSQUARES = 2, OR_FVSC_LEASTSQUARESOPT = 3 };
 
 typedef struct {
     int nCells, nFaces, nInternal, nPoints, nPatches;

@@ -561,13 +561,11 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown Model type " + name + "\n\nValid model types are:\n" + toc(kFvscTable));
     if ((name == "leastSquares" || name == "leastSquaresOpt")) {
         if (mesh->h.nD == 3) throw Error(QGD_ERR_INVALID, "Can't use leastSquares or leastSquaresOpt in 3D case.");
-        if (name == "leastSquaresOpt")
-            throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " is not available on the device yet (no CPU fallback)");
         if (mesh->h.nOwned != mesh->h.nCells)
-            throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme leastSquares on extended sub-meshes (multi-GPU) is not available yet");
+            throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " on extended sub-meshes (multi-GPU) is not available yet");
     }
     op.mesh = mesh;
-    op.lsq = (name == "leastSquares");
+    op.lsq = (name == "leastSquares" || name == "leastSquaresOpt");
     op.reduced = (name == "reduced") || op.lsq;      // boundary faces nf*snGrad, no point values (extendedFaceStencilScalarGrad.C:86-109)
     std::vector<int> vtx, flags;
     std::vector<double> G, hd;
@@ -595,7 +593,7 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         std::vector<int> cells;
         std::vector<double> coef;
         std::vector<char> deg;
-        mesh->h.buildLeastSquares(W, cells, coef, deg);
+        mesh->h.buildLeastSquares(name == "leastSquaresOpt", W, cells, coef, deg);
         const int nI = mesh->h.nInternal;
         const size_t nIs = (size_t)std::max(nI, 1);
         std::vector<int> cd((size_t)W * nIs, 0);

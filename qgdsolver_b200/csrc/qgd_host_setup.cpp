@@ -271,7 +271,7 @@ void HostMesh::buildFaceRecords(bool reduced, std::vector<int>& vtx, std::vector
     }
 }
 
-void HostMesh::buildLeastSquares(int& W, std::vector<int>& cells, std::vector<double>& coef, std::vector<char>& deg) const
+void HostMesh::buildLeastSquares(bool opt, int& W, std::vector<int>& cells, std::vector<double>& coef, std::vector<char>& deg) const
 {
     const double SMALLv = 1e-15;
     // [OF-v2312] primitiveMesh::pointCells(): ascending cell order per point
@@ -315,11 +315,14 @@ void HostMesh::buildLeastSquares(int& W, std::vector<int>& cells, std::vector<do
         const double xx = G[0], xy = G[1], xz = G[2], yy = G[3], yz = G[4], zz = G[5];
         const double detG = xx * yy * zz + xy * yz * xz + xz * xy * yz - xx * yz * yz - xy * xy * zz - xz * yy * xz;
         for (size_t j = 0; j < (size_t)W; ++j) cells[j * nI + f] = owner[f];
-        if (detG < 1) { deg[f] = 1; continue; }
-        double Gi[6];
+        double Gi[6] = {G[0], G[1], G[2], G[3], G[4], G[5]};
+        if (detG < 1) {
+            if (!opt) { deg[f] = 1; continue; }      // leastSquares: nf*snGrad ; leastSquaresOpt: un-inverted (G+G0)&df
+        } else {
         Gi[0] = (yy * zz - yz * yz) / detG; Gi[1] = (xz * yz - xy * zz) / detG; Gi[2] = (xy * yz - xz * yy) / detG;
         Gi[3] = (xx * zz - xz * xz) / detG; Gi[4] = (xy * xz - xx * yz) / detG; Gi[5] = (xx * yy - xy * xy) / detG;
         for (int t = 0; t < 6; ++t) Gi[t] -= G0[t];
+        }
         for (size_t i = 0; i < nb.size(); ++i) {
             const Vec3 d = df[i];
             const double gd[3] = {Gi[0] * d[0] + Gi[1] * d[1] + Gi[2] * d[2], Gi[1] * d[0] + Gi[3] * d[1] + Gi[4] * d[2],

@@ -104,7 +104,8 @@ struct HostMesh {
     // leastSquares scheme (extendedFaceStencilFindNeighbours.C:41-86, extendedFaceStencilCalculateWeights.C:43-155):
     // per internal face (polyMesh order) an ELL row of W neighbour cells and coefficient vectors wf2*Gdf; deg[f] = 1 where
     // the reference falls back to nf*snGrad (det G < 1)
-    void buildLeastSquares(int& W, std::vector<int>& cells /*W*nInternal*/, std::vector<double>& coef /*W*3*nInternal*/,
+    // opt: leastSquaresOpt keeps the (un-inverted) stencil on degenerate faces instead of the fallback
+    void buildLeastSquares(bool opt, int& W, std::vector<int>& cells /*W*nInternal*/, std::vector<double>& coef /*W*3*nInternal*/,
                            std::vector<char>& deg /*nInternal*/) const;
     void buildFaceRecords(bool reduced, std::vector<int>& vtx /*nFaces*4*/, std::vector<int>& flags /*nFaces*/,
                           std::vector<double>& G /*9 arrays of nFaces, SoA: G[k*nFaces+f]*/,

@@ -43,10 +43,10 @@ def _fields(mesh, k, seed):
 
 
 @pytest.mark.parametrize("mesh_name", list(MESHES))
-@pytest.mark.parametrize("scheme", ["GaussVolPoint", "reduced", "leastSquares"])
+@pytest.mark.parametrize("scheme", ["GaussVolPoint", "reduced", "leastSquares", "leastSquaresOpt"])
 def test_fvsc_operators_match_oracle(qgd, oracle_mod, mesh_name, scheme):
     mesh = MESHES[mesh_name]()
-    if scheme == "leastSquares" and mesh.n_geometric_d == 3:
+    if scheme.startswith("leastSquares") and mesh.n_geometric_d == 3:
         pytest.skip("leastSquares is rejected in 3D (fvsc.C:60-63)")
     o = oracle_mod.Oracle(mesh)
     osch = oracle_mod.FVSC_SCHEMES[scheme]
@@ -100,6 +100,10 @@ STEP_CASES = {
     "2d_leastSquares": lambda: cases.case_2d(perturb=0.2, bcs="mixed", scheme="leastSquares"),
     "2d_y_leastSquares_implicit": lambda: cases.case_2d(perturb=0.1, bcs="fixed", axis=1, scheme="leastSquares", implicit=True),
     "sod_leastSquares": lambda: cases.case_sod(200, scheme="leastSquares"),
+    "2d_leastSquaresOpt": lambda: cases.case_2d(perturb=0.2, bcs="qgdflux", scheme="leastSquaresOpt"),
+    # aspect ratio 10: det(G) < 1 on the x-normal faces -> degenerate-stencil branch (extendedFaceStencilCalculateWeights.C:136-140)
+    "2d_leastSquares_degenerate": lambda: cases.case_2d(n=(6, 60), bcs="mixed", scheme="leastSquares"),
+    "2d_leastSquaresOpt_degenerate": lambda: cases.case_2d(n=(6, 60), bcs="mixed", scheme="leastSquaresOpt"),
 }
 
 
