@@ -225,13 +225,17 @@ typedef struct {
     double mu, Pr, beta;            /* constTransport + beta (QHDFoam/createFields.H:110-115)       */
     double g[3];                    /* constant/gravitationalProperties (createFields.H:108)        */
     double Tau, UQHD, Gr, T0;       /* model coefficients                                           */
-    int implicit_diffusion;         /* QGD::implicitDiffusion; only false runs on the device        */
+    int implicit_diffusion;         /* QGD::implicitDiffusion: QHDUEqn.H:46-65, QHDTEqn.H:69-80      */
     double p_tolerance, p_rel_tol;  /* fvSolution::solvers::p                                       */
     int p_max_iter;
     const char* p_preconditioner;   /* "DIC" | "diagonal" | "none"                                  */
     int p_ref_cell; double p_ref_value;   /* setRefCell(p, thermo.subDict("QGD"), ...) createFields.H:162-165 */
     int adjust_time_step;           /* QHDCourantNo.H:37                                            */
     double max_co, max_delta_t, c_tau, delta_t;
+    /* fvSolution::solvers::"(U|T)" for the implicit-diffusion branch: PCG + preconditioner ("DIC" | "diagonal" | "none") */
+    double diff_tolerance, diff_rel_tol;
+    int diff_max_iter;
+    const char* diff_preconditioner;
 } qgd_qhdfoam_desc;
 int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* desc, qgd_qhd_solver** out);
 int qgd_qhdfoam_destroy(qgd_qhd_solver* s);

@@ -49,7 +49,8 @@ class QHDParams(C.Structure):
                 ("g", C.c_double * 3), ("qgdModel", C.c_int), ("Tau", C.c_double), ("UQHD", C.c_double),
                 ("Gr", C.c_double), ("T0", C.c_double), ("implicitDiffusion", C.c_int),
                 ("pTol", C.c_double), ("pRelTol", C.c_double), ("pMaxIter", C.c_int), ("pPrecond", C.c_int),
-                ("pRefCell", C.c_int), ("pRefValue", C.c_double)]
+                ("pRefCell", C.c_int), ("pRefValue", C.c_double),
+                ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int)]
 
 
 QHD_MODELS = {"constTau": 0, "H2bynuQHD": 1, "HbyUQHD": 2, "T0byGr": 3}

@@ -112,10 +112,13 @@ typedef struct {
     double g[3];               // constant/gravitationalProperties
     int qgdModel;              // 0 constTau, 1 H2bynuQHD, 2 HbyUQHD, 3 T0byGr
     double Tau, UQHD, Gr, T0;  // model coefficients
-    int implicitDiffusion;     // only 0 supported
+    int implicitDiffusion;     // QGD::implicitDiffusion
     double pTol, pRelTol;      // fvSolution::solvers::p
     int pMaxIter, pPrecond;    // precond: 0 none, 1 diagonal, 2 DIC
     int pRefCell; double pRefValue;   // setRefCell(p, thermo.subDict("QGD"), ...)
+    // implicitDiffusion branch (QHDUEqn.H:46-65, QHDTEqn.H:69-80): fvSolution controls of the U and T solvers (PCG)
+    double diffTol, diffRelTol;
+    int diffMaxIter, diffPrecond;
 } or_qhd_params_t;
 //  bc kinds per patch: fixedValue | zeroGradient | fixedGradient (qhdFlux behaves as fixedGradient in QHDFoam, see
 //  DESIGN.md quirk (i)); bv*: value on fixedValue faces, gradient on fixedGradient faces

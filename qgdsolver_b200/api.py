@@ -77,7 +77,9 @@ class QHDFoamDesc(C.Structure):
                 ("implicit_diffusion", C.c_int), ("p_tolerance", C.c_double), ("p_rel_tol", C.c_double),
                 ("p_max_iter", C.c_int), ("p_preconditioner", C.c_char_p), ("p_ref_cell", C.c_int),
                 ("p_ref_value", C.c_double), ("adjust_time_step", C.c_int),
-                ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double)]
+                ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double),
+                ("diff_tolerance", C.c_double), ("diff_rel_tol", C.c_double), ("diff_max_iter", C.c_int),
+                ("diff_preconditioner", C.c_char_p)]
 
 
 class _StateHost(C.Structure):
@@ -423,11 +425,12 @@ class QHDFoam:
     def __init__(self, mesh: Mesh, *, rho0, mu, Pr, beta, g, fvsc_scheme="GaussVolPoint", qgd_coeffs="constTau",
                  Tau=0.0, UQHD=1.0, Gr=1.0, T0=1.0, implicit_diffusion=False, tol=1e-8, rel_tol=0.0, max_iter=1000,
                  precond="DIC", p_ref_cell=0, p_ref_value=0.0, adjust_time_step=False, max_co=0.3, max_delta_t=1e30,
-                 c_tau=0.75, delta_t=1e-3):
+                 c_tau=0.75, delta_t=1e-3, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000, diff_precond="DIC"):
         self.mesh = mesh
         d = QHDFoamDesc()
-        self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), precond.encode())
-        d.fvsc_scheme, d.qgd_coeffs_model, d.p_preconditioner = self._names
+        self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), precond.encode(), diff_precond.encode())
+        d.fvsc_scheme, d.qgd_coeffs_model, d.p_preconditioner, d.diff_preconditioner = self._names
+        d.diff_tolerance, d.diff_rel_tol, d.diff_max_iter = diff_tol, diff_rel_tol, diff_max_iter
         d.rho0, d.mu, d.Pr, d.beta = rho0, mu, Pr, beta
         for j in range(3):
             d.g[j] = g[j]

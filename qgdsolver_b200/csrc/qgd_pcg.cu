@@ -264,9 +264,10 @@ __global__ void k_fill_coef(int n, int W, const int* __restrict__ encFace, const
 
 void PcgMatrix::refresh(const double* faceCoef, const double* diagDev, cudaStream_t st)
 {
-    if (!encFace.n) throw Error(QGD_ERR_STATE, "PcgMatrix::refresh: matrix was built without face ids");
+    if (faceCoef && !encFace.n) throw Error(QGD_ERR_STATE, "PcgMatrix::refresh: matrix was built without face ids");
     const int nTail = (int)tailFace.n;
-    k_fill_coef<<<(std::max(n, nTail) + 255) / 256, 256, 0, st>>>(n, W, encFace.p, faceCoef, coef.p, nTail, tailFace.p, tailCoef.p);
+    if (faceCoef)      // nullptr: only the diagonal changed (e.g. a new deltaT)
+        k_fill_coef<<<(std::max(n, nTail) + 255) / 256, 256, 0, st>>>(n, W, encFace.p, faceCoef, coef.p, nTail, tailFace.p, tailCoef.p);
     QGD_CUDA(cudaMemcpyAsync(diag.p, diagDev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (precond == 1) k_recip<<<(n + 255) / 256, 256, 0, st>>>(n, diag.p, rD.p);
     else if (precond == 2) {

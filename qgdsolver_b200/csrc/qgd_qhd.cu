@@ -26,6 +26,7 @@ struct QhdConsts {
     double rho0, nu, Hi, beta, g[3];
     int needRef, refCell;
     double refValue;
+    int implicit;                // QGD::implicitDiffusion: the Laplacians of U and T are solved implicitly (QHDUEqn.H:46-65, QHDTEqn.H:69-80)
 };
 
 struct QhdView {
@@ -47,6 +48,9 @@ struct QhdView {
     const double* srcBnd;        // [nCells] sum of boundaryCoeffs of the cell's boundary faces
     const double* diag0;         // [nCells] pEqn diagonal before boundary contributions and setReference
     double* pcgB;                // [nCells] pEqn source handed to the PCG
+    // implicit branch: time-constant Laplacian row sums / boundary sources, per-step diagonals and right-hand sides
+    const double* sumAU; const double* sumAT; const double* srcBU; const double* srcBT;   // [nC], [nC], [3][nC], [nC]
+    double* diagU; double* diagT; double* bU; double* bT;                                 // [nC], [nC], [3][nC], [nC]
     double* shift;               // [1] reference shift of p
     StepScalars* sc;
 };
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(kB) k_qhd_face_post(QhdConsts k, FaceView fv, 
     for (int j = 0; j < 3; ++j) {
         const double UW = ge.Sf[0] * (c.Uf[0] * Wf[j]) + ge.Sf[1] * (c.Uf[1] * Wf[j]) + ge.Sf[2] * (c.Uf[2] * Wf[j]);   // :39
         const double phiUf = phi * c.Uf[j] - UW;                                       // :41-43
-        const double lap = k.nu * (nd * (uN[j] - uP[j])) * ms;                         // :74 fvc::laplacian(muf/rhof,U)
+        const double lap = k.implicit ? 0.0 : k.nu * (nd * (uN[j] - uP[j])) * ms;      // :74 fvc::laplacian(muf/rhof,U) (explicit branch)
         double tr = 0.0;                                                               // :76 (muf/rhof Sf) & I(T(grad U))
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(kB) k_qhd_face_post(QhdConsts k, FaceView fv, 
     }
     const double phiTf = phi * c.Tf;                                                   // QHDTEqn.H:65
     const double reg = tau * c.phiu * (c.Uf[0] * gT[0] + c.Uf[1] * gT[1] + c.Uf[2] * gT[2]);   // :66
-    const double lapT = k.Hi * (nd * (TN - TP)) * ms;                                  // :87
+    const double lapT = k.implicit ? 0.0 : k.Hi * (nd * (TN - TP)) * ms;               // :87 (explicit branch)
     q.FT[f] = phiTf - lapT - reg;
 }
 
@@ -491,7 +495,7 @@ __global__ void k_qhd_bnd_post(QhdConsts k, FaceView fv, QhdView q)
     for (int j = 0; j < 3; ++j) {
         const double UW = ge.Sf[0] * (c.Uf[0] * Wf[j]) + ge.Sf[1] * (c.Uf[1] * Wf[j]) + ge.Sf[2] * (c.Uf[2] * Wf[j]);
         const double phiUf = phi * c.Uf[j] - UW;
-        const double lap = k.nu * bc.snU[j] * ms;
+        const double lap = k.implicit ? 0.0 : k.nu * bc.snU[j] * ms;
         // boundary value of T(fvc::grad(U)): gaussGrad::correctBoundaryConditions  [OF-v2312]
         //   gradU_b = gradU_P + n (x) (snGrad(U)_b - n . gradU_P) ; the flux needs (gradU_b)_{j i}
         double tr = 0.0;
@@ -506,7 +510,36 @@ __global__ void k_qhd_bnd_post(QhdConsts k, FaceView fv, QhdView q)
         q.FU[j * nF + f] = phiUf - lap - tr + ge.Sf[j] * pb / k.rho0;
     }
     const double reg = c.tau * c.phiu * (c.Uf[0] * gT[0] + c.Uf[1] * gT[1] + c.Uf[2] * gT[2]);
-    q.FT[f] = phi * c.Tf - k.Hi * bc.snT * ms - reg;
+    q.FT[f] = phi * c.Tf - (k.implicit ? 0.0 : k.Hi * bc.snT * ms) - reg;
+}
+
+// implicit branch: diagonals and right-hand sides of the U and T systems (QHDUEqn.H:48-64, QHDTEqn.H:71-79)
+__global__ void __launch_bounds__(kB) k_qhd_cell_sys(QhdConsts k, FaceView fv, QhdView q)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= q.nCells) return;
+    const size_t n = q.nCells, nF = fv.nF;
+    double su[3] = {0, 0, 0}, sT = 0.0;
+    forCellFaces(q, c, [&](int f, int side) {
+        const double sgn = side ? -1.0 : 1.0;
+        su[0] += sgn * q.FU[f]; su[1] += sgn * q.FU[nF + f]; su[2] += sgn * q.FU[2 * nF + f];
+        sT += sgn * q.FT[f];
+    });
+    const double V = __ldg(&q.V[c]);
+    const double rDeltaT = 1.0 / q.sc->dt;
+    const double T = q.Q[3 * n + c];
+    q.diagU[c] = rDeltaT * V + __ldg(&q.sumAU[c]);
+    q.diagT[c] = rDeltaT * V + __ldg(&q.sumAT[c]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        q.bU[j * n + c] = rDeltaT * q.Q[j * n + c] * V - V * (su[j] / V) + V * ((k.beta * T) * k.g[j]) + __ldg(&q.srcBU[j * n + c]);
+    q.bT[c] = rDeltaT * T * V - V * (sT / V) + __ldg(&q.srcBT[c]);
+}
+
+__global__ void k_qhd_pshift(QhdView q)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < q.nCells) q.Q[4 * (size_t)q.nCells + c] += *q.shift;
 }
 
 __global__ void k_qhd_shift(QhdConsts k, QhdView q)
@@ -553,6 +586,10 @@ struct qgd_qhd_solver {
     QhdConsts k{};
     int precond = 2;
     DevBuf<double> Q, P, tauf, upper, F0, FU, FT, phi, GU, UB, TB, pB, bvU, bvT, bvP, intC, bouC, srcBnd, diag0, shift, stage;
+    DevBuf<double> sumAU, sumAT, srcBU, srcBT, diagU, diagT, bU, bT;      // implicit branch
+    PcgMatrix AU, AT;
+    int diffPrecond = 2;
+    std::vector<double> hbvU, hbvT;
     DevBuf<int> bcU, bcT, bcP;
     DevBuf<StepScalars> sc;
     PcgMatrix A;
@@ -574,6 +611,7 @@ struct qgd_qhd_solver {
         q.UB = UB.p; q.TB = TB.p; q.pB = pB.p; q.bcU = bcU.p; q.bcT = bcT.p; q.bcP = bcP.p;
         q.bvU = bvU.p; q.bvT = bvT.p; q.bvP = bvP.p; q.intC = intC.p; q.bouC = bouC.p; q.srcBnd = srcBnd.p; q.diag0 = diag0.p;
         q.pcgB = A.b.p; q.shift = shift.p; q.sc = sc.p;
+        q.sumAU = sumAU.p; q.sumAT = sumAT.p; q.srcBU = srcBU.p; q.srcBT = srcBT.p; q.diagU = diagU.p; q.diagT = diagT.p; q.bU = bU.p; q.bT = bT.p;
         return q;
     }
 };
@@ -624,7 +662,25 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
         if (fv.nI) { k_qhd_face_post<<<nblk(fv.nI), kB, 0, st>>>(k, fv, q); ++n; }
         if (nB) { k_qhd_bnd_post<<<nblk(nB), kB, 0, st>>>(k, fv, q); ++n; }
         k_qhd_shift<<<1, 1, 0, st>>>(k, q); ++n;
-        k_qhd_cell_update<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
+        if (k.implicit) {
+            const size_t nC = q.nCells;
+            const double tol = s->desc.diff_tolerance, rel = s->desc.diff_rel_tol;
+            const int maxIter = s->desc.diff_max_iter > 0 ? s->desc.diff_max_iter : 1000;
+            k_qhd_cell_sys<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
+            s->AU.refresh(nullptr, q.diagU, st);
+            for (int j = 0; j < 3; ++j) {                           // QHDUEqn.H:48-64, segregated components
+                s->AU.bExternal = q.bU + j * nC;
+                s->AU.xExternal = q.Q + j * nC;
+                n += 1 + s->AU.solve(tol, rel, maxIter, st);
+            }
+            s->AT.refresh(nullptr, q.diagT, st);
+            s->AT.bExternal = q.bT;
+            s->AT.xExternal = q.Q + 3 * nC;
+            n += 2 + s->AT.solve(tol, rel, maxIter, st);               // QHDTEqn.H:71-79
+            k_qhd_pshift<<<nblk(q.nCells), kB, 0, st>>>(q); ++n;
+        } else {
+            k_qhd_cell_update<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
+        }
         if (nB) {
             k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 0, 0);                        // U, T correctBoundaryConditions
             k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 1, 1);                        // p_b += shift
@@ -650,12 +706,16 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
                                                    "\n\nValid model types are:\n" + coeffsModelToc());
         if (model != "constTau" && model != "H2bynuQHD" && model != "HbyUQHD" && model != "T0byGr")
             throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not a QHD model available on the device (constTau, H2bynuQHD, HbyUQHD, T0byGr)");
-        if (d->implicit_diffusion)
-            throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true is not available on the device yet; set QGD::implicitDiffusion false");
+        auto precondOf = [](const char* name) {
+            const std::string pc = name ? name : "DIC";
+            if (pc == "DIC") return 2;
+            if (pc == "diagonal") return 1;
+            if (pc == "none") return 0;
+            throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown symmetric matrix preconditioner " + pc + "\n\nValid symmetric matrix preconditioners are:\n3\n(\nDIC\ndiagonal\nnone\n)\n");
+        };
         const std::string pc = d->p_preconditioner ? d->p_preconditioner : "DIC";
-        int precond;
-        if (pc == "DIC") precond = 2; else if (pc == "diagonal") precond = 1; else if (pc == "none") precond = 0;
-        else throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown symmetric matrix preconditioner " + pc + "\n\nValid symmetric matrix preconditioners are:\n3\n(\nDIC\ndiagonal\nnone\n)\n");
+        const int precond = precondOf(d->p_preconditioner);
+        const int diffPrecond = d->implicit_diffusion ? precondOf(d->diff_preconditioner) : 2;
         for (int pk : mesh->h.patchKind)
             if (pk == QGD_PATCH_PROCESSOR) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam: processor patches (multi-GPU) are not available yet");
         if (mesh->h.nOwned != mesh->h.nCells) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam: extended sub-meshes (multi-GPU) are not available yet");
@@ -663,14 +723,15 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
         if (d->p_ref_cell < 0 || d->p_ref_cell >= mesh->h.nCells) throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_create: pRefCell out of range");
         std::unique_ptr<qgd_qhd_solver> s(new qgd_qhd_solver());
         s->mesh = mesh; s->desc = *d; s->model = model; s->precondName = pc; s->precond = precond;
-        s->desc.fvsc_scheme = nullptr; s->desc.qgd_coeffs_model = nullptr; s->desc.p_preconditioner = nullptr;
+        s->desc.fvsc_scheme = nullptr; s->desc.qgd_coeffs_model = nullptr; s->desc.p_preconditioner = nullptr; s->desc.diff_preconditioner = nullptr;
+        s->diffPrecond = diffPrecond;
         s->fvsc.reset(new qgd_fvsc());
         fvscBuild(*s->fvsc, mesh, d->fvsc_scheme);
         if (s->fvsc->lsq) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam with fvsc scheme leastSquares is not available on the device yet");
         QhdConsts& k = s->k;
         k.rho0 = d->rho0; k.nu = d->mu / d->rho0; k.Hi = (d->mu / d->Pr) / d->rho0; k.beta = d->beta;
         for (int j = 0; j < 3; ++j) k.g[j] = d->g[j];
-        k.needRef = 0; k.refCell = d->p_ref_cell; k.refValue = d->p_ref_value;
+        k.needRef = 0; k.refCell = d->p_ref_cell; k.refValue = d->p_ref_value; k.implicit = d->implicit_diffusion ? 1 : 0;
         const HostMesh& h = mesh->h;
         cudaStream_t st = runtimeStream();
         s->Q.alloc(5 * (size_t)h.nCells); s->P.alloc(5 * (size_t)h.nPoints); s->P.zero(st);
@@ -728,6 +789,8 @@ int qgd_qhdfoam_set_bcs(qgd_qhd_solver* s, const int* bc_U, const int* bc_T, con
             if (val_p) p[b] = val_p[b];
         }
         s->hbvP.assign(p.begin(), p.begin() + nB);
+        s->hbvT.assign(t.begin(), t.begin() + nB);
+        s->hbvU.assign(val_U ? val_U : u.data(), (val_U ? val_U : u.data()) + 3 * (size_t)nB);     // AoS as passed in
         s->bvU.upload(u, st); s->bvT.upload(t, st); s->bvP.upload(p, st);
         s->bcsSet = true;
     });
@@ -799,6 +862,29 @@ int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T,
         for (int f = 0; f < nI; ++f) upperDev[f] = upper[perm[f]];
         s->tauf.upload(taufDev, st); s->upper.upload(upperDev, st);
         s->intC.upload(intC, st); s->bouC.upload(bouC, st); s->srcBnd.upload(srcBnd, st); s->diag0.upload(diag, st);
+        if (s->k.implicit) {
+            // U and T systems: -laplacian(muf/rhof, .) and -laplacian(Hif, .) are time-constant; only V/deltaT changes
+            std::vector<double> upU(std::max(nI, 1), 0.0), upT(std::max(nI, 1), 0.0), sAU(nC, 0.0), sAT(nC, 0.0), sBU(3 * (size_t)nC, 0.0), sBT(nC, 0.0), d0(nC, 1.0);
+            const double nu = d.mu / d.rho0, Hi = (d.mu / d.Pr) / d.rho0;
+            for (int f = 0; f < nI; ++f) {
+                const double aU = h.ndC[f] * (nu * h.magSf[f]), aT = h.ndC[f] * (Hi * h.magSf[f]);
+                upU[f] = -aU; upT[f] = -aT;
+                sAU[h.owner[f]] += aU; sAU[h.neighbour[f]] += aU; sAT[h.owner[f]] += aT; sAT[h.neighbour[f]] += aT;
+            }
+            for (int b = 0; b < nB; ++b) {
+                if (h.patchKind[h.bfacePatch[b]] == QGD_PATCH_EMPTY) continue;
+                const int f = nI + b, P = h.owner[f];
+                const double gU = nu * h.magSf[f], gT = Hi * h.magSf[f];
+                if (s->hbcU[b] == QGD_BC_FIXED_VALUE) { sAU[P] += gU * h.ndC[f]; for (int j = 0; j < 3; ++j) sBU[(size_t)j * nC + P] += gU * (h.ndC[f] * s->hbvU[3 * (size_t)b + j]); }
+                else if (s->hbcU[b] == QGD_BC_FIXED_GRADIENT) for (int j = 0; j < 3; ++j) sBU[(size_t)j * nC + P] += gU * s->hbvU[3 * (size_t)b + j];
+                if (s->hbcT[b] == QGD_BC_FIXED_VALUE) { sAT[P] += gT * h.ndC[f]; sBT[P] += gT * (h.ndC[f] * s->hbvT[b]); }
+                else if (s->hbcT[b] == QGD_BC_FIXED_GRADIENT) sBT[P] += gT * s->hbvT[b];
+            }
+            s->AU.build(h, d0.data(), upU.data(), s->diffPrecond, st);
+            s->AT.build(h, d0.data(), upT.data(), s->diffPrecond, st);
+            s->sumAU.upload(sAU, st); s->sumAT.upload(sAT, st); s->srcBU.upload(sBU, st); s->srcBT.upload(sBT, st);
+            s->diagU.alloc(nC); s->diagT.alloc(nC); s->bU.alloc(3 * (size_t)nC); s->bT.alloc(nC);
+        }
         // boundary values of the fields as read
         const FaceView fv = s->fvsc->view();
         const QhdView q = s->view();

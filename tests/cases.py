@@ -150,7 +150,10 @@ class QHDCase:
     def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, fluid=QHD_FLUID, model="constTau",
                  coeffs=None, dt=1e-3, scheme="GaussVolPoint", alphaQGD=None, tol=1e-13, rel_tol=0.0, max_iter=5000,
                  precond="DIC", p_ref_cell=0, p_ref_value=0.0, adjust_time_step=False, max_co=0.3, max_delta_t=1e30,
-                 c_tau=0.75):
+                 c_tau=0.75, implicit=False, diff_solver=None):
+        self.implicit = implicit
+        self.diff_solver = dict(tol=1e-14, rel_tol=0.0, max_iter=2000, precond="DIC")
+        self.diff_solver.update(diff_solver or {})
         self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
         self.bcU, self.bcT, self.bcP = [np.asarray(x, np.int32) for x in (bcU, bcT, bcP)]
         self.bvU, self.bvT, self.bvP = bvU, bvT, bvP
@@ -165,9 +168,11 @@ class QHDCase:
         o = O.Oracle(self.mesh, n_threads=n_threads)
         f, c, sv = self.fluid, self.coeffs, self.solver
         prm = O.QHDParams(rho0=f["rho0"], mu=f["mu"], Pr=f["Pr"], beta=f["beta"], qgdModel=O.QHD_MODELS[self.model],
-                          Tau=c["Tau"], UQHD=c["UQHD"], Gr=c["Gr"], T0=c["T0"], implicitDiffusion=0,
+                          Tau=c["Tau"], UQHD=c["UQHD"], Gr=c["Gr"], T0=c["T0"], implicitDiffusion=int(self.implicit),
                           pTol=sv["tol"], pRelTol=sv["rel_tol"], pMaxIter=sv["max_iter"],
-                          pPrecond=O.PRECONDS[sv["precond"]], pRefCell=self.p_ref_cell, pRefValue=self.p_ref_value)
+                          pPrecond=O.PRECONDS[sv["precond"]], pRefCell=self.p_ref_cell, pRefValue=self.p_ref_value,
+                          diffTol=self.diff_solver["tol"], diffRelTol=self.diff_solver["rel_tol"],
+                          diffMaxIter=self.diff_solver["max_iter"], diffPrecond=O.PRECONDS[self.diff_solver["precond"]])
         for j in range(3):
             prm.g[j] = f["g"][j]
         scheme = O.FVSC_SCHEMES[self.scheme]
@@ -181,8 +186,11 @@ class QHDCase:
 
     def make_solver(self, api, dmesh=None):
         dmesh = dmesh or api.Mesh(self.mesh)
+        ds = self.diff_solver
         s = api.QHDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, p_ref_cell=self.p_ref_cell,
-                        p_ref_value=self.p_ref_value, **self.fluid, **self.coeffs, **self.solver, **self.opts)
+                        p_ref_value=self.p_ref_value, implicit_diffusion=self.implicit, diff_tol=ds["tol"],
+                        diff_rel_tol=ds["rel_tol"], diff_max_iter=ds["max_iter"], diff_precond=ds["precond"],
+                        **self.fluid, **self.coeffs, **self.solver, **self.opts)
         s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
         s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
         return s

@@ -101,6 +101,10 @@ QHD_CASES = {
     "cavity3d_constTau": lambda: cases.qhd_cavity(n=(9, 8, 7), dims=3, dt=1e-3, perturb=0.1),
     "cavity3d_reduced": lambda: cases.qhd_cavity(n=(8, 8, 6), dims=3, dt=1e-3, scheme="reduced"),
     "cavity2d_refcell": lambda: cases.qhd_cavity(n=(14, 12), dt=1e-3, p_ref_cell=37, p_ref_value=0.25),
+    # implicitDiffusion true (the reference's default): QHDUEqn.H:46-65, QHDTEqn.H:69-80
+    "cavity2d_implicit": lambda: cases.qhd_cavity(n=(18, 16), dt=1e-3, perturb=0.1, implicit=True),
+    "cavity3d_implicit_diag": lambda: cases.qhd_cavity(n=(8, 7, 6), dims=3, dt=1e-3, implicit=True, diff_solver=dict(precond="diagonal")),
+    "cavity2d_implicit_adjust": lambda: cases.qhd_cavity(n=(16, 14), dt=1e-3, implicit=True, adjust_time_step=True, max_co=0.05, c_tau=0.4),
 }
 
 
@@ -193,7 +197,7 @@ def test_qhd_error_behaviour(qgd):
         qgd.QHDFoam(dm, precond="GAMG", **kw)
     assert "Unknown symmetric matrix preconditioner GAMG" in e.value.message
     with pytest.raises(qgd.QGDError) as e:
-        qgd.QHDFoam(dm, implicit_diffusion=True, **kw)
+        qgd.QHDFoam(dm, fvsc_scheme="leastSquares", **kw)
     assert e.value.code == qgd.ERR_UNSUPPORTED
     with pytest.raises(qgd.QGDError) as e:
         qgd.QHDFoam(dm, **kw).step(1)
