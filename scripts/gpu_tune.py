@@ -1,6 +1,6 @@
 """Tuning sweep of the pipelined step at size N: python gpu_tune.py N [steps]  (one mesh build, many configurations)."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench as B
 from qgdsolver_b200 import api
 
