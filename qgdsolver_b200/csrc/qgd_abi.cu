@@ -18,6 +18,8 @@ static thread_local std::string g_lastError;
 void setLastError(const std::string& m) { g_lastError = m; }
 
 static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_commStream = nullptr;        // halo exchange overlapped with the interior point gather
+static cudaEvent_t g_evStep = nullptr, g_evHalo = nullptr;
 static bool g_initialised = false;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
@@ -149,6 +151,8 @@ struct qgd_solver {
         DevBuf<double> midSend, midRecv;      // p_b of halo boundary faces (qgdFlux mid-step refresh)
         DevBuf<int> planSendItem, planSendCell, planSendBf, planRecvItem, planRecvCell, planRecvBf;   // k_halo_all plans
         DevBuf<long long> planSendBuf, planRecvBuf;
+        DevBuf<int> ptsInterior, ptsHalo;      // point lists for the overlapped exchange
+        bool pending = false;                  // an exchange is in flight on the communication stream
         bool active = false;
     } halo;
     // per-kernel CUDA-event timing (bench): events of the profiled steps, 6 per step
@@ -168,6 +172,9 @@ struct qgd_solver {
         s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
         s.cfEllW = m.cfEllW; s.cfEll = m.cfEll.p; s.cfTailOff = m.cfTailOff.p; s.cfTailEnc = m.cfTailEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
         s.tauOut = tauOut.n ? tauOut.p : nullptr;
+        const bool split = halo.active && halo.ptsInterior.n > 0 && halo.ptsHalo.n > 0;
+        s.ptsInterior = split ? halo.ptsInterior.p : nullptr; s.nPtsInterior = split ? (int)halo.ptsInterior.n : 0;
+        s.ptsHalo = split ? halo.ptsHalo.p : nullptr; s.nPtsHalo = split ? (int)halo.ptsHalo.n : 0;
         for (int q = 0; q < 5; ++q) { s.FI[q] = Fflux.p + q * strideI; s.FB[q] = Fflux.p + bndOff + q * strideB; }
         s.ringSize = ringSize; s.sc = sc.p;
         return s;
@@ -279,7 +286,7 @@ __global__ void k_scatter1(int n, const int* __restrict__ ids, const double* __r
 }
 
 // full state exchange after the cell update (SURVEY 5.8 C1+C3 in one message per neighbour)
-int haloExchange(qgd_solver* s)
+int haloExchange(qgd_solver* s, cudaStream_t g_stream = qgd::g_stream)
 {
     qgd_solver::Halo& h = s->halo;
     if (!h.active) return 0;
@@ -532,6 +539,13 @@ void runSteps(qgd_solver* s, int n)
                 QGD_NCCL(g_nccl.GroupEnd());
             };
     }
+    // overlap the packed exchange with the next step's interior point gather (fixed deltaT, no mid-step exchange)
+    const bool overlap = multi && g_commStream && !s->desc.adjust_time_step && !s->anyQgdFlux && s->halo.ptsInterior.n > 0 &&
+                         !(getenv("QGD_HALO_OVERLAP") && atoi(getenv("QGD_HALO_OVERLAP")) == 0);
+    if (multi)
+        hooks.waitHalo = [s] {
+            if (s->halo.pending) { QGD_CUDA(cudaStreamWaitEvent(g_stream, g_evHalo, 0)); s->halo.pending = false; }
+        };
     for (int i = 0; i < n; ++i) {
         cudaEvent_t* ev = nullptr;
         if (s->profiling) {
@@ -547,8 +561,17 @@ void runSteps(qgd_solver* s, int n)
         if (usePipe) { ++s->pipe.epoch; pv = s->pview(); }
         s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev,
                                   multi ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid);
-        if (multi) s->launches += haloExchange(s);
+        if (multi) {
+            if (overlap) {
+                QGD_CUDA(cudaEventRecord(g_evStep, g_stream));
+                QGD_CUDA(cudaStreamWaitEvent(g_commStream, g_evStep, 0));
+                s->launches += haloExchange(s, g_commStream);
+                QGD_CUDA(cudaEventRecord(g_evHalo, g_commStream));
+                s->halo.pending = true;
+            } else s->launches += haloExchange(s);
+        }
     }
+    if (multi && s->halo.pending) { QGD_CUDA(cudaStreamWaitEvent(g_stream, g_evHalo, 0)); s->halo.pending = false; }
     QGD_CUDA(cudaGetLastError());
 }
 
@@ -1176,6 +1199,14 @@ int qgd_comm_init(int rank, int n_ranks, const void* id128)
         std::memcpy(&id, id128, sizeof(id));
         QGD_NCCL(g_nccl.CommInitRank(&g_comm, n_ranks, id, rank));
         g_rank = rank; g_nranks = n_ranks;
+        if (!g_commStream) {
+            // highest priority: the exchange's CTAs are placed as soon as an SM has room, ahead of the point gather's
+            int prLo = 0, prHi = 0;
+            QGD_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+            QGD_CUDA(cudaStreamCreateWithPriority(&g_commStream, cudaStreamNonBlocking, prHi));
+            QGD_CUDA(cudaEventCreateWithFlags(&g_evStep, cudaEventDisableTiming));
+            QGD_CUDA(cudaEventCreateWithFlags(&g_evHalo, cudaEventDisableTiming));
+        }
     });
 }
 
@@ -1223,6 +1254,16 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* 
         plan(h.sendCellOff, h.sendBfOff, h.planSendItem, h.planSendCell, h.planSendBf, h.planSendBuf);
         plan(h.recvCellOff, h.recvBfOff, h.planRecvItem, h.planRecvCell, h.planRecvBf, h.planRecvBuf);
         h.active = nn > 0;
+        {   // points whose cells are all owned vs points that read a halo copy (patch points are handled by k_patch_points)
+            std::vector<int> pin, pha;
+            for (int p = 0; p < hm.nPoints; ++p) {
+                if (hm.pcOff[p + 1] == hm.pcOff[p]) continue;
+                bool halo = false;
+                for (int q = hm.pcOff[p]; q < hm.pcOff[p + 1]; ++q) halo = halo || hm.pcCell[q] >= hm.nOwned;
+                (halo ? pha : pin).push_back(p);
+            }
+            if (!pin.empty() && !pha.empty()) { h.ptsInterior.upload(pin, g_stream); h.ptsHalo.upload(pha, g_stream); }
+        }
         // halo copies initialised locally carry wrong mesh-derived values (hQGD of an open halo cell): take the owners'
         if (h.active && s->fieldsSet) { s->launches += haloExchange(s); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
     });

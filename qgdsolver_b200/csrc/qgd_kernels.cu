@@ -412,10 +412,11 @@ __device__ __forceinline__ void blockReduceCo(double coMax, double tauMin, StepS
 
 // ---- cell -> point gather of (rho,U,e,p); ELL rows: every index/weight load of a warp is one coalesced line
 template <int W>
-__global__ void __launch_bounds__(kBlock) k_points(SolverView sv)
+__global__ void __launch_bounds__(kBlock) k_points(SolverView sv, const int* __restrict__ list, int nList)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= sv.nPoints) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nList) return;
+    const int p = list ? __ldg(&list[i]) : i;
     const int cnt = __ldg(&sv.pcCount[p]);
     if (cnt == 0) return;                                   // patch point
     const size_t nP = sv.nPoints, n = sv.nCells;
@@ -1573,15 +1574,26 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
+    auto points = [&](const int* list, int cnt) {
+        if (cnt <= 0) return;
+        if (sv.pcEllW == 4) k_points<4><<<nblk(cnt), kBlock, 0, st>>>(sv, list, cnt);
+        else if (sv.pcEllW == 6) k_points<6><<<nblk(cnt), kBlock, 0, st>>>(sv, list, cnt);
+        else k_points<8><<<nblk(cnt), kBlock, 0, st>>>(sv, list, cnt);
+        ++n;
+    };
     if (pointsNeeded) {
         if (ev) cudaEventRecord(ev[0], st);
-        if (sv.pcEllW == 4) k_points<4><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
-        else if (sv.pcEllW == 6) k_points<6><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
-        else k_points<8><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
-        ++n;
+        if (sv.ptsInterior) {
+            points(sv.ptsInterior, sv.nPtsInterior);                 // overlaps the halo exchange of the previous step
+            if (hooks && hooks->waitHalo) hooks->waitHalo();
+            points(sv.ptsHalo, sv.nPtsHalo);
+        } else {
+            if (hooks && hooks->waitHalo) hooks->waitHalo();
+            points(nullptr, sv.nPoints);
+        }
         if (ev) cudaEventRecord(ev[1], st);
         if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
-    }
+    } else if (hooks && hooks->waitHalo) hooks->waitHalo();
     if (fv.nB && anyQgdFlux) {
         k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
         if (hooks && hooks->midStep) hooks->midStep();
@@ -1626,9 +1638,9 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
     const bool pointsNeeded = !c.reducedScheme;
     if (phase == 0) {          // updateFields + updateFluxes (reduced explicit fluxes), phiTauMC, rho/rhoU update, U system
         if (pointsNeeded) {
-            if (sv.pcEllW == 4) k_points<4><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
-            else if (sv.pcEllW == 6) k_points<6><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
-            else k_points<8><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv);
+            if (sv.pcEllW == 4) k_points<4><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv, nullptr, sv.nPoints);
+            else if (sv.pcEllW == 6) k_points<6><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv, nullptr, sv.nPoints);
+            else k_points<8><<<nblk(sv.nPoints), kBlock, 0, st>>>(sv, nullptr, sv.nPoints);
             ++n;
             if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
         }

@@ -90,6 +90,9 @@ struct SolverView {
     int cfEllW; const int* cfEll;                                              // ELL cell -> faces [W][nCells], -1 pad
     const int* cfTailOff; const int* cfTailEnc;
     const double* V; const double* hQGD; const double* aQGD;
+    // multi-GPU overlap: points whose cells are all owned (gathered while the halo exchange is in flight) and the rest;
+    // null = one launch over all points
+    const int* ptsInterior; int nPtsInterior; const int* ptsHalo; int nPtsHalo;
     double* tauOut;              // nCells or null: tauQGD as the model reports it (models 1n and 2), for qgd_qgdfoam_get
     // face fluxes, 5 doubles per face (k = Fm, FUx, FUy, FUz, FE), SoA:
     //   internal face f : FI[k][slot(f)]            boundary face b : FB[k][b]
@@ -133,7 +136,9 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 // ev (optional): 6 events recorded around k_points, k_face_flux, k_cell_update (begin/end pairs)
 // hooks (optional, multi-GPU): midStep runs after the qgdFlux re-evaluation of p_b (exchange of halo p_b),
 // beforeDt runs before the time-step kernel (all-reduce of the Courant max / tau min)
-struct StepHooks { std::function<void()> midStep, beforeDt; };
+// waitHalo: called right before the first kernel that reads halo copies (the packed exchange of the previous step may
+// still be in flight on the communication stream while the interior points are gathered)
+struct StepHooks { std::function<void()> midStep, beforeDt, waitHalo; };
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr,
                const PipeView* pipe = nullptr, int gridPipe = 0);
