@@ -220,14 +220,15 @@ def run_product(args):
     peak, peak_src = peaks()
     face_ms = kt["face_ms"] / max(kt["steps"], 1)
     pipe = s.get_pipeline()
-    kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else "k_face_flux"
+    tma = os.environ.get("QGD_FACE_TMA", "2") != "0" and mesh.n_faces % 2 == 0
+    kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else ("k_face_flux_tma" if tma else "k_face_flux")
     kbytes = ab["face"] + ab["cell"] if pipe["mode"] == 1 else ab["face"]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "face_flux_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-            if tj.get("n_cells") == mesh.n_cells and kname in tj.get("kernel", ""):
+            if tj.get("n_cells") == mesh.n_cells and kname + "<" in tj.get("kernel", ""):
                 traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": kbytes / (face_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": kbytes / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
