@@ -1,0 +1,316 @@
+"""OpenFOAM case ingestion and write-back (ASCII): the on-disk half of the drop-in.
+
+Reads what the reference solvers read through OpenFOAM's IO layer
+  constant/polyMesh/{points,faces,owner,neighbour,boundary}      (createMesh.H)
+  <time>/U, T, p, alphaQGD                                        (QGDFoam/createFields.H:24-35, QGDCoeffs.C:119-160)
+and writes volScalarField / volVectorField files back, so a case prepared for QGDFoam / QHDFoam can be stepped by
+libqgd_b200 and inspected with the usual tools.  Host-side harness code (numpy); geometry comes from
+PolyMesh.compute_geometry() [OF-v2312 semantics].
+
+Supported subset: ASCII format, label/scalar lists in the `N ( ... )` and `N{v}` forms, faces as `n(v0 v1 ...)`,
+boundary patches of type patch | wall | empty | processor | wedge | symmetry*, patch fields fixedValue | zeroGradient |
+fixedGradient | qgdFlux | qhdFlux | empty | calculated | slip (-> unsupported by the device BC set), `uniform` and
+`nonuniform List<...>` values.  Binary files and `#include` directives are rejected with a clear error.
+"""
+from __future__ import annotations
+
+import os
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .polymesh import PATCH_EMPTY, PATCH_GENERIC, PATCH_PROCESSOR, PATCH_WEDGE, Patch, PolyMesh
+
+_KINDS = {"patch": PATCH_GENERIC, "wall": PATCH_GENERIC, "symmetry": PATCH_GENERIC, "symmetryPlane": PATCH_GENERIC,
+          "empty": PATCH_EMPTY, "processor": PATCH_PROCESSOR, "wedge": PATCH_WEDGE}
+_KIND_WORD = {PATCH_GENERIC: "patch", PATCH_EMPTY: "empty", PATCH_PROCESSOR: "processor", PATCH_WEDGE: "wedge"}
+
+
+class FoamFormatError(ValueError):
+    pass
+
+
+def _strip_comments(text: str) -> str:
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return re.sub(r"//[^\n]*", "", text)
+
+
+def _split_header(text: str) -> Tuple[Dict[str, str], str]:
+    """FoamFile header dictionary and the remaining body."""
+    text = _strip_comments(text)
+    m = re.search(r"FoamFile\s*\{(.*?)\}", text, flags=re.S)
+    hdr: Dict[str, str] = {}
+    body = text
+    if m:
+        for k, v in re.findall(r"(\w+)\s+([^;]+);", m.group(1)):
+            hdr[k] = v.strip().strip('"')
+        body = text[m.end():]
+    if hdr.get("format", "ascii") != "ascii":
+        raise FoamFormatError("binary OpenFOAM files are not supported (convert with foamFormatConvert)")
+    if "#include" in body:
+        raise FoamFormatError("#include directives are not supported")
+    return hdr, body
+
+
+def _read_list_body(body: str) -> Tuple[int, str]:
+    """`N ( ... )` -> (N, inner text)"""
+    m = re.search(r"(\d+)\s*\(", body)
+    if not m:
+        raise FoamFormatError("expected a list `N ( ... )`")
+    n = int(m.group(1))
+    start = m.end()
+    end = body.rindex(")")
+    return n, body[start:end]
+
+
+def read_points(path: str) -> np.ndarray:
+    _, body = _split_header(open(path).read())
+    n, inner = _read_list_body(body)
+    vals = np.array(re.sub(r"[()]", " ", inner).split(), dtype=np.float64)
+    if vals.size != 3 * n:
+        raise FoamFormatError(f"{path}: expected {n} points")
+    return np.ascontiguousarray(vals.reshape(n, 3))
+
+
+def read_labels(path: str) -> np.ndarray:
+    _, body = _split_header(open(path).read())
+    n, inner = _read_list_body(body)
+    vals = np.array(inner.split(), dtype=np.int64)
+    if vals.size != n:
+        raise FoamFormatError(f"{path}: expected {n} labels")
+    return vals.astype(np.int32)
+
+
+def read_faces(path: str) -> Tuple[np.ndarray, np.ndarray]:
+    _, body = _split_header(open(path).read())
+    n, inner = _read_list_body(body)
+    offs = [0]
+    verts: List[int] = []
+    for cnt, vs in re.findall(r"(\d+)\s*\(([^()]*)\)", inner):
+        v = vs.split()
+        if len(v) != int(cnt):
+            raise FoamFormatError(f"{path}: face with {cnt} vertices lists {len(v)}")
+        verts.extend(int(x) for x in v)
+        offs.append(len(verts))
+    if len(offs) - 1 != n:
+        raise FoamFormatError(f"{path}: expected {n} faces, found {len(offs) - 1}")
+    return np.asarray(offs, np.int32), np.asarray(verts, np.int32)
+
+
+def read_boundary(path: str) -> List[Patch]:
+    _, body = _split_header(open(path).read())
+    n, inner = _read_list_body(body)
+    patches = []
+    for name, blk in re.findall(r"(\w+)\s*\{([^{}]*)\}", inner):
+        d = {k: v.strip() for k, v in re.findall(r"(\w+)\s+([^;]+);", blk)}
+        typ = d.get("type", "patch")
+        if typ not in _KINDS:
+            raise FoamFormatError(f"{path}: patch {name} has unsupported type {typ}")
+        patches.append(Patch(name, _KINDS[typ], int(d["startFace"]), int(d["nFaces"]), int(d.get("neighbProcNo", -1))))
+    if len(patches) != n:
+        raise FoamFormatError(f"{path}: expected {n} patches, found {len(patches)}")
+    return patches
+
+
+def read_polymesh(case_dir: str, region: str = "") -> PolyMesh:
+    """constant/polyMesh -> PolyMesh with fvMesh geometry."""
+    d = os.path.join(case_dir, "constant", region, "polyMesh")
+    pts = read_points(os.path.join(d, "points"))
+    offs, verts = read_faces(os.path.join(d, "faces"))
+    owner = read_labels(os.path.join(d, "owner"))
+    neighbour = read_labels(os.path.join(d, "neighbour"))
+    patches = read_boundary(os.path.join(d, "boundary"))
+    n_cells = int(max(owner.max(), neighbour.max() if neighbour.size else -1)) + 1
+    if owner.size != offs.size - 1:
+        raise FoamFormatError("owner and faces disagree on the number of faces")
+    if neighbour.size and not (owner[:neighbour.size] < neighbour).all():
+        raise FoamFormatError("polyMesh is not in upper-triangular order (owner < neighbour)")
+    mesh = PolyMesh(points=pts, face_offsets=offs, face_verts=verts, owner=owner, neighbour=neighbour, patches=patches,
+                    n_cells=n_cells)
+    mesh.compute_geometry()
+    # geometricD: a direction is solved unless an `empty` patch removes it  [OF polyMesh::geometricD]
+    gd = np.ones(3, np.int32)
+    nI = mesh.n_internal
+    for p in patches:
+        if p.kind == PATCH_EMPTY and p.size:
+            nf = mesh.Sf[p.start:p.start + p.size] / mesh.magSf[p.start:p.start + p.size, None]
+            gd[int(np.argmax(np.abs(nf).mean(0)))] = -1
+    mesh.geometric_d = gd
+    del nI
+    return mesh
+
+
+# ------------------------------------------------------------------------------------------------ writers
+_HDR = """/*--------------------------------*- C++ -*----------------------------------*\\
+| qgd-b200 case writer (OpenFOAM ASCII format)                                |
+\\*---------------------------------------------------------------------------*/
+FoamFile
+{{
+    version     2.0;
+    format      ascii;
+    class       {cls};
+    location    "{loc}";
+    object      {obj};
+}}
+// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //
+
+"""
+
+
+def _fmt(v: float) -> str:
+    return repr(float(v))
+
+
+def write_polymesh(mesh: PolyMesh, case_dir: str) -> None:
+    d = os.path.join(case_dir, "constant", "polyMesh")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "points"), "w") as f:
+        f.write(_HDR.format(cls="vectorField", loc="constant/polyMesh", obj="points"))
+        f.write(f"{mesh.n_points}\n(\n" + "\n".join(f"({_fmt(p[0])} {_fmt(p[1])} {_fmt(p[2])})" for p in mesh.points) + "\n)\n")
+    with open(os.path.join(d, "faces"), "w") as f:
+        f.write(_HDR.format(cls="faceList", loc="constant/polyMesh", obj="faces"))
+        o = mesh.face_offsets
+        f.write(f"{mesh.n_faces}\n(\n" + "\n".join(
+            f"{o[i + 1] - o[i]}(" + " ".join(str(int(v)) for v in mesh.face_verts[o[i]:o[i + 1]]) + ")" for i in range(mesh.n_faces)) + "\n)\n")
+    for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
+        with open(os.path.join(d, name), "w") as f:
+            f.write(_HDR.format(cls="labelList", loc="constant/polyMesh", obj=name))
+            f.write(f"{arr.size}\n(\n" + "\n".join(str(int(v)) for v in arr) + "\n)\n")
+    with open(os.path.join(d, "boundary"), "w") as f:
+        f.write(_HDR.format(cls="polyBoundaryMesh", loc="constant/polyMesh", obj="boundary"))
+        f.write(f"{len(mesh.patches)}\n(\n")
+        for p in mesh.patches:
+            f.write(f"    {p.name}\n    {{\n        type            {_KIND_WORD[p.kind]};\n        nFaces          {p.size};\n"
+                    f"        startFace       {p.start};\n    }}\n")
+        f.write(")\n")
+
+
+@dataclass
+class VolField:
+    """GeometricField<Type, fvPatchField, volMesh> as read from a time directory."""
+    name: str
+    ncmpt: int
+    internal: np.ndarray                                   # (nCells,) or (nCells,3)
+    patch_types: Dict[str, str] = field(default_factory=dict)
+    patch_values: Dict[str, np.ndarray] = field(default_factory=dict)      # value entry, expanded to the patch size
+    patch_gradients: Dict[str, np.ndarray] = field(default_factory=dict)   # gradient entry
+    dimensions: str = "[0 0 0 0 0 0 0]"
+
+
+def _parse_value(txt: str, n: int, ncmpt: int) -> np.ndarray:
+    txt = txt.strip()
+    shape = (n, ncmpt) if ncmpt > 1 else (n,)
+    if txt.startswith("uniform"):
+        vals = np.array(re.sub(r"[()]", " ", txt[len("uniform"):]).split(), dtype=np.float64)
+        if vals.size != ncmpt:
+            raise FoamFormatError(f"uniform value with {vals.size} components, expected {ncmpt}")
+        return np.ascontiguousarray(np.broadcast_to(vals if ncmpt > 1 else vals[0], shape)).copy()
+    m = re.match(r"nonuniform\s+List<\w+>\s*(\d+)\s*\((.*)\)\s*$", txt, flags=re.S)
+    if not m:
+        raise FoamFormatError(f"cannot parse field value: {txt[:60]}...")
+    cnt = int(m.group(1))
+    vals = np.array(re.sub(r"[()]", " ", m.group(2)).split(), dtype=np.float64)
+    if cnt != n or vals.size != n * ncmpt:
+        raise FoamFormatError(f"nonuniform list of {cnt} entries, expected {n}")
+    return np.ascontiguousarray(vals.reshape(shape))
+
+
+def _entries(block: str) -> Dict[str, str]:
+    """`key value;` entries of a dictionary block (values may span lines and contain parentheses)."""
+    out, i = {}, 0
+    for m in re.finditer(r"(\w+)\s+((?:[^;{}]|\n)*?);", block):
+        out[m.group(1)] = m.group(2).strip()
+    del i
+    return out
+
+
+def read_field(path: str, mesh: PolyMesh) -> VolField:
+    hdr, body = _split_header(open(path).read())
+    cls = hdr.get("class", "volScalarField")
+    ncmpt = {"volScalarField": 1, "volVectorField": 3}.get(cls)
+    if ncmpt is None:
+        raise FoamFormatError(f"{path}: unsupported field class {cls}")
+    mb = re.search(r"boundaryField\s*\{", body)
+    if not mb:
+        raise FoamFormatError(f"{path}: no boundaryField")
+    top = _entries(body[:mb.start()])
+    fld = VolField(os.path.basename(path), ncmpt, _parse_value(top["internalField"], mesh.n_cells, ncmpt),
+                   dimensions=top.get("dimensions", "[0 0 0 0 0 0 0]"))
+    depth, j = 1, mb.end()
+    while depth and j < len(body):
+        depth += {"{": 1, "}": -1}.get(body[j], 0)
+        j += 1
+    inner = body[mb.end():j - 1]
+    sizes = {p.name: p.size for p in mesh.patches}
+    for name, blk in re.findall(r"(\w+)\s*\{([^{}]*)\}", inner):
+        if name not in sizes:
+            raise FoamFormatError(f"{path}: boundaryField entry {name} is not a patch of the mesh")
+        e = _entries(blk)
+        fld.patch_types[name] = e.get("type", "calculated")
+        if "value" in e:
+            fld.patch_values[name] = _parse_value(e["value"], sizes[name], ncmpt)
+        if "gradient" in e:
+            fld.patch_gradients[name] = _parse_value(e["gradient"], sizes[name], ncmpt)
+    missing = [p.name for p in mesh.patches if p.name not in fld.patch_types]
+    if missing:
+        raise FoamFormatError(f"{path}: no boundaryField entry for patches {missing}")
+    return fld
+
+
+def write_field(path: str, mesh: PolyMesh, name: str, internal: np.ndarray, patch_types: Dict[str, str],
+                boundary: Optional[np.ndarray] = None, dimensions: str = "[0 0 0 0 0 0 0]") -> None:
+    """Write a volScalarField / volVectorField; `boundary` (nBnd[,3]) supplies `value` entries."""
+    internal = np.asarray(internal, np.float64)
+    ncmpt = 1 if internal.ndim == 1 else internal.shape[1]
+    cls, typ = ("volScalarField", "scalar") if ncmpt == 1 else ("volVectorField", "vector")
+
+    def lst(a):
+        if ncmpt == 1:
+            return f"nonuniform List<{typ}> {a.shape[0]}\n(\n" + "\n".join(_fmt(v) for v in a) + "\n)"
+        return f"nonuniform List<{typ}> {a.shape[0]}\n(\n" + "\n".join("(" + " ".join(_fmt(x) for x in v) + ")" for v in a) + "\n)"
+
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(_HDR.format(cls=cls, loc=os.path.basename(os.path.dirname(path)), obj=name))
+        f.write(f"dimensions      {dimensions};\n\ninternalField   {lst(internal)};\n\nboundaryField\n{{\n")
+        nI = mesh.n_internal
+        for p in mesh.patches:
+            t = patch_types.get(p.name, "empty" if p.kind == PATCH_EMPTY else "calculated")
+            f.write(f"    {p.name}\n    {{\n        type            {t};\n")
+            if boundary is not None and p.kind != PATCH_EMPTY and p.size:
+                f.write(f"        value           {lst(np.asarray(boundary)[p.start - nI:p.start - nI + p.size])};\n")
+            f.write("    }\n")
+        f.write("}\n")
+
+
+# ------------------------------------------------------------------------------------------------ solver glue
+_BC_CODE = {"fixedValue": 0, "zeroGradient": 1, "fixedGradient": 2, "qgdFlux": 3, "calculated": 4, "qhdFlux": 5, "empty": 1}
+
+
+def bc_arrays(mesh: PolyMesh, fld: VolField) -> Tuple[np.ndarray, np.ndarray]:
+    """(kinds per patch, values per boundary face) in the form qgd_qgdfoam_set_bcs / qgd_qhdfoam_set_bcs take:
+    fixedValue faces carry the value, fixedGradient / qhdFlux faces the gradient."""
+    kinds = np.zeros(len(mesh.patches), np.int32)
+    nB, nI = mesh.n_bnd, mesh.n_internal
+    vals = np.zeros((nB, fld.ncmpt) if fld.ncmpt > 1 else nB)
+    for i, p in enumerate(mesh.patches):
+        t = fld.patch_types[p.name]
+        if t not in _BC_CODE:
+            raise FoamFormatError(f"patch field type {t} of {fld.name} on {p.name} is outside the device-native set")
+        kinds[i] = _BC_CODE[t]
+        sl = slice(p.start - nI, p.start - nI + p.size)
+        if t == "fixedValue":
+            vals[sl] = fld.patch_values[p.name]
+        elif t in ("fixedGradient", "qhdFlux") and p.name in fld.patch_gradients:
+            vals[sl] = fld.patch_gradients[p.name]
+    return kinds, vals
+
+
+def read_case_fields(case_dir: str, mesh: PolyMesh, time: str = "0", names=("U", "T", "p")) -> Dict[str, VolField]:
+    out = {n: read_field(os.path.join(case_dir, time, n), mesh) for n in names}
+    a = os.path.join(case_dir, time, "alphaQGD")
+    if os.path.exists(a):                                   # QGDCoeffs.C:119-143
+        out["alphaQGD"] = read_field(a, mesh)
+    return out

@@ -273,3 +273,26 @@ def test_error_behaviour_matches_reference_messages(qgd):
         s = qgd.QGDFoam(dm, R=1.0, Cp=3.5)
         s.step(1)
     assert e.value.code == qgd.ERR_STATE
+
+
+def test_case_read_from_disk_runs_like_the_in_memory_case(qgd, oracle_mod, tmp_path):
+    """polyMesh + 0/U,T,p written in OpenFOAM ASCII format, read back with foamcase and stepped on the device."""
+    from qgdsolver_b200 import foamcase as fc
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="mixed")
+    m = c.mesh
+    names = [p.name for p in m.patches]
+    code = {0: "fixedValue", 1: "zeroGradient", 3: "qgdFlux"}
+    fc.write_polymesh(m, str(tmp_path))
+    fc.write_field(str(tmp_path / "0" / "U"), m, "U", c.U0, {n: code[int(k)] for n, k in zip(names, c.bcU)}, c.bvU)
+    fc.write_field(str(tmp_path / "0" / "T"), m, "T", c.T0, {n: code[int(k)] for n, k in zip(names, c.bcT)}, c.bvT)
+    fc.write_field(str(tmp_path / "0" / "p"), m, "p", c.p0, {n: code[int(k)] for n, k in zip(names, c.bcP)}, c.bvP)
+    mesh = fc.read_polymesh(str(tmp_path))
+    f = fc.read_case_fields(str(tmp_path), mesh)
+    (kU, vU), (kT, vT), (kP, vP) = (fc.bc_arrays(mesh, f[n]) for n in ("U", "T", "p"))
+    c2 = cases.Case(mesh, f["U"].internal, f["T"].internal, f["p"].internal, kU, kT, kP, vU, vT, vP, gas=c.gas, dt=c.dt)
+    s = c2.make_solver(qgd)
+    o = c.make_oracle(oracle_mod)
+    s.step(30)
+    c.oracle_step(o, 30)
+    for fld in ("rho", "rhoU", "rhoE"):
+        assert rel_linf(s.get(fld), o.get(fld)) < TOL_STEP
