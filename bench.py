@@ -272,6 +272,39 @@ def run_product(args):
     print(json.dumps(line), flush=True)
 
 
+def run_qgd2d(args):
+    """Extra line (not the driver's default): BASELINE configs[1]-like, QGDFoam on a 2D n x n hex mesh (one cell thick, empty
+    front/back), explicit, FP64.  Algorithmic bytes per step: 104 nC + 184 nF + 148 nP_used."""
+    import torch
+    import cases
+    from qgdsolver_b200 import api
+    torch.cuda.set_device(0)
+    api.init(0)
+    n = args.qhd_size
+    mesh = cases.pm.hex_box(n, n, 1, lengths=(1.0, 1.0, 1.0 / n), patch_kinds={"zMin": "empty", "zMax": "empty"})
+    c = cases._with_bcs(mesh, "zg", GAS, 2.0e-4 * (256.0 / n))
+    s = c.make_solver(api)
+    s.step(args.warmup)
+    api.synchronize()
+    reps = []
+    for _ in range(3):                       # state (~0.3 GB) is larger than L2; no flush
+        api.timer_begin()
+        s.step(args.steps)
+        reps.append(api.timer_end() / args.steps)
+    ms = min(reps)
+    nC, nI = mesh.n_cells, mesh.n_internal
+    alg = 104 * nC + 184 * nI + 148 * (mesh.n_points // 2)
+    peak, src = peaks()
+    line = {"metric": METRIC, "value": nC / ms / 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QGDFoam 2D hex mesh {n}x{n} ({nC} cells, empty front/back), explicit, FP64",
+                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False},
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes_per_step": alg, "peak_source": src},
+            "gpu_launches": int(s.launch_count())}
+    print(json.dumps(line), flush=True)
+
+
 def run_qhd(args):
     """Extra line (not the driver's default): BASELINE configs[2], QHDFoam 2D differentially heated cavity, n x n cells,
     pressure PCG on the device.  A step = one QHDFoam.C:83-139 pass including the whole PCG solve."""
@@ -316,7 +349,8 @@ def main():
     ap.add_argument("--ref-size", type=int, default=64, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--case", default="qgd3d", choices=["qgd3d", "qhd2d"], help="qgd3d = BASELINE configs[3] (default); qhd2d = configs[2]")
+    ap.add_argument("--case", default="qgd3d", choices=["qgd3d", "qgd2d", "qhd2d"],
+                    help="qgd3d = BASELINE configs[3] (default); qgd2d = a configs[1]-sized 2D mesh; qhd2d = configs[2]")
     ap.add_argument("--precond", default="diagonal")
     ap.add_argument("--p-tol", type=float, default=1e-8)
     ap.add_argument("--p-rel-tol", type=float, default=0.0)
@@ -327,6 +361,8 @@ def main():
         args.warmup = 3
     if args.case == "qhd2d":
         run_qhd(args)
+    elif args.case == "qgd2d":
+        run_qgd2d(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -893,6 +893,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         s->sc.upload(std::vector<StepScalars>(1, sc), g_stream);
         if (const char* v = getenv("QGD_FACE_VARIANT")) setFaceVariant(atoi(v));
         if (const char* v = getenv("QGD_FACE_TMA")) setFaceTma(atoi(v));
+        if (const char* v = getenv("QGD_CELL_TMA")) setCellTma(atoi(v));
         s->gridFaces = faceKernelGrid();
         *out = s.release();
     });

@@ -148,6 +148,7 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
 int faceKernelGrid();
 int pipelineKernelGrid(int cfEllW);
 void setFaceVariant(int v);
+void setCellTma(int on);      // env QGD_CELL_TMA
 void setFaceTma(int on);      // env QGD_FACE_TMA: TMA-staged face kernel (default) vs register-prefetch kernel   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
 } // namespace qgd
