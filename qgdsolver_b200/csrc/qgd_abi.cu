@@ -719,7 +719,8 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         {
             int maxRow = 0;
             for (int c = 0; c < h.nCells; ++c) maxRow = std::max(maxRow, h.cfOff[c + 1] - h.cfOff[c]);
-            const int W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+            int W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+            if (const char* v = getenv("QGD_ELL_MAXW")) W = std::min(W, std::max(4, atoi(v)) <= 4 ? 4 : (atoi(v) <= 6 ? 6 : 8));   // test hook: force CSR tails
             m->cfEllW = W;
             std::vector<int> ell((size_t)W * h.nCells, -1), tailOff(h.nCells + 1, 0), tail;
             for (int c = 0; c < h.nCells; ++c) {
@@ -737,7 +738,8 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         {
             int maxRow = 0;
             for (int p = 0; p < h.nPoints; ++p) maxRow = std::max(maxRow, h.pcOff[p + 1] - h.pcOff[p]);
-            const int W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+            int W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+            if (const char* v = getenv("QGD_ELL_MAXW")) W = std::min(W, std::max(4, atoi(v)) <= 4 ? 4 : (atoi(v) <= 6 ? 6 : 8));   // test hook: force CSR tails
             m->pcEllW = W;
             std::vector<int> ell((size_t)W * h.nPoints, 0), cnt(h.nPoints, 0), tailOff(h.nPoints + 1, 0), tailC;
             std::vector<double> ellW((size_t)W * h.nPoints, 0.0), tailW;
@@ -894,6 +896,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         if (const char* v = getenv("QGD_FACE_VARIANT")) setFaceVariant(atoi(v));
         if (const char* v = getenv("QGD_FACE_TMA")) setFaceTma(atoi(v));
         if (const char* v = getenv("QGD_CELL_TMA")) setCellTma(atoi(v));
+        if (const char* v = getenv("QGD_FACE_L2HINT")) setFaceL2Hint(atoi(v));
         s->gridFaces = faceKernelGrid();
         *out = s.release();
     });

@@ -44,6 +44,48 @@ __device__ __forceinline__ RecP loadP(const SolverView& sv, int i)
     const size_t n = sv.nPoints;
     return RecP{__ldg(p), __ldg(p + n), __ldg(p + 2 * n), __ldg(p + 3 * n), __ldg(p + 4 * n), __ldg(p + 5 * n)};
 }
+// L2 cache-policy variants of the gathers (k_face_flux_tma<.., HINT & 2>): cell / point state is re-read by later tiles
+// (the y- and z-neighbours of a cell come back as owners 256 / 65536 cells later on a hex box) while the face constants
+// and the fluxes stream through once, so the state is tagged evict_last and the streams evict_first.
+__device__ __forceinline__ unsigned long long l2PolicyEvictLast()
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2PolicyEvictFirst()
+{
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double ldgKeep(const double* p, unsigned long long pol)
+{
+    double v;
+    asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ RecA loadAKeep(const SolverView& sv, int i, unsigned long long pol)
+{
+    const double* p = sv.S + i;
+    const size_t n = sv.nCells;
+    return RecA{ldgKeep(p, pol), ldgKeep(p + n, pol), ldgKeep(p + 2 * n, pol), ldgKeep(p + 3 * n, pol), ldgKeep(p + 4 * n, pol),
+                ldgKeep(p + 5 * n, pol), ldgKeep(p + 6 * n, pol), ldgKeep(p + 7 * n, pol)};
+}
+__device__ __forceinline__ RecB loadBKeep(const SolverView& sv, int i, unsigned long long pol)
+{
+    const double* p = sv.S + 8 * (size_t)sv.nCells + i;
+    const size_t n = sv.nCells;
+    return RecB{ldgKeep(p, pol), ldgKeep(p + n, pol), ldgKeep(p + 2 * n, pol), ldgKeep(p + 3 * n, pol), ldgKeep(p + 4 * n, pol),
+                ldgKeep(p + 5 * n, pol), ldgKeep(p + 6 * n, pol), ldgKeep(p + 7 * n, pol)};
+}
+__device__ __forceinline__ RecP loadPKeep(const SolverView& sv, int i, unsigned long long pol)
+{
+    const double* p = sv.P + i;
+    const size_t n = sv.nPoints;
+    return RecP{ldgKeep(p, pol), ldgKeep(p + n, pol), ldgKeep(p + 2 * n, pol), ldgKeep(p + 3 * n, pol), ldgKeep(p + 4 * n, pol),
+                ldgKeep(p + 5 * n, pol)};
+}
 // 8 fields of cell i starting at field k0
 __device__ __forceinline__ void storeRec(const SolverView& sv, int k0, int i, const double (&v)[8])
 {
@@ -617,17 +659,23 @@ __device__ __forceinline__ void lsqGrads(const FaceView& fv, const SolverView& s
     }
 }
 
-template <bool ADJUST, bool GEOM, bool SMEM = false, bool LSQ = false>
+template <bool ADJUST, bool GEOM, bool SMEM = false, bool LSQ = false, int HINT = 0>
 __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv, const SolverView& sv, int f, size_t slot, int P, int N,
-                                            int flagsCur, const int4& v, double& coMax, double& tauMin, const double* sd = nullptr, int li = 0)
+                                            int flagsCur, const int4& v, double& coMax, double& tauMin, const double* sd = nullptr, int li = 0,
+                                            unsigned long long polKeep = 0ull)
 {
     const size_t nF = fv.nF;
-    const RecA aP = loadA(sv, P), aN = loadA(sv, N);
-    const RecB bP = loadB(sv, P), bN = loadB(sv, N);
+    const RecA aP = (HINT & 2) ? loadAKeep(sv, P, polKeep) : loadA(sv, P), aN = (HINT & 2) ? loadAKeep(sv, N, polKeep) : loadA(sv, N);
+    const RecB bP = (HINT & 2) ? loadBKeep(sv, P, polKeep) : loadB(sv, P), bN = (HINT & 2) ? loadBKeep(sv, N, polKeep) : loadB(sv, N);
     RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
     if (flagsCur & FF_POINTS) {
-        d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
-        d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
+        if (HINT & 2) {
+            d1 = recDiff(loadPKeep(sv, v.x, polKeep), loadPKeep(sv, v.z, polKeep));
+            d2 = recDiff(loadPKeep(sv, v.y, polKeep), loadPKeep(sv, v.w, polKeep));
+        } else {
+            d1 = recDiff(loadP(sv, v.x), loadP(sv, v.z));
+            d2 = recDiff(loadP(sv, v.y), loadP(sv, v.w));
+        }
     }
     const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
     double g1[3], g2[3], gp[3], Sf[3];
@@ -695,7 +743,12 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     }
     double Fm, FU[3], FE, phiw;
     qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
-    sv.FI[0][slot] = Fm; sv.FI[1][slot] = FU[0]; sv.FI[2][slot] = FU[1]; sv.FI[3][slot] = FU[2]; sv.FI[4][slot] = FE;
+    if (HINT & 1) {                                         // streamed once: evict-first stores
+        __stcs(&sv.FI[0][slot], Fm); __stcs(&sv.FI[1][slot], FU[0]); __stcs(&sv.FI[2][slot], FU[1]); __stcs(&sv.FI[3][slot], FU[2]);
+        __stcs(&sv.FI[4][slot], FE);
+    } else {
+        sv.FI[0][slot] = Fm; sv.FI[1][slot] = FU[0]; sv.FI[2][slot] = FU[1]; sv.FI[3][slot] = FU[2]; sv.FI[4][slot] = FE;
+    }
     if (ADJUST) {                                           // QGDCourantNo.H:38-50
         const double ms = SMEM ? sd[14 * kTmaTile + li] : __ldg(&fv.magSf[f]);
         const double Unf = s.U[0] * (Sf[0] / ms) + s.U[1] * (Sf[1] / ms) + s.U[2] * (Sf[2] / ms);
@@ -816,6 +869,14 @@ __device__ __forceinline__ void bulkLoad(void* dstSmem, const void* srcGlobal, u
                  : "memory");
 }
 
+__device__ __forceinline__ void bulkLoadHint(void* dstSmem, const void* srcGlobal, unsigned bytes, unsigned long long* bar, unsigned long long pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smemAddr(dstSmem)),
+                 "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar)), "l"(pol)
+                 : "memory");
+}
+
 template <bool ADJUST> struct TmaStage {
     static constexpr int kDoubles = ADJUST ? 15 : 14;
     static constexpr int kBytes = kTmaTile * (3 * 4 + 16 + 8 * kDoubles);
@@ -823,12 +884,16 @@ template <bool ADJUST> struct TmaStage {
     static constexpr int oVtx = 0, oD = kTmaTile * 16, oOwn = oD + kTmaTile * 8 * kDoubles, oNei = oOwn + kTmaTile * 4, oFlags = oNei + kTmaTile * 4;
 };
 
-template <bool ADJUST>
-__device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* stage, unsigned long long* bar, int tile)
+template <bool ADJUST, bool STREAM = false>
+__device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* stage, unsigned long long* bar, int tile, unsigned long long pol = 0ull)
 {
     using L = TmaStage<ADJUST>;
     const size_t f0 = (size_t)tile * kTmaTile, nF = fv.nF;
     mbarExpectTx(bar, (unsigned)L::kBytes);
+    auto bulkLoad = [pol](void* d, const void* s, unsigned b, unsigned long long* m) {
+        if (STREAM) bulkLoadHint(d, s, b, m, pol);
+        else qgd::bulkLoad(d, s, b, m);
+    };
     bulkLoad(stage + L::oVtx, fv.vtx + f0, kTmaTile * 16, bar);
     double* d = reinterpret_cast<double*>(stage + L::oD);
 #pragma unroll
@@ -843,9 +908,11 @@ __device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* 
     bulkLoad(stage + L::oFlags, fv.flags + f0, kTmaTile * 4, bar);
 }
 
-template <bool ADJUST, int NST>
+template <bool ADJUST, int NST, int HINT = 0>
 __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceView fv, SolverView sv)
 {
+    const unsigned long long polKeep = (HINT & 2) ? l2PolicyEvictLast() : 0ull;
+    const unsigned long long polStream = (HINT & 1) ? l2PolicyEvictFirst() : 0ull;
     using L = TmaStage<ADJUST>;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NST];
@@ -862,13 +929,14 @@ __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceVie
     if (threadIdx.x == 0) {                                  // prologue: NST-1 tiles in flight
 #pragma unroll
         for (int q = 0; q < NST - 1; ++q)
-            if (tile + q * (int)gridDim.x < nTiles) tmaIssueTile<ADJUST>(fv, smem + q * L::kBytes, &bars[q], tile + q * gridDim.x);
+            if (tile + q * (int)gridDim.x < nTiles)
+                tmaIssueTile<ADJUST, (HINT & 1) != 0>(fv, smem + q * L::kBytes, &bars[q], tile + q * gridDim.x, polStream);
     }
     for (int it = 0; tile < nTiles; ++it, tile += gridDim.x) {
         const int st = it % NST;
         const int next = tile + (NST - 1) * (int)gridDim.x;    // refills the stage consumed in the previous iteration
         const int sn = (it + NST - 1) % NST;
-        if (threadIdx.x == 0 && next < nTiles) tmaIssueTile<ADJUST>(fv, smem + sn * L::kBytes, &bars[sn], next);
+        if (threadIdx.x == 0 && next < nTiles) tmaIssueTile<ADJUST, (HINT & 1) != 0>(fv, smem + sn * L::kBytes, &bars[sn], next, polStream);
         mbarWait(&bars[st], (unsigned)((it / NST) & 1));
         const unsigned char* sg = smem + st * L::kBytes;
         const int li = threadIdx.x;
@@ -876,7 +944,8 @@ __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceVie
         const int P = reinterpret_cast<const int*>(sg + L::oOwn)[li], N = reinterpret_cast<const int*>(sg + L::oNei)[li];
         const int flags = reinterpret_cast<const int*>(sg + L::oFlags)[li];
         const int4 v = reinterpret_cast<const int4*>(sg + L::oVtx)[li];
-        faceFluxOne<ADJUST, false, true>(k, fv, sv, f, (size_t)f, P, N, flags, v, coMax, tauMin, reinterpret_cast<const double*>(sg + L::oD), li);
+        faceFluxOne<ADJUST, false, true, false, HINT>(k, fv, sv, f, (size_t)f, P, N, flags, v, coMax, tauMin,
+                                                      reinterpret_cast<const double*>(sg + L::oD), li, polKeep);
         __syncthreads();                                     // every thread is done with this stage before it is refilled
     }
     // remainder (< one tile): plain loads, one CTA
@@ -1526,12 +1595,28 @@ const FaceVariant kFaceVariants[] = {mkVariant<256, 1>(), mkVariant<256, 2>(), m
                                      mkVariant<128, 6>(), mkVariant<64, 12>(), mkVariant<256, 3>()};
 int g_faceVariant = 1;
 int g_faceTma = 2;          // stages of the TMA ring; QGD_FACE_TMA=0 selects the register-prefetch kernel, 3 a 3-stage ring
+int g_faceHint = 3;         // QGD_FACE_L2HINT bit 0: face constants / fluxes evict_first, bit 1: cell / point gathers evict_last (2-stage ring only)
+template <bool ADJUST> void launchTma2(int hint, int grid, cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv)
+{
+    const int sm = 2 * TmaStage<ADJUST>::kBytes;
+    switch (hint & 3) {
+    case 1: k_face_flux_tma<ADJUST, 2, 1><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    case 2: k_face_flux_tma<ADJUST, 2, 2><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    case 3: k_face_flux_tma<ADJUST, 2, 3><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    default: k_face_flux_tma<ADJUST, 2, 0><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    }
+}
+template <bool ADJUST, int HINT> void tmaSmemAttr()
+{
+    cudaFuncSetAttribute(k_face_flux_tma<ADJUST, 2, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TmaStage<ADJUST>::kBytes);
+}
 template <bool ADJUST, int NST> int tmaGridOf()
 {
     int dev = 0, sms = 148, perSM = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_face_flux_tma<ADJUST, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, NST * TmaStage<ADJUST>::kBytes);
+    if (NST == 2) { tmaSmemAttr<ADJUST, 1>(); tmaSmemAttr<ADJUST, 2>(); tmaSmemAttr<ADJUST, 3>(); }
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux_tma<ADJUST, NST>, kTmaTile, NST * TmaStage<ADJUST>::kBytes);
     return sms * (perSM < 1 ? 1 : perSM);
 }
@@ -1560,6 +1645,7 @@ template <int W> int cellTmaGrid()
 }
 void setCellTma(int on) { g_cellTma = on ? 1 : 0; }
 void setFaceTma(int on) { g_faceTma = on == 0 ? 0 : (on == 3 ? 3 : 2); }
+void setFaceL2Hint(int bits) { g_faceHint = bits & 3; }
 void setFaceVariant(int v) { if (v >= 0 && v < (int)(sizeof(kFaceVariants) / sizeof(kFaceVariants[0]))) g_faceVariant = v; }
 
 int faceKernelGrid()
@@ -1631,8 +1717,8 @@ static void launchFaceKernel(cudaStream_t st, const Consts& c, const FaceView& f
             if (adjust) k_face_flux_tma<true, 3><<<gridT, kTmaTile, 3 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
             else k_face_flux_tma<false, 3><<<gridT, kTmaTile, 3 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
         } else {
-            if (adjust) k_face_flux_tma<true, 2><<<gridT, kTmaTile, 2 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
-            else k_face_flux_tma<false, 2><<<gridT, kTmaTile, 2 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
+            if (adjust) launchTma2<true>(g_faceHint, gridT, st, c, fv, sv);
+            else launchTma2<false>(g_faceHint, gridT, st, c, fv, sv);
         }
     } else
         fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);

@@ -149,6 +149,7 @@ int faceKernelGrid();
 int pipelineKernelGrid(int cfEllW);
 void setFaceVariant(int v);
 void setCellTma(int on);      // env QGD_CELL_TMA
+void setFaceL2Hint(int bits); // env QGD_FACE_L2HINT: bit 0 = streamed constants / fluxes evict_first, bit 1 = state gathers evict_last
 void setFaceTma(int on);      // env QGD_FACE_TMA: TMA-staged face kernel (default) vs register-prefetch kernel   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
 
 } // namespace qgd

@@ -9,6 +9,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "qgd_pcg.cuh"
 
@@ -295,6 +296,7 @@ void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* uppe
         maxRow = std::max(maxRow, k);
     }
     W = maxRow <= 4 ? 4 : (maxRow <= 6 ? 6 : 8);
+    if (const char* v = getenv("QGD_ELL_MAXW")) W = std::min(W, atoi(v) <= 4 ? 4 : (atoi(v) <= 6 ? 6 : 8));   // test hook: force CSR tails
     std::vector<int> e((size_t)W * n), tOff(n + 1, 0), tEnc, level(n, 0), eFace((size_t)W * n, -1), tFace;
     std::vector<double> a((size_t)W * n, 0.0), tCoef;
     for (int c = 0; c < n; ++c) {

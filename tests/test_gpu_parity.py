@@ -296,3 +296,23 @@ def test_case_read_from_disk_runs_like_the_in_memory_case(qgd, oracle_mod, tmp_p
     c.oracle_step(o, 30)
     for fld in ("rho", "rhoU", "rhoE"):
         assert rel_linf(s.get(fld), o.get(fld)) < TOL_STEP
+
+
+def test_ell_tails_and_degenerate_sizes(qgd, oracle_mod):
+    """Edge cases of the device data layout: (a) QGD_ELL_MAXW=4 forces every stencil row of a hex / polyhedral mesh through
+    the CSR tail path (cells with more than W faces, points with more than W cells, PCG rows), run in a fresh process;
+    (b) the smallest meshes: a single cell (no internal face) and a 2-cell line."""
+    import os
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ell_tail_worker.py")
+    r = subprocess.run([sys.executable, worker], env=dict(os.environ, QGD_ELL_MAXW="4"), capture_output=True, text=True, timeout=600)
+    assert "TAILS_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    for n in ((1, 1, 1), (2, 1, 1)):
+        c = cases.case_hex3d(n=n, bcs="fixed")
+        o = c.make_oracle(oracle_mod)
+        s = c.make_solver(qgd)
+        c.oracle_step(o, 10)
+        s.step(10)
+        for f in ("rho", "rhoU", "rhoE"):
+            assert rel_linf(s.get(f), o.get(f)) < TOL_STEP
