@@ -141,10 +141,16 @@ typedef struct {
     double diff_tolerance, diff_rel_tol;
     int diff_max_iter;
     const char* diff_preconditioner;   /* "DIC" | "diagonal" | "none" ; NULL = "DIC"                */
+    /* QGD sub-dictionary entries of varScModel7 (varScModel7.C:96-119): cSc1 (default 1), minSc / maxSc
+     * (default -1 = off).  Read only when qgd_coeffs_model is "varScModel7"; "varScModel6" has none.  */
+    double varsc_cSc1, varsc_minSc, varsc_maxSc;
 } qgd_qgdfoam_desc;
 
 int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* desc, qgd_solver** out);
 int qgd_qgdfoam_destroy(qgd_solver* s);
+/* varScModel7 "constScCellSet" (varScModel7.C:143-158,246-254): polyMesh cell ids whose ScQGD is reset to the
+ * dictionary ScQGD after every sensor evaluation.  Call before qgd_qgdfoam_init_fields.  n = 0 clears the set. */
+int qgd_qgdfoam_set_const_sc_cells(qgd_solver* s, const int* cells, int n);
 /* boundary conditions of U, T, p per patch (0/U, 0/T, 0/p): kinds n_patches each (qgd_bc_kind),
  * fixed values per boundary face: U n_bnd*3, T n_bnd, p n_bnd (read only where the kind is fixedValue). */
 int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const int* bc_p,
@@ -170,7 +176,7 @@ typedef struct {
 } qgd_state_host;
 #define QGD_STATE_DOUBLES_PER_CELL 12
 int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, const qgd_state_host* out);
-/* fields: 0 rho, 1 rhoU(3), 2 rhoE, 3 U(3), 4 e, 5 p, 6 T, 7 c, 8 mu, 9 alpha, 10 tauQGD, 11 H.
+/* fields: 0 rho, 1 rhoU(3), 2 rhoE, 3 U(3), 4 e, 5 p, 6 T, 7 c, 8 mu, 9 alpha, 10 tauQGD, 11 H, 12 ScQGD.
  * cells: n_cells*k host buffer, bnd: n_bnd*k host buffer or NULL. */
 int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd);
 /* face flux of the last step: 0 phiJm, 1 momentum flux (phiJmU+phiP-phiPi, 3), 2 energy flux

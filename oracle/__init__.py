@@ -38,10 +38,11 @@ class QGDParams(C.Structure):
                 ("Hsref", C.c_double), ("mu", C.c_double), ("Pr", C.c_double), ("ScQGD", C.c_double),
                 ("PrQGD", C.c_double), ("implicitDiffusion", C.c_int), ("alphaEffGammaFactor", C.c_int),
                 ("energyDdtRhoEQuirk", C.c_int), ("qgdModel", C.c_int),
-                ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int)]
+                ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int),
+                ("varScCSc1", C.c_double), ("varScMinSc", C.c_double), ("varScMaxSc", C.c_double)]
 
 
-QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2}
+QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2, "varScModel6": 6, "varScModel7": 7}
 
 
 class QHDParams(C.Structure):
@@ -84,6 +85,7 @@ def lib():
         L.or_linear_interpolate.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp]
         L.or_qgd_init.argtypes = [C.c_void_p, C.POINTER(QGDParams), C.c_int, _ip, _ip, _ip, _dp, _dp, _dp,
                                   _dp, _dp, _dp, _dp, C.c_double]
+        L.or_qgd_set_const_sc_cells.argtypes = [C.c_void_p, _ip, C.c_int]
         L.or_qgd_step.restype = C.c_double
         L.or_qgd_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.or_qgd_deltaT.restype = C.c_double
@@ -117,10 +119,10 @@ def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-_CELL_K = {0: 1, 1: 3, 2: 1, 3: 3, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 1}
+_CELL_K = {0: 1, 1: 3, 2: 1, 3: 3, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 1, 12: 1}
 _FACE_K = {0: 1, 1: 3, 2: 3, 3: 3, 4: 1, 5: 1, 6: 1, 7: 1, 8: 9, 9: 3, 10: 3, 11: 3, 12: 1}
 CELL_FIELDS = {"rho": 0, "rhoU": 1, "rhoE": 2, "U": 3, "e": 4, "p": 5, "T": 6, "c": 7, "mu": 8, "alpha": 9,
-               "tauQGD": 10}
+               "tauQGD": 10, "ScQGD": 12}
 FACE_FIELDS = {"phiJm": 0, "phiJmU": 1, "phiP": 2, "phiPi": 3, "phiJmH": 4, "phiQ": 5, "phiPiU": 6,
                "tauQGDf": 7, "gradUf": 8, "gradef": 9, "gradRhof": 10, "gradPf": 11, "phiwStar": 12}
 
@@ -207,7 +209,10 @@ class Oracle:
 
     # ---- QGDFoam
     def qgd_init(self, params: QGDParams, bcU, bcT, bcP, bvU, bvT, bvP, U0, T0, p0, alphaQGD=None,
-                 deltaT=1e-4, scheme=FVSC_GAUSSVOLPOINT):
+                 deltaT=1e-4, scheme=FVSC_GAUSSVOLPOINT, const_sc_cells=None):
+        if const_sc_cells is not None:
+            cs = np.ascontiguousarray(const_sc_cells, np.int32)
+            lib().or_qgd_set_const_sc_cells(self._h, _i(cs), len(cs))
         a = [np.ascontiguousarray(x, np.int32) for x in (bcU, bcT, bcP)]
         f = [_f64(x) for x in (bvU, bvT, bvP, U0, T0, p0, alphaQGD)]
         lib().or_qgd_init(self._h, C.byref(params), scheme, _i(a[0]), _i(a[1]), _i(a[2]),

@@ -90,6 +90,7 @@ struct or_ctx {
     Vec rhoU, rhoUB, rhoE, rhoEB, H, HB;
     Vec aQGD, aQGDB, tauQGD, tauQGDB, muQGD, muQGDB, alphauQGD, alphauQGDB, ScQGD, ScQGDB, PrQGD, PrQGDB, hQGDB;
     Vec pGrad;                  // qgdFlux gradient per bface
+    IVec constScCells;          // varScModel7 constScCellSet
     // surface fields (nFaces*k)
     Vec tauQGDf, rhof, Uf, rhoUf, UrhoUf, pf, cf, gammaf, Hf, alphauf, muf;
     Vec gradUf, divUf, gradef, gradRhof, gradPf, rhoW, phiw, jm, phiJm, phi, phiJmU, phiP, Pif, phiPi,
@@ -728,6 +729,59 @@ void correctP(or_ctx& s)
     }
 }
 
+void patchSnGrad(const or_ctx& s, int k, const IVec& bc, const double* cell, const double* bnd, const double* grad, double* out);
+
+// varScModel6::correct varScModel6.C:210-269 | varScModel7::correct varScModel7.C:176-254 : the pressure-jump sensor
+//   ScQGD_c = cSc1 * |sum_f (+-) dpf| / (sum_f pf / n),  pf = linearInterpolate(p), dpf = fvc::snGrad(p)/deltaCoeffs,
+// summed over mesh.cells()[c] = the faces the cell owns, then the faces it is the neighbour of, each ascending
+// [OF-v2312 primitiveMesh::calcCells]; empty and wedge patch faces are skipped; p is the field as it stands when
+// thermo.correct() runs (QGDFoam.C:149: the old-step pressure).  The boundary ScQGD stays the dictionary value
+// (calculated patches, QGDCoeffs.C:249-261), clamped with the internal field by model 7's min/max.
+void varScCorrect(or_ctx& s)
+{
+    const int model = s.prm.qgdModel;
+    Vec pf(s.nFaces), sn(s.nFaces), bsg(s.nBnd);
+    linearInterpolate(s, 1, s.p.data(), s.pB.data(), nullptr, pf.data());                   // :210-211 | :176-177
+    patchSnGrad(s, 1, s.bcP, s.p.data(), s.pB.data(), s.pGrad.data(), bsg.data());
+    snGrad(s, 1, s.p.data(), bsg.data(), sn.data());
+    for (int f = 0; f < s.nFaces; ++f) sn[f] = sn[f] / s.dC[f];                             // :212-213 | :178-179
+    const double cSc1 = (model == 7) ? s.prm.varScCSc1 : 1.0;
+#pragma omp parallel for num_threads(s.nThreads) schedule(static)
+    for (int c = 0; c < s.nCells; ++c) {                                                   // :215-269 | :181-235
+        double sumDpF = 0.0, sumpf = 0.0, n = 0.0;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int q = s.cfOff[c]; q < s.cfOff[c + 1]; ++q) {
+                const int f = s.cfFace[q];
+                const bool own = (s.owner[f] == c);
+                if (own != (pass == 0)) continue;
+                if (f < s.nInternal) {
+                    sumpf += pf[f];
+                    if (own) sumDpF += sn[f]; else sumDpF -= sn[f];
+                    n = n + 1;
+                } else {
+                    const int b = f - s.nInternal;
+                    if (patchIsEmpty(s, b) || patchIsWedge(s, b)) continue;
+                    sumDpF += sn[f];                    // processor patches never reach the serial oracle (extended sub-meshes)
+                    sumpf += pf[f];
+                    n = n + 1;
+                }
+            }
+        sumpf /= n;
+        s.ScQGD[c] = cSc1 * (std::fabs(sumDpF) / sumpf);
+    }
+    if (model == 7) {
+        if (s.prm.varScMinSc >= 0) {                                                       // :237-240
+            for (double& v : s.ScQGD) v = std::max(v, s.prm.varScMinSc);
+            for (double& v : s.ScQGDB) v = std::max(v, s.prm.varScMinSc);
+        }
+        if (s.prm.varScMaxSc >= 0) {                                                       // :241-244
+            for (double& v : s.ScQGD) v = std::min(v, s.prm.varScMaxSc);
+            for (double& v : s.ScQGDB) v = std::min(v, s.prm.varScMaxSc);
+        }
+        for (int c : s.constScCells) s.ScQGD[c] = s.prm.ScQGD;                             // :246-254, constSc_ = ScQGD :146
+    }
+}
+
 // hePsiQGDThermo::calculate  hePsiQGDThermo.C:37-126 ; constScPrModel1::correct constScPrModel1.C:97-131 ;
 // QGDThermo::correctQGD QGDThermo.C:84-111
 void thermoCorrect(or_ctx& s)
@@ -789,6 +843,7 @@ void thermoCorrect(or_ctx& s)
             for (int c = 0; c < s.nCells; ++c) s.tauQGD[c] = s.aQGD[c] * s.hQGD[c] / s.c[c];   // :104
             for (int b = 0; b < s.nBnd; ++b) if (!patchIsEmpty(s, b)) s.tauQGDB[b] = s.aQGDB[b] * s.hQGDB[b] / s.cB[b];
         }
+        if (model == 6 || model == 7) varScCorrect(s);
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < s.nCells; ++c) {
             s.muQGD[c] = s.p[c] * s.ScQGD[c] * s.tauQGD[c];                                // :108-111
@@ -1125,6 +1180,7 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
 }
 
 double or_qgd_deltaT(or_ctx* s) { return s->deltaT; }
+void or_qgd_set_const_sc_cells(or_ctx* s, const int* cells, int n) { s->constScCells.assign(cells, cells + n); }
 
 // QGDFoam.C:90-163
 double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, double maxDeltaT, double cTau)
@@ -1325,6 +1381,7 @@ void or_qgd_get(or_ctx* s, int field, double* cells, double* bnd)
         case 8: ci = &s->mu; bi = &s->muB; break;
         case 9: ci = &s->alpha; bi = &s->alphaB; break;
         case 10: ci = &s->tauQGD; bi = &s->tauQGDB; break;
+        case 12: ci = &s->ScQGD; bi = &s->ScQGDB; break;
         default: return;
     }
     if (cells) std::copy(ci->begin(), ci->end(), cells);

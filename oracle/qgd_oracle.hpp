@@ -64,10 +64,12 @@ typedef struct {
     int alphaEffGammaFactor;   // heThermo::alphaEff multiplies by gamma for internal energy [OF-v2312]
     int energyDdtRhoEQuirk;    // 1: QGDEEqn.H:67-72 as in the doc snapshot, fvm::ddt(rho,e) - fvc::ddt(rhoE)
                                // 0: fvm::ddt(rho,e) - fvc::ddt(rho,e)  (e keeps rhoE/rho - K)
-    int qgdModel;              // 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2
+    int qgdModel;              // 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2, 6 varScModel6, 7 varScModel7
     // implicitDiffusion branch (QGDUEqn.H:54-75, QGDEEqn.H:53-64): fvSolution controls of the U and e solvers (PCG)
     double diffTol, diffRelTol;
     int diffMaxIter, diffPrecond;
+    // varScModel7 dictionary entries (varScModel7.C:96-119): cSc1 (default 1), minSc / maxSc (default -1 = off)
+    double varScCSc1, varScMinSc, varScMaxSc;
 } or_qgd_params_t;
 
 typedef struct or_ctx or_ctx;
@@ -90,6 +92,9 @@ void or_linear_interpolate(or_ctx*, int ncmpt, const double* cell, const double*
 
 // ---- QGDFoam
 //  bc kinds per patch for U, T, p ; fixed values per boundary face (U: nBnd*3, T,p: nBnd)
+// varScModel7 "constScCellSet" (varScModel7.C:143-158,246-254): cells whose ScQGD is reset to the dictionary ScQGD each step.
+// Call before or_qgd_init.
+void or_qgd_set_const_sc_cells(or_ctx*, const int* cells, int n);
 void or_qgd_init(or_ctx*, const or_qgd_params_t*, int fvscScheme,
                  const int* bcU, const int* bcT, const int* bcP,
                  const double* bvU, const double* bvT, const double* bvP,

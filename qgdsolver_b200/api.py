@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get",
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
-    "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
+    "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
@@ -67,7 +67,8 @@ class QGDFoamDesc(C.Structure):
                 ("adjust_time_step", C.c_int),
                 ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double),
                 ("diff_tolerance", C.c_double), ("diff_rel_tol", C.c_double), ("diff_max_iter", C.c_int),
-                ("diff_preconditioner", C.c_char_p)]
+                ("diff_preconditioner", C.c_char_p),
+                ("varsc_cSc1", C.c_double), ("varsc_minSc", C.c_double), ("varsc_maxSc", C.c_double)]
 
 
 class QHDFoamDesc(C.Structure):
@@ -109,6 +110,7 @@ def load_library():
         fn.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
     L.qgd_qgdfoam_create.argtypes = [C.c_void_p, C.POINTER(QGDFoamDesc), C.POINTER(C.c_void_p)]
     L.qgd_qgdfoam_destroy.argtypes = [C.c_void_p]
+    L.qgd_qgdfoam_set_const_sc_cells.argtypes = [C.c_void_p, _ip, C.c_int]
     L.qgd_qgdfoam_set_bcs.argtypes = [C.c_void_p, _ip, _ip, _ip, _dp, _dp, _dp]
     L.qgd_qgdfoam_init_fields.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     L.qgd_qgdfoam_step.argtypes = [C.c_void_p, C.c_int]
@@ -273,7 +275,7 @@ class FvscStencil:
 
 
 CELL_FIELDS = {"rho": (0, 1), "rhoU": (1, 3), "rhoE": (2, 1), "U": (3, 3), "e": (4, 1), "p": (5, 1), "T": (6, 1),
-               "c": (7, 1), "mu": (8, 1), "alpha": (9, 1), "tauQGD": (10, 1), "H": (11, 1)}
+               "c": (7, 1), "mu": (8, 1), "alpha": (9, 1), "tauQGD": (10, 1), "H": (11, 1), "ScQGD": (12, 1)}
 
 
 class QGDFoam:
@@ -283,9 +285,10 @@ class QGDFoam:
                  fvsc_scheme="GaussVolPoint", qgd_coeffs="constScPrModel1", implicit_diffusion=False,
                  alpha_eff_gamma_factor=True, energy_ddt_rhoE_quirk=True, adjust_time_step=False, max_co=0.3,
                  max_delta_t=1e30, c_tau=0.75, delta_t=1e-4, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000,
-                 diff_precond="DIC"):
+                 diff_precond="DIC", varsc_cSc1=1.0, varsc_minSc=-1.0, varsc_maxSc=-1.0):
         self.mesh = mesh
         d = QGDFoamDesc()
+        d.varsc_cSc1, d.varsc_minSc, d.varsc_maxSc = varsc_cSc1, varsc_minSc, varsc_maxSc
         self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), diff_precond.encode())
         d.fvsc_scheme, d.qgd_coeffs_model, d.diff_preconditioner = self._names
         d.diff_tolerance, d.diff_rel_tol, d.diff_max_iter = diff_tol, diff_rel_tol, diff_max_iter
@@ -297,6 +300,11 @@ class QGDFoam:
         d.max_co, d.max_delta_t, d.c_tau, d.delta_t = max_co, max_delta_t, c_tau, delta_t
         self._h = C.c_void_p()
         _check(load_library().qgd_qgdfoam_create(mesh._h, C.byref(d), C.byref(self._h)))
+
+    def set_const_sc_cells(self, cells):
+        """varScModel7 constScCellSet (varScModel7.C:143-158); call before init_fields."""
+        c = np.ascontiguousarray(cells, np.int32)
+        _check(load_library().qgd_qgdfoam_set_const_sc_cells(self._h, _i(c), int(c.size)))
 
     def set_bcs(self, bcU, bcT, bcP, valU=None, valT=None, valP=None):
         a = [np.ascontiguousarray(x, np.int32) for x in (bcU, bcT, bcP)]

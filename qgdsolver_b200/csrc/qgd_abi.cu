@@ -104,7 +104,8 @@ struct qgd_solver {
     DevBuf<RecA> bA;
     DevBuf<RecB> bB;
     DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
-    DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage, tauOut, tauOutB;
+    DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage, tauOut, tauOutB, scVar;
+    DevBuf<unsigned char> scConst;   // varScModel7 constScCellSet mask
     int stepsDone = 0;
     // implicit-diffusion branch
     struct Implicit {
@@ -172,6 +173,7 @@ struct qgd_solver {
         s.patchPoints = m.patchPoints.p; s.ppOff = m.ppOff.p; s.ppFace = m.ppFace.p; s.ppW = m.ppW.p;
         s.cfEllW = m.cfEllW; s.cfEll = m.cfEll.p; s.cfTailOff = m.cfTailOff.p; s.cfTailEnc = m.cfTailEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
         s.tauOut = tauOut.n ? tauOut.p : nullptr;
+        s.scVar = scVar.n ? scVar.p : nullptr; s.scConst = scConst.n ? scConst.p : nullptr;
         const bool split = halo.active && halo.ptsInterior.n > 0 && halo.ptsHalo.n > 0;
         s.ptsInterior = split ? halo.ptsInterior.p : nullptr; s.nPtsInterior = split ? (int)halo.ptsInterior.n : 0;
         s.ptsHalo = split ? halo.ptsHalo.p : nullptr; s.nPtsHalo = split ? (int)halo.ptsHalo.n : 0;
@@ -851,7 +853,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         if (!inTable(kCoeffsTable, model))     // QGDCoeffs.C:70-79
             throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown QGD coeffs evaluation approach type " + model +
                                                    "\n\nValid model types are:\n" + toc(kCoeffsTable));
-        if (model != "constScPrModel1" && model != "constScPrModel1n" && model != "constScPrModel2")
+        if (model != "constScPrModel1" && model != "constScPrModel1n" && model != "constScPrModel2" && model != "varScModel6" && model != "varScModel7")
             throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not available on the device yet (no CPU fallback)");
         int diffPrecond = 2;
         if (d->implicit_diffusion) {
@@ -876,12 +878,20 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         k.R = d->R; k.Cp = d->Cp; k.Cv = d->Cp - d->R; k.Tref = d->Tref; k.Hsref = d->Hsref; k.mu = d->mu; k.Pr = d->Pr;
         k.ScQGD = d->ScQGD; k.PrQGD = d->PrQGD; k.gamma = d->Cp / (d->Cp - d->R);
         k.alphaEffGamma = d->alpha_eff_gamma_factor; k.energyQuirk = d->energy_ddt_rhoE_quirk; k.reducedScheme = s->fvsc->reduced;
-        k.model = model == "constScPrModel1" ? 0 : (model == "constScPrModel1n" ? 1 : 2);
+        k.model = (model == "constScPrModel1" || model == "varScModel6" || model == "varScModel7") ? 0 : (model == "constScPrModel1n" ? 1 : 2);
+        // varScModel6.C:207-208 / varScModel7.C:173-174: tau as constScPrModel1; ScQGD from the sensor, boundary ScQGD = dict value (clamped by model 7)
+        k.varSc = model == "varScModel6" ? 6 : (model == "varScModel7" ? 7 : 0);
+        k.cSc1 = d->varsc_cSc1; k.minSc = d->varsc_minSc; k.maxSc = d->varsc_maxSc; k.ScB = d->ScQGD;
+        if (k.varSc == 7) {
+            if (k.minSc >= 0) k.ScB = std::max(k.ScB, k.minSc);
+            if (k.maxSc >= 0) k.ScB = std::min(k.ScB, k.maxSc);
+        }
         k.tauMode = 0; k.alphaUniform = 0.5; k.implicit = d->implicit_diffusion ? 1 : 0;
         const HostMesh& h = mesh->h;
         s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
         s->aQGD.alloc(h.nCells);
+        if (k.varSc) { s->scVar.alloc(h.nCells); s->scVar.zero(g_stream); }
         if (k.model != 0) { s->tauOut.alloc(h.nCells); s->tauOutB.alloc(h.nBnd + 1); s->tauOut.zero(g_stream); s->tauOutB.zero(g_stream); }
         s->psiB.alloc(h.nBnd); s->pGrad.alloc(h.nBnd); s->pNew.alloc(h.nBnd); s->phiw.alloc(h.nBnd);
         s->P.zero(g_stream);
@@ -903,6 +913,25 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
 }
 
 int qgd_qgdfoam_destroy(qgd_solver* s) { return guarded([&] { delete s; }); }
+
+int qgd_qgdfoam_set_const_sc_cells(qgd_solver* s, const int* cells, int n)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || (n > 0 && !cells) || n < 0) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_const_sc_cells: bad argument");
+        if (s->k.varSc != 7) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_const_sc_cells: constScCellSet is read by varScModel7 only");
+        if (s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_const_sc_cells: call before qgd_qgdfoam_init_fields");
+        const int nC = s->mesh->h.nCells;
+        if (n == 0) { s->scConst.release(); return; }
+        std::vector<unsigned char> mask(nC, 0);
+        for (int i = 0; i < n; ++i) {
+            if (cells[i] < 0 || cells[i] >= nC) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_const_sc_cells: cell id out of range");
+            mask[cells[i]] = 1;
+        }
+        s->scConst.upload(mask, g_stream);
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+    });
+}
 
 int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const int* bc_p, const double* val_U,
                         const double* val_T, const double* val_p)
@@ -1040,6 +1069,7 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
                     case 9: outp[i] = s->k.alphaEffGamma ? b[i].alphaEff / gam : b[i].alphaEff; break;
                     case 10: outp[i] = b[i].aByC; break;   // scaled below for cells
                     case 11: outp[i] = a[i].H; break;
+                    case 12: outp[i] = s->k.ScB; break;
                     default: throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: unknown field id");
                 }
             }
@@ -1047,10 +1077,13 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
         if (cells) {
             // SoA field index of each public field id (vectors: first component)
             static const int fieldOf[12] = {0, 8, 11, 1, 4, 5, 6, 12, 13, 14, 15, 7};
-            if (field < 0 || field > 11) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: unknown field id");
+            if (field < 0 || field > 12) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: unknown field id");
             const size_t n = h.nCells;
-            const int k0 = fieldOf[field];
-            if (field == 1 || field == 3) {
+            const int k0 = field < 12 ? fieldOf[field] : 0;
+            if (field == 12) {
+                if (s->scVar.n) { d2h(cells, s->scVar.p, n); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
+                else for (size_t c = 0; c < n; ++c) cells[c] = s->k.ScQGD;
+            } else if (field == 1 || field == 3) {
                 std::vector<double> t(3 * n);
                 d2h(t.data(), s->S.p + (size_t)k0 * n, 3 * n);
                 QGD_CUDA(cudaStreamSynchronize(g_stream));

@@ -813,7 +813,7 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     // constScPrModel1::correct  constScPrModel1.C:104-114  (p is still the old pressure here: QGDFoam.C:149-154)
     const bool tauByU = (k.model == 1) && haveU;           // constScPrModel1n.C:119-126
     const double tau = tauByU ? aQGD * hQGD / (sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + c) : aQGD * hQGD / c;
-    const double muQGD = pOld * k.ScQGD * tau;
+    const double muQGD = pOld * (sv.scVar ? sv.scVar[cell] : k.ScQGD) * tau;     // varScModel6.C:313-322
     const double alphauQGD = muQGD / k.PrQGD;
     const double mu = k.mu + muQGD;                      // QGDThermo.C:91-98
     const double alpha = k.mu / k.Pr + alphauQGD;
@@ -1213,12 +1213,12 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
     const bool tauByU = (k.model == 1) && !init;                         // constScPrModel1n.C:119-126 (boundary part)
     const double tauB = tauByU ? aQGD * hf / (sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + c)
                                : aQGD * hf / c;                          // hQGD_b = hQGDf_b  QGDCoeffs.C:373
-    const double muQGD = pOld * k.ScQGD * tauB;                          // constScPrModel1.C:121-124
+    const double muQGD = pOld * k.ScB * tauB;                            // constScPrModel1.C:121-124
     const double mu = k.mu + muQGD;
     const double alpha = k.mu / k.Pr + muQGD / k.PrQGD;
     const double aByC = tauByU ? tauB : aQGD / c;                        // slot: see Consts::tauMode
     const double tauFace = tauByU ? tauB : aByC * hf;                    // tauQGDf on this boundary face after correct()
-    if (bs.tauOutB) bs.tauOutB[b] = (k.model == 2) ? tauB + k.mu / (pOld * k.ScQGD) : tauB;
+    if (bs.tauOutB) bs.tauOutB[b] = (k.model == 2) ? tauB + k.mu / (pOld * k.ScB) : tauB;
     // p.correctBoundaryConditions()   QGDFoam.C:155 ; qgdFluxFvPatchScalarField.C:159-208
     double p;
     const int bcP = bs.bcP[b];
@@ -1306,6 +1306,52 @@ __device__ __forceinline__ void forCellFacesS(const SolverView& sv, int c, F fn)
             const int e = __ldg(&sv.cfTailEnc[t]);
             fn(e >> 1, e & 1);
         }
+}
+
+// ---- varScModel6::correct varScModel6.C:210-269 | varScModel7::correct varScModel7.C:176-254 : ScQGD of a cell from
+// the pressure jumps over its faces, cSc1 |sum +-dpf| / (sum pf / n) with pf = linearInterpolate(p) and
+// dpf = fvc::snGrad(p)/deltaCoeffs, summed like mesh.cells()[c]: the faces the cell owns, then the faces it is the
+// neighbour of, each ascending; empty / wedge faces skipped.  p is the OLD pressure (thermo.correct() runs before
+// p = rho/psi, QGDFoam.C:149-154), so the kernel runs before the cell update overwrites it.  INIT: p as read (p0), the
+// boundary value from the BC of the read field.
+template <bool INIT>
+__global__ void __launch_bounds__(kBlock) k_varsc(Consts k, FaceView fv, SolverView sv, BndState bs, const double* __restrict__ p)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= sv.nOwned) return;
+    const double pc = p[c];
+    double sumDpF = 0.0, sumpf = 0.0, n = 0.0;
+    for (int pass = 0; pass < 2; ++pass)
+        forCellFacesS(sv, c, [&](int f, int side) {
+            if (side != pass) return;
+            if (f < fv.nI) {
+                const int o = side ? __ldg(&fv.own[f]) : __ldg(&fv.nei[f]);
+                const double po = p[o], w = __ldg(&fv.w[f]);
+                sumpf += side ? (w * (po - pc) + pc) : (w * (pc - po) + po);           // w (p_P - p_N) + p_N
+                const double d = (side ? __ldg(&fv.ndC[f]) * (pc - po) : __ldg(&fv.ndC[f]) * (po - pc)) / __ldg(&fv.dC[f]);
+                if (side) sumDpF -= d; else sumDpF += d;
+                n = n + 1;
+            } else {
+                const int b = f - fv.nI;
+                const int kind = __ldg(&fv.bKind[b]);
+                if (kind == QGD_PATCH_EMPTY || kind == QGD_PATCH_WEDGE) return;
+                const int bc = bs.bcP[b];
+                const double dC = __ldg(&fv.dC[f]);
+                const double pb = INIT ? (bc == QGD_BC_FIXED_VALUE ? bs.bvP[b] : pc) : bs.pNew[b];
+                const double sn = bc == QGD_BC_FIXED_VALUE ? dC * (pb - pc) : (bc == QGD_BC_ZERO_GRADIENT ? 0.0 : (INIT ? 0.0 : bs.pGrad[b]));
+                sumDpF += sn / dC;
+                sumpf += pb;
+                n = n + 1;
+            }
+        });
+    sumpf /= n;
+    double sc = (k.varSc == 7 ? k.cSc1 : 1.0) * (fabs(sumDpF) / sumpf);
+    if (k.varSc == 7) {
+        if (k.minSc >= 0) sc = fmax(sc, k.minSc);
+        if (k.maxSc >= 0) sc = fmin(sc, k.maxSc);
+        if (sv.scConst && sv.scConst[c]) sc = k.ScQGD;
+    }
+    sv.scVar[c] = sc;
 }
 
 // boundary value of U.  newU: after the solve (fixedValue keeps its value, zeroGradient follows the cell)
@@ -1697,6 +1743,7 @@ void launchFvscDiv(cudaStream_t st, int K, const FaceView& fv, const double* cel
 void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                 const double* U0, const double* T0, const double* p0)
 {
+    if (c.varSc) k_varsc<true><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, p0);
     k_init_cells<<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, U0, T0, p0);
     if (fv.nB) k_init_bnd<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs, T0);
     QGD_CUDA(cudaGetLastError());
@@ -1773,7 +1820,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
     }
     if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
-    if (pipe && !adjust) {
+    if (pipe && !adjust && !c.varSc) {
         // fixed deltaT: faces and cells in one persistent kernel, fluxes stay in the L2-resident ring
         k_dt<<<1, 1, 0, st>>>(sv.sc, pipe->queue); ++n;
         if (ev) cudaEventRecord(ev[2], st);
@@ -1793,6 +1840,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         }
         if (hooks && hooks->beforeDt) hooks->beforeDt();
         k_dt<<<1, 1, 0, st>>>(sv.sc, nullptr); ++n;
+        if (c.varSc) { k_varsc<false><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, sv.S + 5 * (size_t)sv.nCells); ++n; }
         if (ev) cudaEventRecord(ev[4], st);
         if (g_cellTma && sv.nCells % 4 == 0 && sv.nOwned >= kTmaTile && (sv.cfEllW == 4 || sv.cfEllW == 6)) {
             const int tiles = sv.nOwned / kTmaTile;
@@ -1842,6 +1890,7 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
         k_face_sigma<<<nblk(fv.nF), kBlock, 0, st>>>(fv, sv, bs, iv); ++n;
         k_cell_implB<<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv); ++n;
     } else {                   // after the e solve: conserved variables, thermo, boundary state
+        if (c.varSc) { k_varsc<false><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, sv.S + 5 * (size_t)sv.nCells); ++n; }
         k_cell_implC<<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv); ++n;
         if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     }

@@ -18,6 +18,10 @@ struct Consts {
     int model, tauMode;
     double alphaUniform;
     int implicit;            // QGD::implicitDiffusion: the mu / alpha terms leave the explicit fluxes (updateFluxes.H:95-111,131-135)
+    // varScModel6 / varScModel7 (model stays 0: tau as constScPrModel1): per-cell ScQGD from the pressure-jump sensor
+    // (k_varsc), boundary ScQGD = ScB = the dictionary value clamped by model 7's minSc / maxSc
+    int varSc;               // 0 | 6 | 7
+    double cSc1, minSc, maxSc, ScB;
 };
 
 struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
@@ -94,6 +98,8 @@ struct SolverView {
     // null = one launch over all points
     const int* ptsInterior; int nPtsInterior; const int* ptsHalo; int nPtsHalo;
     double* tauOut;              // nCells or null: tauQGD as the model reports it (models 1n and 2), for qgd_qgdfoam_get
+    double* scVar;               // nCells or null: ScQGD of varScModel6/7, written by k_varsc before the cell thermo
+    const unsigned char* scConst;// nCells or null: varScModel7 constScCellSet mask
     // face fluxes, 5 doubles per face (k = Fm, FUx, FUy, FUz, FE), SoA:
     //   internal face f : FI[k][slot(f)]            boundary face b : FB[k][b]
     // two-kernel form : one [5][nF] array, FI[k] = F + k*nF, FB[k] = FI[k] + nI, slot = f

@@ -13,8 +13,11 @@ GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5,
 
 class Case:
     def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, gas=GAS, dt=1e-4, scheme="GaussVolPoint",
-                 alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, **opts):
+                 alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, varsc=None, **opts):
         self.model, self.implicit = model, implicit
+        # varScModel7 dictionary entries (cSc1, minSc, maxSc) and the constScCellSet cell list
+        self.varsc = dict(cSc1=1.0, minSc=-1.0, maxSc=-1.0, const_sc_cells=None)
+        self.varsc.update(varsc or {})
         self.diff_solver = dict(tol=1e-14, rel_tol=0.0, max_iter=2000, precond="DIC")
         self.diff_solver.update(diff_solver or {})
         self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
@@ -34,10 +37,11 @@ class Case:
                           diffTol=self.diff_solver["tol"], diffRelTol=self.diff_solver["rel_tol"],
                           diffMaxIter=self.diff_solver["max_iter"], diffPrecond=O.PRECONDS[self.diff_solver["precond"]],
                           alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
-                          energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model])
+                          energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model],
+                          varScCSc1=self.varsc["cSc1"], varScMinSc=self.varsc["minSc"], varScMaxSc=self.varsc["maxSc"])
         scheme = O.FVSC_SCHEMES[self.scheme]
         o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
-                   alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme)
+                   alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme, const_sc_cells=self.varsc["const_sc_cells"])
         return o
 
     def oracle_step(self, o, n):
@@ -50,7 +54,10 @@ class Case:
         ds = self.diff_solver
         s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, implicit_diffusion=self.implicit,
                         diff_tol=ds["tol"], diff_rel_tol=ds["rel_tol"], diff_max_iter=ds["max_iter"], diff_precond=ds["precond"],
+                        varsc_cSc1=self.varsc["cSc1"], varsc_minSc=self.varsc["minSc"], varsc_maxSc=self.varsc["maxSc"],
                         **self.gas, **self.opts)
+        if self.varsc["const_sc_cells"] is not None:
+            s.set_const_sc_cells(self.varsc["const_sc_cells"])
         s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
         s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
         return s

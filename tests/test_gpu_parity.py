@@ -89,6 +89,15 @@ STEP_CASES = {
     "hex_model2": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel2"),
     "2d_model1n_qgdflux": lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", model="constScPrModel1n"),
     "prism_model1n_adjust": lambda: cases.case_prism(bcs="fixed", model="constScPrModel1n", adjust_time_step=True, max_co=0.1),
+    # varScModel6 / varScModel7: ScQGD from the pressure-jump sensor (varScModel6.C:210-269, varScModel7.C:176-254)
+    "hex_varSc6_mixed": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="varScModel6"),
+    "poly_varSc6_qgdflux": lambda: cases.case_poly(bcs="qgdflux", model="varScModel6"),
+    "hex_varSc7_fixed_clamped": lambda: cases.case_hex3d(perturb=0.1, bcs="fixed", model="varScModel7",
+                                                         varsc=dict(cSc1=3.0, minSc=0.02, maxSc=0.4, const_sc_cells=np.arange(5, 300, 7))),
+    "2d_varSc7_adjust": lambda: cases.case_2d(perturb=0.1, bcs="mixed", model="varScModel7", varsc=dict(cSc1=2.0, minSc=0.05),
+                                              adjust_time_step=True, max_co=0.1),
+    "sod_varSc7": lambda: cases.case_sod(200, model="varScModel7", varsc=dict(cSc1=1.0, minSc=0.05, maxSc=1.0)),
+    "prism_varSc6_implicit": lambda: cases.case_prism(bcs="fixed", model="varScModel6", implicit=True),
     # implicitDiffusion true (the reference's default): QGDUEqn.H:54-75, QGDEEqn.H:53-64
     "hex_implicit": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", implicit=True),
     "hex_implicit_fixed_diag": lambda: cases.case_hex3d(bcs="fixed", implicit=True, diff_solver=dict(precond="diagonal"),
@@ -117,7 +126,7 @@ def test_qgdfoam_100_steps_match_oracle(qgd, oracle_mod, name):
         assert rel_linf(s.get(f), o.get(f)) < 1e-13, f"init {f}"
     c.oracle_step(o, 100)
     s.step(100)
-    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T", "mu", "tauQGD"):
+    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T", "mu", "tauQGD") + (("ScQGD",) if c.model.startswith("varSc") else ()):
         gc, gb = s.get(f, with_bnd=True)
         oc, ob = o.get(f, with_bnd=True)
         assert np.isfinite(gc).all()

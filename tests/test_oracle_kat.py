@@ -335,3 +335,76 @@ def test_shear_wave_decay_matches_discrete_eigenvalue(oracle_mod, implicit):
     rhoU = o.get("rhoU")
     assert np.abs(rhoU[:, 1] - fac * A * np.sin(np.pi * x)).max() < 1e-11 * A
     assert abs(fac - 1.0) > 5e-4
+
+
+# ---------------------------------------------------------------- varScModel6 / varScModel7 (pressure-jump sensor)
+def _varsc_numpy(mesh, p, pB, bcP, cSc1=1.0):
+    """Independent vectorised restatement of varScModel6.C:210-269 / varScModel7.C:176-235 (zeroGradient / fixedValue p)."""
+    nI, nC = mesh.n_internal, mesh.n_cells
+    own, nei = mesh.owner, mesh.neighbour
+    w = mesh.weights[:nI]
+    pf = w * p[own[:nI]] + (1 - w) * p[nei]
+    dpf = mesh.nonOrthDeltaCoeffs[:nI] * (p[nei] - p[own[:nI]]) / mesh.deltaCoeffs[:nI]
+    kind = mesh.patch_kind_per_bface()
+    act = kind != 1                                            # not empty
+    fixed = bcP[mesh.patch_id_per_bface()] == cases.FV
+    dpb = np.where(fixed, pB - p[own[nI:]], 0.0)
+    sumD, sumP, n = np.zeros(nC), np.zeros(nC), np.zeros(nC)
+    np.add.at(sumD, own[:nI], dpf); np.add.at(sumD, nei, -dpf); np.add.at(sumD, own[nI:][act], dpb[act])
+    np.add.at(sumP, own[:nI], pf); np.add.at(sumP, nei, pf); np.add.at(sumP, own[nI:][act], pB[act])
+    np.add.at(n, own[:nI], 1); np.add.at(n, nei, 1); np.add.at(n, own[nI:][act], 1)
+    return cSc1 * np.abs(sumD) / (sumP / n)
+
+
+@pytest.mark.parametrize("mk", [lambda **k: cases.case_hex3d(perturb=0.2, bcs="fixed", **k), lambda **k: cases.case_poly(**k),
+                                lambda **k: cases.case_2d((12, 10), perturb=0.1, **k), lambda **k: cases.case_sod(40, **k)])
+def test_varsc_sensor_matches_independent_restatement(oracle_mod, mk):
+    c6 = mk(model="varScModel6")
+    o = c6.make_oracle(oracle_mod)
+    p, pB = o.get("p", with_bnd=True)
+    sc, scB = o.get("ScQGD", with_bnd=True)
+    ref = _varsc_numpy(c6.mesh, p, pB, c6.bcP)
+    assert np.abs(sc - ref).max() <= 1e-12 * max(ref.max(), 1e-300)
+    act = c6.mesh.patch_kind_per_bface() != 1
+    assert np.all(scB[act] == c6.gas["ScQGD"])               # calculated patches keep the dictionary value
+    # muQGD = p*ScQGD*tauQGD (varScModel6.C:313-322): mu - mu_molecular
+    mu, tau = o.get("mu"), o.get("tauQGD")
+    assert np.abs((mu - c6.gas["mu"]) - p * sc * tau).max() < 1e-14 * max(np.abs(mu).max(), 1.0)
+    # model 7: cSc1 multiplier, clamps (incl. the boundary field) and the constScCellSet
+    cells = np.arange(0, c6.mesh.n_cells, 3, dtype=np.int32)
+    lo, hi = 0.25 * ref.max(), 0.6 * ref.max()
+    c7 = mk(model="varScModel7", varsc=dict(cSc1=2.5, minSc=lo, maxSc=hi, const_sc_cells=cells))
+    o7 = c7.make_oracle(oracle_mod)
+    sc7, sc7B = o7.get("ScQGD", with_bnd=True)
+    exp = np.clip(2.5 * ref, lo, hi)
+    exp[cells] = c7.gas["ScQGD"]
+    assert np.abs(sc7 - exp).max() <= 1e-12 * max(exp.max(), 1e-300)
+    assert np.all(sc7B[act] == min(max(c7.gas["ScQGD"], lo), hi))
+
+
+def test_varsc_vanishes_for_linear_pressure_on_a_uniform_line(oracle_mod):
+    """On a uniform 1D mesh the sensor is the second difference of p: zero for linear p, 2 h^2 / mean(p_f) for p = x^2."""
+    c = cases.case_sod(50, model="varScModel6")
+    x = c.mesh.C[:, 0]
+    c.p0 = 1.0 + 0.5 * x
+    c.T0 = c.p0.copy()
+    o = c.make_oracle(oracle_mod)
+    sc = o.get("ScQGD")
+    assert np.abs(sc[1:-1]).max() < 1e-14
+    c.p0 = 1.0 + x * x
+    c.T0 = c.p0.copy()
+    o = c.make_oracle(oracle_mod)
+    sc, p = o.get("ScQGD"), o.get("p")
+    h = 1.0 / 50
+    exp = 2 * h * h / ((p[2:] + 2 * p[1:-1] + p[:-2]) / 4)
+    assert np.abs(sc[1:-1] - exp).max() < 1e-12 * exp.max()
+
+
+def test_varsc_steps_stay_conservative(oracle_mod):
+    c = cases.case_sod(100, model="varScModel7", varsc=dict(cSc1=1.0, minSc=0.05, maxSc=1.0))
+    o = c.make_oracle(oracle_mod)
+    m0 = (o.get("rho") * c.mesh.V).sum()
+    c.oracle_step(o, 100)
+    assert abs((o.get("rho") * c.mesh.V).sum() - m0) < 1e-13 * m0
+    sc = o.get("ScQGD")
+    assert sc.min() >= 0.05 and sc.max() <= 1.0 and sc.max() > 0.06     # the sensor fires at the discontinuities
