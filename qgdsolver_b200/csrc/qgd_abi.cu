@@ -19,6 +19,9 @@ void setLastError(const std::string& m) { g_lastError = m; }
 
 static cudaStream_t g_stream = nullptr;
 static cudaStream_t g_commStream = nullptr;        // halo exchange overlapped with the interior point gather
+static cudaStream_t g_sideStream = nullptr;        // boundary kernels beside the point gather (StepFork), high priority
+static cudaEvent_t g_evFork[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static int g_bndFork = 1;                          // env QGD_BND_FORK=0 keeps the boundary kernels in line on the main stream
 static cudaEvent_t g_evStep = nullptr, g_evHalo = nullptr;
 static bool g_initialised = false;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
@@ -516,6 +519,8 @@ void runStepsImplicit(qgd_solver* s, int n)
     QGD_CUDA(cudaGetLastError());
 }
 
+static int h_nB(const qgd_solver* s) { return s->mesh->h.nBnd; }
+
 void runSteps(qgd_solver* s, int n)
 {
     if (s->k.implicit) {
@@ -545,9 +550,14 @@ void runSteps(qgd_solver* s, int n)
     const bool overlap = multi && g_commStream && !s->desc.adjust_time_step && !s->anyQgdFlux && s->halo.ptsInterior.n > 0 &&
                          !(getenv("QGD_HALO_OVERLAP") && atoi(getenv("QGD_HALO_OVERLAP")) == 0);
     if (multi)
-        hooks.waitHalo = [s] {
-            if (s->halo.pending) { QGD_CUDA(cudaStreamWaitEvent(g_stream, g_evHalo, 0)); s->halo.pending = false; }
+        hooks.waitHalo = [s](cudaStream_t st) {
+            if (s->halo.pending) QGD_CUDA(cudaStreamWaitEvent(st, g_evHalo, 0));
         };
+    if (const char* v = getenv("QGD_BND_FORK")) g_bndFork = atoi(v);
+    StepFork fork{g_sideStream, g_evFork[0], g_evFork[1], g_evFork[2], g_evFork[3], g_evFork[4], !multi};
+    // measured on one B200: neutral at 256^3 (the boundary chain's time moves into k_points), -3 % per step at 128^3; multi-GPU: opt-in
+    // (QGD_BND_FORK=2) until measured - there the side stream can only start after the halo wait
+    const bool useFork = (multi ? g_bndFork == 2 : g_bndFork != 0) && g_sideStream && h_nB(s) > 0 && !s->anyQgdFlux && !(s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc);
     for (int i = 0; i < n; ++i) {
         cudaEvent_t* ev = nullptr;
         if (s->profiling) {
@@ -562,7 +572,8 @@ void runSteps(qgd_solver* s, int n)
         const bool usePipe = s->pipe.mode == 1 && !s->desc.adjust_time_step;
         if (usePipe) { ++s->pipe.epoch; pv = s->pview(); }
         s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev,
-                                  multi ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid);
+                                  multi ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid, useFork ? &fork : nullptr);
+        s->halo.pending = false;
         if (multi) {
             if (overlap) {
                 QGD_CUDA(cudaEventRecord(g_evStep, g_stream));
@@ -574,6 +585,7 @@ void runSteps(qgd_solver* s, int n)
         }
     }
     if (multi && s->halo.pending) { QGD_CUDA(cudaStreamWaitEvent(g_stream, g_evHalo, 0)); s->halo.pending = false; }
+    if (useFork && n > 0 && fork.postOnSide) QGD_CUDA(cudaStreamWaitEvent(g_stream, fork.evBndPost, 0));   // join: boundary state closed
     QGD_CUDA(cudaGetLastError());
 }
 
@@ -658,6 +670,13 @@ int qgd_init(int device)
         if (device < 0 || device >= n) throw Error(QGD_ERR_INVALID, "qgd_init: device index out of range");
         QGD_CUDA(cudaSetDevice(device));
         if (!g_stream) QGD_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+        if (!g_sideStream) {
+            int prLo = 0, prHi = 0;
+            QGD_CUDA(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+            QGD_CUDA(cudaStreamCreateWithPriority(&g_sideStream, cudaStreamNonBlocking, prHi));
+            for (cudaEvent_t& e : g_evFork) QGD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        if (const char* v = getenv("QGD_BND_FORK")) g_bndFork = atoi(v);
         if (!g_ev0) { QGD_CUDA(cudaEventCreate(&g_ev0)); QGD_CUDA(cudaEventCreate(&g_ev1)); }
         g_initialised = true;
     });

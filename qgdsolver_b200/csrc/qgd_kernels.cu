@@ -1790,10 +1790,15 @@ template <int W> int pipeGrid()
 int pipelineKernelGrid(int cfEllW) { return cfEllW == 4 ? pipeGrid<4>() : (cfEllW == 6 ? pipeGrid<6>() : pipeGrid<8>()); }
 
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev, const StepHooks* hooks, const PipeView* pipe, int gridPipe)
+               bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev, const StepHooks* hooks, const PipeView* pipe, int gridPipe,
+               const StepFork* fork)
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
+    const bool usePipe = pipe && !adjust && !c.varSc;
+    // boundary kernels beside the point gather (see StepFork); the qgdFlux mid-step sequence and the pipelined form stay in line
+    const bool forked = fork && fv.nB && !anyQgdFlux && !usePipe;
+    cudaStream_t sb = forked ? fork->side : st;
     auto points = [&](const int* list, int cnt) {
         if (cnt <= 0) return;
         if (sv.pcEllW == 4) k_points<4><<<nblk(cnt), kBlock, 0, st>>>(sv, list, cnt);
@@ -1801,26 +1806,39 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         else k_points<8><<<nblk(cnt), kBlock, 0, st>>>(sv, list, cnt);
         ++n;
     };
+    if (forked) {                    // the side stream starts from the state the main stream has reached (cell update / exchange done)
+        cudaEventRecord(fork->evEntry, st);
+        cudaStreamWaitEvent(sb, fork->evEntry, 0);
+    }
     if (pointsNeeded) {
         if (ev) cudaEventRecord(ev[0], st);
         if (sv.ptsInterior) {
             points(sv.ptsInterior, sv.nPtsInterior);                 // overlaps the halo exchange of the previous step
-            if (hooks && hooks->waitHalo) hooks->waitHalo();
+            if (hooks && hooks->waitHalo) hooks->waitHalo(st);
             points(sv.ptsHalo, sv.nPtsHalo);
         } else {
-            if (hooks && hooks->waitHalo) hooks->waitHalo();
+            if (hooks && hooks->waitHalo) hooks->waitHalo(st);
             points(nullptr, sv.nPoints);
         }
         if (ev) cudaEventRecord(ev[1], st);
-        if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
-    } else if (hooks && hooks->waitHalo) hooks->waitHalo();
+        if (forked && hooks && hooks->waitHalo) hooks->waitHalo(sb);
+        if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, sb>>>(sv, bs, 0); ++n; }
+        if (forked) cudaEventRecord(fork->evPatch, sb);
+    } else if (hooks && hooks->waitHalo) {
+        hooks->waitHalo(st);
+        if (forked) hooks->waitHalo(sb);
+    }
     if (fv.nB && anyQgdFlux) {
         k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
         if (hooks && hooks->midStep) hooks->midStep();
         if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
     }
-    if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
-    if (pipe && !adjust && !c.varSc) {
+    if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, sb>>>(c, fv, sv, bs); ++n; }
+    if (forked) {
+        cudaEventRecord(fork->evBndFlux, sb);
+        if (pointsNeeded) cudaStreamWaitEvent(st, fork->evPatch, 0);      // the face kernel gathers boundary points
+    }
+    if (usePipe) {
         // fixed deltaT: faces and cells in one persistent kernel, fluxes stay in the L2-resident ring
         k_dt<<<1, 1, 0, st>>>(sv.sc, pipe->queue); ++n;
         if (ev) cudaEventRecord(ev[2], st);
@@ -1838,6 +1856,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
             ++n;
             if (ev) cudaEventRecord(ev[3], st);
         }
+        if (forked) cudaStreamWaitEvent(st, fork->evBndFlux, 0);         // boundary fluxes + their Courant / tau contributions
         if (hooks && hooks->beforeDt) hooks->beforeDt();
         k_dt<<<1, 1, 0, st>>>(sv.sc, nullptr); ++n;
         if (c.varSc) { k_varsc<false><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, sv.S + 5 * (size_t)sv.nCells); ++n; }
@@ -1852,7 +1871,16 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         ++n;
         if (ev) cudaEventRecord(ev[5], st);
     }
-    if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
+    if (fv.nB) {
+        if (forked && fork->postOnSide) {
+            cudaEventRecord(fork->evCell, st);
+            cudaStreamWaitEvent(sb, fork->evCell, 0);
+            k_bnd_post<<<nblk(fv.nB), kBlock, 0, sb>>>(c, fv, sv, bs); ++n;
+            cudaEventRecord(fork->evBndPost, sb);
+        } else {
+            k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+        }
+    }
     return n;
 }
 

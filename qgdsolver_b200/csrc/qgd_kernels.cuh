@@ -144,10 +144,19 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 // beforeDt runs before the time-step kernel (all-reduce of the Courant max / tau min)
 // waitHalo: called right before the first kernel that reads halo copies (the packed exchange of the previous step may
 // still be in flight on the communication stream while the interior points are gathered)
-struct StepHooks { std::function<void()> midStep, beforeDt, waitHalo; };
+struct StepHooks { std::function<void()> midStep, beforeDt; std::function<void(cudaStream_t)> waitHalo; };
+// Boundary work forked onto a second, high-priority stream: k_patch_points and k_bnd_flux of step n (and, on one GPU,
+// k_bnd_post of step n-1) depend on the cell update only, not on the point gather, so they run beside k_points
+// instead of in front of / behind the face kernel.  Joins: face kernel <- evPatch, k_dt <- evBndFlux, side <- evCell.
+// The caller makes `side` wait for the main stream before the first step and joins evBndPost after the last one.
+struct StepFork {
+    cudaStream_t side;
+    cudaEvent_t evEntry, evPatch, evBndFlux, evCell, evBndPost;
+    bool postOnSide;         // k_bnd_post on the side stream too (single GPU: nothing on the main stream needs it before the next step)
+};
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr,
-               const PipeView* pipe = nullptr, int gridPipe = 0);
+               const PipeView* pipe = nullptr, int gridPipe = 0, const StepFork* fork = nullptr);
 // implicit-diffusion step, phase by phase (the PCG solves run between the phases, see runStepsImplicit in qgd_abi.cu)
 int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                         const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust);
