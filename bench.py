@@ -223,15 +223,21 @@ def run_product(args):
     tma = os.environ.get("QGD_FACE_TMA", "2") != "0" and mesh.n_faces % 2 == 0
     kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else ("k_face_flux_tma" if tma else "k_face_flux")
     kbytes = ab["face"] + ab["cell"] if pipe["mode"] == 1 else ab["face"]
-    traffic = None
+    traffic, traffic_note = None, None
+    l2hint = int(os.environ.get("QGD_FACE_L2HINT", "3")) if tma else 0
     tp = os.path.join(ROOT, "profiles", "face_flux_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
             if tj.get("n_cells") == mesh.n_cells and kname + "<" in tj.get("kernel", ""):
-                traffic = tj.get("dram_bytes_per_launch")
+                if tj.get("l2hint", 0) == l2hint:
+                    traffic = tj.get("dram_bytes_per_launch")
+                else:       # an ncu capture of another variant of the kernel is not this kernel's traffic
+                    traffic_note = (f"no ncu capture of the L2-policy variant (l2hint={l2hint}) yet; the variant without cache policies "
+                                    f"moved {tj.get('dram_bytes_per_launch', 0) / 1e9:.2f} GB per launch ({tj.get('source', '')})")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": kbytes / (face_ms * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": kbytes / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": kbytes / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note, "l2hint": l2hint,
+                "peak_source": peak_src,
                 "alg_bytes_per_launch": kbytes, "avg_launch_ms": face_ms, "pipeline": pipe,
                 "step": {"alg_bytes": ab["total"], "achieved": ab["total"] / (ms_step * 1e-3) / 1e9,
                          "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak},

@@ -25,7 +25,7 @@ from typing import Dict, List, Tuple
 
 import numpy as np
 
-from .polymesh import PATCH_EMPTY, Patch, PolyMesh
+from .polymesh import PATCH_EMPTY, PATCH_PROCESSOR, Patch, PolyMesh
 
 PATCH_CUT = PATCH_EMPTY   # faces towards cells outside the extended set carry no data: treated like `empty`
 
@@ -253,3 +253,168 @@ def gather_owned(subs: List[SubDomain], fields: List[np.ndarray], n_cells: int) 
     for sd, f in zip(subs, fields):
         out[sd.cell_global[:sd.n_owned]] = f[:sd.n_owned]
     return out
+
+
+# ------------------------------------------------------------------------------------------------ decomposePar layout
+@dataclass
+class ProcMesh:
+    """One `processorN/constant/polyMesh` of a decomposePar output with its four addressing lists [OF-v2312
+    domainDecomposition::decomposeMesh semantics, restated; the reference consumes these through `-parallel` runs]."""
+    rank: int
+    mesh: PolyMesh                      # processor mesh: physical patches (same order as the global mesh), then processor patches
+    cell_addr: np.ndarray               # cellProcAddressing     local cell  -> global cell
+    face_addr: np.ndarray               # faceProcAddressing     local face  -> +-(global face + 1), negative = stored reversed
+    point_addr: np.ndarray              # pointProcAddressing    local point -> global point
+    boundary_addr: np.ndarray           # boundaryProcAddressing local patch -> global patch, -1 for processor patches
+
+
+def _reverse_face(v: np.ndarray) -> np.ndarray:
+    """face::reverseFace [OF]: first vertex kept, the rest reversed."""
+    return np.concatenate([v[:1], v[:0:-1]])
+
+
+def processor_meshes(mesh: PolyMesh, cell_rank: np.ndarray, ranks=None) -> List[ProcMesh]:
+    """The processor meshes decomposePar writes for the cell->processor map `cell_rank`:
+    cells and points keep ascending global order; faces = internal faces of the processor (ascending global face id),
+    the physical patches in global order (zero-sized ones kept), then one processor patch per neighbour rank
+    (ascending) whose faces are in ascending global face id on both sides, reversed on the side of the global neighbour
+    cell."""
+    cell_rank = np.asarray(cell_rank, np.int32)
+    n_parts = int(cell_rank.max()) + 1
+    ranks = list(range(n_parts)) if ranks is None else list(ranks)
+    nI = mesh.n_internal
+    go, gn = mesh.owner[:nI], mesh.neighbour
+    ro, rn = cell_rank[go], cell_rank[gn]
+    out = []
+    for r in ranks:
+        cells = np.nonzero(cell_rank == r)[0]
+        g2l = np.full(mesh.n_cells, -1, np.int64)
+        g2l[cells] = np.arange(cells.size)
+        f_int = np.nonzero((ro == r) & (rn == r))[0]
+        faces = [f_int + 1]
+        owners = [g2l[go[f_int]]]
+        neigh = g2l[gn[f_int]]
+        patches, baddr = [], []
+        start = f_int.size
+        for pi, p in enumerate(mesh.patches):
+            ids = np.arange(p.start, p.start + p.size)
+            sel = ids[cell_rank[mesh.owner[ids]] == r]
+            faces.append(sel + 1)
+            owners.append(g2l[mesh.owner[sel]])
+            patches.append(Patch(p.name, p.kind, start, sel.size, p.neighb_rank))
+            baddr.append(pi)
+            start += sel.size
+        as_owner = (ro == r) & (rn != r)
+        as_neigh = (rn == r) & (ro != r)
+        nbrs = np.unique(np.concatenate([rn[as_owner], ro[as_neigh]]))
+        for q in nbrs:
+            fo = np.nonzero(as_owner & (rn == q))[0]
+            fn = np.nonzero(as_neigh & (ro == q))[0]
+            ids = np.concatenate([fo, fn])
+            sign = np.concatenate([np.ones(fo.size, np.int64), -np.ones(fn.size, np.int64)])
+            loc = np.concatenate([g2l[go[fo]], g2l[gn[fn]]])
+            o = np.argsort(ids, kind="stable")
+            faces.append(sign[o] * (ids[o] + 1))
+            owners.append(loc[o])
+            patches.append(Patch(f"procBoundary{r}to{int(q)}", PATCH_PROCESSOR, start, ids.size, int(q)))
+            baddr.append(-1)
+            start += ids.size
+        face_addr = np.concatenate(faces).astype(np.int64)
+        owner = np.concatenate(owners).astype(np.int32)
+        gf = np.abs(face_addr) - 1
+        used = np.zeros(mesh.n_points, bool)
+        for f in gf:
+            used[mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]] = True
+        pts = np.nonzero(used)[0]
+        p2l = np.full(mesh.n_points, -1, np.int64)
+        p2l[pts] = np.arange(pts.size)
+        offs, verts = [0], []
+        for f, a in zip(gf, face_addr):
+            v = mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]
+            if a < 0:
+                v = _reverse_face(v)
+            verts.append(p2l[v])
+            offs.append(offs[-1] + v.size)
+        pm = PolyMesh(points=np.ascontiguousarray(mesh.points[pts]), face_offsets=np.asarray(offs, np.int32),
+                      face_verts=np.concatenate(verts).astype(np.int32) if verts else np.zeros(0, np.int32), owner=owner,
+                      neighbour=neigh.astype(np.int32), patches=patches, n_cells=int(cells.size),
+                      geometric_d=mesh.geometric_d.copy())
+        out.append(ProcMesh(r, pm, cells.astype(np.int32), face_addr.astype(np.int32), pts.astype(np.int32),
+                            np.asarray(baddr, np.int32)))
+    return out
+
+
+def cell_rank_from_procs(procs: List[ProcMesh], n_cells: int) -> np.ndarray:
+    """cell -> processor map recovered from the cellProcAddressing lists (what `decomposePar -cellDist` writes as
+    constant/cellDecomposition); checks that the lists partition the mesh."""
+    rank = np.full(n_cells, -1, np.int32)
+    for p in procs:
+        if (rank[p.cell_addr] != -1).any():
+            raise ValueError("cellProcAddressing lists overlap")
+        rank[p.cell_addr] = p.rank
+    if (rank < 0).any():
+        raise ValueError("cellProcAddressing lists do not cover the mesh")
+    return rank
+
+
+def check_processor_mesh(mesh: PolyMesh, p: ProcMesh) -> None:
+    """Bit-exact consistency of a processor mesh with the undecomposed mesh through its addressing lists."""
+    pm = p.mesh
+    if not np.array_equal(pm.points, mesh.points[p.point_addr]):
+        raise ValueError("pointProcAddressing: coordinates differ")
+    gf = np.abs(p.face_addr.astype(np.int64)) - 1
+    for lf in range(pm.n_faces):
+        v = p.point_addr[pm.face_verts[pm.face_offsets[lf]:pm.face_offsets[lf + 1]]]
+        g = mesh.face_verts[mesh.face_offsets[gf[lf]]:mesh.face_offsets[gf[lf] + 1]]
+        if p.face_addr[lf] < 0:
+            g = _reverse_face(g)
+        if not np.array_equal(v, g):
+            raise ValueError(f"faceProcAddressing: local face {lf} does not match global face {gf[lf]}")
+    nIl = pm.n_internal
+    flipped = p.face_addr < 0
+    own_g = np.where(flipped, mesh.neighbour[np.minimum(gf, mesh.n_internal - 1)] if mesh.n_internal else 0, mesh.owner[gf])
+    if not np.array_equal(p.cell_addr[pm.owner], own_g):
+        raise ValueError("owner does not map through cellProcAddressing")
+    if flipped[:nIl].any() or not np.array_equal(p.cell_addr[pm.neighbour], mesh.neighbour[gf[:nIl]]):
+        raise ValueError("neighbour does not map through cellProcAddressing")
+    if nIl and not (pm.owner[:nIl] < pm.neighbour).all():
+        raise ValueError("processor mesh is not in owner < neighbour order")
+    for lp, patch in enumerate(pm.patches):
+        ga = p.boundary_addr[lp]
+        fs = gf[patch.start:patch.start + patch.size]
+        if ga >= 0:
+            gp = mesh.patches[ga]
+            if patch.name != gp.name or ((fs < gp.start) | (fs >= gp.start + gp.size)).any():
+                raise ValueError(f"patch {patch.name}: faces outside the global patch")
+        elif (fs >= mesh.n_internal).any():
+            raise ValueError(f"processor patch {patch.name} contains a global boundary face")
+
+
+def couple_processor_geometry(procs: List[ProcMesh]) -> None:
+    """Fill the coupled-patch geometry of every processor patch from the neighbour processor's mesh
+    [OF-v2312 processorFvPatch / coupledFvPatch]: neighbFaceCellCentres, weights
+    |Sf.(Cn-Cf)| / (|Sf.(Cf-Cp)| + |Sf.(Cn-Cf)|), deltaCoeffs 1/|Cn-Cp|, nonOrthDeltaCoeffs 1/max(nf.(Cn-Cp), 0.05|Cn-Cp|)."""
+    for p in procs:
+        if p.mesh.C is None:
+            p.mesh.compute_geometry()
+    by_rank = {p.rank: p for p in procs}
+    for p in procs:
+        m = p.mesh
+        nI = m.n_internal
+        for patch in m.patches:
+            if patch.kind != PATCH_PROCESSOR or patch.size == 0:
+                continue
+            q = by_rank[patch.neighb_rank]
+            other = [x for x in q.mesh.patches if x.kind == PATCH_PROCESSOR and x.neighb_rank == p.rank][0]
+            sl = slice(patch.start, patch.start + patch.size)
+            Cn = q.mesh.C[q.mesh.owner[other.start:other.start + other.size]]
+            Cp = m.C[m.owner[sl]]
+            m.neighb_cell_centres[patch.start - nI:patch.start - nI + patch.size] = Cn
+            so = np.abs((m.Sf[sl] * (m.Cf[sl] - Cp)).sum(1))
+            sn = np.abs((m.Sf[sl] * (Cn - m.Cf[sl])).sum(1))
+            m.weights[sl] = sn / (so + sn)
+            d = Cn - Cp
+            md = np.sqrt((d * d).sum(1))
+            m.deltaCoeffs[sl] = 1.0 / md
+            nf = m.Sf[sl] / m.magSf[sl, None]
+            m.nonOrthDeltaCoeffs[sl] = 1.0 / np.maximum((nf * d).sum(1), 0.05 * md)

@@ -164,6 +164,7 @@ def _fmt(v: float) -> str:
 
 
 def write_polymesh(mesh: PolyMesh, case_dir: str) -> None:
+    """constant/polyMesh under `case_dir` (a case or a processorN directory)."""
     d = os.path.join(case_dir, "constant", "polyMesh")
     os.makedirs(d, exist_ok=True)
     with open(os.path.join(d, "points"), "w") as f:
@@ -182,9 +183,105 @@ def write_polymesh(mesh: PolyMesh, case_dir: str) -> None:
         f.write(_HDR.format(cls="polyBoundaryMesh", loc="constant/polyMesh", obj="boundary"))
         f.write(f"{len(mesh.patches)}\n(\n")
         for p in mesh.patches:
-            f.write(f"    {p.name}\n    {{\n        type            {_KIND_WORD[p.kind]};\n        nFaces          {p.size};\n"
-                    f"        startFace       {p.start};\n    }}\n")
+            f.write(f"    {p.name}\n    {{\n        type            {_KIND_WORD[p.kind]};\n")
+            if p.kind == PATCH_PROCESSOR:       # processorPolyPatch::write [OF-v2312]
+                me = re.match(r"procBoundary(\d+)to\d+", p.name)
+                f.write("        inGroups        1(processor);\n")
+            f.write(f"        nFaces          {p.size};\n        startFace       {p.start};\n")
+            if p.kind == PATCH_PROCESSOR:
+                f.write("        matchTolerance  0.0001;\n        transform       unknown;\n"
+                        f"        myProcNo        {int(me.group(1)) if me else 0};\n        neighbProcNo    {p.neighb_rank};\n")
+            f.write("    }\n")
         f.write(")\n")
+
+
+def write_labels(path: str, arr: np.ndarray, loc: str = "constant/polyMesh") -> None:
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(_HDR.format(cls="labelList", loc=loc, obj=os.path.basename(path)))
+        f.write(f"{arr.size}\n(\n" + "\n".join(str(int(v)) for v in arr) + "\n)\n")
+
+
+# ------------------------------------------------------------------------------------------------ decomposePar output
+_ADDR = (("cellProcAddressing", "cell_addr"), ("faceProcAddressing", "face_addr"), ("pointProcAddressing", "point_addr"),
+         ("boundaryProcAddressing", "boundary_addr"))
+
+
+def write_decomposed_case(mesh: PolyMesh, cell_rank: np.ndarray, case_dir: str, write_cell_dist: bool = True):
+    """processor0..N-1/constant/polyMesh + the four *ProcAddressing lists, laid out as `decomposePar` writes them
+    (decompose.processor_meshes), and constant/cellDecomposition as `decomposePar -cellDist` does.  Returns the ProcMesh list."""
+    from . import decompose
+    procs = decompose.processor_meshes(mesh, cell_rank)
+    for p in procs:
+        d = os.path.join(case_dir, f"processor{p.rank}")
+        write_polymesh(p.mesh, d)
+        for fname, attr in _ADDR:
+            write_labels(os.path.join(d, "constant", "polyMesh", fname), getattr(p, attr))
+    if write_cell_dist:
+        write_labels(os.path.join(case_dir, "constant", "cellDecomposition"), np.asarray(cell_rank), loc="constant")
+    return procs
+
+
+def read_decomposed_case(case_dir: str):
+    """All processorN directories of a decomposed case -> list of decompose.ProcMesh (geometry computed per processor)."""
+    from . import decompose
+    procs = []
+    r = 0
+    while os.path.isdir(os.path.join(case_dir, f"processor{r}")):
+        d = os.path.join(case_dir, f"processor{r}")
+        pm = read_polymesh(d)
+        a = {attr: read_labels(os.path.join(d, "constant", "polyMesh", fname)) for fname, attr in _ADDR}
+        procs.append(decompose.ProcMesh(r, pm, a["cell_addr"], a["face_addr"], a["point_addr"], a["boundary_addr"]))
+        r += 1
+    if not procs:
+        raise FoamFormatError(f"{case_dir}: no processor0 directory (run decomposePar first)")
+    return procs
+
+
+def read_cell_decomposition(case_dir: str, n_cells: int) -> np.ndarray:
+    """cell -> processor map of a decomposed case: constant/cellDecomposition when present (decomposePar -cellDist),
+    else rebuilt from the cellProcAddressing lists.  This is the map the multi-GPU path shards by, so the device
+    decomposition is the decomposePar (scotch) decomposition bit for bit."""
+    from . import decompose
+    path = os.path.join(case_dir, "constant", "cellDecomposition")
+    if os.path.exists(path):
+        rank = read_labels(path)
+        if rank.size != n_cells:
+            raise FoamFormatError(f"{path}: {rank.size} entries for a mesh of {n_cells} cells")
+        return rank.astype(np.int32)
+    procs = []
+    r = 0
+    while os.path.isdir(os.path.join(case_dir, f"processor{r}")):
+        ca = read_labels(os.path.join(case_dir, f"processor{r}", "constant", "polyMesh", "cellProcAddressing"))
+        procs.append(decompose.ProcMesh(r, None, ca, None, None, None))
+        r += 1
+    if not procs:
+        raise FoamFormatError(f"{case_dir}: neither constant/cellDecomposition nor processor directories")
+    return decompose.cell_rank_from_procs(procs, n_cells)
+
+
+def write_processor_fields(case_dir: str, time: str, name: str, procs, internal: np.ndarray, patch_types: Dict[str, str],
+                           boundary: Optional[np.ndarray] = None, n_internal_global: int = 0,
+                           dimensions: str = "[0 0 0 0 0 0 0]") -> None:
+    """Scatter a global cell field (and optionally its boundary values, nBnd[,k] in global boundary-face order) into
+    processorN/<time>/<name>, as `decomposePar -fields` / a parallel run would leave it; processor patches get type
+    `processor` with the value of the cell across the patch left to the reader (calculated from the owner here)."""
+    internal = np.asarray(internal)
+    for p in procs:
+        loc = internal[p.cell_addr]
+        pt = dict(patch_types)
+        bl = None
+        if boundary is not None:
+            nIl = p.mesh.n_internal
+            gf = np.abs(p.face_addr[nIl:].astype(np.int64)) - 1
+            phys = gf >= n_internal_global
+            b = np.asarray(boundary)
+            bl = np.where(phys.reshape((-1,) + (1,) * (b.ndim - 1)), b[np.where(phys, gf - n_internal_global, 0)],
+                          loc[p.mesh.owner[nIl:]])
+        for patch in p.mesh.patches:
+            if patch.kind == PATCH_PROCESSOR:
+                pt[patch.name] = "processor"
+        write_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh, name, loc, pt, bl, dimensions)
 
 
 @dataclass
@@ -279,8 +376,11 @@ def write_field(path: str, mesh: PolyMesh, name: str, internal: np.ndarray, patc
         for p in mesh.patches:
             t = patch_types.get(p.name, "empty" if p.kind == PATCH_EMPTY else "calculated")
             f.write(f"    {p.name}\n    {{\n        type            {t};\n")
-            if boundary is not None and p.kind != PATCH_EMPTY and p.size:
-                f.write(f"        value           {lst(np.asarray(boundary)[p.start - nI:p.start - nI + p.size])};\n")
+            if boundary is not None and p.kind != PATCH_EMPTY:
+                if p.size:
+                    f.write(f"        value           {lst(np.asarray(boundary)[p.start - nI:p.start - nI + p.size])};\n")
+                else:           # zero-sized patch of a processor mesh
+                    f.write(f"        value           nonuniform List<{typ}> 0();\n")
             f.write("    }\n")
         f.write("}\n")
 

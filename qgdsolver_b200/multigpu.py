@@ -24,13 +24,22 @@ def init_comm(rank: int, world: int):
 
 
 def make_rank_solver(case, rank: int, world: int, cell_rank=None):
-    """Extended sub-mesh of `rank` + solver with halo lists.  `case` is a tests/cases.Case on the GLOBAL mesh."""
+    """Extended sub-mesh of `rank` + solver with halo lists.  `case` is a tests/cases.Case on the GLOBAL mesh.
+    `cell_rank`: cell -> processor map, e.g. foamcase.read_cell_decomposition(case_dir, n_cells) of a decomposePar'd case
+    (the device decomposition is then the scotch decomposition, bit for bit); default: geometric split."""
     mesh = case.mesh
     if cell_rank is None:
         cell_rank = decompose.geometric_split(mesh, world)
     sub = decompose.extended_submeshes(mesh, cell_rank, ranks=[rank])[0]
     dm = api.Mesh(sub.mesh, n_owned=sub.n_owned, coupled_face=sub.coupled_face)
-    s = api.QGDFoam(dm, fvsc_scheme=case.scheme, qgd_coeffs=getattr(case, 'model', 'constScPrModel1'), delta_t=case.dt, **case.gas, **case.opts)
+    vs = getattr(case, "varsc", None) or dict(cSc1=1.0, minSc=-1.0, maxSc=-1.0, const_sc_cells=None)
+    s = api.QGDFoam(dm, fvsc_scheme=case.scheme, qgd_coeffs=getattr(case, 'model', 'constScPrModel1'), delta_t=case.dt,
+                    varsc_cSc1=vs["cSc1"], varsc_minSc=vs["minSc"], varsc_maxSc=vs["maxSc"], **case.gas, **case.opts)
+    if vs["const_sc_cells"] is not None:            # global cell ids -> local ids of the extended sub-mesh
+        g2l = np.full(mesh.n_cells, -1, np.int64)
+        g2l[sub.cell_global] = np.arange(sub.cell_global.size)
+        loc = g2l[np.asarray(vs["const_sc_cells"], np.int64)]
+        s.set_const_sc_cells(loc[loc >= 0].astype(np.int32))
     # per-patch BC kinds: global patches + the cut patch (kind irrelevant); per-face values follow the local faces
     nI_g = mesh.n_internal
     bf_g = sub.face_global[sub.mesh.n_internal:]
