@@ -7,10 +7,11 @@ and writes volScalarField / volVectorField files back, so a case prepared for QG
 libqgd_b200 and inspected with the usual tools.  Host-side harness code (numpy); geometry comes from
 PolyMesh.compute_geometry() [OF-v2312 semantics].
 
-Supported subset: ASCII format, label/scalar lists in the `N ( ... )` and `N{v}` forms, faces as `n(v0 v1 ...)`,
+Supported subset: ASCII and little-endian binary format (label=32|64, scalar=32|64), label/scalar lists in the `N ( ... )` and `N{v}` forms, faces as `n(v0 v1 ...)`,
 boundary patches of type patch | wall | empty | processor | wedge | symmetry*, patch fields fixedValue | zeroGradient |
 fixedGradient | qgdFlux | qhdFlux | empty | calculated | slip (-> unsupported by the device BC set), `uniform` and
-`nonuniform List<...>` values.  Binary files and `#include` directives are rejected with a clear error.
+`nonuniform List<...>` values; decomposePar output (processorN meshes + *ProcAddressing, cellDecomposition).  `#include`
+directives and big-endian files are rejected with a clear error.
 """
 from __future__ import annotations
 
@@ -37,6 +38,75 @@ def _strip_comments(text: str) -> str:
     return re.sub(r"//[^\n]*", "", text)
 
 
+_NCMPT = {"label": 1, "scalar": 1, "vector": 3, "symmTensor": 6, "tensor": 9}
+
+
+def _load(path: str) -> str:
+    """File content as ASCII text.  `format binary` files (OpenFOAM writes a list as `N` newline `(` raw bytes `)`
+    [OF-v2312 UList::writeList / OSstream::beginRawWrite]; sizes from the header's arch "LSB;label=32|64;scalar=32|64")
+    are transcoded to the equivalent ASCII file, doubles through repr() so nothing is lost."""
+    data = open(path, "rb").read()
+    m = re.search(rb"FoamFile\s*\{(.*?)\}", data, flags=re.S)
+    if not m or not re.search(rb"format\s+binary\s*;", m.group(1)):
+        return data.decode("ascii", errors="replace")
+    hdr = m.group(1).decode("ascii")
+    arch = re.search(r'arch\s+"([^"]*)"', hdr)
+    lab = re.search(r"label=(\d+)", arch.group(1)) if arch else None
+    sca = re.search(r"scalar=(\d+)", arch.group(1)) if arch else None
+    if arch and "MSB" in arch.group(1):
+        raise FoamFormatError(f"{path}: big-endian binary files are not supported")
+    ldt = np.dtype("<i8") if lab and lab.group(1) == "64" else np.dtype("<i4")
+    sdt = np.dtype("<f4") if sca and sca.group(1) == "32" else np.dtype("<f8")
+    cls = re.search(r"class\s+(\w+)\s*;", hdr).group(1)
+    out = [data[:m.end()].decode("ascii").replace("binary", "ascii")]
+    pos = m.end()
+
+    def raw_list(at: int, dt: np.dtype, ncmpt: int):
+        """`N (raw)` starting at `at` (leading whitespace / comment lines allowed) -> (array (N,ncmpt), end position)"""
+        mm = re.compile(rb"(?:\s|//[^\n]*\n)*(\d+)\s*\(").match(data, at)
+        if not mm:
+            raise FoamFormatError(f"{path}: expected a binary list at byte {at}")
+        n = int(mm.group(1))
+        nb = n * ncmpt * dt.itemsize
+        if mm.end() + nb + 1 > len(data):
+            raise FoamFormatError(f"{path}: binary list of {n} entries is truncated")
+        a = np.frombuffer(data, dt, n * ncmpt, mm.end()).reshape(n, ncmpt)
+        if data[mm.end() + nb:mm.end() + nb + 1] != b")":
+            raise FoamFormatError(f"{path}: binary list of {n} entries is not closed by `)`")
+        return a, mm.end() + nb + 1
+
+    def fmt_rows(a: np.ndarray, integer: bool) -> str:
+        if a.shape[1] == 1:
+            return "\n".join(str(int(v)) if integer else repr(float(v)) for v in a[:, 0])
+        return "\n".join("(" + " ".join(repr(float(x)) for x in v) + ")" for v in a)
+
+    if cls in ("vectorField", "labelList", "scalarField"):
+        a, pos = raw_list(pos, ldt if cls == "labelList" else sdt, 3 if cls == "vectorField" else 1)
+        out.append(f"\n{a.shape[0]}\n(\n{fmt_rows(a, cls == 'labelList')}\n)\n")
+    elif cls == "faceCompactList":                      # CompactListList: offsets (nFaces+1) then the flat vertex labels
+        offs, pos = raw_list(pos, ldt, 1)
+        flat, pos = raw_list(pos, ldt, 1)
+        offs, flat = offs[:, 0], flat[:, 0]
+        out[0] = out[0].replace("faceCompactList", "faceList")
+        out.append(f"\n{offs.size - 1}\n(\n" + "\n".join(
+            f"{int(offs[i + 1] - offs[i])}(" + " ".join(str(int(v)) for v in flat[offs[i]:offs[i + 1]]) + ")" for i in range(offs.size - 1)) + "\n)\n")
+    else:                                               # dictionaries / fields: binary only inside `List<type> N(raw)`
+        pat = re.compile(rb"List<(\w+)>\s*(?=\d)")
+        while True:
+            mm = pat.search(data, pos)
+            if not mm:
+                break
+            typ = mm.group(1).decode()
+            if typ not in _NCMPT:
+                raise FoamFormatError(f"{path}: binary List<{typ}> is not supported")
+            a, end = raw_list(mm.end(), ldt if typ == "label" else sdt, _NCMPT[typ])
+            out.append(data[pos:mm.end()].decode("ascii", errors="replace"))
+            out.append(f"{a.shape[0]}\n(\n{fmt_rows(a, typ == 'label')}\n)")
+            pos = end
+    out.append(data[pos:].decode("ascii", errors="replace"))
+    return "".join(out)
+
+
 def _split_header(text: str) -> Tuple[Dict[str, str], str]:
     """FoamFile header dictionary and the remaining body."""
     text = _strip_comments(text)
@@ -48,7 +118,7 @@ def _split_header(text: str) -> Tuple[Dict[str, str], str]:
             hdr[k] = v.strip().strip('"')
         body = text[m.end():]
     if hdr.get("format", "ascii") != "ascii":
-        raise FoamFormatError("binary OpenFOAM files are not supported (convert with foamFormatConvert)")
+        raise FoamFormatError("binary content must go through _load() (internal error)")
     if "#include" in body:
         raise FoamFormatError("#include directives are not supported")
     return hdr, body
@@ -66,7 +136,7 @@ def _read_list_body(body: str) -> Tuple[int, str]:
 
 
 def read_points(path: str) -> np.ndarray:
-    _, body = _split_header(open(path).read())
+    _, body = _split_header(_load(path))
     n, inner = _read_list_body(body)
     vals = np.array(re.sub(r"[()]", " ", inner).split(), dtype=np.float64)
     if vals.size != 3 * n:
@@ -75,7 +145,7 @@ def read_points(path: str) -> np.ndarray:
 
 
 def read_labels(path: str) -> np.ndarray:
-    _, body = _split_header(open(path).read())
+    _, body = _split_header(_load(path))
     n, inner = _read_list_body(body)
     vals = np.array(inner.split(), dtype=np.int64)
     if vals.size != n:
@@ -84,7 +154,7 @@ def read_labels(path: str) -> np.ndarray:
 
 
 def read_faces(path: str) -> Tuple[np.ndarray, np.ndarray]:
-    _, body = _split_header(open(path).read())
+    _, body = _split_header(_load(path))
     n, inner = _read_list_body(body)
     offs = [0]
     verts: List[int] = []
@@ -100,7 +170,7 @@ def read_faces(path: str) -> Tuple[np.ndarray, np.ndarray]:
 
 
 def read_boundary(path: str) -> List[Patch]:
-    _, body = _split_header(open(path).read())
+    _, body = _split_header(_load(path))
     n, inner = _read_list_body(body)
     patches = []
     for name, blk in re.findall(r"(\w+)\s*\{([^{}]*)\}", inner):
@@ -163,22 +233,49 @@ def _fmt(v: float) -> str:
     return repr(float(v))
 
 
-def write_polymesh(mesh: PolyMesh, case_dir: str) -> None:
-    """constant/polyMesh under `case_dir` (a case or a processorN directory)."""
+_ARCH = '    arch        "LSB;label=32;scalar=64";\n'
+
+
+def _hdr(cls: str, loc: str, obj: str, binary: bool) -> bytes:
+    h = _HDR.format(cls=cls, loc=loc, obj=obj)
+    if binary:
+        h = h.replace("format      ascii;\n", "format      binary;\n" + _ARCH)
+    return h.encode("ascii")
+
+
+def _raw(a: np.ndarray, dt: str) -> bytes:
+    """OpenFOAM binary list: N newline ( raw bytes )"""
+    a = np.ascontiguousarray(a, dtype=dt)
+    return f"\n{a.shape[0]}\n(".encode("ascii") + a.tobytes() + b")\n"
+
+
+def write_polymesh(mesh: PolyMesh, case_dir: str, binary: bool = False) -> None:
+    """constant/polyMesh under `case_dir` (a case or a processorN directory).  binary: `format binary` files
+    (points as raw doubles, faces as a faceCompactList, owner / neighbour as raw 32-bit labels); the boundary file is
+    always a plain dictionary."""
     d = os.path.join(case_dir, "constant", "polyMesh")
     os.makedirs(d, exist_ok=True)
-    with open(os.path.join(d, "points"), "w") as f:
-        f.write(_HDR.format(cls="vectorField", loc="constant/polyMesh", obj="points"))
-        f.write(f"{mesh.n_points}\n(\n" + "\n".join(f"({_fmt(p[0])} {_fmt(p[1])} {_fmt(p[2])})" for p in mesh.points) + "\n)\n")
-    with open(os.path.join(d, "faces"), "w") as f:
-        f.write(_HDR.format(cls="faceList", loc="constant/polyMesh", obj="faces"))
-        o = mesh.face_offsets
-        f.write(f"{mesh.n_faces}\n(\n" + "\n".join(
-            f"{o[i + 1] - o[i]}(" + " ".join(str(int(v)) for v in mesh.face_verts[o[i]:o[i + 1]]) + ")" for i in range(mesh.n_faces)) + "\n)\n")
-    for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
-        with open(os.path.join(d, name), "w") as f:
-            f.write(_HDR.format(cls="labelList", loc="constant/polyMesh", obj=name))
-            f.write(f"{arr.size}\n(\n" + "\n".join(str(int(v)) for v in arr) + "\n)\n")
+    if binary:
+        with open(os.path.join(d, "points"), "wb") as f:
+            f.write(_hdr("vectorField", "constant/polyMesh", "points", True) + _raw(mesh.points, "<f8"))
+        with open(os.path.join(d, "faces"), "wb") as f:
+            f.write(_hdr("faceCompactList", "constant/polyMesh", "faces", True) + _raw(mesh.face_offsets, "<i4") + _raw(mesh.face_verts, "<i4"))
+        for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
+            with open(os.path.join(d, name), "wb") as f:
+                f.write(_hdr("labelList", "constant/polyMesh", name, True) + _raw(arr, "<i4"))
+    else:
+        with open(os.path.join(d, "points"), "w") as f:
+            f.write(_HDR.format(cls="vectorField", loc="constant/polyMesh", obj="points"))
+            f.write(f"{mesh.n_points}\n(\n" + "\n".join(f"({_fmt(p[0])} {_fmt(p[1])} {_fmt(p[2])})" for p in mesh.points) + "\n)\n")
+        with open(os.path.join(d, "faces"), "w") as f:
+            f.write(_HDR.format(cls="faceList", loc="constant/polyMesh", obj="faces"))
+            o = mesh.face_offsets
+            f.write(f"{mesh.n_faces}\n(\n" + "\n".join(
+                f"{o[i + 1] - o[i]}(" + " ".join(str(int(v)) for v in mesh.face_verts[o[i]:o[i + 1]]) + ")" for i in range(mesh.n_faces)) + "\n)\n")
+        for name, arr in (("owner", mesh.owner), ("neighbour", mesh.neighbour)):
+            with open(os.path.join(d, name), "w") as f:
+                f.write(_HDR.format(cls="labelList", loc="constant/polyMesh", obj=name))
+                f.write(f"{arr.size}\n(\n" + "\n".join(str(int(v)) for v in arr) + "\n)\n")
     with open(os.path.join(d, "boundary"), "w") as f:
         f.write(_HDR.format(cls="polyBoundaryMesh", loc="constant/polyMesh", obj="boundary"))
         f.write(f"{len(mesh.patches)}\n(\n")
@@ -324,7 +421,7 @@ def _entries(block: str) -> Dict[str, str]:
 
 
 def read_field(path: str, mesh: PolyMesh) -> VolField:
-    hdr, body = _split_header(open(path).read())
+    hdr, body = _split_header(_load(path))
     cls = hdr.get("class", "volScalarField")
     ncmpt = {"volScalarField": 1, "volVectorField": 3}.get(cls)
     if ncmpt is None:
@@ -357,32 +454,43 @@ def read_field(path: str, mesh: PolyMesh) -> VolField:
 
 
 def write_field(path: str, mesh: PolyMesh, name: str, internal: np.ndarray, patch_types: Dict[str, str],
-                boundary: Optional[np.ndarray] = None, dimensions: str = "[0 0 0 0 0 0 0]") -> None:
-    """Write a volScalarField / volVectorField; `boundary` (nBnd[,3]) supplies `value` entries."""
+                boundary: Optional[np.ndarray] = None, dimensions: str = "[0 0 0 0 0 0 0]", binary: bool = False) -> None:
+    """Write a volScalarField / volVectorField; `boundary` (nBnd[,3]) supplies `value` entries.  binary: nonuniform
+    lists are written as raw little-endian doubles (`format binary`)."""
     internal = np.asarray(internal, np.float64)
     ncmpt = 1 if internal.ndim == 1 else internal.shape[1]
     cls, typ = ("volScalarField", "scalar") if ncmpt == 1 else ("volVectorField", "vector")
 
     def lst(a):
+        if binary:
+            return f"nonuniform List<{typ}> ".encode("ascii") + _raw(np.asarray(a, np.float64), "<f8").strip(b"\n")
+        return lst_ascii(a).encode("ascii")
+
+    def lst_ascii(a):
         if ncmpt == 1:
             return f"nonuniform List<{typ}> {a.shape[0]}\n(\n" + "\n".join(_fmt(v) for v in a) + "\n)"
         return f"nonuniform List<{typ}> {a.shape[0]}\n(\n" + "\n".join("(" + " ".join(_fmt(x) for x in v) + ")" for v in a) + "\n)"
 
     os.makedirs(os.path.dirname(path), exist_ok=True)
-    with open(path, "w") as f:
-        f.write(_HDR.format(cls=cls, loc=os.path.basename(os.path.dirname(path)), obj=name))
-        f.write(f"dimensions      {dimensions};\n\ninternalField   {lst(internal)};\n\nboundaryField\n{{\n")
+    with open(path, "wb") as f:
+        w = lambda t: f.write(t.encode("ascii") if isinstance(t, str) else t)
+        w(_hdr(cls, os.path.basename(os.path.dirname(path)), name, binary))
+        w(f"dimensions      {dimensions};\n\ninternalField   ")
+        w(lst(internal))
+        w(";\n\nboundaryField\n{\n")
         nI = mesh.n_internal
         for p in mesh.patches:
             t = patch_types.get(p.name, "empty" if p.kind == PATCH_EMPTY else "calculated")
-            f.write(f"    {p.name}\n    {{\n        type            {t};\n")
+            w(f"    {p.name}\n    {{\n        type            {t};\n")
             if boundary is not None and p.kind != PATCH_EMPTY:
                 if p.size:
-                    f.write(f"        value           {lst(np.asarray(boundary)[p.start - nI:p.start - nI + p.size])};\n")
+                    w("        value           ")
+                    w(lst(np.asarray(boundary)[p.start - nI:p.start - nI + p.size]))
+                    w(";\n")
                 else:           # zero-sized patch of a processor mesh
-                    f.write(f"        value           nonuniform List<{typ}> 0();\n")
-            f.write("    }\n")
-        f.write("}\n")
+                    w(f"        value           nonuniform List<{typ}> 0();\n")
+            w("    }\n")
+        w("}\n")
 
 
 # ------------------------------------------------------------------------------------------------ solver glue

@@ -97,3 +97,45 @@ def test_rejects_what_it_cannot_read(tmp_path):
     f = fc.read_field(str(tmp_path / "p"), m)
     with pytest.raises(fc.FoamFormatError):
         fc.bc_arrays(m, f)
+
+
+def test_binary_format_round_trip_equals_ascii(tmp_path):
+    """`format binary` polyMesh (raw points, faceCompactList faces, raw labels) and fields (raw nonuniform lists) read
+    back to the same arrays as the ASCII files [OF-v2312 binary list layout: N newline ( raw bytes )]."""
+    c = cases.case_hex3d(n=(5, 4, 3), perturb=0.15, bcs="fixed")
+    m = c.mesh
+    a_dir, b_dir = tmp_path / "ascii", tmp_path / "binary"
+    fc.write_polymesh(m, str(a_dir))
+    fc.write_polymesh(m, str(b_dir), binary=True)
+    assert b"format      binary" in open(b_dir / "constant" / "polyMesh" / "points", "rb").read(400)
+    ma, mb = fc.read_polymesh(str(a_dir)), fc.read_polymesh(str(b_dir))
+    for attr in ("points", "face_offsets", "face_verts", "owner", "neighbour", "C", "V", "Sf", "weights"):
+        assert np.array_equal(getattr(ma, attr), getattr(mb, attr)), attr
+        assert np.array_equal(getattr(mb, attr), getattr(m, attr)) or attr in ("C", "V", "Sf", "weights"), attr
+    types = {p.name: "fixedValue" for p in m.patches}
+    for d, binary in ((a_dir, False), (b_dir, True)):
+        fc.write_field(str(d / "0" / "U"), m, "U", c.U0, types, c.bvU, binary=binary)
+        fc.write_field(str(d / "0" / "T"), m, "T", c.T0, types, c.bvT, binary=binary)
+    for name, ref, bref in (("U", c.U0, c.bvU), ("T", c.T0, c.bvT)):
+        fa, fb = fc.read_field(str(a_dir / "0" / name), ma), fc.read_field(str(b_dir / "0" / name), mb)
+        assert np.array_equal(fa.internal, ref) and np.array_equal(fb.internal, ref)
+        nI = m.n_internal
+        for p in m.patches:
+            assert np.array_equal(fb.patch_values[p.name], bref[p.start - nI:p.start - nI + p.size])
+            assert fa.patch_types == fb.patch_types
+    # the raw bytes on disk are the array itself
+    raw = open(b_dir / "constant" / "polyMesh" / "owner", "rb").read()
+    assert m.owner.astype("<i4").tobytes() in raw
+
+
+def test_binary_errors(tmp_path):
+    m = cases.pm.hex_box(2, 2, 2)
+    fc.write_polymesh(m, str(tmp_path), binary=True)
+    p = tmp_path / "constant" / "polyMesh" / "points"
+    data = open(p, "rb").read()
+    open(p, "wb").write(data[:-40])                               # truncated raw block
+    with pytest.raises(fc.FoamFormatError):
+        fc.read_points(str(p))
+    open(p, "wb").write(data.replace(b"LSB", b"MSB"))
+    with pytest.raises(fc.FoamFormatError):
+        fc.read_points(str(p))
