@@ -151,6 +151,14 @@ int qgd_qgdfoam_destroy(qgd_solver* s);
 /* varScModel7 "constScCellSet" (varScModel7.C:143-158,246-254): polyMesh cell ids whose ScQGD is reset to the
  * dictionary ScQGD after every sensor evaluation.  Call before qgd_qgdfoam_init_fields.  n = 0 clears the set. */
 int qgd_qgdfoam_set_const_sc_cells(qgd_solver* s, const int* cells, int n);
+/* Explicit source matrices of the conservative equations: rhoSu (QGDRhoEqn.H:46), rhoUSu (QGDUEqn.H:62,85), rhoESu
+ * (QGDEEqn.H:60,71).  QGDFoam builds them as zero matrices (createZeroSources.H:28-44); particlesQGDFoam fills them
+ * from the Lagrangian cloud.  Each array holds the volume-integrated explicit source of every cell (= minus the
+ * fvMatrix::source() of the right-hand-side matrix; implicit Sp parts are not supported): rhoSu n_cells [kg/s],
+ * rhoUSu n_cells*3 [N], rhoESu n_cells [W]; a NULL array is zero, all NULL removes the sources.  The values stay in
+ * force for every following step until the next call.  As in the reference's explicit branch the momentum source
+ * corrects U only, rhoU keeps the value of the conservative update (QGDUEqn.H:79-89). */
+int qgd_qgdfoam_set_sources(qgd_solver* s, const double* rhoSu, const double* rhoUSu, const double* rhoESu);
 /* boundary conditions of U, T, p per patch (0/U, 0/T, 0/p): kinds n_patches each (qgd_bc_kind),
  * fixed values per boundary face: U n_bnd*3, T n_bnd, p n_bnd (read only where the kind is fixedValue). */
 int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const int* bc_p,

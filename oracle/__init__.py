@@ -86,6 +86,7 @@ def lib():
         L.or_qgd_init.argtypes = [C.c_void_p, C.POINTER(QGDParams), C.c_int, _ip, _ip, _ip, _dp, _dp, _dp,
                                   _dp, _dp, _dp, _dp, C.c_double]
         L.or_qgd_set_const_sc_cells.argtypes = [C.c_void_p, _ip, C.c_int]
+        L.or_qgd_set_sources.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.or_qgd_step.restype = C.c_double
         L.or_qgd_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.or_qgd_deltaT.restype = C.c_double
@@ -217,6 +218,10 @@ class Oracle:
         f = [_f64(x) for x in (bvU, bvT, bvP, U0, T0, p0, alphaQGD)]
         lib().or_qgd_init(self._h, C.byref(params), scheme, _i(a[0]), _i(a[1]), _i(a[2]),
                           *[_d(x) for x in f], deltaT)
+
+    def qgd_set_sources(self, suRho=None, suU=None, suE=None):
+        a = [_f64(x) for x in (suRho, suU, suE)]
+        lib().or_qgd_set_sources(self._h, _d(a[0]), _d(a[1]), _d(a[2]))
 
     def qgd_step(self, n_steps=1, adjust=False, maxCo=0.3, maxDeltaT=1e30, cTau=0.75):
         return lib().or_qgd_step(self._h, n_steps, int(adjust), maxCo, maxDeltaT, cTau)

@@ -91,6 +91,7 @@ struct or_ctx {
     Vec aQGD, aQGDB, tauQGD, tauQGDB, muQGD, muQGDB, alphauQGD, alphauQGDB, ScQGD, ScQGDB, PrQGD, PrQGDB, hQGDB;
     Vec pGrad;                  // qgdFlux gradient per bface
     IVec constScCells;          // varScModel7 constScCellSet
+    Vec suRho, suU, suE;        // explicit source matrices rhoSu / rhoUSu / rhoESu: volume-integrated source per cell (empty = zero)
     // surface fields (nFaces*k)
     Vec tauQGDf, rhof, Uf, rhoUf, UrhoUf, pf, cf, gammaf, Hf, alphauf, muf;
     Vec gradUf, divUf, gradef, gradRhof, gradPf, rhoW, phiw, jm, phiJm, phi, phiJmU, phiP, Pif, phiPi,
@@ -1181,6 +1182,13 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
 
 double or_qgd_deltaT(or_ctx* s) { return s->deltaT; }
 void or_qgd_set_const_sc_cells(or_ctx* s, const int* cells, int n) { s->constScCells.assign(cells, cells + n); }
+void or_qgd_set_sources(or_ctx* s, const double* suRho, const double* suU, const double* suE)
+{
+    const size_t n = s->nCells;
+    if (suRho) s->suRho.assign(suRho, suRho + n); else s->suRho.clear();
+    if (suU) s->suU.assign(suU, suU + 3 * n); else s->suU.clear();
+    if (suE) s->suE.assign(suE, suE + n); else s->suE.clear();
+}
 
 // QGDFoam.C:90-163
 double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, double maxDeltaT, double cTau)
@@ -1215,7 +1223,8 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < nC; ++c) {
             const double diag = rDeltaT * s.V[c];
-            const double source = rDeltaT * rho0[c] * s.V[c] - s.V[c] * d1[c];
+            double source = rDeltaT * rho0[c] * s.V[c] - s.V[c] * d1[c];
+            if (!s.suRho.empty()) source += s.suRho[c];                                   // == rhoSu  QGDRhoEqn.H:46
             s.rho[c] = source / diag;
         }
         // ---- QGDUEqn.H:36-45
@@ -1248,6 +1257,7 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
                     const size_t i = 3 * (size_t)c + j;
                     diag[c] = rDeltaT * s.rho[c] * s.V[c] + diagL[c];
                     src[c] = rDeltaT * rho0[c] * U0[i] * s.V[c] + s.V[c] * (rDeltaT * (s.rho[c] * s.U[i] - rho0[c] * U0[i])) + s.V[c] * d3[i];
+                    if (!s.suU.empty()) src[c] += s.suU[i];                                // == rhoUSu  QGDUEqn.H:62
                     x[c] = s.U[i];
                 }
                 for (int b = 0; b < nB; ++b) {                               // fixedValue: internalCoeffs / boundaryCoeffs
@@ -1289,7 +1299,8 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
             for (int j = 0; j < 3; ++j) {
                 const size_t i = 3 * (size_t)c + j;
                 const double diag = rDeltaT * s.rho[c] * s.V[c];
-                const double source = rDeltaT * rho0[c] * U0[i] * s.V[c] + s.V[c] * (rDeltaT * (s.rhoU[i] - rhoU0[i]));
+                double source = rDeltaT * rho0[c] * U0[i] * s.V[c] + s.V[c] * (rDeltaT * (s.rhoU[i] - rhoU0[i]));
+                if (!s.suU.empty()) source += s.suU[i];                                   // == rhoUSu  QGDUEqn.H:85 (rhoU itself is not touched)
                 s.U[i] = source / diag;
             }
         correctU(s);
@@ -1320,6 +1331,7 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
             for (int c = 0; c < nC; ++c) {
                 diag[c] = rDeltaT * s.rho[c] * s.V[c];
                 src[c] = rDeltaT * rho0[c] * e0[c] * s.V[c] + s.V[c] * (rDeltaT * (s.rho[c] * s.e[c] - rho0[c] * e0[c]));
+                if (!s.suE.empty()) src[c] += s.suE[c];                                   // == rhoESu  QGDEEqn.H:60
             }
             for (int f = 0; f < s.nInternal; ++f) {
                 const double up = s.ndC[f] * (s.alphauf[f] * s.magSf[f]);
@@ -1347,7 +1359,8 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
             const double diag = rDeltaT * s.rho[c] * s.V[c];
             const double ddt = s.prm.energyDdtRhoEQuirk ? (rDeltaT * (s.rhoE[c] - rhoE0[c]))
                                                         : (rDeltaT * (s.rho[c] * s.e[c] - rho0[c] * e0[c]));
-            const double source = rDeltaT * rho0[c] * e0[c] * s.V[c] + s.V[c] * ddt;
+            double source = rDeltaT * rho0[c] * e0[c] * s.V[c] + s.V[c] * ddt;
+            if (!s.suE.empty()) source += s.suE[c];                                       // == rhoESu  QGDEEqn.H:71
             s.e[c] = source / diag;
         }
         correctE(s);

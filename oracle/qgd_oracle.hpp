@@ -95,6 +95,11 @@ void or_linear_interpolate(or_ctx*, int ncmpt, const double* cell, const double*
 // varScModel7 "constScCellSet" (varScModel7.C:143-158,246-254): cells whose ScQGD is reset to the dictionary ScQGD each step.
 // Call before or_qgd_init.
 void or_qgd_set_const_sc_cells(or_ctx*, const int* cells, int n);
+// Explicit source matrices of QGDRhoEqn.H:46 / QGDUEqn.H:62,85 / QGDEEqn.H:60,71 (rhoSu, rhoUSu, rhoESu; zero in QGDFoam,
+// createZeroSources.H:28-44; the Lagrangian cloud's Srho/SU/Sh in particlesQGDFoam): the volume-integrated explicit
+// source of each cell, i.e. minus the fvMatrix::source() of the matrix on the right-hand side.  suRho, suE: nCells,
+// suU: nCells*3; NULL = zero.  They stay in force until changed.
+void or_qgd_set_sources(or_ctx*, const double* suRho, const double* suU, const double* suE);
 void or_qgd_init(or_ctx*, const or_qgd_params_t*, int fvscScheme,
                  const int* bcU, const int* bcT, const int* bcP,
                  const double* bvU, const double* bvT, const double* bvP,

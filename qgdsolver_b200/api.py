@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get",
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
-    "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
+    "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
@@ -111,6 +111,7 @@ def load_library():
     L.qgd_qgdfoam_create.argtypes = [C.c_void_p, C.POINTER(QGDFoamDesc), C.POINTER(C.c_void_p)]
     L.qgd_qgdfoam_destroy.argtypes = [C.c_void_p]
     L.qgd_qgdfoam_set_const_sc_cells.argtypes = [C.c_void_p, _ip, C.c_int]
+    L.qgd_qgdfoam_set_sources.argtypes = [C.c_void_p, _dp, _dp, _dp]
     L.qgd_qgdfoam_set_bcs.argtypes = [C.c_void_p, _ip, _ip, _ip, _dp, _dp, _dp]
     L.qgd_qgdfoam_init_fields.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     L.qgd_qgdfoam_step.argtypes = [C.c_void_p, C.c_int]
@@ -300,6 +301,11 @@ class QGDFoam:
         d.max_co, d.max_delta_t, d.c_tau, d.delta_t = max_co, max_delta_t, c_tau, delta_t
         self._h = C.c_void_p()
         _check(load_library().qgd_qgdfoam_create(mesh._h, C.byref(d), C.byref(self._h)))
+
+    def set_sources(self, rhoSu=None, rhoUSu=None, rhoESu=None):
+        """Explicit rhoSu / rhoUSu / rhoESu (createZeroSources.H:28-44), volume-integrated per cell; None = zero."""
+        a = [_f64(x) for x in (rhoSu, rhoUSu, rhoESu)]
+        _check(load_library().qgd_qgdfoam_set_sources(self._h, _d(a[0]), _d(a[1]), _d(a[2])))
 
     def set_const_sc_cells(self, cells):
         """varScModel7 constScCellSet (varScModel7.C:143-158); call before init_fields."""

@@ -109,6 +109,7 @@ struct qgd_solver {
     DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
     DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage, tauOut, tauOutB, scVar;
     DevBuf<unsigned char> scConst;   // varScModel7 constScCellSet mask
+    DevBuf<double> su;               // [5][nCells] explicit sources (qgd_qgdfoam_set_sources) or empty
     int stepsDone = 0;
     // implicit-diffusion branch
     struct Implicit {
@@ -177,6 +178,7 @@ struct qgd_solver {
         s.cfEllW = m.cfEllW; s.cfEll = m.cfEll.p; s.cfTailOff = m.cfTailOff.p; s.cfTailEnc = m.cfTailEnc.p; s.V = m.V.p; s.hQGD = m.hQGD.p; s.aQGD = aQGD.p;
         s.tauOut = tauOut.n ? tauOut.p : nullptr;
         s.scVar = scVar.n ? scVar.p : nullptr; s.scConst = scConst.n ? scConst.p : nullptr;
+        s.su = su.n ? su.p : nullptr;
         const bool split = halo.active && halo.ptsInterior.n > 0 && halo.ptsHalo.n > 0;
         s.ptsInterior = split ? halo.ptsInterior.p : nullptr; s.nPtsInterior = split ? (int)halo.ptsInterior.n : 0;
         s.ptsHalo = split ? halo.ptsHalo.p : nullptr; s.nPtsHalo = split ? (int)halo.ptsHalo.n : 0;
@@ -932,6 +934,24 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
 }
 
 int qgd_qgdfoam_destroy(qgd_solver* s) { return guarded([&] { delete s; }); }
+
+int qgd_qgdfoam_set_sources(qgd_solver* s, const double* rhoSu, const double* rhoUSu, const double* rhoESu)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_sources: null solver");
+        if (!rhoSu && !rhoUSu && !rhoESu) { s->su.release(); return; }
+        const size_t n = s->mesh->h.nCells;
+        std::vector<double> h(5 * n, 0.0);
+        for (size_t c = 0; c < n; ++c) {
+            if (rhoSu) h[c] = rhoSu[c];
+            if (rhoUSu) for (int j = 0; j < 3; ++j) h[(1 + j) * n + c] = rhoUSu[3 * c + j];
+            if (rhoESu) h[4 * n + c] = rhoESu[c];
+        }
+        QGD_CUDA(cudaStreamSynchronize(g_stream));      // steps in flight still read the previous sources
+        s->su.upload(h, g_stream);
+    });
+}
 
 int qgd_qgdfoam_set_const_sc_cells(qgd_solver* s, const int* cells, int n)
 {

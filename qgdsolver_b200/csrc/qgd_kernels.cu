@@ -1004,22 +1004,30 @@ __device__ __forceinline__ void cellUpdateCore(const Consts& k, const SolverView
         }
     const double rDeltaT = 1.0 / sv.sc->dt;
     const double diag = rDeltaT * V;
+    // explicit source matrices rhoSu / rhoUSu / rhoESu (QGDRhoEqn.H:46, QGDUEqn.H:85, QGDEEqn.H:71): zero in QGDFoam
+    // (createZeroSources.H:28-44), the cloud's sources in particlesQGDFoam; volume-integrated, added to the matrix source
+    const bool src = sv.su != nullptr;
+    const size_t nS = sv.nCells;
     // QGDRhoEqn.H:40-47
-    const double rho = (rDeltaT * a.rho * V - V * (sm / V)) / diag;
+    const double rho = src ? (rDeltaT * a.rho * V - V * (sm / V) + __ldg(sv.su + c)) / diag : (rDeltaT * a.rho * V - V * (sm / V)) / diag;
     // QGDUEqn.H:36-51, 79-86
     double rhoU[3], U[3];
     rhoU[0] = (rDeltaT * b.rhoUx * V - V * (su0 / V)) / diag;
     rhoU[1] = (rDeltaT * b.rhoUy * V - V * (su1 / V)) / diag;
     rhoU[2] = (rDeltaT * b.rhoUz * V - V * (su2 / V)) / diag;
     const double diagR = rDeltaT * rho * V;
-    U[0] = (rDeltaT * a.rho * a.Ux * V + V * (rDeltaT * (rhoU[0] - b.rhoUx))) / diagR;
-    U[1] = (rDeltaT * a.rho * a.Uy * V + V * (rDeltaT * (rhoU[1] - b.rhoUy))) / diagR;
-    U[2] = (rDeltaT * a.rho * a.Uz * V + V * (rDeltaT * (rhoU[2] - b.rhoUz))) / diagR;
+    U[0] = rDeltaT * a.rho * a.Ux * V + V * (rDeltaT * (rhoU[0] - b.rhoUx));
+    U[1] = rDeltaT * a.rho * a.Uy * V + V * (rDeltaT * (rhoU[1] - b.rhoUy));
+    U[2] = rDeltaT * a.rho * a.Uz * V + V * (rDeltaT * (rhoU[2] - b.rhoUz));
+    if (src) { U[0] += __ldg(sv.su + nS + c); U[1] += __ldg(sv.su + 2 * nS + c); U[2] += __ldg(sv.su + 3 * nS + c); }   // U only: rhoU keeps its value (QGDUEqn.H:79-89)
+    U[0] /= diagR; U[1] /= diagR; U[2] /= diagR;
     // QGDEEqn.H:37-50, 65-73
     const double rhoE = (rDeltaT * b.rhoE * V - V * (se / V)) / diag;
     double e = rhoE / rho - 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]);
     const double ddt = k.energyQuirk ? (rDeltaT * (rhoE - b.rhoE)) : (rDeltaT * (rho * e - a.rho * a.e));
-    e = (rDeltaT * a.rho * a.e * V + V * ddt) / diagR;
+    e = rDeltaT * a.rho * a.e * V + V * ddt;
+    if (src) e += __ldg(sv.su + 4 * nS + c);
+    e /= diagR;
     cellThermo(k, rho, U, rhoU, rhoE, e, a.p, a.T, aQ, hQ, sv, c);
 }
 
@@ -1504,7 +1512,8 @@ __global__ void __launch_bounds__(kBlock) k_cell_implA(Consts k, FaceView fv, So
     const double V = __ldg(&sv.V[c]);
     const double rDeltaT = 1.0 / sv.sc->dt;
     const double diag = rDeltaT * V;
-    const double rho = (rDeltaT * a.rho * V - V * (sm / V)) / diag;                         // QGDRhoEqn.H:40-47
+    const bool src = sv.su != nullptr;
+    const double rho = src ? (rDeltaT * a.rho * V - V * (sm / V) + sv.su[c]) / diag : (rDeltaT * a.rho * V - V * (sm / V)) / diag;   // QGDRhoEqn.H:40-47
     const double u0[3] = {a.Ux, a.Uy, a.Uz}, r0[3] = {b.rhoUx, b.rhoUy, b.rhoUz};
     iv.old[c] = a.Ux; iv.old[n + c] = a.Uy; iv.old[2 * n + c] = a.Uz; iv.old[3 * n + c] = a.rho;
     sv.S[c] = rho;
@@ -1516,7 +1525,9 @@ __global__ void __launch_bounds__(kBlock) k_cell_implA(Consts k, FaceView fv, So
         sv.S[(8 + j) * n + c] = rhoU;
         sv.S[(1 + j) * n + c] = Us;
         // :56-62  fvm::ddt(rho,U) - fvc::ddt(rho,U) - fvm::laplacian(muf,U) - fvc::div(phiTauMC) == 0
-        iv.bU[j * n + c] = rDeltaT * a.rho * u0[j] * V + V * (rDeltaT * (rho * Us - a.rho * u0[j])) + V * (st[j] / V) + bB[j];
+        double bj = rDeltaT * a.rho * u0[j] * V + V * (rDeltaT * (rho * Us - a.rho * u0[j])) + V * (st[j] / V);
+        if (src) bj += sv.su[(1 + j) * n + c];                                              // == rhoUSu  :62
+        iv.bU[j * n + c] = bj + bB[j];
     }
 }
 
@@ -1609,7 +1620,9 @@ __global__ void __launch_bounds__(kBlock) k_cell_implB(Consts k, FaceView fv, So
     sv.S[11 * n + c] = rhoE;
     sv.S[4 * n + c] = es;
     iv.diagE[c] = rDeltaT * rho * V + dL + bI;                                              // :55-60
-    iv.bE[c] = rDeltaT * rho0 * e0 * V + V * (rDeltaT * (rho * es - rho0 * e0)) + bB;
+    double be = rDeltaT * rho0 * e0 * V + V * (rDeltaT * (rho * es - rho0 * e0));
+    if (sv.su) be += sv.su[4 * n + c];                                                      // == rhoESu  QGDEEqn.H:60
+    iv.bE[c] = be + bB;
 }
 
 // phase C: rhoE = rho (e + 0.5 |U|^2) ; thermo.correct() ; p = rho/psi   (QGDEEqn.H:63, QGDFoam.C:149-154)

@@ -98,6 +98,7 @@ struct SolverView {
     // null = one launch over all points
     const int* ptsInterior; int nPtsInterior; const int* ptsHalo; int nPtsHalo;
     double* tauOut;              // nCells or null: tauQGD as the model reports it (models 1n and 2), for qgd_qgdfoam_get
+    const double* su;            // [5][nCells] or null: explicit sources rhoSu, rhoUSu (3), rhoESu (volume-integrated; qgd_qgdfoam_set_sources)
     double* scVar;               // nCells or null: ScQGD of varScModel6/7, written by k_varsc before the cell thermo
     const unsigned char* scConst;// nCells or null: varScModel7 constScCellSet mask
     // face fluxes, 5 doubles per face (k = Fm, FUx, FUy, FUz, FE), SoA:

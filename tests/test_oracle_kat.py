@@ -408,3 +408,49 @@ def test_varsc_steps_stay_conservative(oracle_mod):
     assert abs((o.get("rho") * c.mesh.V).sum() - m0) < 1e-13 * m0
     sc = o.get("ScQGD")
     assert sc.min() >= 0.05 and sc.max() <= 1.0 and sc.max() > 0.06     # the sensor fires at the discontinuities
+
+
+# ---------------------------------------------------------------- explicit source matrices rhoSu / rhoUSu / rhoESu
+def _at_rest(n=(6, 5, 4), implicit=False):
+    c = cases.case_hex3d(n=n, bcs="zg", implicit=implicit)
+    c.U0 = np.zeros_like(c.U0)
+    c.p0 = np.full_like(c.p0, 1.0 / 1.4)
+    c.T0 = np.full_like(c.T0, (1.0 / 1.4) / c.gas["R"])
+    return c
+
+
+@pytest.mark.parametrize("implicit", [False, True])
+def test_mass_source_adds_exactly_its_integral(oracle_mod, implicit):
+    """fvm::ddt(rho) + fvc::div(phiJm) == rhoSu on a closed box: total mass grows by dt * sum(rhoSu) per step."""
+    c = _at_rest(implicit=implicit)
+    o = c.make_oracle(oracle_mod)
+    V = c.mesh.V
+    rng = np.random.default_rng(5)
+    su = 1e-3 * V * rng.random(c.mesh.n_cells)
+    o.qgd_set_sources(suRho=su)
+    m0 = (o.get("rho") * V).sum()
+    c.oracle_step(o, 20)
+    assert abs((o.get("rho") * V).sum() - (m0 + 20 * c.dt * su.sum())) < 1e-13 * m0
+    o.qgd_set_sources()                                    # cleared: mass is conserved again
+    m1 = (o.get("rho") * V).sum()
+    c.oracle_step(o, 5)
+    assert abs((o.get("rho") * V).sum() - m1) < 1e-13 * m1
+
+
+def test_momentum_and_energy_sources_first_step_from_rest(oracle_mod):
+    """Explicit branch, uniform gas at rest, one step: U = dt*rhoUSu/(rho V) while rhoU keeps the value of the
+    conservative update (QGDUEqn.H:79-89: the source corrects U only); e rises by dt*rhoESu/(rho V) exactly - the
+    solve of QGDEEqn.H:65-73 replaces e = rhoE/rho - 0.5|U|^2 (:49) by (rho0 e0 + rhoE - rhoE0 + dt Su/V)/rho."""
+    c = _at_rest()
+    o = c.make_oracle(oracle_mod)
+    V = c.mesh.V
+    rho0, e0 = o.get("rho").copy(), o.get("e").copy()
+    suU = np.zeros((c.mesh.n_cells, 3))
+    suU[:, 0] = 2e-2 * V
+    suE = 5e-2 * V
+    o.qgd_set_sources(suU=suU, suE=suE)
+    c.oracle_step(o, 1)
+    U, rhoU, e = o.get("U"), o.get("rhoU"), o.get("e")
+    assert np.abs(rhoU).max() < 1e-14
+    assert np.abs(U[:, 0] - c.dt * 2e-2 / rho0).max() < 1e-14 and np.abs(U[:, 1:]).max() < 1e-16
+    assert np.abs(e - (e0 + c.dt * 5e-2 / rho0)).max() < 1e-14 * e0.max()
