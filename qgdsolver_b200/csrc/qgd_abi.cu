@@ -603,6 +603,23 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         if (mesh->h.nOwned != mesh->h.nCells)
             throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " on extended sub-meshes (multi-GPU) is not available yet");
     }
+    if (name == "GaussVolPoint") {               // fvsc.C:65-82: wedge patches + prism cells are rejected
+        const HostMesh& h = mesh->h;
+        bool wedge = false;
+        for (int pk : h.patchKind) wedge = wedge || pk == QGD_PATCH_WEDGE;
+        if (wedge)
+            for (int c = 0; c < h.nCells; ++c) {     // prismMatcher [OF-v2312]: 5 faces, two triangles and three quads
+                if (h.cfOff[c + 1] - h.cfOff[c] != 5) continue;
+                int tri = 0, quad = 0;
+                for (int q = h.cfOff[c]; q < h.cfOff[c + 1]; ++q) {
+                    const int f = h.cfEnc[q] >> 1, nv = h.faceOff[f + 1] - h.faceOff[f];
+                    tri += nv == 3; quad += nv == 4;
+                }
+                if (tri == 2 && quad == 3)
+                    throw Error(QGD_ERR_INVALID, "GaussVolPoint scheme does not support solving axisymmetric cases with wedge BC and prism cells.\n"
+                                                 "Try to set leastSquares scheme.");
+            }
+    }
     op.mesh = mesh;
     op.lsq = (name == "leastSquares" || name == "leastSquaresOpt");
     op.reduced = (name == "reduced") || op.lsq;      // boundary faces nf*snGrad, no point values (extendedFaceStencilScalarGrad.C:86-109)

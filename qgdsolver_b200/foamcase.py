@@ -200,11 +200,11 @@ def read_polymesh(case_dir: str, region: str = "") -> PolyMesh:
     mesh = PolyMesh(points=pts, face_offsets=offs, face_verts=verts, owner=owner, neighbour=neighbour, patches=patches,
                     n_cells=n_cells)
     mesh.compute_geometry()
-    # geometricD: a direction is solved unless an `empty` patch removes it  [OF polyMesh::geometricD]
+    # geometricD: a direction is solved unless an `empty` or `wedge` patch removes it  [OF polyMesh::calcDirections]
     gd = np.ones(3, np.int32)
     nI = mesh.n_internal
     for p in patches:
-        if p.kind == PATCH_EMPTY and p.size:
+        if p.kind in (PATCH_EMPTY, PATCH_WEDGE) and p.size:
             nf = mesh.Sf[p.start:p.start + p.size] / mesh.magSf[p.start:p.start + p.size, None]
             gd[int(np.argmax(np.abs(nf).mean(0)))] = -1
     mesh.geometric_d = gd

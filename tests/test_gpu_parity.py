@@ -275,6 +275,16 @@ def test_error_behaviour_matches_reference_messages(qgd):
     with pytest.raises(qgd.QGDError) as e:
         qgd.FvscStencil(dm, "leastSquares")            # fvsc.C:60-63
     assert "Can't use leastSquares or leastSquaresOpt in 3D case." in e.value.message
+    # fvsc.C:65-82: GaussVolPoint refuses wedge patches combined with prism cells; hexes with a wedge patch are fine
+    pr = cases.pm.prism_box(3, 3, 2)
+    pr.patches[0].kind = cases.pm.PATCH_WEDGE
+    with pytest.raises(qgd.QGDError) as e:
+        qgd.FvscStencil(qgd.Mesh(pr), "GaussVolPoint")
+    assert "does not support solving axisymmetric cases with wedge BC and prism cells" in e.value.message
+    qgd.FvscStencil(qgd.Mesh(pr), "reduced")
+    hx = cases.pm.hex_box(3, 3, 2)
+    hx.patches[0].kind = cases.pm.PATCH_WEDGE
+    qgd.FvscStencil(qgd.Mesh(hx), "GaussVolPoint")
     with pytest.raises(qgd.QGDError) as e:
         qgd.QGDFoam(dm, R=1.0, Cp=3.5, qgd_coeffs="noModel")      # QGDCoeffs.C:72-78
     assert "Unknown QGD coeffs evaluation approach type noModel" in e.value.message
