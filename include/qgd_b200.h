@@ -250,6 +250,11 @@ typedef struct {
     double diff_tolerance, diff_rel_tol;
     int diff_max_iter;
     const char* diff_preconditioner;
+    /* 1 = the loop body of scalarTransportQHDFoam (scalarTransportQHDFoam.C:70-135) instead of QHDFoam.C:83-139: U, p
+     * and tau stay as initialised, phiu = Sf & Uf is the transporting flux, only
+     *   fvm::ddt(T) + fvc::div(phiu*Tf) - fvc::Sp(fvc::div(phiu),T) - fvm::laplacian(Hif,T) - fvc::div(tauQGDf*phiu*(Uf & gradTf)) == 0
+     * is solved, and only when implicit_diffusion is set (:114); Courant number from mag(Uf)/hQGDf (:88-96). */
+    int scalar_transport;
 } qgd_qhdfoam_desc;
 int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* desc, qgd_qhd_solver** out);
 int qgd_qhdfoam_destroy(qgd_qhd_solver* s);

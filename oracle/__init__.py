@@ -51,7 +51,8 @@ class QHDParams(C.Structure):
                 ("Gr", C.c_double), ("T0", C.c_double), ("implicitDiffusion", C.c_int),
                 ("pTol", C.c_double), ("pRelTol", C.c_double), ("pMaxIter", C.c_int), ("pPrecond", C.c_int),
                 ("pRefCell", C.c_int), ("pRefValue", C.c_double),
-                ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int)]
+                ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int),
+                ("scalarTransport", C.c_int)]
 
 
 QHD_MODELS = {"constTau": 0, "H2bynuQHD": 1, "HbyUQHD": 2, "T0byGr": 3}

@@ -129,6 +129,10 @@ typedef struct {
     // implicitDiffusion branch (QHDUEqn.H:46-65, QHDTEqn.H:69-80): fvSolution controls of the U and T solvers (PCG)
     double diffTol, diffRelTol;
     int diffMaxIter, diffPrecond;
+    // 1: the scalarTransportQHDFoam loop (scalarTransportQHDFoam.C:70-135): U and tau frozen, no pressure or momentum
+    // equation, phi = phiu, T equation (implicitDiffusion only) with the extra -fvc::Sp(fvc::div(phiu),T) term,
+    // Courant number from mag(Uf)/hQGDf
+    int scalarTransport;
 } or_qhd_params_t;
 //  bc kinds per patch: fixedValue | zeroGradient | fixedGradient (qhdFlux behaves as fixedGradient in QHDFoam, see
 //  DESIGN.md quirk (i)); bv*: value on fixedValue faces, gradient on fixedGradient faces

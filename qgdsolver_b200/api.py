@@ -80,7 +80,7 @@ class QHDFoamDesc(C.Structure):
                 ("p_ref_value", C.c_double), ("adjust_time_step", C.c_int),
                 ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double),
                 ("diff_tolerance", C.c_double), ("diff_rel_tol", C.c_double), ("diff_max_iter", C.c_int),
-                ("diff_preconditioner", C.c_char_p)]
+                ("diff_preconditioner", C.c_char_p), ("scalar_transport", C.c_int)]
 
 
 class _StateHost(C.Structure):
@@ -439,9 +439,11 @@ class QHDFoam:
     def __init__(self, mesh: Mesh, *, rho0, mu, Pr, beta, g, fvsc_scheme="GaussVolPoint", qgd_coeffs="constTau",
                  Tau=0.0, UQHD=1.0, Gr=1.0, T0=1.0, implicit_diffusion=False, tol=1e-8, rel_tol=0.0, max_iter=1000,
                  precond="DIC", p_ref_cell=0, p_ref_value=0.0, adjust_time_step=False, max_co=0.3, max_delta_t=1e30,
-                 c_tau=0.75, delta_t=1e-3, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000, diff_precond="DIC"):
+                 c_tau=0.75, delta_t=1e-3, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000, diff_precond="DIC",
+                 scalar_transport=False):
         self.mesh = mesh
         d = QHDFoamDesc()
+        d.scalar_transport = int(scalar_transport)         # scalarTransportQHDFoam.C:70-135 loop body
         self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), precond.encode(), diff_precond.encode())
         d.fvsc_scheme, d.qgd_coeffs_model, d.p_preconditioner, d.diff_preconditioner = self._names
         d.diff_tolerance, d.diff_rel_tol, d.diff_max_iter = diff_tol, diff_rel_tol, diff_max_iter

@@ -27,6 +27,7 @@ struct QhdConsts {
     int needRef, refCell;
     double refValue;
     int implicit;                // QGD::implicitDiffusion: the Laplacians of U and T are solved implicitly (QHDUEqn.H:46-65, QHDTEqn.H:69-80)
+    int scalarTransport;         // scalarTransportQHDFoam.C:70-135: U, p frozen; phi = phiu; T equation with -fvc::Sp(fvc::div(phiu),T); Co from mag(Uf)
 };
 
 struct QhdView {
@@ -251,7 +252,8 @@ __global__ void __launch_bounds__(kB) k_qhd_face_pre(QhdConsts k, FaceView fv, Q
         if (ADJUST) {                                               // QHDCourantNo.H:39-54
             const double ms = __ldg(&fv.magSf[f]);
             const double Unf = c.Uf[0] * (ge.Sf[0] / ms) + c.Uf[1] * (ge.Sf[1] / ms) + c.Uf[2] * (ge.Sf[2] / ms);
-            coMax = fabs(Unf) / __ldg(&fv.hf[f]);
+            coMax = (k.scalarTransport ? sqrt(c.Uf[0] * c.Uf[0] + c.Uf[1] * c.Uf[1] + c.Uf[2] * c.Uf[2])       // scalarTransportQHDFoam.C:88-96
+                                       : fabs(Unf)) / __ldg(&fv.hf[f]);
             tauMin = tau;
         }
     }
@@ -317,7 +319,7 @@ __global__ void k_qhd_bnd_pre(QhdConsts k, FaceView fv, QhdView q, int adjust)
             q.F0[f] = bc.c.phiu - phiwoOf(bc.ge, bc.c);
             const double ms = fv.magSf[f];
             const double Unf = bc.c.Uf[0] * (bc.ge.Sf[0] / ms) + bc.c.Uf[1] * (bc.ge.Sf[1] / ms) + bc.c.Uf[2] * (bc.ge.Sf[2] / ms);
-            coMax = fabs(Unf) / fv.hf[f];
+            coMax = (k.scalarTransport ? sqrt(bc.c.Uf[0] * bc.c.Uf[0] + bc.c.Uf[1] * bc.c.Uf[1] + bc.c.Uf[2] * bc.c.Uf[2]) : fabs(Unf)) / fv.hf[f];
             tauMin = bc.c.tau;
         }
     }
@@ -427,7 +429,8 @@ __global__ void __launch_bounds__(kB) k_qhd_face_post(QhdConsts k, FaceView fv, 
         gPr[i] = ge.g1[i] * dp1 + ge.g2[i] * dp2 + ge.gp[i] * (pP - pN);
     }
     const double up = __ldg(&q.upper[f]);
-    const double phi = q.F0[f] + (up * pN - up * pP);                                 // QHDpEqn.H:47
+    const double phi = k.scalarTransport ? c.phiu                                      // scalarTransportQHDFoam.C:110 qgdFlux(phiu,T,Tf)
+                                         : q.F0[f] + (up * pN - up * pP);              // QHDpEqn.H:47
     q.phi[f] = phi;
     const double ms = __ldg(&fv.magSf[f]), nd = __ldg(&fv.ndC[f]);
     const double pf = w * (pP - pN) + pN;
@@ -485,7 +488,7 @@ __global__ void k_qhd_bnd_post(QhdConsts k, FaceView fv, QhdView q)
             gPr[i] = ge.g1[i] * dp1 + ge.g2[i] * dp2 + ge.gp[i] * dpP;
         }
     }
-    const double phi = q.F0[f] + (q.intC[b] * pP - q.bouC[b]);                         // fvMatrix::flux, boundary part
+    const double phi = k.scalarTransport ? c.phiu : q.F0[f] + (q.intC[b] * pP - q.bouC[b]);   // fvMatrix::flux, boundary part
     q.phi[f] = phi;
     double nrm[3] = {ge.Sf[0] / ms, ge.Sf[1] / ms, ge.Sf[2] / ms};
     double Wf[3];
@@ -519,15 +522,21 @@ __global__ void __launch_bounds__(kB) k_qhd_cell_sys(QhdConsts k, FaceView fv, Q
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= q.nCells) return;
     const size_t n = q.nCells, nF = fv.nF;
-    double su[3] = {0, 0, 0}, sT = 0.0;
+    double su[3] = {0, 0, 0}, sT = 0.0, sPhi = 0.0;
     forCellFaces(q, c, [&](int f, int side) {
         const double sgn = side ? -1.0 : 1.0;
         su[0] += sgn * q.FU[f]; su[1] += sgn * q.FU[nF + f]; su[2] += sgn * q.FU[2 * nF + f];
         sT += sgn * q.FT[f];
+        sPhi += sgn * q.phi[f];
     });
     const double V = __ldg(&q.V[c]);
     const double rDeltaT = 1.0 / q.sc->dt;
     const double T = q.Q[3 * n + c];
+    if (k.scalarTransport) {     // scalarTransportQHDFoam.C:116-124: only T; - fvc::Sp(fvc::div(phiu),T) goes to the source (phi == phiu here)
+        q.diagT[c] = rDeltaT * V + __ldg(&q.sumAT[c]);
+        q.bT[c] = rDeltaT * T * V - V * (sT / V) + V * ((sPhi / V) * T) + __ldg(&q.srcBT[c]);
+        return;
+    }
     q.diagU[c] = rDeltaT * V + __ldg(&q.sumAU[c]);
     q.diagT[c] = rDeltaT * V + __ldg(&q.sumAT[c]);
 #pragma unroll
@@ -649,6 +658,7 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
         }
         if (nB) { k_qhd_bnd_pre<<<nblk(nB), kB, 0, st>>>(k, fv, q, adjust ? 1 : 0); ++n; }
         k_qhd_dt<<<1, 1, 0, st>>>(q.sc); ++n;
+        if (!k.scalarTransport) {                                                        // scalarTransportQHDFoam has no pressure equation
         if (nB) { k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 1, 0); ++n; }           // QHDpEqn.H:35
         k_qhd_cell_pre<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
         // QHDpEqn.H:45 — x is the p slice of the state
@@ -659,6 +669,7 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
             launchPoints<4, 1>(st, q); ++n;
             if (q.nPatchPoints) { k_qhd_patch_points<<<nblk(q.nPatchPoints), kB, 0, st>>>(q, nB, 1); ++n; }
         }
+        }
         if (fv.nI) { k_qhd_face_post<<<nblk(fv.nI), kB, 0, st>>>(k, fv, q); ++n; }
         if (nB) { k_qhd_bnd_post<<<nblk(nB), kB, 0, st>>>(k, fv, q); ++n; }
         k_qhd_shift<<<1, 1, 0, st>>>(k, q); ++n;
@@ -667,18 +678,20 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
             const double tol = s->desc.diff_tolerance, rel = s->desc.diff_rel_tol;
             const int maxIter = s->desc.diff_max_iter > 0 ? s->desc.diff_max_iter : 1000;
             k_qhd_cell_sys<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
+            if (!k.scalarTransport) {
             s->AU.refresh(nullptr, q.diagU, st);
             for (int j = 0; j < 3; ++j) {                           // QHDUEqn.H:48-64, segregated components
                 s->AU.bExternal = q.bU + j * nC;
                 s->AU.xExternal = q.Q + j * nC;
                 n += 1 + s->AU.solve(tol, rel, maxIter, st);
             }
+            }
             s->AT.refresh(nullptr, q.diagT, st);
             s->AT.bExternal = q.bT;
             s->AT.xExternal = q.Q + 3 * nC;
             n += 2 + s->AT.solve(tol, rel, maxIter, st);               // QHDTEqn.H:71-79
             k_qhd_pshift<<<nblk(q.nCells), kB, 0, st>>>(q); ++n;
-        } else {
+        } else if (!k.scalarTransport) {                             // scalarTransportQHDFoam.C:114: nothing is solved without implicitDiffusion
             k_qhd_cell_update<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
         }
         if (nB) {
@@ -732,6 +745,7 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
         k.rho0 = d->rho0; k.nu = d->mu / d->rho0; k.Hi = (d->mu / d->Pr) / d->rho0; k.beta = d->beta;
         for (int j = 0; j < 3; ++j) k.g[j] = d->g[j];
         k.needRef = 0; k.refCell = d->p_ref_cell; k.refValue = d->p_ref_value; k.implicit = d->implicit_diffusion ? 1 : 0;
+        k.scalarTransport = d->scalar_transport ? 1 : 0;
         const HostMesh& h = mesh->h;
         cudaStream_t st = runtimeStream();
         s->Q.alloc(5 * (size_t)h.nCells); s->P.alloc(5 * (size_t)h.nPoints); s->P.zero(st);
@@ -778,7 +792,7 @@ int qgd_qhdfoam_set_bcs(qgd_qhd_solver* s, const int* bc_U, const int* bc_T, con
                 (s->hbcP[b] != QGD_BC_ZERO_GRADIENT && !val_p))
                 throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_set_bcs: fixedValue / fixedGradient patch without values");
         }
-        s->k.needRef = fixesP ? 0 : 1;                                  // p.needReference()
+        s->k.needRef = (fixesP || s->k.scalarTransport) ? 0 : 1;        // p.needReference(); scalarTransportQHDFoam never touches p
         s->bcU.upload(s->hbcU.empty() ? std::vector<int>(1, 1) : s->hbcU, st);
         s->bcT.upload(s->hbcT.empty() ? std::vector<int>(1, 1) : s->hbcT, st);
         s->bcP.upload(s->hbcP.empty() ? std::vector<int>(1, 1) : s->hbcP, st);

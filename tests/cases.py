@@ -157,8 +157,9 @@ class QHDCase:
     def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, fluid=QHD_FLUID, model="constTau",
                  coeffs=None, dt=1e-3, scheme="GaussVolPoint", alphaQGD=None, tol=1e-13, rel_tol=0.0, max_iter=5000,
                  precond="DIC", p_ref_cell=0, p_ref_value=0.0, adjust_time_step=False, max_co=0.3, max_delta_t=1e30,
-                 c_tau=0.75, implicit=False, diff_solver=None):
+                 c_tau=0.75, implicit=False, diff_solver=None, scalar_transport=False):
         self.implicit = implicit
+        self.scalar_transport = scalar_transport          # scalarTransportQHDFoam.C:70-135 instead of QHDFoam.C:83-139
         self.diff_solver = dict(tol=1e-14, rel_tol=0.0, max_iter=2000, precond="DIC")
         self.diff_solver.update(diff_solver or {})
         self.mesh, self.U0, self.T0, self.p0 = mesh, U0, T0, p0
@@ -179,7 +180,8 @@ class QHDCase:
                           pTol=sv["tol"], pRelTol=sv["rel_tol"], pMaxIter=sv["max_iter"],
                           pPrecond=O.PRECONDS[sv["precond"]], pRefCell=self.p_ref_cell, pRefValue=self.p_ref_value,
                           diffTol=self.diff_solver["tol"], diffRelTol=self.diff_solver["rel_tol"],
-                          diffMaxIter=self.diff_solver["max_iter"], diffPrecond=O.PRECONDS[self.diff_solver["precond"]])
+                          diffMaxIter=self.diff_solver["max_iter"], diffPrecond=O.PRECONDS[self.diff_solver["precond"]],
+                          scalarTransport=int(self.scalar_transport))
         for j in range(3):
             prm.g[j] = f["g"][j]
         scheme = O.FVSC_SCHEMES[self.scheme]
@@ -197,7 +199,7 @@ class QHDCase:
         s = api.QHDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, p_ref_cell=self.p_ref_cell,
                         p_ref_value=self.p_ref_value, implicit_diffusion=self.implicit, diff_tol=ds["tol"],
                         diff_rel_tol=ds["rel_tol"], diff_max_iter=ds["max_iter"], diff_precond=ds["precond"],
-                        **self.fluid, **self.coeffs, **self.solver, **self.opts)
+                        scalar_transport=self.scalar_transport, **self.fluid, **self.coeffs, **self.solver, **self.opts)
         s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
         s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
         return s

@@ -202,3 +202,42 @@ def test_qhd_error_behaviour(qgd):
     with pytest.raises(qgd.QGDError) as e:
         qgd.QHDFoam(dm, **kw).step(1)
     assert e.value.code == qgd.ERR_STATE
+
+
+SCALAR_CASES = {
+    # scalarTransportQHDFoam.C:70-135: frozen U (far from solenoidal), T equation with -fvc::Sp(fvc::div(phiu),T), implicit only
+    "st2d_implicit": lambda: cases.qhd_cavity(n=(18, 16), dt=1e-3, perturb=0.1, implicit=True, scalar_transport=True),
+    "st3d_implicit_diag_H2bynu": lambda: cases.qhd_cavity(n=(8, 7, 6), dims=3, dt=1e-3, implicit=True, scalar_transport=True,
+                                                            model="H2bynuQHD", diff_solver=dict(precond="diagonal")),
+    "st2d_implicit_adjust": lambda: cases.qhd_cavity(n=(16, 14), dt=1e-3, implicit=True, scalar_transport=True,
+                                                      adjust_time_step=True, max_co=0.05, c_tau=0.4),
+    "st3d_reduced": lambda: cases.qhd_cavity(n=(8, 8, 6), dims=3, dt=1e-3, scheme="reduced", implicit=True, scalar_transport=True),
+    "st2d_explicit_noop": lambda: cases.qhd_cavity(n=(12, 10), dt=1e-3, implicit=False, scalar_transport=True),
+}
+
+
+@pytest.mark.parametrize("name", list(SCALAR_CASES))
+def test_scalar_transport_qhdfoam_matches_oracle(qgd, oracle_mod, name):
+    c = SCALAR_CASES[name]()
+    m = c.mesh
+    if c.implicit:      # a velocity field with a strong divergence, so the Sp term matters
+        c.U0 = np.stack([0.3 * np.sin(3 * m.C[:, 0]) + 0.1, 0.2 * np.cos(2 * m.C[:, 1]) * m.C[:, 0], 0.1 * m.C[:, 2] * (m.geometric_d[2] > 0)], 1)
+        c.bcU[:] = cases.ZG
+    o = c.make_oracle(oracle_mod)
+    s = c.make_solver(qgd)
+    U0, p0, T0 = s.get("U").copy(), s.get("p").copy(), s.get("T").copy()
+    c.oracle_step(o, 60)
+    s.step(60)
+    kind = m.patch_kind_per_bface()
+    gc, gb = s.get("T", with_bnd=True)
+    oc, ob = o.qhd_get("T", with_bnd=True)
+    scale = float(np.abs(oc).max())
+    assert float(np.abs(gc - oc).max()) / scale < TOL_STEP and float(np.abs(gb[kind != 1] - ob[kind != 1]).max()) / scale < TOL_STEP
+    assert np.array_equal(s.get("U"), U0) and np.array_equal(s.get("p"), p0)          # never touched
+    assert rel_linf(s.get_flux(), o.qhd_get_face("phi")) < 1e-12                      # phi == phiu
+    if c.implicit:
+        assert float(np.abs(gc - T0).max()) > 1e-6                                    # T did move
+    else:
+        assert np.array_equal(gc, T0)                                                 # :114 nothing is solved
+    if c.opts["adjust_time_step"]:
+        assert abs(s.scalars()["deltaT"] - o.qhd_deltaT()) < 1e-10 * o.qhd_deltaT()

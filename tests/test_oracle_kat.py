@@ -454,3 +454,48 @@ def test_momentum_and_energy_sources_first_step_from_rest(oracle_mod):
     assert np.abs(rhoU).max() < 1e-14
     assert np.abs(U[:, 0] - c.dt * 2e-2 / rho0).max() < 1e-14 and np.abs(U[:, 1:]).max() < 1e-16
     assert np.abs(e - (e0 + c.dt * 5e-2 / rho0)).max() < 1e-14 * e0.max()
+
+
+# ---------------------------------------------------------------- scalarTransportQHDFoam (frozen U, T equation only)
+def test_scalar_transport_keeps_uniform_T_for_any_velocity(oracle_mod):
+    """fvc::div(phiu*Tf) - fvc::Sp(fvc::div(phiu),T) vanishes for uniform T whatever div(phiu) is, the regularisation and
+    the Laplacian vanish with grad T: a uniform T stays uniform although U is far from solenoidal; U and p never change
+    (scalarTransportQHDFoam.C:110-125)."""
+    import cases
+    c = cases.qhd_cavity(n=(10, 8), dt=1e-3, perturb=0.15, implicit=True, scalar_transport=True)
+    c.bcT[:] = cases.ZG
+    c.bcU[:] = cases.ZG
+    c.T0 = np.full_like(c.T0, 1.25)
+    c.U0 = np.stack([np.sin(3 * c.mesh.C[:, 0]), c.mesh.C[:, 1] ** 2, 0 * c.mesh.C[:, 0]], 1)
+    o = c.make_oracle(oracle_mod)
+    U0, p0 = o.qhd_get("U").copy(), o.qhd_get("p").copy()
+    c.oracle_step(o, 10)
+    assert np.abs(o.qhd_get("T") - 1.25).max() < 1e-12
+    assert np.array_equal(o.qhd_get("U"), U0) and np.array_equal(o.qhd_get("p"), p0)
+    assert np.array_equal(o.qhd_get_face("phi"), o.qhd_get_face("phiu"))
+
+
+def test_scalar_transport_diffusion_eigenmode_and_explicit_noop(oracle_mod):
+    """U = 0: backward Euler on the discrete Laplacian eigenvector cos(pi x): factor 1/(1 + dt*lambda_h) per step
+    (fvm::laplacian(Hif,T), scalarTransportQHDFoam.C:116-124); with implicitDiffusion false nothing is solved (:114)."""
+    import cases
+    n = 16
+    mk = lambda implicit: cases.qhd_cavity(n=(n, 4), dt=2e-3, implicit=implicit, scalar_transport=True)
+    c = mk(True)
+    m = c.mesh
+    c.U0[:] = 0.0
+    c.bcT[:] = cases.ZG
+    c.T0 = 1.0 + 0.3 * np.cos(np.pi * m.C[:, 0])
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 20)
+    h = 1.0 / n
+    Hi = (c.fluid["mu"] / c.fluid["Pr"]) / c.fluid["rho0"]
+    lam = Hi * (2.0 - 2.0 * np.cos(np.pi * h)) / h ** 2
+    ref = 1.0 + 0.3 * (1.0 + c.dt * lam) ** -20 * np.cos(np.pi * m.C[:, 0])
+    assert np.abs(o.qhd_get("T") - ref).max() < 1e-12
+    e = mk(False)
+    e.T0 = c.T0.copy()
+    oe = e.make_oracle(oracle_mod)
+    T0 = oe.qhd_get("T").copy()
+    e.oracle_step(oe, 5)
+    assert np.array_equal(oe.qhd_get("T"), T0)
