@@ -13,8 +13,9 @@ GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5,
 
 class Case:
     def __init__(self, mesh, U0, T0, p0, bcU, bcT, bcP, bvU, bvT, bvP, gas=GAS, dt=1e-4, scheme="GaussVolPoint",
-                 alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, varsc=None, **opts):
+                 alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, varsc=None, sources=None, **opts):
         self.model, self.implicit = model, implicit
+        self.sources = sources          # (rhoSu, rhoUSu, rhoESu) volume-integrated explicit sources or None (createZeroSources.H:28-44)
         # varScModel7 dictionary entries (cSc1, minSc, maxSc) and the constScCellSet cell list
         self.varsc = dict(cSc1=1.0, minSc=-1.0, maxSc=-1.0, const_sc_cells=None)
         self.varsc.update(varsc or {})
@@ -42,6 +43,8 @@ class Case:
         scheme = O.FVSC_SCHEMES[self.scheme]
         o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
                    alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme, const_sc_cells=self.varsc["const_sc_cells"])
+        if self.sources is not None:
+            o.qgd_set_sources(*self.sources)
         return o
 
     def oracle_step(self, o, n):
@@ -60,7 +63,34 @@ class Case:
             s.set_const_sc_cells(self.varsc["const_sc_cells"])
         s.set_bcs(self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP)
         s.init_fields(self.U0, self.T0, self.p0, self.alphaQGD)
+        if self.sources is not None:
+            s.set_sources(*self.sources)
         return s
+
+
+def smooth_sources(mesh, amp=1.0):
+    """smooth volume-integrated sources for rho, rhoU, rhoE (tests of the rhoSu / rhoUSu / rhoESu coupling)"""
+    V, x = mesh.V, mesh.C
+    act = (mesh.geometric_d > 0).astype(float)
+    suRho = amp * 0.3 * V * np.sin(3 * x[:, 0]) ** 2
+    suU = amp * (V * 0.2)[:, None] * np.stack([np.cos(2 * x[:, 1]), np.sin(x[:, 0] + x[:, 2]), 0.5 * np.cos(x[:, 0])], 1) * act
+    suE = amp * 0.5 * V * (1.0 + np.cos(2 * x[:, 0] + x[:, 1]))
+    return suRho, np.ascontiguousarray(suU), suE
+
+
+def with_sources(case, amp=1.0):
+    case.sources = smooth_sources(case.mesh, amp)
+    return case
+
+
+def scalar_transport_case(**kw):
+    """scalarTransportQHDFoam case: cavity mesh, a frozen velocity field with a strong divergence, zeroGradient U"""
+    c = qhd_cavity(scalar_transport=True, **kw)
+    m = c.mesh
+    c.U0 = np.ascontiguousarray(np.stack([0.3 * np.sin(3 * m.C[:, 0]) + 0.1, 0.2 * np.cos(2 * m.C[:, 1]) * m.C[:, 0],
+                                          0.1 * m.C[:, 2] * (m.geometric_d[2] > 0)], 1))
+    c.bcU[:] = ZG
+    return c
 
 
 def smooth_ic(mesh, gas=GAS, seed=12345, mach=0.1):

@@ -142,7 +142,8 @@ def test_qgdfoam_100_steps_match_oracle(qgd, oracle_mod, name):
 
 
 @pytest.mark.parametrize("name", ["hex_perturbed_mixed", "2d_mixed", "sod_1d", "hex_implicit", "prism_model1n", "qhd_cavity2d",
-                                  "qhd_cavity3d_H2bynu"])
+                                  "qhd_cavity3d_H2bynu", "hex_varSc7", "poly_varSc6", "hex_sources", "2d_sources_implicit",
+                                  "qhd_scalar_transport2d", "qhd_scalar_transport3d_adjust"])
 def test_cuda_path_reproduces_committed_golden_fixtures(qgd, name):
     """tests/golden/*.npz (written by tests/golden/make_golden.py from the oracle) against the CUDA path, no oracle run."""
     import os

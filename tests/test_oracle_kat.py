@@ -183,7 +183,15 @@ GOLDEN_CASES = {"hex_perturbed_mixed": lambda: cases.case_hex3d(perturb=0.2, gra
                 "hex_implicit": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", implicit=True),
                 "prism_model1n": lambda: cases.case_prism(bcs="fixed", model="constScPrModel1n"),
                 "qhd_cavity2d": lambda: cases.qhd_cavity(n=(16, 14), dt=1e-3, perturb=0.1),
-                "qhd_cavity3d_H2bynu": lambda: cases.qhd_cavity(n=(8, 7, 6), dims=3, dt=5e-4, model="H2bynuQHD", precond="diagonal")}
+                "qhd_cavity3d_H2bynu": lambda: cases.qhd_cavity(n=(8, 7, 6), dims=3, dt=5e-4, model="H2bynuQHD", precond="diagonal"),
+                "hex_varSc7": lambda: cases.case_hex3d(perturb=0.1, bcs="fixed", model="varScModel7",
+                                                       varsc=dict(cSc1=3.0, minSc=0.02, maxSc=0.4, const_sc_cells=np.arange(5, 300, 7))),
+                "poly_varSc6": lambda: cases.case_poly(bcs="qgdflux", model="varScModel6"),
+                "hex_sources": lambda: cases.with_sources(cases.case_hex3d(perturb=0.2, bcs="mixed")),
+                "2d_sources_implicit": lambda: cases.with_sources(cases.case_2d(perturb=0.1, bcs="fixed", implicit=True)),
+                "qhd_scalar_transport2d": lambda: cases.scalar_transport_case(n=(16, 14), dt=1e-3, perturb=0.1, implicit=True),
+                "qhd_scalar_transport3d_adjust": lambda: cases.scalar_transport_case(n=(8, 7, 6), dims=3, dt=1e-3, implicit=True,
+                                                                                    adjust_time_step=True, max_co=0.05, c_tau=0.4)}
 
 
 def golden_fields(c, o):
