@@ -507,3 +507,75 @@ def test_scalar_transport_diffusion_eigenmode_and_explicit_noop(oracle_mod):
     T0 = oe.qhd_get("T").copy()
     e.oracle_step(oe, 5)
     assert np.array_equal(oe.qhd_get("T"), T0)
+
+
+# ---------------------------------------------------------------- flux algebra against an einsum restatement
+@pytest.mark.parametrize("implicit", [False, True])
+def test_qgd_flux_algebra_matches_an_independent_einsum_restatement(oracle_mod, implicit):
+    """QGDFoam/updateFields.H:45-80 + updateFluxes.H:54-139 written once more, directly from the listing, with numpy
+    einsum on whole face fields (OpenFOAM index conventions: grad(U)_ij = d_i U_j, (v & T)_j = v_i T_ij,
+    (T & v)_i = T_ij v_j, (A & B)_ij = A_ik B_kj, a*b = outer product).  Inputs: the oracle's cell / boundary state
+    before the step and its fvsc face gradients; outputs compared: every flux the equations consume."""
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.2, bcs="fixed", implicit=implicit, gas=dict(cases.GAS, mu=5e-3))
+    m = c.mesh
+    o = c.make_oracle(oracle_mod)
+    st = {f: o.get(f, with_bnd=True) for f in ("rho", "U", "rhoU", "rhoE", "p", "c", "mu", "alpha")}
+    tau = o.get_face("tauQGDf")                      # as left by the last thermo.correct(): the tau the step's fluxes use
+    c.oracle_step(o, 1)
+    I = lambda f: o.linear_interpolate(*st[f])
+    rho, U, rhoU, p, cs = I("rho"), I("U"), I("rhoU"), I("p"), I("c")
+    UrhoU = o.linear_interpolate(np.einsum("ci,cj->cij", st["U"][0], st["rhoU"][0]).reshape(-1, 9),
+                                 np.einsum("ci,cj->cij", st["U"][1], st["rhoU"][1]).reshape(-1, 9)).reshape(-1, 3, 3)
+    H = o.linear_interpolate((st["rhoE"][0] + st["p"][0]) / st["rho"][0], (st["rhoE"][1] + st["p"][1]) / st["rho"][1])
+    g = c.gas["Cp"] / (c.gas["Cp"] - c.gas["R"])
+    muf, alphaf = I("mu"), I("alpha") * (g if c.opts["alpha_eff_gamma_factor"] else 1.0)     # alphaEff for internal energy [OF heThermo]
+    gU, ge, gR, gP = o.get_face("gradUf").reshape(-1, 3, 3), o.get_face("gradef"), o.get_face("gradRhof"), o.get_face("gradPf")
+    Sf = m.Sf
+    divU = np.einsum("fii->f", gU)
+    rhoW = tau[:, None] * (U * np.einsum("fj,fj->f", gR, U)[:, None] + rhoU * divU[:, None] + np.einsum("fi,fij->fj", rhoU, gU))
+    phiw = np.einsum("fi,fi->f", Sf, rhoW)
+    rhoW = rhoW + tau[:, None] * gP
+    jm = rhoU - rhoW
+    phiJm = np.einsum("fi,fi->f", Sf, jm)
+    eye = np.eye(3)[None]
+    Pi = tau[:, None, None] * (np.einsum("fik,fkj->fij", UrhoU, gU) + np.einsum("fi,fj->fij", U, gP)) \
+        + tau[:, None, None] * (eye * (np.einsum("fi,fi->f", U, gP) + g * p * divU)[:, None, None])
+    q = -tau[:, None] * np.einsum("fij,fj->fi", UrhoU, ge - (p / rho / rho)[:, None] * gR)
+    if not implicit:
+        Pi = Pi + muf[:, None, None] * (gU + np.swapaxes(gU, 1, 2) - (2.0 / 3.0) * eye * divU[:, None, None])
+        q = q - alphaf[:, None] * ge
+    exp = {"phiwStar": phiw, "phiJm": phiJm, "phiJmU": phiJm[:, None] * U, "phiP": Sf * p[:, None],
+           "phiPi": np.einsum("fi,fij->fj", Sf, Pi), "phiJmH": phiJm * H, "phiQ": np.einsum("fi,fi->f", Sf, q),
+           "phiPiU": np.einsum("fi,fi->f", Sf, np.einsum("fij,fj->fi", Pi, U))}
+    for name, ref in exp.items():
+        got = o.get_face(name)
+        assert np.abs(got - ref).max() <= 1e-12 * max(np.abs(ref).max(), 1e-30), name
+    assert np.abs(cs).min() > 0
+
+
+def test_qhd_flux_algebra_matches_an_independent_einsum_restatement(oracle_mod):
+    """QHDFoam/updateFluxes.H:33-38 and QHDpEqn.H:47 once more with einsum: phiu = Sf & Uf,
+    phiwo = Sf & (tauQGDf*((Uf & gradUf) - BdFrcf)), phi = phiu - phiwo + pEqn.flux() with the uncorrected Laplacian
+    flux -(tauQGDf/rhof)|Sf| nonOrthDeltaCoeffs (p_N - p_P); checked on the internal faces after one step."""
+    import cases
+    c = cases.qhd_cavity(n=(7, 6, 5), dims=3, dt=1e-3, perturb=0.15)
+    m = c.mesh
+    nI = m.n_internal
+    o = c.make_oracle(oracle_mod)
+    U0, UB0 = o.qhd_get("U", with_bnd=True)
+    T0, TB0 = o.qhd_get("T", with_bnd=True)
+    c.oracle_step(o, 1)
+    f = c.fluid
+    Uf = o.linear_interpolate(U0, UB0)
+    Bf = o.linear_interpolate(f["beta"] * T0[:, None] * np.asarray(f["g"])[None], f["beta"] * TB0[:, None] * np.asarray(f["g"])[None])
+    gU = o.qhd_get_face("gradUf").reshape(-1, 3, 3)
+    tau = o.qhd_get_face("tauQGDf")
+    phiu = np.einsum("fi,fi->f", m.Sf, Uf)
+    phiwo = np.einsum("fi,fi->f", m.Sf, tau[:, None] * (np.einsum("fi,fij->fj", Uf, gU) - Bf))
+    assert np.abs(o.qhd_get_face("phiu") - phiu)[:nI].max() < 1e-14 * np.abs(phiu).max()
+    assert np.abs(o.qhd_get_face("phiwo") - phiwo)[:nI].max() < 1e-12 * np.abs(phiwo).max()
+    p = o.qhd_get("p")
+    shift = 0.0                                       # p was shifted to the reference value after the flux was formed: differences only
+    flux = -(tau[:nI] / f["rho0"]) * m.magSf[:nI] * m.nonOrthDeltaCoeffs[:nI] * (p[m.neighbour] - p[m.owner[:nI]] + shift)
+    phi = phiu[:nI] - phiwo[:nI] + flux
+    assert np.abs(o.qhd_get_face("phi")[:nI] - phi).max() < 1e-11 * np.abs(phiu).max()
