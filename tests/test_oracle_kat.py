@@ -579,3 +579,87 @@ def test_qhd_flux_algebra_matches_an_independent_einsum_restatement(oracle_mod):
     flux = -(tau[:nI] / f["rho0"]) * m.magSf[:nI] * m.nonOrthDeltaCoeffs[:nI] * (p[m.neighbour] - p[m.owner[:nI]] + shift)
     phi = phiu[:nI] - phiwo[:nI] + flux
     assert np.abs(o.qhd_get_face("phi")[:nI] - phi).max() < 1e-11 * np.abs(phiu).max()
+
+
+@pytest.mark.parametrize("mesh_fn", [lambda: cases.pm.hex_box(5, 4, 3, perturb=0.2, seed=4), lambda: cases.pm.hexprism_poly(4, 3, 3, a=0.1, lz=0.4),
+                                     lambda: cases.case_2d((8, 7), perturb=0.15).mesh])
+def test_vol_point_interpolation_matches_numpy_restatement(oracle_mod, mesh_fn):
+    """[OF-v2312 volPointInterpolation] interior points: inverse-distance weights 1/|x_p - C_c| over the cells around the
+    point, normalised; points on a (non-empty) boundary patch: inverse-distance over the boundary faces around the
+    point, 1/|x_p - Cf_b|, using boundary values only (volPointInterpolation::makeWeights / makeBoundaryWeights)."""
+    mesh = mesh_fn()
+    o = oracle_mod.Oracle(mesh)
+    nI = mesh.n_internal
+    rng = np.random.default_rng(2)
+    cell, bnd = rng.random(mesh.n_cells), rng.random(mesh.n_bnd) + 5.0
+    got = o.vol_point_interpolate(cell, bnd)
+    kind = mesh.patch_kind_per_bface()
+    num, den = np.zeros(mesh.n_points), np.zeros(mesh.n_points)
+    on_patch = np.zeros(mesh.n_points, bool)
+    for b in range(mesh.n_bnd):
+        if kind[b] == 1:
+            continue
+        f = nI + b
+        for v in mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]:
+            w = 1.0 / np.linalg.norm(mesh.points[v] - mesh.Cf[f])
+            num[v] += w * bnd[b]; den[v] += w; on_patch[v] = True
+    seen = set()
+    numc, denc = np.zeros(mesh.n_points), np.zeros(mesh.n_points)
+    for f in range(mesh.n_faces):
+        for cidx in ([mesh.owner[f]] + ([mesh.neighbour[f]] if f < nI else [])):
+            for v in mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]:
+                if (v, cidx) in seen:
+                    continue
+                seen.add((v, cidx))
+                w = 1.0 / np.linalg.norm(mesh.points[v] - mesh.C[cidx])
+                numc[v] += w * cell[cidx]; denc[v] += w
+    ref = np.where(on_patch, num / np.where(den > 0, den, 1.0), numc / denc)
+    assert np.abs(got - ref).max() < 1e-13
+
+
+@pytest.mark.parametrize("mesh_fn", [lambda: cases.pm.hex_box(6, 5, 4, perturb=0.25, grading=(2, 1, 0.5), seed=6),
+                                     lambda: cases.pm.hexprism_poly(4, 4, 3, a=0.1, lz=0.4), lambda: cases.case_2d((9, 7), perturb=0.2).mesh])
+def test_qgd_length_scales_on_distorted_meshes_match_numpy_restatement(oracle_mod, mesh_fn):
+    """QGDCoeffs::updateQGDLength (QGDCoeffs.C:298-362): hQGDf = 2 min(|C_P - Cf|, |C_N - Cf|) on internal faces,
+    2/deltaCoeffs on ordinary patch faces; hQGD = area-weighted mean of hQGDf over the cell's non-empty faces."""
+    mesh = mesh_fn()
+    o = oracle_mod.Oracle(mesh)
+    nI = mesh.n_internal
+    hf = np.zeros(mesh.n_faces)
+    hf[:nI] = 2.0 * np.minimum(np.linalg.norm(mesh.C[mesh.owner[:nI]] - mesh.Cf[:nI], axis=1),
+                               np.linalg.norm(mesh.C[mesh.neighbour] - mesh.Cf[:nI], axis=1))
+    hf[nI:] = 2.0 / mesh.deltaCoeffs[nI:]
+    keep = np.ones(mesh.n_faces, bool)
+    keep[nI:] = mesh.patch_kind_per_bface() != 1
+    assert np.abs(o.hQGDf()[keep] - hf[keep]).max() < 1e-14
+    num, den = np.zeros(mesh.n_cells), np.zeros(mesh.n_cells)
+    for cells, sel in ((mesh.owner, keep), (mesh.neighbour, np.ones(nI, bool))):
+        f = np.nonzero(sel)[0]
+        np.add.at(num, cells[f], hf[f] * mesh.magSf[f])
+        np.add.at(den, cells[f], mesh.magSf[f])
+    assert np.abs(o.hQGD() - num / den).max() < 1e-14
+
+
+def test_thermo_state_identities_with_reference_offsets(oracle_mod):
+    """hePsiQGDThermo + perfectGas + hConst + sensibleInternalEnergy [OF-v2312]: e = Cp (T - Tref) + Hsref - R T,
+    psi = 1/(R T), rho = psi p, c = sqrt(gamma/psi), rhoE = rho (e + |U|^2/2), mu = mu_mol + p ScQGD tau,
+    alpha = mu_mol/Pr + (p ScQGD tau)/PrQGD, tauQGD = alphaQGD hQGD / c (constScPrModel1.C:104-114, QGDThermo.C:91-98)."""
+    gas = cases.GAS_OFFSET
+    c = cases.case_hex3d(n=(5, 4, 3), perturb=0.1, bcs="zg", gas=gas, dt=1e-7)
+    c.p0 = 1.0e5 * (1.0 + 0.05 * np.sin(3 * c.mesh.C[:, 0]))
+    c.T0 = 300.0 * (1.0 + 0.05 * np.cos(2 * c.mesh.C[:, 1]))
+    c.U0 = 30.0 * c.U0 / max(np.abs(c.U0).max(), 1e-30)
+    o = c.make_oracle(oracle_mod)
+    T, p, e, rho, U = o.get("T"), o.get("p"), o.get("e"), o.get("rho"), o.get("U")
+    R, Cp = gas["R"], gas["Cp"]
+    g = Cp / (Cp - R)
+    assert np.abs(T - c.T0).max() < 1e-9 * 300 and np.array_equal(p, c.p0)
+    assert np.abs(e - (Cp * (T - gas["Tref"]) + gas["Hsref"] - R * T)).max() < 1e-10 * np.abs(e).max()
+    assert np.abs(rho - p / (R * T)).max() < 1e-13 * rho.max()
+    assert np.abs(o.get("c") - np.sqrt(g * R * T)).max() < 1e-12 * 400
+    assert np.abs(o.get("rhoE") - rho * (e + 0.5 * (U ** 2).sum(1))).max() < 1e-12 * np.abs(o.get("rhoE")).max()
+    tau = 0.5 * o.hQGD() / o.get("c")
+    assert np.abs(o.get("tauQGD") - tau).max() < 1e-14 * tau.max()
+    muQ = p * gas["ScQGD"] * tau
+    assert np.abs(o.get("mu") - (gas["mu"] + muQ)).max() < 1e-13 * muQ.max()
+    assert np.abs(o.get("alpha") - (gas["mu"] / gas["Pr"] + muQ / gas["PrQGD"])).max() < 1e-13 * muQ.max()
