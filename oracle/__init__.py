@@ -122,11 +122,11 @@ def _f64(a):
 
 
 _CELL_K = {0: 1, 1: 3, 2: 1, 3: 3, 4: 1, 5: 1, 6: 1, 7: 1, 8: 1, 9: 1, 10: 1, 12: 1}
-_FACE_K = {0: 1, 1: 3, 2: 3, 3: 3, 4: 1, 5: 1, 6: 1, 7: 1, 8: 9, 9: 3, 10: 3, 11: 3, 12: 1}
+_FACE_K = {0: 1, 1: 3, 2: 3, 3: 3, 4: 1, 5: 1, 6: 1, 7: 1, 8: 9, 9: 3, 10: 3, 11: 3, 12: 1, 13: 3, 14: 1}
 CELL_FIELDS = {"rho": 0, "rhoU": 1, "rhoE": 2, "U": 3, "e": 4, "p": 5, "T": 6, "c": 7, "mu": 8, "alpha": 9,
                "tauQGD": 10, "ScQGD": 12}
 FACE_FIELDS = {"phiJm": 0, "phiJmU": 1, "phiP": 2, "phiPi": 3, "phiJmH": 4, "phiQ": 5, "phiPiU": 6,
-               "tauQGDf": 7, "gradUf": 8, "gradef": 9, "gradRhof": 10, "gradPf": 11, "phiwStar": 12}
+               "tauQGDf": 7, "gradUf": 8, "gradef": 9, "gradRhof": 10, "gradPf": 11, "phiwStar": 12, "phiTauMC": 13, "phiSigmaDotU": 14}
 
 
 class Oracle:

@@ -1410,6 +1410,7 @@ void or_qgd_get_face(or_ctx* s, int field, double* out)
         case 6: v = &s->phiPiU; break; case 7: v = &s->tauQGDf; break; case 8: v = &s->gradUf; break;
         case 9: v = &s->gradef; break; case 10: v = &s->gradRhof; break; case 11: v = &s->gradPf; break;
         case 12: v = &s->phiw; break;
+        case 13: v = &s->phiTauMC; break; case 14: v = &s->phiSigmaDotU; break;
         default: return;
     }
     std::copy(v->begin(), v->end(), out);
