@@ -784,3 +784,79 @@ def test_qhd_temperature_equation_matches_numpy_restatement(oracle_mod):
     flux = phi * Tf - Hi * sn * m.magSf - tau * phiu * np.einsum("fi,fi->f", Uf, gT)
     Tnew = T0 - c.dt / m.V * _surface_integrate(m, flux)
     assert np.abs(o.qhd_get("T") - Tnew).max() < 1e-13 * np.abs(Tnew).max()
+
+
+def test_qhd_momentum_equation_matches_numpy_restatement(oracle_mod):
+    """QHDUEqn.H:36-85 (explicit branch) restated with numpy from the oracle's phi, tauQGDf, gradUf, gradPf and the solved p:
+    ddt(U) + div(phi Uf - Sf & (Uf*Wf)) - laplacian(nu, U) - div((nu Sf) & interpolate(T(grad U))) == -grad(p)/rho + BdFrc."""
+    import cases
+    c = cases.qhd_cavity(n=(7, 6, 5), dims=3, dt=1e-3, perturb=0.15)
+    m = c.mesh
+    nI, nC = m.n_internal, m.n_cells
+    o = c.make_oracle(oracle_mod)
+    (U0, UB0), (T0, TB0) = o.qhd_get("U", with_bnd=True), o.qhd_get("T", with_bnd=True)
+    c.oracle_step(o, 1)
+    f = c.fluid
+    nu, g, beta = f["mu"] / f["rho0"], np.asarray(f["g"]), f["beta"]
+    Sf, V = m.Sf, m.V
+    Uf = o.linear_interpolate(U0, UB0)
+    Bf = o.linear_interpolate(beta * T0[:, None] * g[None], beta * TB0[:, None] * g[None])
+    phi, phiu, tau = (o.qhd_get_face(k) for k in ("phi", "phiu", "tauQGDf"))
+    gU, gP = o.qhd_get_face("gradUf").reshape(-1, 3, 3), o.qhd_get_face("gradPf")
+    Wf = tau[:, None] * (np.einsum("fi,fij->fj", Uf, gU) + gP / f["rho0"] - Bf)
+    phiUf = phi[:, None] * Uf - phiu[:, None] * Wf
+    sn = np.zeros((m.n_faces, 3))
+    sn[:nI] = m.nonOrthDeltaCoeffs[:nI, None] * (U0[m.neighbour] - U0[m.owner[:nI]])
+    fixedU = c.bcU[m.patch_id_per_bface()] == cases.FV
+    sn[nI:] = np.where(fixedU[:, None], m.deltaCoeffs[nI:, None] * (UB0 - U0[m.owner[nI:]]), 0.0)
+    lap = nu * sn * m.magSf[:, None]
+    gradU = _surface_integrate(m, np.einsum("fi,fj->fij", Sf, Uf)) / V[:, None, None]             # Gauss linear, grad(U)_ij = d_i U_j
+    nrm = Sf[nI:] / m.magSf[nI:, None]
+    gP_ = gradU[m.owner[nI:]]
+    gradUB = gP_ + np.einsum("bi,bj->bij", nrm, sn[nI:] - np.einsum("bi,bij->bj", nrm, gP_))      # gaussGrad::correctBoundaryConditions
+    GTf = o.linear_interpolate(np.swapaxes(gradU, 1, 2).reshape(nC, 9), np.swapaxes(gradUB, 1, 2).reshape(-1, 9)).reshape(-1, 3, 3)
+    flux2 = np.einsum("fi,fij->fj", nu * Sf, GTf)
+    p, pB = o.qhd_get("p", with_bnd=True)
+    # p as it stood when the U equation was formed: before the reference shift of QHDFoam.C:123-131 (a constant: no effect on grad p
+    # except through the boundary values, which were shifted alike)
+    pf = o.linear_interpolate(p, pB)
+    gradp = _surface_integrate(m, Sf * pf[:, None]) / V[:, None]
+    rhs = -_surface_integrate(m, phiUf) / V[:, None] + _surface_integrate(m, lap) / V[:, None] + _surface_integrate(m, flux2) / V[:, None] \
+        - gradp / f["rho0"] + beta * T0[:, None] * g[None]
+    Unew = U0 + c.dt * rhs
+    assert np.abs(o.qhd_get("U") - Unew).max() < 1e-11 * np.abs(Unew).max()
+
+
+def test_qhd_pressure_equation_matches_a_sparse_direct_solve(oracle_mod):
+    """QHDpEqn.H:33-48: -laplacian(tauQGDf/rhof, p) == -div(phiu - phiwo) with a fixedValue p patch (no reference cell),
+    assembled independently with scipy.sparse and solved directly; the oracle's PCG pressure agrees."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    import cases
+    c = cases.qhd_cavity(n=(8, 7, 5), dims=3, dt=1e-3, perturb=0.1, tol=1e-15)
+    m = c.mesh
+    names = [p.name for p in m.patches]
+    pid = m.patch_id_per_bface()
+    c.bcP[names.index("yMax")] = cases.FV
+    c.bvP[pid == names.index("yMax")] = 0.02
+    c.bcP[names.index("xMin")] = cases.FG                      # fixedGradient p on one wall
+    c.bvP[pid == names.index("xMin")] = 0.3
+    for nm in ("xMax", "yMin", "zMin", "zMax"):
+        c.bcP[names.index(nm)] = cases.ZG
+    nI, nC = m.n_internal, m.n_cells
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 1)
+    phiu, phiwo, tau = (o.qhd_get_face(k) for k in ("phiu", "phiwo", "tauQGDf"))
+    a = (tau / c.fluid["rho0"]) * m.magSf * m.nonOrthDeltaCoeffs
+    A = sp.coo_matrix((np.concatenate([a[:nI], a[:nI], -a[:nI], -a[:nI]]),
+                       (np.concatenate([m.owner[:nI], m.neighbour, m.owner[:nI], m.neighbour]),
+                        np.concatenate([m.owner[:nI], m.neighbour, m.neighbour, m.owner[:nI]]))), shape=(nC, nC)).tocsr()
+    nb = m.owner[nI:]
+    kind = c.bcP[pid]
+    dI, rhs = np.zeros(nC), -_surface_integrate(m, phiu - phiwo)
+    fv, fg = kind == cases.FV, kind == cases.FG
+    np.add.at(dI, nb[fv], a[nI:][fv])
+    np.add.at(rhs, nb[fv], a[nI:][fv] * c.bvP[fv])
+    np.add.at(rhs, nb[fg], ((tau / c.fluid["rho0"]) * m.magSf)[nI:][fg] * c.bvP[fg])     # gradient() |Sf| tau/rho
+    x = spl.spsolve((A + sp.diags(dI)).tocsc(), rhs)
+    assert np.abs(o.qhd_get("p") - x).max() < 1e-10 * np.abs(x).max()
