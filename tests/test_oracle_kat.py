@@ -860,3 +860,60 @@ def test_qhd_pressure_equation_matches_a_sparse_direct_solve(oracle_mod):
     np.add.at(rhs, nb[fg], ((tau / c.fluid["rho0"]) * m.magSf)[nI:][fg] * c.bvP[fg])     # gradient() |Sf| tau/rho
     x = spl.spsolve((A + sp.diags(dI)).tocsc(), rhs)
     assert np.abs(o.qhd_get("p") - x).max() < 1e-10 * np.abs(x).max()
+
+
+@pytest.mark.parametrize("axis", [0, 1, 2])
+def test_gaussvolpoint_2d_matches_numpy_restatement(oracle_mod, axis):
+    """GaussVolPointBase2D.C:122-169 (ctor, internal faces) and :315-329 (faceGrad) restated literally with numpy on a
+    distorted one-cell-thick mesh: ip1 / ip3 = the first two face points on the upper side of the neighbour centre,
+    v42 = C_N - C_P, v13 = x_3 - x_1, the direction cosines / sines w.r.t. e1, e2 and
+    g_e1 = dfdn c1 - dfdt c2, g_e2 = dfdt c3 - dfdn c4, g_e3 = 0."""
+    mesh = cases.case_2d((9, 7), perturb=0.2, axis=axis).mesh
+    o = oracle_mod.Oracle(mesh)
+    nI = mesh.n_internal
+    ie3 = axis
+    ie1, ie2 = [d for d in range(3) if d != ie3]
+    rng = np.random.default_rng(9)
+    phi = np.sin(3 * mesh.C[:, ie1]) + mesh.C[:, ie2] ** 2 + 0.1 * rng.random(mesh.n_cells)
+    bnd = np.cos(2 * mesh.Cf[nI:, ie1]) + 0.1 * rng.random(mesh.n_bnd)
+    bsg = mesh.deltaCoeffs[nI:] * (bnd - phi[mesh.owner[nI:]])
+    got = o.fvsc_grad(phi, bnd, bsg)
+    pF = o.vol_point_interpolate(phi, bnd)
+    ref = np.zeros((nI, 3))
+    for f in range(nI):
+        ic2, ic4 = mesh.neighbour[f], mesh.owner[f]
+        fv = mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]
+        up = [v for v in fv if mesh.points[v][ie3] >= mesh.C[ic2][ie3]]
+        ip1, ip3 = up[0], up[1]
+        v42, v13 = mesh.C[ic2] - mesh.C[ic4], mesh.points[ip3] - mesh.points[ip1]
+        m42, m13 = np.linalg.norm(v42), np.linalg.norm(v13)
+        cosa1, cosa2, sina1, sina2 = v42[ie1] / m42, v13[ie1] / m13, v42[ie2] / m42, v13[ie2] / m13
+        den = sina2 * cosa1 - sina1 * cosa2
+        dfdn, dfdt = (phi[ic2] - phi[ic4]) / m42, (pF[ip3] - pF[ip1]) / m13
+        ref[f, ie1] = dfdn * (sina2 / den) - dfdt * (sina1 / den)
+        ref[f, ie2] = dfdt * (cosa1 / den) - dfdn * (cosa2 / den)
+    assert np.abs(got[:nI] - ref).max() < 1e-12 * np.abs(ref).max()
+
+
+def test_gaussvolpoint_3d_boundary_faces_use_the_mirrored_ghost(oracle_mod):
+    """GaussVolPointBase3D.C:129-154, 391-415, 780-801: on an ordinary patch the 'neighbour' of a boundary quad face is the
+    owner centre mirrored through the face centre, v5 = Cn + 2 (Cf - Cn), carrying psi_n = phi_b + snGrad_b |vO - vN| / 2;
+    the same six-point formula as on internal faces then applies (closed form of SURVEY A.2)."""
+    mesh = cases.pm.hex_box(5, 4, 4, perturb=0.2, seed=12)
+    rng = np.random.default_rng(3)
+    nI = mesh.n_internal
+    phi, bnd, bsg = rng.random(mesh.n_cells), rng.random(mesh.n_bnd), rng.random(mesh.n_bnd) - 0.5      # any patch snGrad
+    o = oracle_mod.Oracle(mesh)
+    g = o.fvsc_grad(phi, bnd, bsg)[nI:]
+    pf = o.vol_point_interpolate(phi, bnd)
+    fv = mesh.face_verts.reshape(-1, 4)[nI:]
+    p = mesh.points[fv]
+    Cn = mesh.C[mesh.owner[nI:]]
+    v5 = Cn + 2.0 * (mesh.Cf[nI:] - Cn)
+    d = v5 - Cn
+    psin = bnd + bsg * np.linalg.norm(Cn - v5, axis=1) * 0.5
+    e1, e2 = p[:, 1] - p[:, 3], p[:, 2] - p[:, 0]
+    D = (e2 * np.cross(e1, d)).sum(1)
+    ref = (np.cross(d, e1) * (pf[fv[:, 0]] - pf[fv[:, 2]])[:, None] + np.cross(d, e2) * (pf[fv[:, 1]] - pf[fv[:, 3]])[:, None]
+           + np.cross(e1, e2) * (phi[mesh.owner[nI:]] - psin)[:, None]) / D[:, None]
+    assert np.abs(g - ref).max() / np.abs(ref).max() < 1e-12
