@@ -917,3 +917,44 @@ def test_gaussvolpoint_3d_boundary_faces_use_the_mirrored_ghost(oracle_mod):
     ref = (np.cross(d, e1) * (pf[fv[:, 0]] - pf[fv[:, 2]])[:, None] + np.cross(d, e2) * (pf[fv[:, 1]] - pf[fv[:, 3]])[:, None]
            + np.cross(e1, e2) * (phi[mesh.owner[nI:]] - psin)[:, None]) / D[:, None]
     assert np.abs(g - ref).max() / np.abs(ref).max() < 1e-12
+
+
+def test_gaussvolpoint_3d_triangular_faces_match_literal_coefficients(oracle_mod):
+    """GaussVolPointBase3D.C:175-229 (triCalcWeights) typed in literally: five coefficients per direction for the three
+    face points, the neighbour (index 3) and the owner (index 4), divided by vt = ((p2-p1)^(p3-p1)) & (C_own - C_nei) / 6
+    (the dfdxif macro, :488-513)."""
+    mesh = cases.pm.prism_box(4, 3, 3, perturb=0.15, seed=4)
+    rng = np.random.default_rng(5)
+    nI = mesh.n_internal
+    phi, bnd = rng.random(mesh.n_cells), rng.random(mesh.n_bnd)
+    bsg = mesh.deltaCoeffs[nI:] * (bnd - phi[mesh.owner[nI:]])
+    o = oracle_mod.Oracle(mesh)
+    g = o.fvsc_grad(phi, bnd, bsg)
+    pf = o.vol_point_interpolate(phi, bnd)
+    n = 0
+    for f in range(nI):
+        fv = mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]
+        if fv.size != 3:
+            continue
+        n += 1
+        own, nei = mesh.C[mesh.owner[f]], mesh.C[mesh.neighbour[f]]
+        p1, p2, p3 = (mesh.points[v] for v in fv)
+        x, y, z = 0, 1, 2
+        vt = np.dot(np.cross(p2 - p1, p3 - p1), own - nei) / 6.0
+        S = 1.0 / 6.0
+        atx = [S * ((own[z] - nei[z]) * (p2[y] - p3[y]) + (nei[y] - own[y]) * (p2[z] - p3[z])),
+               S * ((nei[y] - own[y]) * (p3[z] - p1[z]) + (own[z] - nei[z]) * (p3[y] - p1[y])),
+               S * ((nei[y] - own[y]) * (p1[z] - p2[z]) + (own[z] - nei[z]) * (p1[y] - p2[y])),
+               S * (p1[z] * (p2[y] - p3[y]) + p2[z] * (p3[y] - p1[y]) + p3[z] * (p1[y] - p2[y]))]
+        aty = [S * ((own[x] - nei[x]) * (p2[z] - p3[z]) + (nei[z] - own[z]) * (p2[x] - p3[x])),
+               S * ((nei[z] - own[z]) * (p3[x] - p1[x]) + (own[x] - nei[x]) * (p3[z] - p1[z])),
+               S * ((nei[z] - own[z]) * (p1[x] - p2[x]) + (own[x] - nei[x]) * (p1[z] - p2[z])),
+               S * (p1[x] * (p2[z] - p3[z]) + p2[x] * (p3[z] - p1[z]) + p3[x] * (p1[z] - p2[z]))]
+        atz = [S * ((own[y] - nei[y]) * (p2[x] - p3[x]) + (nei[x] - own[x]) * (p2[y] - p3[y])),
+               S * ((nei[x] - own[x]) * (p3[y] - p1[y]) + (own[y] - nei[y]) * (p3[x] - p1[x])),
+               S * ((nei[x] - own[x]) * (p1[y] - p2[y]) + (own[y] - nei[y]) * (p1[x] - p2[x])),
+               S * (p1[y] * (p2[x] - p3[x]) + p2[y] * (p3[x] - p1[x]) + p3[y] * (p1[x] - p2[x]))]
+        vals = [pf[fv[0]], pf[fv[1]], pf[fv[2]], phi[mesh.neighbour[f]], phi[mesh.owner[f]]]
+        ref = np.array([sum(a * v for a, v in zip(A + [-A[3]], vals)) / vt for A in (atx, aty, atz)])
+        assert np.abs(g[f] - ref).max() < 1e-11 * max(np.abs(ref).max(), 1.0), f
+    assert n > 0
