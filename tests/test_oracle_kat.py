@@ -958,3 +958,48 @@ def test_gaussvolpoint_3d_triangular_faces_match_literal_coefficients(oracle_mod
         ref = np.array([sum(a * v for a, v in zip(A + [-A[3]], vals)) / vt for A in (atx, aty, atz)])
         assert np.abs(g[f] - ref).max() < 1e-11 * max(np.abs(ref).max(), 1.0), f
     assert n > 0
+
+
+@pytest.mark.parametrize("mesh_fn", [lambda: cases.case_2d((9, 8), perturb=0.2).mesh, lambda: cases.case_2d((6, 40)).mesh,
+                                     lambda: cases.case_sod(30).mesh])
+def test_least_squares_internal_faces_match_literal_restatement(oracle_mod, mesh_fn):
+    """extendedFaceStencilFindNeighbours.C:48-84 (cells around the face's points), extendedFaceStencilCalculateWeights.C:60-154
+    (wf2 = 1/|df|^2, G = sum wf2 df df + G0 on the empty directions, inverted unless det(G) < 1, minus G0) and
+    extendedFaceStencilScalarGrad.C:52-83 (sum wf2 (G df)(phi_c - phi_f); degenerate faces: nf*snGrad) in plain numpy."""
+    mesh = mesh_fn()
+    nI = mesh.n_internal
+    rng = np.random.default_rng(8)
+    d = np.nonzero(mesh.geometric_d > 0)[0]
+    phi = np.sin(3 * mesh.C[:, d[0]]) + 0.2 * rng.random(mesh.n_cells)
+    bnd = rng.random(mesh.n_bnd)
+    bsg = mesh.deltaCoeffs[nI:] * (bnd - phi[mesh.owner[nI:]])
+    o = oracle_mod.Oracle(mesh)
+    got = o.fvsc_grad(phi, bnd, bsg, scheme=oracle_mod.FVSC_SCHEMES["leastSquares"])
+    sF = o.linear_interpolate(phi, bnd)
+    point_cells = [[] for _ in range(mesh.n_points)]
+    for f in range(mesh.n_faces):
+        for cidx in [mesh.owner[f]] + ([mesh.neighbour[f]] if f < nI else []):
+            for v in mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]:
+                if cidx not in point_cells[v]:
+                    point_cells[v].append(cidx)
+    ndeg = 0
+    for f in range(nI):
+        cells = []
+        for v in mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]:
+            for cidx in point_cells[v]:
+                if cidx not in cells:
+                    cells.append(cidx)
+        df = mesh.C[cells] - mesh.Cf[f]
+        wf2 = 1.0 / (df * df).sum(1)
+        G = np.einsum("c,ci,cj->ij", wf2, df, df)
+        G0 = np.diag([1.0 if abs(G[i, i]) < 1e-15 else 0.0 for i in range(3)])
+        G = G + G0
+        if np.linalg.det(G) < 1:
+            ndeg += 1
+            nf = mesh.Sf[f] / mesh.magSf[f]
+            ref = mesh.nonOrthDeltaCoeffs[f] * (phi[mesh.neighbour[f]] - phi[mesh.owner[f]]) * nf
+        else:
+            Gi = np.linalg.inv(G) - G0
+            ref = np.einsum("c,ci,c->i", wf2, df @ Gi.T, phi[cells] - sF[f])
+        assert np.abs(got[f] - ref).max() < 1e-10 * max(np.abs(ref).max(), 1.0), f
+    assert ndeg > 0 or mesh.n_cells != 240          # the 6 x 40 mesh (aspect ratio ~7) has degenerate stencils
