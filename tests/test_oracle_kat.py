@@ -1003,3 +1003,29 @@ def test_least_squares_internal_faces_match_literal_restatement(oracle_mod, mesh
             ref = np.einsum("c,ci,c->i", wf2, df @ Gi.T, phi[cells] - sF[f])
         assert np.abs(got[f] - ref).max() < 1e-10 * max(np.abs(ref).max(), 1.0), f
     assert ndeg > 0 or mesh.n_cells != 240          # the 6 x 40 mesh (aspect ratio ~7) has degenerate stencils
+
+
+def test_qgdflux_boundary_condition_closes_the_step_as_the_listing_says(oracle_mod):
+    """qgdFluxFvPatchScalarField.C:159-197 + fixedGradient evaluate [OF]: at the p.correctBoundaryConditions() that ends
+    the step (QGDFoam.C:155) gradient = -phiwStar/tauQGDf/|Sf| with this step's phiwStar and the tauQGDf just refreshed by
+    thermo.correct(), p_b = p_P + gradient/deltaCoeffs; then rho_b = psi_b p_b (QGDFoam.C:156)."""
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="qgdflux")
+    c.bcU[:] = cases.ZG                                                   # a moving boundary fluid: phiwStar != 0 on the patches
+    m = c.mesh
+    nI = m.n_internal
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 3)
+    p, pB = o.get("p", with_bnd=True)
+    phiw, tauf = o.get_face("phiwStar"), o.get_face("tauQGDf")
+    grad = -(phiw[nI:] / tauf[nI:] / m.magSf[nI:])
+    assert np.abs(pB - (p[m.owner[nI:]] + grad / m.deltaCoeffs[nI:])).max() < 1e-14 * p.max()
+    assert np.abs(grad).max() > 1e-8                                      # the condition is active
+    T, TB = o.get("T", with_bnd=True)
+    rhoB = o.get("rho", with_bnd=True)[1]
+    assert np.abs(rhoB - pB / (c.gas["R"] * TB)).max() < 1e-13
+    # with no-slip walls (U_b = 0) every term of rhoW carries Uf or rhoUf: phiwStar and the gradient vanish identically
+    w = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="qgdflux")
+    ow = w.make_oracle(oracle_mod)
+    w.oracle_step(ow, 3)
+    assert np.abs(ow.get_face("phiwStar")[nI:]).max() == 0.0
+    assert np.array_equal(ow.get("p", with_bnd=True)[1], ow.get("p")[m.owner[nI:]])

@@ -1,0 +1,39 @@
+"""GPU parity cases written after the round's GPU budget was spent: they have never run on a device.  They are marked
+xfail(strict=False) so that an unexpected mismatch does not hide the verified suite behind `-x`; an XPASS at the
+round-end run means the marker can simply be dropped.  (File name sorts last on purpose.)"""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+TOL_STEP = 1e-10
+NOT_RUN = pytest.mark.xfail(strict=False, reason="written without GPU access (budget exhausted); first run is the driver's")
+
+
+def _open_qgdflux_case(**kw):
+    """qgdFlux p on every patch with zeroGradient U: the boundary fluid moves, so phiwStar and the qgdFlux gradient are
+    NOT identically zero (with the no-slip walls of the other qgdFlux cases every term of rhoW vanishes on the patch)."""
+    c = cases.case_hex3d(perturb=0.15, bcs="qgdflux", **kw)
+    c.bcU[:] = cases.ZG
+    return c
+
+
+@NOT_RUN
+@pytest.mark.parametrize("kw", [dict(), dict(implicit=True), dict(model="varScModel6"), dict(scheme="reduced")],
+                         ids=["explicit", "implicit", "varSc6", "reduced"])
+def test_active_qgdflux_gradient_matches_oracle(qgd, oracle_mod, kw):
+    c = _open_qgdflux_case(**kw)
+    o = c.make_oracle(oracle_mod)
+    s = c.make_solver(qgd)
+    c.oracle_step(o, 60)
+    s.step(60)
+    nI = c.mesh.n_internal
+    if kw.get("scheme") != "reduced":
+        assert np.abs(o.get_face("phiwStar")[nI:]).max() > 1e-8           # the condition is active
+    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T"):
+        gc, gb = s.get(f, with_bnd=True)
+        oc, ob = o.get(f, with_bnd=True)
+        scale = float(np.abs(oc).max())
+        assert float(np.abs(gc - oc).max()) / scale < TOL_STEP, f
+        assert float(np.abs(gb - ob).max()) / scale < TOL_STEP, f"boundary {f}"
