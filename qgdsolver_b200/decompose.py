@@ -75,24 +75,21 @@ class SubDomain:
 
 
 def _point_cells(mesh: PolyMesh):
+    """(point, cell) incidences, one per (face vertex, face cell) - a pair may repeat (a point is reached through several
+    faces of the same cell); every consumer is a boolean scatter, so duplicates are harmless and the 50 M-entry
+    `unique` they would cost at 256^3 is not paid."""
     nv = mesh.face_nverts()
-    fo = np.repeat(mesh.owner, nv)
-    pts_o = mesh.face_verts
     nI = mesh.n_internal
-    nvi = nv[:nI]
-    fn = np.repeat(mesh.neighbour, nvi)
-    pts_n = mesh.face_verts[:mesh.face_offsets[nI]]
-    p = np.concatenate([pts_o, pts_n])
-    c = np.concatenate([fo, fn])
-    key = np.unique(p.astype(np.int64) * mesh.n_cells + c)
-    return (key // mesh.n_cells).astype(np.int64), (key % mesh.n_cells).astype(np.int64)
+    p = np.concatenate([mesh.face_verts, mesh.face_verts[:mesh.face_offsets[nI]]]).astype(np.int64)
+    c = np.concatenate([np.repeat(mesh.owner, nv), np.repeat(mesh.neighbour, nv[:nI])]).astype(np.int64)
+    return p, c
 
 
 def extended_submeshes(mesh: PolyMesh, cell_rank: np.ndarray, ranks=None) -> List[SubDomain]:
     """Build the extended sub-mesh (+ exchange lists) of every rank in `ranks` (default: all)."""
     n_parts = int(cell_rank.max()) + 1
     ranks = list(range(n_parts)) if ranks is None else list(ranks)
-    pp, pc = _point_cells(mesh)                     # (point, cell) incidences, sorted by point
+    pp, pc = _point_cells(mesh)                     # (point, cell) incidences (with repeats)
     nI = mesh.n_internal
     nv = mesh.face_nverts()
     out = []
