@@ -58,10 +58,9 @@ def test_product_does_not_touch_the_oracle():
     assert "oracle" not in out
 
 
-def test_desc_struct_layout_matches_header():
-    # field order / count of the ctypes mirrors follows the C declarations
-    hdr = open(os.path.join(ROOT, "include", "qgd_b200.h")).read()
-    body = hdr[hdr.index("typedef struct {\n    const char* fvsc_scheme;"):hdr.index("} qgd_qgdfoam_desc;")]
+def _struct_fields(hdr, end_marker):
+    end = hdr.index(end_marker)
+    body = hdr[hdr.rindex("typedef struct {", 0, end):end]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
     for decl in body.split(";"):
@@ -69,6 +68,14 @@ def test_desc_struct_layout_matches_header():
         if not decl:
             continue
         first, *rest = decl.split(",")
-        names.append(first.split()[-1].lstrip("*"))
-        names += [r.strip().lstrip("*") for r in rest]
-    assert names == [f[0] for f in api.QGDFoamDesc._fields_]
+        names.append(re.sub(r"\[\d+\]", "", first.split()[-1].lstrip("*")))
+        names += [re.sub(r"\[\d+\]", "", r.strip().lstrip("*")) for r in rest]
+    return names
+
+
+def test_desc_struct_layout_matches_header():
+    # field order / count of the ctypes mirrors follows the C declarations
+    hdr = open(os.path.join(ROOT, "include", "qgd_b200.h")).read()
+    assert _struct_fields(hdr, "} qgd_qgdfoam_desc;") == [f[0] for f in api.QGDFoamDesc._fields_]
+    assert _struct_fields(hdr, "} qgd_qhdfoam_desc;") == [f[0] for f in api.QHDFoamDesc._fields_]
+    assert _struct_fields(hdr, "} qgd_mesh_desc;") == [f[0] for f in api._MeshDesc._fields_]
