@@ -96,6 +96,9 @@ def lib():
         L.or_qgd_get_face.argtypes = [C.c_void_p, C.c_int, _dp]
         L.or_pcg_solve.restype = C.c_int
         L.or_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp]
+        L.or_set_pcg_blocks.argtypes = [C.c_void_p, _ip]
+        L.or_pcg_solve_blocks.restype = C.c_int
+        L.or_pcg_solve_blocks.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _ip]
         L.or_qhd_init.argtypes = [C.c_void_p, C.POINTER(QHDParams), C.c_int, _ip, _ip, _ip, _dp, _dp, _dp,
                                   _dp, _dp, _dp, _dp, C.c_double]
         L.or_qhd_step.restype = C.c_double
@@ -245,12 +248,26 @@ class Oracle:
         lib().or_qgd_get_face(self._h, fid, _d(out))
         return out
 
-    def pcg_solve(self, diag, upper, b, x0, tol=1e-8, relTol=0.0, maxIter=1000, precond=2):
+    def set_pcg_blocks(self, cell_block=None):
+        """linear solvers of the following steps in the decomposed-run form (block-local preconditioner)"""
+        if cell_block is None:
+            lib().or_set_pcg_blocks(self._h, None)
+        else:
+            cb = np.ascontiguousarray(cell_block, np.int32)
+            lib().or_set_pcg_blocks(self._h, _i(cb))
+
+    def pcg_solve(self, diag, upper, b, x0, tol=1e-8, relTol=0.0, maxIter=1000, precond=2, cell_block=None):
+        """cell_block: processor of each cell -> the decomposed-run solver (block-local preconditioner, global reductions)"""
         diag, upper, b = _f64(diag), _f64(upper), _f64(b)
         x = np.array(x0, dtype=np.float64, copy=True)
         r0, r1 = C.c_double(), C.c_double()
-        it = lib().or_pcg_solve(self._h, _d(diag), _d(upper), _d(b), _d(x), tol, relTol, maxIter, precond,
-                                C.byref(r0), C.byref(r1))
+        if cell_block is None:
+            it = lib().or_pcg_solve(self._h, _d(diag), _d(upper), _d(b), _d(x), tol, relTol, maxIter, precond,
+                                    C.byref(r0), C.byref(r1))
+        else:
+            cb = np.ascontiguousarray(cell_block, np.int32)
+            it = lib().or_pcg_solve_blocks(self._h, _d(diag), _d(upper), _d(b), _d(x), tol, relTol, maxIter, precond,
+                                           C.byref(r0), C.byref(r1), _i(cb))
         return x, it, r0.value, r1.value
 
     # ---- QHDFoam

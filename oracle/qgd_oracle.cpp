@@ -91,6 +91,7 @@ struct or_ctx {
     Vec aQGD, aQGDB, tauQGD, tauQGDB, muQGD, muQGDB, alphauQGD, alphauQGDB, ScQGD, ScQGDB, PrQGD, PrQGDB, hQGDB;
     Vec pGrad;                  // qgdFlux gradient per bface
     IVec constScCells;          // varScModel7 constScCellSet
+    IVec pcgBlocks;             // processor of each cell for the linear solvers of a decomposed run (empty = serial)
     Vec suRho, suU, suE;        // explicit source matrices rhoSu / rhoUSu / rhoESu: volume-integrated source per cell (empty = zero)
     // surface fields (nFaces*k)
     Vec tauQGDf, rhof, Uf, rhoUf, UrhoUf, pf, cf, gammaf, Hf, alphauf, muf;
@@ -1182,6 +1183,9 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
 
 double or_qgd_deltaT(or_ctx* s) { return s->deltaT; }
 void or_qgd_set_const_sc_cells(or_ctx* s, const int* cells, int n) { s->constScCells.assign(cells, cells + n); }
+void or_set_pcg_blocks(or_ctx* s, const int* cellBlock) { if (cellBlock) s->pcgBlocks.assign(cellBlock, cellBlock + s->nCells); else s->pcgBlocks.clear(); }
+int or_pcg_solve_blocks(or_ctx* sp, const double* diag, const double* upper, const double* b, double* x, double tol,
+                        double relTol, int maxIter, int precond, double* initRes, double* finalRes, const int* cellBlock);
 void or_qgd_set_sources(or_ctx* s, const double* suRho, const double* suU, const double* suE)
 {
     const size_t n = s->nCells;
@@ -1268,8 +1272,8 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
                     diag[P] += gS * s.ndC[f];
                     src[P] += gS * (s.ndC[f] * s.UB[3 * (size_t)b + j]);
                 }
-                s.lastDiffIters[j] = or_pcg_solve(sp, diag.data(), upper.data(), src.data(), x.data(), s.prm.diffTol, s.prm.diffRelTol,
-                                                  s.prm.diffMaxIter, s.prm.diffPrecond, nullptr, nullptr);
+                s.lastDiffIters[j] = or_pcg_solve_blocks(sp, diag.data(), upper.data(), src.data(), x.data(), s.prm.diffTol, s.prm.diffRelTol,
+                                                  s.prm.diffMaxIter, s.prm.diffPrecond, nullptr, nullptr, s.pcgBlocks.empty() ? nullptr : s.pcgBlocks.data());
                 for (int c = 0; c < nC; ++c) s.U[3 * (size_t)c + j] = x[c];
             }
             correctU(s);
@@ -1345,8 +1349,8 @@ double or_qgd_step(or_ctx* sp, int nSteps, int adjustTimeStep, double maxCo, dou
                 diag[P] += gS * s.ndC[f];
                 src[P] += gS * (s.ndC[f] * s.eB[b]);
             }
-            s.lastDiffIters[3] = or_pcg_solve(sp, diag.data(), upper.data(), src.data(), s.e.data(), s.prm.diffTol, s.prm.diffRelTol,
-                                              s.prm.diffMaxIter, s.prm.diffPrecond, nullptr, nullptr);
+            s.lastDiffIters[3] = or_pcg_solve_blocks(sp, diag.data(), upper.data(), src.data(), s.e.data(), s.prm.diffTol, s.prm.diffRelTol,
+                                              s.prm.diffMaxIter, s.prm.diffPrecond, nullptr, nullptr, s.pcgBlocks.empty() ? nullptr : s.pcgBlocks.data());
             correctE(s);
             for (int c = 0; c < nC; ++c) {
                 const double* u = &s.U[3 * (size_t)c];
@@ -1417,8 +1421,22 @@ void or_qgd_get_face(or_ctx* s, int field, double* out)
 }
 
 // [OF-v2312] lduMatrix PCG with DIC / diagonal / no preconditioner; symmetric matrix
+int or_pcg_solve_blocks(or_ctx* sp, const double* diag, const double* upper, const double* b, double* x, double tol,
+                        double relTol, int maxIter, int precond, double* initRes, double* finalRes, const int* cellBlock);
+
 int or_pcg_solve(or_ctx* sp, const double* diag, const double* upper, const double* b, double* x, double tol,
                  double relTol, int maxIter, int precond, double* initRes, double* finalRes)
+{
+    return or_pcg_solve_blocks(sp, diag, upper, b, x, tol, relTol, maxIter, precond, initRes, finalRes, nullptr);
+}
+
+// The same solver as `mpirun -np N` runs it [OF-v2312 PCG on a decomposed lduMatrix]: the matrix, the dot products
+// (gSumProd) and the residual norms (gSumMag, normFactor with the global average) are those of the whole mesh; only the
+// preconditioner is block-local - DIC is factorised and swept on each processor's own block, faces between cells of
+// different blocks (processor interfaces) are left out of it (DICPreconditioner works on the local lduMatrix).
+// cellBlock: processor of each cell, or NULL = one block (the serial solver).
+int or_pcg_solve_blocks(or_ctx* sp, const double* diag, const double* upper, const double* b, double* x, double tol,
+                        double relTol, int maxIter, int precond, double* initRes, double* finalRes, const int* cellBlock)
 {
     const or_ctx& s = *sp;
     const int n = s.nCells, nf = s.nInternal;
@@ -1427,6 +1445,7 @@ int or_pcg_solve(or_ctx* sp, const double* diag, const double* upper, const doub
         for (int c = 0; c < n; ++c) y[c] = diag[c] * v[c];
         for (int f = 0; f < nf; ++f) { y[u[f]] += upper[f] * v[l[f]]; y[l[f]] += upper[f] * v[u[f]]; }
     };
+    auto inBlock = [&](int f) { return !cellBlock || cellBlock[l[f]] == cellBlock[u[f]]; };
     Vec wA(n), pA(n, 0.0), rA(n), rD;
     Amul(wA, x);
     for (int c = 0; c < n; ++c) rA[c] = b[c] - wA[c];
@@ -1445,7 +1464,7 @@ int or_pcg_solve(or_ctx* sp, const double* diag, const double* upper, const doub
     if (!converged()) {
         if (precond == 2) {
             rD.assign(diag, diag + n);
-            for (int f = 0; f < nf; ++f) rD[u[f]] -= upper[f] * upper[f] / rD[l[f]];
+            for (int f = 0; f < nf; ++f) if (inBlock(f)) rD[u[f]] -= upper[f] * upper[f] / rD[l[f]];
             for (int c = 0; c < n; ++c) rD[c] = 1.0 / rD[c];
         } else if (precond == 1) { rD.resize(n); for (int c = 0; c < n; ++c) rD[c] = 1.0 / diag[c]; }
         double wArA = 1e20, wArAold = wArA;
@@ -1455,8 +1474,8 @@ int or_pcg_solve(or_ctx* sp, const double* diag, const double* upper, const doub
             else {
                 for (int c = 0; c < n; ++c) wA[c] = rD[c] * rA[c];
                 if (precond == 2) {
-                    for (int f = 0; f < nf; ++f) wA[u[f]] -= rD[u[f]] * upper[f] * wA[l[f]];
-                    for (int f = nf - 1; f >= 0; --f) wA[l[f]] -= rD[l[f]] * upper[f] * wA[u[f]];
+                    for (int f = 0; f < nf; ++f) if (inBlock(f)) wA[u[f]] -= rD[u[f]] * upper[f] * wA[l[f]];
+                    for (int f = nf - 1; f >= 0; --f) if (inBlock(f)) wA[l[f]] -= rD[l[f]] * upper[f] * wA[u[f]];
                 }
             }
             wArA = 0; for (int c = 0; c < n; ++c) wArA += wA[c] * rA[c];

@@ -150,5 +150,14 @@ void or_qhd_solver_info(or_ctx*, int* iters, double* res0, double* res);
 //  symmetric: lower == upper.  precond: 0 none, 1 diagonal, 2 DIC.  returns iterations.
 int or_pcg_solve(or_ctx*, const double* diag, const double* upper, const double* b, double* x,
                  double tol, double relTol, int maxIter, int precond, double* initRes, double* finalRes);
+// the decomposed-run form: global matrix, global reductions, preconditioner local to each processor block
+// (cellBlock[c] = processor of cell c; NULL = serial)
+int or_pcg_solve_blocks(or_ctx*, const double* diag, const double* upper, const double* b, double* x,
+                        double tol, double relTol, int maxIter, int precond, double* initRes, double* finalRes,
+                        const int* cellBlock);
+
+// every PCG solve of the following QGDFoam (implicit branch) / QHDFoam steps runs in the decomposed-run form above
+// (NULL: back to serial).  The rest of the step is decomposition-independent in exact arithmetic.
+void or_set_pcg_blocks(or_ctx*, const int* cellBlock);
 
 } // extern "C"

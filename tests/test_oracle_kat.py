@@ -1029,3 +1029,60 @@ def test_qgdflux_boundary_condition_closes_the_step_as_the_listing_says(oracle_m
     w.oracle_step(ow, 3)
     assert np.abs(ow.get_face("phiwStar")[nI:]).max() == 0.0
     assert np.array_equal(ow.get("p", with_bnd=True)[1], ow.get("p")[m.owner[nI:]])
+
+
+def test_decomposed_pcg_semantics(oracle_mod):
+    """PCG as a decomposed run performs it (or_pcg_solve_blocks): global matrix and reductions, DIC local to each
+    processor block.  One block == the serial solver bit for bit; diagonal / no preconditioning do not see the blocks at
+    all (same iterates); block-DIC needs some more iterations than global DIC and reaches the same solution."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from qgdsolver_b200 import decompose
+    mesh = cases.pm.hex_box(10, 9, 8, perturb=0.1, seed=1)
+    nI, nC = mesh.n_internal, mesh.n_cells
+    upper = -(mesh.magSf[:nI] * mesh.deltaCoeffs[:nI])
+    diag = np.zeros(nC)
+    np.subtract.at(diag, mesh.owner[:nI], upper); np.subtract.at(diag, mesh.neighbour, upper)
+    diag += 1e-3 * mesh.V / mesh.V.mean()
+    b = np.random.default_rng(0).standard_normal(nC)
+    o = oracle_mod.Oracle(mesh)
+    x0 = np.zeros(nC)
+    blocks = decompose.geometric_split(mesh, 8)
+    for pc in (0, 1, 2):
+        xs, its, r0s, r1s = o.pcg_solve(diag, upper, b, x0, tol=1e-13, maxIter=3000, precond=pc)
+        x1, it1, _, _ = o.pcg_solve(diag, upper, b, x0, tol=1e-13, maxIter=3000, precond=pc, cell_block=np.zeros(nC, np.int32))
+        assert it1 == its and np.array_equal(x1, xs)
+        xb, itb, r0b, r1b = o.pcg_solve(diag, upper, b, x0, tol=1e-13, maxIter=3000, precond=pc, cell_block=blocks)
+        assert r0b == r0s
+        if pc < 2:
+            assert itb == its and np.array_equal(xb, xs)
+        else:
+            assert its < itb < 2 * its
+            assert np.abs(xb - xs).max() < 1e-9 * np.abs(xs).max()
+    A = sp.coo_matrix((np.concatenate([diag, upper, upper]),
+                       (np.concatenate([np.arange(nC), mesh.owner[:nI], mesh.neighbour]),
+                        np.concatenate([np.arange(nC), mesh.neighbour, mesh.owner[:nI]])))).tocsc()
+    assert np.abs(xb - spl.spsolve(A, b)).max() < 1e-9 * np.abs(xb).max()
+
+
+def test_decomposed_run_oracle_for_qhdfoam_and_implicit_qgdfoam(oracle_mod):
+    """set_pcg_blocks: the steps of a decomposed run differ from the serial ones only through the block-local DIC of the
+    linear solvers - same fields to solver tolerance, more pressure iterations.  This is the oracle the multi-GPU QHDFoam /
+    implicit QGDFoam runs will be compared with."""
+    import cases
+    from qgdsolver_b200 import decompose
+    q = cases.qhd_cavity(n=(12, 10, 6), dims=3, dt=1e-3, perturb=0.1, tol=1e-13)
+    blocks = decompose.geometric_split(q.mesh, 4)
+    a, b = q.make_oracle(oracle_mod), q.make_oracle(oracle_mod)
+    b.set_pcg_blocks(blocks)
+    q.oracle_step(a, 5); q.oracle_step(b, 5)
+    for f in ("U", "T", "p"):
+        assert np.abs(a.qhd_get(f) - b.qhd_get(f)).max() < 1e-9 * np.abs(a.qhd_get(f)).max(), f
+    assert b.qhd_solver_info()["iters"] > a.qhd_solver_info()["iters"]
+    c = cases.case_hex3d(n=(8, 7, 6), perturb=0.15, bcs="fixed", implicit=True, gas=dict(cases.GAS, mu=2e-2))
+    blocks = decompose.geometric_split(c.mesh, 4)
+    a, b = c.make_oracle(oracle_mod), c.make_oracle(oracle_mod)
+    b.set_pcg_blocks(blocks)
+    c.oracle_step(a, 5); c.oracle_step(b, 5)
+    for f in ("rho", "rhoU", "rhoE"):
+        assert np.abs(a.get(f) - b.get(f)).max() < 1e-11 * np.abs(a.get(f)).max(), f
