@@ -72,6 +72,10 @@ class SubDomain:
     send_cells: Dict[int, np.ndarray] = field(default_factory=dict)
     recv_bfaces: Dict[int, np.ndarray] = field(default_factory=dict)   # boundary-face index (face - n_internal)
     send_bfaces: Dict[int, np.ndarray] = field(default_factory=dict)
+    # the face-neighbour subset of the halo (cells across a coupled face): what a linear-solver iteration exchanges
+    # (the search direction of PCG), as opposed to the full vertex-ring state exchange once per step
+    recv_face_cells: Dict[int, np.ndarray] = field(default_factory=dict)
+    send_face_cells: Dict[int, np.ndarray] = field(default_factory=dict)
 
 
 def _point_cells(mesh: PolyMesh):
@@ -231,6 +235,17 @@ def extended_submeshes(mesh: PolyMesh, cell_rank: np.ndarray, ranks=None) -> Lis
             isb = np.zeros(mesh.n_cells, bool); isb[mine] = True
             bf_g = np.nonzero(isb[mesh.owner[nI:]])[0] + nI
             sd.send_bfaces[s] = bm_r[bf_g].astype(np.int32)
+        # face-neighbour halo: cells on either side of the faces cut between r and s, ascending global id on both sides
+        go_, gn_ = mesh.owner[:nI], mesh.neighbour
+        ro_, rn_ = cell_rank[go_], cell_rank[gn_]
+        for s in sorted(set(sd.recv_cells) | set(sd.send_cells)):
+            a = (ro_ == r) & (rn_ == s)
+            b = (ro_ == s) & (rn_ == r)
+            theirs = np.unique(np.concatenate([gn_[a], go_[b]]))
+            mine = np.unique(np.concatenate([go_[a], gn_[b]]))
+            if theirs.size:
+                sd.recv_face_cells[s] = g2l_r[theirs].astype(np.int32)
+                sd.send_face_cells[s] = g2l_r[mine].astype(np.int32)
     return out
 
 
