@@ -133,3 +133,15 @@ def test_face_neighbour_halo_lists_support_a_distributed_spmv():
                 yl[c] += ul[f] * xl[m.neighbour[f] if m.owner[f] == c else m.owner[f]]
         assert np.isfinite(yl).all()                                  # no value outside the face-neighbour halo was touched
         assert np.array_equal(yl, y[sd.cell_global[:sd.n_owned]])
+
+
+def test_two_rank_gloo_pcg():
+    """world_size-2 PCG with block-local DIC over gloo (halo exchange of the search direction + all-reduces) against the
+    oracle's decomposed-run solver."""
+    script = os.path.join(ROOT, "tests", "gloo_pcg_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "PCG_OK" in r.stdout
