@@ -443,6 +443,11 @@ def read_field(path: str, mesh: PolyMesh) -> VolField:
             raise FoamFormatError(f"{path}: boundaryField entry {name} is not a patch of the mesh")
         e = _entries(blk)
         fld.patch_types[name] = e.get("type", "calculated")
+        for key in ("value", "gradient"):       # `value $internalField;` (the usual tutorial idiom): only a uniform field can be expanded
+            if e.get(key, "").startswith("$internalField"):
+                if not top["internalField"].strip().startswith("uniform"):
+                    raise FoamFormatError(f"{path}: `{key} $internalField` on patch {name} with a nonuniform internalField")
+                e[key] = top["internalField"]
         if "value" in e:
             fld.patch_values[name] = _parse_value(e["value"], sizes[name], ncmpt)
         if "gradient" in e:

@@ -139,3 +139,27 @@ def test_binary_errors(tmp_path):
     open(p, "wb").write(data.replace(b"LSB", b"MSB"))
     with pytest.raises(fc.FoamFormatError):
         fc.read_points(str(p))
+
+
+def test_tutorial_idioms_one_line_lists_and_internalfield_macro(tmp_path):
+    """what OpenFOAM itself writes / tutorials contain: short lists on one line `4(0 1 2 3)`, `inGroups 1(wall);` in the
+    boundary file, `value $internalField;`, extra header keys (arch, note)."""
+    m = cases.pm.hex_box(2, 1, 1, lengths=(1.0, 0.1, 0.1), patch_kinds={"zMin": "empty", "zMax": "empty", "yMin": "empty", "yMax": "empty"})
+    fc.write_polymesh(m, str(tmp_path))
+    d = tmp_path / "constant" / "polyMesh"
+    hdr = 'FoamFile\n{\n    version 2.0;\n    format ascii;\n    arch "LSB;label=32;scalar=64";\n    note "nPoints:12";\n    class labelList;\n    object owner;\n}\n'
+    (d / "owner").write_text(hdr + f"{m.owner.size}(" + " ".join(str(int(v)) for v in m.owner) + ")\n")
+    b = (d / "boundary").read_text().replace("type            patch;", "type            wall;\n        inGroups        1(wall);")
+    (d / "boundary").write_text(b)
+    r = fc.read_polymesh(str(tmp_path))
+    assert np.array_equal(r.owner, m.owner) and [p.kind for p in r.patches] == [p.kind for p in m.patches]
+    os.makedirs(tmp_path / "0", exist_ok=True)
+    (tmp_path / "0" / "T").write_text(
+        "FoamFile { version 2.0; format ascii; class volScalarField; object T; }\ndimensions [0 0 0 1 0 0 0];\n"
+        "internalField uniform 300;\nboundaryField\n{\n    xMin { type fixedValue; value $internalField; }\n"
+        "    xMax { type zeroGradient; }\n    yMin { type empty; } yMax { type empty; } zMin { type empty; } zMax { type empty; }\n}\n")
+    T = fc.read_field(str(tmp_path / "0" / "T"), r)
+    assert np.array_equal(T.internal, [300.0, 300.0]) and np.array_equal(T.patch_values["xMin"], [300.0])
+    (tmp_path / "0" / "T").write_text((tmp_path / "0" / "T").read_text().replace("uniform 300", "nonuniform List<scalar> 2(300 301)"))
+    with pytest.raises(fc.FoamFormatError):
+        fc.read_field(str(tmp_path / "0" / "T"), r)
