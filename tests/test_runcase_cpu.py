@@ -1,0 +1,233 @@
+"""Case-directory front end (qgdsolver_b200/foamdict.py, runcase.py) on CPU: the dictionaries the reference solvers read
+ are parsed with OpenFOAM's lookup rules and mapped onto the C-ABI descriptors; the mapping is checked by
+running the ORACLE from the parsed set-up and comparing with the same case built in memory."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from qgdsolver_b200 import foamcase as fc
+from qgdsolver_b200 import foamdict, runcase
+
+HDR = "FoamFile\n{\n    version 2.0;\n    format ascii;\n    class dictionary;\n    object %s;\n}\n"
+
+CONTROL = HDR % "controlDict" + """
+application     QGDFoam;
+startFrom       startTime;
+startTime       0;
+stopAt          endTime;
+endTime         0.02;
+deltaT          2e-4;          // fixed
+writeControl    runTime;
+writeInterval   0.01;
+adjustTimeStep  no;
+maxCo           0.3;
+cTau            0.6;
+"""
+SCHEMES = HDR % "fvSchemes" + """
+ddtSchemes { default Euler; }
+gradSchemes { default Gauss linear; }
+divSchemes { default none; }
+laplacianSchemes { default Gauss linear corrected; }
+interpolationSchemes { default none; }
+snGradSchemes { default corrected; }
+fvsc { default GaussVolPoint; }
+"""
+THERMO = HDR % "thermophysicalProperties" + """
+thermoType
+{
+    type            hePsiQGDThermo;
+    mixture         pureMixture;
+    transport       const;
+    thermo          hConst;
+    equationOfState perfectGas;
+    specie          specie;
+    energy          sensibleInternalEnergy;
+}
+mixture
+{
+    specie { molWeight 8314.47; }        /* R = 1 */
+    thermodynamics { Cp 3.5; Hf 0; Tref 0; }
+    transport { mu 0; Pr 1; }
+}
+QGD
+{
+    implicitDiffusion false;
+    QGDCoeffs constScPrModel1;
+    constScPrModel1Dict { ScQGD 1; PrQGD 1; }
+}
+"""
+
+
+def _write_sod(tmp, n=60):
+    c = cases.case_sod(n)
+    m = c.mesh
+    fc.write_polymesh(m, str(tmp))
+    os.makedirs(tmp / "system")
+    (tmp / "system" / "controlDict").write_text(CONTROL)
+    (tmp / "system" / "fvSchemes").write_text(SCHEMES)
+    (tmp / "constant" / "thermophysicalProperties").write_text(THERMO)
+    zg = {p.name: ("empty" if p.kind == 1 else "zeroGradient") for p in m.patches}
+    fc.write_field(str(tmp / "0" / "U"), m, "U", c.U0, zg)
+    fc.write_field(str(tmp / "0" / "T"), m, "T", c.T0, zg)
+    fc.write_field(str(tmp / "0" / "p"), m, "p", c.p0, zg)
+    return c
+
+
+def _case_from_setup(s):
+    """tests-side stand-in for runcase.make_solver: the same set-up handed to the oracle through cases.Case"""
+    k = s.solver_kwargs
+    (kU, vU), (kT, vT), (kP, vP) = (s.bc[n] for n in ("U", "T", "p"))
+    gas = dict(R=k["R"], Cp=k["Cp"], Hf=k["Hf"], Tref=k["Tref"], Hsref=k["Hsref"], mu=k["mu"], Pr=k["Pr"], ScQGD=k["ScQGD"], PrQGD=k["PrQGD"])
+    return cases.Case(s.mesh, s.fields["U"].internal, s.fields["T"].internal, s.fields["p"].internal, kU, kT, kP, vU, vT, vP, gas=gas,
+                      dt=k["delta_t"], scheme=k["fvsc_scheme"], model=k["qgd_coeffs"], implicit=k["implicit_diffusion"],
+                      adjust_time_step=k["adjust_time_step"], max_co=k["max_co"], max_delta_t=k["max_delta_t"], c_tau=k["c_tau"])
+
+
+def test_dictionary_parser_follows_openfoam_lookup_rules():
+    d = foamdict.parse("""
+        a 1.5; // comment
+        name word; sw on; v (0 -9.81 0); g [0 1 -2 0 0 0 0] (0 0 -1);
+        nu nu [0 2 -1 0 0 0 0] 1e-5;
+        lst 3 ( x y z );
+        sub { b $a; inner { c $b; } }
+        solvers { p { solver PCG; tolerance 1e-8; } "(U|e)" { solver PCG; relTol 0.1; } "(U|T)Final" { $p; } }
+        /* block
+           comment */
+        copy $sub;
+    """, "test")
+    assert d.scalar("a") == 1.5 and d.word("name") == "word" and d.switch("sw") is True
+    assert d.vector("v") == [0.0, -9.81, 0.0] and d.vector("g") == [0.0, 0.0, -1.0] and d.scalar("nu") == 1e-5
+    assert d["lst"] == [["x", "y", "z"]]
+    assert d.sub_dict("sub").scalar("b") == 1.5 and d.sub_dict("sub").sub_dict("inner").scalar("c") == 1.5
+    s = d.sub_dict("solvers")
+    assert s.sub_dict("U").scalar("relTol") == 0.1 and s.sub_dict("e").word("solver") == "PCG" and s.found("p") and not s.found("T")
+    assert d.sub_dict("copy").scalar("b") == 1.5
+    assert d.scalar("missing", 7.0) == 7.0 and d.sub_or_self("noDict") is d
+    with pytest.raises(foamdict.FoamDictError) as e:
+        d.scalar("missing")
+    assert "keyword missing is undefined in dictionary" in str(e.value)
+    for bad in ("a 1", "a { b 1;", "#include \"x\"\n", "a $nope;"):
+        with pytest.raises(foamdict.FoamDictError):
+            foamdict.parse(bad)
+
+
+def test_sod_case_directory_maps_onto_the_solver_descriptor_and_runs_like_the_in_memory_case(tmp_path, oracle_mod):
+    c = _write_sod(tmp_path)
+    s = runcase.load_case(str(tmp_path))
+    k = s.solver_kwargs
+    assert s.solver == "QGDFoam" and s.start_time == "0" and s.end_time == 0.02 and s.write_control == "runTime"
+    assert k["fvsc_scheme"] == "GaussVolPoint" and k["qgd_coeffs"] == "constScPrModel1" and k["implicit_diffusion"] is False
+    assert k["R"] == 1.0 and k["Cp"] == 3.5 and k["Tref"] == 0.0 and k["Hsref"] == 0.0 and k["mu"] == 0.0 and k["c_tau"] == 0.6
+    assert k["adjust_time_step"] is False and k["delta_t"] == 2e-4
+    assert list(s.mesh.geometric_d) == [1, -1, -1]
+    a, b = _case_from_setup(s).make_oracle(oracle_mod), c.make_oracle(oracle_mod)
+    a.qgd_step(100); b.qgd_step(100)
+    for f in ("rho", "rhoU", "rhoE", "p"):
+        assert np.array_equal(a.get(f), b.get(f)), f
+
+
+def test_defaults_and_fatal_lookups_follow_the_reference(tmp_path):
+    _write_sod(tmp_path)
+    th = tmp_path / "constant" / "thermophysicalProperties"
+    th.write_text(THERMO.replace("implicitDiffusion false;", "").replace("Tref 0;", ""))
+    with pytest.raises(foamdict.FoamDictError) as e:                 # implicitDiffusion defaults to true (QGDThermo.C:61) -> needs solvers
+        runcase.load_case(str(tmp_path))
+    assert "implicitDiffusion true needs system/fvSolution" in str(e.value)
+    (tmp_path / "system" / "fvSolution").write_text(HDR % "fvSolution" + 'solvers { "(U|e)" { solver PCG; preconditioner DIC; tolerance 1e-10; relTol 0; } }')
+    s = runcase.load_case(str(tmp_path))
+    k = s.solver_kwargs
+    assert k["implicit_diffusion"] is True and k["diff_tol"] == 1e-10 and k["diff_precond"] == "DIC" and k["Tref"] == runcase.TSTD
+    th.write_text(THERMO.replace("QGDCoeffs constScPrModel1;", "QGDCoeffs noSuchModel;"))
+    with pytest.raises(foamdict.FoamDictError) as e:
+        runcase.load_case(str(tmp_path))
+    assert "Unknown QGD coeffs evaluation approach type noSuchModel" in str(e.value)      # QGDCoeffs.C:72-78
+    th.write_text(THERMO.replace("QGDCoeffs constScPrModel1;", ""))
+    with pytest.raises(foamdict.FoamDictError) as e:
+        runcase.load_case(str(tmp_path))
+    assert "keyword QGDCoeffs is undefined" in str(e.value)                               # QGDThermo.C:56 mandatory
+    th.write_text(THERMO.replace("constScPrModel1;", "constScPrModel2;").replace("constScPrModel1Dict", "constScPrModel2Dict").replace("ScQGD 1;", ""))
+    with pytest.raises(foamdict.FoamDictError) as e:
+        runcase.load_case(str(tmp_path))
+    assert "keyword ScQGD is undefined" in str(e.value)                                   # constScPrModel2.C:60-61 mandatory
+    th.write_text(THERMO)
+    (tmp_path / "system" / "fvSchemes").write_text(SCHEMES.replace("default GaussVolPoint;", 'default GaussVolPoint; "grad(p)" reduced;'))
+    with pytest.raises(foamdict.FoamDictError):
+        runcase.load_case(str(tmp_path))
+    (tmp_path / "system" / "fvSchemes").write_text(SCHEMES.replace("fvsc { default GaussVolPoint; }", "fvsc { }"))
+    with pytest.raises(foamdict.FoamDictError) as e:
+        runcase.load_case(str(tmp_path))
+    assert "keyword default is undefined" in str(e.value)                                  # fvsc.C:57
+
+
+QHD_THERMO = HDR % "thermophysicalProperties" + """
+thermoType { type heRhoQGDThermo; mixture pureMixture; transport const; thermo hConst; equationOfState rhoConst; specie specie;
+             energy sensibleInternalEnergy; }
+mixture
+{
+    specie { molWeight 28.9; }
+    equationOfState { rho 1.0; }
+    thermodynamics { Cp 1000; Hf 0; }
+    transport { mu 1e-2; Pr 0.71; beta 3e-3; }
+}
+QGD { implicitDiffusion false; QGDCoeffs constTau; constTauDict { Tau 1e-3; } pRefCell 3; pRefValue 0.25; }
+"""
+
+
+def test_qhd_cavity_case_directory(tmp_path, oracle_mod):
+    c = cases.qhd_cavity(n=(10, 8), dt=1e-3, p_ref_cell=3, p_ref_value=0.25, tol=1e-12)
+    m = c.mesh
+    fc.write_polymesh(m, str(tmp_path))
+    os.makedirs(tmp_path / "system")
+    (tmp_path / "system" / "controlDict").write_text(CONTROL.replace("QGDFoam", "QHDFoam").replace("2e-4", "1e-3"))
+    (tmp_path / "system" / "fvSchemes").write_text(SCHEMES)
+    (tmp_path / "system" / "fvSolution").write_text(HDR % "fvSolution" + "solvers { p { solver PCG; preconditioner DIC; tolerance 1e-12; relTol 0; maxIter 5000; } }")
+    (tmp_path / "constant" / "thermophysicalProperties").write_text(QHD_THERMO)
+    (tmp_path / "constant" / "gravitationalProperties").write_text(HDR % "gravitationalProperties" + "g g [0 1 -2 0 0 0 0] (0 -9.81 0);")
+    code = {0: "fixedValue", 1: "zeroGradient", 2: "fixedGradient"}
+    names = [p.name for p in m.patches]
+    for nm, arr, kinds, vals in (("U", c.U0, c.bcU, c.bvU), ("T", c.T0, c.bcT, c.bvT), ("p", c.p0, c.bcP, c.bvP)):
+        types = {n: ("empty" if p.kind == 1 else code[int(k)]) for n, k, p in zip(names, kinds, m.patches)}
+        fc.write_field(str(tmp_path / "0" / nm), m, nm, arr, types, vals)
+    # fixedGradient p patches need a `gradient` entry: patch the file (write_field writes `value`)
+    ptxt = (tmp_path / "0" / "p").read_text().replace("type            fixedGradient;", "type            fixedGradient;\n        gradient        uniform 0;")
+    (tmp_path / "0" / "p").write_text(ptxt)
+    s = runcase.load_case(str(tmp_path))
+    k = s.solver_kwargs
+    assert s.solver == "QHDFoam" and k["qgd_coeffs"] == "constTau" and k["Tau"] == 1e-3 and k["g"] == (0.0, -9.81, 0.0)
+    assert k["rho0"] == 1.0 and k["beta"] == 3e-3 and k["p_ref_cell"] == 3 and k["p_ref_value"] == 0.25 and k["precond"] == "DIC"
+    assert k["scalar_transport"] is False and k["tol"] == 1e-12 and k["max_iter"] == 5000
+    (kU, vU), (kT, vT), (kP, vP) = (s.bc[n] for n in ("U", "T", "p"))
+    q = cases.QHDCase(s.mesh, s.fields["U"].internal, s.fields["T"].internal, s.fields["p"].internal, kU, kT, kP, vU, vT, vP,
+                      fluid=dict(rho0=k["rho0"], mu=k["mu"], Pr=k["Pr"], beta=k["beta"], g=k["g"]), model=k["qgd_coeffs"],
+                      coeffs=dict(Tau=k["Tau"], UQHD=k["UQHD"], Gr=k["Gr"], T0=k["T0"]), dt=k["delta_t"], tol=k["tol"], rel_tol=k["rel_tol"],
+                      max_iter=k["max_iter"], precond=k["precond"], p_ref_cell=k["p_ref_cell"], p_ref_value=k["p_ref_value"])
+    a, b = q.make_oracle(oracle_mod), c.make_oracle(oracle_mod)
+    q.oracle_step(a, 10); c.oracle_step(b, 10)
+    for f in ("U", "T", "p"):
+        assert np.abs(a.qhd_get(f) - b.qhd_get(f)).max() <= 1e-13 * max(np.abs(b.qhd_get(f)).max(), 1e-30), f
+    s2 = runcase.load_case(str(tmp_path), "scalarTransportQHDFoam")
+    assert s2.solver_kwargs["scalar_transport"] is True
+
+
+def test_time_loop_plans_whole_write_intervals():
+    """runcase.run with a recording stand-in for the device solver: fixed deltaT -> one C call per write interval"""
+    class Fake:
+        def __init__(self):
+            self.calls, self.t = [], 0.0
+        def step(self, n):
+            self.calls.append(n); self.t += n * 2e-4
+        def scalars(self):
+            return dict(deltaT=2e-4, CoNum=0.1, time=self.t)
+    fake = Fake()
+    setup = runcase.CaseSetup("/nonexistent", "QGDFoam", None, {}, "0", 0.02, 2e-4, "runTime", 0.01, dict(adjust_time_step=False))
+    written = []
+    orig_make, orig_write = runcase.make_solver, runcase.write_time
+    runcase.make_solver = lambda s, api, dmesh=None: fake
+    runcase.write_time = lambda s, sol, t: written.append(runcase.time_name(t)) or runcase.time_name(t)
+    try:
+        runcase.run(setup, api=None, log=lambda *_: None)
+    finally:
+        runcase.make_solver, runcase.write_time = orig_make, orig_write
+    assert fake.calls == [50, 50] and written == ["0.01", "0.02"]

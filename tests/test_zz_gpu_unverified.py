@@ -37,3 +37,23 @@ def test_active_qgdflux_gradient_matches_oracle(qgd, oracle_mod, kw):
         scale = float(np.abs(oc).max())
         assert float(np.abs(gc - oc).max()) / scale < TOL_STEP, f
         assert float(np.abs(gb - ob).max()) / scale < TOL_STEP, f"boundary {f}"
+
+
+@NOT_RUN
+def test_runcase_end_to_end_writes_the_oracle_solution(qgd, oracle_mod, tmp_path):
+    """python -m qgdsolver_b200.runcase on a Sod-tube case directory: dictionaries -> device solver -> time directories;
+    the written 0.02/rho, p, U equal the oracle run from the same set-up."""
+    import os
+    from qgdsolver_b200 import foamcase as fc
+    from qgdsolver_b200 import runcase
+    from test_runcase_cpu import _case_from_setup, _write_sod
+    _write_sod(tmp_path)
+    setup = runcase.load_case(str(tmp_path))
+    written = runcase.run(setup, qgd, log=lambda *_: None)
+    assert [os.path.basename(w) for w in written] == ["0.01", "0.02"]
+    o = _case_from_setup(setup).make_oracle(oracle_mod)
+    o.qgd_step(100)
+    for name in ("rho", "p", "U", "rhoE"):
+        f = fc.read_field(os.path.join(str(tmp_path), "0.02", name), setup.mesh)
+        ref = o.get(name)
+        assert float(np.abs(f.internal - ref).max()) / float(np.abs(ref).max()) < TOL_STEP, name
