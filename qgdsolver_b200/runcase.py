@@ -3,6 +3,7 @@ read the dictionaries the reference solvers read, the mesh and t
 directories back.  Host-side harness (the compiled product is libqgd_b200.so; this file only maps a case onto its C ABI).
 
     python -m qgdsolver_b200.runcase <caseDir> [-solver QGDFoam|QHDFoam|scalarTransportQHDFoam] [-device 0]
+    torchrun --nproc-per-node N -m qgdsolver_b200.runcase <caseDir> -parallel     (a decomposePar'd case, QGDFoam explicit)
 
 What is read, key by key (the reference's defaults are kept; a missing mandatory key fails like dictionary::lookup):
   system/controlDict     application, startFrom/startTime, endTime, deltaT, writeControl, writeInterval,
@@ -230,11 +231,13 @@ def write_time(setup: CaseSetup, s, t: float) -> str:
     return d
 
 
-def run(setup: CaseSetup, api, log=print) -> List[str]:
+def run(setup: CaseSetup, api, log=print, solver=None, writer=None) -> List[str]:
     """the time loop: fixed deltaT -> whole write intervals per C call (no host sync inside); adjustTimeStep -> chunks of
     at most 50 steps, the time being read back after each (write times are not snapped to multiples like
-    Time::adjustDeltaT does: the first step at or past a write time is written)."""
-    s = make_solver(setup, api)
+    Time::adjustDeltaT does: the first step at or past a write time is written).
+    solver / writer: a ready solver object and a `writer(setup, solver, t) -> path` (the parallel driver passes its own)."""
+    s = solver if solver is not None else make_solver(setup, api)
+    writer = writer or write_time
     t, dt = float(setup.start_time), setup.delta_t
     written = []
     adjust = bool(setup.solver_kwargs["adjust_time_step"])
@@ -265,7 +268,7 @@ def run(setup: CaseSetup, api, log=print) -> List[str]:
         steps_since_write += n
         due = (every_n is not None and steps_since_write >= every_n) or (every_t is not None and t >= next_write - eps)
         if due or t >= setup.end_time - eps:
-            written.append(write_time(setup, s, t))
+            written.append(writer(setup, s, t))
             log(f"Time = {time_name(t)}  deltaT = {sc['deltaT']:.6g}  Courant = {sc['CoNum']:.4g}")
             steps_since_write = 0
             if every_t is not None:
@@ -274,21 +277,99 @@ def run(setup: CaseSetup, api, log=print) -> List[str]:
     return written
 
 
+class _RankCase:
+    """the attributes multigpu.make_rank_solver reads, filled from a CaseSetup (QGDFoam, explicit branch)"""
+
+    def __init__(self, setup: CaseSetup):
+        k = setup.solver_kwargs
+        if setup.solver != "QGDFoam" or k["implicit_diffusion"]:
+            raise FoamDictError("-parallel: only QGDFoam with implicitDiffusion false runs on several GPUs yet")
+        self.mesh, self.scheme, self.model, self.dt = setup.mesh, k["fvsc_scheme"], k["qgd_coeffs"], k["delta_t"]
+        self.gas = {n: k[n] for n in ("R", "Cp", "Hf", "Tref", "Hsref", "mu", "Pr", "ScQGD", "PrQGD")}
+        self.opts = {n: k[n] for n in ("adjust_time_step", "max_co", "max_delta_t", "c_tau")}
+        self.varsc = dict(cSc1=k.get("varsc_cSc1", 1.0), minSc=k.get("varsc_minSc", -1.0), maxSc=k.get("varsc_maxSc", -1.0), const_sc_cells=None)
+        if setup.const_sc_cell_set:
+            self.varsc["const_sc_cells"] = foamcase.read_labels(os.path.join(setup.case_dir, "constant", "polyMesh", "sets", setup.const_sc_cell_set))
+        (self.bcU, self.bvU), (self.bcT, self.bvT), (self.bcP, self.bvP) = (setup.bc[n] for n in ("U", "T", "p"))
+        f = setup.fields
+        self.U0, self.T0, self.p0 = f["U"].internal, f["T"].internal, f["p"].internal
+        self.alphaQGD = f["alphaQGD"].internal if "alphaQGD" in f else None
+
+
+def processor_writer(setup: CaseSetup, sub, proc):
+    """writer for one rank of a decomposed run: processorN/<time>/ fields of the rank's owned cells.  `sub` is the rank's
+    decompose.SubDomain (device numbering), `proc` its decompose.ProcMesh (the decomposePar layout on disk): owned cells are
+    in cellProcAddressing order on both sides; boundary values are matched through the global face ids."""
+    nIl = proc.mesh.n_internal
+    gf_proc = np.abs(proc.face_addr[nIl:].astype(np.int64)) - 1                  # global face of every processor-mesh boundary face
+    gf_sub = sub.face_global[sub.mesh.n_internal:]
+    where = {int(g): i for i, g in enumerate(gf_sub)}
+    phys = gf_proc >= setup.mesh.n_internal
+    idx = np.array([where.get(int(g), -1) if ph else -1 for g, ph in zip(gf_proc, phys)], np.int64)
+    if (idx[phys] < 0).any():
+        raise FoamDictError("processor mesh and device sub-mesh disagree on the physical boundary faces")
+    names = ("U", "T", "p", "rho", "e", "rhoU", "rhoE")
+
+    def write(setup_, s, t):
+        d = os.path.join(setup.case_dir, f"processor{proc.rank}", time_name(t))
+        for n in names:
+            cells, bnd = s.get(n, with_bnd=True)
+            own = cells[:sub.n_owned]
+            pb = np.where(phys.reshape((-1,) + (1,) * (bnd.ndim - 1)), bnd[np.maximum(idx, 0)], own[proc.mesh.owner[nIl:]])
+            src = setup.fields.get(n)
+            types = dict(src.patch_types) if src is not None else {}
+            for patch in proc.mesh.patches:
+                if patch.kind == foamcase.PATCH_PROCESSOR:
+                    types[patch.name] = "processor"
+            foamcase.write_field(os.path.join(d, n), proc.mesh, n, own, types, pb, src.dimensions if src is not None else "[0 0 0 0 0 0 0]")
+        return d
+    return write
+
+
+def run_parallel(setup: CaseSetup, api, rank: int, world: int, log=print) -> List[str]:
+    """one rank of `mpirun -np N QGDFoam -parallel`: the cell -> processor map comes from the decomposePar'd case
+    (constant/cellDecomposition or the cellProcAddressing lists), results go to processor<rank>/<time>/"""
+    from . import decompose, multigpu
+    cell_rank = foamcase.read_cell_decomposition(setup.case_dir, setup.mesh.n_cells)
+    if int(cell_rank.max()) + 1 != world:
+        raise FoamDictError(f"case is decomposed into {int(cell_rank.max()) + 1} processors, launched with {world} ranks")
+    s, sub, _dm = multigpu.make_rank_solver(_RankCase(setup), rank, world, cell_rank)
+    proc = decompose.processor_meshes(setup.mesh, cell_rank, ranks=[rank])[0]
+    return run(setup, api, log if rank == 0 else (lambda *_: None), solver=s, writer=processor_writer(setup, sub, proc))
+
+
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv or argv[0] in ("-h", "-help", "--help"):
         print(__doc__)
         return 0
-    case_dir, solver, device = argv[0], None, 0
+    case_dir, solver, device, parallel = argv[0], None, 0, False
     i = 1
     while i < len(argv):
         if argv[i] == "-solver":
             solver = argv[i + 1]; i += 2
         elif argv[i] == "-device":
             device = int(argv[i + 1]); i += 2
+        elif argv[i] == "-parallel":      # under torchrun: one rank per GPU (RANK / LOCAL_RANK / WORLD_SIZE from the environment)
+            parallel = True; i += 1
         else:
             raise SystemExit(f"unknown option {argv[i]}")
     from . import api
+    if parallel:
+        import torch
+        import torch.distributed as dist
+        from . import multigpu
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        api.init(local)
+        multigpu.init_comm(dist.get_rank(), dist.get_world_size())
+        run_parallel(load_case(case_dir, solver), api, dist.get_rank(), dist.get_world_size())
+        api.synchronize()
+        dist.barrier()
+        api.comm_finalize()
+        dist.destroy_process_group()
+        return 0
     api.init(device)                      # fails loudly without a CUDA device: there is no CPU fallback
     setup = load_case(case_dir, solver)
     run(setup, api)

@@ -231,3 +231,58 @@ def test_time_loop_plans_whole_write_intervals():
     finally:
         runcase.make_solver, runcase.write_time = orig_make, orig_write
     assert fake.calls == [50, 50] and written == ["0.01", "0.02"]
+
+
+def test_parallel_writer_puts_owned_results_into_processor_directories(tmp_path):
+    """runcase.processor_writer with a stand-in rank solver that returns a known global field in the device sub-mesh
+    numbering: processorN/<time>/T read back through cellProcAddressing reassembles the global field, physical boundary
+    values land on the right processor patch faces."""
+    from qgdsolver_b200 import decompose
+    _write_sod(tmp_path)                                   # dictionaries + 0/ fields (mesh replaced below by a 3D box)
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.1, bcs="fixed")
+    m = c.mesh
+    fc.write_polymesh(m, str(tmp_path))
+    types = {p.name: "fixedValue" for p in m.patches}
+    for nm, arr, vals in (("U", c.U0, c.bvU), ("T", c.T0, c.bvT), ("p", c.p0, c.bvP)):
+        fc.write_field(str(tmp_path / "0" / nm), m, nm, arr, types, vals)
+    rank = decompose.geometric_split(m, 2)
+    fc.write_decomposed_case(m, rank, str(tmp_path))
+    setup = runcase.load_case(str(tmp_path))
+    rc = runcase._RankCase(setup)
+    assert rc.model == "constScPrModel1" and rc.opts["c_tau"] == 0.6 and rc.gas["R"] == 1.0 and rc.U0.shape == (m.n_cells, 3)
+    gT = np.sin(5 * m.C[:, 0]) + m.C[:, 1]
+    gTb = np.cos(3 * m.Cf[m.n_internal:, 2])
+    back = np.full(m.n_cells, np.nan)
+    for r in range(2):
+        sub = decompose.extended_submeshes(m, rank, ranks=[r])[0]
+        proc = decompose.processor_meshes(m, rank, ranks=[r])[0]
+        gb = sub.face_global[sub.mesh.n_internal:]
+
+        class Fake:
+            def get(self, name, with_bnd=False):
+                k3 = name in ("U", "rhoU")
+                cells = gT[sub.cell_global]
+                bnd = np.where(gb >= m.n_internal, gTb[np.maximum(gb - m.n_internal, 0)], -7.0)
+                if k3:
+                    cells, bnd = np.stack([cells] * 3, 1), np.stack([bnd] * 3, 1)
+                return cells, bnd
+        d = runcase.processor_writer(setup, sub, proc)(setup, Fake(), 0.01)
+        assert d.endswith(os.path.join(f"processor{r}", "0.01"))
+        pm = fc.read_polymesh(str(tmp_path / f"processor{r}"))
+        f = fc.read_field(os.path.join(d, "T"), pm)
+        back[proc.cell_addr] = f.internal
+        for patch in pm.patches:
+            if patch.kind == cases.pm.PATCH_PROCESSOR:
+                assert f.patch_types[patch.name] == "processor"
+            else:
+                gfaces = np.abs(proc.face_addr[patch.start:patch.start + patch.size]) - 1 - m.n_internal
+                assert np.array_equal(f.patch_values[patch.name], gTb[gfaces])
+        fU = fc.read_field(os.path.join(d, "U"), pm)
+        assert fU.internal.shape == (proc.cell_addr.size, 3)
+    assert np.array_equal(back, gT)
+    # wrong world size / unsupported solver are refused before any device call
+    with pytest.raises(foamdict.FoamDictError):
+        runcase.run_parallel(setup, None, 0, 3)
+    setup.solver_kwargs["implicit_diffusion"] = True
+    with pytest.raises(foamdict.FoamDictError):
+        runcase._RankCase(setup)
