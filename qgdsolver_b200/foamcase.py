@@ -381,6 +381,34 @@ def write_processor_fields(case_dir: str, time: str, name: str, procs, internal:
         write_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh, name, loc, pt, bl, dimensions)
 
 
+def reconstruct_fields(case_dir: str, time: str, names, mesh: PolyMesh, binary: bool = False) -> Dict[str, np.ndarray]:
+    """reconstructPar for vol fields: processorN/<time>/<name> of every processor -> <time>/<name> of the undecomposed
+    case through cellProcAddressing / faceProcAddressing; patch types are taken from processor0 (processor patches dropped).
+    Returns the reconstructed internal fields."""
+    procs = read_decomposed_case(case_dir)
+    nI = mesh.n_internal
+    out = {}
+    for name in names:
+        internal, boundary, types = None, None, {}
+        for p in procs:
+            f = read_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh)
+            if internal is None:
+                shape = (mesh.n_cells,) + f.internal.shape[1:]
+                internal = np.zeros(shape)
+                boundary = np.zeros((mesh.n_bnd,) + f.internal.shape[1:])
+            internal[p.cell_addr] = f.internal
+            for patch in p.mesh.patches:
+                if patch.kind == PATCH_PROCESSOR:
+                    continue
+                types.setdefault(patch.name, f.patch_types[patch.name])
+                if patch.size and patch.name in f.patch_values:
+                    gf = np.abs(p.face_addr[patch.start:patch.start + patch.size].astype(np.int64)) - 1
+                    boundary[gf - nI] = f.patch_values[patch.name]
+        write_field(os.path.join(case_dir, time, name), mesh, name, internal, types, boundary, binary=binary)
+        out[name] = internal
+    return out
+
+
 @dataclass
 class VolField:
     """GeometricField<Type, fvPatchField, volMesh> as read from a time directory."""

@@ -51,6 +51,8 @@ class CaseSetup:
     solver_kwargs: Dict[str, object] = field(default_factory=dict)     # keyword arguments of api.QGDFoam / api.QHDFoam
     bc: Dict[str, tuple] = field(default_factory=dict)                 # name -> (kinds per patch, values per boundary face)
     const_sc_cell_set: Optional[str] = None
+    write_binary: bool = False                    # controlDict::writeFormat binary
+    time_precision: int = 6                       # controlDict::timePrecision [OF Time]
 
 
 def _time_dirs(case_dir: str) -> List[str]:
@@ -150,6 +152,8 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
                                  delta_t=control.scalar("deltaT"))
     setup = CaseSetup(case_dir, solver, mesh, fields, start, control.scalar("endTime"), control.scalar("deltaT"),
                       control.word("writeControl", "timeStep"), control.scalar("writeInterval", 1.0), kw)
+    setup.write_binary = control.word("writeFormat", "ascii") == "binary"
+    setup.time_precision = control.label("timePrecision", 6)
     fvsolution = foamdict.read(os.path.join(sysd, "fvSolution")) if os.path.exists(os.path.join(sysd, "fvSolution")) else None
     if not qhd:
         kw.update(R=RR / mix.sub_dict("specie").scalar("molWeight"), Cp=th.scalar("Cp"), Hf=th.scalar("Hf", 0.0),
@@ -214,20 +218,21 @@ def make_solver(setup: CaseSetup, api, dmesh=None):
     return s
 
 
-def time_name(t: float) -> str:
-    """Time::timeName with the default precision 6 [OF]"""
-    return f"{t:.6g}"
+def time_name(t: float, precision: int = 6) -> str:
+    """Time::timeName: general format with controlDict::timePrecision significant digits (default 6) [OF]"""
+    return f"{t:.{precision}g}"
 
 
 def write_time(setup: CaseSetup, s, t: float) -> str:
     """<time>/ fields as the reference's AUTO_WRITE objects (createFields.H): U, T, p (+ rho, e, rhoU, rhoE for QGDFoam)"""
-    d = os.path.join(setup.case_dir, time_name(t))
+    d = os.path.join(setup.case_dir, time_name(t, setup.time_precision))
     names = ("U", "T", "p", "rho", "e", "rhoU", "rhoE") if setup.solver == "QGDFoam" else ("U", "T", "p")
     for n in names:
         cells, bnd = s.get(n, with_bnd=True)
         src = setup.fields.get(n)
         types = dict(src.patch_types) if src is not None else {}
-        foamcase.write_field(os.path.join(d, n), setup.mesh, n, cells, types, bnd, src.dimensions if src is not None else "[0 0 0 0 0 0 0]")
+        foamcase.write_field(os.path.join(d, n), setup.mesh, n, cells, types, bnd, src.dimensions if src is not None else "[0 0 0 0 0 0 0]",
+                             binary=setup.write_binary)
     return d
 
 
@@ -269,7 +274,7 @@ def run(setup: CaseSetup, api, log=print, solver=None, writer=None) -> List[str]
         due = (every_n is not None and steps_since_write >= every_n) or (every_t is not None and t >= next_write - eps)
         if due or t >= setup.end_time - eps:
             written.append(writer(setup, s, t))
-            log(f"Time = {time_name(t)}  deltaT = {sc['deltaT']:.6g}  Courant = {sc['CoNum']:.4g}")
+            log(f"Time = {time_name(t, setup.time_precision)}  deltaT = {sc['deltaT']:.6g}  Courant = {sc['CoNum']:.4g}")
             steps_since_write = 0
             if every_t is not None:
                 while next_write <= t + eps:
@@ -311,7 +316,7 @@ def processor_writer(setup: CaseSetup, sub, proc):
     names = ("U", "T", "p", "rho", "e", "rhoU", "rhoE")
 
     def write(setup_, s, t):
-        d = os.path.join(setup.case_dir, f"processor{proc.rank}", time_name(t))
+        d = os.path.join(setup.case_dir, f"processor{proc.rank}", time_name(t, setup.time_precision))
         for n in names:
             cells, bnd = s.get(n, with_bnd=True)
             own = cells[:sub.n_owned]
@@ -321,7 +326,8 @@ def processor_writer(setup: CaseSetup, sub, proc):
             for patch in proc.mesh.patches:
                 if patch.kind == foamcase.PATCH_PROCESSOR:
                     types[patch.name] = "processor"
-            foamcase.write_field(os.path.join(d, n), proc.mesh, n, own, types, pb, src.dimensions if src is not None else "[0 0 0 0 0 0 0]")
+            foamcase.write_field(os.path.join(d, n), proc.mesh, n, own, types, pb, src.dimensions if src is not None else "[0 0 0 0 0 0 0]",
+                                 binary=setup.write_binary)
         return d
     return write
 

@@ -222,6 +222,7 @@ def test_time_loop_plans_whole_write_intervals():
             return dict(deltaT=2e-4, CoNum=0.1, time=self.t)
     fake = Fake()
     setup = runcase.CaseSetup("/nonexistent", "QGDFoam", None, {}, "0", 0.02, 2e-4, "runTime", 0.01, dict(adjust_time_step=False))
+    assert runcase.time_name(0.0123456789) == "0.0123457" and runcase.time_name(0.0123456789, 3) == "0.0123" and runcase.time_name(2.0) == "2"
     written = []
     orig_make, orig_write = runcase.make_solver, runcase.write_time
     runcase.make_solver = lambda s, api, dmesh=None: fake
@@ -280,6 +281,14 @@ def test_parallel_writer_puts_owned_results_into_processor_directories(tmp_path)
         fU = fc.read_field(os.path.join(d, "U"), pm)
         assert fU.internal.shape == (proc.cell_addr.size, 3)
     assert np.array_equal(back, gT)
+    # reconstructPar: processor time directories -> the undecomposed case
+    rec = fc.reconstruct_fields(str(tmp_path), "0.01", ("T", "U"), m)
+    assert np.array_equal(rec["T"], gT)
+    fT = fc.read_field(str(tmp_path / "0.01" / "T"), m)
+    assert np.array_equal(fT.internal, gT)
+    nI = m.n_internal
+    for p in m.patches:
+        assert np.array_equal(fT.patch_values[p.name], gTb[p.start - nI:p.start - nI + p.size]) and fT.patch_types[p.name] == "fixedValue"
     # wrong world size / unsupported solver are refused before any device call
     with pytest.raises(foamdict.FoamDictError):
         runcase.run_parallel(setup, None, 0, 3)
