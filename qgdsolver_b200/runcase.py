@@ -141,7 +141,8 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
     model = qgd.word("QGDCoeffs")                                     # QGDThermo.C:56
     table = QHD_MODELS if qhd else QGD_MODELS
     if model not in QGD_MODELS + QHD_MODELS:                          # QGDCoeffs.C:70-79
-        raise FoamDictError(f"Unknown QGD coeffs evaluation approach type {model}")
+        toc = sorted(QGD_MODELS + QHD_MODELS)
+        raise FoamDictError(f"Unknown QGD coeffs evaluation approach type {model}\n\nValid model types are:\n{len(toc)}\n(\n" + "\n".join(toc) + "\n)\n")
     if model not in table:
         raise FoamDictError(f"QGDCoeffs {model} is not a model of {solver}")
     coeffs = qgd.sub_or_self(model + "Dict")                          # QGDCoeffs.C:81-116
