@@ -42,7 +42,8 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 static ncclComm_t g_comm = nullptr;
-static int g_rank = 0, g_nranks = 1;
+[[maybe_unused]] static int g_rank = 0;
+static int g_nranks = 1;
 
 static void loadNccl()
 {

@@ -22,8 +22,6 @@ namespace {
 
 constexpr int kBlock = 256;
 
-__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
-
 __device__ __forceinline__ RecA loadA(const SolverView& sv, int i)
 {
     const double* p = sv.S + i;
