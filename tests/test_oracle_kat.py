@@ -1086,3 +1086,42 @@ def test_decomposed_run_oracle_for_qhdfoam_and_implicit_qgdfoam(oracle_mod):
     c.oracle_step(a, 5); c.oracle_step(b, 5)
     for f in ("rho", "rhoU", "rhoE"):
         assert np.abs(a.get(f) - b.get(f)).max() < 1e-11 * np.abs(a.get(f)).max(), f
+
+
+def test_implicit_branch_explicit_stress_parts_match_numpy_restatement(oracle_mod):
+    """updateFluxes.H:107-111 and QGDUEqn.H:72-74 restated with numpy:
+    phiTauMC = Sf & interpolate(muEff dev2(T(fvc::grad(U))))  (Gauss-linear cell gradient of the old U, boundary values by
+    gaussGrad::correctBoundaryConditions), phiSigmaDotU = Sf & ((muf interpolate(fvc::grad(U_new)) + tauMC) & Uf_old)."""
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", implicit=True, gas=dict(cases.GAS, mu=2e-2))
+    m = c.mesh
+    nI, nC = m.n_internal, m.n_cells
+    o = c.make_oracle(oracle_mod)
+    (U0, UB0), (mu0, muB0) = o.get("U", with_bnd=True), o.get("mu", with_bnd=True)
+    c.oracle_step(o, 1)
+    Sf, V = m.Sf, m.V
+    nrm = Sf[nI:] / m.magSf[nI:, None]
+
+    def gauss_grad(U, UB):
+        Uf = o.linear_interpolate(U, UB)
+        g = _surface_integrate(m, np.einsum("fi,fj->fij", Sf, Uf)) / V[:, None, None]
+        sn = m.deltaCoeffs[nI:, None] * (UB - U[m.owner[nI:]])                       # fixedValue patches
+        gP = g[m.owner[nI:]]
+        gB = gP + np.einsum("bi,bj->bij", nrm, sn - np.einsum("bi,bij->bj", nrm, gP))
+        return g, gB, Uf
+
+    def dev2T(mu, g):
+        gt = np.swapaxes(g, 1, 2)
+        return mu[:, None, None] * (gt - (2.0 / 3.0) * np.trace(g, axis1=1, axis2=2)[:, None, None] * np.eye(3)[None])
+
+    g0, g0B, Uf0 = gauss_grad(U0, UB0)
+    tauMC = o.linear_interpolate(dev2T(mu0, g0).reshape(nC, 9), dev2T(muB0, g0B).reshape(-1, 9)).reshape(-1, 3, 3)
+    phiTauMC = np.einsum("fi,fij->fj", Sf, tauMC)
+    got = o.get_face("phiTauMC")
+    assert np.abs(got - phiTauMC).max() < 1e-12 * np.abs(phiTauMC).max()
+    U1, UB1 = o.get("U", with_bnd=True)
+    g1, g1B, _ = gauss_grad(U1, UB1)
+    g1f = o.linear_interpolate(g1.reshape(nC, 9), g1B.reshape(-1, 9)).reshape(-1, 3, 3)
+    muf = o.linear_interpolate(mu0, muB0)
+    sig = np.einsum("fij,fj->fi", muf[:, None, None] * g1f + tauMC, Uf0)
+    phiS = np.einsum("fi,fi->f", Sf, sig)
+    assert np.abs(o.get_face("phiSigmaDotU") - phiS).max() < 1e-11 * np.abs(phiS).max()
