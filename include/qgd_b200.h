@@ -88,6 +88,10 @@ typedef struct {
 } qgd_mesh_desc;
 
 int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out);
+/* faceSet "degenerateStencilFaces" (constant/polyMesh/sets, leastSquaresStencil.C:63-132): polyMesh ids of faces whose
+ * `leastSquares` gradient is replaced by nf*snGrad, in addition to those found degenerate by det(G) < 1.  Call before
+ * qgd_fvsc_create / qgd_*foam_create on this mesh; boundary faces in the list are ignored (serial meshes). */
+int qgd_mesh_set_degenerate_stencil_faces(qgd_mesh* mesh, const int* faces, int n);
 int qgd_mesh_destroy(qgd_mesh* mesh);
 /* derived fields, for write-back / parity checks.  what: 0 hQGDf (n_faces)  QGDCoeffs.C:298-318
  *                                                        1 hQGD  (n_cells)  QGDCoeffs.C:320-362 */

@@ -97,6 +97,7 @@ def lib():
         L.or_pcg_solve.restype = C.c_int
         L.or_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp]
         L.or_set_pcg_blocks.argtypes = [C.c_void_p, _ip]
+        L.or_set_degenerate_faces.argtypes = [C.c_void_p, _ip, C.c_int]
         L.or_pcg_solve_blocks.restype = C.c_int
         L.or_pcg_solve_blocks.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _ip]
         L.or_qhd_init.argtypes = [C.c_void_p, C.POINTER(QHDParams), C.c_int, _ip, _ip, _ip, _dp, _dp, _dp,
@@ -247,6 +248,11 @@ class Oracle:
         out = np.zeros((self.mesh.n_faces, k) if k > 1 else self.mesh.n_faces)
         lib().or_qgd_get_face(self._h, fid, _d(out))
         return out
+
+    def set_degenerate_faces(self, faces):
+        """faceSet degenerateStencilFaces of the leastSquares scheme (leastSquaresStencil.C:63-132)"""
+        f = np.ascontiguousarray(faces, np.int32)
+        lib().or_set_degenerate_faces(self._h, _i(f), int(f.size))
 
     def set_pcg_blocks(self, cell_block=None):
         """linear solvers of the following steps in the decomposed-run form (block-local preconditioner)"""

@@ -92,6 +92,7 @@ struct or_ctx {
     Vec pGrad;                  // qgdFlux gradient per bface
     IVec constScCells;          // varScModel7 constScCellSet
     IVec pcgBlocks;             // processor of each cell for the linear solvers of a decomposed run (empty = serial)
+    IVec lsForcedDeg;           // faceSet degenerateStencilFaces (leastSquaresStencil.C:63-132): internal faces forced to nf*snGrad
     Vec suRho, suU, suE;        // explicit source matrices rhoSu / rhoUSu / rhoESu: volume-integrated source per cell (empty = zero)
     // surface fields (nFaces*k)
     Vec tauQGDf, rhof, Uf, rhoUf, UrhoUf, pf, cf, gammaf, Hf, alphauf, muf;
@@ -473,6 +474,7 @@ void buildLeastSquares(or_ctx& m)
         }
         m.lsOff[f + 1] = (int)m.lsCell.size();
     }
+    for (int f : m.lsForcedDeg) if (f >= 0 && f < m.nInternal) m.lsDeg[f] = 1;            // leastSquaresStencil.C:84-91,117
     m.lsBuilt = true;
 }
 
@@ -1183,6 +1185,7 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
 
 double or_qgd_deltaT(or_ctx* s) { return s->deltaT; }
 void or_qgd_set_const_sc_cells(or_ctx* s, const int* cells, int n) { s->constScCells.assign(cells, cells + n); }
+void or_set_degenerate_faces(or_ctx* s, const int* faces, int n) { s->lsForcedDeg.assign(faces, faces + n); s->lsBuilt = false; }
 void or_set_pcg_blocks(or_ctx* s, const int* cellBlock) { if (cellBlock) s->pcgBlocks.assign(cellBlock, cellBlock + s->nCells); else s->pcgBlocks.clear(); }
 int or_pcg_solve_blocks(or_ctx* sp, const double* diag, const double* upper, const double* b, double* x, double tol,
                         double relTol, int maxIter, int precond, double* initRes, double* finalRes, const int* cellBlock);

@@ -156,6 +156,10 @@ int or_pcg_solve_blocks(or_ctx*, const double* diag, const double* upper, const 
                         double tol, double relTol, int maxIter, int precond, double* initRes, double* finalRes,
                         const int* cellBlock);
 
+// faceSet "degenerateStencilFaces" (leastSquaresStencil.C:63-132): internal faces whose leastSquares gradient is replaced by
+// nf*snGrad, in addition to the faces found degenerate by det(G) < 1.  polyMesh face ids; boundary faces are ignored here
+// (the reference only keeps those on processor patches).
+void or_set_degenerate_faces(or_ctx*, const int* faces, int n);
 // every PCG solve of the following QGDFoam (implicit branch) / QHDFoam steps runs in the decomposed-run form above
 // (NULL: back to serial).  The rest of the step is decomposition-independent in exact arithmetic.
 void or_set_pcg_blocks(or_ctx*, const int* cellBlock);

@@ -24,7 +24,7 @@ QGD_OK, ERR_INVALID, ERR_UNKNOWN_MODEL, ERR_UNSUPPORTED, ERR_CUDA, ERR_COMM, ERR
 # every symbol include/qgd_b200.h declares (checked by tests/test_abi_cpu.py)
 ABI_SYMBOLS = [
     "qgd_init", "qgd_last_error", "qgd_version", "qgd_device_synchronize",
-    "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get",
+    "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get", "qgd_mesh_set_degenerate_stencil_faces",
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
@@ -103,6 +103,7 @@ def load_library():
     L.qgd_init.argtypes = [C.c_int]
     L.qgd_mesh_create.argtypes = [C.POINTER(_MeshDesc), C.POINTER(C.c_void_p)]
     L.qgd_mesh_destroy.argtypes = [C.c_void_p]
+    L.qgd_mesh_set_degenerate_stencil_faces.argtypes = [C.c_void_p, _ip, C.c_int]
     L.qgd_mesh_get.argtypes = [C.c_void_p, C.c_int, _dp]
     L.qgd_fvsc_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     L.qgd_fvsc_destroy.argtypes = [C.c_void_p]
@@ -217,6 +218,11 @@ class Mesh:
             d.geometric_d[j] = int(mesh.geometric_d[j])
         self._h = C.c_void_p()
         _check(load_library().qgd_mesh_create(C.byref(d), C.byref(self._h)))
+
+    def set_degenerate_stencil_faces(self, faces):
+        """faceSet degenerateStencilFaces of the leastSquares scheme (leastSquaresStencil.C:63-132); before any stencil / solver"""
+        f = np.ascontiguousarray(faces, np.int32)
+        _check(load_library().qgd_mesh_set_degenerate_stencil_faces(self._h, _i(f), int(f.size)))
 
     def hQGDf(self):
         out = np.empty(self.mesh.n_faces)

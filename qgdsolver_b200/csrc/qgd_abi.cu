@@ -652,6 +652,8 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         std::vector<char> deg;
         mesh->h.buildLeastSquares(name == "leastSquaresOpt", W, cells, coef, deg);
         const int nI = mesh->h.nInternal;
+        if (name == "leastSquares")                     // leastSquaresStencil.C:63-132: user faceSet of faces forced to nf*snGrad
+            for (int f : mesh->h.forcedDegFaces) if (f >= 0 && f < nI) deg[f] = 1;
         const size_t nIs = (size_t)std::max(nI, 1);
         std::vector<int> cd((size_t)W * nIs, 0);
         std::vector<double> kd((size_t)W * 3 * nIs, 0.0);
@@ -818,6 +820,17 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         m->ndC.upload(permD(h.ndC), g_stream); m->V.upload(h.V, g_stream);
         m->hQGDf.upload(permD(h.hQGDf), g_stream); m->hQGD.upload(h.hQGD, g_stream);
         *out = m.release();
+    });
+}
+
+int qgd_mesh_set_degenerate_stencil_faces(qgd_mesh* m, const int* faces, int n)
+{
+    return guarded([&] {
+        requireInit();
+        if (!m || n < 0 || (n > 0 && !faces)) throw Error(QGD_ERR_INVALID, "qgd_mesh_set_degenerate_stencil_faces: bad argument");
+        for (int i = 0; i < n; ++i)
+            if (faces[i] < 0 || faces[i] >= m->h.nFaces) throw Error(QGD_ERR_INVALID, "qgd_mesh_set_degenerate_stencil_faces: face id out of range");
+        m->h.forcedDegFaces.assign(faces, faces + n);
     });
 }
 

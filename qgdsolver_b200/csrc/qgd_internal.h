@@ -93,6 +93,7 @@ struct HostMesh {
     std::vector<int> bfacePatch;
     // derived
     std::vector<int> cfOff, cfEnc;                 // cell -> faces, enc = (face<<1)|isNeighbourSide
+    std::vector<int> forcedDegFaces;               // faceSet degenerateStencilFaces (leastSquaresStencil.C:63-132), polyMesh face ids
     std::vector<int> pcOff, pcCell;                // non-patch point -> cells
     std::vector<double> pcW;
     std::vector<int> patchPoints;                  // list of patch points

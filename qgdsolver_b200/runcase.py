@@ -207,6 +207,9 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
 def make_solver(setup: CaseSetup, api, dmesh=None):
     """api.QGDFoam / api.QHDFoam initialised from the case (the calls a shim makes through the C ABI)"""
     dmesh = dmesh or api.Mesh(setup.mesh)
+    deg = os.path.join(setup.case_dir, "constant", "polyMesh", "sets", "degenerateStencilFaces")     # leastSquaresStencil.C:63-70 READ_IF_PRESENT
+    if os.path.exists(deg) and setup.solver_kwargs["fvsc_scheme"] == "leastSquares":
+        dmesh.set_degenerate_stencil_faces(foamcase.read_labels(deg))
     cls = api.QGDFoam if setup.solver == "QGDFoam" else api.QHDFoam
     s = cls(dmesh, **setup.solver_kwargs)
     if setup.const_sc_cell_set:

@@ -1125,3 +1125,25 @@ def test_implicit_branch_explicit_stress_parts_match_numpy_restatement(oracle_mo
     sig = np.einsum("fij,fj->fi", muf[:, None, None] * g1f + tauMC, Uf0)
     phiS = np.einsum("fi,fi->f", Sf, sig)
     assert np.abs(o.get_face("phiSigmaDotU") - phiS).max() < 1e-11 * np.abs(phiS).max()
+
+
+def test_least_squares_degenerate_face_set(oracle_mod):
+    """faceSet degenerateStencilFaces (leastSquaresStencil.C:63-132): the listed internal faces get nf*snGrad, every other face
+    keeps its least-squares gradient."""
+    mesh = cases.case_2d((10, 9), perturb=0.15).mesh
+    nI = mesh.n_internal
+    rng = np.random.default_rng(4)
+    phi, bnd = rng.random(mesh.n_cells), rng.random(mesh.n_bnd)
+    bsg = mesh.deltaCoeffs[nI:] * (bnd - phi[mesh.owner[nI:]])
+    sch = oracle_mod.FVSC_SCHEMES["leastSquares"]
+    base = oracle_mod.Oracle(mesh).fvsc_grad(phi, bnd, bsg, scheme=sch)
+    forced = np.arange(3, nI, 7, dtype=np.int32)
+    o = oracle_mod.Oracle(mesh)
+    o.set_degenerate_faces(np.concatenate([forced, [nI + 2]]))            # a boundary face in the set is ignored
+    got = o.fvsc_grad(phi, bnd, bsg, scheme=sch)
+    keep = np.ones(mesh.n_faces, bool); keep[forced] = False
+    assert np.array_equal(got[keep], base[keep])
+    nf = mesh.Sf[forced] / mesh.magSf[forced, None]
+    sn = mesh.nonOrthDeltaCoeffs[forced] * (phi[mesh.neighbour[forced]] - phi[mesh.owner[forced]])
+    assert np.abs(got[forced] - sn[:, None] * nf).max() < 1e-14 * np.abs(got).max()
+    assert np.abs(got[forced] - base[forced]).max() > 1e-3

@@ -57,3 +57,32 @@ def test_runcase_end_to_end_writes_the_oracle_solution(qgd, oracle_mod, tmp_path
         f = fc.read_field(os.path.join(str(tmp_path), "0.02", name), setup.mesh)
         ref = o.get(name)
         assert float(np.abs(f.internal - ref).max()) / float(np.abs(ref).max()) < TOL_STEP, name
+
+
+@NOT_RUN
+def test_least_squares_degenerate_face_set_on_device(qgd, oracle_mod):
+    """qgd_mesh_set_degenerate_stencil_faces (faceSet degenerateStencilFaces, leastSquaresStencil.C:63-132): operator and
+    60 solver steps against the oracle with the same forced faces."""
+    c = cases.case_2d((14, 12), perturb=0.15, bcs="mixed", scheme="leastSquares")
+    m = c.mesh
+    nI = m.n_internal
+    forced = np.arange(2, nI, 5, dtype=np.int32)
+    rng = np.random.default_rng(4)
+    phi, bnd = rng.random(m.n_cells), rng.random(m.n_bnd)
+    bsg = m.deltaCoeffs[nI:] * (bnd - phi[m.owner[nI:]])
+    o = oracle_mod.Oracle(m)
+    o.set_degenerate_faces(forced)
+    dm = qgd.Mesh(m)
+    dm.set_degenerate_stencil_faces(forced)
+    st = qgd.FvscStencil(dm, "leastSquares")
+    ref = o.fvsc_grad(phi, bnd, bsg, scheme=oracle_mod.FVSC_SCHEMES["leastSquares"])
+    assert float(np.abs(st.Grad(phi, bnd, bsg) - ref).max()) / float(np.abs(ref).max()) < 1e-12
+    oc = c.make_oracle(oracle_mod)
+    # the oracle context of the step needs the same set before its first leastSquares evaluation
+    oc.set_degenerate_faces(forced)
+    s = c.make_solver(qgd, dm)
+    c.oracle_step(oc, 60)
+    s.step(60)
+    for f in ("rho", "rhoU", "rhoE"):
+        a, b = s.get(f), oc.get(f)
+        assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < TOL_STEP, f
