@@ -39,7 +39,8 @@ class QGDParams(C.Structure):
                 ("PrQGD", C.c_double), ("implicitDiffusion", C.c_int), ("alphaEffGammaFactor", C.c_int),
                 ("energyDdtRhoEQuirk", C.c_int), ("qgdModel", C.c_int),
                 ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int),
-                ("varScCSc1", C.c_double), ("varScMinSc", C.c_double), ("varScMaxSc", C.c_double)]
+                ("varScCSc1", C.c_double), ("varScMinSc", C.c_double), ("varScMaxSc", C.c_double),
+                ("transportModel", C.c_int), ("mu0", C.c_double), ("T0", C.c_double), ("kExp", C.c_double)]
 
 
 QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2, "varScModel6": 6, "varScModel7": 7}

@@ -651,6 +651,7 @@ void fvscDiv(const or_ctx& m, int scheme, int k, const double* cell, const doubl
 // thermo: perfectGas + hConst + sensibleInternalEnergy + constTransport [OF-v2312]  
 struct Thermo {
     double R, Cp, Hf, Tref, Hsref, mu, Pr;
+    int transport = 0; double mu0 = 0, T0 = 1, kExp = 0;                       // powerLawTransport.C:53-60
     double Cv() const { return Cp - R; }                                       // Cv = Cp - CpMCv, CpMCv = R
     double Es(double /*p*/, double T) const { return Cp * (T - Tref) + Hsref - R * T; }   // Hs - p/rho
     double HE(double p, double T) const { return Es(p, T); }
@@ -666,12 +667,17 @@ struct Thermo {
         return Tnew;
     }
     double psi(double /*p*/, double T) const { return 1.0 / (R * T); }
-    double muF(double, double) const { return mu; }
-    double alphah(double, double) const { return mu / Pr; }
+    double muF(double, double T) const { return transport == 1 ? mu0 * std::pow(T / T0, kExp) : mu; }       // powerLawTransportI.H:121-128
+    double alphah(double p, double T) const { return transport == 1 ? muF(p, T) * (1.0 / Pr) : mu / Pr; }    // :143-150 (rPr_) | constTransport
     double gamma() const { return Cp / Cv(); }
 };
 
-Thermo thermoOf(const or_ctx& s) { return {s.prm.R, s.prm.Cp, s.prm.Hf, s.prm.Tref, s.prm.Hsref, s.prm.mu, s.prm.Pr}; }
+Thermo thermoOf(const or_ctx& s)
+{
+    Thermo t{s.prm.R, s.prm.Cp, s.prm.Hf, s.prm.Tref, s.prm.Hsref, s.prm.mu, s.prm.Pr};
+    t.transport = s.prm.transportModel; t.mu0 = s.prm.mu0; t.T0 = s.prm.T0; t.kExp = s.prm.kExp;
+    return t;
+}
 
 // patch snGrad() of a field with the given BC [OF-v2312 fvPatchField::snGrad, zeroGradient, fixedGradient]
 void patchSnGrad(const or_ctx& s, int k, const IVec& bc, const double* cell, const double* bnd, const double* grad, double* out)

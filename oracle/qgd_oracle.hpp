@@ -70,6 +70,10 @@ typedef struct {
     int diffMaxIter, diffPrecond;
     // varScModel7 dictionary entries (varScModel7.C:96-119): cSc1 (default 1), minSc / maxSc (default -1 = off)
     double varScCSc1, varScMinSc, varScMaxSc;
+    // transport model: 0 const (mu, Pr above), 1 powerLaw  mu = mu0 (T/T0)^k, alphah = mu * (1/Pr)  (powerLawTransportI.H:120-150).
+    // Oracle only so far: the device library implements const transport.
+    int transportModel;
+    double mu0, T0, kExp;
 } or_qgd_params_t;
 
 typedef struct or_ctx or_ctx;

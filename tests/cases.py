@@ -16,6 +16,7 @@ class Case:
                  alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, varsc=None, sources=None, **opts):
         self.model, self.implicit = model, implicit
         self.sources = sources          # (rhoSu, rhoUSu, rhoESu) volume-integrated explicit sources or None (createZeroSources.H:28-44)
+        self.power_law = None           # dict(mu0, T0, k): powerLaw transport - oracle only so far (powerLawTransportI.H:120-150)
         # varScModel7 dictionary entries (cSc1, minSc, maxSc) and the constScCellSet cell list
         self.varsc = dict(cSc1=1.0, minSc=-1.0, maxSc=-1.0, const_sc_cells=None)
         self.varsc.update(varsc or {})
@@ -40,6 +41,8 @@ class Case:
                           alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
                           energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model],
                           varScCSc1=self.varsc["cSc1"], varScMinSc=self.varsc["minSc"], varScMaxSc=self.varsc["maxSc"])
+        if self.power_law:
+            prm.transportModel, prm.mu0, prm.T0, prm.kExp = 1, self.power_law["mu0"], self.power_law["T0"], self.power_law["k"]
         scheme = O.FVSC_SCHEMES[self.scheme]
         o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
                    alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme, const_sc_cells=self.varsc["const_sc_cells"])

@@ -1147,3 +1147,28 @@ def test_least_squares_degenerate_face_set(oracle_mod):
     sn = mesh.nonOrthDeltaCoeffs[forced] * (phi[mesh.neighbour[forced]] - phi[mesh.owner[forced]])
     assert np.abs(got[forced] - sn[:, None] * nf).max() < 1e-14 * np.abs(got).max()
     assert np.abs(got[forced] - base[forced]).max() > 1e-3
+
+
+def test_power_law_transport_in_the_oracle(oracle_mod):
+    """powerLawTransportI.H:120-150: mu = mu0 (T/T0)^k, alphah = mu (1/Pr); the QGD parts are added on top
+    (QGDThermo.C:91-98).  With k = 0 and mu0 = mu the run is the constant-transport run bit for bit.  (Oracle only: the
+    device library implements const transport and refuses anything else.)"""
+    gas = dict(cases.GAS, mu=3e-3)
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=gas)
+    c.power_law = dict(mu0=3e-3, T0=0.7, k=0.76)
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 5)
+    T, p = o.get("T"), o.get("p")
+    tau = o.get("tauQGD")
+    mol = 3e-3 * (T / 0.7) ** 0.76
+    # mu / alpha were formed in thermo.correct() with the pressure before p = rho/psi: reconstruct muQGD from alpha - mu instead
+    mu, alpha = o.get("mu"), o.get("alpha")
+    muQ = mu - mol
+    assert muQ.min() > 0 and np.abs(alpha - (mol * (1.0 / gas["Pr"]) + muQ / gas["PrQGD"])).max() < 1e-15
+    assert np.abs(muQ / (gas["ScQGD"] * tau) - p).max() < 1e-2 * p.max()          # muQGD = p_old ScQGD tau, p_old ~ p
+    same = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=gas)
+    same.power_law = dict(mu0=3e-3, T0=1.0, k=0.0)
+    a, b = same.make_oracle(oracle_mod), cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=gas).make_oracle(oracle_mod)
+    same.oracle_step(a, 10); same.oracle_step(b, 10)
+    assert np.abs(a.get("rho") - b.get("rho")).max() < 1e-14 and np.abs(a.get("rhoE") - b.get("rhoE")).max() < 1e-13
+    assert np.abs(o.get("rhoE") - b.get("rhoE")).max() > 1e-9                      # the temperature dependence matters
