@@ -696,13 +696,24 @@ void patchSnGrad(const or_ctx& s, int k, const IVec& bc, const double* cell, con
     }
 }
 
-// correctBoundaryConditions() for U (fixedValue | zeroGradient)
+// correctBoundaryConditions() for U (fixedValue | zeroGradient | slip)
+// slip / symmetryPlane [OF-v2312 basicSymmetryFvPatchField::evaluate]: (U_P + transform(I - 2 nn, U_P))/2 = U_P - n (n . U_P);
+// its snGrad (transform(I - 2nn, U_P) - U_P) deltaCoeffs/2 equals deltaCoeffs (U_b - U_P), the generic branch of patchSnGrad.
+// Oracle only so far (explicit branch): the device library has no slip condition yet.
 void correctU(or_ctx& s)
 {
     for (int b = 0; b < s.nBnd; ++b) {
         const int pi = s.bfacePatch[b];
         if (s.patchKind[pi] == OR_PATCH_EMPTY) continue;
-        const int P = s.owner[s.nInternal + b];
+        const int f = s.nInternal + b;
+        const int P = s.owner[f];
+        if (s.bcU[pi] == OR_BC_SLIP) {
+            const double* n = &s.nf[3 * (size_t)f];
+            const double* u = &s.U[3 * (size_t)P];
+            const double un = n[0] * u[0] + n[1] * u[1] + n[2] * u[2];
+            for (int j = 0; j < 3; ++j) s.UB[3 * (size_t)b + j] = u[j] - n[j] * un;
+            continue;
+        }
         for (int j = 0; j < 3; ++j)
             s.UB[3 * (size_t)b + j] = (s.bcU[pi] == OR_BC_FIXED_VALUE) ? s.bvU[3 * (size_t)b + j] : s.U[3 * (size_t)P + j];
     }

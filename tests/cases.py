@@ -6,6 +6,7 @@ import numpy as np
 from qgdsolver_b200 import polymesh as pm
 
 FV, ZG, FG, QF = 0, 1, 2, 3   # bc kinds (fixedValue, zeroGradient, fixedGradient, qgdFlux)
+SLIP = 5                      # oracle only so far (OR_BC_SLIP): slip / symmetryPlane velocity
 
 GAS = dict(R=1.0, Cp=3.5, Hf=0.0, Tref=0.0, Hsref=0.0, mu=1.0e-3, Pr=0.71, ScQGD=1.0, PrQGD=1.0)
 GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5, Pr=0.71, ScQGD=0.7, PrQGD=0.9)

@@ -1172,3 +1172,35 @@ def test_power_law_transport_in_the_oracle(oracle_mod):
     same.oracle_step(a, 10); same.oracle_step(b, 10)
     assert np.abs(a.get("rho") - b.get("rho")).max() < 1e-14 and np.abs(a.get("rhoE") - b.get("rhoE")).max() < 1e-13
     assert np.abs(o.get("rhoE") - b.get("rhoE")).max() > 1e-9                      # the temperature dependence matters
+
+
+def test_slip_walls_in_the_oracle(oracle_mod):
+    """slip / symmetryPlane velocity [OF basicSymmetry]: U_b = U_P - n (n . U_P).  A channel with slip side walls, inflow / outflow
+    by zeroGradient: a uniform stream along the channel stays exactly uniform (nothing to regularise, no wall shear), the wall-normal
+    boundary velocity is zero for any interior field, and the mass flux through the slip walls vanishes.  (Oracle only so far.)"""
+    c = cases.case_hex3d(n=(8, 5, 4), bcs="zg", gas=dict(cases.GAS, mu=1e-2))
+    m = c.mesh
+    names = [p.name for p in m.patches]
+    for nm in ("yMin", "yMax", "zMin", "zMax"):
+        c.bcU[names.index(nm)] = cases.SLIP
+    c.U0 = np.tile([0.3, 0.0, 0.0], (m.n_cells, 1))
+    c.p0 = np.full(m.n_cells, 1.0 / 1.4)
+    c.T0 = np.full(m.n_cells, (1.0 / 1.4) / c.gas["R"])
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 20)
+    assert np.abs(o.get("U") - [0.3, 0.0, 0.0]).max() < 1e-14 and np.abs(o.get("rho") - 1.0).max() < 1e-14
+    # a general interior field: the boundary velocity on slip patches has no normal component
+    d = cases.case_hex3d(n=(8, 5, 4), perturb=0.2, bcs="zg")
+    for nm in ("yMin", "yMax", "zMin", "zMax"):
+        d.bcU[names.index(nm)] = cases.SLIP
+    od = d.make_oracle(oracle_mod)
+    d.oracle_step(od, 5)
+    nI = d.mesh.n_internal
+    pid = d.mesh.patch_id_per_bface()
+    slip = np.isin(pid, [names.index(nm) for nm in ("yMin", "yMax", "zMin", "zMax")])
+    UB = od.get("U", with_bnd=True)[1]
+    nrm = d.mesh.Sf[nI:] / d.mesh.magSf[nI:, None]
+    assert np.abs((UB * nrm).sum(1)[slip]).max() < 1e-15
+    UP = od.get("U")[d.mesh.owner[nI:]]
+    assert np.abs(UB - (UP - nrm * (UP * nrm).sum(1)[:, None]))[slip].max() < 1e-15
+    assert np.abs(UB - UP)[~slip].max() == 0.0                                    # zeroGradient elsewhere
