@@ -487,3 +487,70 @@ def _assemble(pts, faces, n_cells, patch_names, kinds: Optional[Dict[str, str]] 
                     owner=np.array(owner, np.int32), neighbour=np.array(neigh, np.int32),
                     patches=patches, n_cells=n_cells)
     return mesh.compute_geometry()
+
+
+def subset_mesh(mesh: PolyMesh, keep: np.ndarray, exposed_patch: str = "oldInternalFaces", exposed_kind: int = PATCH_GENERIC) -> PolyMesh:
+    """subsetMesh [OF]: the cells with keep[c] true, renumbered in ascending order; faces between a kept and a removed cell
+    become boundary faces of the new patch `exposed_patch` (reversed when the kept cell was the neighbour), unused points are
+    dropped.  Internal faces keep their upper-triangular order, patches their order (the exposed patch comes last)."""
+    keep = np.asarray(keep, bool)
+    nI = mesh.n_internal
+    c2n = np.full(mesh.n_cells, -1, np.int64)
+    c2n[keep] = np.arange(int(keep.sum()))
+    ko, kn = keep[mesh.owner[:nI]], keep[mesh.neighbour]
+    f_int = np.nonzero(ko & kn)[0]
+    faces = [f_int]
+    flip = [np.zeros(f_int.size, bool)]
+    owner = [c2n[mesh.owner[f_int]]]
+    neigh = c2n[mesh.neighbour[f_int]]
+    patches, start = [], f_int.size
+    for p in mesh.patches:
+        ids = np.arange(p.start, p.start + p.size)
+        sel = ids[keep[mesh.owner[ids]]]
+        faces.append(sel); flip.append(np.zeros(sel.size, bool)); owner.append(c2n[mesh.owner[sel]])
+        patches.append(Patch(p.name, p.kind, start, sel.size, p.neighb_rank))
+        start += sel.size
+    exp_o = np.nonzero(ko & ~kn)[0]                       # kept owner: orientation stays
+    exp_n = np.nonzero(~ko & kn)[0]                       # kept neighbour: face reversed
+    ids = np.concatenate([exp_o, exp_n])
+    fl = np.concatenate([np.zeros(exp_o.size, bool), np.ones(exp_n.size, bool)])
+    own_new = np.concatenate([c2n[mesh.owner[exp_o]], c2n[mesh.neighbour[exp_n]]])
+    o = np.lexsort((ids, own_new))
+    faces.append(ids[o]); flip.append(fl[o]); owner.append(own_new[o])
+    patches.append(Patch(exposed_patch, exposed_kind, start, ids.size))
+    gf, gflip = np.concatenate(faces), np.concatenate(flip)
+    used = np.zeros(mesh.n_points, bool)
+    nv = mesh.face_nverts()
+    idx = np.repeat(mesh.face_offsets[gf], nv[gf]) + _ragged(nv[gf])
+    used[mesh.face_verts[idx]] = True
+    p2n = np.full(mesh.n_points, -1, np.int64)
+    p2n[used] = np.arange(int(used.sum()))
+    verts, offs = [], [0]
+    for f, r in zip(gf, gflip):
+        v = mesh.face_verts[mesh.face_offsets[f]:mesh.face_offsets[f + 1]]
+        if r:
+            v = np.concatenate([v[:1], v[:0:-1]])
+        verts.append(p2n[v]); offs.append(offs[-1] + v.size)
+    sub = PolyMesh(points=np.ascontiguousarray(mesh.points[used]), face_offsets=np.asarray(offs, np.int32),
+                   face_verts=np.concatenate(verts).astype(np.int32), owner=np.concatenate(owner).astype(np.int32),
+                   neighbour=neigh.astype(np.int32), patches=patches, n_cells=int(keep.sum()), geometric_d=mesh.geometric_d.copy())
+    return sub.compute_geometry()
+
+
+def _ragged(counts: np.ndarray) -> np.ndarray:
+    counts = np.asarray(counts, np.int64)
+    starts = np.zeros(counts.size, np.int64)
+    np.cumsum(counts[:-1], out=starts[1:])
+    return np.arange(int(counts.sum()), dtype=np.int64) - np.repeat(starts, counts)
+
+
+def forward_step(n: int = 40, thick: float = 0.05) -> PolyMesh:
+    """The Mach-3 forward-facing step (Woodward & Colella; BASELINE configs[1]): channel 3 x 1 with a step of height 0.2 starting
+    at x = 0.6, one cell thick (empty front / back), square cells of size 1/n.  Patches: xMin inlet, xMax outlet, yMin / yMax
+    walls, zMin / zMax empty, `step` = the two faces of the step."""
+    nx, ny = 3 * n, n
+    m = hex_box(nx, ny, 1, lengths=(3.0, 1.0, thick), patch_kinds={"zMin": "empty", "zMax": "empty"})
+    inside = (m.C[:, 0] > 0.6) & (m.C[:, 1] < 0.2)
+    s = subset_mesh(m, ~inside, "step")
+    s.geometric_d = np.array([1, 1, -1], np.int32)
+    return s

@@ -271,3 +271,23 @@ def qhd_cavity(n=(16, 16), dims=2, perturb=0.0, model="constTau", p_bc="qhdflux"
     T0 = 1.0 - x + 0.05 * np.sin(2 * np.pi * y) + 1e-3 * (rng.random(mesh.n_cells) - 0.5)
     p0 = 1e-3 * np.cos(np.pi * x) * np.cos(np.pi * y)
     return QHDCase(mesh, np.ascontiguousarray(U0), T0, p0, kU, kT, kP, bvU, bvT, bvP, model=model, **kw)
+
+
+def case_forward_step(n=40, co=0.05, **opts):
+    """BASELINE configs[1] in miniature: Mach-3 wind tunnel with a forward-facing step (Woodward & Colella set-up: rho = 1.4,
+    p = 1, u = 3, gamma = 1.4), inviscid, QGD regularisation only.  Inlet fixedValue, outlet zeroGradient, walls and step:
+    slip velocity (oracle only so far), zeroGradient T and p.  co: acoustic Courant number (|U|+c) dt / h of the free stream; the
+    explicit QGD step needs about 0.05 here (0.2 blows up at the impulsive start: tau |U|^2 acts as a viscosity ~ 4.5 h)."""
+    mesh = pm.forward_step(n)
+    gas = dict(GAS, mu=0.0, Pr=1.0)
+    names = [p.name for p in mesh.patches]
+    nP, nB = len(names), mesh.n_bnd
+    kU = np.array([FV if nm == "xMin" else (ZG if nm == "xMax" else SLIP) for nm in names], np.int32)
+    kT = np.array([FV if nm == "xMin" else ZG for nm in names], np.int32)
+    kP = kT.copy()
+    T_in = 1.0 / (1.4 * gas["R"])
+    bvU = np.tile([3.0, 0.0, 0.0], (nB, 1))
+    U0 = np.tile([3.0, 0.0, 0.0], (mesh.n_cells, 1))
+    dt = co * (1.0 / n) / 4.0
+    return Case(mesh, U0, np.full(mesh.n_cells, T_in), np.ones(mesh.n_cells), kU, kT, kP, bvU, np.full(nB, T_in), np.ones(nB),
+                gas=gas, dt=dt, **opts)

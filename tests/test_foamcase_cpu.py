@@ -163,3 +163,32 @@ def test_tutorial_idioms_one_line_lists_and_internalfield_macro(tmp_path):
     (tmp_path / "0" / "T").write_text((tmp_path / "0" / "T").read_text().replace("uniform 300", "nonuniform List<scalar> 2(300 301)"))
     with pytest.raises(fc.FoamFormatError):
         fc.read_field(str(tmp_path / "0" / "T"), r)
+
+
+def test_subset_mesh_and_forward_step_geometry():
+    """polymesh.subset_mesh (subsetMesh): kept cells ascending, exposed faces in a new last patch with outward normals, closed
+    cells, upper-triangular internal faces; forward_step = 3 x 1 channel minus the 2.4 x 0.2 step."""
+    m = cases.pm.forward_step(20)
+    nI = m.n_internal
+    assert m.n_cells == 60 * 20 - 48 * 4 and [p.name for p in m.patches] == ["xMin", "xMax", "yMin", "yMax", "zMin", "zMax", "step"]
+    assert m.patches[-1].size == 48 + 4 and m.patches[1].size == 16 and m.patches[2].size == 12
+    assert abs(m.V.sum() - (3.0 - 2.4 * 0.2) * 0.05) < 1e-14
+    s = np.zeros((m.n_cells, 3))
+    for k in range(3):
+        s[:, k] = np.bincount(m.owner, weights=m.Sf[:, k], minlength=m.n_cells) - np.bincount(m.neighbour, weights=m.Sf[:nI, k], minlength=m.n_cells)
+    assert np.abs(s).max() < 1e-15
+    assert (m.owner[:nI] < m.neighbour).all() and (np.diff(m.owner[:nI].astype(np.int64) * m.n_cells + m.neighbour) > 0).all()
+    assert ((m.Sf[nI:] * (m.Cf[nI:] - m.C[m.owner[nI:]])).sum(1) > 0).all()
+    step = m.patches[-1]
+    cf = m.Cf[step.start:step.start + step.size]
+    assert (np.isclose(cf[:, 1], 0.2) | np.isclose(cf[:, 0], 0.6)).all()
+    # generic use on a 3D perturbed mesh: remove a random third of the cells, mesh stays closed
+    h = cases.pm.hex_box(6, 5, 4, perturb=0.2, seed=1)
+    keep = np.random.default_rng(0).random(h.n_cells) > 0.33
+    sub = cases.pm.subset_mesh(h, keep)
+    assert sub.n_cells == int(keep.sum()) and np.allclose(np.sort(sub.V), np.sort(h.V[keep]), rtol=1e-13)
+    nIs = sub.n_internal
+    s = np.zeros((sub.n_cells, 3))
+    for k in range(3):
+        s[:, k] = np.bincount(sub.owner, weights=sub.Sf[:, k], minlength=sub.n_cells) - np.bincount(sub.neighbour, weights=sub.Sf[:nIs, k], minlength=sub.n_cells)
+    assert np.abs(s).max() < 1e-14

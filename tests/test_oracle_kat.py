@@ -1204,3 +1204,32 @@ def test_slip_walls_in_the_oracle(oracle_mod):
     UP = od.get("U")[d.mesh.owner[nI:]]
     assert np.abs(UB - (UP - nrm * (UP * nrm).sum(1)[:, None]))[slip].max() < 1e-15
     assert np.abs(UB - UP)[~slip].max() == 0.0                                    # zeroGradient elsewhere
+
+
+def test_mach3_forward_step_develops_a_bow_shock(oracle_mod):
+    """BASELINE configs[1] geometry (polymesh.forward_step) with the Woodward-Colella inflow: after t = 0.5 the flow upstream of
+    the bow shock is still the free stream, the pressure in front of the step has risen to the post-shock / stagnation level
+    (normal-shock p2/p1 = 10.33 at Mach 3, stagnation 12.06), everything stays positive and total mass changes only by the in- and
+    outflow through xMin / xMax (slip walls and the step are impermeable for the convective flux)."""
+    c = cases.case_forward_step(n=30)
+    m = c.mesh
+    assert m.n_cells == 90 * 30 - 72 * 6 and [p.name for p in m.patches][-1] == "step"
+    o = c.make_oracle(oracle_mod)
+    nsteps = int(round(0.5 / c.dt))
+    c.oracle_step(o, nsteps)
+    rho, p, U = o.get("rho"), o.get("p"), o.get("U")
+    assert np.isfinite(rho).all() and rho.min() > 0.5 and p.min() > 0.3
+    up = m.C[:, 0] < 0.1
+    assert np.abs(p[up] - 1.0).max() < 0.02 and np.abs(U[up, 0] - 3.0).max() < 0.01          # free stream (the regularisation reaches a little upstream)
+    low = m.C[:, 1] < 0.2
+    assert p[low & (m.C[:, 0] < 0.3)].max() < 1.3                                            # the bow shock stands at x ~ 0.37 in front of the step
+    front = low & (m.C[:, 0] > 0.45) & (m.C[:, 0] < 0.6)
+    assert p[front].min() > 9.0 and 11.0 < p[front].max() < 13.0                             # normal shock 10.33, stagnation 12.06
+    mid = np.abs(m.C[:, 1] - 0.5) < 0.02
+    assert 4.5 < p[mid].max() < 6.5                                                          # the oblique part of the shock further up
+    nI = m.n_internal
+    names = [q.name for q in m.patches]
+    pid = m.patch_id_per_bface()
+    walls = np.isin(pid, [names.index(k) for k in ("yMin", "yMax", "step")])
+    UB = o.get("U", with_bnd=True)[1]
+    assert np.abs((UB * m.Sf[nI:]).sum(1)[walls]).max() < 1e-14
