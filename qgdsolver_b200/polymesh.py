@@ -554,3 +554,91 @@ def forward_step(n: int = 40, thick: float = 0.05) -> PolyMesh:
     s = subset_mesh(m, ~inside, "step")
     s.geometric_d = np.array([1, 1, -1], np.int32)
     return s
+
+
+def truncated_octahedron_box(nx: int, ny: int, nz: int, h: float = 1.0) -> PolyMesh:
+    """Space-filling polyhedral mesh (bitruncated cubic honeycomb): truncated octahedra centred on a BCC lattice with cubic
+    constant h - nx*ny*nz cells on the corner sub-lattice plus (nx-1)(ny-1)(nz-1) on the body-centre sub-lattice.  Every cell
+    has 14 faces (8 hexagons shared with the other sub-lattice, 6 squares with its own): about 7 internal faces per cell, most
+    of them polygons with more than 4 vertices - the "other faces" path of GaussVolPoint (GaussVolPointBase3D.C:760-768), i.e. the
+    shape of BASELINE configs[4].  Fully vectorised (no Python loop over cells); cells are numbered plane by plane so that
+    neighbours are close in index; the ragged outer surface is split into the six patches xMin..zMax by position."""
+    ia, ja, ka = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ib, jb, kb = np.meshgrid(np.arange(nx - 1), np.arange(ny - 1), np.arange(nz - 1), indexing="ij")
+    cen = np.concatenate([np.stack([4 * ia, 4 * ja, 4 * ka], -1).reshape(-1, 3),
+                          np.stack([4 * ib + 2, 4 * jb + 2, 4 * kb + 2], -1).reshape(-1, 3)]).astype(np.int64)
+    order = np.lexsort((cen[:, 0], cen[:, 1], cen[:, 2]))           # z-major planes, A and B layers interleaved
+    cen = cen[order]
+    nC = cen.shape[0]
+    big = 8 * (max(nx, ny, nz) + 2)
+    key = lambda p: ((p[..., 2] + 4) * big + (p[..., 1] + 4)) * big + (p[..., 0] + 4)
+    ckeys = key(cen)
+    csort = np.argsort(ckeys)
+
+    def cell_at(p):                                                 # cell index of centre p, -1 if absent
+        k = key(p)
+        pos = np.searchsorted(ckeys[csort], k)
+        pos = np.minimum(pos, nC - 1)
+        hit = ckeys[csort][pos] == k
+        return np.where(hit, csort[pos], -1)
+
+    # the 14 face templates: direction to the neighbour centre and the vertex offsets, counter-clockwise seen from outside
+    tmpl = []
+    for ax in range(3):
+        for sg in (1, -1):
+            a1, a2 = (ax + 1) % 3, (ax + 2) % 3
+            ring = [(1, 0), (0, 1), (-1, 0), (0, -1)]
+            if sg < 0:
+                ring = ring[::-1]
+            v = np.zeros((4, 3), np.int64)
+            for q, (u, w) in enumerate(ring):
+                v[q, ax], v[q, a1], v[q, a2] = 2 * sg, u, w
+            d = np.zeros(3, np.int64); d[ax] = 4 * sg
+            tmpl.append((d, v))
+    base = np.array([(2, 1, 0), (1, 2, 0), (0, 2, 1), (0, 1, 2), (1, 0, 2), (2, 0, 1)], np.int64)
+    for sx in (1, -1):
+        for sy in (1, -1):
+            for sz in (1, -1):
+                s = np.array([sx, sy, sz], np.int64)
+                v = base * s
+                if sx * sy * sz < 0:
+                    v = v[::-1]
+                tmpl.append((2 * s, v))
+    f_verts, f_nv, f_own, f_nei, f_cf = [], [], [], [], []
+    me = np.arange(nC)
+    for d, v in tmpl:
+        nb = cell_at(cen + d)
+        mk = (nb > me) | (nb < 0)                                   # one face per pair (owner = lower index) + boundary faces
+        own = me[mk]
+        f_own.append(own); f_nei.append(nb[mk])
+        f_verts.append((cen[own][:, None, :] + v[None]).reshape(-1, 3))
+        f_nv.append(np.full(own.size, v.shape[0], np.int64))
+        f_cf.append(cen[own] * 2 + d)                               # twice the face centre (integer)
+    own = np.concatenate(f_own); nei = np.concatenate(f_nei); nv = np.concatenate(f_nv)
+    vcoord = np.concatenate(f_verts); cf2 = np.concatenate(f_cf)
+    starts = np.zeros(own.size + 1, np.int64); np.cumsum(nv, out=starts[1:])
+    vk, vinv = np.unique(key(vcoord), return_inverse=True)
+    first = np.zeros(vk.size, np.int64); first[vinv[::-1]] = np.arange(vcoord.shape[0])[::-1]
+    pts = vcoord[first].astype(np.float64) * (h / 4.0)
+    # face order: internal faces upper-triangular, then the six patches (by position of the face centre), owner-sorted
+    internal = nei >= 0
+    lo = np.array([0, 0, 0]) * 2 - 0; hi = np.array([4 * (nx - 1), 4 * (ny - 1), 4 * (nz - 1)]) * 2
+    dist = np.stack([lo[0] - cf2[:, 0], cf2[:, 0] - hi[0], lo[1] - cf2[:, 1], cf2[:, 1] - hi[1], lo[2] - cf2[:, 2], cf2[:, 2] - hi[2]], 1)
+    patch_of = np.argmax(dist, 1)
+    grp = np.where(internal, -1, patch_of)
+    sort_key = np.lexsort((np.where(internal, nei, 0), own, grp))
+    own, nei, nv, grp = own[sort_key], nei[sort_key], nv[sort_key], grp[sort_key]
+    src_start = starts[:-1][sort_key]
+    idx = np.repeat(src_start, nv) + _ragged(nv)
+    face_verts = vinv[idx].astype(np.int32)
+    offs = np.zeros(own.size + 1, np.int32); np.cumsum(nv, out=offs[1:])
+    nI = int(internal.sum())
+    names = ["xMin", "xMax", "yMin", "yMax", "zMin", "zMax"]
+    patches, start = [], nI
+    for pi, nm in enumerate(names):
+        cnt = int((grp == pi).sum())
+        patches.append(Patch(nm, PATCH_GENERIC, start, cnt))
+        start += cnt
+    mesh = PolyMesh(points=np.ascontiguousarray(pts), face_offsets=offs, face_verts=face_verts, owner=own.astype(np.int32),
+                    neighbour=nei[:nI].astype(np.int32), patches=patches, n_cells=nC)
+    return mesh.compute_geometry()

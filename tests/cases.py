@@ -291,3 +291,10 @@ def case_forward_step(n=40, co=0.05, **opts):
     dt = co * (1.0 / n) / 4.0
     return Case(mesh, U0, np.full(mesh.n_cells, T_in), np.ones(mesh.n_cells), kU, kT, kP, bvU, np.full(nB, T_in), np.ones(nB),
                 gas=gas, dt=dt, **opts)
+
+
+def case_truncoct(n=(5, 4, 4), bcs="zg", **opts):
+    """QGDFoam on the truncated-octahedron polyhedral mesh (14 faces per cell: hexagon faces take the nf*snGrad branch of
+    GaussVolPoint, square faces the six-point formula; cell->face rows longer than the ELL width exercise the CSR tails)"""
+    mesh = pm.truncated_octahedron_box(*n, h=1.0 / max(n))
+    return _with_bcs(mesh, bcs, GAS, 1e-4, **opts)

@@ -192,3 +192,31 @@ def test_subset_mesh_and_forward_step_geometry():
     for k in range(3):
         s[:, k] = np.bincount(sub.owner, weights=sub.Sf[:, k], minlength=sub.n_cells) - np.bincount(sub.neighbour, weights=sub.Sf[:nIs, k], minlength=sub.n_cells)
     assert np.abs(s).max() < 1e-14
+
+
+def test_truncated_octahedron_polyhedral_mesh():
+    """polymesh.truncated_octahedron_box: BCC lattice of truncated octahedra, 14 faces per cell (8 hexagons + 6 squares),
+    closed cells of volume h^3/2, upper-triangular internal faces, outward boundary normals, every point shared by 4 cells inside."""
+    h = 0.25
+    m = cases.pm.truncated_octahedron_box(5, 4, 3, h=h)
+    nI = m.n_internal
+    assert m.n_cells == 5 * 4 * 3 + 4 * 3 * 2
+    per_cell = np.bincount(m.owner, minlength=m.n_cells) + np.bincount(m.neighbour, minlength=m.n_cells)
+    assert (per_cell == 14).all() and set(np.unique(m.face_nverts())) == {4, 6}
+    assert np.abs(m.V - h ** 3 / 2).max() < 1e-15
+    s = np.zeros((m.n_cells, 3))
+    for k in range(3):
+        s[:, k] = np.bincount(m.owner, weights=m.Sf[:, k], minlength=m.n_cells) - np.bincount(m.neighbour, weights=m.Sf[:nI, k], minlength=m.n_cells)
+    assert np.abs(s).max() < 1e-15
+    assert (m.owner[:nI] < m.neighbour).all() and (np.diff(m.owner[:nI].astype(np.int64) * m.n_cells + m.neighbour) > 0).all()
+    assert ((m.Sf[nI:] * (m.Cf[nI:] - m.C[m.owner[nI:]])).sum(1) > 0).all()
+    assert ((m.Sf[:nI] * (m.C[m.neighbour] - m.C[m.owner[:nI]])).sum(1) > 0).all()
+    assert sum(p.size for p in m.patches) == m.n_bnd and all(p.size > 0 for p in m.patches)
+    big = cases.pm.truncated_octahedron_box(12, 12, 12)
+    assert 6.0 < big.n_internal / big.n_cells < 7.0                                  # ~7 internal faces per cell at scale
+    # round trip through the OpenFOAM files
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        fc.write_polymesh(m, tmp)
+        r = fc.read_polymesh(tmp)
+        assert np.array_equal(r.face_verts, m.face_verts) and np.array_equal(r.points, m.points) and np.array_equal(r.V, m.V)

@@ -86,3 +86,28 @@ def test_least_squares_degenerate_face_set_on_device(qgd, oracle_mod):
     for f in ("rho", "rhoU", "rhoE"):
         a, b = s.get(f), oc.get(f)
         assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < TOL_STEP, f
+
+
+@NOT_RUN
+@pytest.mark.parametrize("bcs", ["mixed", "fixed"])
+def test_truncated_octahedron_mesh_on_device(qgd, oracle_mod, bcs):
+    """14 faces per cell (8 hexagons -> `other` faces, 6 squares): fvsc operators and 60 QGDFoam steps against the oracle; the
+    cell->face rows exceed the ELL width 8, so the CSR tails are on the default path here."""
+    c = cases.case_truncoct(bcs=bcs)
+    m = c.mesh
+    nI = m.n_internal
+    o = oracle_mod.Oracle(m)
+    dm = qgd.Mesh(m)
+    st = qgd.FvscStencil(dm, "GaussVolPoint")
+    rng = np.random.default_rng(3)
+    cell, bnd = rng.random((m.n_cells, 3)), rng.random((m.n_bnd, 3))
+    bsg = m.deltaCoeffs[nI:, None] * (bnd - cell[m.owner[nI:]])
+    ref = o.fvsc_grad(cell, bnd, bsg)
+    assert float(np.abs(st.Grad(cell, bnd, bsg) - ref).max()) / float(np.abs(ref).max()) < 1e-12
+    oc = c.make_oracle(oracle_mod)
+    s = c.make_solver(qgd, dm)
+    c.oracle_step(oc, 60)
+    s.step(60)
+    for f in ("rho", "rhoU", "rhoE", "p"):
+        a, b = s.get(f), oc.get(f)
+        assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < TOL_STEP, f
