@@ -311,6 +311,44 @@ def run_qgd2d(args):
     print(json.dumps(line), flush=True)
 
 
+def run_poly(args):
+    """Extra line (not the driver's default): BASELINE configs[4]-like single-GPU share, QGDFoam on the truncated-octahedron
+    polyhedral mesh (14 faces per cell: hexagons take the `other faces` branch, squares the six-point GaussVolPoint formula).
+    Algorithmic bytes per step: 104 nC + 224 nF_quad + 136 nF_other + 196 nP."""
+    import torch
+    import cases
+    from qgdsolver_b200 import api
+    torch.cuda.set_device(0)
+    api.init(0)
+    n = args.poly_n
+    c = cases.case_truncoct(n=(n, n, n))
+    mesh = c.mesh
+    s = c.make_solver(api)
+    s.step(args.warmup)
+    api.synchronize()
+    reps = []
+    for _ in range(3):
+        api.timer_begin()
+        s.step(args.steps)
+        reps.append(api.timer_end() / args.steps)
+    ms = min(reps)
+    nC, nI = mesh.n_cells, mesh.n_internal
+    nv = mesh.face_nverts()[:nI]
+    nq, no = int((nv <= 4).sum()), int((nv > 4).sum())
+    alg = 104 * nC + 224 * nq + 136 * no + 196 * mesh.n_points
+    peak, src = peaks()
+    line = {"metric": METRIC, "value": nC / ms / 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"QGDFoam 3D polyhedral mesh, truncated octahedra on a {n}^3 BCC lattice ({nC} cells, "
+                                   f"{nI / nC:.2f} internal faces per cell, {no} polygon + {nq} quad faces), explicit, FP64",
+                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False,
+                       "l2": "state and mesh records exceed the 126 MB L2 for n >= 60; no flush"},
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes_per_step": alg, "peak_source": src},
+            "gpu_launches": int(s.launch_count())}
+    print(json.dumps(line), flush=True)
+
+
 def run_qhd(args):
     """Extra line (not the driver's default): BASELINE configs[2], QHDFoam 2D differentially heated cavity, n x n cells,
     pressure PCG on the device.  A step = one QHDFoam.C:83-139 pass including the whole PCG solve."""
@@ -355,8 +393,10 @@ def main():
     ap.add_argument("--ref-size", type=int, default=64, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--case", default="qgd3d", choices=["qgd3d", "qgd2d", "qhd2d"],
-                    help="qgd3d = BASELINE configs[3] (default); qgd2d = a configs[1]-sized 2D mesh; qhd2d = configs[2]")
+    ap.add_argument("--poly-n", type=int, default=100, help="--case poly: BCC lattice edge (cells ~ 2 n^3)")
+    ap.add_argument("--case", default="qgd3d", choices=["qgd3d", "qgd2d", "qhd2d", "poly"],
+                    help="qgd3d = BASELINE configs[3] (default); qgd2d = a configs[1]-sized 2D mesh; qhd2d = configs[2]; "
+                         "poly = a configs[4]-shaped polyhedral mesh (one GPU's share)")
     ap.add_argument("--precond", default="diagonal")
     ap.add_argument("--p-tol", type=float, default=1e-8)
     ap.add_argument("--p-rel-tol", type=float, default=0.0)
@@ -369,6 +409,8 @@ def main():
         run_qhd(args)
     elif args.case == "qgd2d":
         run_qgd2d(args)
+    elif args.case == "poly":
+        run_poly(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

@@ -9,3 +9,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 90 --csv --log-file
 ncu --set full --clock-control none --import-source on -k regex:'k_face_flux|k_cell_update|k_points' -s 9 -c 3 -o gpurun_out/prof_r2a python scripts/gpu_tune.py 256 2 0,0,-1,0 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 python __graft_entry__.py --smoke 2>&1 | tail -3
+# extra lines: polyhedral mesh (configs[4] shape, ~2M cells) and the 2D / QHD cases
+python bench.py --case poly --poly-n 100 --steps 50 --warmup 5 2>/dev/null | tee gpurun_out/bench_poly.json | cut -c1-300

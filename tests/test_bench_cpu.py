@@ -90,6 +90,13 @@ def test_product_arm_assembles_its_json_line_with_a_stand_in_device(monkeypatch,
     assert abs(r["step"]["frac"] - r["step"]["achieved"] / r["peak"]) < 1e-12
     assert j["e2e"]["h2d_bytes_per_step"] == 12 * 8 * 512 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] > 0
     assert "workload" in j["config"] and j["vs_baseline"] is None
+    # the extra polyhedral line (configs[4] shape) through the same stand-in device
+    args.poly_n = 5
+    bench.run_poly(args)
+    jp = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][0])
+    nC = 5 ** 3 + 4 ** 3
+    assert jp["config"]["workload"].startswith("QGDFoam 3D polyhedral mesh") and f"({nC} cells" in jp["config"]["workload"]
+    assert jp["roofline"]["alg_bytes_per_step"] > 104 * nC and jp["value"] > 0 and jp["unit"] == "MCUPS"
     # the traffic figure is only quoted for the kernel variant that was actually captured with ncu
     import tempfile
     with tempfile.TemporaryDirectory() as tmp:
