@@ -84,8 +84,8 @@ def _point_cells(mesh: PolyMesh):
     `unique` they would cost at 256^3 is not paid."""
     nv = mesh.face_nverts()
     nI = mesh.n_internal
-    p = np.concatenate([mesh.face_verts, mesh.face_verts[:mesh.face_offsets[nI]]]).astype(np.int64)
-    c = np.concatenate([np.repeat(mesh.owner, nv), np.repeat(mesh.neighbour, nv[:nI])]).astype(np.int64)
+    p = np.concatenate([mesh.face_verts, mesh.face_verts[:mesh.face_offsets[nI]]])            # int32: 1.6 GB each at 256^3
+    c = np.concatenate([np.repeat(mesh.owner, nv), np.repeat(mesh.neighbour, nv[:nI])])
     return p, c
 
 
