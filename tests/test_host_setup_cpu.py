@@ -1,0 +1,171 @@
+"""The product's host-side set-up code (qgdsolver_b200/csrc/qgd_host_setup.cpp) checked on CPU against the oracle: the file is
+compiled with g++ into a test-only shared library (tests/host_setup/host_setup_shim.cpp adds a C interface); the compact face
+gradient record `G`, the point weights, the QGD length scales and the least-squares stencils it produces are applied to random
+fields in numpy and compared with the oracle's operators.  No GPU, no device call."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from qgdsolver_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+FF_POINTS, FF_TRI_QUIRK, FF_NORMAL_ONLY = 1, 2, 4
+
+
+@pytest.fixture(scope="module")
+def shim():
+    out = os.path.join(ROOT, "tests", "host_setup", "libhost_setup_shim.so")
+    srcs = [os.path.join(ROOT, "tests", "host_setup", "host_setup_shim.cpp"), os.path.join(ROOT, "qgdsolver_b200", "csrc", "qgd_host_setup.cpp")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "qgdsolver_b200", "csrc"),
+                               "-I", "/usr/local/cuda/include", "-o", out] + srcs + ["-L/usr/local/cuda/lib64", "-lcudart"])
+    L = C.CDLL(out)
+    L.hs_create.restype = C.c_void_p
+    L.hs_create.argtypes = [C.POINTER(api._MeshDesc)]
+    L.hs_destroy.argtypes = [C.c_void_p]
+    L.hs_lengths.argtypes = [C.c_void_p, _dp, _dp]
+    L.hs_face_records.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp]
+    L.hs_point_interpolate.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.hs_lsq_width.argtypes = [C.c_void_p, C.c_int]
+    L.hs_lsq.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_char_p]
+    L.hs_cell_faces.argtypes = [C.c_void_p, _ip, _ip]
+    return L
+
+
+class Host:
+    def __init__(self, L, mesh):
+        self.L, self.mesh = L, mesh
+        d = api._MeshDesc()
+        d.n_cells, d.n_faces, d.n_internal_faces, d.n_points, d.n_patches = mesh.n_cells, mesh.n_faces, mesh.n_internal, mesh.n_points, len(mesh.patches)
+        f64 = lambda a: np.ascontiguousarray(a, np.float64)
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        self.keep = dict(points=f64(mesh.points), C=f64(mesh.C), V=f64(mesh.V), Cf=f64(mesh.Cf), Sf=f64(mesh.Sf), magSf=f64(mesh.magSf),
+                         weights=f64(mesh.weights), deltaCoeffs=f64(mesh.deltaCoeffs), nonOrthDeltaCoeffs=f64(mesh.nonOrthDeltaCoeffs),
+                         neighb_cell_centres=f64(np.nan_to_num(mesh.neighb_cell_centres)))
+        self.keepi = dict(face_offsets=i32(mesh.face_offsets), face_verts=i32(mesh.face_verts), owner=i32(mesh.owner), neighbour=i32(mesh.neighbour),
+                          patch_start=i32([p.start for p in mesh.patches]), patch_size=i32([p.size for p in mesh.patches]),
+                          patch_kind=i32([p.kind for p in mesh.patches]))
+        for n, a in self.keep.items():
+            setattr(d, n, a.ctypes.data_as(_dp))
+        for n, a in self.keepi.items():
+            setattr(d, n, a.ctypes.data_as(_ip))
+        for j in range(3):
+            d.geometric_d[j] = int(mesh.geometric_d[j])
+        self.h = L.hs_create(C.byref(d))
+        assert self.h, "HostMesh::build failed"
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.hs_destroy(self.h)
+
+    def records(self, reduced=False):
+        m = self.mesh
+        vtx, flags = np.zeros((m.n_faces, 4), np.int32), np.zeros(m.n_faces, np.int32)
+        G, hd = np.zeros((9, m.n_faces)), np.zeros(max(m.n_bnd, 1))
+        self.L.hs_face_records(self.h, int(reduced), vtx.ctypes.data_as(_ip), flags.ctypes.data_as(_ip), G.ctypes.data_as(_dp), hd.ctypes.data_as(_dp))
+        return vtx, flags, G, hd[:m.n_bnd]
+
+    def points(self, cell, bnd):
+        out = np.zeros(self.mesh.n_points)
+        self.L.hs_point_interpolate(self.h, np.ascontiguousarray(cell).ctypes.data_as(_dp), np.ascontiguousarray(bnd).ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+        return out
+
+
+MESHES = {
+    "hex_perturbed": lambda: cases.pm.hex_box(6, 5, 4, perturb=0.25, grading=(2, 1, 0.5), seed=11),
+    "prism": lambda: cases.pm.prism_box(4, 4, 3, perturb=0.15, seed=2),
+    "poly": lambda: cases.pm.hexprism_poly(5, 4, 3, a=0.1, lz=0.4),
+    "truncoct": lambda: cases.pm.truncated_octahedron_box(4, 3, 3, h=0.3),
+    "2d_z": lambda: cases.case_2d((9, 8), perturb=0.2).mesh,
+    "2d_x": lambda: cases.case_2d((9, 8), perturb=0.2, axis=0).mesh,
+    "1d": lambda: cases.case_sod(30).mesh,
+    "forward_step": lambda: cases.pm.forward_step(10),
+}
+
+
+def _apply_records(host, cell, bnd, bsg, reduced=False):
+    """grad(phi)_f = G1 (phi_v1 - phi_v3) + G2 (phi_v2 - phi_v4) + GP (phi_P - phi_N) with the boundary ghost
+    phi_N := phi_b + snGrad_b * halfDist (FF_NORMAL_ONLY faces: GP * snGrad_b): what k_fvsc_grad does with the records"""
+    m = host.mesh
+    nI = m.n_internal
+    vtx, flags, G, hd = host.records(reduced)
+    P = host.points(cell, bnd) if not reduced else np.zeros(m.n_points)
+    d1 = np.where(flags & FF_POINTS, P[vtx[:, 0]] - P[vtx[:, 2]], 0.0)
+    d2 = np.where(flags & FF_POINTS, P[vtx[:, 1]] - P[vtx[:, 3]], 0.0)
+    dP = np.zeros(m.n_faces)
+    dP[:nI] = cell[m.owner[:nI]] - cell[m.neighbour]
+    normal_only = (flags[nI:] & FF_NORMAL_ONLY) != 0
+    dP[nI:] = np.where(normal_only, bsg, cell[m.owner[nI:]] - (bnd + bsg * hd))
+    d1[nI:] = np.where(normal_only, 0.0, d1[nI:])
+    d2[nI:] = np.where(normal_only, 0.0, d2[nI:])
+    return (G[0:3] * d1 + G[3:6] * d2 + G[6:9] * dP).T
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("reduced", [False, True])
+def test_face_gradient_records_reproduce_the_oracle_operator(shim, oracle_mod, name, reduced):
+    mesh = MESHES[name]()
+    nI = mesh.n_internal
+    rng = np.random.default_rng(5)
+    cell = np.sin(3 * mesh.C[:, 0]) + 0.3 * rng.random(mesh.n_cells)
+    bnd = np.cos(2 * mesh.Cf[nI:, 1]) + 0.3 * rng.random(mesh.n_bnd)
+    bsg = mesh.deltaCoeffs[nI:] * (bnd - cell[mesh.owner[nI:]])
+    bsg[1::2] = rng.random(mesh.n_bnd)[1::2]
+    host = Host(shim, mesh)
+    got = _apply_records(host, cell, bnd, bsg, reduced)
+    ref = oracle_mod.Oracle(mesh).fvsc_grad(cell, bnd, bsg, scheme=oracle_mod.FVSC_SCHEMES["reduced" if reduced else "GaussVolPoint"])
+    keep = np.ones(mesh.n_faces, bool)
+    keep[nI:] = mesh.patch_kind_per_bface() != 1
+    assert np.abs(got[keep] - ref[keep]).max() < 1e-11 * np.abs(ref[keep]).max()
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_point_weights_and_length_scales_match_the_oracle(shim, oracle_mod, name):
+    mesh = MESHES[name]()
+    host = Host(shim, mesh)
+    o = oracle_mod.Oracle(mesh)
+    rng = np.random.default_rng(6)
+    cell, bnd = rng.random(mesh.n_cells), rng.random(mesh.n_bnd) + 3.0
+    assert np.abs(host.points(cell, bnd) - o.vol_point_interpolate(cell, bnd)).max() < 1e-13
+    hf, hc = np.zeros(mesh.n_faces), np.zeros(mesh.n_cells)
+    shim.hs_lengths(host.h, hf.ctypes.data_as(_dp), hc.ctypes.data_as(_dp))
+    keep = np.ones(mesh.n_faces, bool)
+    keep[mesh.n_internal:] = mesh.patch_kind_per_bface() != 1
+    assert np.abs(hf[keep] - o.hQGDf()[keep]).max() < 1e-14 and np.abs(hc - o.hQGD()).max() < 1e-14
+    # cell -> face rows: ascending polyMesh face order, side bit = the cell is the face's neighbour
+    n = shim.hs_cell_faces(host.h, None, None)
+    off, enc = np.zeros(mesh.n_cells + 1, np.int32), np.zeros(n, np.int32)
+    shim.hs_cell_faces(host.h, off.ctypes.data_as(_ip), enc.ctypes.data_as(_ip))
+    ro, rf = mesh.cell_faces_csr()
+    assert np.array_equal(off, ro) and np.array_equal(enc >> 1, rf)
+    cells_of_rows = np.repeat(np.arange(mesh.n_cells), np.diff(off))
+    assert np.array_equal((enc & 1) == 1, mesh.owner[enc >> 1] != cells_of_rows)
+
+
+@pytest.mark.parametrize("name", ["2d_z", "2d_x", "1d"])
+@pytest.mark.parametrize("opt", [False, True])
+def test_least_squares_stencils_reproduce_the_oracle_operator(shim, oracle_mod, name, opt):
+    mesh = MESHES[name]() if name != "2d_z" else cases.case_2d((6, 40)).mesh        # aspect ratio ~7: degenerate stencils
+    nI = mesh.n_internal
+    host = Host(shim, mesh)
+    W = shim.hs_lsq_width(host.h, int(opt))
+    cells, coef, deg = np.zeros((W, nI), np.int32), np.zeros((W, 3, nI)), np.zeros(nI, np.int8)
+    shim.hs_lsq(host.h, int(opt), cells.ctypes.data_as(_ip), coef.ctypes.data_as(_dp), deg.ctypes.data_as(C.c_char_p))
+    rng = np.random.default_rng(7)
+    cell, bnd = rng.random(mesh.n_cells), rng.random(mesh.n_bnd)
+    bsg = mesh.deltaCoeffs[nI:] * (bnd - cell[mesh.owner[nI:]])
+    o = oracle_mod.Oracle(mesh)
+    sF = o.linear_interpolate(cell, bnd)[:nI]
+    lsq = np.einsum("wif,wf->fi", coef, cell[cells] - sF[None])
+    nf = mesh.Sf[:nI] / mesh.magSf[:nI, None]
+    fallback = (mesh.nonOrthDeltaCoeffs[:nI] * (cell[mesh.neighbour] - cell[mesh.owner[:nI]]))[:, None] * nf
+    got = np.where((deg != 0)[:, None], fallback, lsq)
+    ref = o.fvsc_grad(cell, bnd, bsg, scheme=oracle_mod.FVSC_SCHEMES["leastSquaresOpt" if opt else "leastSquares"])[:nI]
+    assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+    if name == "2d_z" and not opt:
+        assert deg.any()
