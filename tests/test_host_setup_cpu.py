@@ -169,3 +169,22 @@ def test_least_squares_stencils_reproduce_the_oracle_operator(shim, oracle_mod, 
     assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
     if name == "2d_z" and not opt:
         assert deg.any()
+
+
+def test_face_flags_mark_the_reference_quirks(shim):
+    """FF_TRI_QUIRK exactly on the internal triangular faces of a 3D mesh (GaussVolPointBase3D.C:844-854), FF_POINTS on tri / quad
+    faces only (polygons take nf*snGrad), FF_NORMAL_ONLY on boundary polygons and on every boundary face of `reduced`."""
+    m = cases.pm.prism_box(4, 3, 3, perturb=0.1)
+    nI = m.n_internal
+    _, flags, _, _ = Host(shim, m).records()
+    nv = m.face_nverts()
+    assert np.array_equal((flags[:nI] & FF_TRI_QUIRK) != 0, nv[:nI] == 3) and not (flags[nI:] & FF_TRI_QUIRK).any()
+    assert ((flags & FF_POINTS) != 0).all()
+    t = cases.pm.truncated_octahedron_box(3, 3, 3)
+    _, flags, G, _ = Host(shim, t).records()
+    nv = t.face_nverts()
+    assert np.array_equal((flags & FF_POINTS) != 0, nv == 4)
+    assert np.array_equal((flags[t.n_internal:] & FF_NORMAL_ONLY) != 0, nv[t.n_internal:] > 4)
+    assert np.abs(G[0:6][:, nv > 4]).max() == 0.0                     # G1 = G2 = 0 on polygons
+    _, flags, _, _ = Host(shim, t).records(reduced=True)
+    assert ((flags[t.n_internal:] & FF_NORMAL_ONLY) != 0).all() and not (flags & FF_POINTS).any()
