@@ -288,6 +288,14 @@ int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const
                   double tolerance, double rel_tol, int max_iter, int precond,
                   int* iters, double* initial_residual, double* final_residual);
 
+/* The same solver cut into one kernel per phase (initial residual, preconditioning + wA.rA, search-direction update, SpMV +
+ * wA.pA, solution / residual update), all scalars and the convergence flag on the device: the form a decomposed run needs, with
+ * a halo exchange of the search direction and all-reduces of the dot products between the phases.  This entry point runs it on
+ * one GPU (no communication); precond 0 | 1.  Experimental: compiled, not yet run on a device at the end of round 1. */
+int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x,
+                           double tolerance, double rel_tol, int max_iter, int precond,
+                           int* iters, double* initial_residual, double* final_residual);
+
 #ifdef __cplusplus
 }
 #endif

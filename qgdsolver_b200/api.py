@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
-    "qgd_pcg_solve",
+    "qgd_pcg_solve", "qgd_pcg_solve_stepwise",
     "qgd_qhdfoam_create", "qgd_qhdfoam_destroy", "qgd_qhdfoam_set_bcs", "qgd_qhdfoam_init_fields", "qgd_qhdfoam_step",
     "qgd_qhdfoam_get", "qgd_qhdfoam_get_flux", "qgd_qhdfoam_get_scalars", "qgd_qhdfoam_solver_info",
     "qgd_qhdfoam_launch_count",
@@ -130,6 +130,8 @@ def load_library():
     L.qgd_comm_unique_id.argtypes = [C.c_void_p]
     L.qgd_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.qgd_qgdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 9
+    L.qgd_pcg_solve_stepwise.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
+                                         _ip, _dp, _dp]
     L.qgd_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
                                 _ip, _dp, _dp]
     L.qgd_qhdfoam_create.argtypes = [C.c_void_p, C.POINTER(QHDFoamDesc), C.POINTER(C.c_void_p)]
@@ -426,12 +428,14 @@ class QGDFoam:
 PRECONDS = {"none": 0, "diagonal": 1, "DIC": 2}
 
 
-def pcg_solve(mesh: Mesh, diag, upper, b, x0, tol=1e-8, rel_tol=0.0, max_iter=1000, precond="DIC"):
-    """lduMatrix PCG on the mesh addressing, fully on the device (qgd_pcg_solve)."""
+def pcg_solve(mesh: Mesh, diag, upper, b, x0, tol=1e-8, rel_tol=0.0, max_iter=1000, precond="DIC", stepwise=False):
+    """lduMatrix PCG on the mesh addressing, fully on the device (qgd_pcg_solve; stepwise: the one-kernel-per-phase form
+    of qgd_pcg_solve_stepwise that decomposed runs build on)."""
     diag, upper, b = _f64(diag), _f64(upper), _f64(b)
     x = np.array(x0, dtype=np.float64, copy=True)
     it, r0, r1 = C.c_int(), C.c_double(), C.c_double()
-    _check(load_library().qgd_pcg_solve(mesh._h, _d(diag), _d(upper), _d(b), _d(x), tol, rel_tol, max_iter,
+    fn = load_library().qgd_pcg_solve_stepwise if stepwise else load_library().qgd_pcg_solve
+    _check(fn(mesh._h, _d(diag), _d(upper), _d(b), _d(x), tol, rel_tol, max_iter,
                                         PRECONDS[precond], C.byref(it), C.byref(r0), C.byref(r1)))
     return x, it.value, r0.value, r1.value
 

@@ -1399,4 +1399,29 @@ int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const
     });
 }
 
+// the stepwise (multi-kernel) form of the same solver on one GPU: validates the kernels a decomposed run will use
+int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x, double tolerance,
+                           double rel_tol, int max_iter, int precond, int* iters, double* initial_residual, double* final_residual)
+{
+    return guarded([&] {
+        requireInit();
+        if (!mesh || !diag || !b || !x || (mesh->h.nInternal > 0 && !upper)) throw Error(QGD_ERR_INVALID, "qgd_pcg_solve_stepwise: null argument");
+        if (precond < 0 || precond > 1) throw Error(QGD_ERR_UNSUPPORTED, "qgd_pcg_solve_stepwise: preconditioner must be 0 (none) or 1 (diagonal)");
+        PcgMatrix A;
+        A.build(mesh->h, diag, upper, precond, g_stream);
+        const size_t n = mesh->h.nCells;
+        QGD_CUDA(cudaMemcpyAsync(A.b.p, b, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        QGD_CUDA(cudaMemcpyAsync(A.x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        StepwisePcg sw;
+        sw.alloc(A, (int)n);
+        PcgResult r;
+        sw.solve(A, A.b.p, A.x.p, tolerance, rel_tol, max_iter, precond, g_stream, nullptr, &r);
+        QGD_CUDA(cudaMemcpyAsync(x, A.x.p, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        if (iters) *iters = r.iters;
+        if (initial_residual) *initial_residual = r.res0;
+        if (final_residual) *final_residual = r.res;
+    });
+}
+
 } // extern "C"

@@ -2,6 +2,8 @@
 // The whole solve — initial residual, normFactor, every iteration and the convergence test — runs inside ONE
 // cooperative persistent kernel; vectors of a ~1M-cell problem stay resident in the 126 MB L2.
 #pragma once
+#include <functional>
+
 #include "qgd_internal.h"
 
 namespace qgd {
@@ -43,6 +45,21 @@ struct PcgMatrix {
     PcgView view(double tol, double relTol, int maxIter) const;
     // solves A x = b for the device vectors b, x (in place); returns kernel launches issued
     int solve(double tol, double relTol, int maxIter, cudaStream_t st);
+};
+
+// ---- stepwise (one kernel per phase) form of the same solver for decomposed runs, see qgd_mpcg.cu
+struct PcgHooks {
+    std::function<void(double* vec, cudaStream_t st)> exchange;                   // fill the halo entries of a cell vector from their owners
+    std::function<void(double* dev, int count, cudaStream_t st)> allreduceSum;    // in-place global sum of device doubles
+};
+struct StepwisePcg {
+    int n = 0, nRows = 0, grid = 1;
+    DevBuf<double> r, w, p, partials, red;
+    DevBuf<int> state;
+    void alloc(const PcgMatrix& A, int rows);     // rows = owned rows [0, rows) of the extended sub-mesh matrix (== A.n on one GPU)
+    // b: rows device doubles ; x: A.n device doubles ; precond 0 none | 1 diagonal ; hooks = nullptr on one GPU ; returns launches
+    int solve(const PcgMatrix& A, const double* b, double* x, double tol, double relTol, int maxIter, int precond, cudaStream_t st,
+              const PcgHooks* hooks, PcgResult* result);
 };
 
 } // namespace qgd

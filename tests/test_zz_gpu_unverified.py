@@ -111,3 +111,32 @@ def test_truncated_octahedron_mesh_on_device(qgd, oracle_mod, bcs):
     for f in ("rho", "rhoU", "rhoE", "p"):
         a, b = s.get(f), oc.get(f)
         assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < TOL_STEP, f
+
+
+@NOT_RUN
+@pytest.mark.parametrize("precond", ["diagonal", "none"])
+def test_stepwise_pcg_matches_oracle_and_the_persistent_kernel(qgd, oracle_mod, precond):
+    """qgd_pcg_solve_stepwise (one kernel per phase, the building block of the multi-GPU solver) on one GPU: same solution and
+    iteration count as the oracle and as the cooperative persistent kernel."""
+    mesh = cases.pm.hex_box(12, 10, 8, perturb=0.1, seed=1)
+    nI = mesh.n_internal
+    upper = -(mesh.magSf[:nI] * mesh.deltaCoeffs[:nI])
+    diag = np.zeros(mesh.n_cells)
+    np.subtract.at(diag, mesh.owner[:nI], upper); np.subtract.at(diag, mesh.neighbour, upper)
+    diag += 1e-3 * mesh.V / mesh.V.mean()
+    b = np.random.default_rng(0).standard_normal(mesh.n_cells)
+    x0 = np.zeros(mesh.n_cells)
+    o = oracle_mod.Oracle(mesh)
+    xr, itr, r0r, r1r = o.pcg_solve(diag, upper, b, x0, tol=1e-12, maxIter=3000, precond=oracle_mod.PRECONDS[precond])
+    dm = qgd.Mesh(mesh)
+    xs, its, r0s, r1s = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-12, max_iter=3000, precond=precond, stepwise=True)
+    xp, itp, _, _ = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-12, max_iter=3000, precond=precond)
+    assert abs(its - itr) <= 1 and abs(its - itp) <= 1
+    assert abs(r0s - r0r) < 1e-12 * r0r and r1s < 1e-12
+    assert float(np.abs(xs - xr).max()) / float(np.abs(xr).max()) < 1e-9
+    assert float(np.abs(xs - xp).max()) / float(np.abs(xp).max()) < 1e-9
+    # a converged start does not iterate; maxIter is honoured
+    _, it0, _, _ = qgd.pcg_solve(dm, diag, upper, b, xr, tol=1e-6, max_iter=3000, precond=precond, stepwise=True)
+    assert it0 == 0
+    _, it5, _, _ = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-30, max_iter=5, precond=precond, stepwise=True)
+    assert it5 == 5
