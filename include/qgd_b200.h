@@ -296,6 +296,17 @@ int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upp
                            double tolerance, double rel_tol, int max_iter, int precond,
                            int* iters, double* initial_residual, double* final_residual);
 
+/* The decomposed run of that solver (after qgd_comm_init; every rank calls it): `mesh` is the rank's extended sub-mesh (created
+ * with n_owned_cells), diag / b / x have n_cells entries (the rows of the owned cells are solved, halo entries of x are refreshed
+ * over NCCL), upper follows the local internal faces.  Exchange lists = the face-neighbour subset of the halo, per neighbour k
+ * (rank nbr_rank[k]): local cell ids send_cells[send_off[k] .. send_off[k+1]) and recv_cells[...], ascending global id on both
+ * sides.  precond 0 | 1.  Experimental: compiled, not yet run on a device at the end of round 1. */
+int qgd_pcg_solve_multi(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x,
+                        double tolerance, double rel_tol, int max_iter, int precond,
+                        int n_neighbours, const int* nbr_rank, const int* send_off, const int* send_cells,
+                        const int* recv_off, const int* recv_cells,
+                        int* iters, double* initial_residual, double* final_residual);
+
 #ifdef __cplusplus
 }
 #endif

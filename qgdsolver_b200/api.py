@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
-    "qgd_pcg_solve", "qgd_pcg_solve_stepwise",
+    "qgd_pcg_solve", "qgd_pcg_solve_stepwise", "qgd_pcg_solve_multi",
     "qgd_qhdfoam_create", "qgd_qhdfoam_destroy", "qgd_qhdfoam_set_bcs", "qgd_qhdfoam_init_fields", "qgd_qhdfoam_step",
     "qgd_qhdfoam_get", "qgd_qhdfoam_get_flux", "qgd_qhdfoam_get_scalars", "qgd_qhdfoam_solver_info",
     "qgd_qhdfoam_launch_count",
@@ -130,6 +130,8 @@ def load_library():
     L.qgd_comm_unique_id.argtypes = [C.c_void_p]
     L.qgd_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.qgd_qgdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 9
+    L.qgd_pcg_solve_multi.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
+                                      C.c_int, _ip, _ip, _ip, _ip, _ip, _ip, _dp, _dp]
     L.qgd_pcg_solve_stepwise.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
                                          _ip, _dp, _dp]
     L.qgd_pcg_solve.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -437,6 +439,30 @@ def pcg_solve(mesh: Mesh, diag, upper, b, x0, tol=1e-8, rel_tol=0.0, max_iter=10
     fn = load_library().qgd_pcg_solve_stepwise if stepwise else load_library().qgd_pcg_solve
     _check(fn(mesh._h, _d(diag), _d(upper), _d(b), _d(x), tol, rel_tol, max_iter,
                                         PRECONDS[precond], C.byref(it), C.byref(r0), C.byref(r1)))
+    return x, it.value, r0.value, r1.value
+
+
+def pcg_solve_multi(mesh: Mesh, sub, diag, upper, b, x0, tol=1e-8, rel_tol=0.0, max_iter=1000, precond="diagonal"):
+    """qgd_pcg_solve_multi on this rank's extended sub-mesh (`sub`: decompose.SubDomain; arrays in local numbering, n_cells long)"""
+    nbrs = sorted(set(sub.send_face_cells) | set(sub.recv_face_cells))
+
+    def pack(d):
+        off = np.zeros(len(nbrs) + 1, np.int32)
+        parts = []
+        for k, r in enumerate(nbrs):
+            a = np.asarray(d.get(r, np.zeros(0, np.int32)), np.int32)
+            parts.append(a)
+            off[k + 1] = off[k] + a.size
+        ids = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+        return off, np.ascontiguousarray(ids if ids.size else np.zeros(1, np.int32))
+    so, sc = pack(sub.send_face_cells)
+    ro, rc = pack(sub.recv_face_cells)
+    nb = np.ascontiguousarray(nbrs if nbrs else [0], np.int32)
+    diag, upper, b = _f64(diag), _f64(upper), _f64(b)
+    x = np.array(x0, dtype=np.float64, copy=True)
+    it, r0, r1 = C.c_int(), C.c_double(), C.c_double()
+    _check(load_library().qgd_pcg_solve_multi(mesh._h, _d(diag), _d(upper), _d(b), _d(x), tol, rel_tol, max_iter, PRECONDS[precond],
+                                              len(nbrs), _i(nb), _i(so), _i(sc), _i(ro), _i(rc), C.byref(it), C.byref(r0), C.byref(r1)))
     return x, it.value, r0.value, r1.value
 
 

@@ -1399,6 +1399,65 @@ int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const
     });
 }
 
+// Decomposed PCG: every rank passes the matrix of its extended sub-mesh (rows of the owned cells are used, the columns of halo
+// cells are read from halo entries), the face-neighbour exchange lists (decompose.SubDomain.send_face_cells / recv_face_cells) and
+// its part of b and x.  Per iteration: one exchange of the search direction over NCCL send/recv and three all-reduced scalars.
+// Oracle: or_pcg_solve_blocks (preconditioner none | diagonal are decomposition-independent); CPU prototype: tests/gloo_pcg_worker.py.
+int qgd_pcg_solve_multi(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x, double tolerance,
+                        double rel_tol, int max_iter, int precond, int n_neighbours, const int* nbr_rank, const int* send_off,
+                        const int* send_cells, const int* recv_off, const int* recv_cells, int* iters, double* initial_residual,
+                        double* final_residual)
+{
+    return guarded([&] {
+        requireInit();
+        if (!g_comm) throw Error(QGD_ERR_STATE, "qgd_pcg_solve_multi: call qgd_comm_init first");
+        if (!mesh || !diag || !b || !x || (mesh->h.nInternal > 0 && !upper) || n_neighbours < 0 ||
+            (n_neighbours > 0 && (!nbr_rank || !send_off || !send_cells || !recv_off || !recv_cells)))
+            throw Error(QGD_ERR_INVALID, "qgd_pcg_solve_multi: null argument");
+        if (precond < 0 || precond > 1) throw Error(QGD_ERR_UNSUPPORTED, "qgd_pcg_solve_multi: preconditioner must be 0 (none) or 1 (diagonal)");
+        const HostMesh& h = mesh->h;
+        const size_t n = h.nCells;
+        const int nOwned = h.nOwned, nn = n_neighbours;
+        std::vector<double> d(diag, diag + n);
+        for (size_t c = nOwned; c < n; ++c) d[c] = 1.0;            // halo rows are never solved; keep 1/diag finite
+        PcgMatrix A;
+        A.build(h, d.data(), upper, precond, g_stream);
+        QGD_CUDA(cudaMemcpyAsync(A.b.p, b, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        QGD_CUDA(cudaMemcpyAsync(A.x.p, x, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        const int nS = nn ? send_off[nn] : 0, nR = nn ? recv_off[nn] : 0;
+        DevBuf<int> sIds, rIds;
+        DevBuf<double> sBuf, rBuf;
+        sIds.upload(std::vector<int>(send_cells, send_cells + std::max(nS, 0)), g_stream);
+        rIds.upload(std::vector<int>(recv_cells, recv_cells + std::max(nR, 0)), g_stream);
+        sBuf.alloc(std::max(nS, 1)); rBuf.alloc(std::max(nR, 1));
+        PcgHooks hooks;
+        hooks.exchange = [&](double* vec, cudaStream_t st) {
+            if (nS) k_gather1<<<(nS + 255) / 256, 256, 0, st>>>(nS, sIds.p, vec, sBuf.p);
+            QGD_NCCL(g_nccl.GroupStart());
+            for (int k = 0; k < nn; ++k) {
+                const int ns = send_off[k + 1] - send_off[k], nr = recv_off[k + 1] - recv_off[k];
+                if (ns) QGD_NCCL(g_nccl.Send(sBuf.p + send_off[k], ns, ncclDouble, nbr_rank[k], g_comm, st));
+                if (nr) QGD_NCCL(g_nccl.Recv(rBuf.p + recv_off[k], nr, ncclDouble, nbr_rank[k], g_comm, st));
+            }
+            QGD_NCCL(g_nccl.GroupEnd());
+            if (nR) k_scatter1<<<(nR + 255) / 256, 256, 0, st>>>(nR, rIds.p, rBuf.p, vec);
+        };
+        hooks.allreduceSum = [&](double* dev, int count, cudaStream_t st) {
+            QGD_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, ncclSum, g_comm, st));
+        };
+        StepwisePcg sw;
+        sw.alloc(A, nOwned);
+        PcgResult r;
+        sw.solve(A, A.b.p, A.x.p, tolerance, rel_tol, max_iter, precond, g_stream, &hooks, &r);
+        hooks.exchange(A.x.p, g_stream);                             // the solution's halo entries for the caller
+        QGD_CUDA(cudaMemcpyAsync(x, A.x.p, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        if (iters) *iters = r.iters;
+        if (initial_residual) *initial_residual = r.res0;
+        if (final_residual) *final_residual = r.res;
+    });
+}
+
 // the stepwise (multi-kernel) form of the same solver on one GPU: validates the kernels a decomposed run will use
 int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x, double tolerance,
                            double rel_tol, int max_iter, int precond, int* iters, double* initial_residual, double* final_residual)
