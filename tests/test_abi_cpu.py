@@ -79,3 +79,11 @@ def test_desc_struct_layout_matches_header():
     assert _struct_fields(hdr, "} qgd_qgdfoam_desc;") == [f[0] for f in api.QGDFoamDesc._fields_]
     assert _struct_fields(hdr, "} qgd_qhdfoam_desc;") == [f[0] for f in api.QHDFoamDesc._fields_]
     assert _struct_fields(hdr, "} qgd_mesh_desc;") == [f[0] for f in api._MeshDesc._fields_]
+
+
+def test_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/qgd_b200.h compiles as C99 (no C++ types in any signature)"""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", os.path.join(ROOT, "include", "qgd_b200.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
