@@ -140,3 +140,23 @@ def test_stepwise_pcg_matches_oracle_and_the_persistent_kernel(qgd, oracle_mod, 
     assert it0 == 0
     _, it5, _, _ = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-30, max_iter=5, precond=precond, stepwise=True)
     assert it5 == 5
+
+
+@NOT_RUN
+@pytest.mark.parametrize("n", [2, 4])
+def test_decomposed_pcg_matches_oracle(n):
+    """qgd_pcg_solve_multi (stepwise PCG + NCCL exchange / all-reduce) on n GPUs against the oracle's decomposed-run solver
+    (skipped on boxes with fewer GPUs)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29640 + n), os.path.join(root, "tests", "multi_gpu_pcg_worker.py")],
+                       capture_output=True, text=True, timeout=900)
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0, r.stderr[-4000:]
+    assert "MPCG_ALL_OK" in r.stdout
