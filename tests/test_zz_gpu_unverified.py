@@ -153,10 +153,13 @@ def test_decomposed_pcg_matches_oracle(n):
     import torch
     if torch.cuda.device_count() < n:
         pytest.skip(f"needs {n} GPUs")
+    if os.environ.get("QGD_RUN_UNVERIFIED_MULTI") != "1":
+        pytest.skip("first multi-GPU run of new NCCL code is started by hand (QGD_RUN_UNVERIFIED_MULTI=1, scripts/r02_multi.sh): an "
+                    "exchange-list mistake would block in ncclRecv rather than fail")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
                         "--master-addr", "127.0.0.1", "--master-port", str(29640 + n), os.path.join(root, "tests", "multi_gpu_pcg_worker.py")],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=180)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stderr[-4000:]
     assert "MPCG_ALL_OK" in r.stdout
