@@ -389,7 +389,7 @@ def reconstruct_fields(case_dir: str, time: str, names, mesh: PolyMesh, binary: 
     nI = mesh.n_internal
     out = {}
     for name in names:
-        internal, boundary, types = None, None, {}
+        internal, boundary, types, have_values = None, None, {}, False
         for p in procs:
             f = read_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh)
             if internal is None:
@@ -402,9 +402,10 @@ def reconstruct_fields(case_dir: str, time: str, names, mesh: PolyMesh, binary: 
                     continue
                 types.setdefault(patch.name, f.patch_types[patch.name])
                 if patch.size and patch.name in f.patch_values:
+                    have_values = True
                     gf = np.abs(p.face_addr[patch.start:patch.start + patch.size].astype(np.int64)) - 1
                     boundary[gf - nI] = f.patch_values[patch.name]
-        write_field(os.path.join(case_dir, time, name), mesh, name, internal, types, boundary, binary=binary)
+        write_field(os.path.join(case_dir, time, name), mesh, name, internal, types, boundary if have_values else None, binary=binary)
         out[name] = internal
     return out
 

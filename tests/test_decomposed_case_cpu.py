@@ -190,3 +190,33 @@ def test_decomposed_case_on_disk_drives_the_device_sharding(tmp_path):
     fld = np.sin(g.C[:, 0] * 5) + g.C[:, 2]
     back = decompose.gather_owned(subs, [fld[s.cell_global[:s.n_owned]] for s in subs], g.n_cells)
     assert np.array_equal(back, fld)
+
+
+def test_decompose_and_reconstruct_command_line(tmp_path):
+    """python -m qgdsolver_b200.decompose_case: case -> processor directories with the start-time fields; after copying the
+    processor fields to a new time, -reconstruct gives back the original fields bit for bit (gradient-type patches keep no value)."""
+    import os
+    import shutil
+    from qgdsolver_b200 import decompose_case as dc
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.1, bcs="fixed")
+    m = c.mesh
+    foamcase.write_polymesh(m, str(tmp_path))
+    fv = {p.name: "fixedValue" for p in m.patches}
+    zg = {p.name: "zeroGradient" for p in m.patches}
+    foamcase.write_field(str(tmp_path / "0" / "U"), m, "U", c.U0, fv, c.bvU)
+    foamcase.write_field(str(tmp_path / "0" / "T"), m, "T", c.T0, zg)
+    assert dc.main([str(tmp_path), "-n", "4"]) == 0
+    procs = foamcase.read_decomposed_case(str(tmp_path))
+    assert len(procs) == 4 and os.path.exists(tmp_path / "constant" / "cellDecomposition")
+    for p in procs:
+        shutil.copytree(tmp_path / f"processor{p.rank}" / "0", tmp_path / f"processor{p.rank}" / "0.5")
+        f = foamcase.read_field(str(tmp_path / f"processor{p.rank}" / "0" / "U"), p.mesh)
+        assert np.array_equal(f.internal, c.U0[p.cell_addr])
+    assert dc.main([str(tmp_path), "-reconstruct", "0.5"]) == 0
+    U = foamcase.read_field(str(tmp_path / "0.5" / "U"), m)
+    T = foamcase.read_field(str(tmp_path / "0.5" / "T"), m)
+    assert np.array_equal(U.internal, c.U0) and np.array_equal(T.internal, c.T0)
+    nI = m.n_internal
+    for p in m.patches:
+        assert U.patch_types[p.name] == "fixedValue" and np.array_equal(U.patch_values[p.name], c.bvU[p.start - nI:p.start - nI + p.size])
+        assert T.patch_types[p.name] == "zeroGradient"
