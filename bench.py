@@ -128,11 +128,36 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_oracle(n: int, budget_s: float, threads: int, min_steps: int = 2):
-    """CPU oracle on an n^3 sample of the same workload; returns MCUPS and the sample description."""
+def host_mem_available_gb() -> float:
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return float(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+ORACLE_BYTES_PER_CELL = 2500      # measured: oracle context of an n^3 hex box (field-at-a-time arrays + 18-coefficient face records)
+MESH_BYTES_PER_CELL = 1900        # python-side PolyMesh arrays of the same box
+
+
+def cpu_sample_size(n: int, have_mesh: bool) -> int:
+    """Edge of the hex box the CPU arm runs: the product arm's own n^3 when the host has the memory for the oracle's
+    field-at-a-time working set (2.5 kB per cell, ~42 GB at 256^3), else the largest power-of-two fraction that fits."""
+    avail = host_mem_available_gb() * 1e9
+    m = n
+    while m > 32 and (ORACLE_BYTES_PER_CELL + (0 if (have_mesh and m == n) else MESH_BYTES_PER_CELL)) * m ** 3 * 1.5 > avail:
+        m //= 2
+    return m
+
+
+def time_oracle(n: int, budget_s: float, threads: int, min_steps: int = 2, case=None):
+    """CPU oracle on an n^3 hex box of the same workload; returns MCUPS and the sample description."""
     import oracle as O
     O.build()
-    c = build_case(n)
+    c = case if case is not None else build_case(n)
     o = c.make_oracle(O, n_threads=threads)
     c.oracle_step(o, 1)                                      # warm-up
     steps, t0 = 0, time.perf_counter()
@@ -149,23 +174,27 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    n = args.ref_size
-    # each "step" = one oracle step over the bounded sample mesh
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # the product arm's own workload (args.size^3 = 256^3) on all host cores when the host memory allows it
+    n = args.ref_size if args.ref_size > 0 else cpu_sample_size(args.size, False)
     import oracle as O
     O.build()
-    c = build_case(n)
+    c = build_case(n, dt=2.0e-4 * (256.0 / n))
     o = c.make_oracle(O, n_threads=threads)
     c.oracle_step(o, max(args.warmup, 1))
     t0 = time.perf_counter()
     c.oracle_step(o, args.steps)
     el = time.perf_counter() - t0
     val = c.mesh.n_cells * args.steps / el / 1e6
+    same = n == args.size
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"QGDFoam 3D hex box, CPU oracle port on a bounded {n}^3 sample of the 256^3 case",
-                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False},
+            "config": {"workload": f"QGDFoam 3D synthetic hex box {n}^3 ({c.mesh.n_cells} cells), explicit, FP64",
+                       "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False, "deltaT": c.dt,
+                       "arm": "CPU oracle port of the reference algorithm (the reference needs OpenFOAM v2312: unbuildable here), "
+                              f"OpenMP over the whole mesh on {threads} host threads in place of mpirun -np {threads}",
+                       "same_workload_as_product_arm": same},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{n}^3 hex box ({c.mesh.n_cells} cells) x {args.steps} steps, OpenMP {threads} threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -220,11 +249,9 @@ def run_product(args):
     peak, peak_src = peaks()
     face_ms = kt["face_ms"] / max(kt["steps"], 1)
     pipe = s.get_pipeline()
-    tma = os.environ.get("QGD_FACE_TMA", "2") != "0" and mesh.n_faces % 2 == 0
-    kname = "k_face_cell_pipeline" if pipe["mode"] == 1 else ("k_face_flux_tma" if tma else "k_face_flux")
+    kname, l2hint = s.face_kernel()              # what the library launched, not a re-derivation
     kbytes = ab["face"] + ab["cell"] if pipe["mode"] == 1 else ab["face"]
     traffic, traffic_note = None, None
-    l2hint = int(os.environ.get("QGD_FACE_L2HINT", "3")) if tma else 0
     tp = os.path.join(ROOT, "profiles", "face_flux_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
@@ -232,8 +259,9 @@ def run_product(args):
             if tj.get("n_cells") == mesh.n_cells and kname + "<" in tj.get("kernel", ""):
                 if tj.get("l2hint", 0) == l2hint:
                     traffic = tj.get("dram_bytes_per_launch")
+                    traffic_note = tj.get("source")
                 else:       # an ncu capture of another variant of the kernel is not this kernel's traffic
-                    traffic_note = (f"no ncu capture of the L2-policy variant (l2hint={l2hint}) yet; the variant without cache policies "
+                    traffic_note = (f"no ncu capture of the l2hint={l2hint} variant; l2hint={tj.get('l2hint', 0)} "
                                     f"moved {tj.get('dram_bytes_per_launch', 0) / 1e9:.2f} GB per launch ({tj.get('source', '')})")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": kbytes / (face_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": kbytes / (face_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_note": traffic_note, "l2hint": l2hint,
@@ -243,30 +271,19 @@ def run_product(args):
                          "frac": ab["total"] / (ms_step * 1e-3) / 1e9 / peak},
                 "kernel_ms": {"k_points": kt["points_ms"] / max(kt["steps"], 1), kname: face_ms,
                               "k_cell_update": kt["cell_ms"] / max(kt["steps"], 1)}}
-    # ---- end-to-end through the C-ABI with host (pinned) buffers: state uploaded and downloaded every step
+    # ---- end-to-end through the C-ABI with host (pinned) buffers, every step: the fields of a time directory (U, T, p) go
+    # up, the state is re-created from them as createFields.H does, one step runs, U, T, p come back (restart semantics)
     nC = mesh.n_cells
-    names = ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")
-    pinned = {k: torch.empty((nC, 3) if k in ("U", "rhoU") else (nC,), dtype=torch.float64, pin_memory=True) for k in names}
-    st = {k: v.numpy() for k, v in pinned.items()}
-    s.step_host(0, None, st)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(3):
-        s.step_host(1, st, st)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        s.step_host(1, st, st)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    nbytes = 12 * 8 * nC
-    e2e = {"value": nC / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "qgd_qgdfoam_step_host: full cell state (12 doubles/cell) H2D + 1 step + D2H per call, pinned host buffers"}
-    # ---- CPU baseline (oracle port) on a bounded sample
+    e2e = e2e_fields(s, nC, max(3, min(args.steps, 10)))
+    if args.e2e_full_state:
+        e2e["full_state"] = e2e_full_state(s, nC, 5)
+    # ---- CPU baseline (oracle port): the same n^3 box when the host memory allows it, bounded number of steps
     cpu = None
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        v, sample, _, _ = time_oracle(args.ref_size, args.cpu_budget, threads)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        m = args.ref_size if args.ref_size > 0 else cpu_sample_size(n, True)
+        del s
+        v, sample, _, _ = time_oracle(m, args.cpu_budget, threads, case=c if m == n else None)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -278,6 +295,44 @@ def run_product(args):
     print(json.dumps(line), flush=True)
 
 
+def e2e_fields(s, nC, steps):
+    import torch
+    pinned = {k: torch.empty((nC, 3) if k == "U" else (nC,), dtype=torch.float64, pin_memory=True) for k in ("U", "T", "p")}
+    fl = {k: v.numpy() for k, v in pinned.items()}
+    s.step_fields_host(0, None, fl)
+    for _ in range(3):
+        s.step_fields_host(1, fl, fl)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.step_fields_host(1, fl, fl)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    nbytes = 5 * 8 * nC
+    return {"value": nC / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "ms_per_step": e2e_s * 1e3, "steps": steps,
+            "api": "qgd_qgdfoam_step_fields_host: U, T, p (5 doubles/cell) H2D, state re-created as createFields.H does, 1 step, "
+                   "U, T, p D2H - every call, pinned host buffers"}
+
+
+def e2e_full_state(s, nC, steps):
+    import torch
+    names = ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")
+    pinned = {k: torch.empty((nC, 3) if k in ("U", "rhoU") else (nC,), dtype=torch.float64, pin_memory=True) for k in names}
+    st = {k: v.numpy() for k, v in pinned.items()}
+    s.step_host(0, None, st)
+    for _ in range(2):
+        s.step_host(1, st, st)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.step_host(1, st, st)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    return {"value": nC / e2e_s / 1e6, "unit": UNIT, "bytes_each_way_per_step": 12 * 8 * nC, "ms_per_step": e2e_s * 1e3,
+            "api": "qgd_qgdfoam_step_host: full cell state (12 doubles/cell) H2D + 1 step + D2H per call"}
+
+
 def run_qgd2d(args):
     """Extra line (not the driver's default): BASELINE configs[1]-like, QGDFoam on a 2D n x n hex mesh (one cell thick, empty
     front/back), explicit, FP64.  Algorithmic bytes per step: 104 nC + 184 nF + 148 nP_used."""
@@ -287,8 +342,16 @@ def run_qgd2d(args):
     torch.cuda.set_device(0)
     api.init(0)
     n = args.qhd_size
-    mesh = cases.pm.hex_box(n, n, 1, lengths=(1.0, 1.0, 1.0 / n), patch_kinds={"zMin": "empty", "zMax": "empty"})
-    c = cases._with_bcs(mesh, "zg", GAS, 2.0e-4 * (256.0 / n))
+    if args.geometry == "step":
+        # BASELINE configs[1]: Mach-3 forward-facing step (Woodward-Colella), slip walls, ~1.03 M hex cells at n = 640
+        n = 640 if n == 1000 else n
+        c = cases.case_forward_step(n=n)
+        mesh = c.mesh
+        what = f"Mach-3 forward-facing step, {3 * n} x {n} cells minus the step"
+    else:
+        mesh = cases.pm.hex_box(n, n, 1, lengths=(1.0, 1.0, 1.0 / n), patch_kinds={"zMin": "empty", "zMax": "empty"})
+        c = cases._with_bcs(mesh, "zg", GAS, 2.0e-4 * (256.0 / n))
+        what = f"hex mesh {n}x{n}"
     s = c.make_solver(api)
     s.step(args.warmup)
     api.synchronize()
@@ -303,7 +366,8 @@ def run_qgd2d(args):
     peak, src = peaks()
     line = {"metric": METRIC, "value": nC / ms / 1e3, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"QGDFoam 2D hex mesh {n}x{n} ({nC} cells, empty front/back), explicit, FP64",
+            "config": {"workload": f"QGDFoam 2D {what} ({nC} cells, empty front/back), explicit, FP64",
+                       "l2": "state and mesh records (~0.4 GB) exceed the 126 MB L2; no flush", "face_kernel": s.face_kernel()[0],
                        "fvsc": "GaussVolPoint", "QGDCoeffs": "constScPrModel1", "implicitDiffusion": False},
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "alg_bytes_per_step": alg, "peak_source": src},
@@ -390,13 +454,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--size", type=int, default=256, help="hex box edge (cells); 256 = BASELINE configs[3]")
-    ap.add_argument("--ref-size", type=int, default=64, help="edge of the bounded CPU sample")
+    ap.add_argument("--ref-size", type=int, default=0, help="edge of the CPU arm's hex box; 0 = --size when the host memory allows it")
+    ap.add_argument("--e2e-full-state", action="store_true", help="also time the 12-doubles-per-cell qgd_qgdfoam_step_host hand-off")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--poly-n", type=int, default=100, help="--case poly: BCC lattice edge (cells ~ 2 n^3)")
     ap.add_argument("--case", default="qgd3d", choices=["qgd3d", "qgd2d", "qhd2d", "poly"],
                     help="qgd3d = BASELINE configs[3] (default); qgd2d = a configs[1]-sized 2D mesh; qhd2d = configs[2]; "
                          "poly = a configs[4]-shaped polyhedral mesh (one GPU's share)")
+    ap.add_argument("--geometry", default="step", choices=["step", "box"], help="--case qgd2d: forward-facing step (configs[1]) or a plain box")
     ap.add_argument("--precond", default="diagonal")
     ap.add_argument("--p-tol", type=float, default=1e-8)
     ap.add_argument("--p-rel-tol", type=float, default=0.0)

@@ -45,7 +45,10 @@ typedef enum {
     QGD_BC_FIXED_GRADIENT = 2,   /* fixedGradient                                */
     QGD_BC_QGD_FLUX = 3,         /* qgdFlux  qgdFluxFvPatchScalarField.C:159-208 */
     QGD_BC_CALCULATED = 4,       /* calculated                                   */
-    QGD_BC_QHD_FLUX = 5          /* qhdFlux  qhdFluxFvPatchScalarField.C:159-219 */
+    QGD_BC_QHD_FLUX = 5,         /* qhdFlux  qhdFluxFvPatchScalarField.C:159-219 */
+    QGD_BC_SLIP = 6              /* slip | symmetryPlane | symmetry for U [OF-v2312 basicSymmetryFvPatchField]:
+                                    U_b = U_P - n (n . U_P); scalars on such patches are zeroGradient.  QGDFoam, explicit
+                                    branch (the Mach-3 forward-facing-step walls, BASELINE configs[1])              */
 } qgd_bc_kind;
 
 typedef struct qgd_mesh qgd_mesh;       /* fvMesh image on the device             */
@@ -188,6 +191,25 @@ typedef struct {
 } qgd_state_host;
 #define QGD_STATE_DOUBLES_PER_CELL 12
 int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, const qgd_state_host* out);
+/* Field-level hand-off with HOST buffers: the caller passes the fields the reference reads from a time directory
+ * (QGDFoam createFields.H:3-109: U n_cells*3, T, p n_cells); the library re-creates the thermodynamic and conserved
+ * state from them exactly as qgd_qgdfoam_init_fields does (boundary conditions and alphaQGD as set before), runs
+ * n_steps of the loop and writes back what the reference writes at a write time: U, T, p and, where the pointer is
+ * non-NULL, rho, rhoU, rhoE.  This is the reference's restart semantics (write + read of a time directory), i.e. 5
+ * doubles per cell each way instead of the 12 of qgd_qgdfoam_step_host; `in` NULL keeps the device state, `out` NULL
+ * skips the download.  Buffers should be page-locked. */
+typedef struct {
+    double* U;     /* n_cells*3 */
+    double* T;     /* n_cells   */
+    double* p;     /* n_cells   */
+    double* rho;   /* n_cells   out only, may be NULL */
+    double* rhoU;  /* n_cells*3 out only, may be NULL */
+    double* rhoE;  /* n_cells   out only, may be NULL */
+} qgd_fields_host;
+int qgd_qgdfoam_step_fields_host(qgd_solver* s, int n_steps, const qgd_fields_host* in, const qgd_fields_host* out);
+/* name of the internal-face kernel the step launches on this solver's mesh ("k_face_flux_tma" | "k_face_flux" |
+ * "k_face_flux_lsq" | "k_face_cell_pipeline") and its L2 cache-policy bits (QGD_FACE_L2HINT); bench bookkeeping */
+const char* qgd_qgdfoam_face_kernel(qgd_solver* s, int* l2hint);
 /* fields: 0 rho, 1 rhoU(3), 2 rhoE, 3 U(3), 4 e, 5 p, 6 T, 7 c, 8 mu, 9 alpha, 10 tauQGD, 11 H, 12 ScQGD.
  * cells: n_cells*k host buffer, bnd: n_bnd*k host buffer or NULL. */
 int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd);

@@ -18,7 +18,7 @@ from .polymesh import PolyMesh
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqgd_b200.so")
 
-BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED, BC_QHD_FLUX = 0, 1, 2, 3, 4, 5
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED, BC_QHD_FLUX, BC_SLIP = 0, 1, 2, 3, 4, 5, 6
 QGD_OK, ERR_INVALID, ERR_UNKNOWN_MODEL, ERR_UNSUPPORTED, ERR_CUDA, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 # every symbol include/qgd_b200.h declares (checked by tests/test_abi_cpu.py)
@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get", "qgd_mesh_set_degenerate_stencil_faces",
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
-    "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
+    "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_step_fields_host", "qgd_qgdfoam_face_kernel", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
@@ -87,6 +87,10 @@ class _StateHost(C.Structure):
     _fields_ = [(n, _dp) for n in ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")]
 
 
+class _FieldsHost(C.Structure):
+    _fields_ = [(n, _dp) for n in ("U", "T", "p", "rho", "rhoU", "rhoE")]
+
+
 _lib = None
 
 
@@ -117,6 +121,9 @@ def load_library():
     L.qgd_qgdfoam_init_fields.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     L.qgd_qgdfoam_step.argtypes = [C.c_void_p, C.c_int]
     L.qgd_qgdfoam_step_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(_StateHost), C.POINTER(_StateHost)]
+    L.qgd_qgdfoam_step_fields_host.argtypes = [C.c_void_p, C.c_int, C.POINTER(_FieldsHost), C.POINTER(_FieldsHost)]
+    L.qgd_qgdfoam_face_kernel.argtypes = [C.c_void_p, _ip]
+    L.qgd_qgdfoam_face_kernel.restype = C.c_char_p
     L.qgd_qgdfoam_get.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     L.qgd_qgdfoam_get_flux.argtypes = [C.c_void_p, C.c_int, _dp]
     L.qgd_qgdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -370,6 +377,25 @@ class QGDFoam:
         so = self._state_struct(state_out) if state_out is not None else None
         _check(load_library().qgd_qgdfoam_step_host(self._h, n_steps, C.byref(si) if si else None,
                                                     C.byref(so) if so else None))
+
+    def step_fields_host(self, n_steps, fields_in: Optional[dict], fields_out: Optional[dict]):
+        """restart-style hand-off: in = U, T, p (as read by createFields.H); out = U, T, p [+ rho, rhoU, rhoE]"""
+        def mk(d):
+            if d is None:
+                return None
+            f = _FieldsHost()
+            for n in ("U", "T", "p", "rho", "rhoU", "rhoE"):
+                setattr(f, n, _d(d.get(n)))
+            return f
+        fi, fo = mk(fields_in), mk(fields_out)
+        _check(load_library().qgd_qgdfoam_step_fields_host(self._h, n_steps, C.byref(fi) if fi else None,
+                                                           C.byref(fo) if fo else None))
+
+    def face_kernel(self):
+        """(name of the internal-face kernel the step launches, its L2 cache-policy bits)"""
+        h = C.c_int()
+        name = load_library().qgd_qgdfoam_face_kernel(self._h, C.byref(h))
+        return name.decode(), h.value
 
     def get(self, name: str, with_bnd: bool = False):
         fid, k = CELL_FIELDS[name]

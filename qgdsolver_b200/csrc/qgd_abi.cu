@@ -241,6 +241,21 @@ __global__ void k_unpack_state(int n, const double* __restrict__ S, double* st)
     st[10 * N + c] = S[11 * N + c]; st[11 * N + c] = S[13 * N + c];
 }
 
+// U (AoS), T, p [, rho, rhoU (AoS), rhoE] of the owned and halo cells into the staging buffer: [3n | n | n | n | 3n | n]
+__global__ void k_unpack_fields(int n, const double* __restrict__ S, double* __restrict__ st, int conserved)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const size_t N = n;
+    st[3 * (size_t)c] = S[N + c]; st[3 * (size_t)c + 1] = S[2 * N + c]; st[3 * (size_t)c + 2] = S[3 * N + c];
+    st[3 * N + c] = S[6 * N + c]; st[4 * N + c] = S[5 * N + c];
+    if (conserved) {
+        st[5 * N + c] = S[c];
+        st[6 * N + 3 * (size_t)c] = S[8 * N + c]; st[6 * N + 3 * (size_t)c + 1] = S[9 * N + c]; st[6 * N + 3 * (size_t)c + 2] = S[10 * N + c];
+        st[9 * N + c] = S[11 * N + c];
+    }
+}
+
 // ---- halo exchange: pack (gather) -> ncclSend/ncclRecv in one group -> unpack (scatter)
 constexpr int kCellDoubles = 16, kBfDoubles = 20;
 // all neighbours in one launch: item i of the concatenated (cells | boundary faces) lists belongs to neighbour k with
@@ -556,7 +571,7 @@ void runSteps(qgd_solver* s, int n)
         hooks.waitHalo = [s](cudaStream_t st) {
             if (s->halo.pending) QGD_CUDA(cudaStreamWaitEvent(st, g_evHalo, 0));
         };
-    if (const char* v = getenv("QGD_BND_FORK")) g_bndFork = atoi(v);
+    { const char* v = getenv("QGD_BND_FORK"); g_bndFork = v ? atoi(v) : 1; }
     StepFork fork{g_sideStream, g_evFork[0], g_evFork[1], g_evFork[2], g_evFork[3], g_evFork[4], !multi};
     // measured on one B200: neutral at 256^3 (the boundary chain's time moves into k_points), -3 % per step at 128^3; multi-GPU: opt-in
     // (QGD_BND_FORK=2) until measured - there the side stream can only start after the halo wait
@@ -631,18 +646,13 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
     const std::vector<int>& perm = mesh->facePerm;
     std::vector<int4> v4(nF);
     std::vector<int> fl(nF);
-    // opt-in (QGD_FACE_GEOM=1): rebuild G in the face kernel instead of streaming it.  Measured on B200 at 256^3: 2.86 ms vs
-    // 2.44 ms for the streaming kernel - the extra FP64 work and gathers cost more than the 3.6 GB they save.
-    const bool geomFaces = getenv("QGD_FACE_GEOM") && atoi(getenv("QGD_FACE_GEOM")) == 1;
-    std::vector<double> Gp(G.size());
+    const size_t fs = (size_t)mesh->faceStride;
+    std::vector<double> Gp(9 * fs, 0.0);
     for (int f = 0; f < nF; ++f) {
         const size_t o = perm[f];
         v4[f] = make_int4(vtx[4 * o], vtx[4 * o + 1], vtx[4 * o + 2], vtx[4 * o + 3]);
         fl[f] = flags[o];
-        if (geomFaces && (int)o < mesh->h.nInternal && mesh->h.nD == 3 && !op.reduced && (flags[o] & FF_POINTS) &&
-            mesh->h.faceOff[o + 1] - mesh->h.faceOff[o] == 4)
-            fl[f] |= FF_GEOM;
-        for (int k = 0; k < 9; ++k) Gp[(size_t)k * nF + f] = G[(size_t)k * nF + o];
+        for (int k = 0; k < 9; ++k) Gp[(size_t)k * fs + f] = G[(size_t)k * nF + o];
     }
     if (op.lsq) {
         // internal faces: least-squares cell stencil; the G record keeps the nf*snGrad fallback of degenerate faces
@@ -668,8 +678,6 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         op.lsqW = W;
         op.lsqCells.upload(cd, g_stream); op.lsqCoef.upload(kd, g_stream);
     }
-    op.allGeom = geomFaces && mesh->nIActive > 0 && !op.lsq;
-    for (int f = 0; f < mesh->nIActive && op.allGeom; ++f) if (!(fl[f] & FF_GEOM)) op.allGeom = false;
     op.vtx.upload(v4, g_stream); op.flags.upload(fl, g_stream); op.G.upload(Gp, g_stream); op.halfDist.upload(hd, g_stream);
 }
 
@@ -806,16 +814,11 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         std::vector<int> bk(h.nBnd);
         for (int b = 0; b < h.nBnd; ++b) bk[b] = h.patchKind[h.bfacePatch[b]];
         m->bfaceKind.upload(bk, g_stream);
-        std::vector<double> sfSoA(3 * (size_t)nF);
+        m->faceStride = (nF + 15) & ~15;
+        std::vector<double> sfSoA(3 * (size_t)m->faceStride, 0.0);
         for (int f = 0; f < nF; ++f)
-            for (int d = 0; d < 3; ++d) sfSoA[(size_t)d * nF + f] = h.Sf[3 * (size_t)perm[f] + d];
+            for (int d = 0; d < 3; ++d) sfSoA[(size_t)d * m->faceStride + f] = h.Sf[3 * (size_t)perm[f] + d];
         m->Sf.upload(sfSoA, g_stream);
-        {
-            std::vector<double> xs(3 * (size_t)h.nPoints), cs(3 * (size_t)h.nCells);
-            for (int p = 0; p < h.nPoints; ++p) for (int d = 0; d < 3; ++d) xs[(size_t)d * h.nPoints + p] = h.points[3 * (size_t)p + d];
-            for (int c = 0; c < h.nCells; ++c) for (int d = 0; d < 3; ++d) cs[(size_t)d * h.nCells + c] = h.C[3 * (size_t)c + d];
-            m->ptsSoA.upload(xs, g_stream); m->ctrSoA.upload(cs, g_stream);
-        }
         m->magSf.upload(permD(h.magSf), g_stream); m->w.upload(permD(h.w), g_stream); m->dC.upload(permD(h.dC), g_stream);
         m->ndC.upload(permD(h.ndC), g_stream); m->V.upload(h.V, g_stream);
         m->hQGDf.upload(permD(h.hQGDf), g_stream); m->hQGD.upload(h.hQGD, g_stream);
@@ -955,9 +958,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         std::memcpy(&sc.tauMinBits, &big, sizeof(double));
         sc.maxCo = d->max_co; sc.maxDeltaT = d->max_delta_t; sc.cTau = d->c_tau; sc.adjust = d->adjust_time_step;
         s->sc.upload(std::vector<StepScalars>(1, sc), g_stream);
-        if (const char* v = getenv("QGD_FACE_VARIANT")) setFaceVariant(atoi(v));
         if (const char* v = getenv("QGD_FACE_TMA")) setFaceTma(atoi(v));
-        if (const char* v = getenv("QGD_CELL_TMA")) setCellTma(atoi(v));
         if (const char* v = getenv("QGD_FACE_L2HINT")) setFaceL2Hint(atoi(v));
         s->gridFaces = faceKernelGrid();
         *out = s.release();
@@ -1016,8 +1017,10 @@ int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const i
             const int pi = h.bfacePatch[b];
             u[b] = bc_U[pi]; t[b] = bc_T[pi]; p[b] = bc_p[pi];
             if (h.patchKind[pi] == QGD_PATCH_EMPTY) continue;
-            if (u[b] != QGD_BC_FIXED_VALUE && u[b] != QGD_BC_ZERO_GRADIENT)
-                throw Error(QGD_ERR_UNSUPPORTED, "U boundary condition outside the device-native set (fixedValue, zeroGradient)");
+            if (u[b] != QGD_BC_FIXED_VALUE && u[b] != QGD_BC_ZERO_GRADIENT && u[b] != QGD_BC_SLIP)
+                throw Error(QGD_ERR_UNSUPPORTED, "U boundary condition outside the device-native set (fixedValue, zeroGradient, slip)");
+            if (u[b] == QGD_BC_SLIP && s->k.implicit)
+                throw Error(QGD_ERR_UNSUPPORTED, "slip / symmetryPlane velocity with implicitDiffusion true is not available (explicit branch only)");
             if (t[b] != QGD_BC_FIXED_VALUE && t[b] != QGD_BC_ZERO_GRADIENT)
                 throw Error(QGD_ERR_UNSUPPORTED, "T boundary condition outside the device-native set (fixedValue, zeroGradient)");
             if (p[b] != QGD_BC_FIXED_VALUE && p[b] != QGD_BC_ZERO_GRADIENT && p[b] != QGD_BC_QGD_FLUX)
@@ -1108,6 +1111,51 @@ int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, 
         }
         QGD_CUDA(cudaStreamSynchronize(g_stream));
     });
+}
+
+int qgd_qgdfoam_step_fields_host(qgd_solver* s, int n_steps, const qgd_fields_host* in, const qgd_fields_host* out)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_fields_host: null solver");
+        if (!s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_step_fields_host: call qgd_qgdfoam_init_fields first");
+        const size_t n = s->mesh->h.nCells;
+        if (s->stage.n < QGD_STATE_DOUBLES_PER_CELL * n) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * n);
+        double* st = s->stage.p;
+        if (in) {
+            if (!in->U || !in->T || !in->p) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_fields_host: incomplete input fields (U, T, p)");
+            QGD_CUDA(cudaMemcpyAsync(st, in->U, 3 * n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+            QGD_CUDA(cudaMemcpyAsync(st + 3 * n, in->T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+            QGD_CUDA(cudaMemcpyAsync(st + 4 * n, in->p, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+            if (s->k.model == 1) { s->k.tauMode = 2; s->stepsDone = 0; }       // "U" is registered after the first correct() again
+            launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), st, st + 3 * n, st + 4 * n);
+            s->launches += 2 + (s->k.varSc ? 1 : 0);
+            if (s->halo.active) s->launches += haloExchange(s);
+        }
+        runSteps(s, n_steps);
+        if (out) {
+            if (!out->U || !out->T || !out->p) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_fields_host: incomplete output fields (U, T, p)");
+            const bool cons = out->rho || out->rhoU || out->rhoE;
+            k_unpack_fields<<<(int)((n + 255) / 256), 256, 0, g_stream>>>((int)n, s->S.p, st, cons ? 1 : 0);
+            s->launches++;
+            QGD_CUDA(cudaMemcpyAsync(out->U, st, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+            QGD_CUDA(cudaMemcpyAsync(out->T, st + 3 * n, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+            QGD_CUDA(cudaMemcpyAsync(out->p, st + 4 * n, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+            if (out->rho) QGD_CUDA(cudaMemcpyAsync(out->rho, st + 5 * n, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+            if (out->rhoU) QGD_CUDA(cudaMemcpyAsync(out->rhoU, st + 6 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+            if (out->rhoE) QGD_CUDA(cudaMemcpyAsync(out->rhoE, st + 9 * n, n * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+        }
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+    });
+}
+
+const char* qgd_qgdfoam_face_kernel(qgd_solver* s, int* l2hint)
+{
+    if (!s) return "";
+    const bool pipe = s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc;
+    const char* name = pipe ? "k_face_cell_pipeline" : faceKernelName(s->fvsc->view());
+    if (l2hint) *l2hint = std::string(name) == "k_face_flux_tma" ? faceKernelL2Hint() : 0;
+    return name;
 }
 
 int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)

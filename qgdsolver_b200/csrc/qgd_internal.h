@@ -76,9 +76,7 @@ enum FaceFlags : int {
     FF_POINTS = 1,     // uses vertex values (G1/G2 non-zero)
     FF_TRI_QUIRK = 2,  // internal triangular face: vector-gradient index pattern of GaussVolPointBase3D.C:844-854
     FF_NORMAL_ONLY = 4, // boundary face evaluated as nf*snGrad (1D, reduced, other faces)
-    FF_LSQ = 16,       // internal face evaluated with the leastSquares cell stencil (FaceView::lsq*)
-    FF_GEOM = 8        // internal 3D quad face: the step kernel rebuilds G from point coordinates and cell centres
-                       // (18 cached gathers) instead of streaming the 72-byte record
+    FF_LSQ = 16        // internal face evaluated with the leastSquares cell stencil (FaceView::lsq*)
 };
 
 // ---------------------------------------------------------------- host-side derived mesh data
@@ -125,6 +123,7 @@ struct qgd_mesh {
     std::vector<int> faceInv;      // polyMesh face -> device face
     qgd::DevBuf<int> facePermDev;
     int nIActive = 0;              // internal faces with an owned owner cell (first in device order)
+    int faceStride = 0;            // column stride of the SoA arrays Sf[3] and G[9]: nFaces rounded up to a multiple of 16
     // ELL (column-major, width W) + CSR tail stencils: coalesced row access for thread-per-row kernels
     int pcEllW = 8, cfEllW = 6;
     qgd::DevBuf<int> pcEll, pcCount, pcTailOff, pcTailCell;      // point -> cells
@@ -132,8 +131,6 @@ struct qgd_mesh {
     qgd::DevBuf<int> cfEll, cfTailOff, cfTailEnc;                // cell -> faces, enc = (deviceFace<<1)|neighbourSide, -1 pad
     qgd::DevBuf<int> owner, neighbour, patchPoints, ppOff, ppFace, bfaceKind;
     qgd::DevBuf<double> ppW;
-    qgd::DevBuf<double> Sf;        // SoA 3*nFaces
+    qgd::DevBuf<double> Sf;        // SoA 3*faceStride
     qgd::DevBuf<double> magSf, w, dC, ndC, V, hQGDf, hQGD;
-    qgd::DevBuf<double> ptsSoA;    // SoA 3*nPoints  polyMesh::points()
-    qgd::DevBuf<double> ctrSoA;    // SoA 3*nCells   fvMesh::C()
 };

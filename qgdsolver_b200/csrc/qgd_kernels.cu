@@ -231,9 +231,9 @@ __global__ void k_fvsc_grad(FaceView fv, const double* __restrict__ cell, const 
     double g1[3], g2[3], gp[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        g1[i] = fv.G[(size_t)(0 + i) * fv.nF + f];
-        g2[i] = fv.G[(size_t)(3 + i) * fv.nF + f];
-        gp[i] = fv.G[(size_t)(6 + i) * fv.nF + f];
+        g1[i] = fv.G[(size_t)(0 + i) * fv.fs + f];
+        g2[i] = fv.G[(size_t)(3 + i) * fv.fs + f];
+        gp[i] = fv.G[(size_t)(6 + i) * fv.fs + f];
     }
     if (f >= fv.nI) {
         const int b = f - fv.nI;
@@ -286,9 +286,9 @@ __global__ void k_fvsc_div(FaceView fv, const double* __restrict__ cell, const d
     double g1[3], g2[3], gp[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        g1[i] = fv.G[(size_t)(0 + i) * fv.nF + f];
-        g2[i] = fv.G[(size_t)(3 + i) * fv.nF + f];
-        gp[i] = fv.G[(size_t)(6 + i) * fv.nF + f];
+        g1[i] = fv.G[(size_t)(0 + i) * fv.fs + f];
+        g2[i] = fv.G[(size_t)(3 + i) * fv.fs + f];
+        gp[i] = fv.G[(size_t)(6 + i) * fv.fs + f];
     }
     if (f >= fv.nI) {
         const int b = f - fv.nI;
@@ -524,7 +524,7 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     const int flags = fv.flags[f];
     const double delta = fv.dC[f];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) o.Sf[i] = fv.Sf[(size_t)i * fv.nF + f];
+    for (int i = 0; i < 3; ++i) o.Sf[i] = fv.Sf[(size_t)i * fv.fs + f];
     // face values = boundary values
     o.s.rho = a.rho; o.s.U[0] = a.Ux; o.s.U[1] = a.Uy; o.s.U[2] = a.Uz;
     o.s.rhoU[0] = bb.rhoUx; o.s.rhoU[1] = bb.rhoUy; o.s.rhoU[2] = bb.rhoUz;
@@ -535,7 +535,8 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     o.s.p = a.p; o.s.c = bb.c; o.s.H = a.H; o.s.alpha = k.implicit ? 0.0 : bb.alphaEff; o.s.mu = k.implicit ? 0.0 : bb.mu;
     o.s.tau = k.tauMode == 1 ? bb.aByC : bb.aByC * fv.hf[f];
     // patch snGrad per field [OF fvPatchField::snGrad / zeroGradient / fixedGradient]
-    const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
+    // slip [OF-v2312 basicSymmetryFvPatchField::snGrad]: (transform(I - 2nn, U_P) - U_P) deltaCoeffs/2 = deltaCoeffs (U_b - U_P)
+    const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE || bs.bcU[b] == QGD_BC_SLIP, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
     const double pB = usePNew ? bs.pNew[b] : a.p;
     RecP sn;
     sn.rho = delta * (a.rho - cA.rho);
@@ -548,9 +549,9 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     double g1[3], g2[3], gp[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        g1[i] = fv.G[(size_t)(0 + i) * fv.nF + f];
-        g2[i] = fv.G[(size_t)(3 + i) * fv.nF + f];
-        gp[i] = fv.G[(size_t)(6 + i) * fv.nF + f];
+        g1[i] = fv.G[(size_t)(0 + i) * fv.fs + f];
+        g2[i] = fv.G[(size_t)(3 + i) * fv.fs + f];
+        gp[i] = fv.G[(size_t)(6 + i) * fv.fs + f];
     }
     if (flags & FF_NORMAL_ONLY) {
 #pragma unroll
@@ -657,12 +658,12 @@ __device__ __forceinline__ void lsqGrads(const FaceView& fv, const SolverView& s
     }
 }
 
-template <bool ADJUST, bool GEOM, bool SMEM = false, bool LSQ = false, int HINT = 0>
+template <bool ADJUST, bool SMEM = false, bool LSQ = false, int HINT = 0>
 __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv, const SolverView& sv, int f, size_t slot, int P, int N,
                                             int flagsCur, const int4& v, double& coMax, double& tauMin, const double* sd = nullptr, int li = 0,
                                             unsigned long long polKeep = 0ull)
 {
-    const size_t nF = fv.nF;
+    (void)f;
     const RecA aP = (HINT & 2) ? loadAKeep(sv, P, polKeep) : loadA(sv, P), aN = (HINT & 2) ? loadAKeep(sv, N, polKeep) : loadA(sv, N);
     const RecB bP = (HINT & 2) ? loadBKeep(sv, P, polKeep) : loadB(sv, P), bN = (HINT & 2) ? loadBKeep(sv, N, polKeep) : loadB(sv, N);
     RecP d1{0, 0, 0, 0, 0, 0}, d2{0, 0, 0, 0, 0, 0};
@@ -678,31 +679,13 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
     double g1[3], g2[3], gp[3], Sf[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sf[i] = SMEM ? sd[(9 + i) * kTmaTile + li] : __ldg(&fv.Sf[(size_t)i * nF + f]);
-    if (GEOM) {
-        // every internal face is a 3D quad (FaceView::allGeom): G rebuilt from the four vertices and the two cell centres (SURVEY A.2 closed form, same operation
-        // order as HostMesh::buildFaceRecords): e1 = p2-p4, e2 = p3-p1, d = C_N-C_P, D = e2.(e1 x d),
-        // G1 = (d x e1)/D, G2 = (d x e2)/D, GP = (e1 x e2)/D.  18 gathers that hit L1/L2 replace a 72-byte stream.
-        double e1[3], e2[3], d[3];
+    for (int i = 0; i < 3; ++i) Sf[i] = SMEM ? sd[(9 + i) * kTmaTile + li] : __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
+    {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double* X = fv.X + (size_t)i * fv.nPts;
-            const double* Cc = fv.Cc + (size_t)i * fv.nCls;
-            e1[i] = __ldg(X + v.y) - __ldg(X + v.w);
-            e2[i] = __ldg(X + v.z) - __ldg(X + v.x);
-            d[i] = __ldg(Cc + N) - __ldg(Cc + P);
-        }
-        const double c1x = e1[1] * d[2] - e1[2] * d[1], c1y = e1[2] * d[0] - e1[0] * d[2], c1z = e1[0] * d[1] - e1[1] * d[0];   // e1 x d
-        const double rD = 1.0 / (e2[0] * c1x + e2[1] * c1y + e2[2] * c1z);
-        g1[0] = rD * (d[1] * e1[2] - d[2] * e1[1]); g1[1] = rD * (d[2] * e1[0] - d[0] * e1[2]); g1[2] = rD * (d[0] * e1[1] - d[1] * e1[0]);
-        g2[0] = rD * (d[1] * e2[2] - d[2] * e2[1]); g2[1] = rD * (d[2] * e2[0] - d[0] * e2[2]); g2[2] = rD * (d[0] * e2[1] - d[1] * e2[0]);
-        gp[0] = rD * (e1[1] * e2[2] - e1[2] * e2[1]); gp[1] = rD * (e1[2] * e2[0] - e1[0] * e2[2]); gp[2] = rD * (e1[0] * e2[1] - e1[1] * e2[0]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            g1[i] = SMEM ? sd[(0 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
-            g2[i] = SMEM ? sd[(3 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
-            gp[i] = SMEM ? sd[(6 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
+            g1[i] = SMEM ? sd[(0 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(0 + i) * fv.fs + f]);
+            g2[i] = SMEM ? sd[(3 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(3 + i) * fv.fs + f]);
+            gp[i] = SMEM ? sd[(6 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(6 + i) * fv.fs + f]);
         }
     }
     FaceGrads g;
@@ -756,8 +739,8 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
 }
 
 // ---- the fused internal-face kernel (two-kernel form: fluxes go to a full-size array)
-template <bool ADJUST, bool GEOM, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv, SolverView sv)
+template <bool ADJUST>
+__global__ void __launch_bounds__(kBlock, 2) k_face_flux(Consts k, FaceView fv, SolverView sv)
 {
     double coMax = 0.0, tauMin = DBL_MAX;
     // software-pipelined indices: the addressing of face f+stride is fetched while face f is computed, so each
@@ -775,9 +758,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_flux(Consts k, FaceView fv
             const int fn = f + stride;
             if (fn < nIA) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
         }
-        faceFluxOne<ADJUST, GEOM>(k, fv, sv, f, (size_t)f, Pc, Nc, flagsCur, vc, coMax, tauMin);
+        faceFluxOne<ADJUST>(k, fv, sv, f, (size_t)f, Pc, Nc, flagsCur, vc, coMax, tauMin);
     }
-    if (ADJUST) blockReduceCo<BLOCK>(coMax, tauMin, sv.sc);
+    if (ADJUST) blockReduceCo<kBlock>(coMax, tauMin, sv.sc);
 }
 
 // setDeltaT-QGDQHD.H:41-61 ; QGDCourantNo.H:47-50
@@ -830,7 +813,7 @@ __global__ void __launch_bounds__(256, 2) k_face_flux_lsq(Consts k, FaceView fv,
 {
     double coMax = 0.0, tauMin = DBL_MAX;
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < fv.nIActive; f += gridDim.x * blockDim.x)
-        faceFluxOne<ADJUST, false, false, true>(k, fv, sv, f, (size_t)f, __ldg(&fv.own[f]), __ldg(&fv.nei[f]), __ldg(&fv.flags[f]),
+        faceFluxOne<ADJUST, false, true>(k, fv, sv, f, (size_t)f, __ldg(&fv.own[f]), __ldg(&fv.nei[f]), __ldg(&fv.flags[f]),
                                                 __ldg(&fv.vtx[f]), coMax, tauMin);
     if (ADJUST) blockReduceCo<256>(coMax, tauMin, sv.sc);
 }
@@ -886,7 +869,7 @@ template <bool ADJUST, bool STREAM = false>
 __device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* stage, unsigned long long* bar, int tile, unsigned long long pol = 0ull)
 {
     using L = TmaStage<ADJUST>;
-    const size_t f0 = (size_t)tile * kTmaTile, nF = fv.nF;
+    const size_t f0 = (size_t)tile * kTmaTile, fs = fv.fs;
     mbarExpectTx(bar, (unsigned)L::kBytes);
     auto bulkLoad = [pol](void* d, const void* s, unsigned b, unsigned long long* m) {
         if (STREAM) bulkLoadHint(d, s, b, m, pol);
@@ -895,9 +878,9 @@ __device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* 
     bulkLoad(stage + L::oVtx, fv.vtx + f0, kTmaTile * 16, bar);
     double* d = reinterpret_cast<double*>(stage + L::oD);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) bulkLoad(d + q * kTmaTile, fv.G + q * nF + f0, kTmaTile * 8, bar);
+    for (int q = 0; q < 9; ++q) bulkLoad(d + q * kTmaTile, fv.G + q * fs + f0, kTmaTile * 8, bar);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) bulkLoad(d + (9 + q) * kTmaTile, fv.Sf + q * nF + f0, kTmaTile * 8, bar);
+    for (int q = 0; q < 3; ++q) bulkLoad(d + (9 + q) * kTmaTile, fv.Sf + q * fs + f0, kTmaTile * 8, bar);
     bulkLoad(d + 12 * kTmaTile, fv.w + f0, kTmaTile * 8, bar);
     bulkLoad(d + 13 * kTmaTile, fv.hf + f0, kTmaTile * 8, bar);
     if (ADJUST) bulkLoad(d + 14 * kTmaTile, fv.magSf + f0, kTmaTile * 8, bar);
@@ -906,12 +889,13 @@ __device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* 
     bulkLoad(stage + L::oFlags, fv.flags + f0, kTmaTile * 4, bar);
 }
 
-template <bool ADJUST, int NST, int HINT = 0>
+template <bool ADJUST, int HINT>
 __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceView fv, SolverView sv)
 {
     const unsigned long long polKeep = (HINT & 2) ? l2PolicyEvictLast() : 0ull;
     const unsigned long long polStream = (HINT & 1) ? l2PolicyEvictFirst() : 0ull;
     using L = TmaStage<ADJUST>;
+    constexpr int NST = 2;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NST];
     double coMax = 0.0, tauMin = DBL_MAX;
@@ -942,7 +926,7 @@ __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceVie
         const int P = reinterpret_cast<const int*>(sg + L::oOwn)[li], N = reinterpret_cast<const int*>(sg + L::oNei)[li];
         const int flags = reinterpret_cast<const int*>(sg + L::oFlags)[li];
         const int4 v = reinterpret_cast<const int4*>(sg + L::oVtx)[li];
-        faceFluxOne<ADJUST, false, true, false, HINT>(k, fv, sv, f, (size_t)f, P, N, flags, v, coMax, tauMin,
+        faceFluxOne<ADJUST, true, false, HINT>(k, fv, sv, f, (size_t)f, P, N, flags, v, coMax, tauMin,
                                                       reinterpret_cast<const double*>(sg + L::oD), li, polKeep);
         __syncthreads();                                     // every thread is done with this stage before it is refilled
     }
@@ -950,7 +934,7 @@ __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceVie
     if (blockIdx.x == gridDim.x - 1) {
         const int f = nTiles * kTmaTile + (int)threadIdx.x;
         if (f < nIA)
-            faceFluxOne<ADJUST, false, false>(k, fv, sv, f, (size_t)f, __ldg(&fv.own[f]), __ldg(&fv.nei[f]), __ldg(&fv.flags[f]), __ldg(&fv.vtx[f]),
+            faceFluxOne<ADJUST>(k, fv, sv, f, (size_t)f, __ldg(&fv.own[f]), __ldg(&fv.nei[f]), __ldg(&fv.flags[f]), __ldg(&fv.vtx[f]),
                                               coMax, tauMin);
     }
     if (ADJUST) blockReduceCo<kTmaTile>(coMax, tauMin, sv.sc);
@@ -1040,71 +1024,6 @@ __device__ __forceinline__ void cellUpdateOne(const Consts& k, const SolverView&
     cellUpdateCore<W, RING>(k, sv, nI, c, a, b, enc, __ldg(&sv.V[c]), __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]));
 }
 
-// ---- TMA-staged cell update: the streamed inputs of a 256-cell tile (ELL rows, 11 old state fields, V, alphaQGD, hQGD) are
-// fetched by cp.async.bulk into a 2-stage shared-memory ring; the flux gathers start as soon as the tile has landed
-template <int W> struct CellStage {
-    static constexpr int kD = 14;     // rho,Ux,Uy,Uz,e,p,T | rhoUx,rhoUy,rhoUz,rhoE | V, aQGD, hQGD
-    static constexpr int kBytes = kTmaTile * (8 * kD + 4 * W);
-    static constexpr int oD = 0, oEnc = kTmaTile * 8 * kD;
-};
-template <int W>
-__device__ __forceinline__ void tmaIssueCells(const SolverView& sv, unsigned char* stage, unsigned long long* bar, int tile)
-{
-    using L = CellStage<W>;
-    const size_t c0 = (size_t)tile * kTmaTile, n = sv.nCells;
-    mbarExpectTx(bar, (unsigned)L::kBytes);
-    double* d = reinterpret_cast<double*>(stage + L::oD);
-#pragma unroll
-    for (int q = 0; q < 7; ++q) bulkLoad(d + q * kTmaTile, sv.S + q * n + c0, kTmaTile * 8, bar);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) bulkLoad(d + (7 + q) * kTmaTile, sv.S + (8 + q) * n + c0, kTmaTile * 8, bar);
-    bulkLoad(d + 11 * kTmaTile, sv.V + c0, kTmaTile * 8, bar);
-    bulkLoad(d + 12 * kTmaTile, sv.aQGD + c0, kTmaTile * 8, bar);
-    bulkLoad(d + 13 * kTmaTile, sv.hQGD + c0, kTmaTile * 8, bar);
-    int* e = reinterpret_cast<int*>(stage + L::oEnc);
-#pragma unroll
-    for (int j = 0; j < W; ++j) bulkLoad(e + j * kTmaTile, sv.cfEll + (size_t)j * n + c0, kTmaTile * 4, bar);
-}
-
-template <int W>
-__global__ void __launch_bounds__(kTmaTile, 3) k_cell_update_tma(Consts k, SolverView sv, int nI)
-{
-    using L = CellStage<W>;
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long bars[2];
-    const int nTiles = sv.nOwned / kTmaTile;
-    if (threadIdx.x == 0) {
-        mbarInit(&bars[0], 1); mbarInit(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    int tile = blockIdx.x;
-    if (threadIdx.x == 0 && tile < nTiles) tmaIssueCells<W>(sv, smem, &bars[0], tile);
-    for (int it = 0; tile < nTiles; ++it, tile += gridDim.x) {
-        const int st = it & 1;
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < nTiles) tmaIssueCells<W>(sv, smem + (st ^ 1) * L::kBytes, &bars[st ^ 1], next);
-        mbarWait(&bars[st], (unsigned)((it >> 1) & 1));
-        const double* d = reinterpret_cast<const double*>(smem + st * L::kBytes + L::oD);
-        const int* e = reinterpret_cast<const int*>(smem + st * L::kBytes + L::oEnc);
-        const int li = threadIdx.x;
-        RecA a; RecB b;
-        a.rho = d[li]; a.Ux = d[kTmaTile + li]; a.Uy = d[2 * kTmaTile + li]; a.Uz = d[3 * kTmaTile + li]; a.e = d[4 * kTmaTile + li];
-        a.p = d[5 * kTmaTile + li]; a.T = d[6 * kTmaTile + li]; a.H = 0.0;
-        b.rhoUx = d[7 * kTmaTile + li]; b.rhoUy = d[8 * kTmaTile + li]; b.rhoUz = d[9 * kTmaTile + li]; b.rhoE = d[10 * kTmaTile + li];
-        b.c = b.mu = b.alphaEff = b.aByC = 0.0;
-        int enc[W];
-#pragma unroll
-        for (int j = 0; j < W; ++j) enc[j] = e[j * kTmaTile + li];
-        cellUpdateCore<W, false>(k, sv, nI, tile * kTmaTile + li, a, b, enc, d[11 * kTmaTile + li], d[12 * kTmaTile + li], d[13 * kTmaTile + li]);
-        __syncthreads();
-    }
-    if (blockIdx.x == gridDim.x - 1) {                       // remainder (< one tile): plain loads
-        const int c = nTiles * kTmaTile + (int)threadIdx.x;
-        if (c < sv.nOwned) cellUpdateOne<W, false>(k, sv, nI, c);
-    }
-}
-
 template <int W>
 __global__ void __launch_bounds__(kBlock) k_cell_update(Consts k, SolverView sv, int nI)
 {
@@ -1183,7 +1102,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_face_cell_pipeline(Consts k, Fa
                 const int4 vc = v;
                 const int fn = f + BLOCK;
                 if (fn < f1) { P = __ldg(&fv.own[fn]); N = __ldg(&fv.nei[fn]); flags = __ldg(&fv.flags[fn]); v = __ldg(&fv.vtx[fn]); }
-                faceFluxOne<false, false>(k, fv, sv, f, (size_t)((unsigned)f % (unsigned)sv.ringSize), Pc, Nc, flagsCur, vc, coMax, tauMin);
+                faceFluxOne<false>(k, fv, sv, f, (size_t)((unsigned)f % (unsigned)sv.ringSize), Pc, Nc, flagsCur, vc, coMax, tauMin);
             }
             publish(pv.doneF, ch, pv.epoch);
         } else {
@@ -1207,6 +1126,13 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
     const double rhoOld = a.rho, pOld = init ? a.p : bs.pNew[b];
     double U[3] = {cA.Ux, cA.Uy, cA.Uz};
     if (fixU) { U[0] = bs.bvU[3 * (size_t)b]; U[1] = bs.bvU[3 * (size_t)b + 1]; U[2] = bs.bvU[3 * (size_t)b + 2]; }
+    else if (bs.bcU[b] == QGD_BC_SLIP) {        // [OF-v2312 basicSymmetryFvPatchField::evaluate] U_b = U_P - n (n . U_P)
+        const double ms = fv.magSf[f];
+        const double n[3] = {fv.Sf[f] / ms, fv.Sf[(size_t)fv.fs + f] / ms, fv.Sf[2 * (size_t)fv.fs + f] / ms};
+        const double un = n[0] * U[0] + n[1] * U[1] + n[2] * U[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) U[j] = U[j] - n[j] * un;
+    }
     double T, e;
     if (fixT) { T = bs.bvT[b]; e = thermoEs(k, T); }                     // fixedEnergy ; hePsiQGDThermo.C:93-105
     else { e = cA.e; T = thermoTHE(k, e, init ? cA.T : a.T); }           // gradientEnergy (gradient 0) ; :109-119
@@ -1373,7 +1299,7 @@ __global__ void __launch_bounds__(kBlock) k_gauss_gradU(FaceView fv, SolverView 
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= sv.nCells) return;
-    const size_t n = sv.nCells, nF = fv.nF;
+    const size_t n = sv.nCells;
     const double uc[3] = {sv.S[n + c], sv.S[2 * n + c], sv.S[3 * n + c]};
     double G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     forCellFacesS(sv, c, [&](int f, int side) {
@@ -1394,7 +1320,7 @@ __global__ void __launch_bounds__(kBlock) k_gauss_gradU(FaceView fv, SolverView 
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double Si = __ldg(&fv.Sf[(size_t)i * nF + f]);
+            const double Si = __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
 #pragma unroll
             for (int j = 0; j < 3; ++j) G[3 * i + j] += sgn * (Si * uf[j]);
         }
@@ -1439,7 +1365,7 @@ __global__ void __launch_bounds__(kBlock) k_face_diff(FaceView fv, SolverView sv
     const size_t n = sv.nCells, nF = fv.nF;
     double Sf[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sf[i] = fv.Sf[(size_t)i * nF + f];
+    for (int i = 0; i < 3; ++i) Sf[i] = fv.Sf[(size_t)i * fv.fs + f];
     const double ms = fv.magSf[f], nd = fv.ndC[f];
     double tMC[9], muf, alf;
     if (f < fv.nI) {
@@ -1534,10 +1460,10 @@ __global__ void __launch_bounds__(kBlock) k_face_sigma(FaceView fv, SolverView s
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= fv.nF) return;
-    const size_t n = sv.nCells, nF = fv.nF;
+    const size_t n = sv.nCells;
     double Sf[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sf[i] = fv.Sf[(size_t)i * nF + f];
+    for (int i = 0; i < 3; ++i) Sf[i] = fv.Sf[(size_t)i * fv.fs + f];
     const double ms = fv.magSf[f];
     double T[9], Uf[3];
     if (f < fv.nI) {
@@ -1642,68 +1568,42 @@ __global__ void __launch_bounds__(kBlock) k_cell_implC(Consts k, SolverView sv)
 static inline int nblk(long n, int b = kBlock) { return (int)((n + b - 1) / b); }
 
 namespace {
-struct FaceVariant { int block; void (*fn[4])(Consts, FaceView, SolverView); };     // [adjust + 2*geom]
-template <int BLOCK, int MINB> constexpr FaceVariant mkVariant()
-{
-    return {BLOCK, {k_face_flux<false, false, BLOCK, MINB>, k_face_flux<true, false, BLOCK, MINB>,
-                    k_face_flux<false, true, BLOCK, MINB>, k_face_flux<true, true, BLOCK, MINB>}};
-}
-const FaceVariant kFaceVariants[] = {mkVariant<256, 1>(), mkVariant<256, 2>(), mkVariant<128, 4>(), mkVariant<128, 5>(),
-                                     mkVariant<128, 6>(), mkVariant<64, 12>(), mkVariant<256, 3>()};
-int g_faceVariant = 1;
-int g_faceTma = 2;          // stages of the TMA ring; QGD_FACE_TMA=0 selects the register-prefetch kernel, 3 a 3-stage ring
-int g_faceHint = 3;         // QGD_FACE_L2HINT bit 0: face constants / fluxes evict_first, bit 1: cell / point gathers evict_last (2-stage ring only)
-template <bool ADJUST> void launchTma2(int hint, int grid, cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv)
+int g_faceTma = 1;          // QGD_FACE_TMA=0 selects the register-prefetch kernel instead of the TMA-staged one
+int g_faceHint = 3;         // QGD_FACE_L2HINT bit 0: face constants / fluxes evict_first, bit 1: cell / point gathers evict_last
+template <bool ADJUST> void launchTma(int hint, int grid, cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv)
 {
     const int sm = 2 * TmaStage<ADJUST>::kBytes;
     switch (hint & 3) {
-    case 1: k_face_flux_tma<ADJUST, 2, 1><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
-    case 2: k_face_flux_tma<ADJUST, 2, 2><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
-    case 3: k_face_flux_tma<ADJUST, 2, 3><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
-    default: k_face_flux_tma<ADJUST, 2, 0><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    case 1: k_face_flux_tma<ADJUST, 1><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    case 2: k_face_flux_tma<ADJUST, 2><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    case 3: k_face_flux_tma<ADJUST, 3><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
+    default: k_face_flux_tma<ADJUST, 0><<<grid, kTmaTile, sm, st>>>(c, fv, sv); break;
     }
 }
 template <bool ADJUST, int HINT> void tmaSmemAttr()
 {
-    cudaFuncSetAttribute(k_face_flux_tma<ADJUST, 2, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TmaStage<ADJUST>::kBytes);
+    cudaFuncSetAttribute(k_face_flux_tma<ADJUST, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TmaStage<ADJUST>::kBytes);
 }
-template <bool ADJUST, int NST> int tmaGridOf()
+template <bool ADJUST> int tmaGridOf()
 {
     int dev = 0, sms = 148, perSM = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_face_flux_tma<ADJUST, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, NST * TmaStage<ADJUST>::kBytes);
-    if (NST == 2) { tmaSmemAttr<ADJUST, 1>(); tmaSmemAttr<ADJUST, 2>(); tmaSmemAttr<ADJUST, 3>(); }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux_tma<ADJUST, NST>, kTmaTile, NST * TmaStage<ADJUST>::kBytes);
+    tmaSmemAttr<ADJUST, 0>(); tmaSmemAttr<ADJUST, 1>(); tmaSmemAttr<ADJUST, 2>(); tmaSmemAttr<ADJUST, 3>();
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux_tma<ADJUST, 3>, kTmaTile, 2 * TmaStage<ADJUST>::kBytes);
     return sms * (perSM < 1 ? 1 : perSM);
 }
 int faceTmaGrid(bool adjust)
 {
-    static int grid[2][2] = {{0, 0}, {0, 0}};
-    int& g = grid[g_faceTma == 3 ? 1 : 0][adjust ? 1 : 0];
-    if (!g) g = g_faceTma == 3 ? (adjust ? tmaGridOf<true, 3>() : tmaGridOf<false, 3>()) : (adjust ? tmaGridOf<true, 2>() : tmaGridOf<false, 2>());
+    static int grid[2] = {0, 0};
+    int& g = grid[adjust ? 1 : 0];
+    if (!g) g = adjust ? tmaGridOf<true>() : tmaGridOf<false>();
     return g;
 }
 }
 
-int g_cellTma = 0;          // QGD_CELL_TMA=1 opts into the TMA-staged cell update (measured slower: 1.53 vs 1.22 ms at 256^3)
-template <int W> int cellTmaGrid()
-{
-    static int g = 0;
-    if (!g) {
-        int dev = 0, sms = 148, perSM = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_cell_update_tma<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CellStage<W>::kBytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_cell_update_tma<W>, kTmaTile, 2 * CellStage<W>::kBytes);
-        g = sms * (perSM < 1 ? 1 : perSM);
-    }
-    return g;
-}
-void setCellTma(int on) { g_cellTma = on ? 1 : 0; }
-void setFaceTma(int on) { g_faceTma = on == 0 ? 0 : (on == 3 ? 3 : 2); }
+void setFaceTma(int on) { g_faceTma = on ? 1 : 0; }
 void setFaceL2Hint(int bits) { g_faceHint = bits & 3; }
-void setFaceVariant(int v) { if (v >= 0 && v < (int)(sizeof(kFaceVariants) / sizeof(kFaceVariants[0]))) g_faceVariant = v; }
 
 int faceKernelGrid()
 {
@@ -1711,8 +1611,7 @@ int faceKernelGrid()
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int perSM = 1;
-    const FaceVariant& fvn = kFaceVariants[g_faceVariant];
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fvn.fn[0], fvn.block, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_face_flux<false>, kBlock, 0);
     if (perSM < 1) perSM = 1;
     return sms * perSM;
 }
@@ -1760,26 +1659,31 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
     QGD_CUDA(cudaGetLastError());
 }
 
-// internal-face kernel of the two-kernel step form: leastSquares | TMA-staged | register-prefetch (+ GEOM) variants
+// the TMA-staged kernel needs one full tile; the SoA columns are 128-B aligned for any face count (FaceView::fs)
+bool faceKernelIsTma(const FaceView& fv) { return g_faceTma && fv.lsqW == 0 && fv.nIActive >= kTmaTile; }
+const char* faceKernelName(const FaceView& fv)
+{
+    if (fv.lsqW > 0) return "k_face_flux_lsq";
+    return faceKernelIsTma(fv) ? "k_face_flux_tma" : "k_face_flux";
+}
+int faceKernelL2Hint() { return g_faceHint; }
+
+// internal-face kernel of the two-kernel step form: leastSquares | TMA-staged | register-prefetch variants
 static void launchFaceKernel(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, bool adjust, int gridFaces)
 {
-    const int grid = std::min(gridFaces, nblk(fv.nIActive, kFaceVariants[g_faceVariant].block));
-    const FaceVariant& fvn = kFaceVariants[g_faceVariant];
     if (fv.lsqW > 0) {
         const int gl = std::min(2 * 148, nblk(fv.nIActive, 256));
         if (adjust) k_face_flux_lsq<true><<<gl, 256, 0, st>>>(c, fv, sv);
         else k_face_flux_lsq<false><<<gl, 256, 0, st>>>(c, fv, sv);
-    } else if (g_faceTma && !fv.allGeom && fv.nF % 2 == 0 && fv.nIActive >= kTmaTile) {
+    } else if (faceKernelIsTma(fv)) {
         const int gridT = std::min(faceTmaGrid(adjust), fv.nIActive / kTmaTile);
-        if (g_faceTma == 3) {
-            if (adjust) k_face_flux_tma<true, 3><<<gridT, kTmaTile, 3 * TmaStage<true>::kBytes, st>>>(c, fv, sv);
-            else k_face_flux_tma<false, 3><<<gridT, kTmaTile, 3 * TmaStage<false>::kBytes, st>>>(c, fv, sv);
-        } else {
-            if (adjust) launchTma2<true>(g_faceHint, gridT, st, c, fv, sv);
-            else launchTma2<false>(g_faceHint, gridT, st, c, fv, sv);
-        }
-    } else
-        fvn.fn[(adjust ? 1 : 0) + (fv.allGeom ? 2 : 0)]<<<grid, fvn.block, 0, st>>>(c, fv, sv);
+        if (adjust) launchTma<true>(g_faceHint, gridT, st, c, fv, sv);
+        else launchTma<false>(g_faceHint, gridT, st, c, fv, sv);
+    } else {
+        const int grid = std::min(gridFaces, nblk(fv.nIActive, kBlock));
+        if (adjust) k_face_flux<true><<<grid, kBlock, 0, st>>>(c, fv, sv);
+        else k_face_flux<false><<<grid, kBlock, 0, st>>>(c, fv, sv);
+    }
 }
 
 namespace {
@@ -1872,11 +1776,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         k_dt<<<1, 1, 0, st>>>(sv.sc, nullptr); ++n;
         if (c.varSc) { k_varsc<false><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, sv.S + 5 * (size_t)sv.nCells); ++n; }
         if (ev) cudaEventRecord(ev[4], st);
-        if (g_cellTma && sv.nCells % 4 == 0 && sv.nOwned >= kTmaTile && (sv.cfEllW == 4 || sv.cfEllW == 6)) {
-            const int tiles = sv.nOwned / kTmaTile;
-            if (sv.cfEllW == 4) k_cell_update_tma<4><<<std::min(cellTmaGrid<4>(), tiles), kTmaTile, 2 * CellStage<4>::kBytes, st>>>(c, sv, fv.nI);
-            else k_cell_update_tma<6><<<std::min(cellTmaGrid<6>(), tiles), kTmaTile, 2 * CellStage<6>::kBytes, st>>>(c, sv, fv.nI);
-        } else if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
+        if (sv.cfEllW == 4) k_cell_update<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
         else if (sv.cfEllW == 6) k_cell_update<6><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
         else k_cell_update<8><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv, fv.nI);
         ++n;

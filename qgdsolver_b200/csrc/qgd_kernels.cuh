@@ -26,6 +26,8 @@ struct Consts {
 
 struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     int nI, nF, nB;
+    int fs;                  // stride of the per-face SoA arrays G[9] and Sf[3] (nF rounded up to 16: every column 128-B aligned, so the
+                             // cp.async.bulk tile copies of k_face_flux_tma are legal for any face count)
     int nIActive;            // internal faces whose owner is an owned cell (device order puts the others last)
     int zeroDivCmpt;         // 2D: out-of-plane component of Div(tensor) stays 0 (GaussVolPointBase2D.C:447-485), else -1
     const int* own;          // nF
@@ -39,12 +41,8 @@ struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     const double* dC;        // nF  deltaCoeffs
     const double* ndC;       // nF  nonOrthDeltaCoeffs
     const double* G;         // SoA 9*nF
-    const double* X;         // SoA 3*nPoints point coordinates (FF_GEOM faces)
-    const double* Cc;        // SoA 3*nCells  cell centres      (FF_GEOM faces)
-    int nPts, nCls;
     int lsqW;                // leastSquares: ELL width, cells [lsqW][nI] and coefficient vectors [lsqW][3][nI] (device face order)
     const int* lsqCells; const double* lsqCoef;
-    int allGeom;             // every active internal face carries FF_GEOM: the step uses the geometry-rebuilding face kernel
     const double* halfDist;  // nB
     const int* bKind;        // nB patch kind per boundary face
     const int* perm;         // nF device face -> polyMesh face (operator outputs are written in polyMesh order)
@@ -163,10 +161,10 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
                         const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust);
 int faceKernelGrid();
 int pipelineKernelGrid(int cfEllW);
-void setFaceVariant(int v);
-void setCellTma(int on);      // env QGD_CELL_TMA
 void setFaceL2Hint(int bits); // env QGD_FACE_L2HINT: bit 0 = streamed constants / fluxes evict_first, bit 1 = state gathers evict_last
-void setFaceTma(int on);      // env QGD_FACE_TMA: TMA-staged face kernel (default) vs register-prefetch kernel   // tuning knob (env QGD_FACE_VARIANT): block size / register cap of k_face_flux
+void setFaceTma(int on);      // env QGD_FACE_TMA: TMA-staged face kernel (default) vs register-prefetch kernel
+const char* faceKernelName(const FaceView& fv);   // the internal-face kernel launchStep selects for this mesh
+int faceKernelL2Hint();
 
 } // namespace qgd
 
@@ -177,7 +175,6 @@ struct qgd_fvsc {
     qgd::DevBuf<int4> vtx;
     qgd::DevBuf<int> flags;
     qgd::DevBuf<double> G, halfDist;
-    bool allGeom = false;
     bool lsq = false;              // leastSquares scheme
     int lsqW = 0;
     qgd::DevBuf<int> lsqCells;
@@ -188,12 +185,12 @@ struct qgd_fvsc {
     {
         const qgd_mesh& m = *mesh;
         qgd::FaceView v;
-        v.nI = m.h.nInternal; v.nF = m.h.nFaces; v.nB = m.h.nBnd;
+        v.nI = m.h.nInternal; v.nF = m.h.nFaces; v.nB = m.h.nBnd; v.fs = m.faceStride;
         v.nIActive = m.nIActive;
         v.zeroDivCmpt = -1;
         if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
         v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
-        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.X = m.ptsSoA.p; v.Cc = m.ctrSoA.p; v.nPts = m.h.nPoints; v.nCls = m.h.nCells; v.allGeom = allGeom ? 1 : 0; v.lsqW = lsq ? lsqW : 0; v.lsqCells = lsqCells.p; v.lsqCoef = lsqCoef.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
+        v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.lsqW = lsq ? lsqW : 0; v.lsqCells = lsqCells.p; v.lsqCoef = lsqCoef.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
         v.perm = m.facePermDev.p;
         return v;
     }

@@ -167,13 +167,12 @@ struct FaceGeo { double g1[3], g2[3], gp[3], Sf[3]; };
 __device__ __forceinline__ FaceGeo loadGeo(const FaceView& fv, int f)
 {
     FaceGeo o;
-    const size_t nF = fv.nF;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        o.g1[i] = __ldg(&fv.G[(size_t)(0 + i) * nF + f]);
-        o.g2[i] = __ldg(&fv.G[(size_t)(3 + i) * nF + f]);
-        o.gp[i] = __ldg(&fv.G[(size_t)(6 + i) * nF + f]);
-        o.Sf[i] = __ldg(&fv.Sf[(size_t)i * nF + f]);
+        o.g1[i] = __ldg(&fv.G[(size_t)(0 + i) * fv.fs + f]);
+        o.g2[i] = __ldg(&fv.G[(size_t)(3 + i) * fv.fs + f]);
+        o.gp[i] = __ldg(&fv.G[(size_t)(6 + i) * fv.fs + f]);
+        o.Sf[i] = __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
     }
     return o;
 }
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(kB) k_qhd_cell_pre(QhdConsts k, FaceView fv, Q
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= q.nCells) return;
-    const size_t n = q.nCells, nF = fv.nF, nB = fv.nB;
+    const size_t n = q.nCells, nB = fv.nB;
     const double uc[3] = {q.Q[c], q.Q[n + c], q.Q[2 * n + c]};
     double s0 = 0.0, G[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     forCellFaces(q, c, [&](int f, int side) {
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(kB) k_qhd_cell_pre(QhdConsts k, FaceView fv, Q
         s0 += sgn * q.F0[f];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const double Si = __ldg(&fv.Sf[(size_t)i * nF + f]);
+            const double Si = __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
 #pragma unroll
             for (int j = 0; j < 3; ++j) G[3 * i + j] += sgn * (Si * uf[j]);
         }

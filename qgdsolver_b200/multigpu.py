@@ -84,26 +84,26 @@ def bench(args, rank: int, world: int, local: int):
     kt = s.kernel_times()
     s.profile(False)
     launches = s.launch_count() - l0
-    # ---- end to end through the C-ABI with pinned HOST state buffers: every rank uploads its sub-domain state, steps once
-    # (halo exchange included) and downloads it again, every step
+    # ---- end to end through the C-ABI with pinned HOST buffers: every rank uploads U, T, p of its sub-domain (halo included),
+    # the state is re-created from them (createFields.H semantics), one step with the NCCL halo exchange runs, U, T, p come back
     nL = sub.mesh.n_cells
-    names = ("rho", "U", "e", "p", "T", "rhoU", "rhoE", "mu")
-    pinned = {k: torch.empty((nL, 3) if k in ("U", "rhoU") else (nL,), dtype=torch.float64, pin_memory=True) for k in names}
-    st = {k: v.numpy() for k, v in pinned.items()}
-    s.step_host(0, None, st)
+    pinned = {k: torch.empty((nL, 3) if k == "U" else (nL,), dtype=torch.float64, pin_memory=True) for k in ("U", "T", "p")}
+    fl = {k: v.numpy() for k, v in pinned.items()}
+    s.step_fields_host(0, None, fl)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(3):
-        s.step_host(1, st, st)
+        s.step_fields_host(1, fl, fl)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        s.step_host(1, st, st)
+        s.step_fields_host(1, fl, fl)
     torch.cuda.synchronize()
     te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device="cuda")
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    tb = torch.tensor([12.0 * 8 * nL], dtype=torch.float64, device="cuda")
+    tb = torch.tensor([5.0 * 8 * nL], dtype=torch.float64, device="cuda")
     dist.all_reduce(tb, op=dist.ReduceOp.SUM)
     e2e_s, e2e_bytes = float(te.item()), int(tb.item())
+    kname, l2hint = s.face_kernel()
     if rank == 0:
         clocks = sampler.stop()
         ms_step = ms / args.steps
@@ -125,9 +125,10 @@ def bench(args, rank: int, world: int, local: int):
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": mesh.n_cells / e2e_s / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": e2e_bytes,
                         "d2h_bytes_per_step": e2e_bytes, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                        "api": "qgd_qgdfoam_step_host on every rank: sub-domain cell state (12 doubles/cell, halo included) H2D + "
-                               "1 step with NCCL halo exchange + D2H per call, pinned host buffers; max over ranks"},
-                "roofline": {"bound": "hbm", "kernel": "k_face_flux (rank 0)", "achieved": ab_face_rank / (face_ms * 1e-3) / 1e9,
+                        "api": "qgd_qgdfoam_step_fields_host on every rank: U, T, p of the sub-domain (5 doubles/cell, halo included) "
+                               "H2D, state re-created as createFields.H does, 1 step with NCCL halo exchange, U, T, p D2H per call, "
+                               "pinned host buffers; max over ranks"},
+                "roofline": {"bound": "hbm", "kernel": f"{kname} (rank 0)", "l2hint": l2hint, "achieved": ab_face_rank / (face_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": ab_face_rank / (face_ms * 1e-3) / 1e9 / peak, "traffic": None,
                              "peak_source": src, "avg_launch_ms": face_ms,
                              "step": {"alg_bytes_global": ab["total"], "achieved_aggregate": ab["total"] / (ms_step * 1e-3) / 1e9,

@@ -6,7 +6,7 @@ import numpy as np
 from qgdsolver_b200 import polymesh as pm
 
 FV, ZG, FG, QF = 0, 1, 2, 3   # bc kinds (fixedValue, zeroGradient, fixedGradient, qgdFlux)
-SLIP = 5                      # oracle only so far (OR_BC_SLIP): slip / symmetryPlane velocity
+SLIP = 6                      # QGD_BC_SLIP / OR_BC_SLIP: slip / symmetryPlane velocity
 
 GAS = dict(R=1.0, Cp=3.5, Hf=0.0, Tref=0.0, Hsref=0.0, mu=1.0e-3, Pr=0.71, ScQGD=1.0, PrQGD=1.0)
 GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5, Pr=0.71, ScQGD=0.7, PrQGD=0.9)
@@ -276,7 +276,7 @@ def qhd_cavity(n=(16, 16), dims=2, perturb=0.0, model="constTau", p_bc="qhdflux"
 def case_forward_step(n=40, co=0.05, **opts):
     """BASELINE configs[1] in miniature: Mach-3 wind tunnel with a forward-facing step (Woodward & Colella set-up: rho = 1.4,
     p = 1, u = 3, gamma = 1.4), inviscid, QGD regularisation only.  Inlet fixedValue, outlet zeroGradient, walls and step:
-    slip velocity (oracle only so far), zeroGradient T and p.  co: acoustic Courant number (|U|+c) dt / h of the free stream; the
+    slip velocity, zeroGradient T and p.  co: acoustic Courant number (|U|+c) dt / h of the free stream; the
     explicit QGD step needs about 0.05 here (0.2 blows up at the impulsive start: tau |U|^2 acts as a viscosity ~ 4.5 h)."""
     mesh = pm.forward_step(n)
     gas = dict(GAS, mu=0.0, Pr=1.0)

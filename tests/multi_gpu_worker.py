@@ -20,6 +20,24 @@ rank, world = dist.get_rank(), dist.get_world_size()
 api.init(local)
 multigpu.init_comm(rank, world)
 
+LOG = None
+if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+    LOG = open(os.path.join(ROOT, "gpurun_out", f"multi_parity_n{world}.log"), "w")
+
+
+def say(msg):
+    print(msg, flush=True)
+    if LOG:
+        LOG.write(msg + "\n"); LOG.flush()
+
+
+def slip_case():
+    c = cases.case_hex3d(n=(12, 10, 8), perturb=0.2, bcs="zg")
+    for i in range(1, len(c.mesh.patches), 2):
+        c.bcU[i] = cases.SLIP
+    return c
+
+
 CASES = {
     # coupled-face rule off: the decomposed run must reproduce the serial semantics on any mesh
     "perturbed_mixed_serialrule": (lambda: cases.case_hex3d(n=(12, 10, 8), perturb=0.2, bcs="mixed"), False),
@@ -28,17 +46,34 @@ CASES = {
     # reference processor-patch rule (hQGDf = |d| on coupled faces): identical to serial on uniform meshes
     "uniform_zg_procrule": (lambda: cases.case_hex3d(n=(12, 10, 8), bcs="mixed"), True),
     "uniform_adjust_procrule": (lambda: cases.case_hex3d(n=(12, 10, 8), bcs="fixed", adjust_time_step=True, dt=1e-3, max_co=0.1, c_tau=0.3), True),
+    # polyhedral cells (14 faces, CSR tails), slip walls, a model with a per-cell ScQGD sensor
+    "truncoct_mixed_serialrule": (lambda: cases.case_truncoct(n=(6, 5, 5), bcs="mixed"), False),
+    "slip_perturbed_serialrule": (slip_case, False),
+    "varSc7_fixed_serialrule": (lambda: cases.case_hex3d(n=(12, 10, 8), perturb=0.1, bcs="fixed", model="varScModel7",
+                                                         varsc=dict(cSc1=3.0, minSc=0.02, maxSc=0.4)), False),
+    # boundary kernels forked onto the side stream in multi-GPU mode
+    "perturbed_mixed_fork2": (lambda: cases.case_hex3d(n=(12, 10, 8), perturb=0.2, bcs="mixed"), False),
+    # 64^3: sub-domains of many TMA tiles per CTA, halo lists of thousands of cells, 100 steps
+    "hex64_mixed_procrule": (lambda: cases._with_bcs(cases.pm.hex_box(64, 64, 64), "mixed", cases.GAS, 8e-4), True),
 }
+if os.environ.get("QGD_MULTI_CASES"):
+    CASES = {k: v for k, v in CASES.items() if k in os.environ["QGD_MULTI_CASES"].split(",")}
 ok = True
 for name, (mk, proc_rule) in CASES.items():
     c = mk()
+    nsteps = 100 if name.startswith("hex64") else 50
+    if name.endswith("fork2"):
+        os.environ["QGD_BND_FORK"] = "2"
+    else:
+        os.environ.pop("QGD_BND_FORK", None)
     cell_rank = decompose.geometric_split(c.mesh, world)
     sub = decompose.extended_submeshes(c.mesh, cell_rank, ranks=[rank])[0]
     if not proc_rule:
         sub.coupled_face[:] = 0
     # same construction as multigpu.make_rank_solver, with the (possibly cleared) coupled flags
     dm = api.Mesh(sub.mesh, n_owned=sub.n_owned, coupled_face=sub.coupled_face)
-    s = api.QGDFoam(dm, fvsc_scheme=c.scheme, delta_t=c.dt, **c.gas, **c.opts)
+    s = api.QGDFoam(dm, fvsc_scheme=c.scheme, qgd_coeffs=c.model, delta_t=c.dt, varsc_cSc1=c.varsc["cSc1"], varsc_minSc=c.varsc["minSc"],
+                    varsc_maxSc=c.varsc["maxSc"], **c.gas, **c.opts)
     nI_g = c.mesh.n_internal
     bf_g = sub.face_global[sub.mesh.n_internal:]
     phys = bf_g >= nI_g
@@ -49,15 +84,15 @@ for name, (mk, proc_rule) in CASES.items():
     cg = sub.cell_global
     s.init_fields(c.U0[cg], c.T0[cg], c.p0[cg], None)
     s.set_halo(sub)
-    s.step(50)
+    s.step(nsteps)
     res = {f: s.get(f)[:sub.n_owned] for f in ("rho", "rhoU", "rhoE", "e", "p")}
     np.savez(f"/tmp/qgd_multi_{name}_{rank}.npz", cells=cg[:sub.n_owned], dt=s.scalars()["deltaT"], **res)
     api.synchronize()
     dist.barrier()
     if rank == 0:
         import oracle as O
-        o = c.make_oracle(O)
-        c.oracle_step(o, 50)
+        o = c.make_oracle(O, n_threads=os.cpu_count() or 1)
+        c.oracle_step(o, nsteps)
         for f in ("rho", "rhoU", "rhoE", "e", "p"):
             ref = o.get(f)
             got = np.zeros_like(ref)
@@ -68,14 +103,14 @@ for name, (mk, proc_rule) in CASES.items():
             status = "ok" if err < 1e-10 else "FAIL"
             if status == "FAIL":
                 ok = False
-            print(f"MULTI {name} {f} relLinf={err:.3e} {status}", flush=True)
+            say(f"MULTI n={world} {name} steps={nsteps} face_kernel={s.face_kernel()[0]} {f} relLinf={err:.3e} {status}")
         if c.opts["adjust_time_step"]:
             z = np.load(f"/tmp/qgd_multi_{name}_0.npz")
             derr = abs(float(z["dt"]) - o.deltaT()) / o.deltaT()
-            print(f"MULTI {name} deltaT rel err={derr:.3e} {'ok' if derr < 1e-10 else 'FAIL'}", flush=True)
+            say(f"MULTI n={world} {name} deltaT rel err={derr:.3e} {'ok' if derr < 1e-10 else 'FAIL'}")
             ok = ok and derr < 1e-10
     dist.barrier()
 if rank == 0:
-    print("MULTI_ALL_OK" if ok else "MULTI_FAILED", flush=True)
+    say("MULTI_ALL_OK" if ok else "MULTI_FAILED")
 api.comm_finalize()
 dist.destroy_process_group()

@@ -19,7 +19,7 @@ def test_reference_arm_prints_the_contract_line():
     assert j["metric"] == "cell-updates/s per QGDFoam step" and j["dtype"] == "f64" and j["vs_baseline"] is None
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
-    assert "workload" in j["config"] and "model" not in j["config"]
+    assert "workload" in j["config"] and "model" not in j["config"] and j["config"]["same_workload_as_product_arm"] is False
 
 
 def test_algorithmic_bytes_follow_the_survey_model():
@@ -65,6 +65,8 @@ def test_product_arm_assembles_its_json_line_with_a_stand_in_device(monkeypatch,
         def kernel_times(self): return dict(points_ms=0.65 * 4, face_ms=2.2 * 4, cell_ms=1.2 * 4, steps=4)
         def get_pipeline(self): return dict(mode=0, chunk_cells=512, lag=0, ring_slots=0, n_chunks=0, grid=0)
         def step_host(self, n, a, b): self.n += n
+        def step_fields_host(self, n, a, b): self.n += n
+        def face_kernel(self): return ("k_face_flux_tma", 3)
     monkeypatch.setattr(api, "Mesh", FakeMesh)
     monkeypatch.setattr(api, "QGDFoam", FakeSolver)
     monkeypatch.setattr(api, "init", lambda d: None)
@@ -75,7 +77,7 @@ def test_product_arm_assembles_its_json_line_with_a_stand_in_device(monkeypatch,
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     real_empty = torch.empty
     monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **k: real_empty(*a, **k))
-    args = argparse.Namespace(gpus=1, steps=4, warmup=3, size=8, ref_size=8, cpu_budget=0.05, no_cpu_baseline=False)
+    args = argparse.Namespace(gpus=1, steps=4, warmup=3, size=8, ref_size=0, cpu_budget=0.05, no_cpu_baseline=False, e2e_full_state=True)
     bench.run_product(args)
     out = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(out) == 1
@@ -88,7 +90,8 @@ def test_product_arm_assembles_its_json_line_with_a_stand_in_device(monkeypatch,
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert r["kernel"] == "k_face_flux_tma" and r["l2hint"] == 3 and r["traffic"] is None      # 8^3 is not the captured 256^3 kernel
     assert abs(r["step"]["frac"] - r["step"]["achieved"] / r["peak"]) < 1e-12
-    assert j["e2e"]["h2d_bytes_per_step"] == 12 * 8 * 512 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] > 0
+    assert j["e2e"]["h2d_bytes_per_step"] == 5 * 8 * 512 and j["e2e"]["full_state"]["bytes_each_way_per_step"] == 12 * 8 * 512 and\
+        "8^3 hex box" in j["cpu_baseline"]["sample"] and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] > 0
     assert "workload" in j["config"] and j["vs_baseline"] is None
     # the extra polyhedral line (configs[4] shape) through the same stand-in device
     args.poly_n = 5
@@ -107,4 +110,4 @@ def test_product_arm_assembles_its_json_line_with_a_stand_in_device(monkeypatch,
                 json.dump({"n_cells": 512, "kernel": "k_face_flux_tma<0, 2>", "dram_bytes_per_launch": 123.0, "l2hint": hint, "source": "x"}, f)
             bench.run_product(args)
             r = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][0])["roofline"]
-            assert r["traffic"] == expect and (r["traffic_note"] is None) == (expect is not None)
+            assert r["traffic"] == expect and (r["traffic_note"] == "x") == (expect is not None)

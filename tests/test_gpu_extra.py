@@ -1,6 +1,5 @@
-"""GPU parity cases written after the round's GPU budget was spent: they have never run on a device.  They are marked
-xfail(strict=False) so that an unexpected mismatch does not hide the verified suite behind `-x`; an XPASS at the
-round-end run means the marker can simply be dropped.  (File name sorts last on purpose.)"""
+"""More GPU parity cases against the CPU oracle: active qgdFlux gradients, runcase end to end, the leastSquares degenerate
+face set, the truncated-octahedron polyhedral mesh (CSR tails on the default path), the stepwise and the decomposed PCG."""
 import numpy as np
 import pytest
 
@@ -8,7 +7,6 @@ import cases
 
 pytestmark = pytest.mark.gpu
 TOL_STEP = 1e-10
-NOT_RUN = pytest.mark.xfail(strict=False, reason="written without GPU access (budget exhausted); first run is the driver's")
 
 
 def _open_qgdflux_case(**kw):
@@ -19,7 +17,6 @@ def _open_qgdflux_case(**kw):
     return c
 
 
-@NOT_RUN
 @pytest.mark.parametrize("kw", [dict(), dict(implicit=True), dict(model="varScModel6"), dict(scheme="reduced")],
                          ids=["explicit", "implicit", "varSc6", "reduced"])
 def test_active_qgdflux_gradient_matches_oracle(qgd, oracle_mod, kw):
@@ -39,7 +36,6 @@ def test_active_qgdflux_gradient_matches_oracle(qgd, oracle_mod, kw):
         assert float(np.abs(gb - ob).max()) / scale < TOL_STEP, f"boundary {f}"
 
 
-@NOT_RUN
 def test_runcase_end_to_end_writes_the_oracle_solution(qgd, oracle_mod, tmp_path):
     """python -m qgdsolver_b200.runcase on a Sod-tube case directory: dictionaries -> device solver -> time directories;
     the written 0.02/rho, p, U equal the oracle run from the same set-up."""
@@ -59,7 +55,6 @@ def test_runcase_end_to_end_writes_the_oracle_solution(qgd, oracle_mod, tmp_path
         assert float(np.abs(f.internal - ref).max()) / float(np.abs(ref).max()) < TOL_STEP, name
 
 
-@NOT_RUN
 def test_least_squares_degenerate_face_set_on_device(qgd, oracle_mod):
     """qgd_mesh_set_degenerate_stencil_faces (faceSet degenerateStencilFaces, leastSquaresStencil.C:63-132): operator and
     60 solver steps against the oracle with the same forced faces."""
@@ -88,7 +83,6 @@ def test_least_squares_degenerate_face_set_on_device(qgd, oracle_mod):
         assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < TOL_STEP, f
 
 
-@NOT_RUN
 @pytest.mark.parametrize("bcs", ["mixed", "fixed"])
 def test_truncated_octahedron_mesh_on_device(qgd, oracle_mod, bcs):
     """14 faces per cell (8 hexagons -> `other` faces, 6 squares): fvsc operators and 60 QGDFoam steps against the oracle; the
@@ -113,7 +107,6 @@ def test_truncated_octahedron_mesh_on_device(qgd, oracle_mod, bcs):
         assert float(np.abs(a - b).max()) / float(np.abs(b).max()) < TOL_STEP, f
 
 
-@NOT_RUN
 @pytest.mark.parametrize("precond", ["diagonal", "none"])
 def test_stepwise_pcg_matches_oracle_and_the_persistent_kernel(qgd, oracle_mod, precond):
     """qgd_pcg_solve_stepwise (one kernel per phase, the building block of the multi-GPU solver) on one GPU: same solution and
@@ -142,7 +135,6 @@ def test_stepwise_pcg_matches_oracle_and_the_persistent_kernel(qgd, oracle_mod, 
     assert it5 == 5
 
 
-@NOT_RUN
 @pytest.mark.parametrize("n", [2, 4])
 def test_decomposed_pcg_matches_oracle(n):
     """qgd_pcg_solve_multi (stepwise PCG + NCCL exchange / all-reduce) on n GPUs against the oracle's decomposed-run solver
@@ -153,13 +145,11 @@ def test_decomposed_pcg_matches_oracle(n):
     import torch
     if torch.cuda.device_count() < n:
         pytest.skip(f"needs {n} GPUs")
-    if os.environ.get("QGD_RUN_UNVERIFIED_MULTI") != "1":
-        pytest.skip("first multi-GPU run of new NCCL code is started by hand (QGD_RUN_UNVERIFIED_MULTI=1, scripts/r02_multi.sh): an "
-                    "exchange-list mistake would block in ncclRecv rather than fail")
+    # an exchange-list mistake would block in ncclRecv rather than fail: the worker runs under a hard timeout
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
                         "--master-addr", "127.0.0.1", "--master-port", str(29640 + n), os.path.join(root, "tests", "multi_gpu_pcg_worker.py")],
-                       capture_output=True, text=True, timeout=180)
+                       capture_output=True, text=True, timeout=120)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stderr[-4000:]
     assert "MPCG_ALL_OK" in r.stdout

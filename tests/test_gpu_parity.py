@@ -113,7 +113,23 @@ STEP_CASES = {
     # aspect ratio 10: det(G) < 1 on the x-normal faces -> degenerate-stencil branch (extendedFaceStencilCalculateWeights.C:136-140)
     "2d_leastSquares_degenerate": lambda: cases.case_2d(n=(6, 60), bcs="mixed", scheme="leastSquares"),
     "2d_leastSquaresOpt_degenerate": lambda: cases.case_2d(n=(6, 60), bcs="mixed", scheme="leastSquaresOpt"),
+    # slip / symmetryPlane velocity [OF-v2312 basicSymmetry]: U_b = U_P - n (n . U_P) on skewed boundary faces
+    "hex_slip_perturbed": lambda: _slip_case(cases.case_hex3d(perturb=0.2, bcs="zg")),
+    "prism_slip_model1n": lambda: _slip_case(cases.case_prism(bcs="zg", model="constScPrModel1n")),
+    "2d_slip_adjust": lambda: _slip_case(cases.case_2d(perturb=0.2, bcs="zg", adjust_time_step=True, max_co=0.1)),
+    "poly_slip_reduced": lambda: _slip_case(cases.case_poly(bcs="zg", scheme="reduced")),
+    # BASELINE configs[1] in miniature: Mach-3 forward-facing step, slip walls + step (polymesh.forward_step)
+    "forward_step_30": lambda: cases.case_forward_step(n=30),
 }
+
+
+def _slip_case(c):
+    """every second patch becomes a slip wall (p: qgdFlux on one of them), the others keep zeroGradient"""
+    for i in range(1, len(c.mesh.patches), 2):
+        if c.mesh.patches[i].kind != 1:
+            c.bcU[i] = cases.SLIP
+    c.bcP[1] = cases.QF if c.mesh.patches[1].kind != 1 else c.bcP[1]
+    return c
 
 
 @pytest.mark.parametrize("name", list(STEP_CASES))
@@ -238,6 +254,95 @@ def test_step_host_equals_device_resident_loop(qgd):
     for f in ("rho", "rhoU", "rhoE", "e", "p"):
         assert rel_linf(s2.get(f), s1.get(f)) < 1e-12
         assert rel_linf(st[f].reshape(s1.get(f).shape), s1.get(f)) < 1e-12
+
+
+def test_step_fields_host_is_the_reference_restart(qgd, oracle_mod):
+    """qgd_qgdfoam_step_fields_host: U, T, p in -> one step -> U, T, p (+ conserved) out, every step.  Reference semantics:
+    a run that is written and restarted each step (createFields.H:3-109 re-creates the state from the three fields), so
+    the comparison is an oracle re-initialised from the oracle's own U, T, p before every step."""
+    c = cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel1n")
+    s = c.make_solver(qgd)
+    n = c.mesh.n_cells
+    fl = dict(U=np.array(c.U0, float), T=np.array(c.T0, float), p=np.array(c.p0, float), rho=np.zeros(n), rhoU=np.zeros((n, 3)), rhoE=np.zeros(n))
+    Uo, To, po = c.U0, c.T0, c.p0
+    for _ in range(6):
+        s.step_fields_host(1, fl, fl)
+        r = cases.Case(c.mesh, np.ascontiguousarray(Uo), To, po, c.bcU, c.bcT, c.bcP, c.bvU, c.bvT, c.bvP, gas=c.gas, dt=c.dt, model=c.model)
+        o = r.make_oracle(oracle_mod)
+        r.oracle_step(o, 1)
+        Uo, To, po = o.get("U"), o.get("T"), o.get("p")
+        for f, ref in (("U", Uo), ("T", To), ("p", po), ("rho", o.get("rho")), ("rhoU", o.get("rhoU")), ("rhoE", o.get("rhoE"))):
+            assert rel_linf(fl[f], ref) < 1e-12, f
+    # in = None keeps the device state: equals the device-resident loop
+    s2 = c.make_solver(qgd)
+    s2.step_fields_host(0, dict(U=c.U0, T=c.T0, p=c.p0), None)
+    s2.step_fields_host(5, None, fl)
+    s3 = c.make_solver(qgd)
+    s3.step(5)
+    assert np.array_equal(fl["rho"], s3.get("rho")) and np.array_equal(fl["p"], s3.get("p"))
+
+
+def test_multi_tile_tma_ring_matches_oracle_64cubed(qgd, oracle_mod):
+    """64^3 hex box x 100 steps against the oracle: 786 432 internal faces = 3024 tiles of 256, so every CTA of the persistent
+    TMA face kernel loops ~10 times over its 2-stage ring (mbarrier phase flips, stage refills) - the small cases above
+    never leave the first iteration."""
+    import os
+    mesh = cases.pm.hex_box(64, 64, 64)
+    c = cases._with_bcs(mesh, "mixed", cases.GAS, 2e-4 * 4)
+    o = c.make_oracle(oracle_mod, n_threads=os.cpu_count() or 1)
+    s = c.make_solver(qgd)
+    assert s.face_kernel()[0] == "k_face_flux_tma"
+    c.oracle_step(o, 100)
+    s.step(100)
+    for f in ("rho", "rhoU", "rhoE", "U", "e", "p", "T"):
+        assert rel_linf(s.get(f), o.get(f)) < TOL_STEP, f
+
+
+def test_tma_face_kernel_on_odd_face_counts(qgd):
+    """Face counts that are not a multiple of 2 used to fall back to the register-prefetch kernel (the SoA columns of G / Sf
+    were then 8-byte aligned only); with the padded column stride the TMA kernel runs on any mesh and stays bit-identical
+    to the plain-load kernel."""
+    import os
+    import subprocess
+    import sys
+    mesh = cases.pm.hex_box(33, 17, 9)                  # 129x129x256-like parity: odd number of faces
+    assert mesh.n_faces % 2 == 1
+    c = cases._with_bcs(mesh, "mixed", cases.GAS, 2e-4)
+    s = c.make_solver(qgd)
+    assert s.face_kernel() == ("k_face_flux_tma", 3)
+    s.step(20)
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np, cases; from qgdsolver_b200 import api; api.init(0);"
+            "c = cases._with_bcs(cases.pm.hex_box(33, 17, 9), 'mixed', cases.GAS, 2e-4); s = c.make_solver(api);"
+            "assert s.face_kernel()[0] == 'k_face_flux'; s.step(20); np.save(sys.argv[1], np.stack([s.get('rho'), s.get('rhoE')]))")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join("/tmp", "qgd_odd_faces.npy")
+    r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "tests")), out], env=dict(os.environ, QGD_FACE_TMA="0"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = np.load(out)
+    assert np.array_equal(ref[0], s.get("rho")) and np.array_equal(ref[1], s.get("rhoE"))
+
+
+def test_forward_step_at_full_size_matches_oracle(qgd, oracle_mod):
+    """BASELINE configs[1]: Mach-3 forward-facing step, n = 640 -> 1 032 192 hex cells (1920 x 640 minus the step), slip walls,
+    explicit, 100 steps from the impulsive start against the oracle (all host threads)."""
+    import os
+    c = cases.case_forward_step(n=640)
+    assert c.mesh.n_cells == 1920 * 640 - 1536 * 128
+    o = c.make_oracle(oracle_mod, n_threads=os.cpu_count() or 1)
+    s = c.make_solver(qgd)
+    c.oracle_step(o, 100)
+    s.step(100)
+    for f in ("rho", "rhoU", "rhoE", "p"):
+        assert rel_linf(s.get(f), o.get(f)) < TOL_STEP, f
+    assert float(np.abs(o.get("p") - 1.0).max()) > 1.0              # the shock in front of the step has formed
+
+
+def test_slip_is_refused_with_implicit_diffusion(qgd):
+    c = _slip_case(cases.case_hex3d(bcs="zg", implicit=True))
+    with pytest.raises(qgd.QGDError) as e:
+        c.make_solver(qgd)
+    assert e.value.code == qgd.ERR_UNSUPPORTED and "slip" in e.value.message
 
 
 def test_conservation_and_finiteness_at_scale(qgd):
