@@ -292,6 +292,14 @@ int qgd_qhdfoam_set_bcs(qgd_qhd_solver* s, const int* bc_U, const int* bc_T, con
 /* U n_cells*3, T, p n_cells, alphaQGD n_cells or NULL (0.5).  Assembles the (time-constant) pressure matrix and its
  * preconditioner on the device. */
 int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T, const double* p, const double* alphaQGD);
+/* Decomposed run (one extended sub-mesh per GPU, after qgd_comm_init; call before qgd_qhdfoam_init_fields).  Two list sets in
+ * the form of qgd_qgdfoam_set_halo: the vertex-ring halo (state U, T, p after every step, p after the pressure solve) and its
+ * face-neighbour subset (search direction of every PCG iteration, fvc::grad(U)).  Replaces the processor-patch updates and
+ * the reduce() calls of lduMatrix::solver PCG in a `mpirun -np N QHDFoam -parallel` run (QHDpEqn.H:45).  On
+ * sub-meshes: explicit branch, p preconditioner diagonal | none, p_ref_cell = local id on the owning rank and -1 elsewhere. */
+int qgd_qhdfoam_set_halo(qgd_qhd_solver* s, int n_neighbours, const int* nbr_rank, const int* send_off, const int* send_cells,
+                         const int* recv_off, const int* recv_cells, int n_face_neighbours, const int* nbr_rank_face,
+                         const int* fsend_off, const int* fsend_cells, const int* frecv_off, const int* frecv_cells);
 int qgd_qhdfoam_step(qgd_qhd_solver* s, int n_steps);
 /* fields: 0 U(3), 1 T, 2 p, 3 tauQGD */
 int qgd_qhdfoam_get(qgd_qhd_solver* s, int field, double* cells, double* bnd);

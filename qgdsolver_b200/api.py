@@ -33,7 +33,7 @@ ABI_SYMBOLS = [
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
     "qgd_pcg_solve", "qgd_pcg_solve_stepwise", "qgd_pcg_solve_multi",
-    "qgd_qhdfoam_create", "qgd_qhdfoam_destroy", "qgd_qhdfoam_set_bcs", "qgd_qhdfoam_init_fields", "qgd_qhdfoam_step",
+    "qgd_qhdfoam_create", "qgd_qhdfoam_destroy", "qgd_qhdfoam_set_bcs", "qgd_qhdfoam_init_fields", "qgd_qhdfoam_set_halo", "qgd_qhdfoam_step",
     "qgd_qhdfoam_get", "qgd_qhdfoam_get_flux", "qgd_qhdfoam_get_scalars", "qgd_qhdfoam_solver_info",
     "qgd_qhdfoam_launch_count",
 ]
@@ -148,6 +148,7 @@ def load_library():
     L.qgd_qhdfoam_set_bcs.argtypes = [C.c_void_p, _ip, _ip, _ip, _dp, _dp, _dp]
     L.qgd_qhdfoam_init_fields.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     L.qgd_qhdfoam_step.argtypes = [C.c_void_p, C.c_int]
+    L.qgd_qhdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 5 + [C.c_int] + [_ip] * 5
     L.qgd_qhdfoam_get.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     L.qgd_qhdfoam_get_flux.argtypes = [C.c_void_p, _dp]
     L.qgd_qhdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -532,6 +533,28 @@ class QHDFoam:
 
     def step(self, n_steps: int = 1):
         _check(load_library().qgd_qhdfoam_step(self._h, n_steps))
+
+    def set_halo(self, sub):
+        """Register the exchange lists of a decompose.SubDomain (after comm_init, before init_fields): the vertex-ring halo and
+        its face-neighbour subset."""
+        def pack(send, recv):
+            nbrs = sorted(set(send) | set(recv))
+            out = []
+            for d in (send, recv):
+                off = np.zeros(len(nbrs) + 1, np.int32)
+                parts = []
+                for k, r in enumerate(nbrs):
+                    a = np.asarray(d.get(r, np.zeros(0, np.int32)), np.int32)
+                    parts.append(a)
+                    off[k + 1] = off[k] + a.size
+                ids = np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+                out += [off, np.ascontiguousarray(ids if ids.size else np.zeros(1, np.int32))]
+            return [len(nbrs), np.ascontiguousarray(nbrs if nbrs else [0], np.int32)] + out
+        a = pack(sub.send_cells, sub.recv_cells)
+        b = pack(sub.send_face_cells, sub.recv_face_cells)
+        self._halo_keep = (a, b)
+        _check(load_library().qgd_qhdfoam_set_halo(self._h, a[0], _i(a[1]), _i(a[2]), _i(a[3]), _i(a[4]), _i(a[5]),
+                                                   b[0], _i(b[1]), _i(b[2]), _i(b[3]), _i(b[4]), _i(b[5])))
 
     def get(self, name: str, with_bnd: bool = False):
         fid, k = QHD_FIELDS[name]

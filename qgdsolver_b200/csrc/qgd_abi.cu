@@ -308,6 +308,23 @@ __global__ void k_scatter1(int n, const int* __restrict__ ids, const double* __r
     if (i < n) dst[ids[i]] = src[i];
 }
 
+// generic cell-field exchange (QHDFoam state, PCG search direction, Gauss gradients): component-major blocks per neighbour
+__global__ void k_halo_fields(int nn, const int* __restrict__ off, const int* __restrict__ ids, double* __restrict__ base, size_t stride,
+                              int nComp, int maxComp, double* __restrict__ buf, int pack)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= off[nn]) return;
+    int k = 0;
+    while (i >= off[k + 1]) ++k;
+    const int cnt = off[k + 1] - off[k], j = i - off[k];
+    double* blk = buf + (size_t)maxComp * off[k];
+    const int c = ids[i];
+    for (int q = 0; q < nComp; ++q) {
+        if (pack) blk[(size_t)q * cnt + j] = base[(size_t)q * stride + c];
+        else base[(size_t)q * stride + c] = blk[(size_t)q * cnt + j];
+    }
+}
+
 // full state exchange after the cell update (SURVEY 5.8 C1+C3 in one message per neighbour)
 int haloExchange(qgd_solver* s, cudaStream_t g_stream = qgd::g_stream)
 {
@@ -608,6 +625,51 @@ void runSteps(qgd_solver* s, int n)
 }
 
 } // namespace
+
+// ---- multi-GPU plumbing shared with qgd_qhd.cu
+int qgd::commRanks() { return g_comm ? g_nranks : 1; }
+
+void qgd::HaloLists::set(int nn, const int* nbrRank, const int* sOff, const int* sIds, const int* rOff, const int* rIds, int nLocal,
+                         int nOwned, int maxComponents, cudaStream_t st)
+{
+    if (nn < 0 || (nn > 0 && (!nbrRank || !sOff || !sIds || !rOff || !rIds))) throw Error(QGD_ERR_INVALID, "halo lists: bad arguments");
+    if (nn > 0 && !g_comm) throw Error(QGD_ERR_STATE, "halo lists: call qgd_comm_init first");
+    nbr.assign(nbrRank, nbrRank + nn);
+    sendOff.assign(sOff, sOff + nn + 1); recvOff.assign(rOff, rOff + nn + 1);
+    for (int i = 0; i < sendOff[nn]; ++i) if (sIds[i] < 0 || sIds[i] >= nOwned) throw Error(QGD_ERR_INVALID, "halo lists: send cell is not an owned cell");
+    for (int i = 0; i < recvOff[nn]; ++i) if (rIds[i] < nOwned || rIds[i] >= nLocal) throw Error(QGD_ERR_INVALID, "halo lists: recv cell is not a halo cell");
+    auto up = [&](DevBuf<int>& d, const int* p, int n) { std::vector<int> v(p, p + n); if (v.empty()) v.push_back(0); d.upload(v, st); };
+    up(sendIds, sIds, sendOff[nn]); up(recvIds, rIds, recvOff[nn]);
+    maxComp = maxComponents;
+    sendBuf.alloc((size_t)maxComp * sendOff[nn] + 1); recvBuf.alloc((size_t)maxComp * recvOff[nn] + 1);
+    offDev.upload(sendOff, st); roffDev.upload(recvOff, st);
+}
+
+int qgd::commExchange(HaloLists& h, double* base, size_t stride, int nComp, cudaStream_t st)
+{
+    if (!h.active()) return 0;
+    if (nComp > h.maxComp) throw Error(QGD_ERR_INVALID, "commExchange: more components than the halo buffers hold");
+    const int nn = (int)h.nbr.size();
+    int launches = 0;
+    const int nS = h.sendOff[nn], nR = h.recvOff[nn];
+    if (nS) { k_halo_fields<<<(nS + 255) / 256, 256, 0, st>>>(nn, h.offDev.p, h.sendIds.p, base, stride, nComp, h.maxComp, h.sendBuf.p, 1); ++launches; }
+    QGD_NCCL(g_nccl.GroupStart());
+    for (int k = 0; k < nn; ++k) {
+        const size_t ns = (size_t)nComp * (h.sendOff[k + 1] - h.sendOff[k]), nr = (size_t)nComp * (h.recvOff[k + 1] - h.recvOff[k]);
+        if (ns) QGD_NCCL(g_nccl.Send(h.sendBuf.p + (size_t)h.maxComp * h.sendOff[k], ns, ncclDouble, h.nbr[k], g_comm, st));
+        if (nr) QGD_NCCL(g_nccl.Recv(h.recvBuf.p + (size_t)h.maxComp * h.recvOff[k], nr, ncclDouble, h.nbr[k], g_comm, st));
+    }
+    QGD_NCCL(g_nccl.GroupEnd());
+    if (nR) { k_halo_fields<<<(nR + 255) / 256, 256, 0, st>>>(nn, h.roffDev.p, h.recvIds.p, base, stride, nComp, h.maxComp, h.recvBuf.p, 0); ++launches; }
+    QGD_CUDA(cudaGetLastError());
+    return launches;
+}
+
+void qgd::commAllReduce(double* dev, int count, CommOp op, cudaStream_t st)
+{
+    if (!g_comm || g_nranks <= 1) return;
+    QGD_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, ncclDouble, op == COMM_SUM ? ncclSum : (op == COMM_MAX ? ncclMax : ncclMin), g_comm, st));
+}
 
 void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
 {

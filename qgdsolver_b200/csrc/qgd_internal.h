@@ -62,6 +62,24 @@ template <class T> struct DevBuf {
     void zero(cudaStream_t st = 0) { if (n) QGD_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
 };
 
+// ---------------------------------------------------------------- multi-GPU plumbing shared by the solvers (qgd_abi.cu)
+// Exchange lists of an extended sub-mesh: for neighbour k (rank nbr[k]) the local cells sendIds[sendOff[k] .. sendOff[k+1]) are
+// packed and sent, the received block is scattered to recvIds[...]; ascending global id on both sides.
+struct HaloLists {
+    std::vector<int> nbr, sendOff, recvOff;
+    DevBuf<int> sendIds, recvIds, offDev, roffDev;
+    DevBuf<double> sendBuf, recvBuf;       // maxComp doubles per listed cell
+    int maxComp = 0;
+    bool active() const { return !nbr.empty(); }
+    void set(int nn, const int* nbrRank, const int* sOff, const int* sIds, const int* rOff, const int* rIds, int nLocal, int nOwned,
+             int maxComponents, cudaStream_t st);
+};
+int commRanks();                           // 1 before qgd_comm_init
+// pack nComp fields (component k of cell c at base[k*stride + c]) -> grouped ncclSend/ncclRecv -> scatter; returns kernel launches
+int commExchange(HaloLists& h, double* base, size_t stride, int nComp, cudaStream_t st);
+enum CommOp { COMM_SUM = 0, COMM_MAX = 1, COMM_MIN = 2 };
+void commAllReduce(double* dev, int count, CommOp op, cudaStream_t st);      // in place, device doubles
+
 // ---------------------------------------------------------------- records
 // cell / boundary-face state, gathered by the face kernels.  64 B each, 64-B aligned.
 struct __align__(16) RecA { double rho, Ux, Uy, Uz, e, p, T, H; };

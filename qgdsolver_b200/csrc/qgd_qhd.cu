@@ -32,6 +32,7 @@ struct QhdConsts {
 
 struct QhdView {
     int nCells, nPoints, nPatchPoints;
+    int nOwned;                  // cells solved by this rank; [nOwned, nCells) are halo copies refreshed by the exchanges (multi-GPU)
     double* Q;                   // [5][nCells]  Ux,Uy,Uz,T,p
     double* P;                   // [5][nPoints]
     int pcEllW; const int* pcEll; const double* pcEllWt; const int* pcCount;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kB) k_qhd_face_pre(QhdConsts k, FaceView fv, Q
         FaceCommon c;
         faceCommon(k, ge, flags, uP, uN, TP, TN, __ldg(&fv.w[f]), d1, d2, tau, c);
         q.F0[f] = c.phiu - phiwoOf(ge, c);
-        if (ADJUST) {                                               // QHDCourantNo.H:39-54
+        if (ADJUST && f < fv.nIActive) {                            // QHDCourantNo.H:39-54 (faces owned by halo cells belong to another rank)
             const double ms = __ldg(&fv.magSf[f]);
             const double Unf = c.Uf[0] * (ge.Sf[0] / ms) + c.Uf[1] * (ge.Sf[1] / ms) + c.Uf[2] * (ge.Sf[2] / ms);
             coMax = (k.scalarTransport ? sqrt(c.Uf[0] * c.Uf[0] + c.Uf[1] * c.Uf[1] + c.Uf[2] * c.Uf[2])       // scalarTransportQHDFoam.C:88-96
@@ -316,10 +317,12 @@ __global__ void k_qhd_bnd_pre(QhdConsts k, FaceView fv, QhdView q, int adjust)
             BndCommon bc;
             bndCommon(k, fv, q, b, bc);
             q.F0[f] = bc.c.phiu - phiwoOf(bc.ge, bc.c);
-            const double ms = fv.magSf[f];
-            const double Unf = bc.c.Uf[0] * (bc.ge.Sf[0] / ms) + bc.c.Uf[1] * (bc.ge.Sf[1] / ms) + bc.c.Uf[2] * (bc.ge.Sf[2] / ms);
-            coMax = (k.scalarTransport ? sqrt(bc.c.Uf[0] * bc.c.Uf[0] + bc.c.Uf[1] * bc.c.Uf[1] + bc.c.Uf[2] * bc.c.Uf[2]) : fabs(Unf)) / fv.hf[f];
-            tauMin = bc.c.tau;
+            if (fv.own[f] < q.nOwned) {
+                const double ms = fv.magSf[f];
+                const double Unf = bc.c.Uf[0] * (bc.ge.Sf[0] / ms) + bc.c.Uf[1] * (bc.ge.Sf[1] / ms) + bc.c.Uf[2] * (bc.ge.Sf[2] / ms);
+                coMax = (k.scalarTransport ? sqrt(bc.c.Uf[0] * bc.c.Uf[0] + bc.c.Uf[1] * bc.c.Uf[1] + bc.c.Uf[2] * bc.c.Uf[2]) : fabs(Unf)) / fv.hf[f];
+                tauMin = bc.c.tau;
+            }
         }
     }
     if (adjust) blockReduceCoQ<kB>(coMax, tauMin, q.sc);
@@ -552,13 +555,14 @@ __global__ void k_qhd_pshift(QhdView q)
 
 __global__ void k_qhd_shift(QhdConsts k, QhdView q)
 {
-    *q.shift = k.needRef ? (k.refValue - q.Q[4 * (size_t)q.nCells + k.refCell]) : 0.0;
+    // decomposed runs: the rank that owns the reference cell computes the shift (refCell = -1 elsewhere), the others receive it by all-reduce
+    *q.shift = (k.needRef && k.refCell >= 0) ? (k.refValue - q.Q[4 * (size_t)q.nCells + k.refCell]) : 0.0;
 }
 
 __global__ void __launch_bounds__(kB) k_qhd_cell_update(QhdConsts k, FaceView fv, QhdView q)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= q.nCells) return;
+    if (c >= q.nOwned) return;
     const size_t n = q.nCells, nF = fv.nF;
     double su[3] = {0, 0, 0}, sT = 0.0;
     forCellFaces(q, c, [&](int f, int side) {
@@ -605,11 +609,19 @@ struct qgd_qhd_solver {
     std::vector<double> hbvP, tauCell, tauBnd;
     long long launches = 0;
     bool bcsSet = false, fieldsSet = false;
+    // decomposed run (extended sub-mesh): vertex-ring lists for the state, face-neighbour lists for the PCG search direction and
+    // the Gauss gradients; the pressure equation is solved by the stepwise PCG with NCCL exchange / all-reduce between its phases
+    HaloLists halo, haloFace;
+    StepwisePcg sw;
+    DevBuf<PcgResult> swOut;
+    bool fixesPLocal = false;
+    bool multi() const { return mesh->h.nOwned != mesh->h.nCells; }
     QhdView view()
     {
         const qgd_mesh& m = *mesh;
         QhdView q;
         q.nCells = m.h.nCells; q.nPoints = m.h.nPoints; q.nPatchPoints = (int)m.h.patchPoints.size();
+        q.nOwned = m.h.nOwned;
         q.Q = Q.p; q.P = P.p;
         q.pcEllW = m.pcEllW; q.pcEll = m.pcEll.p; q.pcEllWt = m.pcEllWt.p; q.pcCount = m.pcCount.p;
         q.pcTailOff = m.pcTailOff.p; q.pcTailCell = m.pcTailCell.p; q.pcTailW = m.pcTailW.p;
@@ -643,6 +655,13 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
     const bool pts = !s->fvsc->reduced && s->mesh->h.nD > 1;
     const bool adjust = s->desc.adjust_time_step != 0;
     const int nB = fv.nB;
+    const bool multi = s->multi();
+    const size_t nCs = q.nCells;
+    PcgHooks hooks;
+    if (multi) {
+        hooks.exchange = [s](double* vec, cudaStream_t cs) { s->launches += commExchange(s->haloFace, vec, 0, 1, cs); };
+        hooks.allreduceSum = [](double* dev, int count, cudaStream_t cs) { commAllReduce(dev, count, COMM_SUM, cs); };
+    }
     for (int i = 0; i < nSteps; ++i) {
         int n = 0;
         if (nB) { k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 0, 0); ++n; }
@@ -656,12 +675,25 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
             ++n;
         }
         if (nB) { k_qhd_bnd_pre<<<nblk(nB), kB, 0, st>>>(k, fv, q, adjust ? 1 : 0); ++n; }
+        if (multi && adjust) {       // gMax / gMin of QHDCourantNo.H:54, setDeltaT-QGDQHD.H:46 (bit patterns of non-negative doubles)
+            commAllReduce(reinterpret_cast<double*>(&q.sc->coMaxBits), 1, COMM_MAX, st);
+            commAllReduce(reinterpret_cast<double*>(&q.sc->tauMinBits), 1, COMM_MIN, st);
+        }
         k_qhd_dt<<<1, 1, 0, st>>>(q.sc); ++n;
         if (!k.scalarTransport) {                                                        // scalarTransportQHDFoam has no pressure equation
         if (nB) { k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 1, 0); ++n; }           // QHDpEqn.H:35
         k_qhd_cell_pre<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
         // QHDpEqn.H:45 — x is the p slice of the state
         s->A.xExternal = q.Q + 4 * (size_t)q.nCells;
+        if (multi) {
+            // fvc::grad(U) of the face-neighbour halo cells (their Gauss sums are incomplete locally), then the decomposed solve
+            n += commExchange(s->haloFace, q.GU, nCs, 9, st);
+            PcgResult r;
+            n += s->sw.solve(s->A, s->A.b.p, s->A.xExternal, s->desc.p_tolerance, s->desc.p_rel_tol, s->desc.p_max_iter, s->precond, st, &hooks, &r);
+            QGD_CUDA(cudaMemcpyAsync(s->A.out.p, &r, sizeof(r), cudaMemcpyHostToDevice, st));
+            QGD_CUDA(cudaStreamSynchronize(st));
+            n += commExchange(s->halo, s->A.xExternal, nCs, 1, st);          // p on the whole vertex ring (point interpolation of p)
+        } else
         n += s->A.solve(s->desc.p_tolerance, s->desc.p_rel_tol, s->desc.p_max_iter, st);
         if (nB) { k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 1, 0); ++n; }           // psi.correctBoundaryConditions()
         if (pts) {
@@ -672,6 +704,7 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
         if (fv.nI) { k_qhd_face_post<<<nblk(fv.nI), kB, 0, st>>>(k, fv, q); ++n; }
         if (nB) { k_qhd_bnd_post<<<nblk(nB), kB, 0, st>>>(k, fv, q); ++n; }
         k_qhd_shift<<<1, 1, 0, st>>>(k, q); ++n;
+        if (multi) commAllReduce(q.shift, 1, COMM_SUM, st);
         if (k.implicit) {
             const size_t nC = q.nCells;
             const double tol = s->desc.diff_tolerance, rel = s->desc.diff_rel_tol;
@@ -691,8 +724,9 @@ void qhdRunSteps(qgd_qhd_solver* s, int nSteps)
             n += 2 + s->AT.solve(tol, rel, maxIter, st);               // QHDTEqn.H:71-79
             k_qhd_pshift<<<nblk(q.nCells), kB, 0, st>>>(q); ++n;
         } else if (!k.scalarTransport) {                             // scalarTransportQHDFoam.C:114: nothing is solved without implicitDiffusion
-            k_qhd_cell_update<<<nblk(q.nCells), kB, 0, st>>>(k, fv, q); ++n;
+            k_qhd_cell_update<<<nblk(q.nOwned), kB, 0, st>>>(k, fv, q); ++n;
         }
+        if (multi) n += commExchange(s->halo, q.Q, nCs, 5, st);              // U, T, p of the halo cells for the next step
         if (nB) {
             k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 0, 0);                        // U, T correctBoundaryConditions
             k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 1, 1);                        // p_b += shift
@@ -730,9 +764,18 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
         const int diffPrecond = d->implicit_diffusion ? precondOf(d->diff_preconditioner) : 2;
         for (int pk : mesh->h.patchKind)
             if (pk == QGD_PATCH_PROCESSOR) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam: processor patches (multi-GPU) are not available yet");
-        if (mesh->h.nOwned != mesh->h.nCells) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam: extended sub-meshes (multi-GPU) are not available yet");
+        const bool sub = mesh->h.nOwned != mesh->h.nCells;
+        if (sub) {          // decomposed run on an extended sub-mesh (qgd_qhdfoam_set_halo): explicit branch, PCG + diagonal | none
+            if (d->implicit_diffusion || d->scalar_transport)
+                throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam on extended sub-meshes (multi-GPU): implicitDiffusion / scalarTransportQHDFoam are not available yet");
+            if (precond == 2)
+                throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam on extended sub-meshes (multi-GPU): the p preconditioner must be diagonal or none "
+                                                 "(DIC is local to a processor block in a decomposed run and not available on sub-meshes yet)");
+        }
         if (!(d->delta_t > 0.0) || !(d->rho0 > 0.0) || !(d->Pr > 0.0)) throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_create: deltaT, rho and Pr must be positive");
-        if (d->p_ref_cell < 0 || d->p_ref_cell >= mesh->h.nCells) throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_create: pRefCell out of range");
+        // decomposed runs: the local id of the global pRefCell on the rank that owns it, -1 on every other rank
+        if (d->p_ref_cell >= mesh->h.nOwned || (d->p_ref_cell < 0 && !(sub && d->p_ref_cell == -1)))
+            throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_create: pRefCell out of range");
         std::unique_ptr<qgd_qhd_solver> s(new qgd_qhd_solver());
         s->mesh = mesh; s->desc = *d; s->model = model; s->precondName = pc; s->precond = precond;
         s->desc.fvsc_scheme = nullptr; s->desc.qgd_coeffs_model = nullptr; s->desc.p_preconditioner = nullptr; s->desc.diff_preconditioner = nullptr;
@@ -791,6 +834,7 @@ int qgd_qhdfoam_set_bcs(qgd_qhd_solver* s, const int* bc_U, const int* bc_T, con
                 (s->hbcP[b] != QGD_BC_ZERO_GRADIENT && !val_p))
                 throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_set_bcs: fixedValue / fixedGradient patch without values");
         }
+        s->fixesPLocal = fixesP;
         s->k.needRef = (fixesP || s->k.scalarTransport) ? 0 : 1;        // p.needReference(); scalarTransportQHDFoam never touches p
         s->bcU.upload(s->hbcU.empty() ? std::vector<int>(1, 1) : s->hbcU, st);
         s->bcT.upload(s->hbcT.empty() ? std::vector<int>(1, 1) : s->hbcT, st);
@@ -819,6 +863,17 @@ int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T,
         cudaStream_t st = runtimeStream();
         const int nC = h.nCells, nF = h.nFaces, nI = h.nInternal, nB = h.nBnd;
         const qgd_qhdfoam_desc& d = s->desc;
+        const bool multi = s->multi();
+        if (multi && !s->halo.active()) throw Error(QGD_ERR_STATE, "qgd_qhdfoam_init_fields: extended sub-mesh without exchange lists (call qgd_qhdfoam_set_halo first)");
+        if (multi) {        // p.needReference() is a global property: a rank may hold no face of the fixedValue patch
+            double flag = s->fixesPLocal ? 1.0 : 0.0;
+            QGD_CUDA(cudaMemcpyAsync(s->shift.p, &flag, sizeof(double), cudaMemcpyHostToDevice, st));
+            commAllReduce(s->shift.p, 1, COMM_MAX, st);
+            QGD_CUDA(cudaMemcpyAsync(&flag, s->shift.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+            QGD_CUDA(cudaStreamSynchronize(st));
+            s->k.needRef = flag > 0.5 ? 0 : 1;
+            s->shift.zero(st);
+        }
         // ---- state (SoA)
         {
             std::vector<double> q(5 * (size_t)nC);
@@ -839,6 +894,13 @@ int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T,
         };
         s->tauCell.resize(nC); s->tauBnd.assign(nB, 0.0);
         for (int c = 0; c < nC; ++c) s->tauCell[c] = tauOf(alphaQGD ? alphaQGD[c] : 0.5, h.hQGD[c]);
+        if (multi) {        // hQGD of a halo cell is incomplete on the sub-mesh (its outer faces are cut): take the owners' tauQGD
+            DevBuf<double> t;
+            t.upload(s->tauCell, st);
+            commExchange(s->halo, t.p, (size_t)nC, 1, st);
+            QGD_CUDA(cudaMemcpyAsync(s->tauCell.data(), t.p, (size_t)nC * sizeof(double), cudaMemcpyDeviceToHost, st));
+            QGD_CUDA(cudaStreamSynchronize(st));
+        }
         for (int b = 0; b < nB; ++b) {
             if (h.patchKind[h.bfacePatch[b]] == QGD_PATCH_EMPTY) continue;
             const int P = h.owner[nI + b];
@@ -865,9 +927,11 @@ int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T,
             else if (s->hbcP[b] == QGD_BC_FIXED_GRADIENT) bouC[b] = gS * s->hbvP[b];
         }
         std::vector<double> diagT(diag);
-        if (s->k.needRef) diagT[s->k.refCell] += diagT[s->k.refCell];                   // fvMatrix::setReference
+        if (s->k.needRef && s->k.refCell >= 0) diagT[s->k.refCell] += diagT[s->k.refCell];   // fvMatrix::setReference
         for (int b = 0; b < nB; ++b) { const int P = h.owner[nI + b]; diagT[P] += intC[b]; srcBnd[P] += bouC[b]; }
+        for (int c = h.nOwned; c < nC; ++c) diagT[c] = 1.0;                             // halo rows are never solved; keep 1/diag finite
         s->A.build(h, diagT.data(), upper.data(), s->precond, st);
+        if (multi) s->sw.alloc(s->A, h.nOwned);
         // device face order for the per-face arrays
         const std::vector<int>& perm = s->mesh->facePerm;
         std::vector<double> taufDev(nF), upperDev(std::max(nI, 1), 0.0);
@@ -901,6 +965,7 @@ int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T,
         // boundary values of the fields as read
         const FaceView fv = s->fvsc->view();
         const QhdView q = s->view();
+        if (multi) commExchange(s->halo, s->Q.p, (size_t)nC, 5, st);     // the caller's halo values may be placeholders
         if (nB) {
             k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 0, 0);
             k_qhd_bnd_eval<<<nblk(nB), kB, 0, st>>>(fv, q, 1, 0);
@@ -908,6 +973,21 @@ int qgd_qhdfoam_init_fields(qgd_qhd_solver* s, const double* U, const double* T,
         QGD_CUDA(cudaGetLastError());
         QGD_CUDA(cudaStreamSynchronize(st));
         s->fieldsSet = true;
+    });
+}
+
+int qgd_qhdfoam_set_halo(qgd_qhd_solver* s, int nn, const int* nbr_rank, const int* send_off, const int* send_cells, const int* recv_off,
+                         const int* recv_cells, int nn_face, const int* nbr_rank_face, const int* fsend_off, const int* fsend_cells,
+                         const int* frecv_off, const int* frecv_cells)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_set_halo: null solver");
+        if (s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qhdfoam_set_halo: call before qgd_qhdfoam_init_fields");
+        const HostMesh& h = s->mesh->h;
+        cudaStream_t st = runtimeStream();
+        s->halo.set(nn, nbr_rank, send_off, send_cells, recv_off, recv_cells, h.nCells, h.nOwned, 9, st);
+        s->haloFace.set(nn_face, nbr_rank_face, fsend_off, fsend_cells, frecv_off, frecv_cells, h.nCells, h.nOwned, 9, st);
     });
 }
 

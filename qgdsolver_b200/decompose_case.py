@@ -48,7 +48,7 @@ def decompose_case(case_dir: str, n: int, time: str = "0") -> int:
             proc_faces = gf < nI
             bnd[proc_faces] = f.internal[p.cell_addr][pm.owner[pm.n_internal:][proc_faces]]
             foamcase.write_field(os.path.join(case_dir, f"processor{p.rank}", time, name), pm, name, f.internal[p.cell_addr], types,
-                                 bnd if have else None, f.dimensions)
+                                 bnd if have else None, f.dimensions, gradients=foamcase.proc_patch_gradients(mesh, f.patch_gradients, p))
     return len(procs)
 
 

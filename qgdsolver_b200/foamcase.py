@@ -125,7 +125,11 @@ def _split_header(text: str) -> Tuple[Dict[str, str], str]:
 
 
 def _read_list_body(body: str) -> Tuple[int, str]:
-    """`N ( ... )` -> (N, inner text)"""
+    """`N ( ... )` -> (N, inner text); the uniform form `N{v}` is expanded to N copies of v"""
+    u = re.match(r"\s*(\d+)\s*\{([^}]*)\}", body)
+    if u:
+        n = int(u.group(1))
+        return n, " ".join([u.group(2).strip()] * n)
     m = re.search(r"(\d+)\s*\(", body)
     if not m:
         raise FoamFormatError("expected a list `N ( ... )`")
@@ -357,9 +361,24 @@ def read_cell_decomposition(case_dir: str, n_cells: int) -> np.ndarray:
     return decompose.cell_rank_from_procs(procs, n_cells)
 
 
+def proc_patch_gradients(mesh: PolyMesh, gradients: Optional[Dict[str, np.ndarray]], proc) -> Optional[Dict[str, np.ndarray]]:
+    """`gradient` entries of a global field (patch name -> per-face array in global patch order) cut down to the faces a
+    processor mesh keeps of each patch (through faceProcAddressing)"""
+    if not gradients:
+        return None
+    start = {p.name: p.start for p in mesh.patches}
+    out = {}
+    for patch in proc.mesh.patches:
+        if patch.name in gradients and patch.name in start:
+            gf = np.abs(proc.face_addr[patch.start:patch.start + patch.size].astype(np.int64)) - 1
+            out[patch.name] = np.asarray(gradients[patch.name])[gf - start[patch.name]]
+    return out
+
+
 def write_processor_fields(case_dir: str, time: str, name: str, procs, internal: np.ndarray, patch_types: Dict[str, str],
                            boundary: Optional[np.ndarray] = None, n_internal_global: int = 0,
-                           dimensions: str = "[0 0 0 0 0 0 0]") -> None:
+                           dimensions: str = "[0 0 0 0 0 0 0]", gradients: Optional[Dict[str, np.ndarray]] = None,
+                           mesh: Optional[PolyMesh] = None) -> None:
     """Scatter a global cell field (and optionally its boundary values, nBnd[,k] in global boundary-face order) into
     processorN/<time>/<name>, as `decomposePar -fields` / a parallel run would leave it; processor patches get type
     `processor` with the value of the cell across the patch left to the reader (calculated from the owner here)."""
@@ -378,7 +397,8 @@ def write_processor_fields(case_dir: str, time: str, name: str, procs, internal:
         for patch in p.mesh.patches:
             if patch.kind == PATCH_PROCESSOR:
                 pt[patch.name] = "processor"
-        write_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh, name, loc, pt, bl, dimensions)
+        write_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh, name, loc, pt, bl, dimensions,
+                    gradients=proc_patch_gradients(mesh, gradients, p) if mesh is not None else None)
 
 
 def reconstruct_fields(case_dir: str, time: str, names, mesh: PolyMesh, binary: bool = False) -> Dict[str, np.ndarray]:
@@ -389,7 +409,7 @@ def reconstruct_fields(case_dir: str, time: str, names, mesh: PolyMesh, binary: 
     nI = mesh.n_internal
     out = {}
     for name in names:
-        internal, boundary, types, have_values = None, None, {}, False
+        internal, boundary, types, have_values, grads = None, None, {}, False, {}
         for p in procs:
             f = read_field(os.path.join(case_dir, f"processor{p.rank}", time, name), p.mesh)
             if internal is None:
@@ -401,11 +421,16 @@ def reconstruct_fields(case_dir: str, time: str, names, mesh: PolyMesh, binary: 
                 if patch.kind == PATCH_PROCESSOR:
                     continue
                 types.setdefault(patch.name, f.patch_types[patch.name])
+                gf = np.abs(p.face_addr[patch.start:patch.start + patch.size].astype(np.int64)) - 1
                 if patch.size and patch.name in f.patch_values:
                     have_values = True
-                    gf = np.abs(p.face_addr[patch.start:patch.start + patch.size].astype(np.int64)) - 1
                     boundary[gf - nI] = f.patch_values[patch.name]
-        write_field(os.path.join(case_dir, time, name), mesh, name, internal, types, boundary if have_values else None, binary=binary)
+                if patch.size and patch.name in f.patch_gradients:
+                    gp = next(q for q in mesh.patches if q.name == patch.name)
+                    g = grads.setdefault(patch.name, np.zeros((gp.size,) + f.internal.shape[1:]))
+                    g[gf - gp.start] = f.patch_gradients[patch.name]
+        write_field(os.path.join(case_dir, time, name), mesh, name, internal, types, boundary if have_values else None, binary=binary,
+                    gradients=grads or None)
         out[name] = internal
     return out
 
@@ -429,6 +454,12 @@ def _parse_value(txt: str, n: int, ncmpt: int) -> np.ndarray:
         vals = np.array(re.sub(r"[()]", " ", txt[len("uniform"):]).split(), dtype=np.float64)
         if vals.size != ncmpt:
             raise FoamFormatError(f"uniform value with {vals.size} components, expected {ncmpt}")
+        return np.ascontiguousarray(np.broadcast_to(vals if ncmpt > 1 else vals[0], shape)).copy()
+    u = re.match(r"nonuniform\s+List<\w+>\s*(\d+)\s*\{([^}]*)\}\s*$", txt, flags=re.S)
+    if u:                                                       # `N{v}`: N identical entries
+        vals = np.array(re.sub(r"[()]", " ", u.group(2)).split(), dtype=np.float64)
+        if int(u.group(1)) != n or vals.size != ncmpt:
+            raise FoamFormatError(f"uniform list {u.group(1)}{{...}} with {vals.size} components, expected {n} entries of {ncmpt}")
         return np.ascontiguousarray(np.broadcast_to(vals if ncmpt > 1 else vals[0], shape)).copy()
     m = re.match(r"nonuniform\s+List<\w+>\s*(\d+)\s*\((.*)\)\s*$", txt, flags=re.S)
     if not m:
@@ -488,9 +519,12 @@ def read_field(path: str, mesh: PolyMesh) -> VolField:
 
 
 def write_field(path: str, mesh: PolyMesh, name: str, internal: np.ndarray, patch_types: Dict[str, str],
-                boundary: Optional[np.ndarray] = None, dimensions: str = "[0 0 0 0 0 0 0]", binary: bool = False) -> None:
-    """Write a volScalarField / volVectorField; `boundary` (nBnd[,3]) supplies `value` entries.  binary: nonuniform
-    lists are written as raw little-endian doubles (`format binary`)."""
+                boundary: Optional[np.ndarray] = None, dimensions: str = "[0 0 0 0 0 0 0]", binary: bool = False,
+                gradients: Optional[Dict[str, np.ndarray]] = None) -> None:
+    """Write a volScalarField / volVectorField; `boundary` (nBnd[,3]) supplies `value` entries, `gradients` (patch name ->
+    per-face gradient) the mandatory `gradient` entry of fixedGradient / qgdFlux / qhdFlux patches (OpenFOAM cannot read such a
+    patch without it, and a restart would silently continue with gradient 0).  binary: nonuniform lists are written as raw
+    little-endian doubles (`format binary`)."""
     internal = np.asarray(internal, np.float64)
     ncmpt = 1 if internal.ndim == 1 else internal.shape[1]
     cls, typ = ("volScalarField", "scalar") if ncmpt == 1 else ("volVectorField", "vector")
@@ -516,6 +550,16 @@ def write_field(path: str, mesh: PolyMesh, name: str, internal: np.ndarray, patc
         for p in mesh.patches:
             t = patch_types.get(p.name, "empty" if p.kind == PATCH_EMPTY else "calculated")
             w(f"    {p.name}\n    {{\n        type            {t};\n")
+            if t in ("fixedGradient", "qgdFlux", "qhdFlux") and p.kind != PATCH_EMPTY:
+                g = None if gradients is None else gradients.get(p.name)
+                if g is None:
+                    if t == "fixedGradient":
+                        raise FoamFormatError(f"write_field {name}: fixedGradient patch {p.name} needs its gradient (gradients=...)")
+                    g = np.zeros((p.size, ncmpt) if ncmpt > 1 else p.size)     # qgdFlux / qhdFlux re-evaluate it in updateCoeffs()
+                g = np.broadcast_to(np.asarray(g, np.float64), (p.size, ncmpt) if ncmpt > 1 else (p.size,))
+                w("        gradient        ")
+                w(lst(g) if p.size else f"nonuniform List<{typ}> 0()")
+                w(";\n")
             if boundary is not None and p.kind != PATCH_EMPTY:
                 if p.size:
                     w("        value           ")
@@ -548,8 +592,11 @@ def bc_arrays(mesh: PolyMesh, fld: VolField) -> Tuple[np.ndarray, np.ndarray]:
         sl = slice(p.start - nI, p.start - nI + p.size)
         if t == "fixedValue":
             vals[sl] = fld.patch_values[p.name]
-        elif t in ("fixedGradient", "qhdFlux") and p.name in fld.patch_gradients:
-            vals[sl] = fld.patch_gradients[p.name]
+        elif t in ("fixedGradient", "qhdFlux"):
+            if p.name in fld.patch_gradients:
+                vals[sl] = fld.patch_gradients[p.name]
+            elif t == "fixedGradient" and p.size:               # fixedGradientFvPatchField reads `gradient` with a mandatory lookup
+                raise FoamFormatError(f"patch {p.name} of {fld.name}: fixedGradient without a `gradient` entry")
     return kinds, vals
 
 

@@ -127,12 +127,42 @@ def parse(text: str, name: str = "") -> FoamDict:
     for bad in ("#include", "#calc", "#codeStream", "#eval"):
         if bad in text:
             raise FoamDictError(f"{name}: {bad} directives are not supported")
-    toks = _TOKEN.findall(text)
-    it = iter(toks)
+    it = _Tokens(text)
     root = FoamDict(name)
     _parse_dict(it, root, top=True)
     root.pop("FoamFile", None)
     return root
+
+
+class _Tokens:
+    """token stream that remembers whether a token is glued to the previous one (no white space in between): OpenFOAM's
+    keyType reads `div(phiJm,U)`, `interpolate(rho)`, `laplacian(taubyrhof,p)` as ONE keyword"""
+
+    def __init__(self, text: str):
+        self.m = list(_TOKEN.finditer(text))
+        self.i = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> str:
+        if self.i >= len(self.m):
+            raise StopIteration
+        self.i += 1
+        return self.m[self.i - 1].group(0)
+
+    def glued_paren_follows(self) -> bool:
+        return 0 < self.i < len(self.m) and self.m[self.i].group(0) == "(" and self.m[self.i].start() == self.m[self.i - 1].end()
+
+    def take_balanced(self) -> str:
+        """consume `( ... )` with nested parentheses and return its text without white space"""
+        depth, out = 0, []
+        for t in self:
+            out.append(t)
+            depth += (t == "(") - (t == ")")
+            if depth == 0:
+                return "".join(out)
+        raise FoamDictError("unbalanced ( in a keyword")
 
 
 def _parse_list(it: Iterator[str], close: str) -> List[Any]:
@@ -168,6 +198,8 @@ def _parse_dict(it: Iterator[str], d: FoamDict, top: bool = False) -> None:
             return
         if key in ";":
             continue
+        if isinstance(it, _Tokens) and not key.startswith('"') and it.glued_paren_follows():
+            key += it.take_balanced()                                     # keyword with an argument list: div(phiJm,U)
         vals: List[Any] = []
         for t in it:
             if t == "{":

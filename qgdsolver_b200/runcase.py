@@ -85,10 +85,47 @@ def _check_schemes(schemes: foamdict.FoamDict) -> str:
         d = schemes.sub_dict("divSchemes")
         for k in d:
             v = d._tokens(k)
-            if k != "default" and v not in (["none"], ["Gauss", "linear"]):
+            if v not in (["none"], ["Gauss", "linear"]):
                 raise FoamDictError(f"fvSchemes::divSchemes::{k}: qgdFlux with a convection scheme other than central (flux*field_f) "
                                     "is not device-native")
+    # the device step (and the oracle) hard-code the discretisation the QGD tutorials use; anything else would run silently
+    # with different numerics than the reference, so it is refused like the entries above
+    def every(name, ok, what):
+        if not schemes.found(name):
+            return
+        d = schemes.sub_dict(name)
+        for k in d:
+            v = [t for t in d._tokens(k) if isinstance(t, str)]
+            if not ok(v):
+                raise FoamDictError(f"fvSchemes::{name}::{k} = {' '.join(v)}: {what}")
+    every("ddtSchemes", lambda v: v == ["Euler"], "only Euler time integration is device-native (QGDUEqn.H:36-87 are written for it)")
+    every("gradSchemes", lambda v: v in (["Gauss", "linear"], ["none"]), "only Gauss linear is device-native for fvc::grad")
     return scheme
+
+
+def _check_laplacian_schemes(schemes: foamdict.FoamDict, mesh) -> None:
+    """laplacianSchemes / snGradSchemes: the device assembles the uncorrected Laplacian (|Sf| nonOrthDeltaCoeffs, no
+    faceFluxCorrection).  `corrected` is the same thing on an orthogonal mesh only, so it is accepted there and refused otherwise."""
+    import numpy as np
+    nI = mesh.n_internal
+    d = mesh.C[mesh.neighbour] - mesh.C[mesh.owner[:nI]]
+    cosang = (d * mesh.Sf[:nI]).sum(1) / (np.linalg.norm(d, axis=1) * mesh.magSf[:nI])
+    orthogonal = nI == 0 or float(np.abs(1.0 - cosang).max()) < 1e-10
+    for name in ("laplacianSchemes", "snGradSchemes"):
+        if not schemes.found(name):
+            continue
+        dct = schemes.sub_dict(name)
+        for k in dct:
+            v = [t for t in dct._tokens(k) if isinstance(t, str)]
+            tail = v[2:] if name == "laplacianSchemes" and v[:2] == ["Gauss", "linear"] else (v if name == "snGradSchemes" else None)
+            if v == ["none"]:
+                continue
+            if tail is None or tail not in (["uncorrected"], ["orthogonal"], ["corrected"]):
+                raise FoamDictError(f"fvSchemes::{name}::{k} = {' '.join(v)}: only Gauss linear uncorrected | orthogonal | corrected "
+                                    "(orthogonal meshes) is device-native")
+            if tail == ["corrected"] and not orthogonal:
+                raise FoamDictError(f"fvSchemes::{name}::{k} = {' '.join(v)}: the non-orthogonal correction is not device-native and "
+                                    "this mesh is non-orthogonal; use uncorrected (what the device assembles) or an orthogonal mesh")
 
 
 def _linear_solver(fvsolution: foamdict.FoamDict, name: str, defaults=(1e-6, 0.0, 1000, "DIC")):
@@ -128,6 +165,7 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
     mesh = foamcase.read_polymesh(case_dir)
     fields = foamcase.read_case_fields(case_dir, mesh, start)
     scheme = _check_schemes(schemes)
+    _check_laplacian_schemes(schemes, mesh)
     # ---- thermophysicalProperties
     tt = thermo.sub_dict("thermoType")
     want = {"type": "heRhoQGDThermo" if qhd else "hePsiQGDThermo", "mixture": "pureMixture", "transport": "const", "thermo": "hConst",
@@ -236,7 +274,7 @@ def write_time(setup: CaseSetup, s, t: float) -> str:
         src = setup.fields.get(n)
         types = dict(src.patch_types) if src is not None else {}
         foamcase.write_field(os.path.join(d, n), setup.mesh, n, cells, types, bnd, src.dimensions if src is not None else "[0 0 0 0 0 0 0]",
-                             binary=setup.write_binary)
+                             binary=setup.write_binary, gradients=src.patch_gradients if src is not None else None)
     return d
 
 
@@ -331,7 +369,8 @@ def processor_writer(setup: CaseSetup, sub, proc):
                 if patch.kind == foamcase.PATCH_PROCESSOR:
                     types[patch.name] = "processor"
             foamcase.write_field(os.path.join(d, n), proc.mesh, n, own, types, pb, src.dimensions if src is not None else "[0 0 0 0 0 0 0]",
-                                 binary=setup.write_binary)
+                                 binary=setup.write_binary,
+                                 gradients=foamcase.proc_patch_gradients(setup.mesh, src.patch_gradients, proc) if src is not None else None)
         return d
     return write
 

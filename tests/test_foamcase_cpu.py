@@ -220,3 +220,38 @@ def test_truncated_octahedron_polyhedral_mesh():
         fc.write_polymesh(m, tmp)
         r = fc.read_polymesh(tmp)
         assert np.array_equal(r.face_verts, m.face_verts) and np.array_equal(r.points, m.points) and np.array_equal(r.V, m.V)
+
+
+def test_fixed_gradient_round_trip_and_uniform_lists(tmp_path):
+    """write -> read -> bc_arrays keeps the gradient of fixedGradient / qhdFlux patches (a restart must not continue with
+    gradient 0); a fixedGradient patch without `gradient` is an error on both sides; `N{v}` uniform lists are read"""
+    import numpy as np
+    import pytest
+    import cases
+    from qgdsolver_b200 import foamcase as fc
+    m = cases.pm.hex_box(3, 2, 2)
+    names = [p.name for p in m.patches]
+    types = {n: "zeroGradient" for n in names}
+    types[names[0]], types[names[1]] = "fixedGradient", "qhdFlux"
+    rng = np.random.default_rng(1)
+    g0, g1 = rng.random(m.patches[0].size), rng.random(m.patches[1].size)
+    bnd = rng.random(m.n_bnd)
+    path = str(tmp_path / "0" / "p")
+    fc.write_field(path, m, "p", rng.random(m.n_cells), types, bnd, gradients={names[0]: g0, names[1]: g1})
+    f = fc.read_field(path, m)
+    assert np.array_equal(f.patch_gradients[names[0]], g0) and np.array_equal(f.patch_gradients[names[1]], g1)
+    kinds, vals = fc.bc_arrays(m, f)
+    nI = m.n_internal
+    assert kinds[0] == 2 and kinds[1] == 5
+    assert np.array_equal(vals[m.patches[0].start - nI:m.patches[0].start - nI + m.patches[0].size], g0)
+    assert np.array_equal(vals[m.patches[1].start - nI:m.patches[1].start - nI + m.patches[1].size], g1)
+    with pytest.raises(fc.FoamFormatError, match="needs its gradient"):
+        fc.write_field(path, m, "p", np.zeros(m.n_cells), types, bnd)
+    f.patch_gradients.pop(names[0])
+    with pytest.raises(fc.FoamFormatError, match="without a `gradient` entry"):
+        fc.bc_arrays(m, f)
+    # uniform lists N{v}
+    (tmp_path / "lab").write_text("FoamFile { version 2.0; format ascii; class labelList; object lab; }\n8{3}\n")
+    assert np.array_equal(fc.read_labels(str(tmp_path / "lab")), np.full(8, 3))
+    assert np.array_equal(fc._parse_value("nonuniform List<scalar> 4{0.5}", 4, 1), np.full(4, 0.5))
+    assert np.array_equal(fc._parse_value("nonuniform List<vector> 2{(1 2 3)}", 2, 3), np.tile([1.0, 2.0, 3.0], (2, 1)))

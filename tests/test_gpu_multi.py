@@ -27,3 +27,17 @@ def test_decomposed_run_matches_oracle(n):
     assert r.returncode == 0, r.stderr[-4000:]
     assert "MULTI_ALL_OK" in r.stdout
 
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_decomposed_qhdfoam_matches_oracle(n):
+    """QHDFoam on n extended sub-meshes (NCCL state exchange, stepwise PCG with exchanged search direction and all-reduced dot
+    products) against the serial oracle; the worker runs under a hard timeout (a list mistake would block in ncclRecv)."""
+    if _n_gpus() < n:
+        pytest.skip(f"needs {n} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", str(29660 + n), os.path.join(ROOT, "tests", "multi_gpu_qhd_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-6000:])
+    assert r.returncode == 0, r.stderr[-4000:]
+    assert "MULTIQHD_ALL_OK" in r.stdout

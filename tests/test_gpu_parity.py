@@ -305,14 +305,14 @@ def test_tma_face_kernel_on_odd_face_counts(qgd):
     import os
     import subprocess
     import sys
-    mesh = cases.pm.hex_box(33, 17, 9)                  # 129x129x256-like parity: odd number of faces
+    mesh = cases.pm.hex_box(33, 17, 8)                  # odd x odd x even like the 129x129x256 sub-mesh: odd number of faces
     assert mesh.n_faces % 2 == 1
     c = cases._with_bcs(mesh, "mixed", cases.GAS, 2e-4)
     s = c.make_solver(qgd)
     assert s.face_kernel() == ("k_face_flux_tma", 3)
     s.step(20)
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import numpy as np, cases; from qgdsolver_b200 import api; api.init(0);"
-            "c = cases._with_bcs(cases.pm.hex_box(33, 17, 9), 'mixed', cases.GAS, 2e-4); s = c.make_solver(api);"
+            "c = cases._with_bcs(cases.pm.hex_box(33, 17, 8), 'mixed', cases.GAS, 2e-4); s = c.make_solver(api);"
             "assert s.face_kernel()[0] == 'k_face_flux'; s.step(20); np.save(sys.argv[1], np.stack([s.get('rho'), s.get('rhoE')]))")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = os.path.join("/tmp", "qgd_odd_faces.npy")

@@ -189,10 +189,8 @@ def test_qhd_cavity_case_directory(tmp_path, oracle_mod):
     names = [p.name for p in m.patches]
     for nm, arr, kinds, vals in (("U", c.U0, c.bcU, c.bvU), ("T", c.T0, c.bcT, c.bvT), ("p", c.p0, c.bcP, c.bvP)):
         types = {n: ("empty" if p.kind == 1 else code[int(k)]) for n, k, p in zip(names, kinds, m.patches)}
-        fc.write_field(str(tmp_path / "0" / nm), m, nm, arr, types, vals)
-    # fixedGradient p patches need a `gradient` entry: patch the file (write_field writes `value`)
-    ptxt = (tmp_path / "0" / "p").read_text().replace("type            fixedGradient;", "type            fixedGradient;\n        gradient        uniform 0;")
-    (tmp_path / "0" / "p").write_text(ptxt)
+        grads = {n: np.zeros((p.size, 3) if nm == "U" else p.size) for n, p in zip(names, m.patches) if types[n] == "fixedGradient"}
+        fc.write_field(str(tmp_path / "0" / nm), m, nm, arr, types, vals, gradients=grads)
     s = runcase.load_case(str(tmp_path))
     k = s.solver_kwargs
     assert s.solver == "QHDFoam" and k["qgd_coeffs"] == "constTau" and k["Tau"] == 1e-3 and k["g"] == (0.0, -9.81, 0.0)
@@ -248,6 +246,10 @@ def test_parallel_writer_puts_owned_results_into_processor_directories(tmp_path)
         fc.write_field(str(tmp_path / "0" / nm), m, nm, arr, types, vals)
     rank = decompose.geometric_split(m, 2)
     fc.write_decomposed_case(m, rank, str(tmp_path))
+    import pytest
+    with pytest.raises(runcase.FoamDictError, match="non-orthogonal"):     # `corrected` schemes on a perturbed mesh are refused
+        runcase.load_case(str(tmp_path))
+    (tmp_path / "system" / "fvSchemes").write_text(SCHEMES.replace("corrected", "uncorrected"))
     setup = runcase.load_case(str(tmp_path))
     rc = runcase._RankCase(setup)
     assert rc.model == "constScPrModel1" and rc.opts["c_tau"] == 0.6 and rc.gas["R"] == 1.0 and rc.U0.shape == (m.n_cells, 3)
@@ -295,3 +297,39 @@ def test_parallel_writer_puts_owned_results_into_processor_directories(tmp_path)
     setup.solver_kwargs["implicit_diffusion"] = True
     with pytest.raises(foamdict.FoamDictError):
         runcase._RankCase(setup)
+
+
+def test_realistic_fvschemes_keywords_and_scheme_validation(tmp_path):
+    """keywords with argument lists (`div(phiJm,U)`, `interpolate(rho)`, `laplacian(taubyrhof,p)`) are single keywords, as in
+    OpenFOAM's keyType; ddt / grad / laplacian / snGrad schemes other than what the device assembles are refused"""
+    import pytest
+    from qgdsolver_b200 import foamdict, runcase
+    realistic = HDR % "fvSchemes" + """
+ddtSchemes { default Euler; }
+gradSchemes { default Gauss linear; grad(p) Gauss linear; }
+divSchemes { default none; div(phiJm) Gauss linear; div(phiJm,U) Gauss linear; div((muf*dev2(T(grad(U))))) Gauss linear; }
+laplacianSchemes { default Gauss linear corrected; laplacian(taubyrhof,p) Gauss linear uncorrected; }
+interpolationSchemes { default none; interpolate(rho) linear; interpolate(U) linear; interpolate((U*rhoU)) linear; }
+snGradSchemes { default corrected; }
+fvsc { default GaussVolPoint; }
+"""
+    d = foamdict.parse(realistic, "fvSchemes")
+    assert d.sub_dict("divSchemes")._tokens("div(phiJm,U)") == ["Gauss", "linear"]
+    assert d.sub_dict("divSchemes")._tokens("div((muf*dev2(T(grad(U)))))") == ["Gauss", "linear"]
+    assert d.sub_dict("interpolationSchemes").word("interpolate(rho)") == "linear"
+    assert d.sub_dict("laplacianSchemes")._tokens("laplacian(taubyrhof,p)") == ["Gauss", "linear", "uncorrected"]
+    assert runcase._check_schemes(d) == "GaussVolPoint"
+    import cases
+    ortho = cases.pm.hex_box(4, 3, 2)
+    skew = cases.pm.hex_box(4, 3, 2, perturb=0.2, seed=1)
+    runcase._check_laplacian_schemes(d, ortho)
+    with pytest.raises(foamdict.FoamDictError, match="non-orthogonal"):
+        runcase._check_laplacian_schemes(d, skew)
+    runcase._check_laplacian_schemes(foamdict.parse(realistic.replace(" corrected;", " uncorrected;"), "fvSchemes"), skew)
+    for bad, what in (("default Euler;", "default backward;"), ("grad(p) Gauss linear;", "grad(p) leastSquares;"),
+                      ("div(phiJm,U) Gauss linear;", "div(phiJm,U) Gauss upwind;"), ("interpolate(U) linear;", "interpolate(U) vanLeer;")):
+        with pytest.raises(foamdict.FoamDictError):
+            runcase._check_schemes(foamdict.parse(realistic.replace(bad, what), "fvSchemes"))
+    with pytest.raises(foamdict.FoamDictError):
+        runcase._check_laplacian_schemes(foamdict.parse(realistic.replace("laplacian(taubyrhof,p) Gauss linear uncorrected;",
+                                                                           "laplacian(taubyrhof,p) Gauss harmonic corrected;"), "fvSchemes"), ortho)
