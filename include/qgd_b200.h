@@ -151,6 +151,15 @@ typedef struct {
     /* QGD sub-dictionary entries of varScModel7 (varScModel7.C:96-119): cSc1 (default 1), minSc / maxSc
      * (default -1 = off).  Read only when qgd_coeffs_model is "varScModel7"; "varScModel6" has none.  */
     double varsc_cSc1, varsc_minSc, varsc_maxSc;
+    /* thermoType instantiations of psiQGDThermos.C:65-111 (all pureMixture / perfectGas / sensibleInternalEnergy):
+     *   transport_model  NULL | "const" (mu, Pr above) | "sutherland" (As, Ts [OF-v2312 sutherlandTransportI.H]) |
+     *                    "powerLaw" (mu0, T0, k_exp, Pr; powerLawTransportI.H:120-150)
+     *   thermo_model     NULL | "hConst" (Cp, Hf, Tref, Hsref above) | "eConst" (Cv, Hf, Tref, Esref; const transport only) */
+    const char* transport_model;
+    double As, Ts;
+    double mu0, T0, k_exp;
+    const char* thermo_model;
+    double Cv, Esref;
 } qgd_qgdfoam_desc;
 
 int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* desc, qgd_solver** out);

@@ -40,7 +40,8 @@ class QGDParams(C.Structure):
                 ("energyDdtRhoEQuirk", C.c_int), ("qgdModel", C.c_int),
                 ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int),
                 ("varScCSc1", C.c_double), ("varScMinSc", C.c_double), ("varScMaxSc", C.c_double),
-                ("transportModel", C.c_int), ("mu0", C.c_double), ("T0", C.c_double), ("kExp", C.c_double)]
+                ("transportModel", C.c_int), ("mu0", C.c_double), ("T0", C.c_double), ("kExp", C.c_double),
+                ("As", C.c_double), ("Ts", C.c_double), ("thermoModel", C.c_int), ("Cv", C.c_double), ("Esref", C.c_double)]
 
 
 QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2, "varScModel6": 6, "varScModel7": 7}

@@ -652,8 +652,13 @@ void fvscDiv(const or_ctx& m, int scheme, int k, const double* cell, const doubl
 struct Thermo {
     double R, Cp, Hf, Tref, Hsref, mu, Pr;
     int transport = 0; double mu0 = 0, T0 = 1, kExp = 0;                       // powerLawTransport.C:53-60
-    double Cv() const { return Cp - R; }                                       // Cv = Cp - CpMCv, CpMCv = R
-    double Es(double /*p*/, double T) const { return Cp * (T - Tref) + Hsref - R * T; }   // Hs - p/rho
+    double As = 0, Ts = 0;                                                     // sutherlandTransport [OF-v2312]
+    int eConst = 0; double CvE = 0, Esref = 0;                                 // eConstThermo [OF-v2312]: Cv, Esref; Cp = Cv + CpMCv
+    double Cv() const { return eConst ? CvE : Cp - R; }                        // hConst: Cv = Cp - CpMCv, CpMCv = R
+    double CpT() const { return eConst ? CvE + R : Cp; }
+    double Es(double /*p*/, double T) const {                                  // hConst: Hs - p/rho ; eConst: eConstThermoI.H Es
+        return eConst ? CvE * (T - Tref) + Esref : Cp * (T - Tref) + Hsref - R * T;
+    }
     double HE(double p, double T) const { return Es(p, T); }
     double THE(double e, double p, double T0) const {                          // thermo::T Newton loop, tol 1e-4
         double Test = T0, Tnew = T0;
@@ -667,15 +672,25 @@ struct Thermo {
         return Tnew;
     }
     double psi(double /*p*/, double T) const { return 1.0 / (R * T); }
-    double muF(double, double T) const { return transport == 1 ? mu0 * std::pow(T / T0, kExp) : mu; }       // powerLawTransportI.H:121-128
-    double alphah(double p, double T) const { return transport == 1 ? muF(p, T) * (1.0 / Pr) : mu / Pr; }    // :143-150 (rPr_) | constTransport
-    double gamma() const { return Cp / Cv(); }
+    double muF(double, double T) const {
+        if (transport == 1) return mu0 * std::pow(T / T0, kExp);               // powerLawTransportI.H:121-128
+        if (transport == 2) return As * std::sqrt(T) / (1.0 + Ts / T);         // sutherlandTransportI.H mu()
+        return mu;
+    }
+    double alphah(double p, double T) const {
+        if (transport == 1) return muF(p, T) * (1.0 / Pr);                     // powerLawTransportI.H:143-150 (rPr_)
+        if (transport == 2) { const double cv = Cv(); return muF(p, T) * cv * (1.32 + 1.77 * R / cv) / CpT(); }   // kappa/Cp, modified Eucken
+        return mu / Pr;                                                        // constTransport
+    }
+    double gamma() const { return CpT() / Cv(); }
 };
 
 Thermo thermoOf(const or_ctx& s)
 {
     Thermo t{s.prm.R, s.prm.Cp, s.prm.Hf, s.prm.Tref, s.prm.Hsref, s.prm.mu, s.prm.Pr};
     t.transport = s.prm.transportModel; t.mu0 = s.prm.mu0; t.T0 = s.prm.T0; t.kExp = s.prm.kExp;
+    t.As = s.prm.As; t.Ts = s.prm.Ts;
+    t.eConst = s.prm.thermoModel == 1; t.CvE = s.prm.Cv; t.Esref = s.prm.Esref;
     return t;
 }
 
@@ -824,7 +839,7 @@ void thermoCorrect(or_ctx& s)
         s.muB[b] = th.muF(s.pB[b], s.TB[b]);
         s.alphaB[b] = th.alphah(s.pB[b], s.TB[b]);
     }
-    const double g = th.Cp / th.Cv();                                                      // :123
+    const double g = th.gamma();                                                           // :123  Cp/Cv
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
     for (int c = 0; c < s.nCells; ++c) { s.gamma[c] = g; s.c[c] = std::sqrt(s.gamma[c] / s.psi[c]); }   // :124
     for (int b = 0; b < s.nBnd; ++b) { s.gammaB[b] = g; s.cB[b] = patchIsEmpty(s, b) ? 1.0 : std::sqrt(s.gammaB[b] / s.psiB[b]); }

@@ -70,10 +70,15 @@ typedef struct {
     int diffMaxIter, diffPrecond;
     // varScModel7 dictionary entries (varScModel7.C:96-119): cSc1 (default 1), minSc / maxSc (default -1 = off)
     double varScCSc1, varScMinSc, varScMaxSc;
-    // transport model: 0 const (mu, Pr above), 1 powerLaw  mu = mu0 (T/T0)^k, alphah = mu * (1/Pr)  (powerLawTransportI.H:120-150).
-    // Oracle only so far: the device library implements const transport.
+    // transport model (psiQGDThermos.C:65-111): 0 const (mu, Pr above), 1 powerLaw  mu = mu0 (T/T0)^k, alphah = mu * (1/Pr)
+    // (powerLawTransportI.H:120-150), 2 sutherland  mu = As sqrt(T)/(1 + Ts/T), alphah = mu Cv (1.32 + 1.77 R/Cv)/Cp [OF-v2312
+    // sutherlandTransportI.H]
     int transportModel;
     double mu0, T0, kExp;
+    double As, Ts;
+    // thermo model: 0 hConst (Cp, Hf, Tref, Hsref above), 1 eConst  Es = Cv (T - Tref) + Esref, Cp = Cv + R [OF-v2312 eConstThermoI.H]
+    int thermoModel;
+    double Cv, Esref;
 } or_qgd_params_t;
 
 typedef struct or_ctx or_ctx;

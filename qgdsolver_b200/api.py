@@ -68,7 +68,10 @@ class QGDFoamDesc(C.Structure):
                 ("max_co", C.c_double), ("max_delta_t", C.c_double), ("c_tau", C.c_double), ("delta_t", C.c_double),
                 ("diff_tolerance", C.c_double), ("diff_rel_tol", C.c_double), ("diff_max_iter", C.c_int),
                 ("diff_preconditioner", C.c_char_p),
-                ("varsc_cSc1", C.c_double), ("varsc_minSc", C.c_double), ("varsc_maxSc", C.c_double)]
+                ("varsc_cSc1", C.c_double), ("varsc_minSc", C.c_double), ("varsc_maxSc", C.c_double),
+                ("transport_model", C.c_char_p), ("As", C.c_double), ("Ts", C.c_double),
+                ("mu0", C.c_double), ("T0", C.c_double), ("k_exp", C.c_double),
+                ("thermo_model", C.c_char_p), ("Cv", C.c_double), ("Esref", C.c_double)]
 
 
 class QHDFoamDesc(C.Structure):
@@ -304,9 +307,13 @@ class QGDFoam:
                  fvsc_scheme="GaussVolPoint", qgd_coeffs="constScPrModel1", implicit_diffusion=False,
                  alpha_eff_gamma_factor=True, energy_ddt_rhoE_quirk=True, adjust_time_step=False, max_co=0.3,
                  max_delta_t=1e30, c_tau=0.75, delta_t=1e-4, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000,
-                 diff_precond="DIC", varsc_cSc1=1.0, varsc_minSc=-1.0, varsc_maxSc=-1.0):
+                 diff_precond="DIC", varsc_cSc1=1.0, varsc_minSc=-1.0, varsc_maxSc=-1.0,
+                 transport="const", As=0.0, Ts=0.0, mu0=0.0, T0=1.0, k_exp=0.0, thermo="hConst", Cv=0.0, Esref=0.0):
         self.mesh = mesh
         d = QGDFoamDesc()
+        self._thermo_names = (transport.encode(), thermo.encode())
+        d.transport_model, d.thermo_model = self._thermo_names
+        d.As, d.Ts, d.mu0, d.T0, d.k_exp, d.Cv, d.Esref = As, Ts, mu0, T0, k_exp, Cv, Esref
         d.varsc_cSc1, d.varsc_minSc, d.varsc_maxSc = varsc_cSc1, varsc_minSc, varsc_maxSc
         self._names = (fvsc_scheme.encode(), qgd_coeffs.encode(), diff_precond.encode())
         d.fvsc_scheme, d.qgd_coeffs_model, d.diff_preconditioner = self._names

@@ -222,7 +222,11 @@ __global__ void k_pack_state(Consts k, int n, double* S, const double* __restric
     const double rhoE = st[10 * N + c], mu = st[11 * N + c];
     const double psi = 1.0 / (k.R * T);
     const double cs = sqrt(k.gamma / psi);
-    const double alpha = k.mu / k.Pr + (mu - k.mu) / k.PrQGD;
+    // thermo:mu = mu(T) + muQGD (QGDThermo.C:91-98): the molecular part follows the transport model, the rest is muQGD
+    double muT = k.mu, aT = k.mu / k.Pr;
+    if (k.transport == 1) { muT = k.mu0 * pow(T / k.T0, k.kExp); aT = muT * k.rPr; }
+    else if (k.transport == 2) { muT = k.As * sqrt(T) / (1.0 + k.Ts / T); aT = muT * k.Cv * (1.32 + 1.77 * k.R / k.Cv) / k.Cp; }
+    const double alpha = aT + (mu - muT) / k.PrQGD;
     const double v[16] = {rho, Ux, Uy, Uz, e, p, T, (rhoE + p) / rho,
                           rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha,
                           k.tauMode == 1 ? aQGD[c] * hQGD[c] / (sqrt(Ux * Ux + Uy * Uy + Uz * Uz) + cs) : aQGD[c] / cs};
@@ -987,13 +991,29 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         std::unique_ptr<qgd_solver> s(new qgd_solver());
         s->mesh = mesh;
         s->desc = *d;
-        s->desc.diff_preconditioner = nullptr;
+        s->desc.diff_preconditioner = nullptr; s->desc.transport_model = nullptr; s->desc.thermo_model = nullptr;
         s->impl.precond = diffPrecond;
         s->fvsc.reset(new qgd_fvsc());
         fvscBuild(*s->fvsc, mesh, d->fvsc_scheme);
         Consts& k = s->k;
         k.R = d->R; k.Cp = d->Cp; k.Cv = d->Cp - d->R; k.Tref = d->Tref; k.Hsref = d->Hsref; k.mu = d->mu; k.Pr = d->Pr;
         k.ScQGD = d->ScQGD; k.PrQGD = d->PrQGD; k.gamma = d->Cp / (d->Cp - d->R);
+        // thermoType instantiations of psiQGDThermos.C:65-111: transport const | sutherland | powerLaw, thermo hConst | eConst
+        const std::string transport = d->transport_model ? d->transport_model : "const";
+        const std::string thermoM = d->thermo_model ? d->thermo_model : "hConst";
+        k.transport = 0; k.eConst = 0; k.mu0 = k.T0 = k.kExp = k.rPr = k.As = k.Ts = k.Esref = 0.0;
+        if (transport == "powerLaw") {
+            if (!(d->T0 > 0.0) || !(d->Pr > 0.0)) throw Error(QGD_ERR_INVALID, "powerLaw transport: T0 and Pr must be positive");
+            k.transport = 1; k.mu0 = d->mu0; k.T0 = d->T0; k.kExp = d->k_exp; k.rPr = 1.0 / d->Pr;
+        } else if (transport == "sutherland") { k.transport = 2; k.As = d->As; k.Ts = d->Ts; }
+        else if (transport != "const")
+            throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown transport type " + transport + "\n\nValid transport types of hePsiQGDThermo are:\n3\n(\nconst\npowerLaw\nsutherland\n)\n");
+        if (thermoM == "eConst") {
+            if (!(d->Cv > 0.0)) throw Error(QGD_ERR_INVALID, "eConst thermo: Cv must be positive");
+            if (k.transport != 0) throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown psiQGDThermo type: eConst is instantiated with const transport only (psiQGDThermos.C:89-99)");
+            k.eConst = 1; k.Cv = d->Cv; k.Cp = d->Cv + d->R; k.Esref = d->Esref; k.gamma = k.Cp / k.Cv;
+        } else if (thermoM != "hConst")
+            throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown thermo type " + thermoM + "\n\nValid thermo types of hePsiQGDThermo are:\n2\n(\neConst\nhConst\n)\n");
         k.alphaEffGamma = d->alpha_eff_gamma_factor; k.energyQuirk = d->energy_ddt_rhoE_quirk; k.reducedScheme = s->fvsc->reduced;
         k.model = (model == "constScPrModel1" || model == "varScModel6" || model == "varScModel7") ? 0 : (model == "constScPrModel1n" ? 1 : 2);
         // varScModel6.C:207-208 / varScModel7.C:173-174: tau as constScPrModel1; ScQGD from the sensor, boundary ScQGD = dict value (clamped by model 7)

@@ -94,7 +94,24 @@ __device__ __forceinline__ void storeRec(const SolverView& sv, int k0, int i, co
 }
 
 // ---- thermo: perfectGas + hConst + sensibleInternalEnergy  [OF-v2312; SURVEY 8c item 9]
-__device__ __forceinline__ double thermoEs(const Consts& k, double T) { return k.Cp * (T - k.Tref) + k.Hsref - k.R * T; }
+__device__ __forceinline__ double thermoEs(const Consts& k, double T)
+{
+    return k.eConst ? k.Cv * (T - k.Tref) + k.Esref             // eConstThermo::Es [OF-v2312]
+                    : k.Cp * (T - k.Tref) + k.Hsref - k.R * T;  // hConstThermo::Hs - p/rho
+}
+// molecular viscosity and alphah of the transport model at temperature T (hePsiQGDThermo.C:59-62)
+__device__ __forceinline__ double muMol(const Consts& k, double T)
+{
+    if (k.transport == 1) return k.mu0 * pow(T / k.T0, k.kExp);          // powerLawTransportI.H:121-128
+    if (k.transport == 2) return k.As * sqrt(T) / (1.0 + k.Ts / T);      // sutherlandTransport::mu [OF-v2312]
+    return k.mu;
+}
+__device__ __forceinline__ double alphahMol(const Consts& k, double muT)
+{
+    if (k.transport == 1) return muT * k.rPr;                            // powerLawTransportI.H:143-150
+    if (k.transport == 2) return muT * k.Cv * (1.32 + 1.77 * k.R / k.Cv) / k.Cp;   // kappa/Cp, modified Eucken [OF-v2312]
+    return k.mu / k.Pr;                                                  // constTransport
+}
 __device__ __forceinline__ double thermoTHE(const Consts& k, double e, double T0)
 {
     double Test = T0, Tnew = T0;
@@ -796,15 +813,16 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     const double tau = tauByU ? aQGD * hQGD / (sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + c) : aQGD * hQGD / c;
     const double muQGD = pOld * (sv.scVar ? sv.scVar[cell] : k.ScQGD) * tau;     // varScModel6.C:313-322
     const double alphauQGD = muQGD / k.PrQGD;
-    const double mu = k.mu + muQGD;                      // QGDThermo.C:91-98
-    const double alpha = k.mu / k.Pr + alphauQGD;
+    const double muT = muMol(k, T);
+    const double mu = muT + muQGD;                       // QGDThermo.C:91-98
+    const double alpha = alphahMol(k, muT) + alphauQGD;
     const double p = rho / psi;                          // QGDFoam.C:152-154
     const double H = (rhoE + p) / rho;                   // updateFields.H:71 (of the next step)
     const double a[8] = {rho, U[0], U[1], U[2], e, p, T, H};
     const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, tauByU ? tau : aQGD / c};
     storeRec(sv, 0, cell, a);
     storeRec(sv, 8, cell, b);
-    if (sv.tauOut) sv.tauOut[cell] = (k.model == 2) ? tau + k.mu / (pOld * k.ScQGD) : tau;     // constScPrModel2.C:112
+    if (sv.tauOut) sv.tauOut[cell] = (k.model == 2) ? tau + muT / (pOld * k.ScQGD) : tau;      // constScPrModel2.C:112
 }
 
 // ---- leastSquares variant (2D / 1D meshes only, fvsc.C:60-63): cell-stencil gradients instead of the G record
@@ -1146,11 +1164,12 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
     const double tauB = tauByU ? aQGD * hf / (sqrt(U[0] * U[0] + U[1] * U[1] + U[2] * U[2]) + c)
                                : aQGD * hf / c;                          // hQGD_b = hQGDf_b  QGDCoeffs.C:373
     const double muQGD = pOld * k.ScB * tauB;                            // constScPrModel1.C:121-124
-    const double mu = k.mu + muQGD;
-    const double alpha = k.mu / k.Pr + muQGD / k.PrQGD;
+    const double muT = muMol(k, T);
+    const double mu = muT + muQGD;
+    const double alpha = alphahMol(k, muT) + muQGD / k.PrQGD;
     const double aByC = tauByU ? tauB : aQGD / c;                        // slot: see Consts::tauMode
     const double tauFace = tauByU ? tauB : aByC * hf;                    // tauQGDf on this boundary face after correct()
-    if (bs.tauOutB) bs.tauOutB[b] = (k.model == 2) ? tauB + k.mu / (pOld * k.ScB) : tauB;
+    if (bs.tauOutB) bs.tauOutB[b] = (k.model == 2) ? tauB + muT / (pOld * k.ScB) : tauB;
     // p.correctBoundaryConditions()   QGDFoam.C:155 ; qgdFluxFvPatchScalarField.C:159-208
     double p;
     const int bcP = bs.bcP[b];

@@ -22,6 +22,10 @@ struct Consts {
     // (k_varsc), boundary ScQGD = ScB = the dictionary value clamped by model 7's minSc / maxSc
     int varSc;               // 0 | 6 | 7
     double cSc1, minSc, maxSc, ScB;
+    // thermo-type instantiations of psiQGDThermos.C:65-111 besides const + hConst:
+    //   transport 1 powerLaw (powerLawTransportI.H:120-150), 2 sutherland [OF-v2312 sutherlandTransportI.H]; eConst [OF-v2312 eConstThermoI.H]
+    int transport, eConst;
+    double mu0, T0, kExp, rPr, As, Ts, Esref;
 };
 
 struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)

@@ -170,9 +170,16 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
     tt = thermo.sub_dict("thermoType")
     want = {"type": "heRhoQGDThermo" if qhd else "hePsiQGDThermo", "mixture": "pureMixture", "transport": "const", "thermo": "hConst",
             "equationOfState": "rhoConst" if qhd else "perfectGas", "energy": "sensibleInternalEnergy"}
+    # psiQGDThermos.C:65-111 instantiates const | sutherland | powerLaw transport with hConst, and const transport with eConst
+    psi_combos = {("const", "hConst"), ("sutherland", "hConst"), ("powerLaw", "hConst"), ("const", "eConst")}
     for k, v in want.items():
+        if not qhd and k in ("transport", "thermo"):
+            continue
         if tt.word(k) != v:
             raise FoamDictError(f"thermoType::{k} {tt.word(k)}: the device-native combination for {solver} is {v}")
+    if not qhd and (tt.word("transport"), tt.word("thermo")) not in psi_combos:
+        raise FoamDictError(f"thermoType transport {tt.word('transport')} + thermo {tt.word('thermo')}: not one of the hePsiQGDThermo "
+                            "instantiations (psiQGDThermos.C:65-111)")
     mix = thermo.sub_dict("mixture")
     tr, th = mix.sub_dict("transport"), mix.sub_dict("thermodynamics")
     qgd = thermo.sub_dict("QGD")
@@ -195,8 +202,19 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
     setup.time_precision = control.label("timePrecision", 6)
     fvsolution = foamdict.read(os.path.join(sysd, "fvSolution")) if os.path.exists(os.path.join(sysd, "fvSolution")) else None
     if not qhd:
-        kw.update(R=RR / mix.sub_dict("specie").scalar("molWeight"), Cp=th.scalar("Cp"), Hf=th.scalar("Hf", 0.0),
-                  Tref=th.scalar("Tref", TSTD), Hsref=th.scalar("Hsref", 0.0), mu=tr.scalar("mu"), Pr=tr.scalar("Pr"))
+        R = RR / mix.sub_dict("specie").scalar("molWeight")
+        kw.update(R=R, Hf=th.scalar("Hf", 0.0), Tref=th.scalar("Tref", TSTD))
+        if tt.word("thermo") == "eConst":                             # eConstThermo: Cv, Hf, Tref, Esref [OF-v2312]
+            kw.update(thermo="eConst", Cv=th.scalar("Cv"), Esref=th.scalar("Esref", 0.0), Cp=th.scalar("Cv") + R, Hsref=0.0)
+        else:
+            kw.update(Cp=th.scalar("Cp"), Hsref=th.scalar("Hsref", 0.0))
+        trm = tt.word("transport")
+        if trm == "sutherland":                                       # sutherlandTransport: As, Ts [OF-v2312]
+            kw.update(transport="sutherland", As=tr.scalar("As"), Ts=tr.scalar("Ts"), mu=0.0, Pr=1.0)
+        elif trm == "powerLaw":                                       # powerLawTransport.C:53-60: mu0, T0, k, Pr
+            kw.update(transport="powerLaw", mu0=tr.scalar("mu0"), T0=tr.scalar("T0"), k_exp=tr.scalar("k"), mu=0.0, Pr=tr.scalar("Pr"))
+        else:
+            kw.update(mu=tr.scalar("mu"), Pr=tr.scalar("Pr"))
         if model in ("constScPrModel1", "constScPrModel1n"):          # constScPrModel1.C:58-89: optional, default 1
             kw.update(ScQGD=coeffs.scalar("ScQGD", 1.0), PrQGD=coeffs.scalar("PrQGD", 1.0))
         else:                                                         # constScPrModel2.C:60-61, varScModel5.C:73-74: mandatory
@@ -333,6 +351,7 @@ class _RankCase:
             raise FoamDictError("-parallel: only QGDFoam with implicitDiffusion false runs on several GPUs yet")
         self.mesh, self.scheme, self.model, self.dt = setup.mesh, k["fvsc_scheme"], k["qgd_coeffs"], k["delta_t"]
         self.gas = {n: k[n] for n in ("R", "Cp", "Hf", "Tref", "Hsref", "mu", "Pr", "ScQGD", "PrQGD")}
+        self.gas.update({n: k[n] for n in ("transport", "As", "Ts", "mu0", "T0", "k_exp", "thermo", "Cv", "Esref") if n in k})
         self.opts = {n: k[n] for n in ("adjust_time_step", "max_co", "max_delta_t", "c_tau")}
         self.varsc = dict(cSc1=k.get("varsc_cSc1", 1.0), minSc=k.get("varsc_minSc", -1.0), maxSc=k.get("varsc_maxSc", -1.0), const_sc_cells=None)
         if setup.const_sc_cell_set:

@@ -17,7 +17,9 @@ class Case:
                  alphaQGD=None, model="constScPrModel1", implicit=False, diff_solver=None, varsc=None, sources=None, **opts):
         self.model, self.implicit = model, implicit
         self.sources = sources          # (rhoSu, rhoUSu, rhoESu) volume-integrated explicit sources or None (createZeroSources.H:28-44)
-        self.power_law = None           # dict(mu0, T0, k): powerLaw transport - oracle only so far (powerLawTransportI.H:120-150)
+        self.power_law = None           # dict(mu0, T0, k): powerLaw transport (powerLawTransportI.H:120-150)
+        self.sutherland = None          # dict(As, Ts): sutherland transport [OF-v2312]
+        self.e_const = None             # dict(Cv, Esref): eConst thermo instead of hConst [OF-v2312]
         # varScModel7 dictionary entries (cSc1, minSc, maxSc) and the constScCellSet cell list
         self.varsc = dict(cSc1=1.0, minSc=-1.0, maxSc=-1.0, const_sc_cells=None)
         self.varsc.update(varsc or {})
@@ -44,6 +46,10 @@ class Case:
                           varScCSc1=self.varsc["cSc1"], varScMinSc=self.varsc["minSc"], varScMaxSc=self.varsc["maxSc"])
         if self.power_law:
             prm.transportModel, prm.mu0, prm.T0, prm.kExp = 1, self.power_law["mu0"], self.power_law["T0"], self.power_law["k"]
+        if self.sutherland:
+            prm.transportModel, prm.As, prm.Ts = 2, self.sutherland["As"], self.sutherland["Ts"]
+        if self.e_const:
+            prm.thermoModel, prm.Cv, prm.Esref = 1, self.e_const["Cv"], self.e_const["Esref"]
         scheme = O.FVSC_SCHEMES[self.scheme]
         o.qgd_init(prm, self.bcU, self.bcT, self.bcP, self.bvU, self.bvT, self.bvP, self.U0, self.T0, self.p0,
                    alphaQGD=self.alphaQGD, deltaT=self.dt, scheme=scheme, const_sc_cells=self.varsc["const_sc_cells"])
@@ -59,7 +65,14 @@ class Case:
     def make_solver(self, api, dmesh=None):
         dmesh = dmesh or api.Mesh(self.mesh)
         ds = self.diff_solver
-        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, implicit_diffusion=self.implicit,
+        tk = {}
+        if self.power_law:
+            tk.update(transport="powerLaw", mu0=self.power_law["mu0"], T0=self.power_law["T0"], k_exp=self.power_law["k"])
+        if self.sutherland:
+            tk.update(transport="sutherland", As=self.sutherland["As"], Ts=self.sutherland["Ts"])
+        if self.e_const:
+            tk.update(thermo="eConst", Cv=self.e_const["Cv"], Esref=self.e_const["Esref"])
+        s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, implicit_diffusion=self.implicit, **tk,
                         diff_tol=ds["tol"], diff_rel_tol=ds["rel_tol"], diff_max_iter=ds["max_iter"], diff_precond=ds["precond"],
                         varsc_cSc1=self.varsc["cSc1"], varsc_minSc=self.varsc["minSc"], varsc_maxSc=self.varsc["maxSc"],
                         **self.gas, **self.opts)
@@ -125,8 +138,8 @@ def case_hex3d(n=(8, 7, 6), perturb=0.0, grading=(1, 1, 1), bcs="zg", gas=GAS, d
     return _with_bcs(mesh, bcs, gas, dt, **opts)
 
 
-def case_prism(n=(5, 4, 4), perturb=0.1, bcs="zg", **opts):
-    return _with_bcs(pm.prism_box(*n, perturb=perturb, seed=5), bcs, GAS, 1e-4, **opts)
+def case_prism(n=(5, 4, 4), perturb=0.1, bcs="zg", gas=GAS, **opts):
+    return _with_bcs(pm.prism_box(*n, perturb=perturb, seed=5), bcs, gas, 1e-4, **opts)
 
 
 def case_poly(n=(5, 5, 4), bcs="zg", **opts):
@@ -134,7 +147,7 @@ def case_poly(n=(5, 5, 4), bcs="zg", **opts):
     return _with_bcs(mesh, bcs, GAS, 1e-4, **opts)
 
 
-def case_2d(n=(24, 20), perturb=0.0, bcs="zg", axis=2, **opts):
+def case_2d(n=(24, 20), perturb=0.0, bcs="zg", axis=2, gas=GAS, **opts):
     kinds = {0: {"xMin": "empty", "xMax": "empty"}, 1: {"yMin": "empty", "yMax": "empty"},
              2: {"zMin": "empty", "zMax": "empty"}}[axis]
     dims = [n[0], n[1]]
@@ -142,7 +155,7 @@ def case_2d(n=(24, 20), perturb=0.0, bcs="zg", axis=2, **opts):
     lengths = [1.0, 1.0]
     lengths.insert(axis, 0.1)
     mesh = pm.hex_box(*dims, lengths=lengths, patch_kinds=kinds, perturb=perturb, seed=7)
-    return _with_bcs(mesh, bcs, GAS, 2e-4, **opts)
+    return _with_bcs(mesh, bcs, gas, 2e-4, **opts)
 
 
 def case_sod(n=200, dt=2e-4, **opts):

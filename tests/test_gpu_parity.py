@@ -118,9 +118,21 @@ STEP_CASES = {
     "prism_slip_model1n": lambda: _slip_case(cases.case_prism(bcs="zg", model="constScPrModel1n")),
     "2d_slip_adjust": lambda: _slip_case(cases.case_2d(perturb=0.2, bcs="zg", adjust_time_step=True, max_co=0.1)),
     "poly_slip_reduced": lambda: _slip_case(cases.case_poly(bcs="zg", scheme="reduced")),
+    # the other thermoType instantiations of psiQGDThermos.C:65-111: powerLaw / sutherland transport, eConst thermo
+    "hex_powerLaw": lambda: _thermo_case(cases.case_hex3d(perturb=0.15, bcs="mixed", gas=dict(cases.GAS, mu=3e-3)), power_law=dict(mu0=3e-3, T0=0.7, k=0.76)),
+    "prism_sutherland_model2": lambda: _thermo_case(cases.case_prism(bcs="fixed", model="constScPrModel2", gas=dict(cases.GAS, mu=3e-3)),
+                                                    sutherland=dict(As=2.5e-3, Ts=0.4)),
+    "2d_sutherland_implicit": lambda: _thermo_case(cases.case_2d(perturb=0.1, bcs="fixed", implicit=True), sutherland=dict(As=2.5e-3, Ts=0.4)),
+    "hex_eConst": lambda: _thermo_case(cases.case_hex3d(perturb=0.1, bcs="mixed", gas=dict(cases.GAS, Tref=0.2)), e_const=dict(Cv=1.5, Esref=0.05)),
+    "sod_eConst_adjust": lambda: _thermo_case(cases.case_sod(200, adjust_time_step=True, max_co=0.2), e_const=dict(Cv=2.5, Esref=0.0)),
     # BASELINE configs[1] in miniature: Mach-3 forward-facing step, slip walls + step (polymesh.forward_step)
     "forward_step_30": lambda: cases.case_forward_step(n=30),
 }
+
+
+def _thermo_case(c, power_law=None, sutherland=None, e_const=None):
+    c.power_law, c.sutherland, c.e_const = power_law, sutherland, e_const
+    return c
 
 
 def _slip_case(c):

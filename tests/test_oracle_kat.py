@@ -1151,8 +1151,7 @@ def test_least_squares_degenerate_face_set(oracle_mod):
 
 def test_power_law_transport_in_the_oracle(oracle_mod):
     """powerLawTransportI.H:120-150: mu = mu0 (T/T0)^k, alphah = mu (1/Pr); the QGD parts are added on top
-    (QGDThermo.C:91-98).  With k = 0 and mu0 = mu the run is the constant-transport run bit for bit.  (Oracle only: the
-    device library implements const transport and refuses anything else.)"""
+    (QGDThermo.C:91-98).  With k = 0 and mu0 = mu the run is the constant-transport run bit for bit."""
     gas = dict(cases.GAS, mu=3e-3)
     c = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=gas)
     c.power_law = dict(mu0=3e-3, T0=0.7, k=0.76)
@@ -1174,10 +1173,49 @@ def test_power_law_transport_in_the_oracle(oracle_mod):
     assert np.abs(o.get("rhoE") - b.get("rhoE")).max() > 1e-9                      # the temperature dependence matters
 
 
+def test_sutherland_transport_and_econst_thermo_in_the_oracle(oracle_mod):
+    """The other two instantiations of psiQGDThermos.C:65-111.  sutherland [OF-v2312 sutherlandTransportI.H]: mu = As sqrt(T)/(1+Ts/T),
+    alphah = kappa/Cp with the modified Eucken kappa = mu Cv (1.32 + 1.77 R/Cv).  eConst [OF-v2312 eConstThermoI.H]: Es = Cv (T - Tref)
+    + Esref, Cp = Cv + R, gamma = Cp/Cv; with Cv = Cp - R, Esref = Hsref - R Tref it is the hConst gas again (same e(T) up to
+    rounding), so the two runs agree to round-off accumulation."""
+    gas = dict(cases.GAS, mu=3e-3)
+    c = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=gas)
+    c.sutherland = dict(As=2.5e-3, Ts=0.4)
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 5)
+    T = o.get("T")
+    mol = 2.5e-3 * np.sqrt(T) / (1.0 + 0.4 / T)
+    Cv = gas["Cp"] - gas["R"]
+    amol = mol * Cv * (1.32 + 1.77 * gas["R"] / Cv) / gas["Cp"]
+    mu, alpha = o.get("mu"), o.get("alpha")
+    muQ = mu - mol
+    assert muQ.min() > 0 and np.abs(alpha - (amol + muQ / gas["PrQGD"])).max() < 1e-15
+    base = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=gas).make_oracle(oracle_mod)
+    c.oracle_step(base, 5)
+    assert np.abs(o.get("rhoE") - base.get("rhoE")).max() > 1e-9
+    # eConst with the equivalent coefficients == hConst
+    g2 = dict(cases.GAS, Tref=0.2, Hsref=0.1)
+    h = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=g2)
+    e = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=g2)
+    e.e_const = dict(Cv=g2["Cp"] - g2["R"], Esref=g2["Hsref"] - g2["R"] * g2["Tref"])
+    oh, oe = h.make_oracle(oracle_mod), e.make_oracle(oracle_mod)
+    assert np.abs(oe.get("e") - ((g2["Cp"] - g2["R"]) * (oe.get("T") - 0.2) + (0.1 - g2["R"] * 0.2))).max() < 1e-15
+    h.oracle_step(oh, 20); e.oracle_step(oe, 20)
+    for f in ("rho", "rhoU", "rhoE", "T", "c"):
+        assert np.abs(oh.get(f) - oe.get(f)).max() < 1e-12 * np.abs(oh.get(f)).max(), f
+    # a genuinely different gas: Cv chosen freely changes gamma = (Cv + R)/Cv and the sound speed c = sqrt(gamma R T)
+    e2 = cases.case_hex3d(n=(6, 5, 4), perturb=0.15, bcs="fixed", gas=g2)
+    e2.e_const = dict(Cv=1.5, Esref=0.05)
+    o2 = e2.make_oracle(oracle_mod)
+    assert np.abs(o2.get("c") - np.sqrt((2.5 / 1.5) * g2["R"] * o2.get("T"))).max() < 1e-14
+    e2.oracle_step(o2, 10)
+    assert np.isfinite(o2.get("rhoE")).all()
+
+
 def test_slip_walls_in_the_oracle(oracle_mod):
     """slip / symmetryPlane velocity [OF basicSymmetry]: U_b = U_P - n (n . U_P).  A channel with slip side walls, inflow / outflow
     by zeroGradient: a uniform stream along the channel stays exactly uniform (nothing to regularise, no wall shear), the wall-normal
-    boundary velocity is zero for any interior field, and the mass flux through the slip walls vanishes.  (Oracle only so far.)"""
+    boundary velocity is zero for any interior field, and the mass flux through the slip walls vanishes."""
     c = cases.case_hex3d(n=(8, 5, 4), bcs="zg", gas=dict(cases.GAS, mu=1e-2))
     m = c.mesh
     names = [p.name for p in m.patches]
