@@ -261,6 +261,12 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int n_neighbours, const int* nbr_rank,
                          const int* send_cell_off, const int* send_cells, const int* recv_cell_off, const int* recv_cells,
                          const int* send_bf_off, const int* send_bfaces, const int* recv_bf_off, const int* recv_bfaces);
 
+/* implicitDiffusion true on extended sub-meshes additionally needs the face-neighbour subset of the halo (same list form):
+ * the search direction of every PCG iteration of the U and e solves (QGDUEqn.H:54-75, QGDEEqn.H:53-64) and the cell-centred
+ * fvc::grad(U) are exchanged over it, the dot products are all-reduced (preconditioner diagonal | none on sub-meshes). */
+int qgd_qgdfoam_set_halo_faces(qgd_solver* s, int n_neighbours, const int* nbr_rank, const int* send_off, const int* send_cells,
+                               const int* recv_off, const int* recv_cells);
+
 /* ---- QHDFoam (solver-level integration) -------------------------------------
  * Replaces the loop body QHDFoam.C:83-139 (explicit branch) with rhoQGDThermo::New -> heRhoQGDThermo<rhoConst,
  * hConst, const> (rhoQGDThermos.C:76-140, heRhoQGDThermo.C:38-139), a QHD-family QGDCoeffs model

@@ -31,7 +31,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
-    "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo",
+    "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo", "qgd_qgdfoam_set_halo_faces",
     "qgd_pcg_solve", "qgd_pcg_solve_stepwise", "qgd_pcg_solve_multi",
     "qgd_qhdfoam_create", "qgd_qhdfoam_destroy", "qgd_qhdfoam_set_bcs", "qgd_qhdfoam_init_fields", "qgd_qhdfoam_set_halo", "qgd_qhdfoam_step",
     "qgd_qhdfoam_get", "qgd_qhdfoam_get_flux", "qgd_qhdfoam_get_scalars", "qgd_qhdfoam_solver_info",
@@ -140,6 +140,7 @@ def load_library():
     L.qgd_comm_unique_id.argtypes = [C.c_void_p]
     L.qgd_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.qgd_qgdfoam_set_halo.argtypes = [C.c_void_p, C.c_int] + [_ip] * 9
+    L.qgd_qgdfoam_set_halo_faces.argtypes = [C.c_void_p, C.c_int] + [_ip] * 5
     L.qgd_pcg_solve_multi.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
                                       C.c_int, _ip, _ip, _ip, _ip, _ip, _ip, _dp, _dp]
     L.qgd_pcg_solve_stepwise.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_int,
@@ -371,6 +372,22 @@ class QGDFoam:
         nb = np.asarray(nbrs, np.int32) if nbrs else np.zeros(1, np.int32)
         _check(load_library().qgd_qgdfoam_set_halo(self._h, len(nbrs), _i(nb), _i(sco), _i(sc), _i(rco), _i(rc),
                                                    _i(sbo), _i(sb), _i(rbo), _i(rb)))
+        # face-neighbour subset (implicit branch: PCG search direction, fvc::grad(U))
+        fn = sorted(set(sub.send_face_cells) | set(sub.recv_face_cells))
+        if fn:
+            def packf(d):
+                off = np.zeros(len(fn) + 1, np.int32)
+                parts = []
+                for k, r in enumerate(fn):
+                    a = np.asarray(d.get(r, np.zeros(0, np.int32)), np.int32)
+                    parts.append(a)
+                    off[k + 1] = off[k] + a.size
+                ids = np.concatenate(parts).astype(np.int32)
+                return off, np.ascontiguousarray(ids if ids.size else np.zeros(1, np.int32))
+            fso, fsc = packf(sub.send_face_cells)
+            fro, frc = packf(sub.recv_face_cells)
+            fnb = np.asarray(fn, np.int32)
+            _check(load_library().qgd_qgdfoam_set_halo_faces(self._h, len(fn), _i(fnb), _i(fso), _i(fsc), _i(fro), _i(frc)))
 
     @staticmethod
     def _state_struct(bufs) -> _StateHost:

@@ -161,6 +161,8 @@ struct qgd_solver {
         bool pending = false;                  // an exchange is in flight on the communication stream
         bool active = false;
     } halo;
+    HaloLists haloFace;                        // face-neighbour subset of the halo (implicit branch: PCG search direction, fvc::grad(U))
+    StepwisePcg sw;                            // decomposed linear solves of the implicit branch
     // per-kernel CUDA-event timing (bench): events of the profiled steps, 6 per step
     bool profiling = false;
     std::vector<cudaEvent_t> events;
@@ -229,7 +231,7 @@ __global__ void k_pack_state(Consts k, int n, double* S, const double* __restric
     const double alpha = aT + (mu - muT) / k.PrQGD;
     const double v[16] = {rho, Ux, Uy, Uz, e, p, T, (rhoE + p) / rho,
                           rUx, rUy, rUz, rhoE, cs, mu, k.alphaEffGamma ? k.gamma * alpha : alpha,
-                          k.tauMode == 1 ? aQGD[c] * hQGD[c] / (sqrt(Ux * Ux + Uy * Uy + Uz * Uz) + cs) : aQGD[c] / cs};
+                          k.tauMode == 1 ? aQGD[c] * hQGD[c] / (sqrt(Ux * Ux + Uy * Uy + Uz * Uz) + cs) : (k.tauMode == 2 ? aQGD[c] : aQGD[c] / cs)};
 #pragma unroll
     for (int j = 0; j < 16; ++j) S[j * N + c] = v[j];
 }
@@ -521,12 +523,17 @@ void runStepsImplicit(qgd_solver* s, int n)
     const HostMesh& h = s->mesh->h;
     const size_t nC = h.nCells, nF = h.nFaces;
     qgd_solver::Implicit& I = s->impl;
+    const bool multi = s->halo.active && g_nranks > 1;
+    if (multi && !s->haloFace.active())
+        throw Error(QGD_ERR_STATE, "implicitDiffusion true on an extended sub-mesh needs the face-neighbour lists (qgd_qgdfoam_set_halo_faces)");
     if (!I.built) {
         I.GU0.alloc(9 * nC); I.GU1.alloc(9 * nC); I.old.alloc(4 * nC); I.FT.alloc(3 * nF); I.aU.alloc(nF); I.aE.alloc(nF); I.Fs.alloc(nF);
         I.diagU.alloc(nC); I.bU.alloc(3 * nC); I.diagE.alloc(nC); I.bE.alloc(nC);
+        I.diagU.zero(g_stream); I.diagE.zero(g_stream);
         std::vector<double> ones(nC, 1.0), zeros(std::max(h.nInternal, 1), 0.0);
         I.AU.build(h, ones.data(), zeros.data(), I.precond, g_stream, &s->mesh->faceInv);
         I.AE.build(h, ones.data(), zeros.data(), I.precond, g_stream, &s->mesh->faceInv);
+        if (multi) s->sw.alloc(I.AU, h.nOwned);
         I.built = true;
     }
     const FaceView fv = s->fvsc->view();
@@ -536,24 +543,48 @@ void runStepsImplicit(qgd_solver* s, int n)
     const bool adjust = s->desc.adjust_time_step != 0;
     const double tol = s->desc.diff_tolerance, rel = s->desc.diff_rel_tol;
     const int maxIter = s->desc.diff_max_iter > 0 ? s->desc.diff_max_iter : 1000;
+    StepHooks hooks;
+    PcgHooks ph;
+    if (multi) {
+        hooks.midStep = [s] { s->launches += haloExchangeMid(s); };
+        hooks.afterGrad = [s, nC](double* G) { s->launches += commExchange(s->haloFace, G, nC, 9, g_stream); };
+        if (adjust)
+            hooks.beforeDt = [s] {
+                StepScalars* sc = s->sc.p;
+                QGD_NCCL(g_nccl.GroupStart());
+                QGD_NCCL(g_nccl.AllReduce(&sc->coMaxBits, &sc->coMaxBits, 1, ncclDouble, ncclMax, g_comm, g_stream));
+                QGD_NCCL(g_nccl.AllReduce(&sc->tauMinBits, &sc->tauMinBits, 1, ncclDouble, ncclMin, g_comm, g_stream));
+                QGD_NCCL(g_nccl.GroupEnd());
+            };
+        ph.exchange = [s](double* vec, cudaStream_t cs) { s->launches += commExchange(s->haloFace, vec, 0, 1, cs); };
+        ph.allreduceSum = [](double* dev, int count, cudaStream_t cs) { commAllReduce(dev, count, COMM_SUM, cs); };
+    }
+    // one linear solve: the cooperative persistent kernel on one GPU, the stepwise solver with exchange / all-reduce on sub-meshes
+    auto solveSys = [&](PcgMatrix& A, double* b, double* x, int slot) {
+        A.bExternal = b; A.xExternal = x;
+        if (multi) {
+            PcgResult r;
+            s->launches += s->sw.solve(A, b, x, tol, rel, maxIter, I.precond, g_stream, &ph, &r);
+            QGD_CUDA(cudaMemcpyAsync(s->stage.p + slot * 4, &r, sizeof(PcgResult), cudaMemcpyHostToDevice, g_stream));
+            QGD_CUDA(cudaStreamSynchronize(g_stream));
+        } else {
+            s->launches += A.solve(tol, rel, maxIter, g_stream);
+            QGD_CUDA(cudaMemcpyAsync(s->stage.p + slot * 4, A.out.p, sizeof(PcgResult), cudaMemcpyDeviceToDevice, g_stream));
+        }
+    };
     for (int i = 0; i < n; ++i) {
         if (s->k.model == 1) s->k.tauMode = s->stepsDone == 0 ? 2 : 1;
         ++s->stepsDone;
-        s->launches += launchImplicitPhase(g_stream, 0, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust);
+        s->launches += launchImplicitPhase(g_stream, 0, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, multi ? &hooks : nullptr);
         I.AU.refresh(iv.aU, iv.diagU, g_stream);
-        for (int j = 0; j < 3; ++j) {                               // QGDUEqn.H:65-68, segregated components
-            I.AU.bExternal = iv.bU + j * nC;
-            I.AU.xExternal = s->S.p + (1 + j) * nC;
-            s->launches += I.AU.solve(tol, rel, maxIter, g_stream);
-            QGD_CUDA(cudaMemcpyAsync(s->stage.p + j * 4, I.AU.out.p, sizeof(PcgResult), cudaMemcpyDeviceToDevice, g_stream));
-        }
-        s->launches += 2 + launchImplicitPhase(g_stream, 1, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust);
+        for (int j = 0; j < 3; ++j) solveSys(I.AU, iv.bU + j * nC, s->S.p + (1 + j) * nC, j);      // QGDUEqn.H:65-68, segregated components
+        if (multi) s->launches += commExchange(s->haloFace, s->S.p + nC, nC, 3, g_stream);          // solved U of the face neighbours
+        s->launches += 2 + launchImplicitPhase(g_stream, 1, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, multi ? &hooks : nullptr);
         I.AE.refresh(iv.aE, iv.diagE, g_stream);
-        I.AE.bExternal = iv.bE;
-        I.AE.xExternal = s->S.p + 4 * nC;
-        s->launches += 2 + I.AE.solve(tol, rel, maxIter, g_stream);   // QGDEEqn.H:55-61
-        QGD_CUDA(cudaMemcpyAsync(s->stage.p + 12, I.AE.out.p, sizeof(PcgResult), cudaMemcpyDeviceToDevice, g_stream));
-        s->launches += launchImplicitPhase(g_stream, 2, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust);
+        s->launches += 2;
+        solveSys(I.AE, iv.bE, s->S.p + 4 * nC, 3);                                                 // QGDEEqn.H:55-61
+        s->launches += launchImplicitPhase(g_stream, 2, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, multi ? &hooks : nullptr);
+        if (multi) s->launches += haloExchange(s);
     }
     QGD_CUDA(cudaGetLastError());
 }
@@ -563,7 +594,6 @@ static int h_nB(const qgd_solver* s) { return s->mesh->h.nBnd; }
 void runSteps(qgd_solver* s, int n)
 {
     if (s->k.implicit) {
-        if (s->halo.active) throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true with a halo exchange (multi-GPU) is not available yet");
         if (s->stage.n < 16) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * (size_t)s->mesh->h.nCells + 16);
         runStepsImplicit(s, n);
         return;
@@ -682,8 +712,8 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
         throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown Model type " + name + "\n\nValid model types are:\n" + toc(kFvscTable));
     if ((name == "leastSquares" || name == "leastSquaresOpt")) {
         if (mesh->h.nD == 3) throw Error(QGD_ERR_INVALID, "Can't use leastSquares or leastSquaresOpt in 3D case.");
-        if (mesh->h.nOwned != mesh->h.nCells)
-            throw Error(QGD_ERR_UNSUPPORTED, "fvsc scheme " + name + " on extended sub-meshes (multi-GPU) is not available yet");
+        // extended sub-meshes: every cell sharing a point with a face of an owned cell is present (vertex-ring halo), so the stencil of
+        // every face this rank evaluates is complete (extendedFaceStencilFindNeighbours.C:41-86); faces owned by halo cells are never computed
     }
     if (name == "GaussVolPoint") {               // fvsc.C:65-82: wedge patches + prism cells are rejected
         const HostMesh& h = mesh->h;
@@ -981,8 +1011,9 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
             const std::string pc = d->diff_preconditioner ? d->diff_preconditioner : "DIC";
             if (pc == "DIC") diffPrecond = 2; else if (pc == "diagonal") diffPrecond = 1; else if (pc == "none") diffPrecond = 0;
             else throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown symmetric matrix preconditioner " + pc + "\n\nValid symmetric matrix preconditioners are:\n3\n(\nDIC\ndiagonal\nnone\n)\n");
-            if (mesh->h.nOwned != mesh->h.nCells)
-                throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true on extended sub-meshes (multi-GPU) is not available yet");
+            if (mesh->h.nOwned != mesh->h.nCells && diffPrecond == 2)
+                throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true on extended sub-meshes (multi-GPU): the (U|e) preconditioner must be "
+                                                 "diagonal or none (DIC is local to a processor block in a decomposed run; not available on sub-meshes yet)");
         }
         for (int pk : mesh->h.patchKind)
             if (pk == QGD_PATCH_PROCESSOR)
@@ -1023,7 +1054,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
             if (k.minSc >= 0) k.ScB = std::max(k.ScB, k.minSc);
             if (k.maxSc >= 0) k.ScB = std::min(k.ScB, k.maxSc);
         }
-        k.tauMode = 0; k.alphaUniform = 0.5; k.implicit = d->implicit_diffusion ? 1 : 0;
+        k.tauMode = 0; k.implicit = d->implicit_diffusion ? 1 : 0;
         const HostMesh& h = mesh->h;
         s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
@@ -1134,11 +1165,7 @@ int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, con
         QGD_CUDA(cudaMemcpyAsync(s->stage.p + 3 * n, T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         QGD_CUDA(cudaMemcpyAsync(s->stage.p + 4 * n, p, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         if (s->k.model == 1) {
-            // constScPrModel1n forms tauQGDf = I(alphaQGD)*hQGDf/I(c) until "U" is registered (first step): the device
-            // path keeps alphaQGD as a constant there
-            s->k.alphaUniform = alphaQGD ? alphaQGD[0] : 0.5;
-            if (alphaQGD) for (size_t c = 0; c < n; ++c) if (alphaQGD[c] != alphaQGD[0])
-                throw Error(QGD_ERR_UNSUPPORTED, "constScPrModel1n on the device needs a uniform alphaQGD field");
+            // constScPrModel1n forms tauQGDf = I(alphaQGD)*hQGDf/I(c) until "U" is registered (first step, constScPrModel1n.C:104-105)
             s->k.tauMode = 2;
             s->stepsDone = 0;
         }
@@ -1503,6 +1530,17 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* 
         }
         // halo copies initialised locally carry wrong mesh-derived values (hQGD of an open halo cell): take the owners'
         if (h.active && s->fieldsSet) { s->launches += haloExchange(s); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
+    });
+}
+
+int qgd_qgdfoam_set_halo_faces(qgd_solver* s, int nn, const int* nbr_rank, const int* send_off, const int* send_cells,
+                               const int* recv_off, const int* recv_cells)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_halo_faces: null solver");
+        const HostMesh& h = s->mesh->h;
+        s->haloFace.set(nn, nbr_rank, send_off, send_cells, recv_off, recv_cells, h.nCells, h.nOwned, 9, g_stream);
     });
 }
 

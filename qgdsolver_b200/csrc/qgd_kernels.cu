@@ -550,7 +550,7 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
 #pragma unroll
         for (int j = 0; j < 3; ++j) o.s.UrhoU[3 * i + j] = o.s.U[i] * o.s.rhoU[j];
     o.s.p = a.p; o.s.c = bb.c; o.s.H = a.H; o.s.alpha = k.implicit ? 0.0 : bb.alphaEff; o.s.mu = k.implicit ? 0.0 : bb.mu;
-    o.s.tau = k.tauMode == 1 ? bb.aByC : bb.aByC * fv.hf[f];
+    o.s.tau = k.tauMode == 1 ? bb.aByC : (k.tauMode == 2 ? bb.aByC * fv.hf[f] / bb.c : bb.aByC * fv.hf[f]);
     // patch snGrad per field [OF fvPatchField::snGrad / zeroGradient / fixedGradient]
     // slip [OF-v2312 basicSymmetryFvPatchField::snGrad]: (transform(I - 2nn, U_P) - U_P) deltaCoeffs/2 = deltaCoeffs (U_b - U_P)
     const bool fixU = bs.bcU[b] == QGD_BC_FIXED_VALUE || bs.bcU[b] == QGD_BC_SLIP, fixT = bs.bcT[b] == QGD_BC_FIXED_VALUE;
@@ -737,7 +737,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
         const double tI = w * (bP.aByC - bN.aByC) + bN.aByC;
         s.tau = k.tauMode == 0 ? tI * hf                     // constScPrModel1.C:103
                                : (k.tauMode == 1 ? tI        // constScPrModel1n.C:128
-                                                 : k.alphaUniform * hf / s.c);   // constScPrModel1n.C:104
+                                                 : tI * hf / s.c);   // constScPrModel1n.C:104-105: I(alphaQGD) hQGDf / I(c)
     }
     double Fm, FU[3], FE, phiw;
     qgdFluxes(k, s, g, Sf, Fm, FU, FE, phiw);
@@ -819,7 +819,9 @@ __device__ __forceinline__ void cellThermo(const Consts& k, double rho, const do
     const double p = rho / psi;                          // QGDFoam.C:152-154
     const double H = (rhoE + p) / rho;                   // updateFields.H:71 (of the next step)
     const double a[8] = {rho, U[0], U[1], U[2], e, p, T, H};
-    const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, tauByU ? tau : aQGD / c};
+    // slot `aByC`: alphaQGD/c (tauMode 0) | tauQGD (tauMode 1) | alphaQGD (tauMode 2: constScPrModel1n until "U" is registered)
+    const double slot = tauByU ? tau : ((k.model == 1) ? aQGD : aQGD / c);
+    const double b[8] = {rhoU[0], rhoU[1], rhoU[2], rhoE, c, mu, k.alphaEffGamma ? k.gamma * alpha : alpha, slot};
     storeRec(sv, 0, cell, a);
     storeRec(sv, 8, cell, b);
     if (sv.tauOut) sv.tauOut[cell] = (k.model == 2) ? tau + muT / (pOld * k.ScQGD) : tau;      // constScPrModel2.C:112
@@ -1167,8 +1169,8 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
     const double muT = muMol(k, T);
     const double mu = muT + muQGD;
     const double alpha = alphahMol(k, muT) + muQGD / k.PrQGD;
-    const double aByC = tauByU ? tauB : aQGD / c;                        // slot: see Consts::tauMode
-    const double tauFace = tauByU ? tauB : aByC * hf;                    // tauQGDf on this boundary face after correct()
+    const double aByC = tauByU ? tauB : ((k.model == 1) ? aQGD : aQGD / c);      // slot: see Consts::tauMode / cellThermo
+    const double tauFace = tauByU ? tauB : ((k.model == 1) ? aQGD * hf / c : aByC * hf);   // tauQGDf on this boundary face after correct()
     if (bs.tauOutB) bs.tauOutB[b] = (k.model == 2) ? tauB + muT / (pOld * k.ScB) : tauB;
     // p.correctBoundaryConditions()   QGDFoam.C:155 ; qgdFluxFvPatchScalarField.C:159-208
     double p;
@@ -1429,9 +1431,13 @@ template <int W>
 __global__ void __launch_bounds__(kBlock) k_cell_implA(Consts k, FaceView fv, SolverView sv, BndState bs, ImplicitView iv)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= sv.nOwned) return;
+    if (c >= sv.nCells) return;
     const size_t n = sv.nCells, nF = fv.nF;
     const RecA a = loadA(sv, c);
+    if (c >= sv.nOwned) {        // halo copy (multi-GPU): only the old U / rho that k_face_sigma interpolates; the row belongs to another rank
+        iv.old[c] = a.Ux; iv.old[n + c] = a.Uy; iv.old[2 * n + c] = a.Uz; iv.old[3 * n + c] = a.rho;
+        return;
+    }
     const RecB b = loadB(sv, c);
     double sm = 0.0, su[3] = {0, 0, 0}, st[3] = {0, 0, 0}, dL = 0.0, bI = 0.0, bB[3] = {0, 0, 0};
     forCellFacesS(sv, c, [&](int f, int side) {
@@ -1815,7 +1821,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
 }
 
 int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-                        const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust)
+                        const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust, const StepHooks* hooks)
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
@@ -1829,22 +1835,26 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
         }
         if (fv.nB && anyQgdFlux) {
             k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+            if (hooks && hooks->midStep) hooks->midStep();
             if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
         }
         k_gauss_gradU<<<nblk(sv.nCells), kBlock, 0, st>>>(fv, sv, bs, iv.GU0, 0); ++n;
+        if (hooks && hooks->afterGrad) hooks->afterGrad(iv.GU0);
         if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
         if (fv.nIActive) {
             launchFaceKernel(st, c, fv, sv, adjust, gridFaces);
             ++n;
         }
         k_face_diff<<<nblk(fv.nF), kBlock, 0, st>>>(fv, sv, bs, iv); ++n;
+        if (hooks && hooks->beforeDt) hooks->beforeDt();
         k_dt<<<1, 1, 0, st>>>(sv.sc, nullptr); ++n;
-        if (sv.cfEllW == 4) k_cell_implA<4><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv);
-        else if (sv.cfEllW == 6) k_cell_implA<6><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv);
-        else k_cell_implA<8><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv);
+        if (sv.cfEllW == 4) k_cell_implA<4><<<nblk(sv.nCells), kBlock, 0, st>>>(c, fv, sv, bs, iv);
+        else if (sv.cfEllW == 6) k_cell_implA<6><<<nblk(sv.nCells), kBlock, 0, st>>>(c, fv, sv, bs, iv);
+        else k_cell_implA<8><<<nblk(sv.nCells), kBlock, 0, st>>>(c, fv, sv, bs, iv);
         ++n;
     } else if (phase == 1) {   // after the U solves: sigmaDotU, rhoE update, e system
         k_gauss_gradU<<<nblk(sv.nCells), kBlock, 0, st>>>(fv, sv, bs, iv.GU1, 1); ++n;
+        if (hooks && hooks->afterGrad) hooks->afterGrad(iv.GU1);
         k_face_sigma<<<nblk(fv.nF), kBlock, 0, st>>>(fv, sv, bs, iv); ++n;
         k_cell_implB<<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, iv); ++n;
     } else {                   // after the e solve: conserved variables, thermo, boundary state

@@ -14,9 +14,8 @@ struct Consts {
     // tauMode selects how tauQGDf is formed from the per-cell slot `aByC` of the state:
     //   0: I(alphaQGD/c)*hQGDf            slot = alphaQGD/c         constScPrModel1.C:103, constScPrModel2.C:82
     //   1: I(tauQGD)                      slot = tauQGD = alphaQGD*hQGD/(|U|+c)   constScPrModel1n.C:126-128
-    //   2: I(alphaQGD)*hQGDf/I(c)         (constScPrModel1n before "U" is registered, i.e. the first step; alphaQGD uniform)
+    //   2: I(alphaQGD)*hQGDf/I(c)         slot = alphaQGD   (constScPrModel1n before "U" is registered, i.e. the first step)
     int model, tauMode;
-    double alphaUniform;
     int implicit;            // QGD::implicitDiffusion: the mu / alpha terms leave the explicit fluxes (updateFluxes.H:95-111,131-135)
     // varScModel6 / varScModel7 (model stays 0: tau as constScPrModel1): per-cell ScQGD from the pressure-jump sensor
     // (k_varsc), boundary ScQGD = ScB = the dictionary value clamped by model 7's minSc / maxSc
@@ -147,7 +146,9 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 // beforeDt runs before the time-step kernel (all-reduce of the Courant max / tau min)
 // waitHalo: called right before the first kernel that reads halo copies (the packed exchange of the previous step may
 // still be in flight on the communication stream while the interior points are gathered)
-struct StepHooks { std::function<void()> midStep, beforeDt; std::function<void(cudaStream_t)> waitHalo; };
+// afterGrad (implicit branch, multi-GPU): runs after each cell-centred Gauss gradient of U with the gradient array, to fetch the
+// gradients of the face-neighbour halo cells from their owners
+struct StepHooks { std::function<void()> midStep, beforeDt; std::function<void(cudaStream_t)> waitHalo; std::function<void(double*)> afterGrad; };
 // Boundary work forked onto a second, high-priority stream: k_patch_points and k_bnd_flux of step n (and, on one GPU,
 // k_bnd_post of step n-1) depend on the cell update only, not on the point gather, so they run beside k_points
 // instead of in front of / behind the face kernel.  Joins: face kernel <- evPatch, k_dt <- evBndFlux, side <- evCell.
@@ -162,7 +163,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
                const PipeView* pipe = nullptr, int gridPipe = 0, const StepFork* fork = nullptr);
 // implicit-diffusion step, phase by phase (the PCG solves run between the phases, see runStepsImplicit in qgd_abi.cu)
 int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-                        const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust);
+                        const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust, const StepHooks* hooks = nullptr);
 int faceKernelGrid();
 int pipelineKernelGrid(int cfEllW);
 void setFaceL2Hint(int bits); // env QGD_FACE_L2HINT: bit 0 = streamed constants / fluxes evict_first, bit 1 = state gathers evict_last

@@ -202,14 +202,41 @@ __device__ __forceinline__ void gradVec(const FaceGeo& ge, int flags, const doub
     }
 }
 
+// leastSquares gradient of state field k (Q[k]) on internal face f: sum_s c_s (phi_s - phi_f), phi_f = linearInterpolate(phi)
+// (extendedFaceStencilScalarGrad.C:52-72); vectors component-wise (leastSquaresStencil.C:145-202)
+__device__ __forceinline__ void lsqGradQ(const FaceView& fv, const QhdView& q, int f, int k, double phiP, double phiN, double w, double (&g)[3])
+{
+    const size_t nI = fv.nI;
+    const double* phi = q.Q + (size_t)k * q.nCells;
+    const double sF = w * (phiP - phiN) + phiN;
+    g[0] = g[1] = g[2] = 0.0;
+    for (int s = 0; s < fv.lsqW; ++s) {
+        const int c = __ldg(&fv.lsqCells[(size_t)s * nI + f]);
+        const double d = phi[c] - sF;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) g[i] += __ldg(&fv.lsqCoef[((size_t)s * 3 + i) * nI + f]) * d;
+    }
+}
+// gradU[3*i+j] = d_i U_j with the least-squares stencil
+__device__ __forceinline__ void lsqGradVecQ(const FaceView& fv, const QhdView& q, int f, const double (&uP)[3], const double (&uN)[3], double w, double (&G)[9])
+{
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double g[3];
+        lsqGradQ(fv, q, f, j, uP[j], uN[j], w, g);
+        G[j] = g[0]; G[3 + j] = g[1]; G[6 + j] = g[2];
+    }
+}
+
 // the part of the face evaluation shared by the pre- and post-solve kernels
 struct FaceCommon { double Uf[3], Tf, Bf[3], G[9], UgU[3], phiu, tau; };
 
 __device__ __forceinline__ void faceCommon(const QhdConsts& k, const FaceGeo& ge, int flags, const double (&uP)[3], const double (&uN)[3],
-                                           double TP, double TN, double w, const double (&d1)[3], const double (&d2)[3], double tau, FaceCommon& o)
+                                           double TP, double TN, double w, const double (&d1)[3], const double (&d2)[3], double tau, FaceCommon& o,
+                                           bool haveG = false)
 {
     const double dP[3] = {uP[0] - uN[0], uP[1] - uN[1], uP[2] - uN[2]};
-    gradVec(ge, flags, d1, d2, dP, o.G);
+    if (!haveG) gradVec(ge, flags, d1, d2, dP, o.G);          // haveG: o.G already holds the leastSquares gradient
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         o.Uf[j] = w * (uP[j] - uN[j]) + uN[j];
@@ -247,7 +274,9 @@ __global__ void __launch_bounds__(kB) k_qhd_face_pre(QhdConsts k, FaceView fv, Q
         const double TP = q.Q[3 * n + P], TN = q.Q[3 * n + N];
         const double tau = __ldg(&q.tauf[f]);
         FaceCommon c;
-        faceCommon(k, ge, flags, uP, uN, TP, TN, __ldg(&fv.w[f]), d1, d2, tau, c);
+        const bool lsq = (flags & FF_LSQ) != 0;
+        if (lsq) lsqGradVecQ(fv, q, f, uP, uN, __ldg(&fv.w[f]), c.G);
+        faceCommon(k, ge, flags, uP, uN, TP, TN, __ldg(&fv.w[f]), d1, d2, tau, c, lsq);
         q.F0[f] = c.phiu - phiwoOf(ge, c);
         if (ADJUST && f < fv.nIActive) {                            // QHDCourantNo.H:39-54 (faces owned by halo cells belong to another rank)
             const double ms = __ldg(&fv.magSf[f]);
@@ -420,15 +449,22 @@ __global__ void __launch_bounds__(kB) k_qhd_face_post(QhdConsts k, FaceView fv, 
     const double TP = q.Q[3 * n + P], TN = q.Q[3 * n + N], pP = q.Q[4 * n + P], pN = q.Q[4 * n + N];
     const double w = __ldg(&fv.w[f]), tau = __ldg(&q.tauf[f]);
     FaceCommon c;
-    faceCommon(k, ge, flags, uP, uN, TP, TN, w, d1, d2, tau, c);
+    const bool lsq = (flags & FF_LSQ) != 0;
+    if (lsq) lsqGradVecQ(fv, q, f, uP, uN, w, c.G);
+    faceCommon(k, ge, flags, uP, uN, TP, TN, w, d1, d2, tau, c, lsq);
     double dT1, dT2, dp1, dp2;
     ptDiff(q, 3, v, flags, dT1, dT2);
     ptDiff(q, 4, v, flags, dp1, dp2);
     double gT[3], gPr[3];
+    if (lsq) {
+        lsqGradQ(fv, q, f, 3, TP, TN, w, gT);
+        lsqGradQ(fv, q, f, 4, pP, pN, w, gPr);
+    } else {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        gT[i] = ge.g1[i] * dT1 + ge.g2[i] * dT2 + ge.gp[i] * (TP - TN);
-        gPr[i] = ge.g1[i] * dp1 + ge.g2[i] * dp2 + ge.gp[i] * (pP - pN);
+        for (int i = 0; i < 3; ++i) {
+            gT[i] = ge.g1[i] * dT1 + ge.g2[i] * dT2 + ge.gp[i] * (TP - TN);
+            gPr[i] = ge.g1[i] * dp1 + ge.g2[i] * dp2 + ge.gp[i] * (pP - pN);
+        }
     }
     const double up = __ldg(&q.upper[f]);
     const double phi = k.scalarTransport ? c.phiu                                      // scalarTransportQHDFoam.C:110 qgdFlux(phiu,T,Tf)
@@ -782,7 +818,6 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
         s->diffPrecond = diffPrecond;
         s->fvsc.reset(new qgd_fvsc());
         fvscBuild(*s->fvsc, mesh, d->fvsc_scheme);
-        if (s->fvsc->lsq) throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam with fvsc scheme leastSquares is not available on the device yet");
         QhdConsts& k = s->k;
         k.rho0 = d->rho0; k.nu = d->mu / d->rho0; k.Hi = (d->mu / d->Pr) / d->rho0; k.beta = d->beta;
         for (int j = 0; j < 3; ++j) k.g[j] = d->g[j];

@@ -89,6 +89,9 @@ STEP_CASES = {
     "hex_model2": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel2"),
     "2d_model1n_qgdflux": lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", model="constScPrModel1n"),
     "prism_model1n_adjust": lambda: cases.case_prism(bcs="fixed", model="constScPrModel1n", adjust_time_step=True, max_co=0.1),
+    # constScPrModel1n with a non-uniform alphaQGD field (first step: I(alphaQGD) hQGDf / I(c), constScPrModel1n.C:104-105)
+    "hex_model1n_alpha_field": lambda: _alpha_case(cases.case_hex3d(perturb=0.15, bcs="mixed", model="constScPrModel1n")),
+    "2d_model1_alpha_field_qgdflux": lambda: _alpha_case(cases.case_2d(perturb=0.1, bcs="qgdflux")),
     # varScModel6 / varScModel7: ScQGD from the pressure-jump sensor (varScModel6.C:210-269, varScModel7.C:176-254)
     "hex_varSc6_mixed": lambda: cases.case_hex3d(perturb=0.15, bcs="mixed", model="varScModel6"),
     "poly_varSc6_qgdflux": lambda: cases.case_poly(bcs="qgdflux", model="varScModel6"),
@@ -128,6 +131,13 @@ STEP_CASES = {
     # BASELINE configs[1] in miniature: Mach-3 forward-facing step, slip walls + step (polymesh.forward_step)
     "forward_step_30": lambda: cases.case_forward_step(n=30),
 }
+
+
+def _alpha_case(c):
+    """0/alphaQGD present and non-uniform (QGDCoeffs.C:119-143)"""
+    x = c.mesh.C
+    c.alphaQGD = 0.35 + 0.3 * np.sin(4 * x[:, 0]) ** 2 + 0.1 * np.random.default_rng(9).random(c.mesh.n_cells)
+    return c
 
 
 def _thermo_case(c, power_law=None, sutherland=None, e_const=None):

@@ -105,6 +105,10 @@ QHD_CASES = {
     "cavity2d_implicit": lambda: cases.qhd_cavity(n=(18, 16), dt=1e-3, perturb=0.1, implicit=True),
     "cavity3d_implicit_diag": lambda: cases.qhd_cavity(n=(8, 7, 6), dims=3, dt=1e-3, implicit=True, diff_solver=dict(precond="diagonal")),
     "cavity2d_implicit_adjust": lambda: cases.qhd_cavity(n=(16, 14), dt=1e-3, implicit=True, adjust_time_step=True, max_co=0.05, c_tau=0.4),
+    # fvsc leastSquares / leastSquaresOpt in QHDFoam (2D only, fvsc.C:60-63): cell-stencil gradients of U, T, p
+    "cavity2d_leastSquares": lambda: cases.qhd_cavity(n=(18, 16), dt=1e-3, perturb=0.15, scheme="leastSquares"),
+    "cavity2d_leastSquaresOpt_implicit": lambda: cases.qhd_cavity(n=(16, 14), dt=1e-3, perturb=0.1, scheme="leastSquaresOpt", implicit=True),
+    "cavity2d_leastSquares_degenerate": lambda: cases.qhd_cavity(n=(6, 48), dt=5e-4, scheme="leastSquares", model="H2bynuQHD"),
 }
 
 
