@@ -271,6 +271,35 @@ void HostMesh::buildFaceRecords(bool reduced, std::vector<int>& vtx, std::vector
     }
 }
 
+// Recursive coordinate bisection: split the owned cells along the longest extent of their centres at the median until a part
+// holds at most targetCells; parts are numbered in creation order (deterministic).  Halo cells get block -1.
+void HostMesh::makePcgBlocks(int targetCells)
+{
+    if (targetCells < 1) targetCells = 1;
+    pcgBlock.assign(nCells, -1);
+    std::vector<int> ids(nOwned);
+    for (int c = 0; c < nOwned; ++c) ids[c] = c;
+    int next = 0;
+    std::vector<std::pair<int, int>> stack{{0, nOwned}};
+    while (!stack.empty()) {
+        const auto [lo, hi] = stack.back();
+        stack.pop_back();
+        if (hi - lo <= targetCells) { for (int i = lo; i < hi; ++i) pcgBlock[ids[i]] = next; ++next; continue; }
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int i = lo; i < hi; ++i)
+            for (int d = 0; d < 3; ++d) { const double x = C[3 * (size_t)ids[i] + d]; mn[d] = std::min(mn[d], x); mx[d] = std::max(mx[d], x); }
+        int dir = 0;
+        for (int d = 1; d < 3; ++d) if (gD[d] > 0 && (gD[dir] <= 0 || mx[d] - mn[d] > mx[dir] - mn[dir])) dir = d;
+        const int mid = lo + (hi - lo) / 2;
+        std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int a, int b) {
+            const double xa = C[3 * (size_t)a + dir], xb = C[3 * (size_t)b + dir];
+            return xa < xb || (xa == xb && a < b);
+        });
+        stack.push_back({mid, hi});
+        stack.push_back({lo, mid});
+    }
+}
+
 void HostMesh::buildLeastSquares(bool opt, int& W, std::vector<int>& cells, std::vector<double>& coef, std::vector<char>& deg) const
 {
     const double SMALLv = 1e-15;

@@ -110,6 +110,11 @@ struct HostMesh {
     // derived
     std::vector<int> cfOff, cfEnc;                 // cell -> faces, enc = (face<<1)|isNeighbourSide
     std::vector<int> forcedDegFaces;               // faceSet degenerateStencilFaces (leastSquaresStencil.C:63-132), polyMesh face ids
+    // DIC blocks: block id of every cell (empty = one block = the serial preconditioner).  In a decomposed reference run the DIC
+    // factorisation and sweeps are local to each processor's lduMatrix; the device uses the same block-local form with blocks small
+    // enough for one CTA (shared memory), so a sweep costs no grid-wide synchronisation (qgd_mesh_set_pcg_blocks / make_pcg_blocks)
+    std::vector<int> pcgBlock;
+    void makePcgBlocks(int targetCells);            // recursive coordinate bisection of the owned cells into compact tiles
     std::vector<int> pcOff, pcCell;                // non-patch point -> cells
     std::vector<double> pcW;
     std::vector<int> patchPoints;                  // list of patch points

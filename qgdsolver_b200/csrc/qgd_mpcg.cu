@@ -198,16 +198,21 @@ void StepwisePcg::alloc(const PcgMatrix& A, int rows)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     grid = std::max(1, std::min(sms * 8, (nRows + kB - 1) / kB));
-    r.alloc(nRows); w.alloc(nRows); p.alloc(n);
-    partials.alloc(2 * (size_t)grid); red.alloc(R_COUNT); state.alloc(S_COUNT);
+    // the block-local DIC works on whole-mesh vectors (halo cells are singleton blocks): r and w span all n cells then
+    r.alloc(A.nBlocks ? n : nRows); w.alloc(A.nBlocks ? n : nRows); p.alloc(n);
+    if (A.nBlocks) { r.zero(); w.zero(); }
+    partials.alloc(2 * (size_t)std::max(grid, dicBlocksGrid(A))); red.alloc(R_COUNT); state.alloc(S_COUNT);
 }
 
 // b: nRows device doubles ; x: n device doubles (owned rows first, halo entries valid on entry) ; precond 0 | 1
 int StepwisePcg::solve(const PcgMatrix& A, const double* b, double* x, double tol, double relTol, int maxIter, int precond,
                        cudaStream_t st, const PcgHooks* hooks, PcgResult* result)
 {
-    if (precond != 0 && precond != 1) throw Error(QGD_ERR_UNSUPPORTED, "stepwise PCG: preconditioner must be none or diagonal (DIC is block-local work in progress)");
-    if (precond == 1 && A.precond != 1) throw Error(QGD_ERR_STATE, "stepwise PCG: the matrix was not built with the diagonal preconditioner");
+    if (precond < 0 || precond > 2) throw Error(QGD_ERR_UNSUPPORTED, "stepwise PCG: preconditioner must be none, diagonal or DIC");
+    if (precond == 2 && A.nBlocks == 0)
+        throw Error(QGD_ERR_UNSUPPORTED, "stepwise PCG: DIC needs DIC blocks on the mesh (qgd_mesh_make_pcg_blocks / qgd_mesh_set_pcg_blocks): in a "
+                                         "decomposed run the preconditioner is local to a block");
+    if (precond != 0 && A.precond != precond) throw Error(QGD_ERR_STATE, "stepwise PCG: the matrix was built with another preconditioner");
     SwView v;
     v.n = n; v.nRows = nRows; v.W = A.W; v.enc = A.enc.p; v.coef = A.coef.p; v.tailOff = A.tailOff.p; v.tailEnc = A.tailEnc.p; v.tailCoef = A.tailCoef.p;
     v.diag = A.diag.p; v.rD = A.rD.p; v.b = b; v.x = x; v.r = r.p; v.w = w.p; v.p = p.p; v.partials = partials.p; v.red = red.p; v.state = state.p;
@@ -231,8 +236,14 @@ int StepwisePcg::solve(const PcgMatrix& A, const double* b, double* x, double to
     int hostState[S_COUNT] = {0, 0};
     for (int it0 = 0; it0 < maxIter; it0 += chunk) {
         for (int k = 0; k < chunk && it0 + k < maxIter; ++k) {
-            k_sw_precond<<<grid, kB, 0, st>>>(v); ++launches;
-            reduce(2, R_WARA, 1);
+            if (precond == 2) {
+                launchDicBlocks(A, r.p, w.p, partials.p, state.p + S_DONE, st); ++launches;
+                k_sw_collect<<<1, kB, 0, st>>>(v, dicBlocksGrid(A), 2); ++launches;
+                if (hooks && hooks->allreduceSum) hooks->allreduceSum(red.p + R_WARA, 1, st);
+            } else {
+                k_sw_precond<<<grid, kB, 0, st>>>(v); ++launches;
+                reduce(2, R_WARA, 1);
+            }
             k_sw_pupdate<<<grid, kB, 0, st>>>(v); ++launches;
             if (hooks && hooks->exchange) hooks->exchange(p.p, st);
             k_sw_spmv<<<grid, kB, 0, st>>>(v); ++launches;

@@ -100,9 +100,134 @@ __device__ void dicSweeps(cg::grid_group& grid, const PcgView& v, int tid, int n
     }
 }
 
+// ---- block-local DIC.  One CTA per block at a time: the block's rows (in-block entries, block order) and its part of the
+// vector are staged in shared memory, the forward / backward sweeps run level by level with __syncthreads() only - no grid-wide
+// synchronisation inside the preconditioner.  Operation order per cell = ascending (forward) / descending (backward) face order
+// of its in-block entries, i.e. the sequential sweeps of DICPreconditioner on the block's own lduMatrix.
+// smem layout: z[B] | rD[B] | coef[Wb][B] | enc[Wb][B]   (B = v.maxBlockCells)
+struct BlockSmem { double* z; double* rD; double* coef; int* enc; };
+__device__ __forceinline__ BlockSmem blockSmem(const PcgView& v, unsigned char* raw)
+{
+    BlockSmem s;
+    const size_t B = v.maxBlockCells;
+    s.z = reinterpret_cast<double*>(raw);
+    s.rD = s.z + B;
+    s.coef = s.rD + B;
+    s.enc = reinterpret_cast<int*>(s.coef + (size_t)v.Wb * B);
+    return s;
+}
+__device__ __forceinline__ void blockLoadRows(const PcgView& v, const BlockSmem& sm, int p0, int nb, const double* rDsrc)
+{
+    const size_t n = v.n, B = v.maxBlockCells;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        const int c = __ldg(&v.bCells[p0 + i]);
+        if (rDsrc) sm.rD[i] = rDsrc[c];
+        for (int j = 0; j < v.Wb; ++j) {
+            sm.enc[j * B + i] = __ldg(&v.bEnc[(size_t)j * n + p0 + i]);
+            sm.coef[j * B + i] = __ldg(&v.bCoef[(size_t)j * n + p0 + i]);
+        }
+    }
+}
+// z = M^-1 r on every block; returns this thread's part of sum(z*r)
+__device__ double dicBlocks(const PcgView& v, unsigned char* raw)
+{
+    const BlockSmem sm = blockSmem(v, raw);
+    const size_t B = v.maxBlockCells;
+    double zr = 0.0;
+    for (int b = blockIdx.x; b < v.nBlocks; b += gridDim.x) {
+        const int p0 = __ldg(&v.bOff[b]), nb = __ldg(&v.bOff[b + 1]) - p0;
+        const int l0 = __ldg(&v.bLvlStart[b]), nl = __ldg(&v.bLvlStart[b + 1]) - l0 - 1;
+        __syncthreads();                                   // the previous block's shared data is no longer read
+        blockLoadRows(v, sm, p0, nb, v.rD);
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) sm.z[i] = sm.rD[i] * v.r[__ldg(&v.bCells[p0 + i])];
+        __syncthreads();
+        for (int l = 1; l < nl; ++l) {                     // wA[u] -= rD[u]*upper*wA[l], faces ascending
+            const int a = __ldg(&v.bLvlOff[l0 + l]) - p0, e = __ldg(&v.bLvlOff[l0 + l + 1]) - p0;
+            for (int i = a + (int)threadIdx.x; i < e; i += blockDim.x) {
+                const double rd = sm.rD[i];
+                double zc = sm.z[i];
+                for (int j = 0; j < v.Wb; ++j) {
+                    const int en = sm.enc[j * B + i];
+                    if (en >= 0 && (en & 1)) zc -= rd * sm.coef[j * B + i] * sm.z[en >> 1];
+                }
+                sm.z[i] = zc;
+            }
+            __syncthreads();
+        }
+        for (int l = nl - 2; l >= 0; --l) {                // wA[l] -= rD[l]*upper*wA[u], faces descending
+            const int a = __ldg(&v.bLvlOff[l0 + l]) - p0, e = __ldg(&v.bLvlOff[l0 + l + 1]) - p0;
+            for (int i = a + (int)threadIdx.x; i < e; i += blockDim.x) {
+                const double rd = sm.rD[i];
+                double zc = sm.z[i];
+                for (int j = v.Wb - 1; j >= 0; --j) {
+                    const int en = sm.enc[j * B + i];
+                    if (en >= 0 && !(en & 1)) zc -= rd * sm.coef[j * B + i] * sm.z[en >> 1];
+                }
+                sm.z[i] = zc;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+            const int c = __ldg(&v.bCells[p0 + i]);
+            const double zc = sm.z[i];
+            v.z[c] = zc;
+            zr += zc * v.r[c];
+        }
+    }
+    return zr;
+}
+
+// DIC::calcReciprocalD on every block: rD = diag ; faces ascending (in-block): rD[u] -= upper^2/rD[l] ; rD = 1/rD
+__global__ void __launch_bounds__(kPcgBlock) k_dic_factor_blocks(PcgView v, double* rDout)
+{
+    extern __shared__ __align__(16) unsigned char rawF[];
+    const BlockSmem sm = blockSmem(v, rawF);
+    const size_t B = v.maxBlockCells;
+    for (int b = blockIdx.x; b < v.nBlocks; b += gridDim.x) {
+        const int p0 = __ldg(&v.bOff[b]), nb = __ldg(&v.bOff[b + 1]) - p0;
+        const int l0 = __ldg(&v.bLvlStart[b]), nl = __ldg(&v.bLvlStart[b + 1]) - l0 - 1;
+        __syncthreads();
+        blockLoadRows(v, sm, p0, nb, v.diag);
+        __syncthreads();
+        for (int l = 1; l < nl; ++l) {
+            const int a = __ldg(&v.bLvlOff[l0 + l]) - p0, e = __ldg(&v.bLvlOff[l0 + l + 1]) - p0;
+            for (int i = a + (int)threadIdx.x; i < e; i += blockDim.x) {
+                double rc = sm.rD[i];
+                for (int j = 0; j < v.Wb; ++j) {
+                    const int en = sm.enc[j * B + i];
+                    if (en >= 0 && (en & 1)) { const double cf = sm.coef[j * B + i]; rc -= cf * cf / sm.rD[en >> 1]; }
+                }
+                sm.rD[i] = rc;
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) rDout[__ldg(&v.bCells[p0 + i])] = 1.0 / sm.rD[i];
+    }
+}
+
+// one preconditioner application as a stand-alone kernel (stepwise / decomposed solver): z = M^-1 r, per-CTA partial of z.r
+__global__ void __launch_bounds__(kPcgBlock) k_dic_apply_blocks(PcgView v, double* partial, const int* done)
+{
+    extern __shared__ __align__(16) unsigned char rawA[];
+    __shared__ double red[kPcgBlock / 32];
+    if (done && *done) return;
+    double zr = dicBlocks(v, rawA);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zr += __shfl_down_sync(0xffffffffu, zr, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = zr;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < kPcgBlock / 32; ++k) t += red[k];
+        partial[blockIdx.x] = t;
+        partial[gridDim.x + blockIdx.x] = 0.0;
+    }
+}
+
 template <int WT>
 __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgView v)
 {
+    extern __shared__ __align__(16) unsigned char rawP[];
     cg::grid_group grid = cg::this_grid();
     const int n = v.n, W = WT ? WT : v.W;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -142,9 +267,12 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgView v)
     int it = 0;
     auto converged = [&]() { return res < v.tol || (v.relTol > 1e-20 && res < v.relTol * res0); };
     if (!converged() && v.maxIter > 0) {
-        if (v.precond == 2) dicSweeps<WT>(grid, v, tid, nth);
         double zr = 0.0;
-        for (int c = tid; c < n; c += nth) zr += v.z[c] * v.r[c];
+        if (v.precond == 2 && v.nBlocks > 0) zr = dicBlocks(v, rawP);
+        else {
+            if (v.precond == 2) dicSweeps<WT>(grid, v, tid, nth);
+            for (int c = tid; c < n; c += nth) zr += v.z[c] * v.r[c];
+        }
         s = gridSum2(grid, zr, 0.0, v.partials, slot);
         double wArA = s.x, wArAold = wArA;
         double* po = v.p0;
@@ -194,9 +322,12 @@ __global__ void __launch_bounds__(kPcgBlock) k_pcg(PcgView v)
             wArAold = wArA;
             wArA = s.y;
             if (v.precond == 2) {
-                dicSweeps<WT>(grid, v, tid, nth);
                 zr = 0.0;
-                for (int c = tid; c < n; c += nth) zr += v.z[c] * v.r[c];
+                if (v.nBlocks > 0) zr = dicBlocks(v, rawP);
+                else {
+                    dicSweeps<WT>(grid, v, tid, nth);
+                    for (int c = tid; c < n; c += nth) zr += v.z[c] * v.r[c];
+                }
                 s = gridSum2(grid, zr, 0.0, v.partials, slot);
                 wArA = s.x;
             }
@@ -238,12 +369,13 @@ __global__ void k_recip(int n, const double* __restrict__ d, double* __restrict_
     if (c < n) o[c] = 1.0 / d[c];
 }
 
-template <class K> int coopGrid(K kernel)
+template <class K> int coopGrid(K kernel, size_t smem = 0)
 {
     int dev = 0, sms = 148, perSM = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kPcgBlock, 0);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, kPcgBlock, smem);
     if (perSM < 1) perSM = 1;
     if (perSM > 4) perSM = 4;
     return sms * perSM;
@@ -263,21 +395,43 @@ __global__ void k_fill_coef(int n, int W, const int* __restrict__ encFace, const
     if (c < nTail) { const int f = tailFace[c]; tailCoef[c] = f >= 0 ? -faceCoef[f] : 0.0; }
 }
 
+int dicBlocksGrid(const PcgMatrix& A) { return std::max(1, std::min(A.nBlocks, 148 * 8)); }
+// z = M^-1 r with the block-local DIC of A as a stand-alone launch (stepwise / decomposed solver); partials: 2*dicBlocksGrid(A) doubles
+void launchDicBlocks(const PcgMatrix& A, const double* r, double* z, double* partials, const int* done, cudaStream_t st)
+{
+    PcgView v = A.view(0, 0, 0);
+    v.r = const_cast<double*>(r); v.z = z;
+    const size_t smem = A.dicSmemBytes();
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_dic_apply_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_dic_apply_blocks<<<dicBlocksGrid(A), kPcgBlock, smem, st>>>(v, partials, done);
+}
+
+static void dicFactor(PcgMatrix& A, cudaStream_t st)
+{
+    PcgView v = A.view(0, 0, 0);
+    double* raw = A.rD.p;
+    if (A.nBlocks > 0) {
+        const size_t smem = A.dicSmemBytes();
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_dic_factor_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_dic_factor_blocks<<<std::min(A.nBlocks, 148 * 8), kPcgBlock, smem, st>>>(v, raw);
+        return;
+    }
+    void* args[] = {&v, &raw};
+    const int g = std::max(1, std::min(coopGrid(k_dic_factor), (A.n + kPcgBlock - 1) / kPcgBlock));
+    QGD_CUDA(cudaLaunchCooperativeKernel((void*)k_dic_factor, dim3(g), dim3(kPcgBlock), args, 0, st));
+}
+
 void PcgMatrix::refresh(const double* faceCoef, const double* diagDev, cudaStream_t st)
 {
     if (faceCoef && !encFace.n) throw Error(QGD_ERR_STATE, "PcgMatrix::refresh: matrix was built without face ids");
     const int nTail = (int)tailFace.n;
     if (faceCoef)      // nullptr: only the diagonal changed (e.g. a new deltaT)
         k_fill_coef<<<(std::max(n, nTail) + 255) / 256, 256, 0, st>>>(n, W, encFace.p, faceCoef, coef.p, nTail, tailFace.p, tailCoef.p);
+    if (faceCoef && nBlocks > 0)       // the block-ordered copy of the in-block coefficients
+        k_fill_coef<<<(n + 255) / 256, 256, 0, st>>>(n, Wb, bEncFace.p, faceCoef, bCoef.p, 0, nullptr, nullptr);
     QGD_CUDA(cudaMemcpyAsync(diag.p, diagDev, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (precond == 1) k_recip<<<(n + 255) / 256, 256, 0, st>>>(n, diag.p, rD.p);
-    else if (precond == 2) {
-        PcgView v = view(0, 0, 0);
-        double* raw = rD.p;
-        void* args[] = {&v, &raw};
-        const int g = std::max(1, std::min(coopGrid(k_dic_factor), (n + kPcgBlock - 1) / kPcgBlock));
-        QGD_CUDA(cudaLaunchCooperativeKernel((void*)k_dic_factor, dim3(g), dim3(kPcgBlock), args, 0, st));
-    }
+    else if (precond == 2) dicFactor(*this, st);
     QGD_CUDA(cudaGetLastError());
 }
 
@@ -331,20 +485,80 @@ void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* uppe
     }
     enc.upload(e, st); coef.upload(a, st); tailOff.upload(tOff, st); tailEnc.upload(tEnc, st); tailCoef.upload(tCoef, st);
     lvlOff.upload(lOff, st); lvlCells.upload(lCells, st);
+    // ---- block-local DIC (HostMesh::pcgBlock): cells ordered (block, level inside the block, id); rows restricted to in-block entries
+    nBlocks = 0; Wb = 0; maxBlockCells = 0;
+    if (precond == 2 && !h.pcgBlock.empty()) {
+        const std::vector<int>& blk = h.pcgBlock;
+        int nb = 0;
+        for (int c = 0; c < n; ++c) nb = std::max(nb, blk[c] + 1);
+        // cells without a block (halo copies of a sub-mesh) form singleton blocks: their rows are never solved
+        std::vector<int> bid(n);
+        for (int c = 0; c < n; ++c) bid[c] = blk[c] >= 0 ? blk[c] : nb++;
+        std::vector<int> lvl(n, 0), rowLenB(n, 0);
+        for (int c = 0; c < n; ++c)
+            for (int q = h.cfOff[c]; q < h.cfOff[c + 1]; ++q) {
+                const int f = h.cfEnc[q] >> 1;
+                if (f >= nI) continue;
+                const int lowerSide = h.cfEnc[q] & 1;
+                const int o = lowerSide ? h.owner[f] : h.neighbour[f];
+                if (bid[o] != bid[c]) continue;
+                ++rowLenB[c];
+                if (lowerSide) lvl[c] = std::max(lvl[c], lvl[o] + 1);
+            }
+        for (int c = 0; c < n; ++c) Wb = std::max(Wb, rowLenB[c]);
+        Wb = std::max(Wb, 1);
+        std::vector<int> order(n);
+        for (int c = 0; c < n; ++c) order[c] = c;
+        std::sort(order.begin(), order.end(), [&](int x, int y) {
+            if (bid[x] != bid[y]) return bid[x] < bid[y];
+            if (lvl[x] != lvl[y]) return lvl[x] < lvl[y];
+            return x < y;
+        });
+        std::vector<int> pos(n), off(nb + 1, 0), lvlStart(nb + 1, 0), lvlOffB;
+        for (int p = 0; p < n; ++p) { pos[order[p]] = p; off[bid[order[p]] + 1]++; }
+        for (int b = 0; b < nb; ++b) { off[b + 1] += off[b]; maxBlockCells = std::max(maxBlockCells, off[b + 1] - off[b]); }
+        for (int b = 0; b < nb; ++b) {
+            lvlStart[b] = (int)lvlOffB.size();
+            int cur = -1;
+            for (int p = off[b]; p < off[b + 1]; ++p)
+                while (cur < lvl[order[p]]) { lvlOffB.push_back(p); ++cur; }
+            lvlOffB.push_back(off[b + 1]);
+        }
+        lvlStart[nb] = (int)lvlOffB.size();
+        std::vector<int> be((size_t)Wb * n, -1), bf((size_t)Wb * n, -1);
+        std::vector<double> bc((size_t)Wb * n, 0.0);
+        for (int c = 0; c < n; ++c) {
+            int j = 0;
+            const int p = pos[c];
+            for (int q = h.cfOff[c]; q < h.cfOff[c + 1]; ++q) {
+                const int f = h.cfEnc[q] >> 1;
+                if (f >= nI) continue;
+                const int lowerSide = h.cfEnc[q] & 1;
+                const int o = lowerSide ? h.owner[f] : h.neighbour[f];
+                if (bid[o] != bid[c]) continue;
+                be[(size_t)j * n + p] = ((pos[o] - off[bid[c]]) << 1) | lowerSide;
+                bc[(size_t)j * n + p] = upper[f];
+                bf[(size_t)j * n + p] = faceInv ? (*faceInv)[f] : f;
+                ++j;
+            }
+        }
+        nBlocks = nb;
+        bOff.upload(off, st); bLvlStart.upload(lvlStart, st); bLvlOff.upload(lvlOffB, st); bCells.upload(order, st);
+        bEnc.upload(be, st); bCoef.upload(bc, st);
+        if (faceInv) bEncFace.upload(bf, st);
+        if (dicSmemBytes() > 200 * 1024)
+            throw Error(QGD_ERR_INVALID, "PCG: a DIC block of " + std::to_string(maxBlockCells) + " cells with " + std::to_string(Wb) +
+                                             " in-block neighbours does not fit the shared memory of one CTA; use smaller blocks");
+    }
     diag.upload(std::vector<double>(hdiag, hdiag + n), st);
     rD.alloc(n); b.alloc(n); x.alloc(n); r.alloc(n); w.alloc(n); z.alloc(n); p0.alloc(n); p1.alloc(n);
     out.alloc(1);
-    gridBlocks = std::min(std::min(coopGrid(k_pcg<4>), coopGrid(k_pcg<6>)), coopGrid(k_pcg<8>));
+    const size_t smem = dicSmemBytes();
+    gridBlocks = std::min(std::min(coopGrid(k_pcg<4>, smem), coopGrid(k_pcg<6>, smem)), coopGrid(k_pcg<8>, smem));
     gridBlocks = std::max(1, std::min(gridBlocks, (n + kPcgBlock - 1) / kPcgBlock));
     partials.alloc(4 * (size_t)gridBlocks);
     if (precond == 1) k_recip<<<(n + 255) / 256, 256, 0, st>>>(n, diag.p, rD.p);
-    else if (precond == 2) {
-        PcgView v = view(0, 0, 0);
-        double* raw = rD.p;
-        void* args[] = {&v, &raw};
-        const int g = std::max(1, std::min(coopGrid(k_dic_factor), (n + kPcgBlock - 1) / kPcgBlock));
-        QGD_CUDA(cudaLaunchCooperativeKernel((void*)k_dic_factor, dim3(g), dim3(kPcgBlock), args, 0, st));
-    }
+    else if (precond == 2) dicFactor(*this, st);
     QGD_CUDA(cudaGetLastError());
     QGD_CUDA(cudaStreamSynchronize(st));
 }
@@ -355,6 +569,8 @@ PcgView PcgMatrix::view(double tol, double relTol, int maxIter) const
     v.n = n; v.W = W; v.enc = enc.p; v.coef = coef.p; v.tailOff = tailOff.p; v.tailEnc = tailEnc.p; v.tailCoef = tailCoef.p;
     v.diag = diag.p; v.rD = rD.p; v.b = bExternal ? bExternal : b.p; v.x = xExternal ? xExternal : x.p; v.r = r.p; v.w = w.p; v.z = z.p; v.p0 = p0.p; v.p1 = p1.p;
     v.partials = partials.p; v.nLevels = nLevels; v.lvlOff = lvlOff.p; v.lvlCells = lvlCells.p;
+    v.nBlocks = nBlocks; v.Wb = Wb; v.maxBlockCells = maxBlockCells;
+    v.bOff = bOff.p; v.bLvlStart = bLvlStart.p; v.bLvlOff = bLvlOff.p; v.bCells = bCells.p; v.bEnc = bEnc.p; v.bCoef = bCoef.p;
     v.tol = tol; v.relTol = relTol; v.maxIter = maxIter; v.precond = precond; v.out = out.p;
     return v;
 }
@@ -364,7 +580,7 @@ int PcgMatrix::solve(double tol, double relTol, int maxIter, cudaStream_t st)
     PcgView v = view(tol, relTol, maxIter);
     void* args[] = {&v};
     void* fn = (W == 4) ? (void*)k_pcg<4> : (W == 6 ? (void*)k_pcg<6> : (void*)k_pcg<8>);
-    QGD_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks), dim3(kPcgBlock), args, 0, st));
+    QGD_CUDA(cudaLaunchCooperativeKernel(fn, dim3(gridBlocks), dim3(kPcgBlock), args, dicSmemBytes(), st));
     return 1;
 }
 

@@ -23,6 +23,12 @@ struct PcgView {
     double* r; double* w; double* z; double* p0; double* p1;
     double* partials;            // [2 slots][2 values][gridDim.x]
     int nLevels; const int* lvlOff; const int* lvlCells;     // DIC level schedule (cells grouped by dependency depth)
+    // block-local DIC (HostMesh::pcgBlock): cells ordered (block, level, id); position p of that order holds cell bCells[p].
+    // Block b owns positions [bOff[b], bOff[b+1]) and the level offsets bLvlOff[bLvlStart[b] .. bLvlStart[b+1]] (absolute
+    // positions).  Rows in block order, in-block entries only, ELL width Wb: bEnc[j*n + p] = (local position of the other cell
+    // << 1) | lowerSide, -1 = none; bCoef the matching coefficient.  nBlocks = 0: the global level schedule above.
+    int nBlocks, Wb, maxBlockCells;
+    const int* bOff; const int* bLvlStart; const int* bLvlOff; const int* bCells; const int* bEnc; const double* bCoef;
     double tol, relTol; int maxIter, precond;
     PcgResult* out;
 };
@@ -33,6 +39,11 @@ struct PcgMatrix {
     DevBuf<double> coef, tailCoef, diag, rD, b, x, r, w, z, p0, p1, partials;
     DevBuf<PcgResult> out;
     DevBuf<int> encFace, tailFace;   // device face id of every ELL / tail entry (-1: padding), for refresh()
+    // block-local DIC (see PcgView)
+    int nBlocks = 0, Wb = 0, maxBlockCells = 0;
+    DevBuf<int> bOff, bLvlStart, bLvlOff, bCells, bEnc, bEncFace;
+    DevBuf<double> bCoef;
+    size_t dicSmemBytes() const { return nBlocks ? (size_t)maxBlockCells * (16 + 12 * (size_t)Wb) : 0; }
     int gridBlocks = 0;
     double* bExternal = nullptr;     // when set, the right-hand side lives in the caller's array
     double* xExternal = nullptr;     // when set, the solution vector lives in the caller's array (e.g. the p slice of the QHD state)
@@ -47,6 +58,9 @@ struct PcgMatrix {
     int solve(double tol, double relTol, int maxIter, cudaStream_t st);
 };
 
+int dicBlocksGrid(const PcgMatrix& A);
+void launchDicBlocks(const PcgMatrix& A, const double* r, double* z, double* partials, const int* done, cudaStream_t st);
+
 // ---- stepwise (one kernel per phase) form of the same solver for decomposed runs, see qgd_mpcg.cu
 struct PcgHooks {
     std::function<void(double* vec, cudaStream_t st)> exchange;                   // fill the halo entries of a cell vector from their owners
@@ -57,7 +71,8 @@ struct StepwisePcg {
     DevBuf<double> r, w, p, partials, red;
     DevBuf<int> state;
     void alloc(const PcgMatrix& A, int rows);     // rows = owned rows [0, rows) of the extended sub-mesh matrix (== A.n on one GPU)
-    // b: rows device doubles ; x: A.n device doubles ; precond 0 none | 1 diagonal ; hooks = nullptr on one GPU ; returns launches
+    // b: rows device doubles ; x: A.n device doubles ; precond 0 none | 1 diagonal | 2 DIC on the matrix's blocks (PcgMatrix::nBlocks > 0) ;
+    // hooks = nullptr on one GPU ; returns launches
     int solve(const PcgMatrix& A, const double* b, double* x, double tol, double relTol, int maxIter, int precond, cudaStream_t st,
               const PcgHooks* hooks, PcgResult* result);
 };

@@ -200,9 +200,10 @@ def test_qhd_error_behaviour(qgd):
     with pytest.raises(qgd.QGDError) as e:
         qgd.QHDFoam(dm, precond="GAMG", **kw)
     assert "Unknown symmetric matrix preconditioner GAMG" in e.value.message
-    with pytest.raises(qgd.QGDError) as e:
-        qgd.QHDFoam(dm, fvsc_scheme="leastSquares", **kw)
-    assert e.value.code == qgd.ERR_UNSUPPORTED
+    qgd.QHDFoam(dm, fvsc_scheme="leastSquares", **kw)                  # 2D: available since round 2
+    with pytest.raises(qgd.QGDError) as e:                              # fvsc.C:60-63
+        qgd.QHDFoam(qgd.Mesh(cases.pm.hex_box(3, 3, 3)), fvsc_scheme="leastSquares", **kw)
+    assert "Can't use leastSquares or leastSquaresOpt in 3D case." in e.value.message
     with pytest.raises(qgd.QGDError) as e:
         qgd.QHDFoam(dm, **kw).step(1)
     assert e.value.code == qgd.ERR_STATE
