@@ -95,6 +95,17 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out);
  * `leastSquares` gradient is replaced by nf*snGrad, in addition to those found degenerate by det(G) < 1.  Call before
  * qgd_fvsc_create / qgd_*foam_create on this mesh; boundary faces in the list are ignored (serial meshes). */
 int qgd_mesh_set_degenerate_stencil_faces(qgd_mesh* mesh, const int* faces, int n);
+/* DIC blocks.  In `mpirun -np N` runs of the reference the DIC preconditioner of PCG (QHDpEqn.H:45; QGDUEqn.H:54-75,
+ * QGDEEqn.H:53-64) is factorised and swept on each processor's own lduMatrix: faces between cells of different processors
+ * are left out of it [OF-v2312 DICPreconditioner].  The device uses the same block-local form, with blocks small enough to
+ * be swept by one CTA in shared memory (no grid-wide synchronisation inside the preconditioner); without blocks the
+ * preconditioner is the serial one (exact operation order, level-scheduled: one grid synchronisation per level - only
+ * usable on small meshes).  cell_block: block id >= 0 of every cell (halo cells of a sub-mesh are ignored), NULL clears.
+ * make: recursive coordinate bisection of the owned cells into compact tiles of at most target_cells cells.
+ * Call before qgd_pcg_solve / qgd_*foam_init_fields on this mesh.  get: -1 for halo cells or when no blocks are set. */
+int qgd_mesh_set_pcg_blocks(qgd_mesh* mesh, const int* cell_block);
+int qgd_mesh_make_pcg_blocks(qgd_mesh* mesh, int target_cells, int* n_blocks);
+int qgd_mesh_get_pcg_blocks(qgd_mesh* mesh, int* cell_block);
 int qgd_mesh_destroy(qgd_mesh* mesh);
 /* derived fields, for write-back / parity checks.  what: 0 hQGDf (n_faces)  QGDCoeffs.C:298-318
  *                                                        1 hQGD  (n_cells)  QGDCoeffs.C:320-362 */

@@ -25,6 +25,7 @@ QGD_OK, ERR_INVALID, ERR_UNKNOWN_MODEL, ERR_UNSUPPORTED, ERR_CUDA, ERR_COMM, ERR
 ABI_SYMBOLS = [
     "qgd_init", "qgd_last_error", "qgd_version", "qgd_device_synchronize",
     "qgd_mesh_create", "qgd_mesh_destroy", "qgd_mesh_get", "qgd_mesh_set_degenerate_stencil_faces",
+    "qgd_mesh_set_pcg_blocks", "qgd_mesh_make_pcg_blocks", "qgd_mesh_get_pcg_blocks",
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_step_fields_host", "qgd_qgdfoam_face_kernel", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
@@ -112,6 +113,9 @@ def load_library():
     L.qgd_mesh_destroy.argtypes = [C.c_void_p]
     L.qgd_mesh_set_degenerate_stencil_faces.argtypes = [C.c_void_p, _ip, C.c_int]
     L.qgd_mesh_get.argtypes = [C.c_void_p, C.c_int, _dp]
+    L.qgd_mesh_set_pcg_blocks.argtypes = [C.c_void_p, _ip]
+    L.qgd_mesh_make_pcg_blocks.argtypes = [C.c_void_p, C.c_int, _ip]
+    L.qgd_mesh_get_pcg_blocks.argtypes = [C.c_void_p, _ip]
     L.qgd_fvsc_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     L.qgd_fvsc_destroy.argtypes = [C.c_void_p]
     for fn in (L.qgd_fvsc_grad, L.qgd_fvsc_div):
@@ -239,6 +243,25 @@ class Mesh:
         """faceSet degenerateStencilFaces of the leastSquares scheme (leastSquaresStencil.C:63-132); before any stencil / solver"""
         f = np.ascontiguousarray(faces, np.int32)
         _check(load_library().qgd_mesh_set_degenerate_stencil_faces(self._h, _i(f), int(f.size)))
+
+    def set_pcg_blocks(self, cell_block):
+        """DIC blocks (block id per cell; None clears): the preconditioner of every PCG on this mesh becomes block-local"""
+        if cell_block is None:
+            _check(load_library().qgd_mesh_set_pcg_blocks(self._h, None))
+            return
+        b = np.ascontiguousarray(cell_block, np.int32)
+        _check(load_library().qgd_mesh_set_pcg_blocks(self._h, _i(b)))
+
+    def make_pcg_blocks(self, target_cells: int = 512) -> np.ndarray:
+        """compact tiles of at most target_cells cells by recursive coordinate bisection; returns the block id per cell"""
+        nb = C.c_int()
+        _check(load_library().qgd_mesh_make_pcg_blocks(self._h, int(target_cells), C.byref(nb)))
+        return self.pcg_blocks()
+
+    def pcg_blocks(self) -> np.ndarray:
+        out = np.empty(self.mesh.n_cells, np.int32)
+        _check(load_library().qgd_mesh_get_pcg_blocks(self._h, _i(out)))
+        return out
 
     def hQGDf(self):
         out = np.empty(self.mesh.n_faces)

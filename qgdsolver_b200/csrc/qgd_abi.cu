@@ -743,12 +743,30 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
     std::vector<int4> v4(nF);
     std::vector<int> fl(nF);
     const size_t fs = (size_t)mesh->faceStride;
-    std::vector<double> Gp(9 * fs, 0.0);
+    // device record: G1[3], G2[3] and the scalar gpS with GP = gpS * Sf.  GP is parallel to the face area vector in every scheme
+    // (quad: (e1 x e2)/D with the diagonals e1, e2; tri: A_f/(3 vt); 2D: the in-plane normal of v13; 1D / reduced / polygon faces:
+    // -nf delta), so 7 doubles per face carry the 9 of the full record (GaussVolPointBase3D.C:186-229,346-389; ...2D.C:122-169)
+    std::vector<double> Gp(7 * fs, 0.0);
     for (int f = 0; f < nF; ++f) {
         const size_t o = perm[f];
         v4[f] = make_int4(vtx[4 * o], vtx[4 * o + 1], vtx[4 * o + 2], vtx[4 * o + 3]);
         fl[f] = flags[o];
-        for (int k = 0; k < 9; ++k) Gp[(size_t)k * fs + f] = G[(size_t)k * nF + o];
+        for (int k = 0; k < 6; ++k) Gp[(size_t)k * fs + f] = G[(size_t)k * nF + o];
+        const double* S = &mesh->h.Sf[3 * o];
+        const double gP[3] = {G[(size_t)6 * nF + o], G[(size_t)7 * nF + o], G[(size_t)8 * nF + o]};
+        const double SS = S[0] * S[0] + S[1] * S[1] + S[2] * S[2];
+        const double gS = SS > 0.0 ? (gP[0] * S[0] + gP[1] * S[1] + gP[2] * S[2]) / SS : 0.0;
+        double dev = 0.0, nrm = 0.0;
+        for (int i = 0; i < 3; ++i) { dev = std::max(dev, std::fabs(gP[i] - gS * S[i])); nrm = std::max(nrm, std::fabs(gP[i])); }
+        if (dev > 1e-9 * nrm)
+            throw Error(QGD_ERR_INVALID, "fvsc: face " + std::to_string(o) + " has a gradient record whose cell-difference vector is not "
+                                         "parallel to the face area vector (degenerate face geometry)");
+        Gp[(size_t)6 * fs + f] = gS;
+    }
+    op.flagsUniform = -1;
+    if (mesh->nIActive > 0) {
+        op.flagsUniform = fl[0];
+        for (int f = 1; f < mesh->nIActive; ++f) if (fl[f] != fl[0]) { op.flagsUniform = -1; break; }
     }
     if (op.lsq) {
         // internal faces: least-squares cell stencil; the G record keeps the nf*snGrad fallback of degenerate faces
@@ -933,6 +951,40 @@ int qgd_mesh_set_degenerate_stencil_faces(qgd_mesh* m, const int* faces, int n)
     });
 }
 
+int qgd_mesh_set_pcg_blocks(qgd_mesh* m, const int* cell_block)
+{
+    return guarded([&] {
+        if (!m) throw Error(QGD_ERR_INVALID, "qgd_mesh_set_pcg_blocks: null mesh");
+        if (!cell_block) { m->h.pcgBlock.clear(); return; }
+        const int n = m->h.nCells;
+        std::vector<int> b(cell_block, cell_block + n);
+        for (int c = 0; c < n; ++c) {
+            if (c >= m->h.nOwned) b[c] = -1;
+            else if (b[c] < 0) throw Error(QGD_ERR_INVALID, "qgd_mesh_set_pcg_blocks: negative block id");
+        }
+        m->h.pcgBlock.swap(b);
+    });
+}
+
+int qgd_mesh_make_pcg_blocks(qgd_mesh* m, int target_cells, int* n_blocks)
+{
+    return guarded([&] {
+        if (!m || target_cells < 1) throw Error(QGD_ERR_INVALID, "qgd_mesh_make_pcg_blocks: bad argument");
+        m->h.makePcgBlocks(target_cells);
+        int nb = 0;
+        for (int v : m->h.pcgBlock) nb = std::max(nb, v + 1);
+        if (n_blocks) *n_blocks = nb;
+    });
+}
+
+int qgd_mesh_get_pcg_blocks(qgd_mesh* m, int* cell_block)
+{
+    return guarded([&] {
+        if (!m || !cell_block) throw Error(QGD_ERR_INVALID, "qgd_mesh_get_pcg_blocks: null argument");
+        for (int c = 0; c < m->h.nCells; ++c) cell_block[c] = m->h.pcgBlock.empty() ? -1 : m->h.pcgBlock[c];
+    });
+}
+
 int qgd_mesh_destroy(qgd_mesh* mesh) { return guarded([&] { delete mesh; }); }
 
 int qgd_mesh_get(qgd_mesh* mesh, int what, double* out)
@@ -1011,9 +1063,9 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
             const std::string pc = d->diff_preconditioner ? d->diff_preconditioner : "DIC";
             if (pc == "DIC") diffPrecond = 2; else if (pc == "diagonal") diffPrecond = 1; else if (pc == "none") diffPrecond = 0;
             else throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown symmetric matrix preconditioner " + pc + "\n\nValid symmetric matrix preconditioners are:\n3\n(\nDIC\ndiagonal\nnone\n)\n");
-            if (mesh->h.nOwned != mesh->h.nCells && diffPrecond == 2)
-                throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true on extended sub-meshes (multi-GPU): the (U|e) preconditioner must be "
-                                                 "diagonal or none (DIC is local to a processor block in a decomposed run; not available on sub-meshes yet)");
+            if (mesh->h.nOwned != mesh->h.nCells && diffPrecond == 2 && mesh->h.pcgBlock.empty())
+                throw Error(QGD_ERR_UNSUPPORTED, "implicitDiffusion true on extended sub-meshes (multi-GPU): DIC is local to a block in a decomposed "
+                                                 "run - set DIC blocks first (qgd_mesh_make_pcg_blocks) or use diagonal | none");
         }
         for (int pk : mesh->h.patchKind)
             if (pk == QGD_PATCH_PROCESSOR)
@@ -1582,7 +1634,8 @@ int qgd_pcg_solve_multi(qgd_mesh* mesh, const double* diag, const double* upper,
         if (!mesh || !diag || !b || !x || (mesh->h.nInternal > 0 && !upper) || n_neighbours < 0 ||
             (n_neighbours > 0 && (!nbr_rank || !send_off || !send_cells || !recv_off || !recv_cells)))
             throw Error(QGD_ERR_INVALID, "qgd_pcg_solve_multi: null argument");
-        if (precond < 0 || precond > 1) throw Error(QGD_ERR_UNSUPPORTED, "qgd_pcg_solve_multi: preconditioner must be 0 (none) or 1 (diagonal)");
+        if (precond < 0 || precond > 2 || (precond == 2 && mesh->h.pcgBlock.empty()))
+            throw Error(QGD_ERR_UNSUPPORTED, "qgd_pcg_solve_multi: preconditioner must be 0 (none), 1 (diagonal) or 2 (DIC, with DIC blocks set on the mesh)");
         const HostMesh& h = mesh->h;
         const size_t n = h.nCells;
         const int nOwned = h.nOwned, nn = n_neighbours;
@@ -1633,7 +1686,8 @@ int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upp
     return guarded([&] {
         requireInit();
         if (!mesh || !diag || !b || !x || (mesh->h.nInternal > 0 && !upper)) throw Error(QGD_ERR_INVALID, "qgd_pcg_solve_stepwise: null argument");
-        if (precond < 0 || precond > 1) throw Error(QGD_ERR_UNSUPPORTED, "qgd_pcg_solve_stepwise: preconditioner must be 0 (none) or 1 (diagonal)");
+        if (precond < 0 || precond > 2 || (precond == 2 && mesh->h.pcgBlock.empty()))
+            throw Error(QGD_ERR_UNSUPPORTED, "qgd_pcg_solve_stepwise: preconditioner must be 0 (none), 1 (diagonal) or 2 (DIC, with DIC blocks set on the mesh)");
         PcgMatrix A;
         A.build(mesh->h, diag, upper, precond, g_stream);
         const size_t n = mesh->h.nCells;

@@ -250,7 +250,7 @@ __global__ void k_fvsc_grad(FaceView fv, const double* __restrict__ cell, const 
     for (int i = 0; i < 3; ++i) {
         g1[i] = fv.G[(size_t)(0 + i) * fv.fs + f];
         g2[i] = fv.G[(size_t)(3 + i) * fv.fs + f];
-        gp[i] = fv.G[(size_t)(6 + i) * fv.fs + f];
+        gp[i] = fv.G[6 * (size_t)fv.fs + f] * fv.Sf[(size_t)i * fv.fs + f];      // GP = gpS * Sf
     }
     if (f >= fv.nI) {
         const int b = f - fv.nI;
@@ -305,7 +305,7 @@ __global__ void k_fvsc_div(FaceView fv, const double* __restrict__ cell, const d
     for (int i = 0; i < 3; ++i) {
         g1[i] = fv.G[(size_t)(0 + i) * fv.fs + f];
         g2[i] = fv.G[(size_t)(3 + i) * fv.fs + f];
-        gp[i] = fv.G[(size_t)(6 + i) * fv.fs + f];
+        gp[i] = fv.G[6 * (size_t)fv.fs + f] * fv.Sf[(size_t)i * fv.fs + f];      // GP = gpS * Sf
     }
     if (f >= fv.nI) {
         const int b = f - fv.nI;
@@ -568,7 +568,7 @@ __device__ __forceinline__ void bndFaceSetup(const Consts& k, const FaceView& fv
     for (int i = 0; i < 3; ++i) {
         g1[i] = fv.G[(size_t)(0 + i) * fv.fs + f];
         g2[i] = fv.G[(size_t)(3 + i) * fv.fs + f];
-        gp[i] = fv.G[(size_t)(6 + i) * fv.fs + f];
+        gp[i] = fv.G[6 * (size_t)fv.fs + f] * fv.Sf[(size_t)i * fv.fs + f];      // GP = gpS * Sf
     }
     if (flags & FF_NORMAL_ONLY) {
 #pragma unroll
@@ -644,7 +644,7 @@ __global__ void k_bnd_flux(Consts k, FaceView fv, SolverView sv, BndState bs)
 }
 
 // ---- one internal face: 11 interpolations + 4 GaussVolPoint gradients + QGD flux algebra -> 5 flux doubles at `slot`
-// SMEM: the streamed per-face constants (G, Sf, w, hQGDf, |Sf|) were staged by TMA into shared memory: sd[k*kTmaTile + li]
+// SMEM: the streamed per-face constants (G1, G2, gpS | Sf | w, hQGDf, |Sf|) were staged by TMA into shared memory: sd[k*kTmaTile + li]
 constexpr int kTmaTile = 256;
 // leastSquares gradients of (rho, U, e, p) on an internal face of the step kernel
 __device__ __forceinline__ void lsqGrads(const FaceView& fv, const SolverView& sv, int f, const RecA& aP, const RecA& aN, double w, FaceGrads& g)
@@ -696,18 +696,18 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     const RecP dP{aP.rho - aN.rho, aP.Ux - aN.Ux, aP.Uy - aN.Uy, aP.Uz - aN.Uz, aP.e - aN.e, aP.p - aN.p};
     double g1[3], g2[3], gp[3], Sf[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) Sf[i] = SMEM ? sd[(9 + i) * kTmaTile + li] : __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
+    for (int i = 0; i < 3; ++i) Sf[i] = SMEM ? sd[(7 + i) * kTmaTile + li] : __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
     {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             g1[i] = SMEM ? sd[(0 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(0 + i) * fv.fs + f]);
             g2[i] = SMEM ? sd[(3 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(3 + i) * fv.fs + f]);
-            gp[i] = SMEM ? sd[(6 + i) * kTmaTile + li] : __ldg(&fv.G[(size_t)(6 + i) * fv.fs + f]);
+            gp[i] = (SMEM ? sd[6 * kTmaTile + li] : __ldg(&fv.G[6 * (size_t)fv.fs + f])) * Sf[i];    // GP = gpS * Sf
         }
     }
     FaceGrads g;
     // linearInterpolate: w*(phiP - phiN) + phiN   [OF surfaceInterpolationScheme::interpolate]
-    const double w = SMEM ? sd[12 * kTmaTile + li] : __ldg(&fv.w[f]);
+    const double w = SMEM ? sd[10 * kTmaTile + li] : __ldg(&fv.w[f]);
     if (LSQ && (flagsCur & FF_LSQ)) lsqGrads(fv, sv, f, aP, aN, w, g);
     else gradsFromDiffs(g1, g2, gp, flagsCur, d1, d2, dP, g);
     FaceState s;
@@ -732,7 +732,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
     // implicitDiffusion: the mu / alpha terms are solved implicitly, the explicit fluxes carry none (updateFluxes.H:95,131)
     s.alpha = k.implicit ? 0.0 : w * (bP.alphaEff - bN.alphaEff) + bN.alphaEff;
     s.mu = k.implicit ? 0.0 : w * (bP.mu - bN.mu) + bN.mu;
-    const double hf = SMEM ? sd[13 * kTmaTile + li] : __ldg(&fv.hf[f]);
+    const double hf = SMEM ? sd[11 * kTmaTile + li] : __ldg(&fv.hf[f]);
     {
         const double tI = w * (bP.aByC - bN.aByC) + bN.aByC;
         s.tau = k.tauMode == 0 ? tI * hf                     // constScPrModel1.C:103
@@ -748,7 +748,7 @@ __device__ __forceinline__ void faceFluxOne(const Consts& k, const FaceView& fv,
         sv.FI[0][slot] = Fm; sv.FI[1][slot] = FU[0]; sv.FI[2][slot] = FU[1]; sv.FI[3][slot] = FU[2]; sv.FI[4][slot] = FE;
     }
     if (ADJUST) {                                           // QGDCourantNo.H:38-50
-        const double ms = SMEM ? sd[14 * kTmaTile + li] : __ldg(&fv.magSf[f]);
+        const double ms = SMEM ? sd[12 * kTmaTile + li] : __ldg(&fv.magSf[f]);
         const double Unf = s.U[0] * (Sf[0] / ms) + s.U[1] * (Sf[1] / ms) + s.U[2] * (Sf[2] / ms);
         coMax = fmax(coMax, fmax(fabs(Unf + s.c), fabs(Unf - s.c)) / hf);
         tauMin = fmin(tauMin, s.tau);
@@ -879,8 +879,8 @@ __device__ __forceinline__ void bulkLoadHint(void* dstSmem, const void* srcGloba
 }
 
 template <bool ADJUST> struct TmaStage {
-    static constexpr int kDoubles = ADJUST ? 15 : 14;
-    static constexpr int kBytes = kTmaTile * (3 * 4 + 16 + 8 * kDoubles);
+    static constexpr int kDoubles = ADJUST ? 13 : 12;       // G1[3] G2[3] gpS | Sf[3] | w | hQGDf [| |Sf|]
+    static constexpr int kBytes = kTmaTile * (3 * 4 + 16 + 8 * kDoubles);      // stage size (flags slot included)
     // layout inside a stage: vtx int4[T] | doubles [kDoubles][T] | own int[T] | nei int[T] | flags int[T]
     static constexpr int oVtx = 0, oD = kTmaTile * 16, oOwn = oD + kTmaTile * 8 * kDoubles, oNei = oOwn + kTmaTile * 4, oFlags = oNei + kTmaTile * 4;
 };
@@ -890,7 +890,8 @@ __device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* 
 {
     using L = TmaStage<ADJUST>;
     const size_t f0 = (size_t)tile * kTmaTile, fs = fv.fs;
-    mbarExpectTx(bar, (unsigned)L::kBytes);
+    // uniform flags (hex / single-type meshes): the 4-byte column is not streamed at all
+    mbarExpectTx(bar, (unsigned)(L::kBytes - (fv.flagsUniform >= 0 ? kTmaTile * 4 : 0)));
     auto bulkLoad = [pol](void* d, const void* s, unsigned b, unsigned long long* m) {
         if (STREAM) bulkLoadHint(d, s, b, m, pol);
         else qgd::bulkLoad(d, s, b, m);
@@ -898,15 +899,15 @@ __device__ __forceinline__ void tmaIssueTile(const FaceView& fv, unsigned char* 
     bulkLoad(stage + L::oVtx, fv.vtx + f0, kTmaTile * 16, bar);
     double* d = reinterpret_cast<double*>(stage + L::oD);
 #pragma unroll
-    for (int q = 0; q < 9; ++q) bulkLoad(d + q * kTmaTile, fv.G + q * fs + f0, kTmaTile * 8, bar);
+    for (int q = 0; q < 7; ++q) bulkLoad(d + q * kTmaTile, fv.G + q * fs + f0, kTmaTile * 8, bar);
 #pragma unroll
-    for (int q = 0; q < 3; ++q) bulkLoad(d + (9 + q) * kTmaTile, fv.Sf + q * fs + f0, kTmaTile * 8, bar);
-    bulkLoad(d + 12 * kTmaTile, fv.w + f0, kTmaTile * 8, bar);
-    bulkLoad(d + 13 * kTmaTile, fv.hf + f0, kTmaTile * 8, bar);
-    if (ADJUST) bulkLoad(d + 14 * kTmaTile, fv.magSf + f0, kTmaTile * 8, bar);
+    for (int q = 0; q < 3; ++q) bulkLoad(d + (7 + q) * kTmaTile, fv.Sf + q * fs + f0, kTmaTile * 8, bar);
+    bulkLoad(d + 10 * kTmaTile, fv.w + f0, kTmaTile * 8, bar);
+    bulkLoad(d + 11 * kTmaTile, fv.hf + f0, kTmaTile * 8, bar);
+    if (ADJUST) bulkLoad(d + 12 * kTmaTile, fv.magSf + f0, kTmaTile * 8, bar);
     bulkLoad(stage + L::oOwn, fv.own + f0, kTmaTile * 4, bar);
     bulkLoad(stage + L::oNei, fv.nei + f0, kTmaTile * 4, bar);
-    bulkLoad(stage + L::oFlags, fv.flags + f0, kTmaTile * 4, bar);
+    if (fv.flagsUniform < 0) bulkLoad(stage + L::oFlags, fv.flags + f0, kTmaTile * 4, bar);
 }
 
 template <bool ADJUST, int HINT>
@@ -944,7 +945,7 @@ __global__ void __launch_bounds__(kTmaTile, 2) k_face_flux_tma(Consts k, FaceVie
         const int li = threadIdx.x;
         const int f = tile * kTmaTile + li;
         const int P = reinterpret_cast<const int*>(sg + L::oOwn)[li], N = reinterpret_cast<const int*>(sg + L::oNei)[li];
-        const int flags = reinterpret_cast<const int*>(sg + L::oFlags)[li];
+        const int flags = fv.flagsUniform >= 0 ? fv.flagsUniform : reinterpret_cast<const int*>(sg + L::oFlags)[li];
         const int4 v = reinterpret_cast<const int4*>(sg + L::oVtx)[li];
         faceFluxOne<ADJUST, true, false, HINT>(k, fv, sv, f, (size_t)f, P, N, flags, v, coMax, tauMin,
                                                       reinterpret_cast<const double*>(sg + L::oD), li, polKeep);

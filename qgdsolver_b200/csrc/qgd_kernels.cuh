@@ -43,7 +43,8 @@ struct FaceView {            // all faces: internal [0,nI) then boundary [nI,nF)
     const double* hf;        // nF  hQGDf
     const double* dC;        // nF  deltaCoeffs
     const double* ndC;       // nF  nonOrthDeltaCoeffs
-    const double* G;         // SoA 9*nF
+    const double* G;         // SoA 7*fs: G1[3], G2[3], gpS with GP = gpS * Sf (in every fvsc scheme GP is parallel to the face area vector)
+    int flagsUniform;        // >= 0: every active internal face carries these flags (the TMA kernel then skips the flags column)
     int lsqW;                // leastSquares: ELL width, cells [lsqW][nI] and coefficient vectors [lsqW][3][nI] (device face order)
     const int* lsqCells; const double* lsqCoef;
     const double* halfDist;  // nB
@@ -180,6 +181,7 @@ struct qgd_fvsc {
     qgd::DevBuf<int4> vtx;
     qgd::DevBuf<int> flags;
     qgd::DevBuf<double> G, halfDist;
+    int flagsUniform = -1;
     bool lsq = false;              // leastSquares scheme
     int lsqW = 0;
     qgd::DevBuf<int> lsqCells;
@@ -196,7 +198,7 @@ struct qgd_fvsc {
         if (m.h.nD == 2 && !reduced) for (int d = 0; d < 3; ++d) if (m.h.gD[d] < 1) v.zeroDivCmpt = d;
         v.own = m.owner.p; v.nei = m.neighbour.p; v.vtx = vtx.p; v.flags = flags.p; v.Sf = m.Sf.p; v.magSf = m.magSf.p;
         v.w = m.w.p; v.hf = m.hQGDf.p; v.dC = m.dC.p; v.ndC = m.ndC.p; v.lsqW = lsq ? lsqW : 0; v.lsqCells = lsqCells.p; v.lsqCoef = lsqCoef.p; v.G = G.p; v.halfDist = halfDist.p; v.bKind = m.bfaceKind.p;
-        v.perm = m.facePermDev.p;
+        v.perm = m.facePermDev.p; v.flagsUniform = flagsUniform;
         return v;
     }
 };

@@ -172,8 +172,8 @@ __device__ __forceinline__ FaceGeo loadGeo(const FaceView& fv, int f)
     for (int i = 0; i < 3; ++i) {
         o.g1[i] = __ldg(&fv.G[(size_t)(0 + i) * fv.fs + f]);
         o.g2[i] = __ldg(&fv.G[(size_t)(3 + i) * fv.fs + f]);
-        o.gp[i] = __ldg(&fv.G[(size_t)(6 + i) * fv.fs + f]);
         o.Sf[i] = __ldg(&fv.Sf[(size_t)i * fv.fs + f]);
+        o.gp[i] = __ldg(&fv.G[6 * (size_t)fv.fs + f]) * o.Sf[i];            // GP = gpS * Sf
     }
     return o;
 }
@@ -804,9 +804,9 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
         if (sub) {          // decomposed run on an extended sub-mesh (qgd_qhdfoam_set_halo): explicit branch, PCG + diagonal | none
             if (d->implicit_diffusion || d->scalar_transport)
                 throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam on extended sub-meshes (multi-GPU): implicitDiffusion / scalarTransportQHDFoam are not available yet");
-            if (precond == 2)
-                throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam on extended sub-meshes (multi-GPU): the p preconditioner must be diagonal or none "
-                                                 "(DIC is local to a processor block in a decomposed run and not available on sub-meshes yet)");
+            if (precond == 2 && mesh->h.pcgBlock.empty())
+                throw Error(QGD_ERR_UNSUPPORTED, "QHDFoam on extended sub-meshes (multi-GPU): DIC is local to a block in a decomposed run - set DIC "
+                                                 "blocks first (qgd_mesh_make_pcg_blocks) or use diagonal | none");
         }
         if (!(d->delta_t > 0.0) || !(d->rho0 > 0.0) || !(d->Pr > 0.0)) throw Error(QGD_ERR_INVALID, "qgd_qhdfoam_create: deltaT, rho and Pr must be positive");
         // decomposed runs: the local id of the global pRefCell on the rank that owns it, -1 on every other rank

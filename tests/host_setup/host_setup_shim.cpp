@@ -71,6 +71,16 @@ void hs_lsq(void* p, int opt, int* cells, double* coef, char* deg)
     std::memcpy(deg, d.data(), d.size());
 }
 
+// DIC blocks by recursive coordinate bisection (HostMesh::makePcgBlocks): block id per cell, returns the number of blocks
+int hs_pcg_blocks(void* p, int target, int* out)
+{
+    HostMesh& h = *static_cast<HostMesh*>(p);
+    h.makePcgBlocks(target);
+    int nb = 0;
+    for (int c = 0; c < h.nCells; ++c) { out[c] = h.pcgBlock[c]; nb = nb > out[c] + 1 ? nb : out[c] + 1; }
+    return nb;
+}
+
 // cell -> faces rows (CSR) as the device ELL / tail builder consumes them
 int hs_cell_faces(void* p, int* off, int* enc)
 {

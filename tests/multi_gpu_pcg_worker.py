@@ -33,7 +33,12 @@ sub = decompose.extended_submeshes(mesh, cell_rank, ranks=[rank])[0]
 dm = api.Mesh(sub.mesh, n_owned=sub.n_owned, coupled_face=sub.coupled_face)
 cg = sub.cell_global
 ok = True
-for precond in ("diagonal", "none"):
+# DIC in a decomposed run is block-local: tiles inside every rank's owned cells (qgd_mesh_make_pcg_blocks); the oracle gets the
+# same map in global numbering (rank r's blocks follow those of ranks < r)
+blk_local = dm.make_pcg_blocks(60)[:sub.n_owned]
+np.save(f"/tmp/qgd_multi_pcg_blk_{rank}.npy", blk_local)
+dist.barrier()
+for precond in ("diagonal", "none", "DIC"):
     x, it, r0, r1 = api.pcg_solve_multi(dm, sub, diag_g[cg], upper_g[sub.face_global[:sub.mesh.n_internal]], b_g[cg], np.zeros(cg.size),
                                         tol=1e-12, max_iter=3000, precond=precond)
     np.save(f"/tmp/qgd_multi_pcg_{rank}.npy", x[:sub.n_owned])
@@ -42,7 +47,15 @@ for precond in ("diagonal", "none"):
     if rank == 0:
         import oracle as O
         o = O.Oracle(mesh)
-        xs, its, r0s, r1s = o.pcg_solve(diag_g, upper_g, b_g, np.zeros(nC), tol=1e-12, maxIter=3000, precond=O.PRECONDS[precond], cell_block=cell_rank)
+        blocks = cell_rank
+        if precond == "DIC":
+            blocks, base = np.zeros(nC, np.int32), 0
+            for r in range(world):
+                s_r = decompose.extended_submeshes(mesh, cell_rank, ranks=[r])[0]
+                b_r = np.load(f"/tmp/qgd_multi_pcg_blk_{r}.npy")
+                blocks[s_r.cell_global[:s_r.n_owned]] = base + b_r
+                base += int(b_r.max()) + 1
+        xs, its, r0s, r1s = o.pcg_solve(diag_g, upper_g, b_g, np.zeros(nC), tol=1e-12, maxIter=3000, precond=O.PRECONDS[precond], cell_block=blocks)
         got = np.zeros(nC)
         for r in range(world):
             s_r = decompose.extended_submeshes(mesh, cell_rank, ranks=[r])[0]

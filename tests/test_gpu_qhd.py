@@ -79,6 +79,65 @@ def test_pcg_iterates_are_identical_for_a_fixed_iteration_count(qgd, oracle_mod)
             assert rel_linf(xg, xo) < 1e-12 and abs(r1g - r1o) < 1e-10 * r1o
 
 
+@pytest.mark.parametrize("mesh_name,target", [("hex3d", 40), ("hex2d", 64), ("prism", 30), ("poly", 25), ("line", 8)])
+def test_block_local_dic_matches_the_decomposed_run_oracle(qgd, oracle_mod, mesh_name, target):
+    """DIC blocks (qgd_mesh_make_pcg_blocks): the preconditioner is factorised and swept per block by one CTA in shared memory;
+    the oracle is the decomposed-run solver or_pcg_solve_blocks with the same cell -> block map (what `mpirun -np N` does with
+    N = number of blocks).  Fixed iteration counts agree to rounding, the converged solves agree in iterations and solution;
+    the stepwise (one kernel per phase) solver takes the same preconditioner."""
+    mesh = PCG_MESHES[mesh_name]()
+    diag, upper, b, x_true = _poisson(mesh, 31)
+    o = oracle_mod.Oracle(mesh)
+    dm = qgd.Mesh(mesh)
+    blk = dm.make_pcg_blocks(target)
+    assert blk.min() == 0 and np.bincount(blk).max() <= target and blk.max() + 1 >= mesh.n_cells // target
+    x0 = 0.1 * np.cos(mesh.C[:, 0])
+    for k in (1, 3, 8):
+        xo, ito, _, r1o = o.pcg_solve(diag, upper, b, x0, tol=0.0, relTol=0.0, maxIter=k, precond=2, cell_block=blk)
+        xg, itg, _, r1g = qgd.pcg_solve(dm, diag, upper, b, x0, tol=0.0, rel_tol=0.0, max_iter=k, precond="DIC")
+        assert ito == itg == k and rel_linf(xg, xo) < 1e-12 and abs(r1g - r1o) < 1e-10 * r1o
+    xo, ito, r0o, _ = o.pcg_solve(diag, upper, b, x0, tol=1e-12, maxIter=3000, precond=2, cell_block=blk)
+    xg, itg, r0g, r1g = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-12, max_iter=3000, precond="DIC")
+    assert abs(itg - ito) <= max(2, ito // 20) and r1g < 1e-12 and rel_linf(xg, xo) < 1e-9 and rel_linf(xg, x_true) < 1e-9
+    xs, its, _, r1s = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-12, max_iter=3000, precond="DIC", stepwise=True)
+    assert abs(its - ito) <= max(2, ito // 20) and r1s < 1e-12 and rel_linf(xs, xo) < 1e-9
+    _, itd, _, _ = qgd.pcg_solve(dm, diag, upper, b, x0, tol=1e-12, max_iter=3000, precond="diagonal")
+    if mesh_name != "line":
+        assert itg < itd                                   # the point of the exercise
+    # one block = the serial DIC: identical to the level-scheduled kernel
+    dm.set_pcg_blocks(np.zeros(mesh.n_cells, np.int32))
+    x1, it1, _, _ = qgd.pcg_solve(dm, diag, upper, b, x0, tol=0.0, max_iter=5, precond="DIC")
+    dm.set_pcg_blocks(None)
+    x2, it2, _, _ = qgd.pcg_solve(dm, diag, upper, b, x0, tol=0.0, max_iter=5, precond="DIC")
+    assert it1 == it2 == 5 and rel_linf(x1, x2) < 1e-13
+
+
+def test_block_dic_in_the_solvers(qgd, oracle_mod):
+    """QHDFoam pressure solve and the implicit U / e solves of QGDFoam with DIC blocks against the oracle with set_pcg_blocks"""
+    c = cases.qhd_cavity(n=(24, 20), dt=1e-3, perturb=0.1)
+    dm = qgd.Mesh(c.mesh)
+    blk = dm.make_pcg_blocks(48)
+    o = c.make_oracle(oracle_mod)
+    o.set_pcg_blocks(blk)
+    s = c.make_solver(qgd, dm)
+    c.oracle_step(o, 60)
+    s.step(60)
+    for f in ("U", "T", "p"):
+        assert rel_linf(s.get(f), o.qhd_get(f)) < TOL_STEP, f
+    gi, oi = s.solver_info(), o.qhd_solver_info()
+    assert abs(gi["iters"] - oi["iters"]) <= max(2, oi["iters"] // 10)
+    g = cases.case_hex3d(perturb=0.15, bcs="mixed", implicit=True)
+    dg = qgd.Mesh(g.mesh)
+    bg = dg.make_pcg_blocks(60)
+    og = g.make_oracle(oracle_mod)
+    og.set_pcg_blocks(bg)
+    sg = g.make_solver(qgd, dg)
+    g.oracle_step(og, 60)
+    sg.step(60)
+    for f in ("rho", "rhoU", "rhoE", "e"):
+        assert rel_linf(sg.get(f), og.get(f)) < TOL_STEP, f
+
+
 def test_pcg_relative_tolerance_and_converged_start(qgd, oracle_mod):
     mesh = PCG_MESHES["hex2d"]()
     diag, upper, b, x_true = _poisson(mesh, 5)

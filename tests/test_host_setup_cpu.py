@@ -34,6 +34,7 @@ def shim():
     L.hs_lsq_width.argtypes = [C.c_void_p, C.c_int]
     L.hs_lsq.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_char_p]
     L.hs_cell_faces.argtypes = [C.c_void_p, _ip, _ip]
+    L.hs_pcg_blocks.argtypes = [C.c_void_p, C.c_int, _ip]
     return L
 
 
@@ -188,3 +189,57 @@ def test_face_flags_mark_the_reference_quirks(shim):
     assert np.abs(G[0:6][:, nv > 4]).max() == 0.0                     # G1 = G2 = 0 on polygons
     _, flags, _, _ = Host(shim, t).records(reduced=True)
     assert ((flags[t.n_internal:] & FF_NORMAL_ONLY) != 0).all() and not (flags & FF_POINTS).any()
+
+
+def test_pcg_blocks_are_compact_tiles_and_precondition_like_dic(shim, oracle_mod):
+    """HostMesh::makePcgBlocks (recursive coordinate bisection): every cell in exactly one block, block sizes within
+    (target/2, target], tiles compact (a 64 x 64 mesh cut into 256-cell tiles: 16 x 16 squares); with these blocks the oracle's
+    block-local DIC (or_pcg_solve_blocks = what `mpirun -np N` does) needs far fewer iterations than the diagonal preconditioner."""
+    import cases
+    n = 64
+    mesh = cases.pm.hex_box(n, n, 1, lengths=(1.0, 1.0, 0.1), patch_kinds={"zMin": "empty", "zMax": "empty"})
+    host = Host(shim, mesh)
+    blk = np.empty(mesh.n_cells, np.int32)
+    nb = shim.hs_pcg_blocks(host.h, 256, blk.ctypes.data_as(_ip))
+    assert nb == 16 and blk.min() == 0 and blk.max() == nb - 1
+    cnt = np.bincount(blk)
+    assert cnt.max() <= 256 and cnt.min() > 128
+    for b in range(nb):                                  # 16 x 16 squares
+        c = mesh.C[blk == b]
+        assert np.ptp(c[:, 0]) < 16.0 / n and np.ptp(c[:, 1]) < 16.0 / n
+    nb2 = shim.hs_pcg_blocks(host.h, 100, blk.ctypes.data_as(_ip))
+    cnt = np.bincount(blk)
+    assert nb2 == 64 and cnt.max() <= 100 and cnt.min() >= 50
+    nI = mesh.n_internal
+    upper = -(mesh.magSf[:nI] * mesh.deltaCoeffs[:nI])
+    diag = np.zeros(mesh.n_cells)
+    np.subtract.at(diag, mesh.owner[:nI], upper); np.subtract.at(diag, mesh.neighbour, upper)
+    diag[0] += diag[0]
+    b = np.random.default_rng(0).standard_normal(mesh.n_cells)
+    o = oracle_mod.Oracle(mesh)
+    its = {}
+    for name, pc, cb in (("diagonal", 1, None), ("DIC", 2, None), ("blockDIC", 2, blk)):
+        _, its[name], _, res = o.pcg_solve(diag, upper, b, np.zeros(mesh.n_cells), tol=1e-8, maxIter=5000, precond=pc, cell_block=cb)
+        assert res < 1e-8
+    assert its["DIC"] <= its["blockDIC"] < 0.55 * its["diagonal"]
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("reduced", [False, True])
+def test_cell_difference_vector_of_every_record_is_parallel_to_sf(shim, name, reduced):
+    """The device keeps GP as one scalar times Sf (7 doubles per face instead of 9): in every fvsc scheme and on every face type
+    GP is parallel to the face area vector - quad: (e1 x e2)/D with the two diagonals (half their cross product is the vector area
+    of ANY quadrilateral, planar or warped); tri: A_f / (3 vt); 2D: the in-plane normal of the edge v13; 1D / reduced / polygon
+    faces: -nf delta.  Also checked on a strongly warped hex mesh."""
+    import cases
+    meshes = [MESHES[name]()]
+    if name == "hex_perturbed":
+        meshes.append(cases.pm.hex_box(6, 5, 4, perturb=0.35, grading=(3, 1, 0.3), seed=23))
+    for mesh in meshes:
+        _, flags, G, _ = Host(shim, mesh).records(reduced)
+        keep = np.ones(mesh.n_faces, bool)
+        keep[mesh.n_internal:] = mesh.patch_kind_per_bface() != 1
+        GP, S = G[6:9].T[keep], mesh.Sf[keep]
+        s = (GP * S).sum(1) / (S * S).sum(1)
+        assert np.abs(GP - s[:, None] * S).max() <= 1e-12 * np.abs(GP).max()
+        assert np.abs(s).min() > 0
