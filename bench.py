@@ -487,7 +487,7 @@ def main():
                          "poly = a configs[4]-shaped polyhedral mesh (one GPU's share)")
     ap.add_argument("--geometry", default="step", choices=["step", "box"], help="--case qgd2d: forward-facing step (configs[1]) or a plain box")
     ap.add_argument("--precond", default="diagonal")
-    ap.add_argument("--pcg-blocks", type=int, default=512, help="--precond DIC: target cells per DIC block (0 = the serial, level-scheduled DIC)")
+    ap.add_argument("--pcg-blocks", type=int, default=128, help="--precond DIC: target cells per DIC block (0 = the serial, level-scheduled DIC)")
     ap.add_argument("--p-tol", type=float, default=1e-8)
     ap.add_argument("--p-rel-tol", type=float, default=0.0)
     ap.add_argument("--qhd-dt", type=float, default=1e-5, help="explicit QHD step: dt < h^2/(4 nu) = 2.5e-5 at 1000^2")

@@ -100,12 +100,15 @@ __device__ void dicSweeps(cg::grid_group& grid, const PcgView& v, int tid, int n
     }
 }
 
-// ---- block-local DIC.  One CTA per block at a time: the block's rows (in-block entries, block order) and its part of the
-// vector are staged in shared memory, the forward / backward sweeps run level by level with __syncthreads() only - no grid-wide
-// synchronisation inside the preconditioner.  Operation order per cell = ascending (forward) / descending (backward) face order
-// of its in-block entries, i.e. the sequential sweeps of DICPreconditioner on the block's own lduMatrix.
-// smem layout: z[B] | rD[B] | coef[Wb][B] | enc[Wb][B]   (B = v.maxBlockCells)
-struct BlockSmem { double* z; double* rD; double* coef; int* enc; };
+// ---- block-local DIC.  One work unit per block at a time: the block's rows (in-block entries, block order), its level offsets
+// and its part of the vector are staged in shared memory, the forward / backward sweeps run level by level with a unit-local
+// barrier only - no grid-wide synchronisation inside the preconditioner.  The unit is a WARP when a block fits a warp's share of
+// the shared memory (PcgView::dicWarp: 8 blocks in flight per CTA, __syncwarp between levels - the levels of a small tile hold at
+// most a few dozen cells, so a CTA-wide barrier would idle 7 of 8 warps), else the whole CTA.  Operation order per cell =
+// ascending (forward) / descending (backward) face order of its in-block entries, i.e. the sequential sweeps of DICPreconditioner
+// on the block's own lduMatrix.
+// smem layout of one unit: z[B] | rD[B] | coef[Wb][B] | enc[Wb][B] | lvl[maxLevels+2]   (B = v.maxBlockCells)
+struct BlockSmem { double* z; double* rD; double* coef; int* enc; int* lvl; };
 __device__ __forceinline__ BlockSmem blockSmem(const PcgView& v, unsigned char* raw)
 {
     BlockSmem s;
@@ -114,36 +117,50 @@ __device__ __forceinline__ BlockSmem blockSmem(const PcgView& v, unsigned char* 
     s.rD = s.z + B;
     s.coef = s.rD + B;
     s.enc = reinterpret_cast<int*>(s.coef + (size_t)v.Wb * B);
+    s.lvl = s.enc + (size_t)v.Wb * B;
     return s;
 }
-__device__ __forceinline__ void blockLoadRows(const PcgView& v, const BlockSmem& sm, int p0, int nb, const double* rDsrc)
+template <bool WARP> struct Unit {
+    __device__ static int lanes() { return WARP ? 32 : (int)blockDim.x; }
+    __device__ static int lane() { return WARP ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+    __device__ static int id() { return WARP ? (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : (int)blockIdx.x; }
+    __device__ static int count() { return WARP ? (int)(gridDim.x * (blockDim.x >> 5)) : (int)gridDim.x; }
+    __device__ static void sync() { if (WARP) __syncwarp(); else __syncthreads(); }
+};
+// stage rows + level offsets of block [p0, p0+nb); src: the per-cell array that seeds rD (the reciprocal diagonal or, for the
+// factorisation, the matrix diagonal)
+template <bool WARP>
+__device__ __forceinline__ int blockStage(const PcgView& v, const BlockSmem& sm, int b, int& p0, int& nb, const double* src)
 {
     const size_t n = v.n, B = v.maxBlockCells;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-        const int c = __ldg(&v.bCells[p0 + i]);
-        if (rDsrc) sm.rD[i] = rDsrc[c];
+    p0 = __ldg(&v.bOff[b]); nb = __ldg(&v.bOff[b + 1]) - p0;
+    const int l0 = __ldg(&v.bLvlStart[b]), nl = __ldg(&v.bLvlStart[b + 1]) - l0 - 1;
+    for (int i = Unit<WARP>::lane(); i <= nl; i += Unit<WARP>::lanes()) sm.lvl[i] = __ldg(&v.bLvlOff[l0 + i]) - p0;
+    for (int i = Unit<WARP>::lane(); i < nb; i += Unit<WARP>::lanes()) {
+        sm.rD[i] = src[__ldg(&v.bCells[p0 + i])];
         for (int j = 0; j < v.Wb; ++j) {
             sm.enc[j * B + i] = __ldg(&v.bEnc[(size_t)j * n + p0 + i]);
             sm.coef[j * B + i] = __ldg(&v.bCoef[(size_t)j * n + p0 + i]);
         }
     }
+    return nl;
 }
 // z = M^-1 r on every block; returns this thread's part of sum(z*r)
-__device__ double dicBlocks(const PcgView& v, unsigned char* raw)
+template <bool WARP>
+__device__ double dicBlocksT(const PcgView& v, unsigned char* raw)
 {
-    const BlockSmem sm = blockSmem(v, raw);
+    const BlockSmem sm = blockSmem(v, raw + (WARP ? (size_t)(threadIdx.x >> 5) * v.dicUnitSmem : 0));
     const size_t B = v.maxBlockCells;
+    const int L = Unit<WARP>::lanes(), t = Unit<WARP>::lane();
     double zr = 0.0;
-    for (int b = blockIdx.x; b < v.nBlocks; b += gridDim.x) {
-        const int p0 = __ldg(&v.bOff[b]), nb = __ldg(&v.bOff[b + 1]) - p0;
-        const int l0 = __ldg(&v.bLvlStart[b]), nl = __ldg(&v.bLvlStart[b + 1]) - l0 - 1;
-        __syncthreads();                                   // the previous block's shared data is no longer read
-        blockLoadRows(v, sm, p0, nb, v.rD);
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) sm.z[i] = sm.rD[i] * v.r[__ldg(&v.bCells[p0 + i])];
-        __syncthreads();
+    for (int b = Unit<WARP>::id(); b < v.nBlocks; b += Unit<WARP>::count()) {
+        int p0, nb;
+        Unit<WARP>::sync();                                // the previous block's shared data is no longer read
+        const int nl = blockStage<WARP>(v, sm, b, p0, nb, v.rD);
+        for (int i = t; i < nb; i += L) sm.z[i] = sm.rD[i] * v.r[__ldg(&v.bCells[p0 + i])];
+        Unit<WARP>::sync();
         for (int l = 1; l < nl; ++l) {                     // wA[u] -= rD[u]*upper*wA[l], faces ascending
-            const int a = __ldg(&v.bLvlOff[l0 + l]) - p0, e = __ldg(&v.bLvlOff[l0 + l + 1]) - p0;
-            for (int i = a + (int)threadIdx.x; i < e; i += blockDim.x) {
+            for (int i = sm.lvl[l] + t; i < sm.lvl[l + 1]; i += L) {
                 const double rd = sm.rD[i];
                 double zc = sm.z[i];
                 for (int j = 0; j < v.Wb; ++j) {
@@ -152,11 +169,10 @@ __device__ double dicBlocks(const PcgView& v, unsigned char* raw)
                 }
                 sm.z[i] = zc;
             }
-            __syncthreads();
+            Unit<WARP>::sync();
         }
         for (int l = nl - 2; l >= 0; --l) {                // wA[l] -= rD[l]*upper*wA[u], faces descending
-            const int a = __ldg(&v.bLvlOff[l0 + l]) - p0, e = __ldg(&v.bLvlOff[l0 + l + 1]) - p0;
-            for (int i = a + (int)threadIdx.x; i < e; i += blockDim.x) {
+            for (int i = sm.lvl[l] + t; i < sm.lvl[l + 1]; i += L) {
                 const double rd = sm.rD[i];
                 double zc = sm.z[i];
                 for (int j = v.Wb - 1; j >= 0; --j) {
@@ -165,33 +181,37 @@ __device__ double dicBlocks(const PcgView& v, unsigned char* raw)
                 }
                 sm.z[i] = zc;
             }
-            __syncthreads();
+            Unit<WARP>::sync();
         }
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        for (int i = t; i < nb; i += L) {
             const int c = __ldg(&v.bCells[p0 + i]);
             const double zc = sm.z[i];
             v.z[c] = zc;
             zr += zc * v.r[c];
         }
     }
+    if (!WARP) __syncthreads();
     return zr;
+}
+__device__ __forceinline__ double dicBlocks(const PcgView& v, unsigned char* raw)
+{
+    return v.dicWarp ? dicBlocksT<true>(v, raw) : dicBlocksT<false>(v, raw);
 }
 
 // DIC::calcReciprocalD on every block: rD = diag ; faces ascending (in-block): rD[u] -= upper^2/rD[l] ; rD = 1/rD
-__global__ void __launch_bounds__(kPcgBlock) k_dic_factor_blocks(PcgView v, double* rDout)
+template <bool WARP>
+__device__ void dicFactorT(const PcgView& v, unsigned char* raw, double* rDout)
 {
-    extern __shared__ __align__(16) unsigned char rawF[];
-    const BlockSmem sm = blockSmem(v, rawF);
+    const BlockSmem sm = blockSmem(v, raw + (WARP ? (size_t)(threadIdx.x >> 5) * v.dicUnitSmem : 0));
     const size_t B = v.maxBlockCells;
-    for (int b = blockIdx.x; b < v.nBlocks; b += gridDim.x) {
-        const int p0 = __ldg(&v.bOff[b]), nb = __ldg(&v.bOff[b + 1]) - p0;
-        const int l0 = __ldg(&v.bLvlStart[b]), nl = __ldg(&v.bLvlStart[b + 1]) - l0 - 1;
-        __syncthreads();
-        blockLoadRows(v, sm, p0, nb, v.diag);
-        __syncthreads();
+    const int L = Unit<WARP>::lanes(), t = Unit<WARP>::lane();
+    for (int b = Unit<WARP>::id(); b < v.nBlocks; b += Unit<WARP>::count()) {
+        int p0, nb;
+        Unit<WARP>::sync();
+        const int nl = blockStage<WARP>(v, sm, b, p0, nb, v.diag);
+        Unit<WARP>::sync();
         for (int l = 1; l < nl; ++l) {
-            const int a = __ldg(&v.bLvlOff[l0 + l]) - p0, e = __ldg(&v.bLvlOff[l0 + l + 1]) - p0;
-            for (int i = a + (int)threadIdx.x; i < e; i += blockDim.x) {
+            for (int i = sm.lvl[l] + t; i < sm.lvl[l + 1]; i += L) {
                 double rc = sm.rD[i];
                 for (int j = 0; j < v.Wb; ++j) {
                     const int en = sm.enc[j * B + i];
@@ -199,10 +219,15 @@ __global__ void __launch_bounds__(kPcgBlock) k_dic_factor_blocks(PcgView v, doub
                 }
                 sm.rD[i] = rc;
             }
-            __syncthreads();
+            Unit<WARP>::sync();
         }
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) rDout[__ldg(&v.bCells[p0 + i])] = 1.0 / sm.rD[i];
+        for (int i = t; i < nb; i += L) rDout[__ldg(&v.bCells[p0 + i])] = 1.0 / sm.rD[i];
     }
+}
+__global__ void __launch_bounds__(kPcgBlock) k_dic_factor_blocks(PcgView v, double* rDout)
+{
+    extern __shared__ __align__(16) unsigned char rawF[];
+    if (v.dicWarp) dicFactorT<true>(v, rawF, rDout); else dicFactorT<false>(v, rawF, rDout);
 }
 
 // one preconditioner application as a stand-alone kernel (stepwise / decomposed solver): z = M^-1 r, per-CTA partial of z.r
@@ -395,7 +420,11 @@ __global__ void k_fill_coef(int n, int W, const int* __restrict__ encFace, const
     if (c < nTail) { const int f = tailFace[c]; tailCoef[c] = f >= 0 ? -faceCoef[f] : 0.0; }
 }
 
-int dicBlocksGrid(const PcgMatrix& A) { return std::max(1, std::min(A.nBlocks, 148 * 8)); }
+int dicBlocksGrid(const PcgMatrix& A)
+{
+    const int units = A.dicWarp ? (A.nBlocks + kPcgBlock / 32 - 1) / (kPcgBlock / 32) : A.nBlocks;
+    return std::max(1, std::min(units, 148 * (A.dicWarp ? 2 : 8)));
+}
 // z = M^-1 r with the block-local DIC of A as a stand-alone launch (stepwise / decomposed solver); partials: 2*dicBlocksGrid(A) doubles
 void launchDicBlocks(const PcgMatrix& A, const double* r, double* z, double* partials, const int* done, cudaStream_t st)
 {
@@ -413,7 +442,7 @@ static void dicFactor(PcgMatrix& A, cudaStream_t st)
     if (A.nBlocks > 0) {
         const size_t smem = A.dicSmemBytes();
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_dic_factor_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_dic_factor_blocks<<<std::min(A.nBlocks, 148 * 8), kPcgBlock, smem, st>>>(v, raw);
+        k_dic_factor_blocks<<<dicBlocksGrid(A), kPcgBlock, smem, st>>>(v, raw);
         return;
     }
     void* args[] = {&v, &raw};
@@ -543,6 +572,9 @@ void PcgMatrix::build(const HostMesh& h, const double* hdiag, const double* uppe
             }
         }
         nBlocks = nb;
+        maxBlockLevels = 0;
+        for (int b = 0; b < nb; ++b) maxBlockLevels = std::max(maxBlockLevels, lvlStart[b + 1] - lvlStart[b] - 1);
+        dicWarp = dicUnitSmem() <= 12 * 1024;          // a warp per block, 8 blocks in flight per CTA
         bOff.upload(off, st); bLvlStart.upload(lvlStart, st); bLvlOff.upload(lvlOffB, st); bCells.upload(order, st);
         bEnc.upload(be, st); bCoef.upload(bc, st);
         if (faceInv) bEncFace.upload(bf, st);
@@ -569,7 +601,7 @@ PcgView PcgMatrix::view(double tol, double relTol, int maxIter) const
     v.n = n; v.W = W; v.enc = enc.p; v.coef = coef.p; v.tailOff = tailOff.p; v.tailEnc = tailEnc.p; v.tailCoef = tailCoef.p;
     v.diag = diag.p; v.rD = rD.p; v.b = bExternal ? bExternal : b.p; v.x = xExternal ? xExternal : x.p; v.r = r.p; v.w = w.p; v.z = z.p; v.p0 = p0.p; v.p1 = p1.p;
     v.partials = partials.p; v.nLevels = nLevels; v.lvlOff = lvlOff.p; v.lvlCells = lvlCells.p;
-    v.nBlocks = nBlocks; v.Wb = Wb; v.maxBlockCells = maxBlockCells;
+    v.nBlocks = nBlocks; v.Wb = Wb; v.maxBlockCells = maxBlockCells; v.dicWarp = dicWarp ? 1 : 0; v.dicUnitSmem = (int)dicUnitSmem();
     v.bOff = bOff.p; v.bLvlStart = bLvlStart.p; v.bLvlOff = bLvlOff.p; v.bCells = bCells.p; v.bEnc = bEnc.p; v.bCoef = bCoef.p;
     v.tol = tol; v.relTol = relTol; v.maxIter = maxIter; v.precond = precond; v.out = out.p;
     return v;

@@ -28,6 +28,7 @@ struct PcgView {
     // positions).  Rows in block order, in-block entries only, ELL width Wb: bEnc[j*n + p] = (local position of the other cell
     // << 1) | lowerSide, -1 = none; bCoef the matching coefficient.  nBlocks = 0: the global level schedule above.
     int nBlocks, Wb, maxBlockCells;
+    int dicWarp, dicUnitSmem;    // work unit of the block sweeps: a warp (8 blocks in flight per CTA) or the CTA; bytes of shared memory per unit
     const int* bOff; const int* bLvlStart; const int* bLvlOff; const int* bCells; const int* bEnc; const double* bCoef;
     double tol, relTol; int maxIter, precond;
     PcgResult* out;
@@ -40,10 +41,12 @@ struct PcgMatrix {
     DevBuf<PcgResult> out;
     DevBuf<int> encFace, tailFace;   // device face id of every ELL / tail entry (-1: padding), for refresh()
     // block-local DIC (see PcgView)
-    int nBlocks = 0, Wb = 0, maxBlockCells = 0;
+    int nBlocks = 0, Wb = 0, maxBlockCells = 0, maxBlockLevels = 0;
+    bool dicWarp = false;
     DevBuf<int> bOff, bLvlStart, bLvlOff, bCells, bEnc, bEncFace;
     DevBuf<double> bCoef;
-    size_t dicSmemBytes() const { return nBlocks ? (size_t)maxBlockCells * (16 + 12 * (size_t)Wb) : 0; }
+    size_t dicUnitSmem() const { return nBlocks ? (((size_t)maxBlockCells * (16 + 12 * (size_t)Wb) + 4 * ((size_t)maxBlockLevels + 2) + 15) & ~(size_t)15) : 0; }
+    size_t dicSmemBytes() const { return dicUnitSmem() * (dicWarp ? 8 : 1); }
     int gridBlocks = 0;
     double* bExternal = nullptr;     // when set, the right-hand side lives in the caller's array
     double* xExternal = nullptr;     // when set, the solution vector lives in the caller's array (e.g. the p slice of the QHD state)

@@ -21,6 +21,17 @@ rank, world = dist.get_rank(), dist.get_world_size()
 api.init(local)
 multigpu.init_comm(rank, world)
 
+LOG = None
+if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+    LOG = open(os.path.join(ROOT, "gpurun_out", f"multi_pcg_parity_n{world}.log"), "w")
+
+
+def say(msg):
+    print(msg, flush=True)
+    if LOG:
+        LOG.write(msg + "\n"); LOG.flush()
+
+
 mesh = cases.pm.hex_box(14, 12, 10, perturb=0.1, seed=4)
 nI, nC = mesh.n_internal, mesh.n_cells
 upper_g = -(mesh.magSf[:nI] * mesh.deltaCoeffs[:nI])
@@ -63,11 +74,11 @@ for precond in ("diagonal", "none", "DIC"):
         err = float(np.abs(got - xs).max() / np.abs(xs).max())
         good = err < 1e-9 and abs(it - its) <= 1 and abs(r0 - r0s) < 1e-10 * r0s
         ok = ok and good
-        print(f"MPCG {precond} iterations {it} (oracle {its}) relLinf={err:.3e} {'ok' if good else 'FAIL'}", flush=True)
+        say(f"MPCG n={world} {precond} iterations {it} (oracle {its}) relLinf={err:.3e} {'ok' if good else 'FAIL'}")
     # the halo entries of the returned solution are the owners' values
     full = np.zeros(nC)
     dist.barrier()
 if rank == 0:
-    print("MPCG_ALL_OK" if ok else "MPCG_FAILED", flush=True)
+    say("MPCG_ALL_OK" if ok else "MPCG_FAILED")
 api.comm_finalize()
 dist.destroy_process_group()

@@ -79,7 +79,8 @@ def test_pcg_iterates_are_identical_for_a_fixed_iteration_count(qgd, oracle_mod)
             assert rel_linf(xg, xo) < 1e-12 and abs(r1g - r1o) < 1e-10 * r1o
 
 
-@pytest.mark.parametrize("mesh_name,target", [("hex3d", 40), ("hex2d", 64), ("prism", 30), ("poly", 25), ("line", 8)])
+# small tiles are swept by one warp each (8 in flight per CTA), tiles beyond 12 KB of rows by the whole CTA: ("hex2d", 300), ("hex3d", 260)
+@pytest.mark.parametrize("mesh_name,target", [("hex3d", 40), ("hex2d", 64), ("prism", 30), ("poly", 25), ("line", 8), ("hex2d", 300), ("hex3d", 260)])
 def test_block_local_dic_matches_the_decomposed_run_oracle(qgd, oracle_mod, mesh_name, target):
     """DIC blocks (qgd_mesh_make_pcg_blocks): the preconditioner is factorised and swept per block by one CTA in shared memory;
     the oracle is the decomposed-run solver or_pcg_solve_blocks with the same cell -> block map (what `mpirun -np N` does with
