@@ -237,6 +237,10 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd);
  * (phiJmH+phiQ-phiPiU); n_faces*k host buffer */
 int qgd_qgdfoam_get_flux(qgd_solver* s, int which, double* out);
 int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, double* time);
+/* The reference dumps U, e, rho when an update leaves min(e) <= 0 or min(rho) <= 0 and carries on (QGDFoam.C:142-147).  The
+ * device records the first such step (1-based count of steps taken by this solver, 0 = never); the shim polls this after a
+ * batch of steps and performs the writes (qgd_qgdfoam_get fields 3, 4, 0). */
+int qgd_qgdfoam_state_guard(qgd_solver* s, int* first_step);
 /* Step form.  mode 0 (default): two kernels (faces, then cells) with a full-size flux array; always used with
  * adjustTimeStep, whose global Courant maximum must be known before any cell is updated; needed for
  * qgd_qgdfoam_get_flux.  mode 1 (fixed deltaT only): internal faces and cells are processed by ONE persistent kernel whose

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "qgd_fvsc_create", "qgd_fvsc_destroy", "qgd_fvsc_grad", "qgd_fvsc_div",
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_step_fields_host", "qgd_qgdfoam_face_kernel", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
-    "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
+    "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_state_guard", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
     "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo", "qgd_qgdfoam_set_halo_faces",
@@ -134,6 +134,7 @@ def load_library():
     L.qgd_qgdfoam_get.argtypes = [C.c_void_p, C.c_int, _dp, _dp]
     L.qgd_qgdfoam_get_flux.argtypes = [C.c_void_p, C.c_int, _dp]
     L.qgd_qgdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
+    L.qgd_qgdfoam_state_guard.argtypes = [C.c_void_p, _ip]
     L.qgd_qgdfoam_launch_count.restype = C.c_longlong
     L.qgd_qgdfoam_launch_count.argtypes = [C.c_void_p]
     L.qgd_qgdfoam_profile.argtypes = [C.c_void_p, C.c_int]
@@ -463,6 +464,12 @@ class QGDFoam:
         dt, co, t = C.c_double(), C.c_double(), C.c_double()
         _check(load_library().qgd_qgdfoam_get_scalars(self._h, C.byref(dt), C.byref(co), C.byref(t)))
         return dict(deltaT=dt.value, CoNum=co.value, time=t.value)
+
+    def state_guard(self) -> int:
+        """first step (1-based) whose update left min(e) <= 0 or min(rho) <= 0 (QGDFoam.C:142-147), 0 = never"""
+        v = C.c_int()
+        _check(load_library().qgd_qgdfoam_state_guard(self._h, C.byref(v)))
+        return v.value
 
     def set_pipeline(self, mode: int, chunk_cells: int = 0, lag: int = -1, ring_slots: int = 0):
         """mode 1: pipelined face+cell kernel with the L2-resident flux ring; mode 0: two kernels, fluxes kept in HBM."""

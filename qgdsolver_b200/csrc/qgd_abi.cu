@@ -1421,6 +1421,18 @@ int qgd_qgdfoam_get_scalars(qgd_solver* s, double* delta_t, double* courant, dou
     });
 }
 
+int qgd_qgdfoam_state_guard(qgd_solver* s, int* first_step)
+{
+    return guarded([&] {
+        requireInit();
+        if (!s || !first_step) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_state_guard: null argument");
+        StepScalars sc;
+        QGD_CUDA(cudaMemcpyAsync(&sc, s->sc.p, sizeof(sc), cudaMemcpyDeviceToHost, g_stream));
+        QGD_CUDA(cudaStreamSynchronize(g_stream));
+        *first_step = sc.guardStep;
+    });
+}
+
 long long qgd_qgdfoam_launch_count(qgd_solver* s) { return s ? s->launches : 0; }
 
 int qgd_qgdfoam_diffusion_iterations(qgd_solver* s, int iters[4])

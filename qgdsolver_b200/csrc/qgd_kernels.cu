@@ -795,6 +795,7 @@ __global__ void k_dt(StepScalars* sc, int* pipeQueue)
         sc->dt = fmin(deltaTFact * sc->dt, maxDeltaT1);
     }
     sc->time += sc->dt;
+    sc->stepIndex += 1;
     sc->coMaxBits = 0ull;
     sc->tauMinBits = dbits(DBL_MAX);
 }
@@ -1031,6 +1032,7 @@ __device__ __forceinline__ void cellUpdateCore(const Consts& k, const SolverView
     e = rDeltaT * a.rho * a.e * V + V * ddt;
     if (src) e += __ldg(sv.su + 4 * nS + c);
     e /= diagR;
+    if (e <= 0.0 || rho <= 0.0) atomicCAS(&sv.sc->guardStep, 0, sv.sc->stepIndex);      // QGDFoam.C:142-147 (rare: no cost otherwise)
     cellThermo(k, rho, U, rhoU, rhoE, e, a.p, a.T, aQ, hQ, sv, c);
 }
 
@@ -1585,6 +1587,7 @@ __global__ void __launch_bounds__(kBlock) k_cell_implC(Consts k, SolverView sv)
     const double U[3] = {sv.S[n + c], sv.S[2 * n + c], sv.S[3 * n + c]};
     const double rhoU[3] = {rho * U[0], rho * U[1], rho * U[2]};
     const double rhoE = rho * (e + 0.5 * (U[0] * U[0] + U[1] * U[1] + U[2] * U[2]));
+    if (e <= 0.0 || rho <= 0.0) atomicCAS(&sv.sc->guardStep, 0, sv.sc->stepIndex);
     cellThermo(k, rho, U, rhoU, rhoE, e, pOld, TOld, __ldg(&sv.aQGD[c]), __ldg(&sv.hQGD[c]), sv, c);
 }
 

@@ -72,6 +72,9 @@ struct StepScalars {         // device-resident time-step control
     unsigned long long tauMinBits;  // min over faces of tauQGDf
     double maxCo, maxDeltaT, cTau;
     int adjust;
+    // QGDFoam.C:142-147: `if (min(e) <= 0 || min(rho) <= 0) { U.write(); e.write(); rho.write(); }` - the device records the
+    // first step (1-based, counted by k_dt) whose update produced a non-positive e or rho; 0 = never
+    int stepIndex, guardStep;
 };
 
 // ---- generic fvsc operator kernels (operator-level API)

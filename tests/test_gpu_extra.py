@@ -153,3 +153,24 @@ def test_decomposed_pcg_matches_oracle(n):
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stderr[-4000:]
     assert "MPCG_ALL_OK" in r.stdout
+
+
+def test_negative_state_guard_reports_the_first_bad_step(qgd, oracle_mod):
+    """QGDFoam.C:142-147: the reference dumps U, e, rho when an update leaves min(e) <= 0 or min(rho) <= 0.  The device records
+    the first such step; a healthy run reports 0, an unstable one (time step far beyond the stability limit) the same step at
+    which the oracle's fields first turn non-positive."""
+    ok = cases.case_hex3d(perturb=0.1, bcs="mixed")
+    s = ok.make_solver(qgd)
+    s.step(30)
+    assert s.state_guard() == 0
+    bad = cases.case_sod(100, dt=2e-2)
+    sb = bad.make_solver(qgd)
+    o = bad.make_oracle(oracle_mod)
+    first = 0
+    for k in range(1, 41):
+        bad.oracle_step(o, 1)
+        with np.errstate(invalid="ignore"):
+            if first == 0 and ((o.get("e") <= 0).any() or (o.get("rho") <= 0).any()):
+                first = k
+    sb.step(40)
+    assert first > 0 and sb.state_guard() == first
