@@ -1190,10 +1190,14 @@ int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const i
                 throw Error(QGD_ERR_UNSUPPORTED, "T boundary condition outside the device-native set (fixedValue, zeroGradient)");
             if (p[b] != QGD_BC_FIXED_VALUE && p[b] != QGD_BC_ZERO_GRADIENT && p[b] != QGD_BC_QGD_FLUX)
                 throw Error(QGD_ERR_UNSUPPORTED, "p boundary condition outside the device-native set (fixedValue, zeroGradient, qgdFlux)");
-            if (p[b] == QGD_BC_QGD_FLUX) s->anyQgdFlux = true;
             if ((u[b] == QGD_BC_FIXED_VALUE && !val_U) || (t[b] == QGD_BC_FIXED_VALUE && !val_T) || (p[b] == QGD_BC_FIXED_VALUE && !val_p))
                 throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_bcs: fixedValue patch without values");
         }
+        // Whether the qgdFlux mid-step sequence runs (k_bnd_pre + the halo exchange of p_b) must be the same decision on every rank
+        // of a decomposed run: it follows from the PATCH table - a sub-mesh keeps every global patch, possibly with no local face
+        // (a rank that held no qgdFlux face used to skip the exchange its neighbours were waiting in: N = 8 hang, round 2)
+        for (int pi = 0; pi < h.nPatches; ++pi)
+            if (h.patchKind[pi] != QGD_PATCH_EMPTY && bc_p[pi] == QGD_BC_QGD_FLUX) s->anyQgdFlux = true;
         s->bcU.upload(u, g_stream); s->bcT.upload(t, g_stream); s->bcP.upload(p, g_stream);
         std::vector<double> zero3(3 * (size_t)h.nBnd, 0.0), zero1(h.nBnd, 0.0);
         h2d(s->bvU, val_U ? val_U : zero3.data(), 3 * (size_t)h.nBnd);
