@@ -145,3 +145,40 @@ def test_two_rank_gloo_pcg():
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "PCG_OK" in r.stdout
+
+
+def test_every_rank_keeps_the_global_patch_table_even_without_faces_on_a_patch():
+    """Decisions that change the sequence of collective calls must be identical on every rank.  The qgdFlux mid-step exchange
+    is such a decision: with 2 x 2 x 2 sub-domains a corner rank holds no face of the odd patches (xMax, yMax, zMax), while its
+    neighbours do - a rank-local test ("do I hold a qgdFlux face?") then skips an exchange the neighbours wait in (the N = 8
+    hang of round 2).  The library now decides from the patch table, which every extended sub-mesh keeps complete: same
+    names, kinds and order as the global mesh (possibly zero-sized), plus the cut patch."""
+    c = cases.case_hex3d(n=(12, 10, 8), perturb=0.2, bcs="mixed")
+    mesh = c.mesh
+    rank = decompose.geometric_split(mesh, 8)
+    subs = decompose.extended_submeshes(mesh, rank)
+    names = [p.name for p in mesh.patches]
+    some_rank_misses_a_qgdflux_patch = False
+    for sd in subs:
+        local = sd.mesh.patches
+        assert [p.name for p in local[:-1]] == names and [p.kind for p in local[:-1]] == [p.kind for p in mesh.patches]
+        assert local[-1].name == "cutFaces" and local[-1].kind == cases.pm.PATCH_EMPTY
+        # what a rank-local decision would see: qgdFlux faces among the boundary faces of OWNED cells
+        holds = False
+        for i, p in enumerate(local[:-1]):
+            own = sd.mesh.owner[p.start:p.start + p.size]
+            if c.bcP[i] == cases.QF and (own < sd.n_owned).any():
+                holds = True
+        some_rank_misses_a_qgdflux_patch |= not holds
+        # the patch-table decision is the same everywhere
+        assert any(c.bcP[i] == cases.QF and p.kind != cases.pm.PATCH_EMPTY for i, p in enumerate(local[:-1]))
+    assert some_rank_misses_a_qgdflux_patch          # the situation that hung: at least one rank has no local qgdFlux face
+    # the boundary-face lists of the mid-step exchange pair up in size for every neighbour pair
+    by_rank = {sd.rank: sd for sd in subs}
+    for sd in subs:
+        assert set(sd.recv_cells) == set(sd.send_cells) == set(sd.recv_bfaces) == set(sd.send_bfaces)
+        for r, rb in sd.recv_bfaces.items():
+            assert rb.size == by_rank[r].send_bfaces[sd.rank].size
+        assert set(sd.recv_face_cells) == set(sd.send_face_cells)
+        for r, rc in sd.recv_face_cells.items():
+            assert rc.size == by_rank[r].send_face_cells[sd.rank].size
