@@ -19,7 +19,7 @@ def test_reference_arm_prints_the_contract_line():
     assert j["metric"] == "cell-updates/s per QGDFoam step" and j["dtype"] == "f64" and j["vs_baseline"] is None
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
-    assert "workload" in j["config"] and "model" not in j["config"] and j["config"]["same_workload_as_product_arm"] is False
+    assert "workload" in j["config"] and "model" not in j["config"] and j["same_workload_as_product_arm"] is False and "OpenMP" in j["arm"]
 
 
 def test_algorithmic_bytes_follow_the_survey_model():
