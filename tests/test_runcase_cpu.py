@@ -333,3 +333,38 @@ fvsc { default GaussVolPoint; }
     with pytest.raises(foamdict.FoamDictError):
         runcase._check_laplacian_schemes(foamdict.parse(realistic.replace("laplacian(taubyrhof,p) Gauss linear uncorrected;",
                                                                            "laplacian(taubyrhof,p) Gauss harmonic corrected;"), "fvSchemes"), ortho)
+
+
+def test_thermo_type_instantiations_and_slip_patches_from_the_dictionaries(tmp_path):
+    """thermoType transport / thermo entries map to the four hePsiQGDThermo instantiations of psiQGDThermos.C:65-111 (anything else
+    is refused like the reference's `Unknown psiQGDThermo type`); slip / symmetryPlane velocity patches map to QGD_BC_SLIP, on
+    scalars to zeroGradient."""
+    _write_sod(tmp_path)
+    th = tmp_path / "constant" / "thermophysicalProperties"
+    s = runcase.load_case(str(tmp_path))
+    assert "transport" not in s.solver_kwargs and s.solver_kwargs["mu"] == 0.0
+    th.write_text(THERMO.replace("transport       const;", "transport       sutherland;").replace("transport { mu 0; Pr 1; }", "transport { As 1.4792e-06; Ts 116; }"))
+    k = runcase.load_case(str(tmp_path)).solver_kwargs
+    assert k["transport"] == "sutherland" and k["As"] == 1.4792e-06 and k["Ts"] == 116.0
+    th.write_text(THERMO.replace("transport       const;", "transport       powerLaw;").replace("transport { mu 0; Pr 1; }", "transport { mu0 1.8e-5; T0 300; k 0.76; Pr 0.71; }"))
+    k = runcase.load_case(str(tmp_path)).solver_kwargs
+    assert (k["transport"], k["mu0"], k["T0"], k["k_exp"], k["Pr"]) == ("powerLaw", 1.8e-5, 300.0, 0.76, 0.71)        # powerLawTransport.C:53-60
+    th.write_text(THERMO.replace("thermo          hConst;", "thermo          eConst;").replace("thermodynamics { Cp 3.5; Hf 0; Tref 0; }", "thermodynamics { Cv 2.5; Hf 0; Tref 0; Esref 0.1; }"))
+    k = runcase.load_case(str(tmp_path)).solver_kwargs
+    assert (k["thermo"], k["Cv"], k["Esref"], k["Cp"]) == ("eConst", 2.5, 0.1, 3.5)
+    th.write_text(THERMO.replace("thermo          hConst;", "thermo          eConst;").replace("transport       const;", "transport       sutherland;"))
+    with pytest.raises(foamdict.FoamDictError, match="psiQGDThermos"):
+        runcase.load_case(str(tmp_path))
+    th.write_text(THERMO.replace("thermo          hConst;", "thermo          janaf;"))
+    with pytest.raises(foamdict.FoamDictError):
+        runcase.load_case(str(tmp_path))
+    # slip patches
+    c = cases.case_hex3d(n=(4, 3, 3))
+    m = c.mesh
+    types = {p.name: "zeroGradient" for p in m.patches}
+    types[m.patches[1].name], types[m.patches[2].name], types[m.patches[3].name] = "slip", "symmetryPlane", "symmetry"
+    fc.write_field(str(tmp_path / "s" / "U"), m, "U", c.U0, types)
+    fc.write_field(str(tmp_path / "s" / "p"), m, "p", c.p0, types)
+    kU, _ = fc.bc_arrays(m, fc.read_field(str(tmp_path / "s" / "U"), m))
+    kP, _ = fc.bc_arrays(m, fc.read_field(str(tmp_path / "s" / "p"), m))
+    assert list(kU) == [1, 6, 6, 6, 1, 1] and list(kP) == [1, 1, 1, 1, 1, 1]
