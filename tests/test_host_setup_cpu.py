@@ -39,9 +39,13 @@ def shim():
 
 
 class Host:
-    def __init__(self, L, mesh):
+    def __init__(self, L, mesh, n_owned=0, coupled_face=None):
         self.L, self.mesh = L, mesh
         d = api._MeshDesc()
+        d.n_owned_cells = int(n_owned)
+        self._coupled = None if coupled_face is None else np.ascontiguousarray(coupled_face, np.int32)
+        if self._coupled is not None:
+            d.coupled_internal_face = self._coupled.ctypes.data_as(_ip)
         d.n_cells, d.n_faces, d.n_internal_faces, d.n_points, d.n_patches = mesh.n_cells, mesh.n_faces, mesh.n_internal, mesh.n_points, len(mesh.patches)
         f64 = lambda a: np.ascontiguousarray(a, np.float64)
         i32 = lambda a: np.ascontiguousarray(a, np.int32)
@@ -243,3 +247,51 @@ def test_cell_difference_vector_of_every_record_is_parallel_to_sf(shim, name, re
         s = (GP * S).sum(1) / (S * S).sum(1)
         assert np.abs(GP - s[:, None] * S).max() <= 1e-12 * np.abs(GP).max()
         assert np.abs(s).min() > 0
+
+
+@pytest.mark.parametrize("mesh_fn,parts", [
+    (lambda: cases.pm.hex_box(8, 6, 5, perturb=0.25, grading=(2, 1, 0.5), seed=11), 2),
+    (lambda: cases.pm.hex_box(8, 8, 6, perturb=0.2, seed=4), 8),
+    (lambda: cases.pm.prism_box(4, 4, 3, perturb=0.15, seed=2), 4),
+    (lambda: cases.case_2d((12, 10), perturb=0.2).mesh, 4),
+])
+def test_decomposed_length_scales_match_the_n_subdomain_oracle(shim, oracle_mod, mesh_fn, parts):
+    """north_star: an N-GPU run must equal the N-SUBDOMAIN reference, whose QGD length scales differ from the serial run on
+    non-uniform meshes: hQGDf = 1/deltaCoeffs = |C_N - C_P| on processor-patch faces (QGDCoeffs.C:195-199) instead of
+    2 min(|C_P - C_f|, |C_N - C_f|) (:303-308), and hQGD (:320-362) averages those.  This is the ONLY decomposition-dependent
+    quantity of the path and it is host set-up code: the product's HostMesh::build on every rank's extended sub-mesh (coupled-face
+    flags) against the oracle run on the decomposePar-layout processor mesh of the same rank (processor patches, coupled geometry)."""
+    from qgdsolver_b200 import decompose
+    mesh = mesh_fn()
+    rank = decompose.geometric_split(mesh, parts)
+    subs = decompose.extended_submeshes(mesh, rank)
+    procs = decompose.processor_meshes(mesh, rank)
+    decompose.couple_processor_geometry(procs)
+    serial = oracle_mod.Oracle(mesh)
+    hf_serial = serial.hQGDf()
+    differs = 0.0
+    for sd, pr in zip(subs, procs):
+        host = Host(shim, sd.mesh, n_owned=sd.n_owned, coupled_face=sd.coupled_face)
+        hf, hc = np.zeros(sd.mesh.n_faces), np.zeros(sd.mesh.n_cells)
+        shim.hs_lengths(host.h, hf.ctypes.data_as(_dp), hc.ctypes.data_as(_dp))
+        o = oracle_mod.Oracle(pr.mesh)
+        ohf, ohc = o.hQGDf(), o.hQGD()
+        # cells: owned cells of the sub-mesh are the processor mesh's cells, in cellProcAddressing order
+        assert np.array_equal(sd.cell_global[:sd.n_owned], pr.cell_addr)
+        assert np.abs(hc[:sd.n_owned] - ohc).max() < 1e-14 * np.abs(ohc).max()
+        # faces: compare through the global face id (processor-mesh faces incl. its processor-patch faces)
+        g_proc = np.abs(pr.face_addr.astype(np.int64)) - 1
+        where = {int(g): i for i, g in enumerate(sd.face_global)}
+        kinds = np.full(pr.mesh.n_faces, 0)
+        for ptc in pr.mesh.patches:
+            kinds[ptc.start:ptc.start + ptc.size] = ptc.kind
+        idx = np.array([where[int(g)] for g in g_proc])
+        keep = kinds != cases.pm.PATCH_EMPTY
+        assert np.abs(hf[idx][keep] - ohf[keep]).max() < 1e-14 * np.abs(ohf[keep]).max()
+        # the coupled faces really follow the processor-patch rule, and it differs from the serial value on this mesh
+        proc_faces = kinds == cases.pm.PATCH_PROCESSOR
+        if proc_faces.any():
+            d = 1.0 / pr.mesh.deltaCoeffs[proc_faces]
+            assert np.abs(hf[idx][proc_faces] - d).max() < 1e-14 * d.max()
+            differs = max(differs, float(np.abs(hf[idx][proc_faces] - hf_serial[g_proc[proc_faces]]).max()))
+    assert differs > 1e-4          # non-uniform mesh: the decomposed run is NOT the serial run
