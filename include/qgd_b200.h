@@ -351,7 +351,8 @@ int qgd_pcg_solve(qgd_mesh* mesh, const double* diag, const double* upper, const
 /* The same solver cut into one kernel per phase (initial residual, preconditioning + wA.rA, search-direction update, SpMV +
  * wA.pA, solution / residual update), all scalars and the convergence flag on the device: the form a decomposed run needs, with
  * a halo exchange of the search direction and all-reduces of the dot products between the phases.  This entry point runs it on
- * one GPU (no communication); precond 0 | 1.  Experimental: compiled, not yet run on a device at the end of round 1. */
+ * one GPU (no communication); precond 0 | 1 | 2 (2 = DIC on the mesh's DIC blocks, which must be set).  Parity: tests/test_gpu_extra.py,
+ * tests/test_gpu_qhd.py::test_block_local_dic_matches_the_decomposed_run_oracle. */
 int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x,
                            double tolerance, double rel_tol, int max_iter, int precond,
                            int* iters, double* initial_residual, double* final_residual);
@@ -360,7 +361,7 @@ int qgd_pcg_solve_stepwise(qgd_mesh* mesh, const double* diag, const double* upp
  * with n_owned_cells), diag / b / x have n_cells entries (the rows of the owned cells are solved, halo entries of x are refreshed
  * over NCCL), upper follows the local internal faces.  Exchange lists = the face-neighbour subset of the halo, per neighbour k
  * (rank nbr_rank[k]): local cell ids send_cells[send_off[k] .. send_off[k+1]) and recv_cells[...], ascending global id on both
- * sides.  precond 0 | 1.  Experimental: compiled, not yet run on a device at the end of round 1. */
+ * sides.  precond 0 | 1 | 2 (DIC blocks inside the owned cells).  Parity at N = 2 and N = 8: tests/multi_gpu_pcg_worker.py. */
 int qgd_pcg_solve_multi(qgd_mesh* mesh, const double* diag, const double* upper, const double* b, double* x,
                         double tolerance, double rel_tol, int max_iter, int precond,
                         int n_neighbours, const int* nbr_rank, const int* send_off, const int* send_cells,

@@ -1,4 +1,4 @@
-// Stepwise PCG: the same algorithm as k_pcg (OpenFOAM v2312 PCG.C + diagonal / no preconditioner, normFactor residual
+// Stepwise PCG: the same algorithm as k_pcg (OpenFOAM v2312 PCG.C + DIC (blocks) / diagonal / no preconditioner, normFactor residual
 // norm; SURVEY.md App. A.5, call site QHDpEqn.H:45) cut into one kernel per phase, so that a halo exchange of the search
 // direction and all-reduces of the dot products can be placed between the phases: the form a decomposed (multi-GPU) run needs,
 // where every rank owns the rows [0, nRows) of its extended sub-mesh matrix and reads neighbour values from halo entries
@@ -9,8 +9,9 @@
 // at the flag once per chunk of iterations.  Without hooks the solver runs on one GPU (qgd_pcg_solve_stepwise, used to
 // validate the kernels against the oracle before any communication is involved).
 //
-// STATUS: written at the end of round 1 after the GPU budget was spent - compiled for sm_100a, never run on a device yet;
-// not used by any solver path (multi-GPU QHDFoam / implicit QGDFoam are still refused by their create calls).
+// Used by QHDFoam (pressure) and the implicit branch of QGDFoam (U, e) on extended sub-meshes; preconditioner none | diagonal |
+// block-local DIC (launchDicBlocks, qgd_pcg.cu).  Parity with the oracle: 1 GPU (tests/test_gpu_extra.py), 2 and 8 GPUs
+// (tests/multi_gpu_pcg_worker.py, multi_gpu_qhd_worker.py, multi_gpu_worker.py implicit cases).
 #include <algorithm>
 
 #include "qgd_pcg.cuh"
