@@ -41,10 +41,13 @@ class QGDParams(C.Structure):
                 ("diffTol", C.c_double), ("diffRelTol", C.c_double), ("diffMaxIter", C.c_int), ("diffPrecond", C.c_int),
                 ("varScCSc1", C.c_double), ("varScMinSc", C.c_double), ("varScMaxSc", C.c_double),
                 ("transportModel", C.c_int), ("mu0", C.c_double), ("T0", C.c_double), ("kExp", C.c_double),
-                ("As", C.c_double), ("Ts", C.c_double), ("thermoModel", C.c_int), ("Cv", C.c_double), ("Esref", C.c_double)]
+                ("As", C.c_double), ("Ts", C.c_double), ("thermoModel", C.c_int), ("Cv", C.c_double), ("Esref", C.c_double),
+                ("varSc5SmoothCoeff", C.c_double), ("varSc5RC", C.c_double), ("varSc5BadQualitySc", C.c_double),
+                ("varSc5MaxAspectRatio", C.c_double)]
 
 
-QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2, "varScModel6": 6, "varScModel7": 7}
+QGD_MODELS = {"constScPrModel1": 0, "constScPrModel1n": 1, "constScPrModel2": 2, "varScModel5": 5, "varScModel6": 6,
+              "varScModel7": 7}
 
 
 class QHDParams(C.Structure):
@@ -90,6 +93,9 @@ def lib():
                                   _dp, _dp, _dp, _dp, C.c_double]
         L.or_qgd_set_const_sc_cells.argtypes = [C.c_void_p, _ip, C.c_int]
         L.or_qgd_set_sources.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.or_fvc_smooth.restype = C.c_int
+        L.or_fvc_smooth.argtypes = [C.c_void_p, _dp, C.c_double]
+        L.or_varsc5_cell_quality.argtypes = [C.c_void_p, C.c_double, C.c_double, _dp, _dp]
         L.or_qgd_step.restype = C.c_double
         L.or_qgd_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
         L.or_qgd_deltaT.restype = C.c_double
@@ -225,6 +231,18 @@ class Oracle:
         f = [_f64(x) for x in (bvU, bvT, bvP, U0, T0, p0, alphaQGD)]
         lib().or_qgd_init(self._h, C.byref(params), scheme, _i(a[0]), _i(a[1]), _i(a[2]),
                           *[_d(x) for x in f], deltaT)
+
+    def fvc_smooth(self, field, coeff):
+        """[OF-v2312] fvc::smooth(field, coeff) as varScModel5.C:232 uses it; returns (smoothed field, FaceCellWave iterations)"""
+        f = np.array(field, dtype=np.float64, copy=True)
+        it = lib().or_fvc_smooth(self._h, _d(f), float(coeff))
+        return f, it
+
+    def varsc5_cell_quality(self, bad_quality_sc=0.05, max_aspect_ratio=1.5):
+        """varScModel5.C:112-132: (cqSc, aspectRatio) per cell"""
+        q, ar = np.zeros(self.mesh.n_cells), np.zeros(self.mesh.n_cells)
+        lib().or_varsc5_cell_quality(self._h, bad_quality_sc, max_aspect_ratio, _d(q), _d(ar))
+        return q, ar
 
     def qgd_set_sources(self, suRho=None, suU=None, suE=None):
         a = [_f64(x) for x in (suRho, suU, suE)]

@@ -90,7 +90,8 @@ struct or_ctx {
     Vec rhoU, rhoUB, rhoE, rhoEB, H, HB;
     Vec aQGD, aQGDB, tauQGD, tauQGDB, muQGD, muQGDB, alphauQGD, alphauQGDB, ScQGD, ScQGDB, PrQGD, PrQGDB, hQGDB;
     Vec pGrad;                  // qgdFlux gradient per bface
-    IVec constScCells;          // varScModel7 constScCellSet
+    IVec constScCells;          // varScModel7 / varScModel5 constScCellSet
+    Vec cqSc;                   // varScModel5: mesh-quality floor of ScQGD (varScModel5.C:112-132)
     IVec pcgBlocks;             // processor of each cell for the linear solvers of a decomposed run (empty = serial)
     IVec lsForcedDeg;           // faceSet degenerateStencilFaces (leastSquaresStencil.C:63-132): internal faces forced to nf*snGrad
     Vec suRho, suU, suE;        // explicit source matrices rhoSu / rhoUSu / rhoESu: volume-integrated source per cell (empty = zero)
@@ -818,6 +819,153 @@ void varScCorrect(or_ctx& s)
     }
 }
 
+// ---- [OF-v2312] primitiveMeshTools::cellClosedness, the aspect-ratio part (restated from the OpenFOAM source as remembered;
+// unverified like every [OF] item): per cell the sums of |Sf| components over all its faces; aspect ratio = max/min of the
+// sums over the solved directions, in 3D also at least (1/6) sum(|Sf| components) / V^(2/3) (1 for a cube)
+void cellAspectRatio(const or_ctx& m, Vec& aratio)
+{
+    Vec sumMag(3 * (size_t)m.nCells, 0.0);
+    for (int f = 0; f < m.nFaces; ++f)                       // forAll(own, facei): every face adds to its owner
+        for (int d = 0; d < 3; ++d) sumMag[3 * (size_t)m.owner[f] + d] += std::fabs(m.Sf[3 * (size_t)f + d]);
+    for (int f = 0; f < m.nInternal; ++f)                    // forAll(nei, facei)
+        for (int d = 0; d < 3; ++d) sumMag[3 * (size_t)m.neighbour[f] + d] += std::fabs(m.Sf[3 * (size_t)f + d]);
+    const double ROOTVSMALL = 1.0e-150, VGREAT = 1.0e+300;
+    aratio.assign(m.nCells, 1.0);
+    for (int c = 0; c < m.nCells; ++c) {
+        double minC = VGREAT, maxC = -VGREAT;
+        for (int d = 0; d < 3; ++d)
+            if (m.gD[d] == 1) { minC = std::min(minC, sumMag[3 * (size_t)c + d]); maxC = std::max(maxC, sumMag[3 * (size_t)c + d]); }
+        double ar = maxC / (minC + ROOTVSMALL);
+        if (m.nD == 3) {
+            const double v = std::max(ROOTVSMALL, m.V[c]);
+            ar = std::max(ar, 1.0 / 6.0 * (sumMag[3 * (size_t)c] + sumMag[3 * (size_t)c + 1] + sumMag[3 * (size_t)c + 2]) / std::pow(v, 2.0 / 3.0));
+        }
+        aratio[c] = ar;
+    }
+}
+
+// varScModel5.C:112-132 : cqSc = badQualitySc * aspectRatio / maxAspectRatio where aspectRatio > maxAspectRatio, else 0
+void varSc5CellQuality(const or_ctx& m, double badQualitySc, double thr, Vec& cqSc, Vec* aratioOut = nullptr)
+{
+    Vec ar;
+    cellAspectRatio(m, ar);
+    cqSc.assign(m.nCells, 0.0);
+    for (int c = 0; c < m.nCells; ++c)
+        if (ar[c] > thr) cqSc[c] = badQualitySc * ar[c] / thr;
+    if (aratioOut) *aratioOut = ar;
+}
+
+// ---- [OF-v2312] fvc::smooth(field, coeff)  (finiteVolume/fvc/fvcSmooth/smooth.C + smoothData + FaceCellWave), restated
+// sequentially in the reference's visiting order, because the result depends on it inside the 1 % propagation tolerance:
+//   * initial changed faces: internal faces, ascending, whose two cell values differ by more than maxRatio = 1 + coeff; the
+//     face carries the larger value (no coupled patches on a serial mesh);
+//   * faceToCell: the changed faces in list order, owner then neighbour; a cell that differs from the face value takes
+//     smoothData::updateCell = update(scale = maxRatio): an unset / ~zero cell copies the face value, otherwise the cell is
+//     raised to faceValue/maxRatio when faceValue > (1 + tol) maxRatio cellValue (tol = FaceCellWave::propagationTol_ = 0.01);
+//     a cell enters the changed-cell list the first time it changes;
+//   * cellToFace: the changed cells in list order, their faces in mesh.cells() order (owned faces ascending, then the faces
+//     the cell is the neighbour of); smoothData::updateFace = update(scale = 1); boundary faces take part (they receive the
+//     owner's value and later offer it back, which can never raise the owner, so they only lengthen the lists);
+//   * until a sweep changes nothing.  Returns the number of completed iterations.
+int fvcSmooth(const or_ctx& m, double* field, double coeff)
+{
+    const double maxRatio = 1.0 + coeff, tol = 0.01, SMALL_ = 1.0e-15, VSMALL_ = 1.0e-300, GREAT_ = 1.0e+15;
+    const int nC = m.nCells, nF = m.nFaces, nI = m.nInternal;
+    std::vector<double> cellV(field, field + nC), faceV(nF, -GREAT_);          // smoothData() : value_(-GREAT)
+    auto valid = [&](double v) { return v > -SMALL_; };
+    auto update = [&](double& mine, double other, double scale) {            // smoothDataI.H update()
+        if (!valid(mine) || mine < VSMALL_) { mine = other; return true; }
+        if (other > (1 + tol) * scale * mine) { mine = other / scale; return true; }
+        return false;
+    };
+    std::vector<int> chF, chC;
+    std::vector<char> inF(nF, 0), inC(nC, 0);
+    for (int f = 0; f < nI; ++f) {                                             // smooth.C: initial field on faces
+        const int own = m.owner[f], nbr = m.neighbour[f];
+        double v;
+        if (field[own] > maxRatio * field[nbr]) v = field[own];
+        else if (field[nbr] > maxRatio * field[own]) v = field[nbr];
+        else continue;
+        faceV[f] = v; inF[f] = 1; chF.push_back(f);                            // FaceCellWave::setFaceInfo
+    }
+    // mesh.cells()[c]: owned faces ascending, then neighbour-side faces ascending [OF-v2312 primitiveMesh::calcCells]
+    auto forCellFaces = [&](int c, auto fn) {
+        for (int q = m.cfOff[c]; q < m.cfOff[c + 1]; ++q) if (m.owner[m.cfFace[q]] == c) fn(m.cfFace[q]);
+        for (int q = m.cfOff[c]; q < m.cfOff[c + 1]; ++q) if (m.owner[m.cfFace[q]] != c) fn(m.cfFace[q]);
+    };
+    int iter = 0;
+    while (true) {
+        // faceToCell
+        for (int f : chF) {
+            const double fv = faceV[f];
+            const int cells[2] = {m.owner[f], f < nI ? m.neighbour[f] : -1};
+            for (int c : cells) {
+                if (c < 0) continue;
+                if (cellV[c] == fv) continue;                                  // !currInfo.equal(newInfo)
+                if (update(cellV[c], fv, maxRatio) && !inC[c]) { inC[c] = 1; chC.push_back(c); }
+            }
+            inF[f] = 0;
+        }
+        chF.clear();
+        if (chC.empty()) break;
+        // cellToFace
+        for (int c : chC) {
+            const double cv = cellV[c];
+            forCellFaces(c, [&](int f) {
+                if (faceV[f] == cv) return;
+                if (update(faceV[f], cv, 1.0) && !inF[f]) { inF[f] = 1; chF.push_back(f); }
+            });
+            inC[c] = 0;
+        }
+        chC.clear();
+        if (chF.empty()) break;
+        ++iter;
+    }
+    std::copy(cellV.begin(), cellV.end(), field);
+    return iter;
+}
+
+void gaussGradCells(const or_ctx& s, int k, const double* phif, double* out);
+// varScModel5::correct varScModel5.C:197-232 : the density-gradient sensor, relaxed against the previous ScQGD, clamped, floored
+// by the mesh-quality value, then smoothed with fvc::smooth.  rho = qgdThermo.rho() = psi*p [OF-v2312 psiThermo::rho] with the
+// psi just computed and the pressure of the old step (thermo.correct() runs before p = rho/psi, QGDFoam.C:149-154), boundary
+// values psi_b*p_b.  fvc::grad(rho) [OF-v2312 Gauss linear]: cell values (1/V) sum_f Sf rho_f; boundary values (they enter the
+// boundary ScQGD) gaussGrad::correctBoundaryConditions: g_P + n (snGrad_b - n.g_P) with the snGrad of a calculated patch,
+// deltaCoeffs (rho_b - rho_P).  ScQGD is a calculated-patch field (QGDCoeffs.C:249-261): its boundary values follow the same
+// algebra and the clamps; cqSc, the cell set and fvc::smooth act on the cells only (varScModel5.C:219-232).
+void varSc5Correct(or_ctx& s)
+{
+    const int nC = s.nCells, nB = s.nBnd;
+    const double rC = s.prm.varSc5RC;
+    Vec rho(nC), rhoB(nB, 0.0), rhof(s.nFaces), g(3 * (size_t)nC), gB(3 * (size_t)nB, 0.0);
+    for (int c = 0; c < nC; ++c) rho[c] = s.p[c] * s.psi[c];                               // :202
+    for (int b = 0; b < nB; ++b) if (!patchIsEmpty(s, b)) rhoB[b] = s.pB[b] * s.psiB[b];
+    linearInterpolate(s, 1, rho.data(), rhoB.data(), nullptr, rhof.data());
+    gaussGradCells(s, 1, rhof.data(), g.data());
+    for (int b = 0; b < nB; ++b) {
+        if (patchIsEmpty(s, b)) continue;
+        const int f = s.nInternal + b, P = s.owner[f];
+        const double* n = &s.nf[3 * (size_t)f];
+        const double sn = s.dC[f] * (rhoB[b] - rho[P]);
+        const double nG = n[0] * g[3 * (size_t)P] + n[1] * g[3 * (size_t)P + 1] + n[2] * g[3 * (size_t)P + 2];
+        for (int i = 0; i < 3; ++i) gB[3 * (size_t)b + i] = g[3 * (size_t)P + i] + n[i] * (sn - nG);
+    }
+    for (int c = 0; c < nC; ++c) {                                                         // :209-212
+        const double mg = std::sqrt(g[3 * (size_t)c] * g[3 * (size_t)c] + g[3 * (size_t)c + 1] * g[3 * (size_t)c + 1] + g[3 * (size_t)c + 2] * g[3 * (size_t)c + 2]);
+        s.ScQGD[c] = rC * (mg * s.hQGD[c] / rho[c]) + (1.0 - rC) * s.ScQGD[c];
+    }
+    for (int b = 0; b < nB; ++b) {
+        if (patchIsEmpty(s, b)) continue;
+        const double mg = std::sqrt(gB[3 * (size_t)b] * gB[3 * (size_t)b] + gB[3 * (size_t)b + 1] * gB[3 * (size_t)b + 1] + gB[3 * (size_t)b + 2] * gB[3 * (size_t)b + 2]);
+        s.ScQGDB[b] = rC * (mg * s.hQGDB[b] / rhoB[b]) + (1.0 - rC) * s.ScQGDB[b];
+    }
+    for (double& v : s.ScQGD) v = std::min(std::max(v, s.prm.varScMinSc), s.prm.varScMaxSc);          // :214-217
+    for (int b = 0; b < nB; ++b) if (!patchIsEmpty(s, b)) s.ScQGDB[b] = std::min(std::max(s.ScQGDB[b], s.prm.varScMinSc), s.prm.varScMaxSc);
+    for (int c = 0; c < nC; ++c) s.ScQGD[c] = std::max(s.ScQGD[c], s.cqSc[c]);             // :219-220
+    for (int c : s.constScCells) s.ScQGD[c] = s.prm.ScQGD;                                 // :222-230, constSc_ = ScQGD :137
+    fvcSmooth(s, s.ScQGD.data(), s.prm.varSc5SmoothCoeff);                                 // :232 (calculated patches: boundary unchanged)
+}
+
 // hePsiQGDThermo::calculate  hePsiQGDThermo.C:37-126 ; constScPrModel1::correct constScPrModel1.C:97-131 ;
 // QGDThermo::correctQGD QGDThermo.C:84-111
 void thermoCorrect(or_ctx& s)
@@ -860,7 +1008,15 @@ void thermoCorrect(or_ctx& s)
             }
             linearInterpolate(s, 1, s.tauQGD.data(), s.tauQGDB.data(), nullptr, s.tauQGDf.data());
         } else {
-            if (model == 1) {                                                              // constScPrModel1n.C:104-105
+            if (model == 5) {                                                              // varScModel5.C:204-205
+                Vec af(s.nFaces), cf(s.nFaces);
+                linearInterpolate(s, 1, s.aQGD.data(), s.aQGDB.data(), nullptr, af.data());
+                linearInterpolate(s, 1, s.c.data(), s.cB.data(), nullptr, cf.data());
+                for (int f = 0; f < s.nFaces; ++f) {
+                    if (f >= s.nInternal && patchIsEmpty(s, f - s.nInternal)) { s.tauQGDf[f] = 0.0; continue; }
+                    s.tauQGDf[f] = af[f] / cf[f] * s.hQGDf[f];
+                }
+            } else if (model == 1) {                                                       // constScPrModel1n.C:104-105
                 Vec af(s.nFaces), cf(s.nFaces);
                 linearInterpolate(s, 1, s.aQGD.data(), s.aQGDB.data(), nullptr, af.data());
                 linearInterpolate(s, 1, s.c.data(), s.cB.data(), nullptr, cf.data());
@@ -880,6 +1036,7 @@ void thermoCorrect(or_ctx& s)
             for (int b = 0; b < s.nBnd; ++b) if (!patchIsEmpty(s, b)) s.tauQGDB[b] = s.aQGDB[b] * s.hQGDB[b] / s.cB[b];
         }
         if (model == 6 || model == 7) varScCorrect(s);
+        if (model == 5) varSc5Correct(s);
 #pragma omp parallel for num_threads(s.nThreads) schedule(static)
         for (int c = 0; c < s.nCells; ++c) {
             s.muQGD[c] = s.p[c] * s.ScQGD[c] * s.tauQGD[c];                                // :108-111
@@ -1172,6 +1329,7 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
     s.aQGDB.assign(nB, 0.0); s.hQGDB.assign(nB, 0.0);
     for (int b = 0; b < nB; ++b) { s.aQGDB[b] = s.aQGD[s.owner[s.nInternal + b]]; s.hQGDB[b] = s.hQGDf[s.nInternal + b]; }   // QGDCoeffs.C:373
     s.ScQGD.assign(nC, prm->ScQGD); s.ScQGDB.assign(nB, prm->ScQGD); s.PrQGD.assign(nC, prm->PrQGD); s.PrQGDB.assign(nB, prm->PrQGD);
+    if (prm->qgdModel == 5) varSc5CellQuality(s, prm->varSc5BadQualitySc, prm->varSc5MaxAspectRatio, s.cqSc);   // varScModel5.C:112-132
     for (Vec* v : {&s.tauQGDf, &s.rhof, &s.pf, &s.cf, &s.gammaf, &s.Hf, &s.alphauf, &s.muf, &s.divUf, &s.phiw, &s.phiJm, &s.phi,
                    &s.phiJmH, &s.phiQ, &s.phiPiU, &s.phiSigmaDotU}) z(*v, nF);
     for (Vec* v : {&s.Uf, &s.rhoUf, &s.gradef, &s.gradRhof, &s.gradPf, &s.rhoW, &s.jm, &s.phiJmU, &s.phiP, &s.phiPi, &s.qf}) z(*v, 3 * (size_t)nF);
@@ -1216,6 +1374,14 @@ void or_qgd_init(or_ctx* sp, const or_qgd_params_t* prm, int fvscScheme, const i
 }
 
 double or_qgd_deltaT(or_ctx* s) { return s->deltaT; }
+int or_fvc_smooth(or_ctx* s, double* field, double coeff) { return fvcSmooth(*s, field, coeff); }
+void or_varsc5_cell_quality(or_ctx* s, double badQualitySc, double maxAspectRatio, double* cqSc, double* aspectRatio)
+{
+    Vec q, ar;
+    varSc5CellQuality(*s, badQualitySc, maxAspectRatio, q, &ar);
+    std::copy(q.begin(), q.end(), cqSc);
+    if (aspectRatio) std::copy(ar.begin(), ar.end(), aspectRatio);
+}
 void or_qgd_set_const_sc_cells(or_ctx* s, const int* cells, int n) { s->constScCells.assign(cells, cells + n); }
 void or_set_degenerate_faces(or_ctx* s, const int* faces, int n) { s->lsForcedDeg.assign(faces, faces + n); s->lsBuilt = false; }
 void or_set_pcg_blocks(or_ctx* s, const int* cellBlock) { if (cellBlock) s->pcgBlocks.assign(cellBlock, cellBlock + s->nCells); else s->pcgBlocks.clear(); }

@@ -64,7 +64,7 @@ typedef struct {
     int alphaEffGammaFactor;   // heThermo::alphaEff multiplies by gamma for internal energy [OF-v2312]
     int energyDdtRhoEQuirk;    // 1: QGDEEqn.H:67-72 as in the doc snapshot, fvm::ddt(rho,e) - fvc::ddt(rhoE)
                                // 0: fvm::ddt(rho,e) - fvc::ddt(rho,e)  (e keeps rhoE/rho - K)
-    int qgdModel;              // 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2, 6 varScModel6, 7 varScModel7
+    int qgdModel;              // 0 constScPrModel1, 1 constScPrModel1n, 2 constScPrModel2, 5 varScModel5, 6 varScModel6, 7 varScModel7
     // implicitDiffusion branch (QGDUEqn.H:54-75, QGDEEqn.H:53-64): fvSolution controls of the U and e solvers (PCG)
     double diffTol, diffRelTol;
     int diffMaxIter, diffPrecond;
@@ -79,6 +79,9 @@ typedef struct {
     // thermo model: 0 hConst (Cp, Hf, Tref, Hsref above), 1 eConst  Es = Cv (T - Tref) + Esref, Cp = Cv + R [OF-v2312 eConstThermoI.H]
     int thermoModel;
     double Cv, Esref;
+    // varScModel5 dictionary entries (varScModel5.C:61-110; qgdModel 5): smoothCoeff (0.1), rC (0.5), badQualitySc (0.05),
+    // maxAspectRatio (1.5); its minSc (0.05) / maxSc (1.0) travel in varScMinSc / varScMaxSc above
+    double varSc5SmoothCoeff, varSc5RC, varSc5BadQualitySc, varSc5MaxAspectRatio;
 } or_qgd_params_t;
 
 typedef struct or_ctx or_ctx;
@@ -104,6 +107,11 @@ void or_linear_interpolate(or_ctx*, int ncmpt, const double* cell, const double*
 // varScModel7 "constScCellSet" (varScModel7.C:143-158,246-254): cells whose ScQGD is reset to the dictionary ScQGD each step.
 // Call before or_qgd_init.
 void or_qgd_set_const_sc_cells(or_ctx*, const int* cells, int n);
+// [OF-v2312] fvc::smooth(field, coeff) (fvcSmooth/smooth.C: FaceCellWave<smoothData>) on a cell field, as varScModel5.C:232
+// applies it to ScQGD; returns the number of FaceCellWave iterations.  Serial meshes only (no coupled patches).
+int or_fvc_smooth(or_ctx*, double* field /*nCells, in/out*/, double coeff);
+// varScModel5.C:112-132: the per-cell quality floor cqSc from primitiveMeshTools::cellClosedness [OF-v2312]; aspectRatio may be NULL
+void or_varsc5_cell_quality(or_ctx*, double badQualitySc, double maxAspectRatio, double* cqSc /*nCells*/, double* aspectRatio);
 // Explicit source matrices of QGDRhoEqn.H:46 / QGDUEqn.H:62,85 / QGDEEqn.H:60,71 (rhoSu, rhoUSu, rhoESu; zero in QGDFoam,
 // createZeroSources.H:28-44; the Lagrangian cloud's Srho/SU/Sh in particlesQGDFoam): the volume-integrated explicit
 // source of each cell, i.e. minus the fvMatrix::source() of the matrix on the right-hand side.  suRho, suE: nCells,

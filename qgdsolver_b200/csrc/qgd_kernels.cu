@@ -1772,10 +1772,10 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         hooks->waitHalo(st);
         if (forked) hooks->waitHalo(sb);
     }
-    if (fv.nB && anyQgdFlux) {
-        k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+    if (anyQgdFlux) {                // a global decision (patch table): the exchange in midStep is matched by every neighbour rank,
+        if (fv.nB) { k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }      // also by one that holds no boundary face
         if (hooks && hooks->midStep) hooks->midStep();
-        if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
+        if (fv.nB && pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
     }
     if (fv.nB) { k_bnd_flux<<<nblk(fv.nB), kBlock, 0, sb>>>(c, fv, sv, bs); ++n; }
     if (forked) {
@@ -1837,10 +1837,10 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
             ++n;
             if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 0); ++n; }
         }
-        if (fv.nB && anyQgdFlux) {
-            k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+        if (anyQgdFlux) {            // global decision, see launchStep
+            if (fv.nB) { k_bnd_pre<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
             if (hooks && hooks->midStep) hooks->midStep();
-            if (pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
+            if (fv.nB && pointsNeeded && sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, st>>>(sv, bs, 1); ++n; }
         }
         k_gauss_gradU<<<nblk(sv.nCells), kBlock, 0, st>>>(fv, sv, bs, iv.GU0, 0); ++n;
         if (hooks && hooks->afterGrad) hooks->afterGrad(iv.GU0);

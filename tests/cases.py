@@ -22,6 +22,8 @@ class Case:
         self.e_const = None             # dict(Cv, Esref): eConst thermo instead of hConst [OF-v2312]
         # varScModel7 dictionary entries (cSc1, minSc, maxSc) and the constScCellSet cell list
         self.varsc = dict(cSc1=1.0, minSc=-1.0, maxSc=-1.0, const_sc_cells=None)
+        if model == "varScModel5":      # dictionary defaults of varScModel5.C:61-66
+            self.varsc.update(minSc=0.05, maxSc=1.0, smoothCoeff=0.1, rC=0.5, badQualitySc=0.05, maxAspectRatio=1.5)
         self.varsc.update(varsc or {})
         self.diff_solver = dict(tol=1e-14, rel_tol=0.0, max_iter=2000, precond="DIC")
         self.diff_solver.update(diff_solver or {})
@@ -44,6 +46,10 @@ class Case:
                           alphaEffGammaFactor=int(self.opts["alpha_eff_gamma_factor"]),
                           energyDdtRhoEQuirk=int(self.opts["energy_ddt_rhoE_quirk"]), qgdModel=O.QGD_MODELS[self.model],
                           varScCSc1=self.varsc["cSc1"], varScMinSc=self.varsc["minSc"], varScMaxSc=self.varsc["maxSc"])
+        if self.model == "varScModel5":
+            v = self.varsc
+            prm.varSc5SmoothCoeff, prm.varSc5RC = v["smoothCoeff"], v["rC"]
+            prm.varSc5BadQualitySc, prm.varSc5MaxAspectRatio = v["badQualitySc"], v["maxAspectRatio"]
         if self.power_law:
             prm.transportModel, prm.mu0, prm.T0, prm.kExp = 1, self.power_law["mu0"], self.power_law["T0"], self.power_law["k"]
         if self.sutherland:
