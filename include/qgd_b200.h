@@ -142,7 +142,8 @@ int qgd_fvsc_div(qgd_fvsc* op, int ncmpt, const double* cell, const double* bnd,
  * fvSchemes::fvsc, controlDict (QGDCourantNo.H:36, setDeltaT-QGDQHD.H:41-58). */
 typedef struct {
     const char* fvsc_scheme;        /* fvSchemes::fvsc::default                                     */
-    const char* qgd_coeffs_model;   /* QGD::QGDCoeffs : "constScPrModel1"                           */
+    const char* qgd_coeffs_model;   /* QGD::QGDCoeffs : "constScPrModel1" | "constScPrModel1n" | "constScPrModel2" |
+                                       "varScModel5" | "varScModel6" | "varScModel7"                */
     double R;                       /* perfectGas: R = 8314.47/W                                    */
     double Cp, Hf, Tref, Hsref;     /* hConst                                                       */
     double mu, Pr;                  /* constTransport                                               */
@@ -171,12 +172,19 @@ typedef struct {
     double mu0, T0, k_exp;
     const char* thermo_model;
     double Cv, Esref;
+    /* QGD sub-dictionary entries of varScModel5 (varScModel5.C:61-110), read only when qgd_coeffs_model is "varScModel5":
+     * smoothCoeff (0.1), rC (0.5), badQualitySc (0.05), maxAspectRatio (1.5); its minSc (0.05) / maxSc (1.0) travel in
+     * varsc_minSc / varsc_maxSc above.  The shim passes the dictionary value or the default given in brackets.
+     * varScModel5 on the device: explicit branch, serial mesh; ScQGD = rC |grad(psi p)| hQGD / (psi p) + (1 - rC) ScQGD, clamped,
+     * floored by the cellClosedness aspect-ratio value, smoothed with fvc::smooth (FaceCellWave, reference visiting order). */
+    double varsc5_smoothCoeff, varsc5_rC, varsc5_badQualitySc, varsc5_maxAspectRatio;
 } qgd_qgdfoam_desc;
 
 int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* desc, qgd_solver** out);
 int qgd_qgdfoam_destroy(qgd_solver* s);
-/* varScModel7 "constScCellSet" (varScModel7.C:143-158,246-254): polyMesh cell ids whose ScQGD is reset to the
- * dictionary ScQGD after every sensor evaluation.  Call before qgd_qgdfoam_init_fields.  n = 0 clears the set. */
+/* varScModel7 / varScModel5 "constScCellSet" (varScModel7.C:143-158,246-254; varScModel5.C:134-149,222-230): polyMesh cell
+ * ids whose ScQGD is reset to the dictionary ScQGD after every sensor evaluation (model 5: before the smoothing).  Call
+ * before qgd_qgdfoam_init_fields.  n = 0 clears the set. */
 int qgd_qgdfoam_set_const_sc_cells(qgd_solver* s, const int* cells, int n);
 /* Explicit source matrices of the conservative equations: rhoSu (QGDRhoEqn.H:46), rhoUSu (QGDUEqn.H:62,85), rhoESu
  * (QGDEEqn.H:60,71).  QGDFoam builds them as zero matrices (createZeroSources.H:28-44); particlesQGDFoam fills them

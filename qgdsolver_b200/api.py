@@ -72,7 +72,9 @@ class QGDFoamDesc(C.Structure):
                 ("varsc_cSc1", C.c_double), ("varsc_minSc", C.c_double), ("varsc_maxSc", C.c_double),
                 ("transport_model", C.c_char_p), ("As", C.c_double), ("Ts", C.c_double),
                 ("mu0", C.c_double), ("T0", C.c_double), ("k_exp", C.c_double),
-                ("thermo_model", C.c_char_p), ("Cv", C.c_double), ("Esref", C.c_double)]
+                ("thermo_model", C.c_char_p), ("Cv", C.c_double), ("Esref", C.c_double),
+                ("varsc5_smoothCoeff", C.c_double), ("varsc5_rC", C.c_double), ("varsc5_badQualitySc", C.c_double),
+                ("varsc5_maxAspectRatio", C.c_double)]
 
 
 class QHDFoamDesc(C.Structure):
@@ -332,10 +334,18 @@ class QGDFoam:
                  fvsc_scheme="GaussVolPoint", qgd_coeffs="constScPrModel1", implicit_diffusion=False,
                  alpha_eff_gamma_factor=True, energy_ddt_rhoE_quirk=True, adjust_time_step=False, max_co=0.3,
                  max_delta_t=1e30, c_tau=0.75, delta_t=1e-4, diff_tol=1e-9, diff_rel_tol=0.0, diff_max_iter=1000,
-                 diff_precond="DIC", varsc_cSc1=1.0, varsc_minSc=-1.0, varsc_maxSc=-1.0,
-                 transport="const", As=0.0, Ts=0.0, mu0=0.0, T0=1.0, k_exp=0.0, thermo="hConst", Cv=0.0, Esref=0.0):
+                 diff_precond="DIC", varsc_cSc1=1.0, varsc_minSc=None, varsc_maxSc=None,
+                 transport="const", As=0.0, Ts=0.0, mu0=0.0, T0=1.0, k_exp=0.0, thermo="hConst", Cv=0.0, Esref=0.0,
+                 varsc5_smoothCoeff=0.1, varsc5_rC=0.5, varsc5_badQualitySc=0.05, varsc5_maxAspectRatio=1.5):
         self.mesh = mesh
         d = QGDFoamDesc()
+        # dictionary defaults: varScModel7.C:96-119 (-1 = off), varScModel5.C:63-64 (0.05 / 1.0)
+        if varsc_minSc is None:
+            varsc_minSc = 0.05 if qgd_coeffs == "varScModel5" else -1.0
+        if varsc_maxSc is None:
+            varsc_maxSc = 1.0 if qgd_coeffs == "varScModel5" else -1.0
+        d.varsc5_smoothCoeff, d.varsc5_rC = varsc5_smoothCoeff, varsc5_rC
+        d.varsc5_badQualitySc, d.varsc5_maxAspectRatio = varsc5_badQualitySc, varsc5_maxAspectRatio
         self._thermo_names = (transport.encode(), thermo.encode())
         d.transport_model, d.thermo_model = self._thermo_names
         d.As, d.Ts, d.mu0, d.T0, d.k_exp, d.Cv, d.Esref = As, Ts, mu0, T0, k_exp, Cv, Esref
@@ -358,7 +368,7 @@ class QGDFoam:
         _check(load_library().qgd_qgdfoam_set_sources(self._h, _d(a[0]), _d(a[1]), _d(a[2])))
 
     def set_const_sc_cells(self, cells):
-        """varScModel7 constScCellSet (varScModel7.C:143-158); call before init_fields."""
+        """varScModel7 / varScModel5 constScCellSet (varScModel7.C:143-158, varScModel5.C:134-149); call before init_fields."""
         c = np.ascontiguousarray(cells, np.int32)
         _check(load_library().qgd_qgdfoam_set_const_sc_cells(self._h, _i(c), int(c.size)))
 

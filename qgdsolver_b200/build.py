@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqgd_b200.so")
-SOURCES = ["qgd_kernels.cu", "qgd_pcg.cu", "qgd_mpcg.cu", "qgd_qhd.cu", "qgd_abi.cu", "qgd_host_setup.cpp"]
+SOURCES = ["qgd_kernels.cu", "qgd_pcg.cu", "qgd_mpcg.cu", "qgd_qhd.cu", "qgd_varsc5.cu", "qgd_abi.cu", "qgd_host_setup.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3", "-shared", "-cudart", "shared"]

@@ -11,6 +11,7 @@
 
 #include "qgd_kernels.cuh"
 #include "qgd_pcg.cuh"
+#include "qgd_varsc5_dev.h"
 
 namespace qgd {
 
@@ -109,7 +110,12 @@ struct qgd_solver {
     DevBuf<RecB> bB;
     DevBuf<double> S, P;    // cell state 16 x nCells, point values 6 x nPoints (SoA)
     DevBuf<double> aQGD, Fflux, psiB, pGrad, pNew, phiw, bvU, bvT, bvP, stage, tauOut, tauOutB, scVar;
-    DevBuf<unsigned char> scConst;   // varScModel7 constScCellSet mask
+    DevBuf<unsigned char> scConst;   // varScModel7 / varScModel5 constScCellSet mask
+    std::unique_ptr<VarSc5Device> v5; // varScModel5: its own pass after every step (qgd_varsc5.h); scVar holds its ScQGD
+    VarSc5View v5view()
+    {
+        return v5->view(S.p, bA.p, bB.p, psiB.p, aQGD.p, mesh->V.p, mesh->hQGD.p, scVar.p, scConst.n ? scConst.p : nullptr);
+    }
     DevBuf<double> su;               // [5][nCells] explicit sources (qgd_qgdfoam_set_sources) or empty
     int stepsDone = 0;
     // implicit-diffusion branch
@@ -591,6 +597,24 @@ void runStepsImplicit(qgd_solver* s, int n)
 
 static int h_nB(const qgd_solver* s) { return s->mesh->h.nBnd; }
 
+// varScModel5 at start-up: QGDCoeffs::correct runs twice before the first step - in the thermo constructor
+// (hePsiQGDThermo ctor -> calculate()) and in thermo.correct() (QGDFoam/createFields.H:8) - each time relaxing ScQGD from the
+// dictionary value towards the sensor and smoothing it.  p is the field as read, p_b the boundary value k_init_bnd left in pNew.
+static void varSc5Init(qgd_solver* s)
+{
+    const HostMesh& h = s->mesh->h;
+    VarSc5Device& m = *s->v5;
+    std::vector<double> sc0(h.nCells, s->desc.ScQGD), scb(h.nBnd + 1, s->desc.ScQGD);     // varScModel5.C:76-80
+    QGD_CUDA(cudaMemcpyAsync(s->scVar.p, sc0.data(), (size_t)h.nCells * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    QGD_CUDA(cudaMemcpyAsync(m.ScB.p, scb.data(), scb.size() * sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    QGD_CUDA(cudaMemcpyAsync(m.pOld.p, s->S.p + 5 * (size_t)h.nCells, (size_t)h.nCells * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    if (h.nBnd) QGD_CUDA(cudaMemcpyAsync(m.pOldB.p, s->pNew.p, (size_t)h.nBnd * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+    QGD_CUDA(cudaStreamSynchronize(g_stream));          // sc0 / scb are host temporaries
+    const VarSc5View v = s->v5view();
+    s->launches += m.correct(v, g_stream);
+    s->launches += m.correct(v, g_stream);
+}
+
 void runSteps(qgd_solver* s, int n)
 {
     if (s->k.implicit) {
@@ -603,6 +627,12 @@ void runSteps(qgd_solver* s, int n)
     const BndState bs = s->bview();
     StepHooks hooks;
     const bool multi = s->halo.active && g_nranks > 1;
+    const bool model5 = (bool)s->v5;
+    if (model5)        // varScModel5 reads the p_b the closing correctBoundaryConditions() is about to replace (varScModel5.C:255-263)
+        hooks.beforeBndPost = [s] {
+            if (s->mesh->h.nBnd)
+                QGD_CUDA(cudaMemcpyAsync(s->v5->pOldB.p, s->pNew.p, (size_t)s->mesh->h.nBnd * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+        };
     if (multi) {
         hooks.midStep = [s] { s->launches += haloExchangeMid(s); };
         if (s->desc.adjust_time_step)
@@ -626,7 +656,8 @@ void runSteps(qgd_solver* s, int n)
     StepFork fork{g_sideStream, g_evFork[0], g_evFork[1], g_evFork[2], g_evFork[3], g_evFork[4], !multi};
     // measured on one B200: neutral at 256^3 (the boundary chain's time moves into k_points), -3 % per step at 128^3; multi-GPU: opt-in
     // (QGD_BND_FORK=2) until measured - there the side stream can only start after the halo wait
-    const bool useFork = (multi ? g_bndFork == 2 : g_bndFork != 0) && g_sideStream && h_nB(s) > 0 && !s->anyQgdFlux && !(s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc);
+    const bool useFork = (multi ? g_bndFork == 2 : g_bndFork != 0) && g_sideStream && h_nB(s) > 0 && !s->anyQgdFlux && !model5 &&
+                         !(s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc);
     for (int i = 0; i < n; ++i) {
         cudaEvent_t* ev = nullptr;
         if (s->profiling) {
@@ -640,8 +671,12 @@ void runSteps(qgd_solver* s, int n)
         PipeView pv;
         const bool usePipe = s->pipe.mode == 1 && !s->desc.adjust_time_step;
         if (usePipe) { ++s->pipe.epoch; pv = s->pview(); }
+        if (model5)    // the pressure of the old step: thermo.correct() runs before p = rho/psi (QGDFoam.C:149-154)
+            QGD_CUDA(cudaMemcpyAsync(s->v5->pOld.p, s->S.p + 5 * (size_t)s->mesh->h.nCells, (size_t)s->mesh->h.nCells * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, g_stream));
         s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev,
-                                  multi ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid, useFork ? &fork : nullptr);
+                                  (multi || model5) ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid, useFork ? &fork : nullptr);
+        if (model5) s->launches += s->v5->correct(s->v5view(), g_stream);      // varScModel5::correct on the closed state
         s->halo.pending = false;
         if (multi) {
             if (overlap) {
@@ -1056,8 +1091,18 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         if (!inTable(kCoeffsTable, model))     // QGDCoeffs.C:70-79
             throw Error(QGD_ERR_UNKNOWN_MODEL, "Unknown QGD coeffs evaluation approach type " + model +
                                                    "\n\nValid model types are:\n" + toc(kCoeffsTable));
-        if (model != "constScPrModel1" && model != "constScPrModel1n" && model != "constScPrModel2" && model != "varScModel6" && model != "varScModel7")
-            throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not available on the device yet (no CPU fallback)");
+        if (model != "constScPrModel1" && model != "constScPrModel1n" && model != "constScPrModel2" && model != "varScModel5" &&
+            model != "varScModel6" && model != "varScModel7")
+            throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is a QHDFoam model: it is not available in QGDFoam");
+        if (model == "varScModel5") {
+            if (d->implicit_diffusion)
+                throw Error(QGD_ERR_UNSUPPORTED, "varScModel5 with implicitDiffusion true is not available on the device (explicit branch only)");
+            if (mesh->h.nOwned != mesh->h.nCells)
+                throw Error(QGD_ERR_UNSUPPORTED, "varScModel5 on extended sub-meshes (multi-GPU) is not available: fvc::smooth crosses processor "
+                                                 "patches inside FaceCellWave");
+            if (!(d->varsc5_smoothCoeff >= 0.0) || !(d->varsc5_maxAspectRatio > 0.0) || !(d->varsc_minSc <= d->varsc_maxSc))
+                throw Error(QGD_ERR_INVALID, "varScModel5: smoothCoeff must be >= 0, maxAspectRatio > 0 and minSc <= maxSc");
+        }
         int diffPrecond = 2;
         if (d->implicit_diffusion) {
             const std::string pc = d->diff_preconditioner ? d->diff_preconditioner : "DIC";
@@ -1108,6 +1153,16 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         }
         k.tauMode = 0; k.implicit = d->implicit_diffusion ? 1 : 0;
         const HostMesh& h = mesh->h;
+        if (model == "varScModel5") {
+            // the ordinary kernels see model 0 with tauQGDf = I(alphaQGD) hQGDf / I(c) (varScModel5.C:204-205); everything that depends
+            // on ScQGD is rewritten by the model's own pass after each step (qgd_varsc5.h)
+            k.model = 0; k.varSc = 0; k.tauMode = 2;
+            s->v5.reset(new VarSc5Device());
+            s->v5->create(h, k, d->varsc5_rC, d->varsc_minSc, d->varsc_maxSc, d->ScQGD, d->varsc5_smoothCoeff, d->varsc5_badQualitySc,
+                          d->varsc5_maxAspectRatio, g_stream);
+            std::vector<double> sc0(h.nCells, d->ScQGD);                    // ScQGD_.primitiveFieldRef() = ScQGD (varScModel5.C:76)
+            s->scVar.upload(sc0, g_stream);
+        }
         s->S.alloc(16 * (size_t)h.nCells); s->P.alloc(6 * (size_t)h.nPoints);
         s->bA.alloc(h.nBnd); s->bB.alloc(h.nBnd);
         s->aQGD.alloc(h.nCells);
@@ -1116,7 +1171,7 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
         s->psiB.alloc(h.nBnd); s->pGrad.alloc(h.nBnd); s->pNew.alloc(h.nBnd); s->phiw.alloc(h.nBnd);
         s->P.zero(g_stream);
         // default step form: two kernels (measured faster on B200 at 256^3); QGD_PIPELINE=1 opts in
-        configurePipeline(s.get(), (getenv("QGD_PIPELINE") && atoi(getenv("QGD_PIPELINE")) && !d->adjust_time_step) ? 1 : 0, 0, -1, 0);
+        configurePipeline(s.get(), (getenv("QGD_PIPELINE") && atoi(getenv("QGD_PIPELINE")) && !d->adjust_time_step && !s->v5) ? 1 : 0, 0, -1, 0);
         StepScalars sc{};
         sc.dt = d->delta_t; sc.time = 0.0; sc.coNum = -1.0; sc.coMaxBits = 0ull;
         const double big = DBL_MAX;
@@ -1155,7 +1210,7 @@ int qgd_qgdfoam_set_const_sc_cells(qgd_solver* s, const int* cells, int n)
     return guarded([&] {
         requireInit();
         if (!s || (n > 0 && !cells) || n < 0) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_const_sc_cells: bad argument");
-        if (s->k.varSc != 7) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_const_sc_cells: constScCellSet is read by varScModel7 only");
+        if (s->k.varSc != 7 && !s->v5) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_const_sc_cells: constScCellSet is read by varScModel7 and varScModel5 only");
         if (s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_const_sc_cells: call before qgd_qgdfoam_init_fields");
         const int nC = s->mesh->h.nCells;
         if (n == 0) { s->scConst.release(); return; }
@@ -1228,6 +1283,7 @@ int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, con
         if (alphaQGD) QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, alphaQGD, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         else { std::vector<double> a(n, 0.5); QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, a.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream)); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
         launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), s->stage.p, s->stage.p + 3 * n, s->stage.p + 4 * n);
+        if (s->v5) varSc5Init(s);
         if (s->halo.active) s->launches += haloExchange(s);
         QGD_CUDA(cudaStreamSynchronize(g_stream));
         s->fieldsSet = true;
@@ -1250,6 +1306,7 @@ int qgd_qgdfoam_step_host(qgd_solver* s, int n_steps, const qgd_state_host* in, 
         requireInit();
         if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_host: null solver");
         if (!s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_step_host: call qgd_qgdfoam_init_fields first");
+        if (s->v5) throw Error(QGD_ERR_UNSUPPORTED, "qgd_qgdfoam_step_host: varScModel5 keeps ScQGD between steps (relaxation), which the host state does not carry; use qgd_qgdfoam_step");
         const size_t n = s->mesh->h.nCells;
         if (s->stage.n < QGD_STATE_DOUBLES_PER_CELL * n) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * n);
         double* st = s->stage.p;
@@ -1284,6 +1341,7 @@ int qgd_qgdfoam_step_fields_host(qgd_solver* s, int n_steps, const qgd_fields_ho
         requireInit();
         if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_step_fields_host: null solver");
         if (!s->fieldsSet) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_step_fields_host: call qgd_qgdfoam_init_fields first");
+        if (s->v5) throw Error(QGD_ERR_UNSUPPORTED, "qgd_qgdfoam_step_fields_host: varScModel5 keeps ScQGD between steps (relaxation), which U, T, p do not carry; use qgd_qgdfoam_step");
         const size_t n = s->mesh->h.nCells;
         if (s->stage.n < QGD_STATE_DOUBLES_PER_CELL * n) s->stage.alloc(QGD_STATE_DOUBLES_PER_CELL * n);
         double* st = s->stage.p;
@@ -1352,7 +1410,7 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
                     case 9: outp[i] = s->k.alphaEffGamma ? b[i].alphaEff / gam : b[i].alphaEff; break;
                     case 10: outp[i] = b[i].aByC; break;   // scaled below for cells
                     case 11: outp[i] = a[i].H; break;
-                    case 12: outp[i] = s->k.ScB; break;
+                    case 12: outp[i] = s->k.ScB; break;       // varScModel5: per-face values, copied below
                     default: throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_get: unknown field id");
                 }
             }
@@ -1366,6 +1424,11 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
             if (field == 12) {
                 if (s->scVar.n) { d2h(cells, s->scVar.p, n); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
                 else for (size_t c = 0; c < n; ++c) cells[c] = s->k.ScQGD;
+            } else if (field == 10 && s->v5) {          // varScModel5.C:207: tauQGD = alphaQGD hQGD / c (the slot holds alphaQGD)
+                std::vector<double> cs(n);
+                d2h(cells, s->S.p + 15 * n, n); d2h(cs.data(), s->S.p + 12 * n, n);
+                QGD_CUDA(cudaStreamSynchronize(g_stream));
+                for (size_t c = 0; c < n; ++c) cells[c] = cells[c] * h.hQGD[c] / cs[c];
             } else if (field == 1 || field == 3) {
                 std::vector<double> t(3 * n);
                 d2h(t.data(), s->S.p + (size_t)k0 * n, 3 * n);
@@ -1382,7 +1445,15 @@ int qgd_qgdfoam_get(qgd_solver* s, int field, double* cells, double* bnd)
             }
         }
         fetch(s->bA.p, s->bB.p, h.nBnd, bnd);
-        if (field == 10 && bnd) {
+        if (s->v5 && bnd && h.nBnd && (field == 10 || field == 12)) {
+            if (field == 12) { d2h(bnd, s->v5->ScB.p, (size_t)h.nBnd); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
+            else {
+                std::vector<RecB> b(h.nBnd);
+                QGD_CUDA(cudaMemcpyAsync(b.data(), s->bB.p, (size_t)h.nBnd * sizeof(RecB), cudaMemcpyDeviceToHost, g_stream));
+                QGD_CUDA(cudaStreamSynchronize(g_stream));
+                for (int i = 0; i < h.nBnd; ++i) bnd[i] = b[i].aByC * h.hQGDf[h.nInternal + i] / b[i].c;
+            }
+        } else if (field == 10 && bnd) {
             if (s->tauOutB.n) { d2h(bnd, s->tauOutB.p, (size_t)h.nBnd); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
             else for (int b = 0; b < h.nBnd; ++b) bnd[b] *= h.hQGDf[h.nInternal + b];
         }
@@ -1459,6 +1530,7 @@ int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, 
         requireInit();
         if (!s) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_pipeline: null solver");
         if (mode != 0 && mode != 1) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_pipeline: mode must be 0 or 1");
+        if (mode == 1 && s->v5) throw Error(QGD_ERR_UNSUPPORTED, "qgd_qgdfoam_set_pipeline: varScModel5 runs in the two-kernel step form");
         QGD_CUDA(cudaStreamSynchronize(g_stream));
         configurePipeline(s, mode, chunk_cells, lag, ring_slots);
     });
@@ -1558,6 +1630,7 @@ int qgd_qgdfoam_set_halo(qgd_solver* s, int nn, const int* nbr_rank, const int* 
         requireInit();
         if (!s || nn < 0) throw Error(QGD_ERR_INVALID, "qgd_qgdfoam_set_halo: bad arguments");
         if (nn > 0 && !g_comm) throw Error(QGD_ERR_STATE, "qgd_qgdfoam_set_halo: call qgd_comm_init first");
+        if (s->v5) throw Error(QGD_ERR_UNSUPPORTED, "qgd_qgdfoam_set_halo: varScModel5 is not available in decomposed runs");
         qgd_solver::Halo& h = s->halo;
         h.nbr.assign(nbr_rank, nbr_rank + nn);
         h.sendCellOff.assign(send_cell_off, send_cell_off + nn + 1); h.recvCellOff.assign(recv_cell_off, recv_cell_off + nn + 1);

@@ -11,6 +11,7 @@
 #include <cmath>
 
 #include "qgd_internal.h"
+#include "qgd_varsc5.h"
 
 namespace qgd {
 
@@ -359,6 +360,68 @@ void HostMesh::buildLeastSquares(bool opt, int& W, std::vector<int>& cells, std:
             cells[i * nI + f] = nb[i];
             for (int q = 0; q < 3; ++q) coef[(i * 3 + q) * nI + f] = wf2[i] * gd[q];
         }
+    }
+}
+
+} // namespace qgd
+
+// ---------------------------------------------------------------- varScModel5: time-constant host data (qgd_varsc5.h)
+namespace qgd {
+
+// mesh.cells() lists, the position of every internal face inside them, and the mesh-quality floor cqSc of varScModel5.C:112-132:
+// primitiveMeshTools::cellClosedness [OF-v2312, as remembered]: per cell the component-wise sums of |Sf| over all its faces;
+// aspectRatio = max / min of the sums over the solved directions, in 3D at least (1/6) (sum of all three) / V^(2/3);
+// cqSc = badQualitySc * aspectRatio / maxAspectRatio where aspectRatio > maxAspectRatio, else 0
+void buildVarSc5Host(const HostMesh& h, double badQualitySc, double maxAspectRatio, VarSc5Host& o)
+{
+    const int nC = h.nCells, nF = h.nFaces, nI = h.nInternal, nB = h.nBnd;
+    o.nC = nC; o.nI = nI; o.nB = nB;
+    o.own = h.owner; o.nei = h.neighbour;
+    o.w.assign(h.w.begin(), h.w.begin() + nI);
+    o.Sf = h.Sf;
+    o.bMagSf.assign(h.magSf.begin() + nI, h.magSf.end());
+    o.bDC.assign(h.dC.begin() + nI, h.dC.end());
+    o.bHf.assign(h.hQGDf.begin() + nI, h.hQGDf.end());
+    o.bKind.resize(nB);
+    for (int b = 0; b < nB; ++b) o.bKind[b] = h.patchKind[h.bfacePatch[b]];
+    // primitiveMesh::calcCells: owner loop over all faces, then neighbour loop over the internal faces
+    o.ccOff.assign(nC + 1, 0);
+    for (int f = 0; f < nF; ++f) o.ccOff[h.owner[f] + 1]++;
+    for (int f = 0; f < nI; ++f) o.ccOff[h.neighbour[f] + 1]++;
+    o.maxCellFaces = 0;
+    for (int c = 0; c < nC; ++c) { o.maxCellFaces = std::max(o.maxCellFaces, o.ccOff[c + 1]); o.ccOff[c + 1] += o.ccOff[c]; }
+    o.ccFace.assign(o.ccOff[nC], -1);
+    o.lidxOwn.assign(nI, -1); o.lidxNei.assign(nI, -1);
+    std::vector<int> fill(nC, 0);
+    for (int f = 0; f < nF; ++f) {
+        const int c = h.owner[f];
+        if (f < nI) o.lidxOwn[f] = fill[c];
+        o.ccFace[o.ccOff[c] + fill[c]++] = f;
+    }
+    for (int f = 0; f < nI; ++f) {
+        const int c = h.neighbour[f];
+        o.lidxNei[f] = fill[c];
+        o.ccFace[o.ccOff[c] + fill[c]++] = f;
+    }
+    // cellClosedness
+    std::vector<double> sumMag(3 * (size_t)nC, 0.0);
+    for (int f = 0; f < nF; ++f)
+        for (int d = 0; d < 3; ++d) sumMag[3 * (size_t)h.owner[f] + d] += std::fabs(h.Sf[3 * (size_t)f + d]);
+    for (int f = 0; f < nI; ++f)
+        for (int d = 0; d < 3; ++d) sumMag[3 * (size_t)h.neighbour[f] + d] += std::fabs(h.Sf[3 * (size_t)f + d]);
+    const double ROOTVSMALL = 1.0e-150, VGREAT = 1.0e+300;
+    o.aspectRatio.assign(nC, 1.0); o.cqSc.assign(nC, 0.0);
+    for (int c = 0; c < nC; ++c) {
+        double minC = VGREAT, maxC = -VGREAT;
+        for (int d = 0; d < 3; ++d)
+            if (h.gD[d] == 1) { minC = std::min(minC, sumMag[3 * (size_t)c + d]); maxC = std::max(maxC, sumMag[3 * (size_t)c + d]); }
+        double ar = maxC / (minC + ROOTVSMALL);
+        if (h.nD == 3) {
+            const double v = std::max(ROOTVSMALL, h.V[c]);
+            ar = std::max(ar, 1.0 / 6.0 * (sumMag[3 * (size_t)c] + sumMag[3 * (size_t)c + 1] + sumMag[3 * (size_t)c + 2]) / std::pow(v, 2.0 / 3.0));
+        }
+        o.aspectRatio[c] = ar;
+        if (ar > maxAspectRatio) o.cqSc[c] = badQualitySc * ar / maxAspectRatio;
     }
 }
 

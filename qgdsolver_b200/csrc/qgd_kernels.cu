@@ -1811,6 +1811,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         ++n;
         if (ev) cudaEventRecord(ev[5], st);
     }
+    if (hooks && hooks->beforeBndPost) hooks->beforeBndPost();
     if (fv.nB) {
         if (forked && fork->postOnSide) {
             cudaEventRecord(fork->evCell, st);

@@ -152,7 +152,9 @@ void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const Solv
 // still be in flight on the communication stream while the interior points are gathered)
 // afterGrad (implicit branch, multi-GPU): runs after each cell-centred Gauss gradient of U with the gradient array, to fetch the
 // gradients of the face-neighbour halo cells from their owners
-struct StepHooks { std::function<void()> midStep, beforeDt; std::function<void(cudaStream_t)> waitHalo; std::function<void(double*)> afterGrad; };
+// beforeBndPost: runs right before k_bnd_post overwrites the boundary state (varScModel5 keeps the p_b of that moment)
+struct StepHooks { std::function<void()> midStep, beforeDt; std::function<void(cudaStream_t)> waitHalo; std::function<void(double*)> afterGrad;
+                   std::function<void()> beforeBndPost; };
 // Boundary work forked onto a second, high-priority stream: k_patch_points and k_bnd_flux of step n (and, on one GPU,
 // k_bnd_post of step n-1) depend on the cell update only, not on the point gather, so they run beside k_points
 // instead of in front of / behind the face kernel.  Joins: face kernel <- evPatch, k_dt <- evBndFlux, side <- evCell.

@@ -223,6 +223,12 @@ def load_case(case_dir: str, solver: Optional[str] = None) -> CaseSetup:
             kw.update(varsc_cSc1=coeffs.scalar("cSc1", 1.0), varsc_minSc=coeffs.scalar("minSc", -1.0), varsc_maxSc=coeffs.scalar("maxSc", -1.0))
             if coeffs.found("constScCellSet"):
                 setup.const_sc_cell_set = coeffs.word("constScCellSet")
+        if model == "varScModel5":                                    # varScModel5.C:61-110,134-149
+            kw.update(varsc_minSc=coeffs.scalar("minSc", 0.05), varsc_maxSc=coeffs.scalar("maxSc", 1.0),
+                      varsc5_smoothCoeff=coeffs.scalar("smoothCoeff", 0.1), varsc5_rC=coeffs.scalar("rC", 0.5),
+                      varsc5_badQualitySc=coeffs.scalar("badQualitySc", 0.05), varsc5_maxAspectRatio=coeffs.scalar("maxAspectRatio", 1.5))
+            if coeffs.found("constScCellSet"):
+                setup.const_sc_cell_set = coeffs.word("constScCellSet")
         if implicit:
             if fvsolution is None:
                 raise FoamDictError("implicitDiffusion true needs system/fvSolution (solvers for U and e)")

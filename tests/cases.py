@@ -78,6 +78,10 @@ class Case:
             tk.update(transport="sutherland", As=self.sutherland["As"], Ts=self.sutherland["Ts"])
         if self.e_const:
             tk.update(thermo="eConst", Cv=self.e_const["Cv"], Esref=self.e_const["Esref"])
+        if self.model == "varScModel5":
+            v = self.varsc
+            tk.update(varsc5_smoothCoeff=v["smoothCoeff"], varsc5_rC=v["rC"], varsc5_badQualitySc=v["badQualitySc"],
+                      varsc5_maxAspectRatio=v["maxAspectRatio"])
         s = api.QGDFoam(dmesh, fvsc_scheme=self.scheme, qgd_coeffs=self.model, delta_t=self.dt, implicit_diffusion=self.implicit, **tk,
                         diff_tol=ds["tol"], diff_rel_tol=ds["rel_tol"], diff_max_iter=ds["max_iter"], diff_precond=ds["precond"],
                         varsc_cSc1=self.varsc["cSc1"], varsc_minSc=self.varsc["minSc"], varsc_maxSc=self.varsc["maxSc"],
