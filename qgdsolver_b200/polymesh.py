@@ -182,12 +182,15 @@ class PolyMesh:
         dC[:nI] = 1.0 / md
         nf = Sf[:nI] / magSf[:nI, None]
         ndC[:nI] = 1.0 / np.maximum((nf * delta).sum(1), 0.05 * md)
-        # boundary: delta = Cf - Cn (ordinary); processor patches are fixed up by decompose()
-        db = Cf[nI:] - C[own[nI:]]
-        mdb = np.sqrt((db * db).sum(1))
+        # boundary [OF-v2312 fvPatch::delta(), "use patch-normal delta for all non-coupled BCs"]: delta = nf (nf . (Cf - Cn)), so
+        # deltaCoeffs = nonOrthDeltaCoeffs = 1 / |nf . (Cf - Cn)| (the Foundation line uses the full vector Cf - Cn; the two differ
+        # on non-orthogonal boundary cells only).  Processor patches (full vector, neighbour cell centre) are fixed up by decompose()
         with np.errstate(divide="ignore", invalid="ignore"):
-            dC[nI:] = 1.0 / mdb
             nfb = Sf[nI:] / magSf[nI:, None]
+            dn = ((Cf[nI:] - C[own[nI:]]) * nfb).sum(1)
+            db = nfb * dn[:, None]
+            mdb = np.sqrt((db * db).sum(1))
+            dC[nI:] = 1.0 / mdb
             ndC[nI:] = 1.0 / np.maximum((nfb * db).sum(1), 0.05 * mdb)
         self.C, self.V, self.Cf, self.Sf, self.magSf = C, V, Cf, Sf, magSf
         self.weights, self.deltaCoeffs, self.nonOrthDeltaCoeffs = w, dC, ndC
