@@ -46,9 +46,15 @@ typedef enum {
     QGD_BC_QGD_FLUX = 3,         /* qgdFlux  qgdFluxFvPatchScalarField.C:159-208 */
     QGD_BC_CALCULATED = 4,       /* calculated                                   */
     QGD_BC_QHD_FLUX = 5,         /* qhdFlux  qhdFluxFvPatchScalarField.C:159-219 */
-    QGD_BC_SLIP = 6              /* slip | symmetryPlane | symmetry for U [OF-v2312 basicSymmetryFvPatchField]:
+    QGD_BC_SLIP = 6,             /* slip | symmetryPlane | symmetry for U [OF-v2312 basicSymmetryFvPatchField]:
                                     U_b = U_P - n (n . U_P); scalars on such patches are zeroGradient.  QGDFoam, explicit
                                     branch (the Mach-3 forward-facing-step walls, BASELINE configs[1])              */
+    QGD_BC_WEDGE = 7             /* wedge for U on a QGD_PATCH_WEDGE patch [OF-v2312 wedgeFvPatchField::evaluate]:
+                                    U_b = faceT . U_P with faceT = rotationTensor(centre-plane normal, patch normal)
+                                    (wedgePolyPatch); scalars on wedge patches are zeroGradient.  The face derivatives
+                                    stay zero there (GaussVolPointBase2D.C:175-179) and the vertices of wedge patches
+                                    lose the patch-normal component of interpolated vectors / tensors [OF-v2312
+                                    pointConstraints].  QGDFoam, explicit branch.                                  */
 } qgd_bc_kind;
 
 typedef struct qgd_mesh qgd_mesh;       /* fvMesh image on the device             */

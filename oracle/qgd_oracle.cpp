@@ -66,6 +66,7 @@ struct or_ctx {
     IVec pcOff, pcCell; Vec pcW;       // point -> cells, weights (non patch points)
     std::vector<char> isPatchPoint;
     IVec pbOff, pbFace; Vec pbW;       // patch point -> boundary faces (bface index), weights
+    IVec wedgePts; Vec wedgeN;         // points on a wedge patch and the patch normal (pointConstraints [OF-v2312])
     // QGDCoeffs
     Vec hQGDf, hQGD;
     // GaussVolPointBase3D
@@ -165,6 +166,22 @@ void volPointInterpolate(const or_ctx& m, int k, const double* cell, const doubl
                 for (int j = 0; j < k; ++j) pf[(long)p * k + j] += m.pbW[q] * bnd[(long)m.pbFace[q] * k + j];
         }
     }
+    // [OF-v2312] pointConstraints::constrain -> wedgePointPatchField::evaluate: on the points of a wedge patch a vector loses its
+    // component along the patch normal, transform(I - nHat nHat, v); a tensor becomes R.T.R^T with R = I - nHat nHat; scalars stay
+    if (k == 3 || k == 9)
+        for (size_t i = 0; i < m.wedgePts.size(); ++i) {
+            const double* n = &m.wedgeN[3 * i];
+            double* v = &pf[(long)m.wedgePts[i] * k];
+            if (k == 3) {
+                const double vn = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
+                for (int j = 0; j < 3; ++j) v[j] -= n[j] * vn;
+            } else {
+                double R[9], t[9];
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[3 * a + b] = (a == b ? 1.0 : 0.0) - n[a] * n[b];
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { t[3 * a + b] = 0.0; for (int c = 0; c < 3; ++c) t[3 * a + b] += R[3 * a + c] * v[3 * c + b]; }
+                for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { v[3 * a + b] = 0.0; for (int c = 0; c < 3; ++c) v[3 * a + b] += t[3 * a + c] * R[3 * b + c]; }
+            }
+        }
 }
 
 void buildDerived(or_ctx& m)
@@ -234,6 +251,20 @@ void buildDerived(or_ctx& m)
                 sum += m.pcW[q];
             }
             for (int q = m.pcOff[p]; q < m.pcOff[p + 1]; ++q) m.pcW[q] /= sum;
+        }
+        {   // points of wedge patches, with the (planar) patch's normal: wedgePointPatchField takes pointNormals()[0] of the patch
+            std::vector<char> seen(m.nPoints, 0);
+            for (int b = 0; b < m.nBnd; ++b) {
+                if (m.patchKind[m.bfacePatch[b]] != OR_PATCH_WEDGE) continue;
+                const int f = m.nInternal + b, f0 = m.patchStart[m.bfacePatch[b]];
+                for (int q = m.faceOff[f]; q < m.faceOff[f + 1]; ++q) {
+                    const int p = m.faceVerts[q];
+                    if (seen[p]) continue;
+                    seen[p] = 1;
+                    m.wedgePts.push_back(p);
+                    for (int d = 0; d < 3; ++d) m.wedgeN.push_back(m.Sf[3 * (size_t)f0 + d] / m.magSf[f0]);
+                }
+            }
         }
         m.pbOff.assign(m.nPoints + 1, 0);
         for (int p = 0; p < m.nPoints; ++p) m.pbOff[p + 1] = m.pbOff[p] + (int)pb[p].size();
@@ -695,6 +726,33 @@ Thermo thermoOf(const or_ctx& s)
     return t;
 }
 
+// [OF-v2312] wedgePolyPatch::calcGeometry + rotationTensor (restated from the OpenFOAM source as remembered): the patch normal n,
+// the centre-plane normal = the coordinate axis n is closest to (components sign(n_i) (max(|n_i|, 0.5) - 0.5), normalised),
+// faceT = rotationTensor(centreNormal, n) = s I + (1 - s) n3 n3 / |n3|^2 + (n n1 - n1 n) with n1 = centreNormal, s = n1 . n,
+// n3 = n1 x n; cellT = faceT . faceT.  OpenFOAM averages n over the (planar) patch; here it is the face's own normal.
+static void wedgeFaceT(const double* n, double (&T)[9])
+{
+    auto sgn = [](double v) { return v >= 0 ? 1.0 : -1.0; };
+    double n1[3];
+    for (int i = 0; i < 3; ++i) n1[i] = sgn(n[i]) * (std::max(std::fabs(n[i]), 0.5) - 0.5);
+    const double m1 = std::sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+    for (int i = 0; i < 3; ++i) n1[i] /= m1;
+    const double s = n1[0] * n[0] + n1[1] * n[1] + n1[2] * n[2];
+    const double n3[3] = {n1[1] * n[2] - n1[2] * n[1], n1[2] * n[0] - n1[0] * n[2], n1[0] * n[1] - n1[1] * n[0]};
+    const double m3 = n3[0] * n3[0] + n3[1] * n3[1] + n3[2] * n3[2];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double v = (i == j) ? s : 0.0;
+            if (m3 > 1.0e-15) v += (1.0 - s) * n3[i] * n3[j] / m3 + (n[i] * n1[j] - n1[i] * n[j]);      // SMALL
+            else v = (i == j) ? 1.0 : 0.0;                                                             // n == centreNormal
+            T[3 * i + j] = v;
+        }
+}
+static inline void matVec(const double (&T)[9], const double* u, double (&o)[3])
+{
+    for (int i = 0; i < 3; ++i) o[i] = T[3 * i] * u[0] + T[3 * i + 1] * u[1] + T[3 * i + 2] * u[2];
+}
+
 // patch snGrad() of a field with the given BC [OF-v2312 fvPatchField::snGrad, zeroGradient, fixedGradient]
 void patchSnGrad(const or_ctx& s, int k, const IVec& bc, const double* cell, const double* bnd, const double* grad, double* out)
 {
@@ -706,13 +764,21 @@ void patchSnGrad(const or_ctx& s, int k, const IVec& bc, const double* cell, con
             if (s.patchKind[pi] == OR_PATCH_EMPTY) v = 0.0;
             else if (bc[pi] == OR_BC_ZERO_GRADIENT) v = 0.0;
             else if (bc[pi] == OR_BC_FIXED_GRADIENT || bc[pi] == OR_BC_QGD_FLUX) v = grad ? grad[(long)b * k + j] : 0.0;
+            else if (bc[pi] == OR_BC_WEDGE && k == 3) {      // [OF-v2312 wedgeFvPatchField::snGrad] (cellT . U_P - U_P) deltaCoeffs / 2
+                double T[9], t1[3], t2[3];
+                wedgeFaceT(&s.nf[3 * (size_t)f], T);
+                matVec(T, &cell[(long)s.owner[f] * 3], t1);
+                matVec(T, t1, t2);
+                v = (t2[j] - cell[(long)s.owner[f] * 3 + j]) * (0.5 * s.dC[f]);
+            }
             else v = s.dC[f] * (bnd[(long)b * k + j] - cell[(long)s.owner[f] * k + j]);
             out[(long)b * k + j] = v;
         }
     }
 }
 
-// correctBoundaryConditions() for U (fixedValue | zeroGradient | slip)
+// correctBoundaryConditions() for U (fixedValue | zeroGradient | slip | wedge)
+// wedge [OF-v2312 wedgeFvPatchField::evaluate]: U_b = transform(faceT, U_P)
 // slip / symmetryPlane [OF-v2312 basicSymmetryFvPatchField::evaluate]: (U_P + transform(I - 2 nn, U_P))/2 = U_P - n (n . U_P);
 // its snGrad (transform(I - 2nn, U_P) - U_P) deltaCoeffs/2 equals deltaCoeffs (U_b - U_P), the generic branch of patchSnGrad.
 // Oracle only so far (explicit branch): the device library has no slip condition yet.
@@ -728,6 +794,13 @@ void correctU(or_ctx& s)
             const double* u = &s.U[3 * (size_t)P];
             const double un = n[0] * u[0] + n[1] * u[1] + n[2] * u[2];
             for (int j = 0; j < 3; ++j) s.UB[3 * (size_t)b + j] = u[j] - n[j] * un;
+            continue;
+        }
+        if (s.bcU[pi] == OR_BC_WEDGE) {
+            double T[9], ub[3];
+            wedgeFaceT(&s.nf[3 * (size_t)f], T);
+            matVec(T, &s.U[3 * (size_t)P], ub);
+            for (int j = 0; j < 3; ++j) s.UB[3 * (size_t)b + j] = ub[j];
             continue;
         }
         for (int j = 0; j < 3; ++j)

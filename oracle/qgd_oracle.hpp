@@ -24,7 +24,8 @@ extern "C" {
 enum { OR_PATCH_GENERIC = 0, OR_PATCH_EMPTY = 1, OR_PATCH_PROCESSOR = 2, OR_PATCH_WEDGE = 3 };
 // boundary-condition kinds per patch and field
 enum { OR_BC_FIXED_VALUE = 0, OR_BC_ZERO_GRADIENT = 1, OR_BC_FIXED_GRADIENT = 2, OR_BC_QGD_FLUX = 3,
-       OR_BC_CALCULATED = 4, OR_BC_QHD_FLUX = 5, OR_BC_SLIP = 6 };
+       OR_BC_CALCULATED = 4, OR_BC_QHD_FLUX = 5, OR_BC_SLIP = 6,
+       OR_BC_WEDGE = 7 };   // wedge [OF-v2312 wedgeFvPatchField]: U_b = faceT . U_P on a wedge patch (scalars there: zeroGradient)
 // fvsc schemes
 enum { OR_FVSC_GAUSSVOLPOINT = 0, OR_FVSC_REDUCED = 1, OR_FVSC_LEASTSQUARES = 2, OR_FVSC_LEASTSQUARESOPT = 3 };
 

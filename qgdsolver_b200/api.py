@@ -18,7 +18,7 @@ from .polymesh import PolyMesh
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqgd_b200.so")
 
-BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED, BC_QHD_FLUX, BC_SLIP = 0, 1, 2, 3, 4, 5, 6
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_FIXED_GRADIENT, BC_QGD_FLUX, BC_CALCULATED, BC_QHD_FLUX, BC_SLIP, BC_WEDGE = 0, 1, 2, 3, 4, 5, 6, 7
 QGD_OK, ERR_INVALID, ERR_UNKNOWN_MODEL, ERR_UNSUPPORTED, ERR_CUDA, ERR_COMM, ERR_STATE = 0, -1, -2, -3, -4, -5, -6
 
 # every symbol include/qgd_b200.h declares (checked by tests/test_abi_cpu.py)

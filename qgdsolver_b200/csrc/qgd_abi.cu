@@ -658,6 +658,7 @@ void runSteps(qgd_solver* s, int n)
     // (QGD_BND_FORK=2) until measured - there the side stream can only start after the halo wait
     const bool useFork = (multi ? g_bndFork == 2 : g_bndFork != 0) && g_sideStream && h_nB(s) > 0 && !s->anyQgdFlux && !model5 &&
                          !(s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc);
+    const WedgeView wedge{(int)s->mesh->h.wedgePts.size(), s->mesh->wedgePts.p, s->mesh->wedgeN.p};
     for (int i = 0; i < n; ++i) {
         cudaEvent_t* ev = nullptr;
         if (s->profiling) {
@@ -675,7 +676,8 @@ void runSteps(qgd_solver* s, int n)
             QGD_CUDA(cudaMemcpyAsync(s->v5->pOld.p, s->S.p + 5 * (size_t)s->mesh->h.nCells, (size_t)s->mesh->h.nCells * sizeof(double),
                                      cudaMemcpyDeviceToDevice, g_stream));
         s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, ev,
-                                  (multi || model5) ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid, useFork ? &fork : nullptr);
+                                  (multi || model5) ? &hooks : nullptr, usePipe ? &pv : nullptr, s->pipe.grid, useFork ? &fork : nullptr,
+                                  wedge.n ? &wedge : nullptr);
         if (model5) s->launches += s->v5->correct(s->v5view(), g_stream);      // varScModel5::correct on the closed state
         s->halo.pending = false;
         if (multi) {
@@ -971,6 +973,7 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         m->magSf.upload(permD(h.magSf), g_stream); m->w.upload(permD(h.w), g_stream); m->dC.upload(permD(h.dC), g_stream);
         m->ndC.upload(permD(h.ndC), g_stream); m->V.upload(h.V, g_stream);
         m->hQGDf.upload(permD(h.hQGDf), g_stream); m->hQGD.upload(h.hQGD, g_stream);
+        if (!h.wedgePts.empty()) { m->wedgePts.upload(h.wedgePts, g_stream); m->wedgeN.upload(h.wedgeN, g_stream); }
         *out = m.release();
     });
 }
@@ -1237,10 +1240,15 @@ int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const i
             const int pi = h.bfacePatch[b];
             u[b] = bc_U[pi]; t[b] = bc_T[pi]; p[b] = bc_p[pi];
             if (h.patchKind[pi] == QGD_PATCH_EMPTY) continue;
-            if (u[b] != QGD_BC_FIXED_VALUE && u[b] != QGD_BC_ZERO_GRADIENT && u[b] != QGD_BC_SLIP)
-                throw Error(QGD_ERR_UNSUPPORTED, "U boundary condition outside the device-native set (fixedValue, zeroGradient, slip)");
+            if (u[b] != QGD_BC_FIXED_VALUE && u[b] != QGD_BC_ZERO_GRADIENT && u[b] != QGD_BC_SLIP && u[b] != QGD_BC_WEDGE)
+                throw Error(QGD_ERR_UNSUPPORTED, "U boundary condition outside the device-native set (fixedValue, zeroGradient, slip, wedge)");
             if (u[b] == QGD_BC_SLIP && s->k.implicit)
                 throw Error(QGD_ERR_UNSUPPORTED, "slip / symmetryPlane velocity with implicitDiffusion true is not available (explicit branch only)");
+            if (u[b] == QGD_BC_WEDGE) {
+                if (h.patchKind[pi] != QGD_PATCH_WEDGE) throw Error(QGD_ERR_INVALID, "wedge velocity condition on a patch that is not a wedge patch");
+                if (s->k.implicit) throw Error(QGD_ERR_UNSUPPORTED, "wedge patches with implicitDiffusion true are not available (explicit branch only)");
+                if (h.nOwned != h.nCells) throw Error(QGD_ERR_UNSUPPORTED, "wedge patches on extended sub-meshes (multi-GPU) are not available");
+            }
             if (t[b] != QGD_BC_FIXED_VALUE && t[b] != QGD_BC_ZERO_GRADIENT)
                 throw Error(QGD_ERR_UNSUPPORTED, "T boundary condition outside the device-native set (fixedValue, zeroGradient)");
             if (p[b] != QGD_BC_FIXED_VALUE && p[b] != QGD_BC_ZERO_GRADIENT && p[b] != QGD_BC_QGD_FLUX)

@@ -163,6 +163,24 @@ void HostMesh::build(const qgd_mesh_desc& d)
         }
     }
 
+    // ---- vertices of wedge patches (pointConstraints): the patch normal is that of the patch's first face, as wedgePointPatchField
+    // takes pointNormals()[0] of the planar patch
+    {
+        std::vector<char> seen(nPoints, 0);
+        wedgePts.clear(); wedgeN.clear();
+        for (int b = 0; b < nBnd; ++b) {
+            if (patchKind[bfacePatch[b]] != QGD_PATCH_WEDGE) continue;
+            const int f = nInternal + b, f0 = patchStart[bfacePatch[b]];
+            for (int q = faceOff[f]; q < faceOff[f + 1]; ++q) {
+                const int p = faceVerts[q];
+                if (seen[p]) continue;
+                seen[p] = 1;
+                wedgePts.push_back(p);
+                for (int d = 0; d < 3; ++d) wedgeN.push_back(Sf[3 * (size_t)f0 + d] / magSf[f0]);
+            }
+        }
+    }
+
     // ---- QGD length scales
     hQGDf.assign(nFaces, 0.0);
     for (int f = 0; f < nInternal; ++f) {

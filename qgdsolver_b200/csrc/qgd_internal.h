@@ -121,6 +121,10 @@ struct HostMesh {
     std::vector<int> ppOff, ppFace;                // patch point (by list position) -> boundary faces
     std::vector<double> ppW;
     std::vector<double> hQGDf, hQGD;
+    // vertices of wedge patches and the (planar) patch's normal: volPointInterpolation constrains vectors / tensors there
+    // [OF-v2312 pointConstraints -> wedgePointPatchField::evaluate: transform(I - nHat nHat, .)]
+    std::vector<int> wedgePts;
+    std::vector<double> wedgeN;                    // 3 per listed point
     void build(const qgd_mesh_desc& d);
     // face gradient records for a scheme ("GaussVolPoint" / "reduced")
     // leastSquares scheme (extendedFaceStencilFindNeighbours.C:41-86, extendedFaceStencilCalculateWeights.C:43-155):
@@ -156,4 +160,6 @@ struct qgd_mesh {
     qgd::DevBuf<double> ppW;
     qgd::DevBuf<double> Sf;        // SoA 3*faceStride
     qgd::DevBuf<double> magSf, w, dC, ndC, V, hQGDf, hQGD;
+    qgd::DevBuf<int> wedgePts;     // HostMesh::wedgePts / wedgeN (empty without wedge patches)
+    qgd::DevBuf<double> wedgeN;
 };

@@ -15,6 +15,7 @@
 #include <cstdio>
 
 #include "qgd_kernels.cuh"
+#include "qgd_wedge.h"
 
 namespace qgd {
 
@@ -525,6 +526,48 @@ __global__ void k_patch_points(SolverView sv, BndState bs, int onlyP)
     o[5 * nP] = a5;
     if (onlyP) return;
     o[0] = a0; o[nP] = a1; o[2 * nP] = a2; o[3 * nP] = a3; o[4 * nP] = a4;
+}
+
+// [OF-v2312] pointConstraints::constrain -> wedgePointPatchField::evaluate on the vertices of wedge patches: a vector loses its
+// component along the patch normal (transform(I - nHat nHat, v)), a tensor becomes R.T.R^T with R = I - nHat nHat.
+// step form: the velocity rows (fields 1..3) of the SoA point array P[6][nPoints]
+__global__ void k_wedge_points(int n, const int* __restrict__ pts, const double* __restrict__ nrm, double* __restrict__ P, size_t nPoints)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = pts[i];
+    const double nx = nrm[3 * (size_t)i], ny = nrm[3 * (size_t)i + 1], nz = nrm[3 * (size_t)i + 2];
+    double* u = P + nPoints + p;
+    const double vn = nx * u[0] + ny * u[nPoints] + nz * u[2 * nPoints];
+    u[0] -= nx * vn; u[nPoints] -= ny * vn; u[2 * nPoints] -= nz * vn;
+}
+// operator form: AoS point values pts[p*K + j], K = 3 (vector) or 9 (tensor)
+template <int K>
+__global__ void k_wedge_points_generic(int n, const int* __restrict__ list, const double* __restrict__ nrm, double* __restrict__ pv)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double nv[3] = {nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2]};
+    double* v = pv + (size_t)list[i] * K;
+    if (K == 3) {
+        const double vn = nv[0] * v[0] + nv[1] * v[1] + nv[2] * v[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[j] -= nv[j] * vn;
+    } else {
+        double R[9], t[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) R[3 * a + b] = (a == b ? 1.0 : 0.0) - nv[a] * nv[b];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { t[3 * a + b] = 0.0; for (int c = 0; c < 3; ++c) t[3 * a + b] += R[3 * a + c] * v[3 * c + b]; }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) { double r = 0.0; for (int c = 0; c < 3; ++c) r += t[3 * a + c] * R[3 * b + c]; v[3 * a + b] = r; }
+    }
 }
 
 // boundary-face inputs shared by k_bnd_pre and k_bnd_flux
@@ -1155,6 +1198,14 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
         const double un = n[0] * U[0] + n[1] * U[1] + n[2] * U[2];
 #pragma unroll
         for (int j = 0; j < 3; ++j) U[j] = U[j] - n[j] * un;
+    } else if (bs.bcU[b] == QGD_BC_WEDGE) {     // [OF-v2312 wedgeFvPatchField::evaluate] U_b = transform(faceT, U_P)
+        const double ms = fv.magSf[f];
+        const double n[3] = {fv.Sf[f] / ms, fv.Sf[(size_t)fv.fs + f] / ms, fv.Sf[2 * (size_t)fv.fs + f] / ms};
+        double Tw[9];
+        wedgeFaceT(n, Tw);
+        const double u0 = U[0], u1 = U[1], u2 = U[2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) U[j] = Tw[3 * j] * u0 + Tw[3 * j + 1] * u1 + Tw[3 * j + 2] * u2;
     }
     double T, e;
     if (fixT) { T = bs.bvT[b]; e = thermoEs(k, T); }                     // fixedEnergy ; hePsiQGDThermo.C:93-105
@@ -1658,6 +1709,9 @@ void launchPointGather(cudaStream_t st, int K, const qgd_mesh& m, const double* 
         default: throw Error(QGD_ERR_INVALID, "fvsc: unsupported number of components");
     }
 #undef QGD_PG
+    const int nW = (int)m.h.wedgePts.size();        // pointConstraints on the vertices of wedge patches (vectors, tensors)
+    if (nW && K == 3) k_wedge_points_generic<3><<<nblk(nW), kBlock, 0, st>>>(nW, m.wedgePts.p, m.wedgeN.p, pts);
+    if (nW && K == 9) k_wedge_points_generic<9><<<nblk(nW), kBlock, 0, st>>>(nW, m.wedgePts.p, m.wedgeN.p, pts);
     QGD_CUDA(cudaGetLastError());
 }
 
@@ -1735,7 +1789,7 @@ int pipelineKernelGrid(int cfEllW) { return cfEllW == 4 ? pipeGrid<4>() : (cfEll
 
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev, const StepHooks* hooks, const PipeView* pipe, int gridPipe,
-               const StepFork* fork)
+               const StepFork* fork, const WedgeView* wedge)
 {
     int n = 0;
     const bool pointsNeeded = !c.reducedScheme;
@@ -1767,6 +1821,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
         if (ev) cudaEventRecord(ev[1], st);
         if (forked && hooks && hooks->waitHalo) hooks->waitHalo(sb);
         if (sv.nPatchPoints) { k_patch_points<<<nblk(sv.nPatchPoints), kBlock, 0, sb>>>(sv, bs, 0); ++n; }
+        if (wedge && wedge->n) { k_wedge_points<<<nblk(wedge->n), kBlock, 0, sb>>>(wedge->n, wedge->pts, wedge->nrm, sv.P, (size_t)sv.nPoints); ++n; }
         if (forked) cudaEventRecord(fork->evPatch, sb);
     } else if (hooks && hooks->waitHalo) {
         hooks->waitHalo(st);

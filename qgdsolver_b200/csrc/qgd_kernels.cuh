@@ -164,9 +164,11 @@ struct StepFork {
     cudaEvent_t evEntry, evPatch, evBndFlux, evCell, evBndPost;
     bool postOnSide;         // k_bnd_post on the side stream too (single GPU: nothing on the main stream needs it before the next step)
 };
+// vertices of wedge patches: after the patch-point kernel their velocity loses the patch-normal component (pointConstraints [OF-v2312])
+struct WedgeView { int n; const int* pts; const double* nrm; };
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr,
-               const PipeView* pipe = nullptr, int gridPipe = 0, const StepFork* fork = nullptr);
+               const PipeView* pipe = nullptr, int gridPipe = 0, const StepFork* fork = nullptr, const WedgeView* wedge = nullptr);
 // implicit-diffusion step, phase by phase (the PCG solves run between the phases, see runStepsImplicit in qgd_abi.cu)
 int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                         const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust, const StepHooks* hooks = nullptr);

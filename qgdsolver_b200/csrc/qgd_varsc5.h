@@ -28,10 +28,12 @@
 
 #include "qgd_kernels.cuh"
 
+#ifndef QGD_HD
 #ifdef __CUDACC__
 #define QGD_HD __host__ __device__ __forceinline__
 #else
 #define QGD_HD inline
+#endif
 #endif
 
 namespace qgd {

@@ -573,7 +573,7 @@ def write_field(path: str, mesh: PolyMesh, name: str, internal: np.ndarray, patc
 
 # ------------------------------------------------------------------------------------------------ solver glue
 _BC_CODE = {"fixedValue": 0, "zeroGradient": 1, "fixedGradient": 2, "qgdFlux": 3, "calculated": 4, "qhdFlux": 5, "empty": 1,
-            "slip": 6, "symmetryPlane": 6, "symmetry": 6}
+            "slip": 6, "symmetryPlane": 6, "symmetry": 6, "wedge": 7}
 
 
 def bc_arrays(mesh: PolyMesh, fld: VolField) -> Tuple[np.ndarray, np.ndarray]:
@@ -587,7 +587,7 @@ def bc_arrays(mesh: PolyMesh, fld: VolField) -> Tuple[np.ndarray, np.ndarray]:
         if t not in _BC_CODE:
             raise FoamFormatError(f"patch field type {t} of {fld.name} on {p.name} is outside the device-native set")
         kinds[i] = _BC_CODE[t]
-        if kinds[i] == 6 and fld.ncmpt == 1:        # basicSymmetry on a scalar is zeroGradient [OF-v2312]
+        if kinds[i] in (6, 7) and fld.ncmpt == 1:   # basicSymmetry / wedge on a scalar: the patch-internal value [OF-v2312]
             kinds[i] = 1
         sl = slice(p.start - nI, p.start - nI + p.size)
         if t == "fixedValue":

@@ -351,6 +351,25 @@ def hex_box(nx: int, ny: int, nz: int,
     return mesh
 
 
+def wedge_box(nx: int, nr: int, lengths=(1.0, 1.0), r0: float = 0.5, angle_deg: float = 5.0, perturb: float = 0.0,
+              seed: int = 0) -> PolyMesh:
+    """Axisymmetric wedge block (axis = x): hex cells over x in [0, Lx], r in [r0, r0 + Lr], one cell thick in the circumferential
+    direction, front / back planes at -+angle/2 about the centre plane z = 0 - what blockMesh produces for a `wedge` case away
+    from the axis (r0 > 0: no prism cells, which GaussVolPoint rejects together with wedge patches, fvsc.C:65-82).  Patches
+    xMin, xMax, yMin (inner radius), yMax (outer radius) and the two `wedge` patches zMin, zMax; geometricD = (1, 1, -1)."""
+    if not r0 > 0.0:
+        raise ValueError("wedge_box: r0 must be positive (cells on the axis would be prisms)")
+    m = hex_box(nx, nr, 1, lengths=(lengths[0], lengths[1], 1.0), origin=(0.0, r0, 0.0), patch_kinds={"zMin": "empty", "zMax": "empty"},
+                perturb=perturb, seed=seed, compute_geometry=False)
+    half = np.deg2rad(angle_deg) / 2.0
+    r, side = m.points[:, 1].copy(), np.where(m.points[:, 2] > 0.5, 1.0, -1.0)
+    m.points[:, 1] = r * np.cos(half)
+    m.points[:, 2] = side * r * np.sin(half)
+    m.patches = [Patch(p.name, PATCH_WEDGE if p.name in ("zMin", "zMax") else p.kind, p.start, p.size) for p in m.patches]
+    m.geometric_d = np.array([1, 1, -1], np.int32)
+    return m.compute_geometry()
+
+
 def prism_box(nx: int, ny: int, nz: int, lengths=(1.0, 1.0, 1.0), perturb: float = 0.0,
               seed: int = 0) -> PolyMesh:
     """Each hex of a box split into two triangular prisms (diagonal in the xy plane):

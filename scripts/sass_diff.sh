@@ -14,7 +14,7 @@ python3 - "$wt/qgdsolver_b200/libqgd_b200.so" "$root/qgdsolver_b200/libqgd_b200.
 import re, subprocess, sys
 def funcs(lib):
     txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-    txt = re.sub(r"_GLOBAL__N__[0-9a-f_]*qgd_[a-z]*_cu_[0-9a-f]*", "ANON", txt)
+    txt = re.sub(r"_GLOBAL__N__[0-9a-f_]*qgd_[a-z0-9]*_cu_[0-9a-f]*", "ANON", txt)
     out, name, buf = {}, None, []
     for line in txt.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)

@@ -7,6 +7,7 @@ from qgdsolver_b200 import polymesh as pm
 
 FV, ZG, FG, QF = 0, 1, 2, 3   # bc kinds (fixedValue, zeroGradient, fixedGradient, qgdFlux)
 SLIP = 6                      # QGD_BC_SLIP / OR_BC_SLIP: slip / symmetryPlane velocity
+WEDGE = 7                     # QGD_BC_WEDGE / OR_BC_WEDGE: wedge velocity (U_b = faceT . U_P) on wedge patches
 
 GAS = dict(R=1.0, Cp=3.5, Hf=0.0, Tref=0.0, Hsref=0.0, mu=1.0e-3, Pr=0.71, ScQGD=1.0, PrQGD=1.0)
 GAS_OFFSET = dict(R=287.0, Cp=1004.5, Hf=0.0, Tref=298.15, Hsref=0.0, mu=1.8e-5, Pr=0.71, ScQGD=0.7, PrQGD=0.9)
@@ -321,3 +322,17 @@ def case_truncoct(n=(5, 4, 4), bcs="zg", **opts):
     GaussVolPoint, square faces the six-point formula; cell->face rows longer than the ELL width exercise the CSR tails)"""
     mesh = pm.truncated_octahedron_box(*n, h=1.0 / max(n))
     return _with_bcs(mesh, bcs, GAS, 1e-4, **opts)
+
+
+def case_wedge(n=(16, 12), angle_deg=5.0, r0=0.5, perturb=0.0, bcs="fixed", gas=GAS, lengths=(1.0, 1.0), **opts):
+    """Axisymmetric QGDFoam case on a wedge mesh (polymesh.wedge_box): `wedge` velocity on the two wedge patches (scalars there are
+    zeroGradient), the other four patches as `bcs` says; a smooth in-plane initial state (no circumferential velocity)."""
+    mesh = pm.wedge_box(n[0], n[1], lengths=lengths, r0=r0, angle_deg=angle_deg, perturb=perturb, seed=13)
+    c = _with_bcs(mesh, bcs, gas, 1e-4, **opts)
+    for i, p in enumerate(mesh.patches):
+        if p.kind == pm.PATCH_WEDGE:
+            c.bcU[i], c.bcT[i], c.bcP[i] = WEDGE, ZG, ZG
+    x, y = mesh.C[:, 0], mesh.C[:, 1]
+    c.U0 = np.ascontiguousarray(np.stack([0.1 * np.sin(2 * np.pi * x) * np.cos(3 * y), 0.08 * np.cos(2 * np.pi * x) * np.sin(3 * y),
+                                          np.zeros(mesh.n_cells)], 1))
+    return c

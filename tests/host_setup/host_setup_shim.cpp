@@ -198,3 +198,26 @@ int hs_varsc5_correct(void* p, const double* prm, double* S, const double* bT, c
 }
 
 } // extern "C"
+
+// ---------------------------------------------------------------- wedge patches: the product's vertex list / normals and face tensor
+#include "qgd_wedge.h"
+
+extern "C" {
+
+int hs_wedge_points(void* p, int* pts, double* nrm)     // returns the count; pts / nrm may be NULL to query it
+{
+    const HostMesh& h = *static_cast<HostMesh*>(p);
+    if (pts) std::memcpy(pts, h.wedgePts.data(), sizeof(int) * h.wedgePts.size());
+    if (nrm) std::memcpy(nrm, h.wedgeN.data(), sizeof(double) * h.wedgeN.size());
+    return (int)h.wedgePts.size();
+}
+
+void hs_wedge_face_t(const double* n, double* T)
+{
+    const double nn[3] = {n[0], n[1], n[2]};
+    double t[9];
+    qgd::wedgeFaceT(nn, t);
+    std::memcpy(T, t, sizeof(t));
+}
+
+} // extern "C"

@@ -52,7 +52,7 @@ def test_varsc5_steps_match_oracle(qgd, oracle_mod, name):
         assert rel_linf(s.get(f), o.get(f)) < 1e-10, f
     a, ab = s.get("ScQGD", with_bnd=True)
     b, bb = o.get("ScQGD", with_bnd=True)
-    assert b.max() > 1.5 * b.min()                         # the sensor is active: ScQGD is not a constant field
+    assert b.max() > 1.1 * b.min()                         # the sensor is active: ScQGD is not a constant field
     assert rel_linf(a, b) < 1e-9 and rel_linf(ab[live], bb[live]) < 1e-9
     for f in ("mu", "alpha", "tauQGD", "T", "p"):
         x, xb = s.get(f, with_bnd=True)
