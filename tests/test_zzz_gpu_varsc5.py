@@ -1,82 +1,35 @@
 """varScModel5 on the device (varScModel5.C:52-269; qgdsolver_b200/csrc/qgd_varsc5.*) against the CPU oracle through the C ABI.
 
 Written after the round's GPU budget was spent: the per-item device code and its launch sequences are verified on CPU under a
-serial executor (tests/test_varsc5_host_cpu.py), the CUDA executor, the C-ABI plumbing and the interplay with the ordinary step
-kernels have their first device run in the driver's round-end suite.  The file sorts after every device-verified test file and
-the cases are non-strict xfail so that a first-run surprise cannot mask the verified suite; an XPASS is the parity evidence."""
-import numpy as np
+serial executor (tests/test_varsc5_host_cpu.py); the CUDA executor, the C-ABI plumbing and the interplay with the ordinary step
+kernels have their first device run in the driver's round-end suite.  Each case therefore runs in its own process
+(tests/first_run_worker.py: a crash or hang stays contained), the file sorts after every device-verified test file, and the cases
+are non-strict xfail so that a first-run surprise cannot mask the verified suite; an XPASS is the parity evidence."""
+import os
+import subprocess
+import sys
+
 import pytest
 
-import cases
-from test_gpu_parity import rel_linf
+from first_run_worker import VARSC5
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+pytestmark = pytest.mark.gpu
 first_run = pytest.mark.xfail(strict=False, reason="first device run is the driver's round-end suite (GPU budget of the round spent)")
-
-CASES = {
-    "hex_mixed": (lambda: cases.case_hex3d(n=(10, 9, 8), perturb=0.15, bcs="mixed", model="varScModel5"), 60),
-    "hex_fixed_quality_floor": (lambda: cases.case_hex3d(n=(7, 6, 5), perturb=0.2, bcs="fixed", model="varScModel5",
-                                                         varsc=dict(rC=0.35, smoothCoeff=0.15, maxAspectRatio=1.2)), 60),
-    "2d_mixed_cellset": (lambda: cases.case_2d((24, 20), perturb=0.2, bcs="mixed", model="varScModel5",
-                                               varsc=dict(const_sc_cells=np.array([3, 50, 77, 300], np.int32))), 60),
-    "truncoct_zg": (lambda: cases.case_truncoct(n=(5, 4, 4), bcs="zg", model="varScModel5", varsc=dict(smoothCoeff=0.05)), 40),
-    "prism_qgdflux_offsets": (lambda: cases.case_prism(bcs="qgdflux", model="varScModel5", gas=dict(cases.GAS, Tref=0.2, Hsref=0.1)), 60),
-    "sod_adjust": (lambda: cases.case_sod(200, model="varScModel5", adjust_time_step=True, max_co=0.2, varsc=dict(rC=0.7)), 100),
-    "hex_sutherland": (lambda: _sutherland(cases.case_hex3d(perturb=0.1, bcs="mixed", model="varScModel5", gas=dict(cases.GAS, mu=3e-3))), 40),
-    "hex_reduced_scheme": (lambda: cases.case_hex3d(perturb=0.1, bcs="mixed", model="varScModel5", scheme="reduced"), 40),
-}
+WORKER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "first_run_worker.py")
 
 
-def _sutherland(c):
-    c.sutherland = dict(As=2.5e-3, Ts=0.4)
-    return c
+def run_isolated(*args, timeout=900):
+    r = subprocess.run([sys.executable, WORKER, *args], capture_output=True, text=True, timeout=timeout)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0 and "FIRST_RUN_OK" in r.stdout, (r.stdout[-3000:] + r.stderr[-3000:])
 
 
 @first_run
-@pytest.mark.parametrize("name", list(CASES))
-def test_varsc5_steps_match_oracle(qgd, oracle_mod, name):
-    fn, n_steps = CASES[name]
-    c = fn()
-    o = c.make_oracle(oracle_mod)
-    s = c.make_solver(qgd)
-    kind = c.mesh.patch_kind_per_bface()
-    live = kind != 1
-    # start-up: QGDCoeffs::correct has run twice (thermo constructor + thermo.correct(), createFields.H:3-8)
-    a, ab = s.get("ScQGD", with_bnd=True)
-    b, bb = o.get("ScQGD", with_bnd=True)
-    assert rel_linf(a, b) < 1e-12 and rel_linf(ab[live], bb[live]) < 1e-12
-    assert rel_linf(s.get("mu"), o.get("mu")) < 1e-12
-    c.oracle_step(o, n_steps)
-    s.step(n_steps)
-    for f in ("rho", "rhoU", "rhoE"):
-        assert rel_linf(s.get(f), o.get(f)) < 1e-10, f
-    a, ab = s.get("ScQGD", with_bnd=True)
-    b, bb = o.get("ScQGD", with_bnd=True)
-    assert b.max() > 1.1 * b.min()                         # the sensor is active: ScQGD is not a constant field
-    assert rel_linf(a, b) < 1e-9 and rel_linf(ab[live], bb[live]) < 1e-9
-    for f in ("mu", "alpha", "tauQGD", "T", "p"):
-        x, xb = s.get(f, with_bnd=True)
-        y, yb = o.get(f, with_bnd=True)
-        assert rel_linf(x, y) < 1e-9, f
-        assert rel_linf(xb[live], yb[live]) < 1e-9, f + " (boundary)"
-    if c.opts["adjust_time_step"]:
-        assert abs(s.scalars()["deltaT"] - o.deltaT()) < 1e-12 * o.deltaT()
+@pytest.mark.parametrize("name", list(VARSC5))
+def test_varsc5_steps_match_oracle(name):
+    run_isolated("varsc5", name)
 
 
 @first_run
-def test_varsc5_refusals_and_bookkeeping(qgd, oracle_mod):
-    c = cases.case_hex3d(perturb=0.1, bcs="zg", model="varScModel5")
-    s = c.make_solver(qgd)
-    n0 = s.launch_count()
-    s.step(2)
-    assert s.launch_count() - n0 >= 2 * (6 + 8)             # the step kernels + the model's own pass (at least its 8 field kernels)
-    with pytest.raises(qgd.QGDError) as e:
-        s.step_fields_host(1, None, None)
-    assert e.value.code == qgd.ERR_UNSUPPORTED and "ScQGD" in e.value.message
-    with pytest.raises(qgd.QGDError) as e:
-        s.set_pipeline(1)
-    assert e.value.code == qgd.ERR_UNSUPPORTED
-    ci = cases.case_hex3d(bcs="zg", model="varScModel5", implicit=True)
-    with pytest.raises(qgd.QGDError) as e:
-        ci.make_solver(qgd)
-    assert e.value.code == qgd.ERR_UNSUPPORTED and "implicitDiffusion" in e.value.message
+def test_varsc5_refusals_and_bookkeeping():
+    run_isolated("varsc5_refusals")

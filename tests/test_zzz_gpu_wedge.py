@@ -3,71 +3,27 @@
 GaussVolPoint path on a wedge mesh whose every vertex is a patch point.
 
 Written after the round's GPU budget was spent (first device run = the driver's round-end suite; CPU-side evidence:
-tests/test_wedge_host_cpu.py, tests/test_oracle_wedge.py).  Sorted after every device-verified file, non-strict xfail."""
-import numpy as np
+tests/test_wedge_host_cpu.py, tests/test_oracle_wedge.py).  Each case runs in its own process (tests/first_run_worker.py), the
+file sorts after every device-verified file, non-strict xfail."""
 import pytest
 
-import cases
-from qgdsolver_b200 import polymesh as pm
-from test_gpu_parity import rel_linf
+from first_run_worker import WEDGE
+from test_zzz_gpu_varsc5 import first_run, run_isolated
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
-first_run = pytest.mark.xfail(strict=False, reason="first device run is the driver's round-end suite (GPU budget of the round spent)")
-
-CASES = {
-    "wedge_fixed": lambda: cases.case_wedge(n=(16, 12), bcs="fixed"),
-    "wedge_perturbed_mixed": lambda: cases.case_wedge(n=(14, 10), perturb=0.15, bcs="mixed", angle_deg=3.0),
-    "wedge_qgdflux_adjust": lambda: cases.case_wedge(n=(12, 10), bcs="qgdflux", adjust_time_step=True, max_co=0.1),
-    "wedge_reduced": lambda: cases.case_wedge(n=(12, 10), bcs="fixed", scheme="reduced"),
-    "wedge_model1n": lambda: cases.case_wedge(n=(12, 10), perturb=0.1, bcs="mixed", model="constScPrModel1n"),
-}
+pytestmark = pytest.mark.gpu
 
 
 @first_run
-@pytest.mark.parametrize("name", list(CASES))
-def test_wedge_steps_match_oracle(qgd, oracle_mod, name):
-    c = CASES[name]()
-    o = c.make_oracle(oracle_mod)
-    s = c.make_solver(qgd)
-    live = c.mesh.patch_kind_per_bface() != 1
-    a, ab = s.get("U", with_bnd=True)
-    b, bb = o.get("U", with_bnd=True)
-    assert rel_linf(ab[live], bb[live]) < 1e-14                  # U_b = faceT . U_P at start-up
-    c.oracle_step(o, 100)
-    s.step(100)
-    for f in ("rho", "rhoU", "rhoE"):
-        assert rel_linf(s.get(f), o.get(f)) < 1e-10, f
-    for f in ("U", "p", "T"):
-        x, xb = s.get(f, with_bnd=True)
-        y, yb = o.get(f, with_bnd=True)
-        assert rel_linf(xb[live], yb[live]) < 1e-10, f + " (boundary)"
-    if c.opts["adjust_time_step"]:
-        assert abs(s.scalars()["deltaT"] - o.deltaT()) < 1e-12 * o.deltaT()
+@pytest.mark.parametrize("name", list(WEDGE))
+def test_wedge_steps_match_oracle(name):
+    run_isolated("wedge", name)
 
 
 @first_run
-def test_fvsc_operators_on_a_wedge_mesh_match_oracle(qgd, oracle_mod):
-    """operator level: fvsc::grad / fvsc::div of scalar, vector and tensor fields on a wedge mesh (vertex constraint on K = 3, 9)"""
-    from test_gpu_parity import _fields
-    mesh = pm.wedge_box(9, 7, angle_deg=6.0, perturb=0.15, seed=5)
-    o = oracle_mod.Oracle(mesh)
-    st = qgd.FvscStencil(qgd.Mesh(mesh), "GaussVolPoint")
-    for k in (1, 3):
-        cell, bnd, bsg = _fields(mesh, k, 300 + k)
-        assert rel_linf(st.Grad(cell, bnd, bsg), o.fvsc_grad(cell, bnd, bsg)) < 1e-12
-    for k in (3, 9):
-        cell, bnd, bsg = _fields(mesh, k, 400 + k)
-        assert rel_linf(st.Div(cell, bnd, bsg), o.fvsc_div(cell, bnd, bsg)) < 1e-12
+def test_fvsc_operators_on_a_wedge_mesh_match_oracle():
+    run_isolated("wedge_ops")
 
 
 @first_run
-def test_wedge_refusals(qgd):
-    c = cases.case_wedge(n=(6, 5), implicit=True)
-    with pytest.raises(qgd.QGDError) as e:
-        c.make_solver(qgd)
-    assert e.value.code == qgd.ERR_UNSUPPORTED and "wedge" in e.value.message
-    c2 = cases.case_hex3d(bcs="zg")
-    c2.bcU[0] = cases.WEDGE                                      # wedge velocity on an ordinary patch
-    with pytest.raises(qgd.QGDError) as e:
-        c2.make_solver(qgd)
-    assert e.value.code == qgd.ERR_INVALID
+def test_wedge_refusals():
+    run_isolated("wedge_refusals")
