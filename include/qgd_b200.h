@@ -263,6 +263,11 @@ int qgd_qgdfoam_state_guard(qgd_solver* s, int* first_step);
  * bit-identical in both forms. */
 int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, int ring_slots);
 int qgd_qgdfoam_get_pipeline(qgd_solver* s, int* mode, int* chunk_cells, int* lag, int* ring_slots, int* n_chunks, int* grid);
+/* Opt-in, environment QGD_STEP_GRAPH=1: qgd_qgdfoam_step captures one step (all its kernels on both streams) as a CUDA graph
+ * and replays it n_steps times; the adaptive time step stays on the device, so no re-capture is needed.  Single GPU, two-kernel
+ * step form, explicit branch, not with varScModel5 (its smoothing loop is host-driven) or per-kernel profiling; other
+ * configurations silently use the stream launches.  Results are bit-identical.  Returns the steps replayed from a graph so far. */
+long long qgd_qgdfoam_graph_steps(qgd_solver* s);
 /* implicit-diffusion branch: PCG iterations of the last Ux, Uy, Uz and e solves */
 int qgd_qgdfoam_diffusion_iterations(qgd_solver* s, int iters[4]);
 /* kernel launches issued by this solver so far (bench bookkeeping) */

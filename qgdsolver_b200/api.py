@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "qgd_qgdfoam_create", "qgd_qgdfoam_destroy", "qgd_qgdfoam_set_bcs", "qgd_qgdfoam_init_fields",
     "qgd_qgdfoam_set_const_sc_cells", "qgd_qgdfoam_set_sources", "qgd_qgdfoam_step", "qgd_qgdfoam_step_host", "qgd_qgdfoam_step_fields_host", "qgd_qgdfoam_face_kernel", "qgd_qgdfoam_get", "qgd_qgdfoam_get_flux",
     "qgd_qgdfoam_get_scalars", "qgd_qgdfoam_state_guard", "qgd_qgdfoam_launch_count", "qgd_qgdfoam_profile", "qgd_qgdfoam_kernel_times",
-    "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations",
+    "qgd_qgdfoam_set_pipeline", "qgd_qgdfoam_get_pipeline", "qgd_qgdfoam_diffusion_iterations", "qgd_qgdfoam_graph_steps",
     "qgd_timer_begin", "qgd_timer_end",
     "qgd_comm_unique_id", "qgd_comm_init", "qgd_comm_finalize", "qgd_qgdfoam_set_halo", "qgd_qgdfoam_set_halo_faces",
     "qgd_pcg_solve", "qgd_pcg_solve_stepwise", "qgd_pcg_solve_multi",
@@ -137,6 +137,8 @@ def load_library():
     L.qgd_qgdfoam_get_flux.argtypes = [C.c_void_p, C.c_int, _dp]
     L.qgd_qgdfoam_get_scalars.argtypes = [C.c_void_p, _dp, _dp, _dp]
     L.qgd_qgdfoam_state_guard.argtypes = [C.c_void_p, _ip]
+    L.qgd_qgdfoam_graph_steps.restype = C.c_longlong
+    L.qgd_qgdfoam_graph_steps.argtypes = [C.c_void_p]
     L.qgd_qgdfoam_launch_count.restype = C.c_longlong
     L.qgd_qgdfoam_launch_count.argtypes = [C.c_void_p]
     L.qgd_qgdfoam_profile.argtypes = [C.c_void_p, C.c_int]
@@ -502,6 +504,10 @@ class QGDFoam:
         it = (C.c_int * 4)()
         _check(load_library().qgd_qgdfoam_diffusion_iterations(self._h, it))
         return list(it)
+
+    def graph_steps(self) -> int:
+        """steps replayed from a captured CUDA graph so far (QGD_STEP_GRAPH=1)"""
+        return int(load_library().qgd_qgdfoam_graph_steps(self._h))
 
     def launch_count(self) -> int:
         return int(load_library().qgd_qgdfoam_launch_count(self._h))

@@ -118,6 +118,7 @@ struct qgd_solver {
     }
     DevBuf<double> su;               // [5][nCells] explicit sources (qgd_qgdfoam_set_sources) or empty
     int stepsDone = 0;
+    long long graphSteps = 0;        // steps replayed from a captured CUDA graph (QGD_STEP_GRAPH=1)
     // implicit-diffusion branch
     struct Implicit {
         DevBuf<double> GU0, GU1, old, FT, aU, aE, Fs, diagU, bU, diagE, bE;
@@ -659,6 +660,56 @@ void runSteps(qgd_solver* s, int n)
     const bool useFork = (multi ? g_bndFork == 2 : g_bndFork != 0) && g_sideStream && h_nB(s) > 0 && !s->anyQgdFlux && !model5 &&
                          !(s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc);
     const WedgeView wedge{(int)s->mesh->h.wedgePts.size(), s->mesh->wedgePts.p, s->mesh->wedgeN.p};
+    // ---- opt-in (QGD_STEP_GRAPH=1): the step as a CUDA graph.  One step is captured from the very launch sequence below (side
+    // stream included: it joins the capture through evEntry and is joined back before the capture ends) and replayed n times; the
+    // time-step control lives on the device (k_dt), so adaptive deltaT needs no re-capture.  Single GPU, two-kernel step form, no
+    // per-kernel profiling events; constScPrModel1n takes its first step (tauMode 2) outside the graph.
+    int i0 = 0;
+    {
+        const char* gv = getenv("QGD_STEP_GRAPH");
+        const bool wantGraph = gv && atoi(gv) != 0 && !multi && !model5 && !s->profiling && s->pipe.mode == 0 && n >= 2;
+        if (wantGraph) {
+            if (s->k.model == 1 && s->stepsDone == 0) {             // the first correct() of constScPrModel1n differs (constScPrModel1n.C:102-129)
+                s->k.tauMode = 2;
+                ++s->stepsDone;
+                s->launches += launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, nullptr,
+                                          nullptr, nullptr, 0, useFork ? &fork : nullptr, wedge.n ? &wedge : nullptr);
+                if (useFork && fork.postOnSide) QGD_CUDA(cudaStreamWaitEvent(g_stream, fork.evBndPost, 0));
+                i0 = 1;
+            }
+            if (s->k.model == 1) s->k.tauMode = 1;
+            warmFaceKernel(s->desc.adjust_time_step != 0);             // kernel attributes / occupancy query: not inside a capture
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            QGD_CUDA(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+            int perStep = 0;
+            try {
+                perStep = launchStep(g_stream, s->k, fv, sv, bs, s->anyQgdFlux, s->gridFaces, s->desc.adjust_time_step != 0, nullptr,
+                                     nullptr, nullptr, 0, useFork ? &fork : nullptr, wedge.n ? &wedge : nullptr);
+                if (useFork && fork.postOnSide) QGD_CUDA(cudaStreamWaitEvent(g_stream, fork.evBndPost, 0));
+            } catch (...) {
+                cudaStreamEndCapture(g_stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            QGD_CUDA(cudaStreamEndCapture(g_stream, &graph));
+            cudaError_t ge = cudaGraphInstantiate(&exec, graph, 0);
+            if (ge != cudaSuccess) { cudaGraphDestroy(graph); QGD_CUDA(ge); }
+            for (int i = i0; i < n; ++i) {
+                ge = cudaGraphLaunch(exec, g_stream);
+                if (ge != cudaSuccess) break;
+                ++s->stepsDone;
+                s->launches += perStep;
+            }
+            if (ge == cudaSuccess) ge = cudaStreamSynchronize(g_stream);     // the executable graph must outlive its launches
+            cudaGraphExecDestroy(exec);
+            cudaGraphDestroy(graph);
+            QGD_CUDA(ge);
+            QGD_CUDA(cudaGetLastError());
+            s->graphSteps += n - i0;
+            return;
+        }
+    }
     for (int i = 0; i < n; ++i) {
         cudaEvent_t* ev = nullptr;
         if (s->profiling) {
@@ -1543,6 +1594,8 @@ int qgd_qgdfoam_set_pipeline(qgd_solver* s, int mode, int chunk_cells, int lag, 
         configurePipeline(s, mode, chunk_cells, lag, ring_slots);
     });
 }
+
+long long qgd_qgdfoam_graph_steps(qgd_solver* s) { return s ? s->graphSteps : 0; }
 
 int qgd_qgdfoam_get_pipeline(qgd_solver* s, int* mode, int* chunk_cells, int* lag, int* ring_slots, int* n_chunks, int* grid)
 {

@@ -1682,6 +1682,7 @@ int faceTmaGrid(bool adjust)
 }
 }
 
+void warmFaceKernel(bool adjust) { (void)faceTmaGrid(adjust); }
 void setFaceTma(int on) { g_faceTma = on ? 1 : 0; }
 void setFaceL2Hint(int bits) { g_faceHint = bits & 3; }
 

@@ -173,6 +173,7 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
 int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                         const ImplicitView& iv, bool anyQgdFlux, int gridFaces, bool adjust, const StepHooks* hooks = nullptr);
 int faceKernelGrid();
+void warmFaceKernel(bool adjust);   // sets the TMA face kernel's attributes / grid once (must not happen inside a stream capture)
 int pipelineKernelGrid(int cfEllW);
 void setFaceL2Hint(int bits); // env QGD_FACE_L2HINT: bit 0 = streamed constants / fluxes evict_first, bit 1 = state gathers evict_last
 void setFaceTma(int on);      // env QGD_FACE_TMA: TMA-staged face kernel (default) vs register-prefetch kernel

@@ -154,6 +154,53 @@ def run_wedge_refusals(qgd, O):
     refused(lambda: c2.make_solver(qgd), qgd.ERR_INVALID, "wedge")
 
 
+GRAPH = {
+    "hex_zg_forked_boundary_stream": lambda: cases.case_hex3d(n=(12, 10, 9), perturb=0.1, bcs="zg"),
+    "hex_mixed_qgdflux": lambda: cases.case_hex3d(perturb=0.2, bcs="mixed"),
+    "2d_adjust_dt": lambda: cases.case_2d(perturb=0.1, bcs="fixed", adjust_time_step=True, max_co=0.1),
+    "prism_model1n": lambda: cases.case_prism(bcs="fixed", model="constScPrModel1n"),
+    "hex_varSc7": lambda: cases.case_hex3d(perturb=0.1, bcs="fixed", model="varScModel7", varsc=dict(cSc1=3.0, minSc=0.02, maxSc=0.4)),
+    "forward_step_slip": lambda: cases.case_forward_step(n=30),
+    "sod_leastSquares": lambda: cases.case_sod(200, scheme="leastSquares"),
+}
+
+
+def run_graph(qgd, O, name):
+    """QGD_STEP_GRAPH=1: the captured-and-replayed step must give bit-identical fields to the stream launches"""
+    n = 40
+    os.environ.pop("QGD_STEP_GRAPH", None)
+    c = GRAPH[name]()
+    s1 = c.make_solver(qgd)
+    l0 = s1.launch_count()
+    s1.step(n)
+    l1 = s1.launch_count() - l0
+    check(s1.graph_steps() == 0, "graph used without the switch")
+    os.environ["QGD_STEP_GRAPH"] = "1"
+    try:
+        s2 = c.make_solver(qgd)
+        l0 = s2.launch_count()
+        s2.step(n)
+        l2 = s2.launch_count() - l0
+        first_outside = 1 if c.model == "constScPrModel1n" else 0
+        check(s2.graph_steps() == n - first_outside, f"graph steps {s2.graph_steps()}")
+        s2.step(1)                                   # a single step takes the stream path again
+        s1.step(1)
+    finally:
+        os.environ.pop("QGD_STEP_GRAPH", None)
+    check(l1 == l2, f"kernel launches per {n} steps differ: {l1} vs {l2}")
+    for f in ("rho", "rhoU", "rhoE", "p", "T", "mu"):
+        a, ab = s1.get(f, with_bnd=True)
+        b, bb = s2.get(f, with_bnd=True)
+        check(np.array_equal(a, b) and np.array_equal(ab, bb), f + " differs between graph replay and stream launches")
+    check(s1.scalars() == s2.scalars(), "time-step scalars differ")
+    o = c.make_oracle(O)
+    c.oracle_step(o, n + 1)
+    for f in ("rho", "rhoU", "rhoE"):
+        e = rel_linf(s2.get(f), o.get(f))
+        print(f"graph {name} steps={n + 1} {f} relLinf vs oracle={e:.3e}")
+        check(e < 1e-10, f)
+
+
 def main():
     kind = sys.argv[1]
     name = sys.argv[2] if len(sys.argv) > 2 else None
@@ -164,7 +211,7 @@ def main():
     api.init(0)
     {"varsc5": lambda: run_varsc5(api, O, name), "varsc5_refusals": lambda: run_varsc5_refusals(api, O),
      "wedge": lambda: run_wedge(api, O, name), "wedge_ops": lambda: run_wedge_ops(api, O),
-     "wedge_refusals": lambda: run_wedge_refusals(api, O)}[kind]()
+     "wedge_refusals": lambda: run_wedge_refusals(api, O), "graph": lambda: run_graph(api, O, name)}[kind]()
     print("FIRST_RUN_OK", kind, name or "")
 
 
