@@ -181,7 +181,7 @@ typedef struct {
     /* QGD sub-dictionary entries of varScModel5 (varScModel5.C:61-110), read only when qgd_coeffs_model is "varScModel5":
      * smoothCoeff (0.1), rC (0.5), badQualitySc (0.05), maxAspectRatio (1.5); its minSc (0.05) / maxSc (1.0) travel in
      * varsc_minSc / varsc_maxSc above.  The shim passes the dictionary value or the default given in brackets.
-     * varScModel5 on the device: explicit branch, serial mesh; ScQGD = rC |grad(psi p)| hQGD / (psi p) + (1 - rC) ScQGD, clamped,
+     * varScModel5 on the device: explicit and implicit-diffusion branch, serial mesh; ScQGD = rC |grad(psi p)| hQGD / (psi p) + (1 - rC) ScQGD, clamped,
      * floored by the cellClosedness aspect-ratio value, smoothed with fvc::smooth (FaceCellWave, reference visiting order). */
     double varsc5_smoothCoeff, varsc5_rC, varsc5_badQualitySc, varsc5_maxAspectRatio;
 } qgd_qgdfoam_desc;

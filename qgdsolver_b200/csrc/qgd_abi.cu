@@ -552,6 +552,13 @@ void runStepsImplicit(qgd_solver* s, int n)
     const int maxIter = s->desc.diff_max_iter > 0 ? s->desc.diff_max_iter : 1000;
     StepHooks hooks;
     PcgHooks ph;
+    const bool model5 = (bool)s->v5;
+    if (model5)        // varScModel5 reads the p_b the closing correctBoundaryConditions() is about to replace (varScModel5.C:255-263)
+        hooks.beforeBndPost = [s] {
+            if (s->mesh->h.nBnd)
+                QGD_CUDA(cudaMemcpyAsync(s->v5->pOldB.p, s->pNew.p, (size_t)s->mesh->h.nBnd * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+        };
+    const StepHooks* hp = (multi || model5) ? &hooks : nullptr;
     if (multi) {
         hooks.midStep = [s] { s->launches += haloExchangeMid(s); };
         hooks.afterGrad = [s, nC](double* G) { s->launches += commExchange(s->haloFace, G, nC, 9, g_stream); };
@@ -582,15 +589,18 @@ void runStepsImplicit(qgd_solver* s, int n)
     for (int i = 0; i < n; ++i) {
         if (s->k.model == 1) s->k.tauMode = s->stepsDone == 0 ? 2 : 1;
         ++s->stepsDone;
-        s->launches += launchImplicitPhase(g_stream, 0, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, multi ? &hooks : nullptr);
+        s->launches += launchImplicitPhase(g_stream, 0, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, hp);
         I.AU.refresh(iv.aU, iv.diagU, g_stream);
         for (int j = 0; j < 3; ++j) solveSys(I.AU, iv.bU + j * nC, s->S.p + (1 + j) * nC, j);      // QGDUEqn.H:65-68, segregated components
         if (multi) s->launches += commExchange(s->haloFace, s->S.p + nC, nC, 3, g_stream);          // solved U of the face neighbours
-        s->launches += 2 + launchImplicitPhase(g_stream, 1, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, multi ? &hooks : nullptr);
+        s->launches += 2 + launchImplicitPhase(g_stream, 1, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, hp);
         I.AE.refresh(iv.aE, iv.diagE, g_stream);
         s->launches += 2;
         solveSys(I.AE, iv.bE, s->S.p + 4 * nC, 3);                                                 // QGDEEqn.H:55-61
-        s->launches += launchImplicitPhase(g_stream, 2, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, multi ? &hooks : nullptr);
+        if (model5)    // the pressure of the old step (p is rewritten by the closing cell kernel of phase 2)
+            QGD_CUDA(cudaMemcpyAsync(s->v5->pOld.p, s->S.p + 5 * nC, nC * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
+        s->launches += launchImplicitPhase(g_stream, 2, s->k, fv, sv, bs, iv, s->anyQgdFlux, s->gridFaces, adjust, hp);
+        if (model5) s->launches += s->v5->correct(s->v5view(), g_stream);      // varScModel5::correct on the closed state
         if (multi) s->launches += haloExchange(s);
     }
     QGD_CUDA(cudaGetLastError());
@@ -1149,8 +1159,6 @@ int qgd_qgdfoam_create(qgd_mesh* mesh, const qgd_qgdfoam_desc* d, qgd_solver** o
             model != "varScModel6" && model != "varScModel7")
             throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is a QHDFoam model: it is not available in QGDFoam");
         if (model == "varScModel5") {
-            if (d->implicit_diffusion)
-                throw Error(QGD_ERR_UNSUPPORTED, "varScModel5 with implicitDiffusion true is not available on the device (explicit branch only)");
             if (mesh->h.nOwned != mesh->h.nCells)
                 throw Error(QGD_ERR_UNSUPPORTED, "varScModel5 on extended sub-meshes (multi-GPU) is not available: fvc::smooth crosses processor "
                                                  "patches inside FaceCellWave");

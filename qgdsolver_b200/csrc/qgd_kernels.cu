@@ -1921,6 +1921,7 @@ int launchImplicitPhase(cudaStream_t st, int phase, const Consts& c, const FaceV
     } else {                   // after the e solve: conserved variables, thermo, boundary state
         if (c.varSc) { k_varsc<false><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, sv.S + 5 * (size_t)sv.nCells); ++n; }
         k_cell_implC<<<nblk(sv.nOwned), kBlock, 0, st>>>(c, sv); ++n;
+        if (hooks && hooks->beforeBndPost) hooks->beforeBndPost();
         if (fv.nB) { k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n; }
     }
     return n;

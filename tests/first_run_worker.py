@@ -38,6 +38,11 @@ VARSC5 = {
     "sod_adjust": (lambda: cases.case_sod(200, model="varScModel5", adjust_time_step=True, max_co=0.2, varsc=dict(rC=0.7)), 100),
     "hex_sutherland": (lambda: _sutherland(cases.case_hex3d(perturb=0.1, bcs="mixed", model="varScModel5", gas=dict(cases.GAS, mu=3e-3))), 40),
     "hex_reduced_scheme": (lambda: cases.case_hex3d(perturb=0.1, bcs="mixed", model="varScModel5", scheme="reduced"), 40),
+    # implicitDiffusion true (the reference's default): the model's pass follows the closing phase of the implicit step
+    "prism_implicit": (lambda: cases.case_prism(bcs="fixed", model="varScModel5", implicit=True), 40),
+    "2d_implicit_qgdflux_adjust": (lambda: cases.case_2d(perturb=0.1, bcs="qgdflux", model="varScModel5", implicit=True,
+                                                         adjust_time_step=True, max_co=0.1,
+                                                         varsc=dict(rC=0.9, minSc=0.002, smoothCoeff=0.3)), 40),
 }
 
 WEDGE = {
@@ -97,7 +102,6 @@ def run_varsc5_refusals(qgd, O):
         raise AssertionError("not refused")
     refused(lambda: s.step_fields_host(1, None, None), qgd.ERR_UNSUPPORTED, "ScQGD")
     refused(lambda: s.set_pipeline(1), qgd.ERR_UNSUPPORTED, "varScModel5")
-    refused(lambda: cases.case_hex3d(bcs="zg", model="varScModel5", implicit=True).make_solver(qgd), qgd.ERR_UNSUPPORTED, "implicitDiffusion")
 
 
 def run_wedge(qgd, O, name):

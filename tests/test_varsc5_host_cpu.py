@@ -90,7 +90,8 @@ def test_quality_floor_matches_the_oracle(shim, oracle_mod, name):
     lambda: cases.case_hex3d(n=(6, 6, 5), perturb=0.1, bcs="mixed", model="varScModel5", gas=cases.GAS_OFFSET, dt=1e-6),
     lambda: cases.case_2d((12, 10), perturb=0.2, bcs="mixed", model="varScModel5", varsc=dict(const_sc_cells=np.array([3, 50, 77], np.int32))),
     lambda: cases.case_truncoct(n=(4, 3, 3), bcs="zg", model="varScModel5", varsc=dict(smoothCoeff=0.05)),
-], ids=["hex_fixed", "hex_mixed_offsets", "2d_mixed_cellset", "truncoct"])
+    lambda: cases.case_prism(bcs="fixed", model="varScModel5", implicit=True),
+], ids=["hex_fixed", "hex_mixed_offsets", "2d_mixed_cellset", "truncoct", "prism_implicit"])
 def test_device_form_of_the_whole_correct_matches_the_oracle(shim, oracle_mod, case_fn):
     """state before / after one oracle step -> the inputs the device pass sees (T, c and boundary state closed by the ordinary
     kernels, old p and p_b, old ScQGD) -> v5Correct -> ScQGD, mu, alphaEff and the tau slot against the oracle's fields"""
