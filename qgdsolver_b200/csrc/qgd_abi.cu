@@ -1349,7 +1349,8 @@ int qgd_qgdfoam_init_fields(qgd_solver* s, const double* U, const double* T, con
         }
         if (alphaQGD) QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, alphaQGD, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         else { std::vector<double> a(n, 0.5); QGD_CUDA(cudaMemcpyAsync(s->aQGD.p, a.data(), n * sizeof(double), cudaMemcpyHostToDevice, g_stream)); QGD_CUDA(cudaStreamSynchronize(g_stream)); }
-        launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), s->stage.p, s->stage.p + 3 * n, s->stage.p + 4 * n);
+        launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), s->stage.p, s->stage.p + 3 * n, s->stage.p + 4 * n,
+                   !h.wedgePts.empty());
         if (s->v5) varSc5Init(s);
         if (s->halo.active) s->launches += haloExchange(s);
         QGD_CUDA(cudaStreamSynchronize(g_stream));
@@ -1418,7 +1419,7 @@ int qgd_qgdfoam_step_fields_host(qgd_solver* s, int n_steps, const qgd_fields_ho
             QGD_CUDA(cudaMemcpyAsync(st + 3 * n, in->T, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
             QGD_CUDA(cudaMemcpyAsync(st + 4 * n, in->p, n * sizeof(double), cudaMemcpyHostToDevice, g_stream));
             if (s->k.model == 1) { s->k.tauMode = 2; s->stepsDone = 0; }       // "U" is registered after the first correct() again
-            launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), st, st + 3 * n, st + 4 * n);
+            launchInit(g_stream, s->k, s->fvsc->view(), s->sview(), s->bview(), st, st + 3 * n, st + 4 * n, !s->mesh->h.wedgePts.empty());
             s->launches += 2 + (s->k.varSc ? 1 : 0);
             if (s->halo.active) s->launches += haloExchange(s);
         }

@@ -1198,14 +1198,6 @@ __device__ __forceinline__ void bndClose(const Consts& k, const FaceView& fv, co
         const double un = n[0] * U[0] + n[1] * U[1] + n[2] * U[2];
 #pragma unroll
         for (int j = 0; j < 3; ++j) U[j] = U[j] - n[j] * un;
-    } else if (bs.bcU[b] == QGD_BC_WEDGE) {     // [OF-v2312 wedgeFvPatchField::evaluate] U_b = transform(faceT, U_P)
-        const double ms = fv.magSf[f];
-        const double n[3] = {fv.Sf[f] / ms, fv.Sf[(size_t)fv.fs + f] / ms, fv.Sf[2 * (size_t)fv.fs + f] / ms};
-        double Tw[9];
-        wedgeFaceT(n, Tw);
-        const double u0 = U[0], u1 = U[1], u2 = U[2];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) U[j] = Tw[3 * j] * u0 + Tw[3 * j + 1] * u1 + Tw[3 * j + 2] * u2;
     }
     double T, e;
     if (fixT) { T = bs.bvT[b]; e = thermoEs(k, T); }                     // fixedEnergy ; hePsiQGDThermo.C:93-105
@@ -1253,6 +1245,33 @@ __global__ void k_bnd_post(Consts k, FaceView fv, SolverView sv, BndState bs)
     const int P = fv.own[fv.nI + b];
     if (P >= sv.nOwned) return;
     bndClose(k, fv, sv, bs, b, false, loadA(sv, P), sv.aQGD[P]);
+}
+
+// wedge velocity condition [OF-v2312 wedgeFvPatchField::evaluate]: U_b = transform(faceT, U_P).  bndClose has just closed the face
+// like a zeroGradient one (U_b = U_P, rhoU_b = rho_b U_P); the condition is a rotation, so it is applied to the two stored vectors
+// afterwards (|U| and with it rhoE_b, H_b are unchanged) - the closing kernels themselves stay as they are.
+__global__ void k_wedge_bnd(FaceView fv, SolverView sv, BndState bs)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= fv.nB) return;
+    if (fv.bKind[b] != QGD_PATCH_WEDGE || bs.bcU[b] != QGD_BC_WEDGE) return;
+    const int f = fv.nI + b;
+    if (fv.own[f] >= sv.nOwned) return;
+    const double ms = fv.magSf[f];
+    const double n[3] = {fv.Sf[f] / ms, fv.Sf[(size_t)fv.fs + f] / ms, fv.Sf[2 * (size_t)fv.fs + f] / ms};
+    double Tw[9];
+    wedgeFaceT(n, Tw);
+    RecA a = bs.A[b];
+    RecB bb = bs.B[b];
+    const double u[3] = {a.Ux, a.Uy, a.Uz}, r[3] = {bb.rhoUx, bb.rhoUy, bb.rhoUz};
+    a.Ux = Tw[0] * u[0] + Tw[1] * u[1] + Tw[2] * u[2];
+    a.Uy = Tw[3] * u[0] + Tw[4] * u[1] + Tw[5] * u[2];
+    a.Uz = Tw[6] * u[0] + Tw[7] * u[1] + Tw[8] * u[2];
+    bb.rhoUx = Tw[0] * r[0] + Tw[1] * r[1] + Tw[2] * r[2];
+    bb.rhoUy = Tw[3] * r[0] + Tw[4] * r[1] + Tw[5] * r[2];
+    bb.rhoUz = Tw[6] * r[0] + Tw[7] * r[1] + Tw[8] * r[2];
+    bs.A[b] = a;
+    bs.B[b] = bb;
 }
 
 // ---- initialisation: QGDFoam/createFields.H:3-87 on the device
@@ -1735,11 +1754,12 @@ void launchFvscDiv(cudaStream_t st, int K, const FaceView& fv, const double* cel
 }
 
 void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-                const double* U0, const double* T0, const double* p0)
+                const double* U0, const double* T0, const double* p0, bool wedge)
 {
     if (c.varSc) k_varsc<true><<<nblk(sv.nOwned), kBlock, 0, st>>>(c, fv, sv, bs, p0);
     k_init_cells<<<nblk(sv.nCells), kBlock, 0, st>>>(c, sv, U0, T0, p0);
     if (fv.nB) k_init_bnd<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs, T0);
+    if (fv.nB && wedge) k_wedge_bnd<<<nblk(fv.nB), kBlock, 0, st>>>(fv, sv, bs);
     QGD_CUDA(cudaGetLastError());
 }
 
@@ -1873,9 +1893,11 @@ int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const Solve
             cudaEventRecord(fork->evCell, st);
             cudaStreamWaitEvent(sb, fork->evCell, 0);
             k_bnd_post<<<nblk(fv.nB), kBlock, 0, sb>>>(c, fv, sv, bs); ++n;
+            if (wedge && wedge->n) { k_wedge_bnd<<<nblk(fv.nB), kBlock, 0, sb>>>(fv, sv, bs); ++n; }
             cudaEventRecord(fork->evBndPost, sb);
         } else {
             k_bnd_post<<<nblk(fv.nB), kBlock, 0, st>>>(c, fv, sv, bs); ++n;
+            if (wedge && wedge->n) { k_wedge_bnd<<<nblk(fv.nB), kBlock, 0, st>>>(fv, sv, bs); ++n; }
         }
     }
     return n;

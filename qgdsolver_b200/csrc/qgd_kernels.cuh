@@ -142,8 +142,9 @@ struct PipeView {
     int* queue;              // work-item counter, reset by k_dt
 };
 
+// wedge: the mesh has wedge patches (the wedge velocity condition is applied to the closed boundary state, k_wedge_bnd)
 void launchInit(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
-                const double* U0, const double* T0, const double* p0);
+                const double* U0, const double* T0, const double* p0, bool wedge = false);
 // one QGDFoam.C:90-163 loop body; returns number of kernel launches issued
 // ev (optional): 6 events recorded around k_points, k_face_flux, k_cell_update (begin/end pairs)
 // hooks (optional, multi-GPU): midStep runs after the qgdFlux re-evaluation of p_b (exchange of halo p_b),

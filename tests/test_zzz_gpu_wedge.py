@@ -1,5 +1,5 @@
 """Axisymmetric (wedge) QGDFoam cases on the device against the CPU oracle through the C ABI: the wedge velocity condition
-(QGD_BC_WEDGE, k_bnd_post / k_init_bnd), the wedge vertex constraint (k_wedge_points, k_wedge_points_generic) and the 2D
+(QGD_BC_WEDGE, k_wedge_bnd), the wedge vertex constraint (k_wedge_points, k_wedge_points_generic) and the 2D
 GaussVolPoint path on a wedge mesh whose every vertex is a patch point.
 
 Written after the round's GPU budget was spent (first device run = the driver's round-end suite; CPU-side evidence:
