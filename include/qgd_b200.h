@@ -145,7 +145,12 @@ int qgd_fvsc_div(qgd_fvsc* op, int ncmpt, const double* cell, const double* bnd,
  * Dictionary content the reference reads: thermophysicalProperties (thermoType hePsiQGDThermo /
  * pureMixture / const / hConst / perfectGas / sensibleInternalEnergy, psiQGDThermos.C:65-111),
  * its QGD sub-dictionary (QGDThermo.C:48-82, QGDCoeffs.C:58-117, constScPrModel1.C:58-89),
- * fvSchemes::fvsc, controlDict (QGDCourantNo.H:36, setDeltaT-QGDQHD.H:41-58). */
+ * fvSchemes::fvsc, controlDict (QGDCourantNo.H:36, setDeltaT-QGDQHD.H:41-58).
+ * fvSchemes assumed by the fused face kernels: ddt Euler, grad Gauss linear, interpolationSchemes linear (or default none)
+ * and divSchemes none | Gauss linear - the branches of qgdInterpolate / qgdFlux<T> (QGDInterpolate.H:38-118) that return
+ * linearInterpolate(psi) and flux*psif, or fvc::interpolate / fvc::flux with the `linear` scheme, which give the same values.
+ * Any other interpolation or convection scheme (upwind, limited ...) needs OpenFOAM's scheme objects and a registered flux
+ * field; the shim must refuse such an fvSchemes (qgdsolver_b200/runcase.py does), it cannot be expressed through this ABI. */
 typedef struct {
     const char* fvsc_scheme;        /* fvSchemes::fvsc::default                                     */
     const char* qgd_coeffs_model;   /* QGD::QGDCoeffs : "constScPrModel1" | "constScPrModel1n" | "constScPrModel2" |
