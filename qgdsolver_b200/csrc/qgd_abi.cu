@@ -837,6 +837,10 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
     std::vector<double> G, hd;
     mesh->h.buildFaceRecords(op.reduced, vtx, flags, G, hd);
     const int nF = mesh->h.nFaces;
+    if (op.lsq)      // leastSquares leaves the faces of constraint patches at zero (extendedFaceStencilScalarGrad.C:86-109: empty, wedge, coupled ...)
+        for (int b = 0; b < mesh->h.nBnd; ++b)
+            if (mesh->h.patchKind[mesh->h.bfacePatch[b]] == QGD_PATCH_WEDGE)
+                for (int k = 6; k < 9; ++k) G[(size_t)k * nF + mesh->h.nInternal + b] = 0.0;
     const std::vector<int>& perm = mesh->facePerm;
     std::vector<int4> v4(nF);
     std::vector<int> fl(nF);
@@ -1307,6 +1311,9 @@ int qgd_qgdfoam_set_bcs(qgd_solver* s, const int* bc_U, const int* bc_T, const i
                 if (h.patchKind[pi] != QGD_PATCH_WEDGE) throw Error(QGD_ERR_INVALID, "wedge velocity condition on a patch that is not a wedge patch");
                 if (s->k.implicit) throw Error(QGD_ERR_UNSUPPORTED, "wedge patches with implicitDiffusion true are not available (explicit branch only)");
                 if (h.nOwned != h.nCells) throw Error(QGD_ERR_UNSUPPORTED, "wedge patches on extended sub-meshes (multi-GPU) are not available");
+                // `reduced` keeps nf*snGrad on wedge faces too (reducedFaceNormalStencil.C:69-108), with the wedge patch's own snGrad
+                // (cellT . U_P - U_P) deltaCoeffs / 2, which the fused boundary kernels do not form; the operator-level calls take it from the caller
+                if (s->fvsc->reduced && !s->fvsc->lsq) throw Error(QGD_ERR_UNSUPPORTED, "wedge patches with the fvsc scheme `reduced` are not available in the solver step (GaussVolPoint / leastSquares only)");
             }
             if (t[b] != QGD_BC_FIXED_VALUE && t[b] != QGD_BC_ZERO_GRADIENT)
                 throw Error(QGD_ERR_UNSUPPORTED, "T boundary condition outside the device-native set (fixedValue, zeroGradient)");

@@ -49,7 +49,7 @@ WEDGE = {
     "wedge_fixed": lambda: cases.case_wedge(n=(16, 12), bcs="fixed"),
     "wedge_perturbed_mixed": lambda: cases.case_wedge(n=(14, 10), perturb=0.15, bcs="mixed", angle_deg=3.0),
     "wedge_qgdflux_adjust": lambda: cases.case_wedge(n=(12, 10), bcs="qgdflux", adjust_time_step=True, max_co=0.1),
-    "wedge_reduced": lambda: cases.case_wedge(n=(12, 10), bcs="fixed", scheme="reduced"),
+    "wedge_leastSquares": lambda: cases.case_wedge(n=(12, 10), bcs="fixed", scheme="leastSquares"),
     "wedge_model1n": lambda: cases.case_wedge(n=(12, 10), perturb=0.1, bcs="mixed", model="constScPrModel1n"),
 }
 
@@ -131,17 +131,21 @@ def run_wedge_ops(qgd, O):
     from test_gpu_parity import _fields
     mesh = pm.wedge_box(9, 7, angle_deg=6.0, perturb=0.15, seed=5)
     o = O.Oracle(mesh)
-    st = qgd.FvscStencil(qgd.Mesh(mesh), "GaussVolPoint")
-    for k in (1, 3):
-        cell, bnd, bsg = _fields(mesh, k, 300 + k)
-        e = rel_linf(st.Grad(cell, bnd, bsg), o.fvsc_grad(cell, bnd, bsg))
-        print(f"wedge ops grad k={k} relLinf={e:.3e}")
-        check(e < 1e-12, f"grad k={k}")
-    for k in (3, 9):
-        cell, bnd, bsg = _fields(mesh, k, 400 + k)
-        e = rel_linf(st.Div(cell, bnd, bsg), o.fvsc_div(cell, bnd, bsg))
-        print(f"wedge ops div k={k} relLinf={e:.3e}")
-        check(e < 1e-12, f"div k={k}")
+    dm = qgd.Mesh(mesh)
+    # GaussVolPoint: no derivative on wedge faces; reduced: nf*snGrad there too; leastSquares: constraint patches stay zero
+    for scheme in ("GaussVolPoint", "reduced", "leastSquares"):
+        st = qgd.FvscStencil(dm, scheme)
+        osch = O.FVSC_SCHEMES[scheme]
+        for k in (1, 3):
+            cell, bnd, bsg = _fields(mesh, k, 300 + k)
+            e = rel_linf(st.Grad(cell, bnd, bsg), o.fvsc_grad(cell, bnd, bsg, scheme=osch))
+            print(f"wedge ops {scheme} grad k={k} relLinf={e:.3e}")
+            check(e < 1e-12, f"{scheme} grad k={k}")
+        for k in (3, 9):
+            cell, bnd, bsg = _fields(mesh, k, 400 + k)
+            e = rel_linf(st.Div(cell, bnd, bsg), o.fvsc_div(cell, bnd, bsg, scheme=osch))
+            print(f"wedge ops {scheme} div k={k} relLinf={e:.3e}")
+            check(e < 1e-12, f"{scheme} div k={k}")
 
 
 def run_wedge_refusals(qgd, O):
@@ -153,6 +157,7 @@ def run_wedge_refusals(qgd, O):
             return
         raise AssertionError("not refused")
     refused(lambda: cases.case_wedge(n=(6, 5), implicit=True).make_solver(qgd), qgd.ERR_UNSUPPORTED, "wedge")
+    refused(lambda: cases.case_wedge(n=(6, 5), scheme="reduced").make_solver(qgd), qgd.ERR_UNSUPPORTED, "reduced")
     c2 = cases.case_hex3d(bcs="zg")
     c2.bcU[0] = cases.WEDGE                                      # wedge velocity on an ordinary patch
     refused(lambda: c2.make_solver(qgd), qgd.ERR_INVALID, "wedge")

@@ -90,6 +90,7 @@ MESHES = {
     "2d_x": lambda: cases.case_2d((9, 8), perturb=0.2, axis=0).mesh,
     "1d": lambda: cases.case_sod(30).mesh,
     "forward_step": lambda: cases.pm.forward_step(10),
+    "wedge": lambda: cases.pm.wedge_box(8, 6, angle_deg=6.0, perturb=0.15, seed=4),      # every vertex is a patch point, wedge faces get no derivative
 }
 
 
@@ -242,7 +243,10 @@ def test_cell_difference_vector_of_every_record_is_parallel_to_sf(shim, name, re
     for mesh in meshes:
         _, flags, G, _ = Host(shim, mesh).records(reduced)
         keep = np.ones(mesh.n_faces, bool)
-        keep[mesh.n_internal:] = mesh.patch_kind_per_bface() != 1
+        kind = mesh.patch_kind_per_bface()
+        keep[mesh.n_internal:] = (kind != 1) & (kind != 3)          # empty faces carry nothing, wedge faces get no derivative (record = 0)
+        if not reduced:     # `reduced` keeps nf*snGrad on wedge faces (reducedFaceNormalStencil.C:69-108), GaussVolPoint nothing (GaussVolPointBase2D.C:175-179)
+            assert np.abs(G[:, mesh.n_internal:][:, kind == 3]).max(initial=0.0) == 0.0
         GP, S = G[6:9].T[keep], mesh.Sf[keep]
         s = (GP * S).sum(1) / (S * S).sum(1)
         assert np.abs(GP - s[:, None] * S).max() <= 1e-12 * np.abs(GP).max()
