@@ -36,7 +36,12 @@ typedef enum {
 /* polyPatch kinds the path distinguishes (emptyFvPatch, wedgeFvPatch,
  * processorFvPatch tests at QGDCoeffs.C:346-348, GaussVolPointBase2D.C:175-199,
  * GaussVolPointBase3D.C:76-79) */
-typedef enum { QGD_PATCH_GENERIC = 0, QGD_PATCH_EMPTY = 1, QGD_PATCH_PROCESSOR = 2, QGD_PATCH_WEDGE = 3 } qgd_patch_kind;
+typedef enum { QGD_PATCH_GENERIC = 0, QGD_PATCH_EMPTY = 1, QGD_PATCH_PROCESSOR = 2, QGD_PATCH_WEDGE = 3,
+               QGD_PATCH_SYMMETRY_PLANE = 4   /* polyPatch type symmetryPlane: an ordinary patch for the face derivatives and length
+                                                 scales; its vertices are constrained like those of wedge patches [OF-v2312
+                                                 pointConstraints] and leastSquares leaves its faces at zero
+                                                 (extendedFaceStencilScalarGrad.C:86-109).  Field condition: QGD_BC_SLIP. */
+} qgd_patch_kind;
 
 /* boundary-condition kinds of the closed device-native set */
 typedef enum {

@@ -66,7 +66,7 @@ struct or_ctx {
     IVec pcOff, pcCell; Vec pcW;       // point -> cells, weights (non patch points)
     std::vector<char> isPatchPoint;
     IVec pbOff, pbFace; Vec pbW;       // patch point -> boundary faces (bface index), weights
-    IVec wedgePts; Vec wedgeN;         // points on a wedge patch and the patch normal (pointConstraints [OF-v2312])
+    IVec conPts; Vec conR;             // vertices of constraint patches (wedge, symmetryPlane) and their constraint tensor (pointConstraints [OF-v2312])
     // QGDCoeffs
     Vec hQGDf, hQGD;
     // GaussVolPointBase3D
@@ -166,18 +166,18 @@ void volPointInterpolate(const or_ctx& m, int k, const double* cell, const doubl
                 for (int j = 0; j < k; ++j) pf[(long)p * k + j] += m.pbW[q] * bnd[(long)m.pbFace[q] * k + j];
         }
     }
-    // [OF-v2312] pointConstraints::constrain -> wedgePointPatchField::evaluate: on the points of a wedge patch a vector loses its
-    // component along the patch normal, transform(I - nHat nHat, v); a tensor becomes R.T.R^T with R = I - nHat nHat; scalars stay
+    // [OF-v2312] pointConstraints::constrain: wedgePointPatchField / symmetryPlanePointPatchField::evaluate take the patch-normal
+    // component out of a vector at the patch's vertices (transform(I - nHat nHat, v)), constrainCorners applies the combined
+    // constraint where such patches meet; with the constraint tensor R of the vertex: v -> R.v, a tensor T -> R.T.R^T; scalars stay
     if (k == 3 || k == 9)
-        for (size_t i = 0; i < m.wedgePts.size(); ++i) {
-            const double* n = &m.wedgeN[3 * i];
-            double* v = &pf[(long)m.wedgePts[i] * k];
+        for (size_t i = 0; i < m.conPts.size(); ++i) {
+            const double* R = &m.conR[9 * i];
+            double* v = &pf[(long)m.conPts[i] * k];
             if (k == 3) {
-                const double vn = n[0] * v[0] + n[1] * v[1] + n[2] * v[2];
-                for (int j = 0; j < 3; ++j) v[j] -= n[j] * vn;
+                const double u[3] = {v[0], v[1], v[2]};
+                for (int a = 0; a < 3; ++a) v[a] = R[3 * a] * u[0] + R[3 * a + 1] * u[1] + R[3 * a + 2] * u[2];
             } else {
-                double R[9], t[9];
-                for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) R[3 * a + b] = (a == b ? 1.0 : 0.0) - n[a] * n[b];
+                double t[9];
                 for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { t[3 * a + b] = 0.0; for (int c = 0; c < 3; ++c) t[3 * a + b] += R[3 * a + c] * v[3 * c + b]; }
                 for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { v[3 * a + b] = 0.0; for (int c = 0; c < 3; ++c) v[3 * a + b] += t[3 * a + c] * R[3 * b + c]; }
             }
@@ -252,18 +252,35 @@ void buildDerived(or_ctx& m)
             }
             for (int q = m.pcOff[p]; q < m.pcOff[p + 1]; ++q) m.pcW[q] /= sum;
         }
-        {   // points of wedge patches, with the (planar) patch's normal: wedgePointPatchField takes pointNormals()[0] of the patch
-            std::vector<char> seen(m.nPoints, 0);
-            for (int b = 0; b < m.nBnd; ++b) {
-                if (m.patchKind[m.bfacePatch[b]] != OR_PATCH_WEDGE) continue;
-                const int f = m.nInternal + b, f0 = m.patchStart[m.bfacePatch[b]];
-                for (int q = m.faceOff[f]; q < m.faceOff[f + 1]; ++q) {
-                    const int p = m.faceVerts[q];
-                    if (seen[p]) continue;
-                    seen[p] = 1;
-                    m.wedgePts.push_back(p);
-                    for (int d = 0; d < 3; ++d) m.wedgeN.push_back(m.Sf[3 * (size_t)f0 + d] / m.magSf[f0]);
-                }
+        {   // vertices of the constraint patches (wedge, symmetryPlane) and their pointConstraint [OF-v2312 pointConstraintI.H]: each
+            // patch the vertex lies on adds its (planar) normal - the patch's first point normal = its face normal - in patch order:
+            //   none yet -> one plane (n) ; one -> a line along n x n_old if the two normals differ (|n x n_old| > 1e-3) ;
+            //   a line -> fixed if n is not perpendicular to it (|n . d| > 1e-3)
+            // constraintTransformation: I - n n | d d | 0
+            std::vector<int> cnt(m.nPoints, 0);
+            std::vector<V3> dir(m.nPoints, V3{0, 0, 0});
+            for (int pi = 0; pi < m.nPatches; ++pi) {
+                if ((m.patchKind[pi] != OR_PATCH_WEDGE && m.patchKind[pi] != OR_PATCH_SYMMETRY_PLANE) || m.patchSize[pi] == 0) continue;
+                const int f0 = m.patchStart[pi];
+                const V3 n = (1.0 / m.magSf[f0]) * ld3(m.Sf.data(), f0);
+                std::vector<char> done(m.nPoints, 0);
+                for (int f = f0; f < f0 + m.patchSize[pi]; ++f)
+                    for (int q = m.faceOff[f]; q < m.faceOff[f + 1]; ++q) {
+                        const int p = m.faceVerts[q];
+                        if (done[p]) continue;
+                        done[p] = 1;
+                        if (cnt[p] == 0) { cnt[p] = 1; dir[p] = n; }
+                        else if (cnt[p] == 1) { const V3 pl = cross(n, dir[p]); const double mp = mag(pl); if (mp > 1e-3) { cnt[p] = 2; dir[p] = (1.0 / mp) * pl; } }
+                        else if (cnt[p] == 2) { if (std::fabs(dot(n, dir[p])) > 1e-3) { cnt[p] = 3; dir[p] = V3{0, 0, 0}; } }
+                    }
+            }
+            for (int p = 0; p < m.nPoints; ++p) {
+                if (!cnt[p]) continue;
+                m.conPts.push_back(p);
+                const double d[3] = {dir[p].x, dir[p].y, dir[p].z};
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b)
+                        m.conR.push_back(cnt[p] == 1 ? (a == b ? 1.0 : 0.0) - d[a] * d[b] : (cnt[p] == 2 ? d[a] * d[b] : 0.0));
             }
         }
         m.pbOff.assign(m.nPoints + 1, 0);
@@ -537,7 +554,7 @@ void leastSquaresGrad(const or_ctx& mc, int k, const double* cell, const double*
     for (int b = 0; b < m.nBnd; ++b) {                                                     // :86-109
         const int f = m.nInternal + b;
         const int kind = m.patchKind[m.bfacePatch[b]];
-        const bool constrained = kind == OR_PATCH_EMPTY || kind == OR_PATCH_WEDGE || kind == OR_PATCH_PROCESSOR;
+        const bool constrained = kind == OR_PATCH_EMPTY || kind == OR_PATCH_WEDGE || kind == OR_PATCH_PROCESSOR || kind == OR_PATCH_SYMMETRY_PLANE;
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < k; ++j) out[(size_t)f * ok + k * i + j] = constrained ? 0.0 : m.nf[3 * (size_t)f + i] * bsg[(size_t)b * k + j];
     }

@@ -21,7 +21,8 @@
 extern "C" {
 
 // patch kinds (same numbering as include/qgd_b200.h)
-enum { OR_PATCH_GENERIC = 0, OR_PATCH_EMPTY = 1, OR_PATCH_PROCESSOR = 2, OR_PATCH_WEDGE = 3 };
+enum { OR_PATCH_GENERIC = 0, OR_PATCH_EMPTY = 1, OR_PATCH_PROCESSOR = 2, OR_PATCH_WEDGE = 3,
+       OR_PATCH_SYMMETRY_PLANE = 4 };   // polyPatch type symmetryPlane: an ordinary patch for the face derivatives, a constraint patch for the vertices
 // boundary-condition kinds per patch and field
 enum { OR_BC_FIXED_VALUE = 0, OR_BC_ZERO_GRADIENT = 1, OR_BC_FIXED_GRADIENT = 2, OR_BC_QGD_FLUX = 3,
        OR_BC_CALCULATED = 4, OR_BC_QHD_FLUX = 5, OR_BC_SLIP = 6,

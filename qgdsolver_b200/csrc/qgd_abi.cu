@@ -669,7 +669,7 @@ void runSteps(qgd_solver* s, int n)
     // (QGD_BND_FORK=2) until measured - there the side stream can only start after the halo wait
     const bool useFork = (multi ? g_bndFork == 2 : g_bndFork != 0) && g_sideStream && h_nB(s) > 0 && !s->anyQgdFlux && !model5 &&
                          !(s->pipe.mode == 1 && !s->desc.adjust_time_step && !s->k.varSc);
-    const WedgeView wedge{(int)s->mesh->h.wedgePts.size(), s->mesh->wedgePts.p, s->mesh->wedgeN.p};
+    const WedgeView wedge{(int)s->mesh->h.wedgePts.size(), s->mesh->wedgePts.p, s->mesh->wedgeR.p};
     // ---- opt-in (QGD_STEP_GRAPH=1): the step as a CUDA graph.  One step is captured from the very launch sequence below (side
     // stream included: it joins the capture through evEntry and is joined back before the capture ends) and replayed n times; the
     // time-step control lives on the device (k_dt), so adaptive deltaT needs no re-capture.  Single GPU, two-kernel step form, no
@@ -839,7 +839,7 @@ void qgd::fvscBuild(qgd_fvsc& op, qgd_mesh* mesh, const std::string& name)
     const int nF = mesh->h.nFaces;
     if (op.lsq)      // leastSquares leaves the faces of constraint patches at zero (extendedFaceStencilScalarGrad.C:86-109: empty, wedge, coupled ...)
         for (int b = 0; b < mesh->h.nBnd; ++b)
-            if (mesh->h.patchKind[mesh->h.bfacePatch[b]] == QGD_PATCH_WEDGE)
+            if (mesh->h.patchKind[mesh->h.bfacePatch[b]] == QGD_PATCH_WEDGE || mesh->h.patchKind[mesh->h.bfacePatch[b]] == QGD_PATCH_SYMMETRY_PLANE)
                 for (int k = 6; k < 9; ++k) G[(size_t)k * nF + mesh->h.nInternal + b] = 0.0;
     const std::vector<int>& perm = mesh->facePerm;
     std::vector<int4> v4(nF);
@@ -1038,7 +1038,7 @@ int qgd_mesh_create(const qgd_mesh_desc* desc, qgd_mesh** out)
         m->magSf.upload(permD(h.magSf), g_stream); m->w.upload(permD(h.w), g_stream); m->dC.upload(permD(h.dC), g_stream);
         m->ndC.upload(permD(h.ndC), g_stream); m->V.upload(h.V, g_stream);
         m->hQGDf.upload(permD(h.hQGDf), g_stream); m->hQGD.upload(h.hQGD, g_stream);
-        if (!h.wedgePts.empty()) { m->wedgePts.upload(h.wedgePts, g_stream); m->wedgeN.upload(h.wedgeN, g_stream); }
+        if (!h.wedgePts.empty()) { m->wedgePts.upload(h.wedgePts, g_stream); m->wedgeR.upload(h.wedgeR, g_stream); }
         *out = m.release();
     });
 }

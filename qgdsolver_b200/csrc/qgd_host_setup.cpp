@@ -163,21 +163,33 @@ void HostMesh::build(const qgd_mesh_desc& d)
         }
     }
 
-    // ---- vertices of wedge patches (pointConstraints): the patch normal is that of the patch's first face, as wedgePointPatchField
-    // takes pointNormals()[0] of the planar patch
+    // ---- vertices of the constraint patches (wedge, symmetryPlane): every such patch a vertex lies on adds its planar normal (that of
+    // the patch's first face, as the point patch fields take pointNormals()[0]) to the vertex's pointConstraint, in patch order
     {
-        std::vector<char> seen(nPoints, 0);
-        wedgePts.clear(); wedgeN.clear();
-        for (int b = 0; b < nBnd; ++b) {
-            if (patchKind[bfacePatch[b]] != QGD_PATCH_WEDGE) continue;
-            const int f = nInternal + b, f0 = patchStart[bfacePatch[b]];
-            for (int q = faceOff[f]; q < faceOff[f + 1]; ++q) {
-                const int p = faceVerts[q];
-                if (seen[p]) continue;
-                seen[p] = 1;
-                wedgePts.push_back(p);
-                for (int d = 0; d < 3; ++d) wedgeN.push_back(Sf[3 * (size_t)f0 + d] / magSf[f0]);
-            }
+        std::vector<int> cnt(nPoints, 0);
+        std::vector<Vec3> dir(nPoints, Vec3{{0, 0, 0}});
+        std::vector<int> stamp(nPoints, -1);
+        for (int pi = 0; pi < nPatches; ++pi) {
+            if ((patchKind[pi] != QGD_PATCH_WEDGE && patchKind[pi] != QGD_PATCH_SYMMETRY_PLANE) || patchSize[pi] == 0) continue;
+            const int f0 = patchStart[pi];
+            const Vec3 n = scale(1.0 / magSf[f0], at(Sf, f0));
+            for (int f = f0; f < f0 + patchSize[pi]; ++f)
+                for (int q = faceOff[f]; q < faceOff[f + 1]; ++q) {
+                    const int p = faceVerts[q];
+                    if (stamp[p] == pi) continue;
+                    stamp[p] = pi;
+                    if (cnt[p] == 0) { cnt[p] = 1; dir[p] = n; }                                   // pointConstraint::applyConstraint
+                    else if (cnt[p] == 1) { const Vec3 pl = cross3(n, dir[p]); const double mp = norm3(pl); if (mp > 1e-3) { cnt[p] = 2; dir[p] = scale(1.0 / mp, pl); } }
+                    else if (cnt[p] == 2) { if (std::fabs(dot3(n, dir[p])) > 1e-3) { cnt[p] = 3; dir[p] = Vec3{{0, 0, 0}}; } }
+                }
+        }
+        wedgePts.clear(); wedgeR.clear();
+        for (int p = 0; p < nPoints; ++p) {
+            if (!cnt[p]) continue;
+            wedgePts.push_back(p);
+            for (int a = 0; a < 3; ++a)                                                            // constraintTransformation
+                for (int b = 0; b < 3; ++b)
+                    wedgeR.push_back(cnt[p] == 1 ? (a == b ? 1.0 : 0.0) - dir[p][a] * dir[p][b] : (cnt[p] == 2 ? dir[p][a] * dir[p][b] : 0.0));
         }
     }
 

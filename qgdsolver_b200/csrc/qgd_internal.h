@@ -121,10 +121,11 @@ struct HostMesh {
     std::vector<int> ppOff, ppFace;                // patch point (by list position) -> boundary faces
     std::vector<double> ppW;
     std::vector<double> hQGDf, hQGD;
-    // vertices of wedge patches and the (planar) patch's normal: volPointInterpolation constrains vectors / tensors there
-    // [OF-v2312 pointConstraints -> wedgePointPatchField::evaluate: transform(I - nHat nHat, .)]
+    // vertices of the constraint patches (wedge, symmetryPlane) and their constraint tensor R: volPointInterpolation turns a vector v
+    // into R.v and a tensor T into R.T.R^T there [OF-v2312 pointConstraints: wedge / symmetryPlane point patch fields + constrainCorners;
+    // pointConstraintI.H: one plane I - n n, two different planes d d with d along n1 x n2, three: 0]
     std::vector<int> wedgePts;
-    std::vector<double> wedgeN;                    // 3 per listed point
+    std::vector<double> wedgeR;                    // 9 per listed point
     void build(const qgd_mesh_desc& d);
     // face gradient records for a scheme ("GaussVolPoint" / "reduced")
     // leastSquares scheme (extendedFaceStencilFindNeighbours.C:41-86, extendedFaceStencilCalculateWeights.C:43-155):
@@ -160,6 +161,6 @@ struct qgd_mesh {
     qgd::DevBuf<double> ppW;
     qgd::DevBuf<double> Sf;        // SoA 3*faceStride
     qgd::DevBuf<double> magSf, w, dC, ndC, V, hQGDf, hQGD;
-    qgd::DevBuf<int> wedgePts;     // HostMesh::wedgePts / wedgeN (empty without wedge patches)
-    qgd::DevBuf<double> wedgeN;
+    qgd::DevBuf<int> wedgePts;     // HostMesh::wedgePts / wedgeR (empty without constraint patches)
+    qgd::DevBuf<double> wedgeR;
 };

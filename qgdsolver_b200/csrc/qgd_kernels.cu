@@ -528,18 +528,20 @@ __global__ void k_patch_points(SolverView sv, BndState bs, int onlyP)
     o[0] = a0; o[nP] = a1; o[2 * nP] = a2; o[3 * nP] = a3; o[4 * nP] = a4;
 }
 
-// [OF-v2312] pointConstraints::constrain -> wedgePointPatchField::evaluate on the vertices of wedge patches: a vector loses its
-// component along the patch normal (transform(I - nHat nHat, v)), a tensor becomes R.T.R^T with R = I - nHat nHat.
+// [OF-v2312] pointConstraints::constrain on the vertices of the constraint patches (wedge, symmetryPlane): with the vertex's
+// constraint tensor R (HostMesh::wedgeR: I - n n on one plane, d d where two planes meet) a vector becomes R.v, a tensor R.T.R^T.
 // step form: the velocity rows (fields 1..3) of the SoA point array P[6][nPoints]
-__global__ void k_wedge_points(int n, const int* __restrict__ pts, const double* __restrict__ nrm, double* __restrict__ P, size_t nPoints)
+__global__ void k_wedge_points(int n, const int* __restrict__ pts, const double* __restrict__ R9, double* __restrict__ P, size_t nPoints)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int p = pts[i];
-    const double nx = nrm[3 * (size_t)i], ny = nrm[3 * (size_t)i + 1], nz = nrm[3 * (size_t)i + 2];
+    const double* R = R9 + 9 * (size_t)i;
     double* u = P + nPoints + p;
-    const double vn = nx * u[0] + ny * u[nPoints] + nz * u[2 * nPoints];
-    u[0] -= nx * vn; u[nPoints] -= ny * vn; u[2 * nPoints] -= nz * vn;
+    const double u0 = u[0], u1 = u[nPoints], u2 = u[2 * nPoints];
+    u[0] = R[0] * u0 + R[1] * u1 + R[2] * u2;
+    u[nPoints] = R[3] * u0 + R[4] * u1 + R[5] * u2;
+    u[2 * nPoints] = R[6] * u0 + R[7] * u1 + R[8] * u2;
 }
 // operator form: AoS point values pts[p*K + j], K = 3 (vector) or 9 (tensor)
 template <int K>
@@ -547,18 +549,16 @@ __global__ void k_wedge_points_generic(int n, const int* __restrict__ list, cons
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double nv[3] = {nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2]};
+    double R[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) R[q] = nrm[9 * (size_t)i + q];
     double* v = pv + (size_t)list[i] * K;
     if (K == 3) {
-        const double vn = nv[0] * v[0] + nv[1] * v[1] + nv[2] * v[2];
+        const double u0 = v[0], u1 = v[1], u2 = v[2];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) v[j] -= nv[j] * vn;
+        for (int j = 0; j < 3; ++j) v[j] = R[3 * j] * u0 + R[3 * j + 1] * u1 + R[3 * j + 2] * u2;
     } else {
-        double R[9], t[9];
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int b = 0; b < 3; ++b) R[3 * a + b] = (a == b ? 1.0 : 0.0) - nv[a] * nv[b];
+        double t[9];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -1730,8 +1730,8 @@ void launchPointGather(cudaStream_t st, int K, const qgd_mesh& m, const double* 
     }
 #undef QGD_PG
     const int nW = (int)m.h.wedgePts.size();        // pointConstraints on the vertices of wedge patches (vectors, tensors)
-    if (nW && K == 3) k_wedge_points_generic<3><<<nblk(nW), kBlock, 0, st>>>(nW, m.wedgePts.p, m.wedgeN.p, pts);
-    if (nW && K == 9) k_wedge_points_generic<9><<<nblk(nW), kBlock, 0, st>>>(nW, m.wedgePts.p, m.wedgeN.p, pts);
+    if (nW && K == 3) k_wedge_points_generic<3><<<nblk(nW), kBlock, 0, st>>>(nW, m.wedgePts.p, m.wedgeR.p, pts);
+    if (nW && K == 9) k_wedge_points_generic<9><<<nblk(nW), kBlock, 0, st>>>(nW, m.wedgePts.p, m.wedgeR.p, pts);
     QGD_CUDA(cudaGetLastError());
 }
 

@@ -165,7 +165,8 @@ struct StepFork {
     cudaEvent_t evEntry, evPatch, evBndFlux, evCell, evBndPost;
     bool postOnSide;         // k_bnd_post on the side stream too (single GPU: nothing on the main stream needs it before the next step)
 };
-// vertices of wedge patches: after the patch-point kernel their velocity loses the patch-normal component (pointConstraints [OF-v2312])
+// vertices of constraint patches (wedge, symmetryPlane): after the patch-point kernel their velocity is multiplied by the vertex's
+// constraint tensor (pointConstraints [OF-v2312]); nrm = 9 doubles per listed vertex
 struct WedgeView { int n; const int* pts; const double* nrm; };
 int launchStep(cudaStream_t st, const Consts& c, const FaceView& fv, const SolverView& sv, const BndState& bs,
                bool anyQgdFlux, int gridFaces, bool adjust, cudaEvent_t* ev = nullptr, const StepHooks* hooks = nullptr,

@@ -22,11 +22,13 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .polymesh import PATCH_EMPTY, PATCH_GENERIC, PATCH_PROCESSOR, PATCH_WEDGE, Patch, PolyMesh
+from .polymesh import PATCH_EMPTY, PATCH_GENERIC, PATCH_PROCESSOR, PATCH_SYMMETRY_PLANE, PATCH_WEDGE, Patch, PolyMesh
 
-_KINDS = {"patch": PATCH_GENERIC, "wall": PATCH_GENERIC, "symmetry": PATCH_GENERIC, "symmetryPlane": PATCH_GENERIC,
+# `symmetry` (non-planar) is read as an ordinary patch: its per-vertex normals are not restated; `symmetryPlane` keeps its vertex constraint
+_KINDS = {"patch": PATCH_GENERIC, "wall": PATCH_GENERIC, "symmetry": PATCH_GENERIC, "symmetryPlane": PATCH_SYMMETRY_PLANE,
           "empty": PATCH_EMPTY, "processor": PATCH_PROCESSOR, "wedge": PATCH_WEDGE}
-_KIND_WORD = {PATCH_GENERIC: "patch", PATCH_EMPTY: "empty", PATCH_PROCESSOR: "processor", PATCH_WEDGE: "wedge"}
+_KIND_WORD = {PATCH_GENERIC: "patch", PATCH_EMPTY: "empty", PATCH_PROCESSOR: "processor", PATCH_WEDGE: "wedge",
+              PATCH_SYMMETRY_PLANE: "symmetryPlane"}
 
 
 class FoamFormatError(ValueError):

@@ -29,11 +29,12 @@ import numpy as np
 PATCH_GENERIC = 0      # patch / wall : ordinary boundary
 PATCH_EMPTY = 1        # empty        : 1D/2D reduction
 PATCH_PROCESSOR = 2    # processor    : inter-subdomain
-PATCH_WEDGE = 3        # wedge (recognised, skipped like the reference does)
+PATCH_WEDGE = 3        # wedge (no face derivatives, skipped in hQGD; vertices constrained)
+PATCH_SYMMETRY_PLANE = 4   # symmetryPlane: an ordinary patch for the face derivatives, its vertices are constrained [OF pointConstraints]
 
 _KIND_NAMES = {"patch": PATCH_GENERIC, "wall": PATCH_GENERIC,
                "empty": PATCH_EMPTY, "processor": PATCH_PROCESSOR,
-               "wedge": PATCH_WEDGE}
+               "wedge": PATCH_WEDGE, "symmetryPlane": PATCH_SYMMETRY_PLANE}
 
 
 @dataclass

@@ -336,3 +336,14 @@ def case_wedge(n=(16, 12), angle_deg=5.0, r0=0.5, perturb=0.0, bcs="fixed", gas=
     c.U0 = np.ascontiguousarray(np.stack([0.1 * np.sin(2 * np.pi * x) * np.cos(3 * y), 0.08 * np.cos(2 * np.pi * x) * np.sin(3 * y),
                                           np.zeros(mesh.n_cells)], 1))
     return c
+
+
+def with_symmetry_planes(c, names):
+    """the named patches become polyPatch type symmetryPlane (vertex constraint of volPointInterpolation [OF-v2312 pointConstraints],
+    leastSquares leaves their faces at zero) with the symmetryPlane field conditions: slip velocity, zeroGradient scalars"""
+    m = c.mesh
+    m.patches = [pm.Patch(p.name, pm.PATCH_SYMMETRY_PLANE if p.name in names else p.kind, p.start, p.size) for p in m.patches]
+    for i, p in enumerate(m.patches):
+        if p.name in names:
+            c.bcU[i], c.bcT[i], c.bcP[i] = SLIP, ZG, ZG
+    return c

@@ -51,6 +51,10 @@ WEDGE = {
     "wedge_qgdflux_adjust": lambda: cases.case_wedge(n=(12, 10), bcs="qgdflux", adjust_time_step=True, max_co=0.1),
     "wedge_leastSquares": lambda: cases.case_wedge(n=(12, 10), bcs="fixed", scheme="leastSquares"),
     "wedge_model1n": lambda: cases.case_wedge(n=(12, 10), perturb=0.1, bcs="mixed", model="constScPrModel1n"),
+    # polyPatch type symmetryPlane: slip velocity + constrained vertices (combined where two planes meet)
+    "symplane_hex": lambda: cases.with_symmetry_planes(cases.case_hex3d(n=(9, 8, 7), perturb=0.2, bcs="mixed"), ("yMin", "yMax", "zMax")),
+    "symplane_forward_step": lambda: cases.with_symmetry_planes(cases.case_forward_step(n=30), ("yMin", "yMax", "step")),
+    "symplane_2d_leastSquares": lambda: cases.with_symmetry_planes(cases.case_2d((20, 16), perturb=0.15, bcs="fixed", scheme="leastSquares"), ("yMin", "xMax")),
 }
 
 

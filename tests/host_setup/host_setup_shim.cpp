@@ -204,11 +204,11 @@ int hs_varsc5_correct(void* p, const double* prm, double* S, const double* bT, c
 
 extern "C" {
 
-int hs_wedge_points(void* p, int* pts, double* nrm)     // returns the count; pts / nrm may be NULL to query it
+int hs_wedge_points(void* p, int* pts, double* R9)      // returns the count; pts / R9 (9 per vertex) may be NULL to query it
 {
     const HostMesh& h = *static_cast<HostMesh*>(p);
     if (pts) std::memcpy(pts, h.wedgePts.data(), sizeof(int) * h.wedgePts.size());
-    if (nrm) std::memcpy(nrm, h.wedgeN.data(), sizeof(double) * h.wedgeN.size());
+    if (R9) std::memcpy(R9, h.wedgeR.data(), sizeof(double) * h.wedgeR.size());
     return (int)h.wedgePts.size();
 }
 

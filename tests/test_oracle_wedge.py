@@ -147,3 +147,32 @@ def test_wedge_faces_carry_no_mass_and_the_step_conserves_it(oracle_mod):
     assert np.abs(phi[nI:][wedge]).max() < 1e-17 and np.abs(phi[nI:][~wedge]).max() > 1e-6
     mass1 = (o.get("rho") * m.V).sum()
     assert abs((mass1 - mass0) + c.dt * phi[nI:][~wedge].sum()) < 1e-16
+
+
+def test_symmetry_plane_patches_in_the_oracle(oracle_mod):
+    """polyPatch type symmetryPlane: free stream along the planes is preserved (slip + constrained vertices), the vertex velocity has
+    no component along the plane normal, and leastSquares leaves the faces of such patches at zero (extendedFaceStencilScalarGrad.C:86-109)"""
+    c = cases.with_symmetry_planes(cases.case_hex3d(n=(7, 6, 5), perturb=0.2, bcs="zg"), ("yMin", "yMax", "zMin", "zMax"))
+    c.U0 = np.tile([0.4, 0.0, 0.0], (c.mesh.n_cells, 1))
+    c.T0[:] = 0.9
+    c.p0[:] = 0.8
+    o = c.make_oracle(oracle_mod)
+    c.oracle_step(o, 20)
+    assert np.abs(o.get("U") - c.U0).max() < 1e-13 and np.abs(o.get("p") - 0.8).max() < 1e-13
+    m = c.mesh
+    rng = np.random.default_rng(1)
+    pv = oracle_mod.Oracle(m).vol_point_interpolate(rng.random((m.n_cells, 3)), rng.random((m.n_bnd, 3)))
+    ony = (np.abs(m.points[:, 1]) < 1e-12) | (np.abs(m.points[:, 1] - 1) < 1e-12)
+    onz = (np.abs(m.points[:, 2]) < 1e-12) | (np.abs(m.points[:, 2] - 1) < 1e-12)
+    assert np.abs(pv[ony, 1]).max() < 1e-15 and np.abs(pv[onz, 2]).max() < 1e-15
+    assert np.abs(pv[~ony & ~onz]).min() > 0
+    c2 = cases.with_symmetry_planes(cases.case_2d((10, 8), perturb=0.1, bcs="fixed"), ("yMin",))
+    m2 = c2.mesh
+    o2 = oracle_mod.Oracle(m2)
+    cell, bnd = rng.random(m2.n_cells), rng.random(m2.n_bnd)
+    bsg = rng.random(m2.n_bnd)
+    g = o2.fvsc_grad(cell, bnd, bsg, scheme=oracle_mod.FVSC_SCHEMES["leastSquares"])
+    pid = m2.patch_id_per_bface()
+    sym = np.array([p.kind == pm.PATCH_SYMMETRY_PLANE for p in m2.patches])[pid]
+    kind = m2.patch_kind_per_bface()
+    assert np.abs(g[m2.n_internal:][sym]).max() == 0.0 and np.abs(g[m2.n_internal:][~sym & (kind != 1)]).max(1).min() > 0

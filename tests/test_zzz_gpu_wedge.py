@@ -1,4 +1,4 @@
-"""Axisymmetric (wedge) QGDFoam cases on the device against the CPU oracle through the C ABI: the wedge velocity condition
+"""Axisymmetric (wedge) and symmetryPlane-patch QGDFoam cases on the device against the CPU oracle through the C ABI: the wedge velocity condition
 (QGD_BC_WEDGE, k_wedge_bnd), the wedge vertex constraint (k_wedge_points, k_wedge_points_generic) and the 2D
 GaussVolPoint path on a wedge mesh whose every vertex is a patch point.
 
