@@ -51,6 +51,11 @@ CASES = {
     "varSc7_fixed_serialrule": (lambda: cases.case_hex3d(n=(12, 10, 8), perturb=0.1, bcs="fixed", model="varScModel7",
                                                          varsc=dict(cSc1=3.0, minSc=0.02, maxSc=0.4)), False),
     "2d_leastSquares_serialrule": (lambda: cases.case_2d((20, 16), perturb=0.2, bcs="mixed", scheme="leastSquares"), False),
+    # implicitDiffusion true on sub-meshes: stepwise PCG, search direction exchanged every iteration, all-reduced dot products
+    "perturbed_mixed_implicit_serialrule": (lambda: cases.case_hex3d(n=(12, 10, 8), perturb=0.2, bcs="mixed", implicit=True,
+                                                                     diff_solver=dict(precond="diagonal")), False),
+    "2d_qgdflux_implicit_adjust_serialrule": (lambda: cases.case_2d((20, 16), perturb=0.15, bcs="qgdflux", implicit=True, adjust_time_step=True,
+                                                                    max_co=0.1, diff_solver=dict(precond="none")), False),
 }
 
 api.load_library()
@@ -81,8 +86,10 @@ for name in names:
     if not proc_rule:
         sub.coupled_face[:] = 0
     dm = api.Mesh(sub.mesh, n_owned=sub.n_owned, coupled_face=sub.coupled_face)
+    ds = c.diff_solver
     s = api.QGDFoam(dm, fvsc_scheme=c.scheme, qgd_coeffs=c.model, delta_t=c.dt, varsc_cSc1=c.varsc["cSc1"], varsc_minSc=c.varsc["minSc"],
-                    varsc_maxSc=c.varsc["maxSc"], **c.gas, **c.opts)
+                    varsc_maxSc=c.varsc["maxSc"], implicit_diffusion=c.implicit, diff_tol=ds["tol"], diff_rel_tol=ds["rel_tol"],
+                    diff_max_iter=ds["max_iter"], diff_precond=ds["precond"], **c.gas, **c.opts)
     nI_g = c.mesh.n_internal
     bf_g = sub.face_global[sub.mesh.n_internal:]
     phys = bf_g >= nI_g

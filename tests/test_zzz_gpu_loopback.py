@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 
 SETS = {
     8: ["perturbed_mixed_serialrule,uniform_adjust_procrule", "2d_qgdflux_serialrule,truncoct_mixed_serialrule,slip_perturbed_serialrule"],
-    4: ["perturbed_mixed_serialrule,prism_fixed_serialrule,uniform_zg_procrule", "varSc7_fixed_serialrule,2d_leastSquares_serialrule"],
+    4: ["perturbed_mixed_serialrule,prism_fixed_serialrule,uniform_zg_procrule", "varSc7_fixed_serialrule,2d_leastSquares_serialrule",
+        "perturbed_mixed_implicit_serialrule,2d_qgdflux_implicit_adjust_serialrule"],
     2: ["perturbed_mixed_serialrule,uniform_adjust_procrule,truncoct_mixed_serialrule"],
 }
 
