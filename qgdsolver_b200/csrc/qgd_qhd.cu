@@ -788,6 +788,8 @@ int qgd_qhdfoam_create(qgd_mesh* mesh, const qgd_qhdfoam_desc* d, qgd_qhd_solver
                                                    "\n\nValid model types are:\n" + coeffsModelToc());
         if (model != "constTau" && model != "H2bynuQHD" && model != "HbyUQHD" && model != "T0byGr")
             throw Error(QGD_ERR_UNSUPPORTED, "QGDCoeffs model " + model + " is not a QHD model available on the device (constTau, H2bynuQHD, HbyUQHD, T0byGr)");
+        if (!mesh->h.wedgePts.empty())               // their vertex constraint (pointConstraints) lives in the QGDFoam step only
+            throw Error(QGD_ERR_UNSUPPORTED, "wedge / symmetryPlane patches are not available in QHDFoam on the device");
         auto precondOf = [](const char* name) {
             const std::string pc = name ? name : "DIC";
             if (pc == "DIC") return 2;
