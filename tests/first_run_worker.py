@@ -215,6 +215,8 @@ def run_graph(qgd, O, name):
 
 
 def main():
+    import signal
+    signal.alarm(270)                            # never-run device code: a hang ends here, not in the test session
     kind = sys.argv[1]
     name = sys.argv[2] if len(sys.argv) > 2 else None
     import oracle as O

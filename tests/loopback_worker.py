@@ -17,7 +17,7 @@ from qgdsolver_b200 import api, decompose  # noqa: E402
 
 import signal  # noqa: E402
 
-signal.alarm(400)                               # a rank left alone in an exchange ends by itself
+signal.alarm(330)                               # a rank left alone in an exchange ends by itself
 rank, world, rdv = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 names = sys.argv[4].split(",")
 

@@ -44,7 +44,7 @@ def test_decomposed_qgdfoam_on_one_gpu_matches_oracle(world, names):
             if any(p.poll() not in (None, 0) for p in procs):
                 why = "a rank failed"                       # do not let its neighbours wait for it
                 break
-            if time.time() - t0 > 420:
+            if time.time() - t0 > 300:
                 why = "a rank blocked in an exchange its neighbours never entered (timeout)"
                 break
             time.sleep(0.2)

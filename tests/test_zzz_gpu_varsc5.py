@@ -18,7 +18,7 @@ first_run = pytest.mark.xfail(strict=False, reason="first device run is the driv
 WORKER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "first_run_worker.py")
 
 
-def run_isolated(*args, timeout=900):
+def run_isolated(*args, timeout=300):
     r = subprocess.run([sys.executable, WORKER, *args], capture_output=True, text=True, timeout=timeout)
     print(r.stdout[-3000:])
     assert r.returncode == 0 and "FIRST_RUN_OK" in r.stdout, (r.stdout[-3000:] + r.stderr[-3000:])
