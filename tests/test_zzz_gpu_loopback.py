@@ -16,7 +16,7 @@ import time
 import pytest
 
 from test_fake_nccl_cpu import FAKE, ROOT, build_fake_nccl
-from test_zzz_gpu_varsc5 import first_run
+from test_zzz_gpu_varsc5 import BUDGET, budget_ok, first_run
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +31,7 @@ SETS = {
 @first_run
 @pytest.mark.parametrize("world,names", [(w, n) for w, sets in SETS.items() for n in sets])
 def test_decomposed_qgdfoam_on_one_gpu_matches_oracle(world, names):
+    assert budget_ok(), "first-run budget used up by earlier cases (time-outs / 20 minutes): not started"
     build_fake_nccl()
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = FAKE + os.pathsep + env.get("LD_LIBRARY_PATH", "")
@@ -46,12 +47,14 @@ def test_decomposed_qgdfoam_on_one_gpu_matches_oracle(world, names):
                 break
             if time.time() - t0 > 300:
                 why = "a rank blocked in an exchange its neighbours never entered (timeout)"
+                BUDGET["timeouts"] += 1
                 break
             time.sleep(0.2)
         for p in procs:
             if p.poll() is None:
                 p.kill()
             p.wait()
+        BUDGET["spent"] += time.time() - t0
         outs = []
         for f in logs:
             f.seek(0)
