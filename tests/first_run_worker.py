@@ -1,4 +1,4 @@
-"""Runs ONE first-run device case in its own process (tests/test_zzz_gpu_*.py spawn it), so that a crash or a hang of code that
+"""Runs ONE first-run device case in its own process (tests/test_zzz_*_gpu_*.py spawn it), so that a crash or a hang of code that
 has never run on a device stays inside that process: `python tests/first_run_worker.py <kind> [<case>]` prints FIRST_RUN_OK."""
 import os
 import sys

@@ -8,7 +8,7 @@ file sorts after every device-verified file, non-strict xfail."""
 import pytest
 
 from first_run_worker import WEDGE
-from test_zzz_gpu_varsc5 import first_run, run_isolated
+from first_run_common import first_run, run_isolated
 
 pytestmark = pytest.mark.gpu
 

@@ -16,7 +16,7 @@ import time
 import pytest
 
 from test_fake_nccl_cpu import FAKE, ROOT, build_fake_nccl
-from test_zzz_gpu_varsc5 import BUDGET, budget_ok, first_run
+from first_run_common import BUDGET, budget_ok, first_run
 
 pytestmark = pytest.mark.gpu
 
